@@ -1,0 +1,225 @@
+/* ldso_b200 — C ABI of the B200-native photometric bundle-adjustment / coarse-tracker hot path of LDSO.
+ *
+ * This is the drop-in boundary. LDSO has no FFI of its own; the entry points
+ * below are what link-compatible replacements of the reference's
+ *     src/internal/Residuals.cc, src/internal/OptimizationBackend/{AccumulatedTopHessian,AccumulatedSCHessian,
+ *     EnergyFunctional}.cc, src/internal/FrameFramePrecalc.cc and src/frontend/CoarseTracker.cc
+ * forward to (see INTEGRATION.md for the C++ side). Each function cites the reference interface it replaces
+ * (paths relative to the LDSO source tree).
+ *
+ * Conventions: plain pointers and sizes only; every pointer is HOST memory unless the name says `_dev`;
+ * the library copies and never retains host pointers past a call; matrices are column-major like Eigen's
+ * MatXX (dimension n = 8*nFrames + 4, order [fx fy cx cy | frame0(8) | frame1(8) ...]); all functions return
+ * 0 on success and a negative code on failure (ldso_b200_last_error() gives the text). There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with LDSO_B200_ERR_CUDA.
+ */
+#ifndef LDSO_B200_H_
+#define LDSO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDSO_B200_MAX_FRAMES 8      /* setting_maxFrames(7)+1, src/Setting.cc:33 */
+#define LDSO_B200_MAX_LEVELS 6      /* PYR_LEVELS, include/Settings.h:8 */
+#define LDSO_B200_PATTERN 8         /* patternNum, include/Settings.h:163 */
+
+#define LDSO_B200_OK 0
+#define LDSO_B200_ERR_ARG (-1)
+#define LDSO_B200_ERR_CUDA (-2)
+#define LDSO_B200_ERR_STATE (-3)
+
+/* ResState, include/internal/Residuals.h:32-34 */
+#define LDSO_B200_RES_IN 0
+#define LDSO_B200_RES_OOB 1
+#define LDSO_B200_RES_OUTLIER 2
+
+typedef struct ldso_b200_ctx ldso_b200_ctx;
+
+/* The mutable globals of src/Setting.cc the path reads (reference defaults in ldso_b200_default_settings). */
+typedef struct ldso_b200_settings {
+    float huberTH;                    /* setting_huberTH                 Setting.cc:76 */
+    float outlierTHSumComponent;      /* setting_outlierTHSumComponent   :41 */
+    float affineOptModeA;             /* setting_affineOptModeA          :65 */
+    float affineOptModeB;             /* setting_affineOptModeB          :66 */
+    float idepthFixPrior;             /* setting_idepthFixPrior          :16 */
+    float initialTransPrior;          /* :19 */
+    float initialRotPrior;            /* :18 */
+    float initialAffAPrior;           /* :21 */
+    float initialAffBPrior;           /* :20 */
+    float initialCalibHessian;        /* :22 */
+    float frameEnergyTHN;             /* :78 */
+    float frameEnergyTHFacMedian;     /* :80 */
+    float frameEnergyTHConstWeight;   /* :77 */
+    float overallEnergyTHWeight;      /* :81 */
+    float coarseCutoffTH;             /* :82 */
+    float thOptIterations;            /* :37 */
+    double solverModeDelta;           /* :24 */
+    float margWeightFac;              /* setting_margWeightFac           :45 */
+} ldso_b200_settings;
+
+void ldso_b200_default_settings(ldso_b200_settings *s);
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+/* w,h = wG[0],hG[0]; pyr_levels = pyrLevelsUsed (src/internal/GlobalCalib.cc:20-75). */
+ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_levels, const ldso_b200_settings *settings);
+void ldso_b200_destroy(ldso_b200_ctx *ctx);
+const char *ldso_b200_last_error(const ldso_b200_ctx *ctx);
+/* Run all work of this context on the caller's CUDA stream (cudaStream_t passed as void*). */
+int ldso_b200_set_stream(ldso_b200_ctx *ctx, void *cuda_stream);
+int ldso_b200_synchronize(ldso_b200_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long ldso_b200_launch_count(const ldso_b200_ctx *ctx);
+
+/* ---- keyframe images -----------------------------------------------------------------------------------
+ * Replaces the host-resident FrameHessian::dIp[lvl] (include/internal/FrameHessian.h:169): `dIp[l]` is the
+ * (I,dx,dy) Eigen::Vector3f array of level l exactly as FrameHessian::makeImages leaves it
+ * (src/internal/FrameHessian.cc:44-98). Stored on the device as 16-byte texels. slot in [0, 2*MAX_FRAMES). */
+int ldso_b200_upload_frame(ldso_b200_ctx *ctx, int slot, const float *const *dIp, int n_levels);
+/* Device-side FrameHessian::makeImages: upload the raw irradiance image (w*h floats) and build the pyramid
+ * with gradients on the GPU. */
+int ldso_b200_make_images(ldso_b200_ctx *ctx, int slot, const float *color);
+/* read a level back as (I,dx,dy) AoS — tests only */
+int ldso_b200_download_frame_level(ldso_b200_ctx *ctx, int slot, int lvl, float *dIp_out);
+
+/* ---- the optimisation window ---------------------------------------------------------------------------
+ * Flattened EnergyFunctional::allPoints (EnergyFunctional.cc:385-401, points ordered by host keyframe as
+ * makeIDX produces them) with each point's PointHessian::residuals list (CSR). */
+typedef struct ldso_b200_window {
+    int nPoints;
+    int nResiduals;
+    const int32_t *pt_host;          /* [nPoints]  FrameHessian::idx of the host, non-decreasing */
+    const float *pt_u, *pt_v;        /* [nPoints]  PointHessian::u,v                 PointHessian.h:83 */
+    const float *pt_idepth;          /* [nPoints]  idepth      (== idepth_scaled, SCALE_IDEPTH = 1) */
+    const float *pt_idepth_zero;     /* [nPoints]  idepth_zero */
+    const uint8_t *pt_has_prior;     /* [nPoints]  hasDepthPrior                     PointHessian.h:86 */
+    const float *pt_color;           /* [nPoints*8] color[]                          PointHessian.h:106 */
+    const float *pt_weights;         /* [nPoints*8] weights[]                        PointHessian.h:107 */
+    const int32_t *res_begin;        /* [nPoints+1] CSR offsets into the residual arrays */
+    const int32_t *res_target;       /* [nResiduals] targetIDX                       Residuals.h:109 */
+    const uint8_t *res_state;        /* [nResiduals] state_state, may be NULL (=> IN after resetOOB) */
+    const uint8_t *res_is_linearized;/* [nResiduals] isLinearized, may be NULL (=> 0) */
+    const float *res_toZeroF;        /* [nResiduals*8] res_toZeroF, may be NULL */
+} ldso_b200_window;
+
+int ldso_b200_set_window(ldso_b200_ctx *ctx, const ldso_b200_window *win);
+
+/* One keyframe's state record (include/internal/FrameHessian.h:163-201). */
+typedef struct ldso_b200_frame_state {
+    double evalR[9];       /* worldToCam_evalPT rotation, row-major */
+    double evalT[3];       /* worldToCam_evalPT translation */
+    double state_zero[10]; /* get_state_zero() (unscaled) */
+    double state[10];      /* get_state()      (unscaled) */
+    float ab_exposure;
+    float frameEnergyTH;
+    int32_t frame_id;      /* Frame::id; 0 => the gauge priors of FrameHessian::getPrior (FrameHessian.h:125-150) */
+    int32_t image_slot;    /* slot given to ldso_b200_upload_frame */
+} ldso_b200_frame_state;
+
+/* Replaces EnergyFunctional::insertFrame/setAdjointsF/setDeltaF and FullSystem::setPrecalcValues
+ * (EnergyFunctional.cc:30-61,403-489; FullSystem.cc:1423-1431; FrameFramePrecalc.cc:6-35): uploads the nF
+ * keyframe states and the calibration (value_scaled = [fx fy cx cy] of CalibHessian, value_zero its
+ * unscaled linearisation point; CalibHessian.h:71-100), computes adjoints, the 64 frame-pair precalc
+ * records, adHTdeltaF and the null-space projector of EnergyFunctional::orthogonalize (:685-717). */
+int ldso_b200_set_frames(ldso_b200_ctx *ctx, int nFrames, const ldso_b200_frame_state *frames,
+                         const double calib_value_scaled[4], const double calib_value_zero[4]);
+
+/* EnergyFunctional::HM / bM (EnergyFunctional.h:153-154). NULL => zero prior. */
+int ldso_b200_set_marg_prior(ldso_b200_ctx *ctx, const double *HM, const double *bM);
+int ldso_b200_get_marg_prior(ldso_b200_ctx *ctx, double *HM, double *bM);
+
+/* ---- piecewise operations (each maps to one reference call) ------------------------------------------- */
+/* FullSystem::linearizeAll(fixLinearization) restricted to the path (FullSystem.cc:1442-1543):
+ * PointFrameResidual::linearize on every active residual (Residuals.cc:13-214), energy sum,
+ * setNewFrameEnergyTH (:1762-1793), and for fixLinearization: applyRes(true).
+ * flags: bit0 = store the full RawResidualJacobian / projectedTo / centerProjectedTo for read-back. */
+int ldso_b200_linearize_all(ldso_b200_ctx *ctx, int fixLinearization, int flags, double *energy_out);
+/* FullSystem::applyRes_Reductor -> PointFrameResidual::applyRes(true) (Residuals.h:70-87, FullSystem.cc:1706) */
+int ldso_b200_apply_res(ldso_b200_ctx *ctx);
+/* FullSystem::backupState (non-momentum branch), FullSystem.cc:1662-1676 */
+int ldso_b200_backup_state(ldso_b200_ctx *ctx);
+/* EnergyFunctional::solveSystemF(iteration, lambda, HCalib) (EnergyFunctional.cc:240-351) for the default
+ * solver mode (SOLVER_FIX_LAMBDA | SOLVER_ORTHOGONALIZE_X_LATER): accumulateAF/LF/SCF_MT, the scaled 68x68
+ * LDLT, orthogonalize, resubstituteF_MT. Needs a stored Jacobian (linearize_all with flags bit0) or uses the
+ * on-chip records of the last linearize. Outputs may be NULL. */
+int ldso_b200_solve_system(ldso_b200_ctx *ctx, int iteration, double *lastHS, double *lastbS, double *lastX);
+/* The four stitched pieces of the last solve: AccumulatedTopHessianSSE::stitchDoubleMT (mode A, no priors;
+ * AccumulatedTopHessian.h:64-105) and AccumulatedSCHessianSSE::stitchDoubleMT (AccumulatedSCHessian.h:64-98). */
+int ldso_b200_get_system(ldso_b200_ctx *ctx, double *H_A, double *b_A, double *H_sc, double *b_sc, int *resInA);
+/* FullSystem::doStepFromBackup(1,1,1,1,1) + setPrecalcValues (FullSystem.cc:1587-1622); returns canbreak. */
+int ldso_b200_do_step(ldso_b200_ctx *ctx, int *canbreak);
+
+/* ---- the fused, device-resident Gauss-Newton loop ------------------------------------------------------
+ * FullSystem::optimize's prologue (resetOOB + linearizeAll(false) + applyRes, FullSystem.cc:734-771). */
+int ldso_b200_optimize_begin(ldso_b200_ctx *ctx, double *energy_out);
+/* n_iterations bodies of the loop FullSystem.cc:777-831 (forceAcceptStep) without any host round trip:
+ * backupState, solveSystemF, doStepFromBackup, linearizeAll(false), applyRes. Iteration numbers
+ * first_iteration.. are passed to solveSystemF (orthogonalize from iteration 2). Asynchronous on the
+ * context's stream; results are fetched with the getters below (which synchronise). */
+int ldso_b200_gn_iterations(ldso_b200_ctx *ctx, int first_iteration, int n_iterations);
+/* Multi-GPU: points are sharded over ranks (one context per GPU), frames/images replicated. A GN
+ * iteration is split around the ONE collective: gn_phase_a(iteration) runs [solve + frame step of `iteration`
+ * (skipped when iteration < 0 = the optimize() prologue)] + resubstitute/linearize/accumulate on this rank's
+ * shard and leaves the reduced system (doubles) in the buffer ldso_b200_reduce_buffer returns (device pointer);
+ * the caller all-reduces (sum) that buffer over ranks on the same stream (NCCL through torch.distributed);
+ * gn_phase_b() stitches the all-reduced accumulators and updates the newest frame's energy threshold. Every
+ * rank then solves the 68x68 system redundantly in its next gn_phase_a. set_shard positions this rank's
+ * newest-frame residual energies inside the shared select array (offset, global total) and switches the
+ * context to sharded mode; call it before the first launch. */
+int ldso_b200_reduce_buffer(ldso_b200_ctx *ctx, void **buf_dev, size_t *n_doubles);
+int ldso_b200_set_shard(ldso_b200_ctx *ctx, int newest_slot_offset, int newest_total);
+int ldso_b200_gn_phase_a(ldso_b200_ctx *ctx, int iteration);
+int ldso_b200_gn_phase_b(ldso_b200_ctx *ctx);
+
+/* ---- read-back (host mirrors of PointHessian / PointFrameResidual / FrameHessian fields) --------------- */
+int ldso_b200_get_energy(ldso_b200_ctx *ctx, double *energy, int *canbreak);
+int ldso_b200_get_last_solution(ldso_b200_ctx *ctx, double *lastHS, double *lastbS, double *lastX);
+/* any pointer may be NULL. Hcd4 is [nPoints*4]. */
+int ldso_b200_get_points(ldso_b200_ctx *ctx, float *idepth, float *idepth_zero, float *step, float *HdiF,
+                         float *bdSumF, float *Hdd_accAF, float *bd_accAF, float *Hcd4_accAF);
+/* J74 per residual: resF[8] Jpdxi[2][6] Jpdc[2][4] Jpdd[2] JIdx[2][8] JabF[2][8] JIdx2[4] JabJIdx[4] Jab2[4]
+ * (RawResidualJacobian.h:13-39); valid after linearize_all with flags bit0. */
+int ldso_b200_get_residuals(ldso_b200_ctx *ctx, uint8_t *state_state, uint8_t *state_NewState, float *state_energy,
+                            float *state_NewEnergy, float *state_NewEnergyWithOutlier, uint8_t *isActive,
+                            float *JpJdF8, float *J74, float *projectedTo16, float *centerProjectedTo3);
+/* per frame: state[10], step[10], frameEnergyTH; per pair (h + nF*t): precalc40 =
+ * [RTll_0(9) tTll_0(3) RTll(9) tTll(3) KRKiTll(9) KtTll(3) aff(2) b0 distanceLL], adHost/adTarget 8x8 row-major
+ * doubles, adHTdeltaF[8]; calib_value[4] (unscaled CalibHessian::value). */
+int ldso_b200_get_frames(ldso_b200_ctx *ctx, double *state10, double *step10, float *frameEnergyTH, float *precalc40,
+                         double *adHost64, double *adTarget64, float *adHTdeltaF8, double *calib_value4);
+int ldso_b200_get_nullspace_projector(ldso_b200_ctx *ctx, double *P);
+
+/* ---- coarse tracker (src/frontend/CoarseTracker.cc) ---------------------------------------------------- */
+/* CoarseTracker::makeK (:219-246) */
+int ldso_b200_tracker_make_k(ldso_b200_ctx *ctx, float fx, float fy, float cx, float cy);
+/* Point cloud of the reference keyframe as makeCoarseDepthL0 leaves it (:398-437): pc_u, pc_v, pc_idepth,
+ * pc_color of level lvl. */
+int ldso_b200_tracker_set_ref_level(ldso_b200_ctx *ctx, int lvl, int n, const float *pc_u, const float *pc_v,
+                                    const float *pc_idepth, const float *pc_color);
+/* Device-side CoarseTracker::makeCoarseDepthL0 (:258-438): n contributions (centerProjectedTo[3], HdiF) of the
+ * ACTIVE points whose newest residual is IN; ref_slot = image slot of lastRef. */
+int ldso_b200_tracker_make_coarse_depth(ldso_b200_ctx *ctx, int ref_slot, int n, const float *centerProjectedTo3,
+                                        const float *HdiF);
+int ldso_b200_tracker_get_ref_level(ldso_b200_ctx *ctx, int lvl, int *n, float *pc_u, float *pc_v, float *pc_idepth,
+                                    float *pc_color);
+/* lastRef_aff_g2l, lastRef->ab_exposure, newFrame image slot and newFrame->ab_exposure */
+int ldso_b200_tracker_set_frames(ldso_b200_ctx *ctx, float ref_aff_a, float ref_aff_b, float ref_exposure, int new_slot,
+                                 float new_exposure);
+/* One CoarseTracker::calcRes (:440-572) followed by calcGSSSE (:574-632) at the given pose: res6 =
+ * [E, numTermsInE, flowT, 0, flowRT, satRatio]; H (8x8 row-major) and b as calcGSSSE scales them.
+ * refToNew given as rotation R (row-major) and translation t. H/b may be NULL (calcRes only). */
+int ldso_b200_tracker_eval(ldso_b200_ctx *ctx, int lvl, const double R[9], const double t[3], float aff_a, float aff_b,
+                           float cutoffTH, double res6[6], double H[64], double b[8]);
+/* CoarseTracker::trackNewestCoarse (:61-217) with the LM loop resident on the device. R,t,aff in/out.
+ * Returns 1/0 (tracking good / bad) in *ok. */
+int ldso_b200_tracker_track(ldso_b200_ctx *ctx, double R[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl,
+                            const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3],
+                            int *ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDSO_B200_H_ */

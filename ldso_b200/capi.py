@@ -1,0 +1,379 @@
+"""ctypes binding of the C ABI in include/ldso_b200.h (libldso_b200.so, built in-tree by ldso_b200.build).
+
+This is plumbing only: it marshals numpy arrays into the `extern "C"` entry points. All arithmetic of the hot path
+runs in the sm_100a kernels of ldso_b200/csrc; there is no CPU fallback — if the library or a CUDA device is missing
+every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libldso_b200.so")
+
+MAX_FRAMES = 8
+RES_IN, RES_OOB, RES_OUTLIER = 0, 1, 2
+
+c_fp = C.POINTER(C.c_float)
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_bp = C.POINTER(C.c_uint8)
+
+
+class Settings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "huberTH", "outlierTHSumComponent", "affineOptModeA", "affineOptModeB", "idepthFixPrior", "initialTransPrior",
+        "initialRotPrior", "initialAffAPrior", "initialAffBPrior", "initialCalibHessian", "frameEnergyTHN",
+        "frameEnergyTHFacMedian", "frameEnergyTHConstWeight", "overallEnergyTHWeight", "coarseCutoffTH",
+        "thOptIterations")] + [("solverModeDelta", C.c_double), ("margWeightFac", C.c_float)]
+
+
+class WindowC(C.Structure):
+    _fields_ = [("nPoints", C.c_int), ("nResiduals", C.c_int), ("pt_host", c_ip), ("pt_u", c_fp), ("pt_v", c_fp),
+                ("pt_idepth", c_fp), ("pt_idepth_zero", c_fp), ("pt_has_prior", c_bp), ("pt_color", c_fp),
+                ("pt_weights", c_fp), ("res_begin", c_ip), ("res_target", c_ip), ("res_state", c_bp),
+                ("res_is_linearized", c_bp), ("res_toZeroF", c_fp)]
+
+
+class FrameStateC(C.Structure):
+    _fields_ = [("evalR", C.c_double * 9), ("evalT", C.c_double * 3), ("state_zero", C.c_double * 10),
+                ("state", C.c_double * 10), ("ab_exposure", C.c_float), ("frameEnergyTH", C.c_float),
+                ("frame_id", C.c_int32), ("image_slot", C.c_int32)]
+
+
+# every symbol include/ldso_b200.h declares (tests check the shared object exports all of them)
+SYMBOLS = [
+    "ldso_b200_default_settings", "ldso_b200_create", "ldso_b200_destroy", "ldso_b200_last_error", "ldso_b200_set_stream",
+    "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_upload_frame", "ldso_b200_make_images",
+    "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
+    "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_optimize_begin",
+    "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
+    "ldso_b200_gn_phase_b", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
+    "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
+    "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
+    "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
+]
+
+_lib = None
+
+
+def load():
+    """Load libldso_b200.so (raises if it has not been built: there is nothing to fall back to)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m ldso_b200.build` (nvcc, sm_100a). "
+                               "ldso_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.ldso_b200_create.restype = C.c_void_p
+        L.ldso_b200_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Settings)]
+        L.ldso_b200_destroy.argtypes = [C.c_void_p]
+        L.ldso_b200_last_error.restype = C.c_char_p
+        L.ldso_b200_last_error.argtypes = [C.c_void_p]
+        L.ldso_b200_launch_count.restype = C.c_longlong
+        L.ldso_b200_launch_count.argtypes = [C.c_void_p]
+        L.ldso_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        for name in SYMBOLS:
+            fn = getattr(L, name)
+            if name not in ("ldso_b200_create", "ldso_b200_destroy", "ldso_b200_last_error", "ldso_b200_launch_count",
+                            "ldso_b200_default_settings", "ldso_b200_set_stream"):
+                fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def default_settings() -> Settings:
+    s = Settings()
+    load().ldso_b200_default_settings(C.byref(s))
+    return s
+
+
+def _f(a):
+    return None if a is None else a.ctypes.data_as(c_fp)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(c_ip)
+
+
+def _b(a):
+    return None if a is None else a.ctypes.data_as(c_bp)
+
+
+class Error(RuntimeError):
+    pass
+
+
+class Context:
+    """One ldso_b200 context = one GPU's device-resident keyframe window + coarse tracker."""
+
+    def __init__(self, w, h, levels, device=0, settings: Settings | None = None):
+        self.L = load()
+        self.w, self.h, self.levels = int(w), int(h), int(levels)
+        self.ctx = self.L.ldso_b200_create(int(device), self.w, self.h, self.levels, C.byref(settings) if settings is not None else None)
+        if not self.ctx:
+            raise Error("ldso_b200_create failed: no usable CUDA device (ldso_b200 has no CPU fallback)")
+        self.ctx = C.c_void_p(self.ctx)
+        self.nF = 0
+        self.nP = 0
+        self.nR = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.ldso_b200_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise Error(f"ldso_b200 error {rc}: {self.L.ldso_b200_last_error(self.ctx).decode()}")
+
+    @property
+    def n(self):
+        return 8 * self.nF + 4
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream_ptr: int):
+        self._chk(self.L.ldso_b200_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._chk(self.L.ldso_b200_synchronize(self.ctx))
+
+    def launch_count(self) -> int:
+        return int(self.L.ldso_b200_launch_count(self.ctx))
+
+    # ---- images
+    def upload_frame(self, slot, pyramid):
+        lv = [np.ascontiguousarray(p, np.float32) for p in pyramid]
+        arr = (c_fp * len(lv))(*[_f(p) for p in lv])
+        self._chk(self.L.ldso_b200_upload_frame(self.ctx, int(slot), arr, len(lv)))
+
+    def make_images(self, slot, color):
+        color = np.ascontiguousarray(color, np.float32)
+        assert color.shape == (self.h, self.w)
+        self._chk(self.L.ldso_b200_make_images(self.ctx, int(slot), _f(color)))
+
+    def download_frame_level(self, slot, lvl):
+        out = np.zeros((self.h >> lvl, self.w >> lvl, 3), np.float32)
+        self._chk(self.L.ldso_b200_download_frame_level(self.ctx, int(slot), int(lvl), _f(out)))
+        return out
+
+    # ---- window
+    def set_frames(self, Rcw, tcw, state_zero, state, ab_exposure, frame_id, slots, K_scaled, K_zero=None,
+                   frame_energy_th=None):
+        nF = len(Rcw)
+        arr = (FrameStateC * nF)()
+        for i in range(nF):
+            f = arr[i]
+            f.evalR[:] = np.asarray(Rcw[i], np.float64).reshape(-1).tolist()
+            f.evalT[:] = np.asarray(tcw[i], np.float64).tolist()
+            f.state_zero[:] = np.asarray(state_zero[i], np.float64).tolist()
+            f.state[:] = np.asarray(state[i], np.float64).tolist()
+            f.ab_exposure = float(ab_exposure[i])
+            f.frameEnergyTH = float(8 * 8 * 8 if frame_energy_th is None else frame_energy_th[i])
+            f.frame_id = int(frame_id[i])
+            f.image_slot = int(slots[i])
+        Ks = np.ascontiguousarray(K_scaled, np.float64)
+        if K_zero is None:   # CalibHessian ctor: value_zero = value = SCALE_*_INVERSE * value_scaled
+            K_zero = Ks * np.float64(np.float32(1.0) / np.float32(50.0))
+        Kz = np.ascontiguousarray(K_zero, np.float64)
+        self._chk(self.L.ldso_b200_set_frames(self.ctx, nF, arr, _d(Ks), _d(Kz)))
+        self.nF = nF
+
+    def set_window(self, pt_host, pt_u, pt_v, pt_idepth, pt_idepth_zero, pt_has_prior, pt_color, pt_weights, res_begin,
+                   res_target, res_state=None, res_is_linearized=None, res_toZeroF=None):
+        keep = dict(
+            pt_host=np.ascontiguousarray(pt_host, np.int32), pt_u=np.ascontiguousarray(pt_u, np.float32),
+            pt_v=np.ascontiguousarray(pt_v, np.float32), pt_idepth=np.ascontiguousarray(pt_idepth, np.float32),
+            pt_idepth_zero=np.ascontiguousarray(pt_idepth_zero, np.float32),
+            pt_has_prior=np.ascontiguousarray(pt_has_prior, np.uint8), pt_color=np.ascontiguousarray(pt_color, np.float32),
+            pt_weights=np.ascontiguousarray(pt_weights, np.float32), res_begin=np.ascontiguousarray(res_begin, np.int32),
+            res_target=np.ascontiguousarray(res_target, np.int32))
+        w = WindowC()
+        w.nPoints = int(keep["pt_host"].shape[0])
+        w.nResiduals = int(keep["res_target"].shape[0])
+        w.pt_host = _i(keep["pt_host"]); w.pt_u = _f(keep["pt_u"]); w.pt_v = _f(keep["pt_v"])
+        w.pt_idepth = _f(keep["pt_idepth"]); w.pt_idepth_zero = _f(keep["pt_idepth_zero"])
+        w.pt_has_prior = _b(keep["pt_has_prior"]); w.pt_color = _f(keep["pt_color"]); w.pt_weights = _f(keep["pt_weights"])
+        w.res_begin = _i(keep["res_begin"]); w.res_target = _i(keep["res_target"])
+        if res_state is not None:
+            keep["res_state"] = np.ascontiguousarray(res_state, np.uint8); w.res_state = _b(keep["res_state"])
+        if res_is_linearized is not None:
+            keep["lin"] = np.ascontiguousarray(res_is_linearized, np.uint8); w.res_is_linearized = _b(keep["lin"])
+        if res_toZeroF is not None:
+            keep["rtz"] = np.ascontiguousarray(res_toZeroF, np.float32); w.res_toZeroF = _f(keep["rtz"])
+        self._chk(self.L.ldso_b200_set_window(self.ctx, C.byref(w)))
+        self.nP, self.nR = w.nPoints, w.nResiduals
+
+    def load_synth_window(self, win, upload_images=True):
+        """Convenience: push a ldso_b200.synth.Window (images, frames, points, residuals)."""
+        if upload_images:
+            for i in range(win.nF):
+                self.upload_frame(i, win.pyramids[i])
+        self.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(win.nF)), win.K)
+        self.set_window(win.pt_host, win.pt_u, win.pt_v, win.pt_idepth, win.pt_idepth_zero, win.pt_has_prior,
+                        win.pt_color, win.pt_weights, win.res_begin, win.res_target)
+
+    def set_marg_prior(self, HM=None, bM=None):
+        HMc = None if HM is None else np.asfortranarray(HM, np.float64)
+        bMc = None if bM is None else np.ascontiguousarray(bM, np.float64)
+        self._chk(self.L.ldso_b200_set_marg_prior(self.ctx, _d(HMc), _d(bMc)))
+
+    # ---- piecewise
+    def linearize_all(self, fix=False, flags=1):
+        e = C.c_double()
+        self._chk(self.L.ldso_b200_linearize_all(self.ctx, int(fix), int(flags), C.byref(e)))
+        return e.value
+
+    def apply_res(self):
+        self._chk(self.L.ldso_b200_apply_res(self.ctx))
+
+    def backup_state(self):
+        self._chk(self.L.ldso_b200_backup_state(self.ctx))
+
+    def solve_system(self, iteration):
+        n = self.n
+        HS = np.zeros((n, n), np.float64, order="F")
+        bS = np.zeros(n)
+        X = np.zeros(n)
+        self._chk(self.L.ldso_b200_solve_system(self.ctx, int(iteration), _d(HS), _d(bS), _d(X)))
+        return HS, bS, X
+
+    def do_step(self):
+        cb = C.c_int()
+        self._chk(self.L.ldso_b200_do_step(self.ctx, C.byref(cb)))
+        return bool(cb.value)
+
+    # ---- fused loop
+    def optimize_begin(self):
+        e = C.c_double()
+        self._chk(self.L.ldso_b200_optimize_begin(self.ctx, C.byref(e)))
+        return e.value
+
+    def gn_iterations(self, first, n):
+        self._chk(self.L.ldso_b200_gn_iterations(self.ctx, int(first), int(n)))
+
+    def reduce_buffer(self):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._chk(self.L.ldso_b200_reduce_buffer(self.ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_shard(self, offset, total):
+        self._chk(self.L.ldso_b200_set_shard(self.ctx, int(offset), int(total)))
+
+    def gn_phase_a(self, iteration):
+        self._chk(self.L.ldso_b200_gn_phase_a(self.ctx, int(iteration)))
+
+    def gn_phase_b(self):
+        self._chk(self.L.ldso_b200_gn_phase_b(self.ctx))
+
+    # ---- read-back
+    def energy(self):
+        e = C.c_double()
+        cb = C.c_int()
+        self._chk(self.L.ldso_b200_get_energy(self.ctx, C.byref(e), C.byref(cb)))
+        return e.value, bool(cb.value)
+
+    def last_solution(self):
+        n = self.n
+        HS = np.zeros((n, n), np.float64, order="F")
+        bS = np.zeros(n)
+        X = np.zeros(n)
+        self._chk(self.L.ldso_b200_get_last_solution(self.ctx, _d(HS), _d(bS), _d(X)))
+        return dict(lastHS=HS, lastbS=bS, lastX=X)
+
+    def system(self):
+        n = self.n
+        out = dict(HA=np.zeros((n, n), np.float64, order="F"), bA=np.zeros(n), Hsc=np.zeros((n, n), np.float64, order="F"),
+                   bsc=np.zeros(n))
+        r = C.c_int()
+        self._chk(self.L.ldso_b200_get_system(self.ctx, _d(out["HA"]), _d(out["bA"]), _d(out["Hsc"]), _d(out["bsc"]), C.byref(r)))
+        out["resInA"] = r.value
+        return out
+
+    def points(self):
+        nP = self.nP
+        keys = ("idepth", "idepth_zero", "step", "HdiF", "bdSumF", "Hdd_accAF", "bd_accAF")
+        out = {k: np.zeros(nP, np.float32) for k in keys}
+        out["Hcd_accAF"] = np.zeros((nP, 4), np.float32)
+        self._chk(self.L.ldso_b200_get_points(self.ctx, *[_f(out[k]) for k in keys], _f(out["Hcd_accAF"])))
+        return out
+
+    def residuals(self, with_J=True):
+        nR = self.nR
+        out = dict(state_state=np.zeros(nR, np.uint8), state_NewState=np.zeros(nR, np.uint8),
+                   state_energy=np.zeros(nR, np.float32), state_NewEnergy=np.zeros(nR, np.float32),
+                   state_NewEnergyWithOutlier=np.zeros(nR, np.float32), isActive=np.zeros(nR, np.uint8),
+                   JpJdF=np.zeros((nR, 8), np.float32))
+        if with_J:
+            out.update(J=np.zeros((nR, 74), np.float32), projectedTo=np.zeros((nR, 8, 2), np.float32),
+                       centerProjectedTo=np.zeros((nR, 3), np.float32))
+        self._chk(self.L.ldso_b200_get_residuals(
+            self.ctx, _b(out["state_state"]), _b(out["state_NewState"]), _f(out["state_energy"]), _f(out["state_NewEnergy"]),
+            _f(out["state_NewEnergyWithOutlier"]), _b(out["isActive"]), _f(out["JpJdF"]), _f(out.get("J")),
+            _f(out.get("projectedTo")), _f(out.get("centerProjectedTo"))))
+        return out
+
+    def frames(self):
+        nF = self.nF
+        out = dict(state=np.zeros((nF, 10)), step=np.zeros((nF, 10)), frameEnergyTH=np.zeros(nF, np.float32),
+                   precalc=np.zeros((nF * nF, 40), np.float32), adHost=np.zeros((nF * nF, 8, 8)),
+                   adTarget=np.zeros((nF * nF, 8, 8)), adHTdeltaF=np.zeros((nF * nF, 8), np.float32), calib_value=np.zeros(4))
+        self._chk(self.L.ldso_b200_get_frames(self.ctx, _d(out["state"]), _d(out["step"]), _f(out["frameEnergyTH"]),
+                                              _f(out["precalc"]), _d(out["adHost"]), _d(out["adTarget"]), _f(out["adHTdeltaF"]),
+                                              _d(out["calib_value"])))
+        return out
+
+    def nullspace_projector(self):
+        n = self.n
+        P = np.zeros((n, n), np.float64, order="F")
+        self._chk(self.L.ldso_b200_get_nullspace_projector(self.ctx, _d(P)))
+        return P
+
+    # ---- tracker
+    def tracker_make_k(self, fx, fy, cx, cy):
+        self._chk(self.L.ldso_b200_tracker_make_k(self.ctx, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))
+
+    def tracker_set_ref_level(self, lvl, u, v, idepth, color):
+        a = [np.ascontiguousarray(x, np.float32) for x in (u, v, idepth, color)]
+        self._chk(self.L.ldso_b200_tracker_set_ref_level(self.ctx, int(lvl), int(a[0].shape[0]), *[_f(x) for x in a]))
+
+    def tracker_set_frames(self, ref_a, ref_b, ref_exposure, new_slot, new_exposure):
+        self._chk(self.L.ldso_b200_tracker_set_frames(self.ctx, C.c_float(ref_a), C.c_float(ref_b), C.c_float(ref_exposure),
+                                                      int(new_slot), C.c_float(new_exposure)))
+
+    def tracker_eval(self, lvl, R, t, aff_a, aff_b, cutoff, with_H=True):
+        R = np.ascontiguousarray(R, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        res = np.zeros(6)
+        H = np.zeros((8, 8))
+        b = np.zeros(8)
+        self._chk(self.L.ldso_b200_tracker_eval(self.ctx, int(lvl), _d(R), _d(t), C.c_float(aff_a), C.c_float(aff_b),
+                                                C.c_float(cutoff), _d(res), _d(H) if with_H else None, _d(b) if with_H else None))
+        return res, H, b
+
+    def tracker_track(self, R, t, aff_a, aff_b, coarsest, min_res=None):
+        R = np.array(R, np.float64, order="C")
+        t = np.array(t, np.float64)
+        a = C.c_float(aff_a)
+        b = C.c_float(aff_b)
+        mr = np.full(5, np.nan) if min_res is None else np.ascontiguousarray(min_res, np.float64)
+        lr = np.zeros(5)
+        lf = np.zeros(3)
+        ok = C.c_int()
+        self._chk(self.L.ldso_b200_tracker_track(self.ctx, _d(R), _d(t), C.byref(a), C.byref(b), int(coarsest), _d(mr), _d(lr),
+                                                 _d(lf), C.byref(ok)))
+        return bool(ok.value), R, t, a.value, b.value, lr, lf

@@ -1,0 +1,962 @@
+// ldso_b200 C ABI implementation (include/ldso_b200.h): context, device memory, kernel launches.
+// No CPU fallback anywhere: every compute entry point launches sm_100a kernels or fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "se3_math.cuh"
+#include "host_math.h"
+#include "img_kernels.cuh"
+#include "ba_k1.cuh"
+#include "ba_k2.cuh"
+#include "tracker_kernels.cuh"
+
+static_assert(K1_THREADS / 32 == MAXF, "phase B maps one warp to one target frame");
+
+#define NSLOTS (2 * MAXF)
+
+struct ldso_b200_ctx {
+    int device = 0, w = 0, h = 0, levels = 0;
+    int lw[MAXLVL], lh[MAXLVL];
+    ldso_b200_settings S;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    long long launches = 0;
+    int sm_count = 148;
+
+    float4 *img[NSLOTS][MAXLVL];
+    float *scratch = nullptr;          // upload staging (w*h*3 floats)
+    size_t scratch_floats = 0;
+
+    // window
+    DevWindow d;
+    std::vector<void *> win_allocs;
+    bool have_window = false, have_frames = false, derived_dirty = true;
+    std::vector<int> h_pt_host, h_res_begin, h_res_target;
+    int nF = 0, n = 0;
+    int slots[MAXF];
+    WinState *ws_dev = nullptr;
+    WinState *ws_host = nullptr;       // pinned staging copy
+    SolveBufs sb;
+    double *solve_mem = nullptr;
+    int *iteration_dev = nullptr;
+    uint8_t *pt_sel_dev = nullptr;
+    size_t k1_smem = 0;
+    bool multi = false;
+
+    // tracker
+    TrkLevel trk[MAXLVL];
+    float *trk_pc[MAXLVL][4];
+    int trk_cap[MAXLVL];
+    float trk_fx[MAXLVL], trk_fy[MAXLVL], trk_cx[MAXLVL], trk_cy[MAXLVL];
+    float trk_Ki[MAXLVL][9];
+    float ref_aff_a = 0, ref_aff_b = 0, ref_exposure = 1, new_exposure = 1;
+    int new_slot = -1;
+    float *trk_partials = nullptr;
+    unsigned *trk_counter = nullptr;
+    double *trk_out_dev = nullptr;
+    TrkTrackOut *trk_track_out = nullptr;
+
+    int fail(int code, const char *msg) { err = msg; return code; }
+    int fail_cuda(cudaError_t e, const char *call, const char *file, int line) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, call);
+        err = buf;
+        return LDSO_B200_ERR_CUDA;
+    }
+};
+
+extern "C" void ldso_b200_default_settings(ldso_b200_settings *s) {
+    s->huberTH = 9;
+    s->outlierTHSumComponent = 50 * 50;
+    s->affineOptModeA = 1e12f;
+    s->affineOptModeB = 1e8f;
+    s->idepthFixPrior = 50 * 50;
+    s->initialTransPrior = 1e10f;
+    s->initialRotPrior = 1e11f;
+    s->initialAffAPrior = 1e14f;
+    s->initialAffBPrior = 1e14f;
+    s->initialCalibHessian = 5e9f;
+    s->frameEnergyTHN = 0.7f;
+    s->frameEnergyTHFacMedian = 1.5f;
+    s->frameEnergyTHConstWeight = 0.5f;
+    s->overallEnergyTHWeight = 1;
+    s->coarseCutoffTH = 20;
+    s->thOptIterations = 1.2f;
+    s->solverModeDelta = 0.00001;
+    s->margWeightFac = 0.5f * 0.5f;
+}
+
+extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_levels, const ldso_b200_settings *settings) {
+    if (w <= 0 || h <= 0 || pyr_levels < 1 || pyr_levels > MAXLVL) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+        fprintf(stderr, "ldso_b200: no CUDA device available (there is no CPU fallback)\n");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    ldso_b200_ctx *c = new ldso_b200_ctx();
+    c->device = device; c->w = w; c->h = h; c->levels = pyr_levels;
+    if (settings) c->S = *settings; else ldso_b200_default_settings(&c->S);
+    for (int l = 0; l < MAXLVL; l++) { c->lw[l] = w >> l; c->lh[l] = h >> l; }
+    memset(c->img, 0, sizeof(c->img));
+    memset(&c->d, 0, sizeof(c->d));
+    memset(&c->sb, 0, sizeof(c->sb));
+    memset(c->trk, 0, sizeof(c->trk));
+    memset(c->trk_pc, 0, sizeof(c->trk_pc));
+    memset(c->trk_cap, 0, sizeof(c->trk_cap));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->own_stream = true;
+    ok = ok && cudaMalloc(&c->ws_dev, sizeof(WinState)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->ws_host, sizeof(WinState)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->iteration_dev, sizeof(int)) == cudaSuccess;
+    // solve buffers: 4 + 1 + 1 + 1 matrices (n x n) and 6 vectors
+    const size_t nn = (size_t) MAXN * MAXN;
+    ok = ok && cudaMalloc(&c->solve_mem, sizeof(double) * (7 * nn + 8 * MAXN)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->trk_partials, sizeof(float) * 1024 * TRK_NACC) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->trk_counter, sizeof(unsigned)) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->trk_out_dev, sizeof(double) * 80) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->trk_track_out, sizeof(TrkTrackOut)) == cudaSuccess;
+    if (!ok) { fprintf(stderr, "ldso_b200: context allocation failed: %s\n", cudaGetErrorString(cudaGetLastError())); delete c; return nullptr; }
+    cudaMemset(c->solve_mem, 0, sizeof(double) * (7 * nn + 8 * MAXN));
+    cudaMemset(c->trk_counter, 0, sizeof(unsigned));
+    cudaMemset(c->iteration_dev, 0, sizeof(int));
+    cudaMemset(c->ws_dev, 0, sizeof(WinState));
+    memset(c->ws_host, 0, sizeof(WinState));
+    double *p = c->solve_mem;
+    c->sb.H_A = p; p += nn; c->sb.H_sc = p; p += nn; c->sb.HM = p; p += nn; c->sb.Pns = p; p += nn; c->sb.lastHS = p; p += nn;
+    p += 2 * nn;   // spare
+    c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
+    cudaFuncSetAttribute(k1_linearize_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem_bytes(64));
+    cudaFuncSetAttribute(k3_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K3_SMEM_BYTES);
+    return c;
+}
+
+static void free_window(ldso_b200_ctx *c) {
+    for (void *p : c->win_allocs) cudaFree(p);
+    c->win_allocs.clear();
+    c->have_window = false;
+}
+
+extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_window(c);
+    for (int s = 0; s < NSLOTS; s++) for (int l = 0; l < MAXLVL; l++) if (c->img[s][l]) cudaFree(c->img[s][l]);
+    for (int l = 0; l < MAXLVL; l++) for (int k = 0; k < 4; k++) if (c->trk_pc[l][k]) cudaFree(c->trk_pc[l][k]);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->ws_dev) cudaFree(c->ws_dev);
+    if (c->ws_host) cudaFreeHost(c->ws_host);
+    if (c->iteration_dev) cudaFree(c->iteration_dev);
+    if (c->solve_mem) cudaFree(c->solve_mem);
+    if (c->trk_partials) cudaFree(c->trk_partials);
+    if (c->trk_counter) cudaFree(c->trk_counter);
+    if (c->trk_out_dev) cudaFree(c->trk_out_dev);
+    if (c->trk_track_out) cudaFree(c->trk_track_out);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *ldso_b200_last_error(const ldso_b200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" long long ldso_b200_launch_count(const ldso_b200_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int ldso_b200_set_stream(ldso_b200_ctx *c, void *cuda_stream) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t) cuda_stream;
+    c->own_stream = false;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_synchronize(ldso_b200_ctx *c) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+#define LAUNCH_CHECK(c)                                            \
+    do {                                                           \
+        (c)->launches++;                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return (c)->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------- images
+static int ensure_slot(ldso_b200_ctx *c, int slot) {
+    if (slot < 0 || slot >= NSLOTS) return c->fail(LDSO_B200_ERR_ARG, "image slot out of range");
+    for (int l = 0; l < c->levels; l++)
+        if (!c->img[slot][l]) CUDA_CHECK_RET(c, cudaMalloc(&c->img[slot][l], sizeof(float4) * (size_t) c->lw[l] * c->lh[l]));
+    if (!c->scratch) {
+        c->scratch_floats = (size_t) c->w * c->h * 3;
+        CUDA_CHECK_RET(c, cudaMalloc(&c->scratch, sizeof(float) * c->scratch_floats));
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_upload_frame(ldso_b200_ctx *c, int slot, const float *const *dIp, int n_levels) {
+    if (!c || !dIp) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (n_levels != c->levels) return c->fail(LDSO_B200_ERR_ARG, "n_levels != pyr_levels of the context");
+    int rc = ensure_slot(c, slot);
+    if (rc) return rc;
+    for (int l = 0; l < c->levels; l++) {
+        const int npx = c->lw[l] * c->lh[l];
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->scratch, dIp[l], sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
+        k_repack_aos3<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->scratch, c->img[slot][l], npx);
+        LAUNCH_CHECK(c);
+        // the staging buffer is reused by the next level: the copies are stream-ordered, but the host buffer
+        // of a pageable cudaMemcpyAsync is consumed before the call returns, so this is safe.
+    }
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *color) {
+    if (!c || !color) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    int rc = ensure_slot(c, slot);
+    if (rc) return rc;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->scratch, color, sizeof(float) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
+    for (int l = 0; l < c->levels; l++) {
+        const int npx = c->lw[l] * c->lh[l];
+        k_pyr_intensity<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->scratch, l == 0 ? nullptr : c->img[slot][l - 1], c->img[slot][l],
+                                                                    c->lw[l], c->lh[l], l == 0 ? 0 : c->lw[l - 1]);
+        LAUNCH_CHECK(c);
+        k_pyr_gradients<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->img[slot][l], c->lw[l], c->lh[l]);
+        LAUNCH_CHECK(c);
+    }
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_download_frame_level(ldso_b200_ctx *c, int slot, int lvl, float *out) {
+    if (!c || !out || slot < 0 || slot >= NSLOTS || lvl < 0 || lvl >= c->levels || !c->img[slot][lvl]) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int npx = c->lw[lvl] * c->lh[lvl];
+    k_unpack_aos3<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->img[slot][lvl], c->scratch, npx);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out, c->scratch, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- window
+template<typename T>
+static int dev_alloc(ldso_b200_ctx *c, T **p, size_t count) {
+    void *q = nullptr;
+    CUDA_CHECK_RET(c, cudaMalloc(&q, sizeof(T) * std::max<size_t>(count, 1)));
+    c->win_allocs.push_back(q);
+    *p = (T *) q;
+    return 0;
+}
+template<typename T>
+static int dev_upload(ldso_b200_ctx *c, T *dst, const T *src, size_t count) {
+    if (count == 0) return 0;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *win) {
+    if (!c || !win) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int nP = win->nPoints, nR = win->nResiduals;
+    if (nP < 0 || nR < 0) return c->fail(LDSO_B200_ERR_ARG, "negative sizes");
+    for (int p = 0; p < nP; p++) {
+        if (win->pt_host[p] < 0 || win->pt_host[p] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "pt_host out of range");
+        if (p > 0 && win->pt_host[p] < win->pt_host[p - 1]) return c->fail(LDSO_B200_ERR_ARG, "points must be ordered by host frame");
+        if (win->res_begin[p + 1] < win->res_begin[p]) return c->fail(LDSO_B200_ERR_ARG, "res_begin must be non-decreasing");
+        if (win->res_begin[p + 1] - win->res_begin[p] > MAXF) return c->fail(LDSO_B200_ERR_ARG, "more than MAX_FRAMES residuals on a point");
+    }
+    if (nP > 0 && (win->res_begin[0] != 0 || win->res_begin[nP] != nR)) return c->fail(LDSO_B200_ERR_ARG, "res_begin does not cover the residual arrays");
+    for (int r = 0; r < nR; r++) if (win->res_target[r] < 0 || win->res_target[r] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "res_target out of range");
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    free_window(c);
+    DevWindow &d = c->d;
+    memset(&d, 0, sizeof(d));
+    d.nP = nP; d.nR = nR;
+    c->h_pt_host.assign(win->pt_host, win->pt_host + nP);
+    c->h_res_begin.assign(win->res_begin, win->res_begin + nP + 1);
+    if (nP == 0) c->h_res_begin.assign(1, 0);
+    c->h_res_target.assign(win->res_target, win->res_target + nR);
+
+    int *pt_host, *pt_res_begin, *res_point, *res_target;
+    int rc = 0;
+    rc |= dev_alloc(c, &pt_host, nP); rc |= dev_alloc(c, &pt_res_begin, nP + 1);
+    rc |= dev_alloc(c, &res_point, nR); rc |= dev_alloc(c, &res_target, nR);
+    rc |= dev_alloc(c, &d.pt_u, nP); rc |= dev_alloc(c, &d.pt_v, nP); rc |= dev_alloc(c, &d.pt_idepth, nP);
+    rc |= dev_alloc(c, &d.pt_idepth_zero, nP); rc |= dev_alloc(c, &d.pt_idepth_backup, nP); rc |= dev_alloc(c, &d.pt_step, nP);
+    rc |= dev_alloc(c, &d.pt_color, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_weights, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_priorF, nP);
+    rc |= dev_alloc(c, &d.pt_HdiF, nP); rc |= dev_alloc(c, &d.pt_bdSumF, nP); rc |= dev_alloc(c, &d.pt_Hcd, (size_t) nP * 4);
+    rc |= dev_alloc(c, &d.pt_Hdd, nP); rc |= dev_alloc(c, &d.pt_bd, nP);
+    rc |= dev_alloc(c, &d.res_state, nR); rc |= dev_alloc(c, &d.res_new_state, nR); rc |= dev_alloc(c, &d.res_active, nR);
+    rc |= dev_alloc(c, &d.res_lin, nR); rc |= dev_alloc(c, &d.res_energy, nR); rc |= dev_alloc(c, &d.res_new_energy, nR);
+    rc |= dev_alloc(c, &d.res_new_energy_wo, nR); rc |= dev_alloc(c, &d.res_JpJdF, (size_t) nR * 8);
+    rc |= dev_alloc(c, &d.res_JpJdF_new, (size_t) nR * 8); rc |= dev_alloc(c, &d.res_J, (size_t) nR * 74);
+    rc |= dev_alloc(c, &d.res_proj, (size_t) nR * 16); rc |= dev_alloc(c, &d.res_cpt, (size_t) nR * 3);
+    rc |= dev_alloc(c, &d.res_toZero, (size_t) nR * 8);
+    rc |= dev_alloc(c, &c->pt_sel_dev, nP);
+    if (rc) return LDSO_B200_ERR_CUDA;
+    d.pt_host = pt_host; d.pt_res_begin = pt_res_begin; d.res_point = res_point; d.res_target = res_target;
+
+    std::vector<int> h_res_point(nR);
+    for (int p = 0; p < nP; p++) for (int r = c->h_res_begin[p]; r < c->h_res_begin[p + 1]; r++) h_res_point[r] = p;
+    std::vector<float> priorF(nP);
+    for (int p = 0; p < nP; p++)   // PointHessian::takeData (PointHessian.h:112-117)
+        priorF[p] = (win->pt_has_prior && win->pt_has_prior[p]) ? c->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0.f;
+    std::vector<uint8_t> st(nR, (uint8_t) LDSO_B200_RES_IN), lin(nR, 0);
+    if (win->res_state) st.assign(win->res_state, win->res_state + nR);
+    if (win->res_is_linearized) lin.assign(win->res_is_linearized, win->res_is_linearized + nR);
+
+    rc |= dev_upload(c, pt_host, win->pt_host, nP);
+    rc |= dev_upload(c, pt_res_begin, c->h_res_begin.data(), nP + 1);
+    rc |= dev_upload(c, res_point, h_res_point.data(), nR);
+    rc |= dev_upload(c, res_target, win->res_target, nR);
+    rc |= dev_upload(c, d.pt_u, win->pt_u, nP); rc |= dev_upload(c, d.pt_v, win->pt_v, nP);
+    rc |= dev_upload(c, d.pt_idepth, win->pt_idepth, nP); rc |= dev_upload(c, d.pt_idepth_zero, win->pt_idepth_zero, nP);
+    rc |= dev_upload(c, d.pt_idepth_backup, win->pt_idepth, nP);
+    rc |= dev_upload(c, d.pt_color, win->pt_color, (size_t) nP * 8); rc |= dev_upload(c, d.pt_weights, win->pt_weights, (size_t) nP * 8);
+    rc |= dev_upload(c, d.pt_priorF, priorF.data(), nP);
+    rc |= dev_upload(c, d.res_state, st.data(), nR); rc |= dev_upload(c, d.res_lin, lin.data(), nR);
+    if (win->res_toZeroF) rc |= dev_upload(c, d.res_toZero, win->res_toZeroF, (size_t) nR * 8);
+    if (rc) return LDSO_B200_ERR_CUDA;
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_step, 0, sizeof(float) * std::max(nP, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_HdiF, 0, sizeof(float) * std::max(nP, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_bdSumF, 0, sizeof(float) * std::max(nP, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_Hcd, 0, sizeof(float) * 4 * std::max(nP, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_active, 0, std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_state, LDSO_B200_RES_OUTLIER, std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_energy, 0, sizeof(float) * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_energy, 0, sizeof(float) * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_energy_wo, 0, sizeof(float) * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_JpJdF, 0, sizeof(float) * 8 * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_JpJdF_new, 0, sizeof(float) * 8 * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * std::max(nR, 1), c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // host vectors above go out of scope
+    d.newest_offset = 0;
+    d.newest_total = -1;   // derived
+    c->have_window = true;
+    c->derived_dirty = true;
+    return LDSO_B200_OK;
+}
+
+// work items, newest-frame slots, partial buffers: need both the window and nF
+static int build_derived(ldso_b200_ctx *c) {
+    if (!c->have_window || !c->have_frames) return c->fail(LDSO_B200_ERR_STATE, "set_frames and set_window must both be called first");
+    if (!c->derived_dirty) return LDSO_B200_OK;
+    DevWindow &d = c->d;
+    const int nP = d.nP, nR = d.nR, nF = c->nF;
+    for (int p = 0; p < nP; p++) if (c->h_pt_host[p] >= nF) return c->fail(LDSO_B200_ERR_ARG, "pt_host >= nFrames");
+    for (int r = 0; r < nR; r++) if (c->h_res_target[r] >= nF) return c->fail(LDSO_B200_ERR_ARG, "res_target >= nFrames");
+    int ppi = (nP + c->sm_count - 1) / std::max(c->sm_count, 1);
+    ppi = std::max(8, std::min(64, ppi));
+    d.pts_per_item = ppi;
+    c->k1_smem = k1_smem_bytes(ppi);
+    std::vector<int4> items;
+    std::vector<int> hib(MAXF + 1, 0);
+    int p = 0;
+    for (int h = 0; h < MAXF; h++) {
+        hib[h] = (int) items.size();
+        while (p < nP && c->h_pt_host[p] == h) {
+            int e = p;
+            while (e < nP && c->h_pt_host[e] == h && e - p < ppi) e++;
+            items.push_back(make_int4(h, p, e, 0));
+            p = e;
+        }
+    }
+    hib[MAXF] = (int) items.size();
+    d.nItems = (int) items.size();
+    std::vector<int> slot(nR, -1);
+    int ns = 0;
+    for (int r = 0; r < nR; r++) if (c->h_res_target[r] == nF - 1) slot[r] = ns++;
+    const int local_newest = ns;
+    if (d.newest_total < 0 || !c->multi) { d.newest_total = local_newest; d.newest_offset = 0; }
+    for (int r = 0; r < nR; r++) if (slot[r] >= 0) slot[r] += d.newest_offset;
+
+    int4 *items_dev; int *hib_dev, *slot_dev;
+    int rc = 0;
+    rc |= dev_alloc(c, &items_dev, items.size()); rc |= dev_alloc(c, &hib_dev, MAXF + 1); rc |= dev_alloc(c, &slot_dev, nR);
+    rc |= dev_alloc(c, &d.partials, (size_t) std::max(d.nItems, 1) * PART_STRIDE);
+    rc |= dev_alloc(c, &d.item_stats, (size_t) std::max(d.nItems, 1) * 4);
+    rc |= dev_alloc(c, &d.red, (size_t) RED_SELECT + std::max(d.newest_total, 1) + 16);
+    if (rc) return LDSO_B200_ERR_CUDA;
+    rc |= dev_upload(c, items_dev, items.data(), items.size());
+    rc |= dev_upload(c, hib_dev, hib.data(), MAXF + 1);
+    rc |= dev_upload(c, slot_dev, slot.data(), nR);
+    if (rc) return LDSO_B200_ERR_CUDA;
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.red, 0, sizeof(double) * ((size_t) RED_SELECT + std::max(d.newest_total, 1) + 16), c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(d.partials, 0, sizeof(float) * (size_t) std::max(d.nItems, 1) * PART_STRIDE, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    d.items = items_dev; d.host_item_begin = hib_dev; d.res_newest_slot = slot_dev;
+    c->derived_dirty = false;
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- frames
+extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b200_frame_state *frames,
+                                    const double calib_value_scaled[4], const double calib_value_zero[4]) {
+    if (!c || !frames || !calib_value_scaled || !calib_value_zero) return LDSO_B200_ERR_ARG;
+    if (nFrames < 1 || nFrames > MAXF) return c->fail(LDSO_B200_ERR_ARG, "nFrames must be in [1, LDSO_B200_MAX_FRAMES]");
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    using namespace hostmath;
+    WinState &W = *c->ws_host;
+    memset(&W, 0, sizeof(W));
+    const int nF = nFrames, n = 8 * nF + CPARS;
+    W.nF = nF; W.n = n; W.w = c->w; W.h = c->h;
+    W.wM3G = (float) (c->w - 3); W.hM3G = (float) (c->h - 3);      // GlobalCalib.cc:42-43
+    W.S = c->S;
+    std::vector<Pose> ev(nF);
+    for (int i = 0; i < nF; i++) {
+        const ldso_b200_frame_state &f = frames[i];
+        if (f.image_slot < 0 || f.image_slot >= NSLOTS || !c->img[f.image_slot][0]) return c->fail(LDSO_B200_ERR_ARG, "frame image slot not uploaded");
+        FrameDev &D = W.fr[i];
+        memcpy(D.evalR, f.evalR, sizeof(D.evalR)); memcpy(D.evalT, f.evalT, sizeof(D.evalT));
+        memcpy(D.state, f.state, sizeof(D.state)); memcpy(D.state_zero, f.state_zero, sizeof(D.state_zero));
+        memcpy(D.state_backup, f.state, sizeof(D.state));
+        D.frameEnergyTH = f.frameEnergyTH; D.ab_exposure = f.ab_exposure; D.frame_id = f.frame_id; D.slot = f.image_slot;
+        // FrameHessian::getPrior (FrameHessian.h:125-150), takeData (FrameHessian.cc:108-112)
+        double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (f.frame_id == 0) {
+            p[0] = p[1] = p[2] = c->S.initialTransPrior;
+            p[3] = p[4] = p[5] = c->S.initialRotPrior;
+            p[6] = c->S.initialAffAPrior;
+            p[7] = c->S.initialAffBPrior;
+        } else {
+            p[6] = (c->S.affineOptModeA < 0) ? c->S.initialAffAPrior : c->S.affineOptModeA;
+            p[7] = (c->S.affineOptModeB < 0) ? c->S.initialAffBPrior : c->S.affineOptModeB;
+        }
+        for (int k = 0; k < 8; k++) D.prior[k] = p[k];
+        memcpy(ev[i].R, f.evalR, sizeof(ev[i].R)); memcpy(ev[i].t, f.evalT, sizeof(ev[i].t));
+        W.img0[i] = c->img[f.image_slot][0];
+        c->slots[i] = f.image_slot;
+    }
+    // calibration (CalibHessian::setValueScaled, CalibHessian.h:87-100)
+    CalibDev &C = W.calib;
+    for (int i = 0; i < 4; i++) { C.value_scaled[i] = calib_value_scaled[i]; C.value_zero[i] = calib_value_zero[i]; }
+    C.value[0] = (double) (1.0f / SCALE_F) * C.value_scaled[0]; C.value[1] = (double) (1.0f / SCALE_F) * C.value_scaled[1];
+    C.value[2] = (double) (1.0f / SCALE_C) * C.value_scaled[2]; C.value[3] = (double) (1.0f / SCALE_C) * C.value_scaled[3];
+    for (int i = 0; i < 4; i++) C.value_backup[i] = C.value[i];
+    C.fxl = (float) C.value_scaled[0]; C.fyl = (float) C.value_scaled[1]; C.cxl = (float) C.value_scaled[2]; C.cyl = (float) C.value_scaled[3];
+    C.fxli = 1.0f / C.fxl; C.fyli = 1.0f / C.fyl; C.cxli = -C.cxl / C.fxl; C.cyli = -C.cyl / C.fyl;
+    for (int i = 0; i < 4; i++) { C.cDeltaF[i] = (float) (C.value[i] - C.value_zero[i]); W.cPrior[i] = c->S.initialCalibHessian; }
+
+    // EnergyFunctional::setAdjointsF (EnergyFunctional.cc:431-489)
+    for (int h = 0; h < nF; h++)
+        for (int t = 0; t < nF; t++) {
+            Pose hostToTarget = mul(ev[t], inv(ev[h]));
+            double Adj[36];
+            adjoint(hostToTarget, Adj);
+            double *AH = W.adHost[h + nF * t], *AT = W.adTarget[h + nF * t];
+            for (int i = 0; i < 8; i++) AH[i * 8 + i] = AT[i * 8 + i] = 1.0;
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) AH[i * 8 + j] = -Adj[j * 6 + i];
+            float eF = frames[h].ab_exposure, eT = frames[t].ab_exposure;
+            if (eF == 0 || eT == 0) eT = eF = 1;
+            const float a0h = (float) (frames[h].state_zero[6] * SCALE_A), a0t = (float) (frames[t].state_zero[6] * SCALE_A);
+            const float affLL0 = expf(a0t - a0h) * eT / eF;
+            AT[6 * 8 + 6] = -affLL0; AH[6 * 8 + 6] = affLL0; AT[7 * 8 + 7] = -1; AH[7 * 8 + 7] = affLL0;
+            for (int j = 0; j < 8; j++) {
+                for (int i = 0; i < 3; i++) { AH[i * 8 + j] *= SCALE_XI_TRANS; AT[i * 8 + j] *= SCALE_XI_TRANS; }
+                for (int i = 3; i < 6; i++) { AH[i * 8 + j] *= SCALE_XI_ROT; AT[i * 8 + j] *= SCALE_XI_ROT; }
+                AH[6 * 8 + j] *= SCALE_A; AT[6 * 8 + j] *= SCALE_A;
+                AH[7 * 8 + j] *= SCALE_B; AT[7 * 8 + j] *= SCALE_B;
+            }
+            for (int i = 0; i < 64; i++) { W.adHostF[h + nF * t][i] = (float) AH[i]; W.adTargetF[h + nF * t][i] = (float) AT[i]; }
+        }
+
+    // null spaces (FrameHessian::setStateZero, FrameHessian.cc:11-42; FullSystem::getNullspaces, FullSystem.cc:1711-1760)
+    // and the projector EnergyFunctional::orthogonalize applies (pose + scale, EnergyFunctional.cc:687-716)
+    std::vector<double> N((size_t) n * 7, 0.0);
+    for (int f = 0; f < nF; f++) {
+        const Pose evI = inv(ev[f]);
+        for (int i = 0; i < 6; i++) {
+            double e[6] = {0, 0, 0, 0, 0, 0}, m[6] = {0, 0, 0, 0, 0, 0};
+            e[i] = 1e-3; m[i] = -1e-3;
+            double lp[6], lm[6];
+            logm(mul(mul(ev[f], expm(e)), evI), lp);
+            logm(mul(mul(ev[f], expm(m)), evI), lm);
+            for (int r = 0; r < 6; r++) {
+                double v = (lp[r] - lm[r]) / 2e-3;
+                v *= (r < 3) ? (double) (1.0f / SCALE_XI_TRANS) : (double) (1.0f / SCALE_XI_ROT);
+                N[(size_t) i * n + CPARS + 8 * f + r] = v;
+            }
+        }
+        Pose P = ev[f], M = ev[f];
+        for (int k = 0; k < 3; k++) { P.t[k] *= 1.00001; M.t[k] /= 1.00001; }
+        double lp[6], lm[6];
+        logm(mul(P, evI), lp);
+        logm(mul(M, evI), lm);
+        for (int r = 0; r < 6; r++) {
+            double v = (lp[r] - lm[r]) / 2e-3;
+            v *= (r < 3) ? (double) (1.0f / SCALE_XI_TRANS) : (double) (1.0f / SCALE_XI_ROT);
+            N[(size_t) 6 * n + CPARS + 8 * f + r] = v;
+        }
+    }
+    for (int j = 0; j < 7; j++) {   // N.col(i) = ns[i].normalized()
+        double s = 0;
+        for (int r = 0; r < n; r++) s += N[(size_t) j * n + r] * N[(size_t) j * n + r];
+        s = sqrt(s);
+        if (s > 0) for (int r = 0; r < n; r++) N[(size_t) j * n + r] /= s;
+    }
+    std::vector<double> P;
+    range_projector(N, n, 7, c->S.solverModeDelta, P);
+
+    c->nF = nF; c->n = n;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->ws_dev, c->ws_host, sizeof(WinState), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.Pns, P.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
+    k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    c->have_frames = true;
+    c->derived_dirty = true;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_set_marg_prior(ldso_b200_ctx *c, const double *HM, const double *bM) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const int n = c->n;
+    if (HM) CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.HM, HM, sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
+    if (bM) CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.bM, bM, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_get_marg_prior(ldso_b200_ctx *c, double *HM, double *bM) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const int n = c->n;
+    if (HM) CUDA_CHECK_RET(c, cudaMemcpyAsync(HM, c->sb.HM, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+    if (bM) CUDA_CHECK_RET(c, cudaMemcpyAsync(bM, c->sb.bM, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- launches
+static int launch_k1(ldso_b200_ctx *c, int flags, const uint8_t *sel = nullptr) {
+    if (c->d.nItems == 0) return LDSO_B200_OK;
+    k1_linearize_accumulate<<<c->d.nItems, K1_THREADS, c->k1_smem, c->stream>>>(c->d, c->ws_dev, flags, sel);
+    LAUNCH_CHECK(c);
+    return LDSO_B200_OK;
+}
+static int launch_k2a(ldso_b200_ctx *c, int full) {
+    const int nb = (MAXF * PART_USED + 255) / 256 + 1;
+    k2a_reduce<<<nb, 256, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
+    LAUNCH_CHECK(c);
+    return LDSO_B200_OK;
+}
+static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select) {
+    const int nb = c->nF * c->nF + c->nF + 2;
+    k2b_stitch<<<nb, K2B_THREADS, 0, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select);
+    LAUNCH_CHECK(c);
+    return LDSO_B200_OK;
+}
+static int launch_k3(ldso_b200_ctx *c, int flags) {
+    k3_solve_step<<<1, K3_THREADS, K3_SMEM_BYTES, c->stream>>>(c->ws_dev, c->sb, flags, c->iteration_dev);
+    LAUNCH_CHECK(c);
+    return LDSO_B200_OK;
+}
+static int set_iteration(ldso_b200_ctx *c, int it) {
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->iteration_dev, &it, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return LDSO_B200_OK;
+}
+static int clear_select(ldso_b200_ctx *c) {   // multi-GPU: slots owned by other ranks must be zero before the all-reduce
+    if (c->multi && c->d.newest_total > 0)
+        CUDA_CHECK_RET(c, cudaMemsetAsync(c->d.red + RED_SELECT, 0, sizeof(double) * c->d.newest_total, c->stream));
+    return LDSO_B200_OK;
+}
+#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+extern "C" int ldso_b200_linearize_all(ldso_b200_ctx *c, int fixLinearization, int flags, double *energy_out) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    (void) flags;   // the piecewise path always keeps the full Jacobian: solve_system rebuilds its records from it
+    int f = K1F_LINEARIZE | K1F_STORE_J;
+    if (fixLinearization) f |= K1F_APPLY_RES;
+    RET_IF(clear_select(c));
+    RET_IF(launch_k1(c, f));
+    RET_IF(launch_k2a(c, 0));
+    RET_IF(launch_k2b(c, 0, 1));
+    if (energy_out) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(energy_out, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_apply_res(ldso_b200_ctx *c) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    if (c->d.nR > 0) {
+        k_apply_res<<<(c->d.nR + 255) / 256, 256, 0, c->stream>>>(c->d);
+        LAUNCH_CHECK(c);
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_backup_state(ldso_b200_ctx *c) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(launch_k3(c, K3F_BACKUP));
+    if (c->d.nP > 0) {
+        k_points<<<(c->d.nP + 255) / 256, 256, 0, c->stream>>>(c->d, c->ws_dev, 1);
+        LAUNCH_CHECK(c);
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *lastHS, double *lastbS, double *lastX) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(launch_k1(c, K1F_ACCUMULATE));                 // mode 0 records from the stored Jacobians
+    RET_IF(launch_k2a(c, 1));
+    RET_IF(launch_k2b(c, 1, 0));
+    RET_IF(set_iteration(c, iteration));
+    RET_IF(launch_k3(c, K3F_SOLVE));
+    if (c->d.nP > 0) {
+        k_points<<<(c->d.nP + 255) / 256, 256, 0, c->stream>>>(c->d, c->ws_dev, 2);
+        LAUNCH_CHECK(c);
+    }
+    return ldso_b200_get_last_solution(c, lastHS, lastbS, lastX);
+}
+
+extern "C" int ldso_b200_get_last_solution(ldso_b200_ctx *c, double *lastHS, double *lastbS, double *lastX) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const int n = c->n;
+    if (lastHS) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastHS, c->sb.lastHS, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+    if (lastbS) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastbS, c->sb.lastbS, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (lastX) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastX, c->sb.lastX, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_get_system(ldso_b200_ctx *c, double *H_A, double *b_A, double *H_sc, double *b_sc, int *resInA) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const int n = c->n;
+    if (H_A) CUDA_CHECK_RET(c, cudaMemcpyAsync(H_A, c->sb.H_A, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+    if (b_A) CUDA_CHECK_RET(c, cudaMemcpyAsync(b_A, c->sb.b_A, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (H_sc) CUDA_CHECK_RET(c, cudaMemcpyAsync(H_sc, c->sb.H_sc, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+    if (b_sc) CUDA_CHECK_RET(c, cudaMemcpyAsync(b_sc, c->sb.b_sc, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (resInA) CUDA_CHECK_RET(c, cudaMemcpyAsync(resInA, &c->ws_dev->resInA, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_do_step(ldso_b200_ctx *c, int *canbreak) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    k_sum_nid<<<1, 256, 0, c->stream>>>(c->d, c->ws_dev);
+    LAUNCH_CHECK(c);
+    RET_IF(launch_k3(c, K3F_STEP));
+    if (c->d.nP > 0) {
+        k_points<<<(c->d.nP + 255) / 256, 256, 0, c->stream>>>(c->d, c->ws_dev, 4);
+        LAUNCH_CHECK(c);
+    }
+    if (canbreak) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(canbreak, &c->ws_dev->canbreak, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    }
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- fused loop
+static const int K1_FUSED = K1F_LINEARIZE | K1F_ACCUMULATE | K1F_APPLY_RES;
+
+extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(clear_select(c));
+    RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
+    RET_IF(launch_k2a(c, 1));
+    if (c->multi) return LDSO_B200_OK;     // caller all-reduces, then gn_phase_b
+    RET_IF(launch_k2b(c, 1, 1));
+    if (energy_out) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(energy_out, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, int n_iterations) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    if (c->multi) return c->fail(LDSO_B200_ERR_STATE, "sharded context: use gn_phase_a / all-reduce / gn_phase_b");
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(set_iteration(c, first_iteration));
+    for (int i = 0; i < n_iterations; i++) {
+        RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
+        RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
+        RET_IF(launch_k2a(c, 1));
+        RET_IF(launch_k2b(c, 1, 1));
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_reduce_buffer(ldso_b200_ctx *c, void **buf_dev, size_t *n_doubles) {
+    if (!c || !buf_dev || !n_doubles) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    *buf_dev = c->d.red;
+    *n_doubles = (size_t) RED_SELECT + std::max(c->d.newest_total, 0);
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_set_shard(ldso_b200_ctx *c, int newest_slot_offset, int newest_total) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    if (newest_slot_offset < 0 || newest_total < newest_slot_offset) return c->fail(LDSO_B200_ERR_ARG, "bad shard description");
+    c->multi = true;
+    c->d.newest_offset = newest_slot_offset;
+    c->d.newest_total = newest_total;
+    c->derived_dirty = true;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_gn_phase_a(ldso_b200_ctx *c, int iteration) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(clear_select(c));
+    if (iteration < 0) {
+        RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
+    } else {
+        RET_IF(set_iteration(c, iteration));
+        RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
+        RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
+    }
+    RET_IF(launch_k2a(c, 1));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_gn_phase_b(ldso_b200_ctx *c) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    RET_IF(launch_k2b(c, 1, 1));
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- read-back
+extern "C" int ldso_b200_get_energy(ldso_b200_ctx *c, double *energy, int *canbreak) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    if (energy) CUDA_CHECK_RET(c, cudaMemcpyAsync(energy, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (canbreak) CUDA_CHECK_RET(c, cudaMemcpyAsync(canbreak, &c->ws_dev->canbreak, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+#define D2H(dst, src, bytes) do { if (dst) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
+
+extern "C" int ldso_b200_get_points(ldso_b200_ctx *c, float *idepth, float *idepth_zero, float *step, float *HdiF,
+                                    float *bdSumF, float *Hdd, float *bd, float *Hcd4) {
+    if (!c || !c->have_window) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const size_t nP = c->d.nP;
+    D2H(idepth, c->d.pt_idepth, 4 * nP); D2H(idepth_zero, c->d.pt_idepth_zero, 4 * nP); D2H(step, c->d.pt_step, 4 * nP);
+    D2H(HdiF, c->d.pt_HdiF, 4 * nP); D2H(bdSumF, c->d.pt_bdSumF, 4 * nP); D2H(Hdd, c->d.pt_Hdd, 4 * nP); D2H(bd, c->d.pt_bd, 4 * nP);
+    D2H(Hcd4, c->d.pt_Hcd, 16 * nP);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_get_residuals(ldso_b200_ctx *c, uint8_t *state_state, uint8_t *state_NewState, float *state_energy,
+                                       float *state_NewEnergy, float *state_NewEnergyWithOutlier, uint8_t *isActive,
+                                       float *JpJdF8, float *J74, float *projectedTo16, float *centerProjectedTo3) {
+    if (!c || !c->have_window) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    const size_t nR = c->d.nR;
+    D2H(state_state, c->d.res_state, nR); D2H(state_NewState, c->d.res_new_state, nR); D2H(state_energy, c->d.res_energy, 4 * nR);
+    D2H(state_NewEnergy, c->d.res_new_energy, 4 * nR); D2H(state_NewEnergyWithOutlier, c->d.res_new_energy_wo, 4 * nR);
+    D2H(isActive, c->d.res_active, nR); D2H(JpJdF8, c->d.res_JpJdF, 32 * nR); D2H(J74, c->d.res_J, 296 * nR);
+    D2H(projectedTo16, c->d.res_proj, 64 * nR); D2H(centerProjectedTo3, c->d.res_cpt, 12 * nR);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *step10, float *frameEnergyTH, float *precalc40,
+                                    double *adHost64, double *adTarget64, float *adHTdeltaF8, double *calib_value4) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->ws_host, c->ws_dev, sizeof(WinState), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    const WinState &W = *c->ws_host;
+    const int nF = W.nF;
+    for (int h = 0; h < nF; h++) {
+        if (state10) memcpy(state10 + 10 * h, W.fr[h].state, 80);
+        if (step10) memcpy(step10 + 10 * h, W.fr[h].step, 80);
+        if (frameEnergyTH) frameEnergyTH[h] = W.fr[h].frameEnergyTH;
+    }
+    for (int q = 0; q < nF * nF; q++) {
+        if (precalc40) {
+            float *d = precalc40 + 40 * q;
+            const PairRec &p = W.pair[q];
+            const PairRecFull &f = W.pairFull[q];
+            memcpy(d, p.R0, 36); memcpy(d + 9, p.t0, 12); memcpy(d + 12, f.RTll, 36); memcpy(d + 21, f.tTll, 12);
+            memcpy(d + 24, p.KRKi, 36); memcpy(d + 33, p.Kt, 12);
+            d[36] = p.aff[0]; d[37] = p.aff[1]; d[38] = p.b0; d[39] = p.distanceLL;
+        }
+        if (adHost64) memcpy(adHost64 + 64 * q, W.adHost[q], 512);
+        if (adTarget64) memcpy(adTarget64 + 64 * q, W.adTarget[q], 512);
+        if (adHTdeltaF8) memcpy(adHTdeltaF8 + 8 * q, W.adHTdeltaF[q], 32);
+    }
+    if (calib_value4) memcpy(calib_value4, W.calib.value, 32);
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_get_nullspace_projector(ldso_b200_ctx *c, double *P) {
+    if (!c || !c->have_frames || !P) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(P, c->sb.Pns, sizeof(double) * c->n * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tracker
+extern "C" int ldso_b200_tracker_make_k(ldso_b200_ctx *c, float fx, float fy, float cx, float cy) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    // CoarseTracker::makeK (CoarseTracker.cc:219-246)
+    c->trk_fx[0] = fx; c->trk_fy[0] = fy; c->trk_cx[0] = cx; c->trk_cy[0] = cy;
+    for (int l = 1; l < c->levels; l++) {
+        c->trk_fx[l] = c->trk_fx[l - 1] * 0.5;
+        c->trk_fy[l] = c->trk_fy[l - 1] * 0.5;
+        c->trk_cx[l] = (c->trk_cx[0] + 0.5) / ((int) 1 << l) - 0.5;
+        c->trk_cy[l] = (c->trk_cy[0] + 0.5) / ((int) 1 << l) - 0.5;
+    }
+    for (int l = 0; l < c->levels; l++) {
+        const float K[9] = {c->trk_fx[l], 0, c->trk_cx[l], 0, c->trk_fy[l], c->trk_cy[l], 0, 0, 1};
+        m33f_inverse(K, c->trk_Ki[l]);
+    }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_tracker_set_ref_level(ldso_b200_ctx *c, int lvl, int n, const float *pc_u, const float *pc_v,
+                                               const float *pc_idepth, const float *pc_color) {
+    if (!c || lvl < 0 || lvl >= c->levels || n < 0) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (n > c->trk_cap[lvl]) {
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < 4; k++) {
+            if (c->trk_pc[lvl][k]) cudaFree(c->trk_pc[lvl][k]);
+            CUDA_CHECK_RET(c, cudaMalloc(&c->trk_pc[lvl][k], sizeof(float) * n));
+        }
+        c->trk_cap[lvl] = n;
+    }
+    const float *src[4] = {pc_u, pc_v, pc_idepth, pc_color};
+    for (int k = 0; k < 4; k++)
+        if (n > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(c->trk_pc[lvl][k], src[k], sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    c->trk[lvl].n = n;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_tracker_get_ref_level(ldso_b200_ctx *c, int lvl, int *n, float *pc_u, float *pc_v, float *pc_idepth, float *pc_color) {
+    if (!c || lvl < 0 || lvl >= c->levels) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int m = c->trk[lvl].n;
+    if (n) *n = m;
+    float *dst[4] = {pc_u, pc_v, pc_idepth, pc_color};
+    for (int k = 0; k < 4; k++) if (dst[k] && m > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst[k], c->trk_pc[lvl][k], sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_tracker_set_frames(ldso_b200_ctx *c, float ref_aff_a, float ref_aff_b, float ref_exposure, int new_slot, float new_exposure) {
+    if (!c || new_slot < 0 || new_slot >= NSLOTS || !c->img[new_slot][0]) return LDSO_B200_ERR_ARG;
+    c->ref_aff_a = ref_aff_a; c->ref_aff_b = ref_aff_b; c->ref_exposure = ref_exposure;
+    c->new_slot = new_slot; c->new_exposure = new_exposure;
+    return LDSO_B200_OK;
+}
+
+static void fill_level(ldso_b200_ctx *c, int l, TrkLevel &L) {
+    L.pc_u = c->trk_pc[l][0]; L.pc_v = c->trk_pc[l][1]; L.pc_idepth = c->trk_pc[l][2]; L.pc_color = c->trk_pc[l][3];
+    L.n = c->trk[l].n;
+    L.img = c->img[c->new_slot][l];
+    L.w = c->lw[l]; L.h = c->lh[l];
+    L.fx = c->trk_fx[l]; L.fy = c->trk_fy[l]; L.cx = c->trk_cx[l]; L.cy = c->trk_cy[l];
+    memcpy(L.Ki, c->trk_Ki[l], sizeof(L.Ki));
+}
+
+extern "C" int ldso_b200_tracker_eval(ldso_b200_ctx *c, int lvl, const double R[9], const double t[3], float aff_a, float aff_b,
+                                      float cutoffTH, double res6[6], double H[64], double b[8]) {
+    if (!c || lvl < 0 || lvl >= c->levels || !R || !t || !res6) return LDSO_B200_ERR_ARG;
+    if (c->new_slot < 0) return c->fail(LDSO_B200_ERR_STATE, "tracker_set_frames not called");
+    cudaSetDevice(c->device);
+    TrkLevel L;
+    fill_level(c, lvl, L);
+    TrkPose P;
+    float Rf[9];
+    for (int i = 0; i < 9; i++) Rf[i] = (float) R[i];
+    m33f_mul(Rf, L.Ki, P.RKi);
+    for (int i = 0; i < 3; i++) P.t[i] = (float) t[i];
+    float eF = c->ref_exposure, eT = c->new_exposure;
+    if (eF == 0 || eT == 0) eT = eF = 1;
+    const float a = expf(aff_a - c->ref_aff_a) * eT / eF;
+    P.affLL0 = a; P.affLL1 = aff_b - a * c->ref_aff_b; P.b0 = c->ref_aff_b;
+    P.cutoffTH = cutoffTH; P.huberTH = c->S.huberTH;
+    P.maxEnergy = 2 * c->S.huberTH * cutoffTH - c->S.huberTH * c->S.huberTH;
+    int grid = std::max(1, std::min(1024, (L.n + TRK_EVAL_THREADS - 1) / TRK_EVAL_THREADS));
+    k_trk_eval<<<grid, TRK_EVAL_THREADS, 0, c->stream>>>(L, P, lvl == 0 ? 1 : 0, c->trk_partials, c->trk_counter, c->trk_out_dev, (H && b) ? 1 : 0);
+    LAUNCH_CHECK(c);
+    double out[78];
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out, c->trk_out_dev, sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    memcpy(res6, out, 48);
+    if (H && b) { memcpy(H, out + 6, 512); memcpy(b, out + 70, 64); }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_tracker_track(ldso_b200_ctx *c, double R[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl,
+                                       const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3], int *ok) {
+    if (!c || !R || !t || !aff_a || !aff_b || !ok) return LDSO_B200_ERR_ARG;
+    if (coarsestLvl < 0 || coarsestLvl >= 5 || coarsestLvl >= c->levels) return c->fail(LDSO_B200_ERR_ARG, "coarsestLvl out of range");
+    if (c->new_slot < 0) return c->fail(LDSO_B200_ERR_STATE, "tracker_set_frames not called");
+    cudaSetDevice(c->device);
+    TrkTrackArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int l = 0; l < c->levels; l++) fill_level(c, l, A.L[l]);
+    A.nLevels = c->levels;
+    A.ref_aff_a = c->ref_aff_a; A.ref_aff_b = c->ref_aff_b; A.ref_exposure = c->ref_exposure; A.new_exposure = c->new_exposure;
+    A.huberTH = c->S.huberTH; A.coarseCutoffTH = c->S.coarseCutoffTH; A.affineOptModeA = c->S.affineOptModeA; A.affineOptModeB = c->S.affineOptModeB;
+    memcpy(A.R, R, 72); memcpy(A.t, t, 24);
+    A.aff_a = *aff_a; A.aff_b = *aff_b;
+    A.coarsestLvl = coarsestLvl;
+    for (int i = 0; i < 5; i++) A.minResForAbort[i] = minResForAbort ? minResForAbort[i] : NAN;
+    k_trk_track<<<1, TRK_TRACK_THREADS, 0, c->stream>>>(A, c->trk_track_out);
+    LAUNCH_CHECK(c);
+    TrkTrackOut o;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(&o, c->trk_track_out, sizeof(o), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    memcpy(R, o.R, 72); memcpy(t, o.t, 24);
+    *aff_a = o.aff_a; *aff_b = o.aff_b;
+    if (lastResiduals) memcpy(lastResiduals, o.lastResiduals, 40);
+    if (lastFlowIndicators) memcpy(lastFlowIndicators, o.lastFlowIndicators, 24);
+    *ok = o.ok;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_tracker_make_coarse_depth(ldso_b200_ctx *c, int ref_slot, int n, const float *centerProjectedTo3, const float *HdiF) {
+    (void) ref_slot; (void) n; (void) centerProjectedTo3; (void) HdiF;
+    if (!c) return LDSO_B200_ERR_ARG;
+    return c->fail(LDSO_B200_ERR_STATE, "tracker_make_coarse_depth: device makeCoarseDepthL0 not built yet (SURVEY §8f rank 1)");
+}

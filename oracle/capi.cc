@@ -1,0 +1,355 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// Flat extern "C" surface over the oracle so tests/ (ctypes), __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs can drive it. Nothing in ldso_b200/ may load this.
+#include "ba.h"
+#include "tracker.h"
+#include <chrono>
+
+using namespace oracle;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------- BA window
+void *oracle_ba_create(int w, int h, int threads_mode) { return new Window(w, h, threads_mode); }
+void oracle_ba_destroy(void *o) { delete (Window *) o; }
+
+void oracle_ba_set_calib(void *o, const double value_scaled[4]) {
+    Window *W = (Window *) o;
+    W->HCalib.setValueScaled(value_scaled);
+    for (int i = 0; i < 4; i++) W->HCalib.value_zero[i] = W->HCalib.value[i];  // CalibHessian ctor :29-31
+    W->HCalib.setValueScaled(value_scaled);
+}
+// shift the calibration state away from its linearisation point (value = value_zero + delta)
+void oracle_ba_set_calib_delta(void *o, const double delta[4]) {
+    Window *W = (Window *) o;
+    double v[4];
+    for (int i = 0; i < 4; i++) v[i] = W->HCalib.value_zero[i] + delta[i];
+    W->HCalib.setValue(v);
+}
+
+int oracle_ba_add_frame(void *o, const double R[9], const double t[3], const double state_zero[10],
+                        const double state[10], float ab_exposure, int frame_id, const float *dI) {
+    Window *W = (Window *) o;
+    Frame f;
+    f.w = W->wG0;
+    f.h = W->hG0;
+    f.dI = dI;
+    f.ab_exposure = ab_exposure;
+    f.id = frame_id;
+    f.frameID = (int) W->frames.size();
+    f.worldToCam_evalPT = SE3::fromRt(R, t);
+    // setEvalPT(worldToCam_evalPT, state_zero) then setState(state)  (FrameHessian.h:107-112)
+    f.setState(state_zero);
+    f.setStateZero(state_zero);
+    f.setState(state);
+    W->frames.push_back(f);
+    return (int) W->frames.size() - 1;
+}
+
+int oracle_ba_add_point(void *o, int host, float u, float v, float idepth_zero, float idepth, int hasDepthPrior,
+                        const float color[8], const float weights[8]) {
+    Window *W = (Window *) o;
+    Point p;
+    p.host = host;
+    p.u = u;
+    p.v = v;
+    p.hasDepthPrior = hasDepthPrior != 0;
+    p.setIdepthZero(idepth_zero);
+    p.setIdepth(idepth);
+    for (int i = 0; i < 8; i++) { p.color[i] = color[i]; p.weights[i] = weights[i]; }
+    // PointHessian::takeData (PointHessian.h:112-117)
+    p.priorF = p.hasDepthPrior ? W->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0;
+    p.deltaF = p.idepth - p.idepth_zero;
+    W->points.push_back(p);
+    return (int) W->points.size() - 1;
+}
+
+int oracle_ba_add_residual(void *o, int point, int target) {
+    Window *W = (Window *) o;
+    Residual r;
+    r.point = point;
+    r.host = W->points[point].host;
+    r.target = target;
+    r.resetOOB();
+    W->residuals.push_back(r);
+    W->points[point].residuals.push_back((int) W->residuals.size() - 1);
+    return (int) W->residuals.size() - 1;
+}
+
+void oracle_ba_set_frame_energy_th(void *o, int frame, float th) { ((Window *) o)->frames[frame].frameEnergyTH = th; }
+
+void oracle_ba_finalize(void *o) {
+    Window *W = (Window *) o;
+    W->insertFrames();
+    W->setPrecalcValues();
+}
+
+void oracle_ba_set_marg_prior(void *o, const double *HM_colmajor, const double *bM) {
+    Window *W = (Window *) o;
+    int n = 8 * W->nFrames + CPARS;
+    W->HM = MatX(n, n);
+    W->bM.assign(n, 0.0);
+    for (int i = 0; i < n * n; i++) W->HM.d[i] = HM_colmajor[i];
+    for (int i = 0; i < n; i++) W->bM[i] = bM[i];
+}
+
+double oracle_ba_optimize_begin(void *o) {
+    Window *W = (Window *) o;
+    W->optimizeBegin();
+    return W->lastEnergyP;
+}
+int oracle_ba_gn_iteration(void *o, int iteration) { return ((Window *) o)->gnIteration(iteration) ? 1 : 0; }
+
+// finer-grained steps
+double oracle_ba_linearize_all(void *o, int fix) { return ((Window *) o)->linearizeAll(fix != 0); }
+void oracle_ba_apply_res(void *o) { ((Window *) o)->applyResAll(); }
+void oracle_ba_solve_system(void *o, int iteration) {
+    Window *W = (Window *) o;
+    W->backupState();
+    W->getNullspaces();
+    W->solveSystemF(iteration, 1e-1);
+}
+int oracle_ba_do_step(void *o) { return ((Window *) o)->doStepFromBackup(1, 1, 1, 1, 1) ? 1 : 0; }
+double oracle_ba_last_energy(void *o) { return ((Window *) o)->lastEnergyP; }
+double oracle_ba_calc_m_energy(void *o) { return ((Window *) o)->calcMEnergyF(); }
+double oracle_ba_calc_l_energy(void *o) { return ((Window *) o)->calcLEnergyF_MT(); }
+
+// fixLinearizationF on every active residual of the listed points, then marginalizePointsF on them
+void oracle_ba_marginalize_points(void *o, int n, const int *pointIdx, float priorFac) {
+    Window *W = (Window *) o;
+    std::vector<int> idx(pointIdx, pointIdx + n);
+    for (int pi : idx) {
+        Point &p = W->points[pi];
+        for (int ri : p.residuals) {
+            Residual &r = W->residuals[ri];
+            r.resetOOB();
+            W->linearize(r);
+            r.isLinearized = false;
+            W->applyRes(r, true);
+            if (r.isActive()) W->fixLinearizationF(r);
+        }
+        p.priorF *= priorFac;
+    }
+    W->marginalizePointsF(idx);
+}
+
+int oracle_ba_dims(void *o, int *nFrames, int *nPoints, int *nResiduals) {
+    Window *W = (Window *) o;
+    *nFrames = (int) W->frames.size();
+    *nPoints = (int) W->points.size();
+    *nResiduals = (int) W->residuals.size();
+    return 0;
+}
+
+static void copy_mat(const MatX &M, double *out) { if (out && M.r > 0) memcpy(out, M.d.data(), sizeof(double) * M.d.size()); }
+static void copy_vec(const VecXd &v, double *out) { if (out && !v.empty()) memcpy(out, v.data(), sizeof(double) * v.size()); }
+
+// all matrices column-major (8nF+4)^2, vectors (8nF+4)
+void oracle_ba_get_system(void *o, double *HA, double *bA, double *Hsc, double *bsc, double *lastHS, double *lastbS,
+                          double *lastX, double *HL, double *bL) {
+    Window *W = (Window *) o;
+    copy_mat(W->last_HA, HA); copy_vec(W->last_bA, bA);
+    copy_mat(W->last_Hsc, Hsc); copy_vec(W->last_bsc, bsc);
+    copy_mat(W->lastHS, lastHS); copy_vec(W->lastbS, lastbS); copy_vec(W->lastX, lastX);
+    copy_mat(W->last_HL, HL); copy_vec(W->last_bL, bL);
+}
+void oracle_ba_get_marg_prior(void *o, double *HM, double *bM) {
+    Window *W = (Window *) o;
+    copy_mat(W->HM, HM);
+    copy_vec(W->bM, bM);
+}
+int oracle_ba_res_counts(void *o, int *resInA, int *resInL, int *resInM) {
+    Window *W = (Window *) o;
+    *resInA = W->resInA; *resInL = W->resInL; *resInM = W->resInM;
+    return 0;
+}
+
+void oracle_ba_get_points(void *o, float *idepth, float *idepth_zero, float *step, float *HdiF, float *bdSumF,
+                          float *Hdd_accAF, float *bd_accAF, float *Hcd_accAF /*4 per*/, float *deltaF) {
+    Window *W = (Window *) o;
+    for (size_t i = 0; i < W->points.size(); i++) {
+        const Point &p = W->points[i];
+        if (idepth) idepth[i] = p.idepth;
+        if (idepth_zero) idepth_zero[i] = p.idepth_zero;
+        if (step) step[i] = p.step;
+        if (HdiF) HdiF[i] = p.HdiF;
+        if (bdSumF) bdSumF[i] = p.bdSumF;
+        if (Hdd_accAF) Hdd_accAF[i] = p.Hdd_accAF;
+        if (bd_accAF) bd_accAF[i] = p.bd_accAF;
+        if (Hcd_accAF) for (int k = 0; k < 4; k++) Hcd_accAF[4 * i + k] = p.Hcd_accAF[k];
+        if (deltaF) deltaF[i] = p.deltaF;
+    }
+}
+
+// J layout per residual (74 floats): resF[8] Jpdxi[12] Jpdc[8] Jpdd[2] JIdx[16] JabF[16] JIdx2[4] JabJIdx[4] Jab2[4]
+void oracle_ba_get_residuals(void *o, int *state_state, int *state_NewState, double *state_energy,
+                             double *state_NewEnergy, double *state_NewEnergyWithOutlier, float *J74,
+                             float *JpJdF, float *projectedTo /*16*/, float *centerProjectedTo /*3*/,
+                             unsigned char *isActive, unsigned char *isLinearized, float *res_toZeroF) {
+    Window *W = (Window *) o;
+    for (size_t i = 0; i < W->residuals.size(); i++) {
+        const Residual &r = W->residuals[i];
+        if (state_state) state_state[i] = r.state_state;
+        if (state_NewState) state_NewState[i] = r.state_NewState;
+        if (state_energy) state_energy[i] = r.state_energy;
+        if (state_NewEnergy) state_NewEnergy[i] = r.state_NewEnergy;
+        if (state_NewEnergyWithOutlier) state_NewEnergyWithOutlier[i] = r.state_NewEnergyWithOutlier;
+        if (J74) {
+            float *d = J74 + 74 * i;
+            const RawResidualJacobian &J = r.J;
+            memcpy(d, J.resF, 32); d += 8;
+            memcpy(d, J.Jpdxi, 48); d += 12;
+            memcpy(d, J.Jpdc, 32); d += 8;
+            memcpy(d, J.Jpdd, 8); d += 2;
+            memcpy(d, J.JIdx, 64); d += 16;
+            memcpy(d, J.JabF, 64); d += 16;
+            memcpy(d, J.JIdx2, 16); d += 4;
+            memcpy(d, J.JabJIdx, 16); d += 4;
+            memcpy(d, J.Jab2, 16);
+        }
+        if (JpJdF) memcpy(JpJdF + 8 * i, r.JpJdF, 32);
+        if (projectedTo) memcpy(projectedTo + 16 * i, r.projectedTo, 64);
+        if (centerProjectedTo) memcpy(centerProjectedTo + 3 * i, r.centerProjectedTo, 12);
+        if (isActive) isActive[i] = r.isActiveAndIsGoodNEW ? 1 : 0;
+        if (isLinearized) isLinearized[i] = r.isLinearized ? 1 : 0;
+        if (res_toZeroF) memcpy(res_toZeroF + 8 * i, r.res_toZeroF, 32);
+    }
+}
+
+// per-frame: state[10], frameEnergyTH; per pair (h + nF*t): precalc 40 floats
+//   [RTll_0(9) tTll_0(3) RTll(9) tTll(3) KRKiTll(9) KtTll(3) aff(2) b0(1) distanceLL(1)],
+//   adHost/adTarget 64 doubles row-major, adHTdeltaF 8 floats
+void oracle_ba_get_frames(void *o, double *state, double *step, float *frameEnergyTH, float *precalc40, double *adHost,
+                          double *adTarget, float *adHTdeltaF, double *calib_value, double *prior8, double *delta_prior8,
+                          double *delta8) {
+    Window *W = (Window *) o;
+    int nF = (int) W->frames.size();
+    for (int h = 0; h < nF; h++) {
+        const Frame &f = W->frames[h];
+        if (state) memcpy(state + 10 * h, f.state, 80);
+        if (step) memcpy(step + 10 * h, f.step, 80);
+        if (frameEnergyTH) frameEnergyTH[h] = f.frameEnergyTH;
+        if (prior8) memcpy(prior8 + 8 * h, f.prior, 64);
+        if (delta_prior8) memcpy(delta_prior8 + 8 * h, f.delta_prior, 64);
+        if (delta8) memcpy(delta8 + 8 * h, f.delta, 64);
+        if (precalc40)
+            for (int t = 0; t < nF; t++) {
+                const FramePrecalc &pc = f.targetPrecalc[t];
+                float *d = precalc40 + 40 * (h + nF * t);
+                memcpy(d, pc.PRE_RTll_0, 36); d += 9;
+                memcpy(d, pc.PRE_tTll_0, 12); d += 3;
+                memcpy(d, pc.PRE_RTll, 36); d += 9;
+                memcpy(d, pc.PRE_tTll, 12); d += 3;
+                memcpy(d, pc.PRE_KRKiTll, 36); d += 9;
+                memcpy(d, pc.PRE_KtTll, 12); d += 3;
+                d[0] = pc.PRE_aff_mode[0]; d[1] = pc.PRE_aff_mode[1]; d[2] = pc.PRE_b0_mode; d[3] = pc.distanceLL;
+            }
+    }
+    if (adHost) memcpy(adHost, W->adHost.data(), sizeof(double) * W->adHost.size());
+    if (adTarget) memcpy(adTarget, W->adTarget.data(), sizeof(double) * W->adTarget.size());
+    if (adHTdeltaF) memcpy(adHTdeltaF, W->adHTdeltaF.data(), sizeof(float) * W->adHTdeltaF.size());
+    if (calib_value) memcpy(calib_value, W->HCalib.value, 32);
+}
+
+// nullspace projector NNpiTS (n x n col-major) that orthogonalize() applies: x -= P x
+void oracle_ba_get_nullspace_projector(void *o, double *P) {
+    Window *W = (Window *) o;
+    W->getNullspaces();
+    int n = 8 * W->nFrames + CPARS;
+    for (int c = 0; c < n; c++) {
+        VecXd e(n, 0.0);
+        e[c] = 1.0;
+        VecXd x = e;
+        W->orthogonalize(&x, 0);
+        for (int r = 0; r < n; r++) P[(size_t) c * n + r] = e[r] - x[r];
+    }
+}
+
+// time `iters` GN iterations (after `warmup`), returns seconds per iteration (median)
+double oracle_ba_time_gn(void *o, int iters, int warmup) {
+    Window *W = (Window *) o;
+    for (int i = 0; i < warmup; i++) W->gnIteration(3);
+    std::vector<double> ts;
+    for (int i = 0; i < iters; i++) {
+        auto t0 = std::chrono::steady_clock::now();
+        W->gnIteration(3);
+        auto t1 = std::chrono::steady_clock::now();
+        ts.push_back(std::chrono::duration<double>(t1 - t0).count());
+    }
+    std::sort(ts.begin(), ts.end());
+    return ts.empty() ? 0.0 : ts[ts.size() / 2];
+}
+
+// ---------------------------------------------------------------------------- misc primitives
+void oracle_make_images(const float *color, int w, int h, int levels, float **dIp) { makeImages(color, w, h, levels, dIp); }
+
+void oracle_se3_exp(const double a[6], double R[9], double t[3]) {
+    SE3 T = SE3::exp(a);
+    M3 m = T.rotationMatrix();
+    memcpy(R, m.m, 72);
+    for (int i = 0; i < 3; i++) t[i] = T.t[i];
+}
+void oracle_se3_log(const double R[9], const double t[3], double a[6]) { SE3::fromRt(R, t).log(a); }
+
+void oracle_ldlt_solve(int n, const double *A_colmajor, const double *b, double *x) {
+    MatX A(n, n);
+    memcpy(A.d.data(), A_colmajor, sizeof(double) * n * n);
+    VecXd bb(b, b + n);
+    VecXd xx = ldlt_solve(A, bb);
+    memcpy(x, xx.data(), sizeof(double) * n);
+}
+
+void oracle_sample33(const float *dI, int width, float x, float y, float out[3]) { getInterpolatedElement33(dI, x, y, width, out); }
+void oracle_sample33_bilin(const float *dI, int width, float x, float y, float out[3]) { getInterpolatedElement33BiLin(dI, x, y, width, out); }
+
+// ---------------------------------------------------------------------------- coarse tracker
+void *oracle_tracker_create(int w, int h, int levels) { return new CoarseTracker(w, h, levels); }
+void oracle_tracker_destroy(void *o) { delete (CoarseTracker *) o; }
+void oracle_tracker_make_k(void *o, float fx, float fy, float cx, float cy) { ((CoarseTracker *) o)->makeK(fx, fy, cx, cy); }
+void oracle_tracker_set_ref(void *o, const float **refDIp, float aff_a, float aff_b, float ab_exposure, int n,
+                            const float *cpt, const float *HdiF) {
+    CoarseTracker *T = (CoarseTracker *) o;
+    for (int l = 0; l < T->pyrLevelsUsed; l++) T->refDIp[l] = refDIp[l];
+    T->lastRef_aff_a = aff_a;
+    T->lastRef_aff_b = aff_b;
+    T->lastRef_ab_exposure = ab_exposure;
+    T->makeCoarseDepthL0(n, cpt, HdiF);
+}
+void oracle_tracker_set_new_frame(void *o, const float **newDIp, float ab_exposure) {
+    CoarseTracker *T = (CoarseTracker *) o;
+    for (int l = 0; l < T->pyrLevelsUsed; l++) T->newDIp[l] = newDIp[l];
+    T->newFrame_ab_exposure = ab_exposure;
+}
+int oracle_tracker_pc_n(void *o, int lvl) { return ((CoarseTracker *) o)->pc_n[lvl]; }
+void oracle_tracker_get_pc(void *o, int lvl, float *u, float *v, float *idepth, float *color) {
+    CoarseTracker *T = (CoarseTracker *) o;
+    int n = T->pc_n[lvl];
+    memcpy(u, T->pc_u[lvl].data(), 4 * n);
+    memcpy(v, T->pc_v[lvl].data(), 4 * n);
+    memcpy(idepth, T->pc_idepth[lvl].data(), 4 * n);
+    memcpy(color, T->pc_color[lvl].data(), 4 * n);
+}
+// one calcRes (+ calcGSSSE) evaluation; H row-major 8x8
+void oracle_tracker_eval(void *o, int lvl, const double R[9], const double t[3], float aff_a, float aff_b,
+                         float cutoffTH, double res6[6], double H[64], double b[8]) {
+    CoarseTracker *T = (CoarseTracker *) o;
+    SE3 P = SE3::fromRt(R, t);
+    T->calcRes(lvl, P, aff_a, aff_b, cutoffTH, res6);
+    if (H && b) T->calcGSSSE(lvl, H, b, P, aff_a, aff_b);
+}
+int oracle_tracker_track(void *o, double R[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl,
+                         const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3],
+                         int *n_evals) {
+    CoarseTracker *T = (CoarseTracker *) o;
+    SE3 P = SE3::fromRt(R, t);
+    bool ok = T->trackNewestCoarse(P, *aff_a, *aff_b, coarsestLvl, minResForAbort);
+    M3 m = P.rotationMatrix();
+    memcpy(R, m.m, 72);
+    for (int i = 0; i < 3; i++) t[i] = P.t[i];
+    memcpy(lastResiduals, T->lastResiduals, 40);
+    memcpy(lastFlowIndicators, T->lastFlowIndicators, 24);
+    if (n_evals) *n_evals = T->lm_iterations_total;
+    return ok ? 1 : 0;
+}
+
+}  // extern "C"

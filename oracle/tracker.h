@@ -1,0 +1,51 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// CPU restatement of the reference's coarse direct tracker:
+//   include/frontend/CoarseTracker.h:17-127, src/frontend/CoarseTracker.cc:61-246,258-632
+#pragma once
+#include "ba.h"
+
+namespace oracle {
+
+static const int PYR_LEVELS = 6;
+
+struct CoarseTracker {
+    Settings S;
+    int pyrLevelsUsed = 0;
+    int w[PYR_LEVELS], h[PYR_LEVELS];
+    float fx[PYR_LEVELS], fy[PYR_LEVELS], cx[PYR_LEVELS], cy[PYR_LEVELS];
+    float fxi[PYR_LEVELS], fyi[PYR_LEVELS], cxi[PYR_LEVELS], cyi[PYR_LEVELS];
+    float K[PYR_LEVELS][9], Ki[PYR_LEVELS][9];
+
+    // reference frame data
+    const float *refDIp[PYR_LEVELS];   // lastRef->dIp[lvl], AoS (I,dx,dy), not owned
+    float lastRef_aff_a = 0, lastRef_aff_b = 0;
+    float lastRef_ab_exposure = 1;
+    // new frame data
+    const float *newDIp[PYR_LEVELS];
+    float newFrame_ab_exposure = 1;
+
+    std::vector<float> idepth[PYR_LEVELS], weightSums[PYR_LEVELS], weightSums_bak[PYR_LEVELS];
+    std::vector<float> pc_u[PYR_LEVELS], pc_v[PYR_LEVELS], pc_idepth[PYR_LEVELS], pc_color[PYR_LEVELS];
+    int pc_n[PYR_LEVELS];
+
+    std::vector<float> buf_warped_idepth, buf_warped_u, buf_warped_v, buf_warped_dx, buf_warped_dy,
+            buf_warped_residual, buf_warped_weight, buf_warped_refColor;
+    int buf_warped_n = 0;
+    Accumulator9 acc;
+
+    double lastResiduals[5];
+    double lastFlowIndicators[3];
+    int lm_iterations_total = 0;  // diagnostic: number of calcRes evaluations in the last track
+
+    CoarseTracker(int ww, int hh, int levels);
+    void makeK(float fxl, float fyl, float cxl, float cyl);                         // CoarseTracker.cc:219-246
+    // makeCoarseDepthL0 (:258-438): contributions = (centerProjectedTo[0..2], HdiF) of every ACTIVE
+    // point whose newest residual targets lastRef and is IN.
+    void makeCoarseDepthL0(int n, const float *cpt /*n*3*/, const float *HdiF /*n*/);
+    void calcRes(int lvl, const SE3 &refToNew, float aff_a, float aff_b, float cutoffTH, double res[6]);  // :440-572
+    void calcGSSSE(int lvl, double H_out[64] /*row-major*/, double b_out[8], const SE3 &refToNew, float aff_a, float aff_b);  // :574-632
+    bool trackNewestCoarse(SE3 &lastToNew_out, float &aff_a_out, float &aff_b_out, int coarsestLvl,
+                           const double minResForAbort[5]);                          // :61-217
+};
+
+}  // namespace oracle

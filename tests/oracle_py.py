@@ -1,0 +1,257 @@
+"""ctypes driver for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package (ldso_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+_libs = {}
+
+c_fp = C.POINTER(C.c_float)
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_bp = C.POINTER(C.c_ubyte)
+
+
+def build(force=False):
+    need = force or not all(os.path.exists(os.path.join(ORACLE_DIR, n)) for n in ("liboracle.so", "liboracle_fast.so"))
+    if not need:
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cc", ".h"))]
+        newest = max(os.path.getmtime(s) for s in srcs)
+        need = newest > os.path.getmtime(os.path.join(ORACLE_DIR, "liboracle.so"))
+    if need:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+def lib(fast=False):
+    key = "fast" if fast else "ieee"
+    if key not in _libs:
+        build()
+        L = C.CDLL(os.path.join(ORACLE_DIR, "liboracle_fast.so" if fast else "liboracle.so"))
+        L.oracle_ba_create.restype = C.c_void_p
+        L.oracle_ba_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.oracle_ba_destroy.argtypes = [C.c_void_p]
+        L.oracle_ba_optimize_begin.restype = C.c_double
+        L.oracle_ba_linearize_all.restype = C.c_double
+        L.oracle_ba_last_energy.restype = C.c_double
+        L.oracle_ba_calc_m_energy.restype = C.c_double
+        L.oracle_ba_calc_l_energy.restype = C.c_double
+        L.oracle_ba_time_gn.restype = C.c_double
+        L.oracle_tracker_create.restype = C.c_void_p
+        _libs[key] = L
+    return _libs[key]
+
+
+def _f(a):
+    return a.ctypes.data_as(c_fp)
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+class OracleBA:
+    """One oracle window built from a ldso_b200.synth.Window."""
+
+    def __init__(self, win, threads_mode=0, fast=False, calib_delta=None):
+        self.L = lib(fast)
+        self.win = win
+        self.o = C.c_void_p(self.L.oracle_ba_create(win.w, win.h, threads_mode))
+        self._keep = []
+        K = np.ascontiguousarray(win.K, np.float64)
+        self.L.oracle_ba_set_calib(self.o, _d(K))
+        if calib_delta is not None:
+            cd = np.ascontiguousarray(calib_delta, np.float64)
+            self.L.oracle_ba_set_calib_delta(self.o, _d(cd))
+        for i in range(win.nF):
+            dI = np.ascontiguousarray(win.pyramids[i][0], np.float32)
+            self._keep.append(dI)
+            R = np.ascontiguousarray(win.Rcw[i], np.float64)
+            t = np.ascontiguousarray(win.tcw[i], np.float64)
+            sz = np.ascontiguousarray(win.state_zero[i], np.float64)
+            st = np.ascontiguousarray(win.state[i], np.float64)
+            self.L.oracle_ba_add_frame(self.o, _d(R), _d(t), _d(sz), _d(st), C.c_float(float(win.ab_exposure[i])),
+                                       int(win.frame_id[i]), _f(dI))
+        col = np.ascontiguousarray(win.pt_color, np.float32)
+        wts = np.ascontiguousarray(win.pt_weights, np.float32)
+        for p in range(win.nP):
+            self.L.oracle_ba_add_point(self.o, int(win.pt_host[p]), C.c_float(float(win.pt_u[p])), C.c_float(float(win.pt_v[p])),
+                                       C.c_float(float(win.pt_idepth_zero[p])), C.c_float(float(win.pt_idepth[p])),
+                                       int(win.pt_has_prior[p]), _f(col[p]), _f(wts[p]))
+        rp = win.res_point
+        for r in range(win.nR):
+            self.L.oracle_ba_add_residual(self.o, int(rp[r]), int(win.res_target[r]))
+        self.L.oracle_ba_finalize(self.o)
+        self.n = 8 * win.nF + 4
+
+    def __del__(self):
+        try:
+            self.L.oracle_ba_destroy(self.o)
+        except Exception:
+            pass
+
+    def set_marg_prior(self, HM, bM):
+        HMc = np.asfortranarray(HM, np.float64)
+        bMc = np.ascontiguousarray(bM, np.float64)
+        self.L.oracle_ba_set_marg_prior(self.o, HMc.ctypes.data_as(c_dp), _d(bMc))
+
+    def optimize_begin(self):
+        return self.L.oracle_ba_optimize_begin(self.o)
+
+    def gn_iteration(self, it):
+        return bool(self.L.oracle_ba_gn_iteration(self.o, it))
+
+    def linearize_all(self, fix=False):
+        return self.L.oracle_ba_linearize_all(self.o, int(fix))
+
+    def apply_res(self):
+        self.L.oracle_ba_apply_res(self.o)
+
+    def solve_system(self, it):
+        self.L.oracle_ba_solve_system(self.o, it)
+
+    def do_step(self):
+        return bool(self.L.oracle_ba_do_step(self.o))
+
+    def time_gn(self, iters, warmup):
+        return self.L.oracle_ba_time_gn(self.o, iters, warmup)
+
+    def system(self):
+        n = self.n
+        mats = {k: np.zeros((n, n), np.float64, order="F") for k in ("HA", "Hsc", "lastHS", "HL")}
+        vecs = {k: np.zeros(n, np.float64) for k in ("bA", "bsc", "lastbS", "lastX", "bL")}
+        self.L.oracle_ba_get_system(self.o, _d(mats["HA"]), _d(vecs["bA"]), _d(mats["Hsc"]), _d(vecs["bsc"]),
+                                    _d(mats["lastHS"]), _d(vecs["lastbS"]), _d(vecs["lastX"]), _d(mats["HL"]), _d(vecs["bL"]))
+        out = dict(mats)
+        out.update(vecs)
+        return out
+
+    def marg_prior(self):
+        n = self.n
+        HM = np.zeros((n, n), np.float64, order="F")
+        bM = np.zeros(n, np.float64)
+        self.L.oracle_ba_get_marg_prior(self.o, _d(HM), _d(bM))
+        return HM, bM
+
+    def res_counts(self):
+        a, l, m = C.c_int(), C.c_int(), C.c_int()
+        self.L.oracle_ba_res_counts(self.o, C.byref(a), C.byref(l), C.byref(m))
+        return a.value, l.value, m.value
+
+    def points(self):
+        nP = self.win.nP
+        keys = ("idepth", "idepth_zero", "step", "HdiF", "bdSumF", "Hdd_accAF", "bd_accAF")
+        out = {k: np.zeros(nP, np.float32) for k in keys}
+        out["Hcd_accAF"] = np.zeros((nP, 4), np.float32)
+        out["deltaF"] = np.zeros(nP, np.float32)
+        self.L.oracle_ba_get_points(self.o, *[_f(out[k]) for k in keys], _f(out["Hcd_accAF"]), _f(out["deltaF"]))
+        return out
+
+    def residuals(self):
+        nR = self.win.nR
+        out = dict(
+            state_state=np.zeros(nR, np.int32), state_NewState=np.zeros(nR, np.int32),
+            state_energy=np.zeros(nR, np.float64), state_NewEnergy=np.zeros(nR, np.float64),
+            state_NewEnergyWithOutlier=np.zeros(nR, np.float64), J=np.zeros((nR, 74), np.float32),
+            JpJdF=np.zeros((nR, 8), np.float32), projectedTo=np.zeros((nR, 8, 2), np.float32),
+            centerProjectedTo=np.zeros((nR, 3), np.float32), isActive=np.zeros(nR, np.uint8),
+            isLinearized=np.zeros(nR, np.uint8), res_toZeroF=np.zeros((nR, 8), np.float32))
+        self.L.oracle_ba_get_residuals(
+            self.o, out["state_state"].ctypes.data_as(c_ip), out["state_NewState"].ctypes.data_as(c_ip),
+            _d(out["state_energy"]), _d(out["state_NewEnergy"]), _d(out["state_NewEnergyWithOutlier"]), _f(out["J"]),
+            _f(out["JpJdF"]), _f(out["projectedTo"]), _f(out["centerProjectedTo"]),
+            out["isActive"].ctypes.data_as(c_bp), out["isLinearized"].ctypes.data_as(c_bp), _f(out["res_toZeroF"]))
+        return out
+
+    def frames(self):
+        nF = self.win.nF
+        out = dict(state=np.zeros((nF, 10)), step=np.zeros((nF, 10)), frameEnergyTH=np.zeros(nF, np.float32),
+                   precalc=np.zeros((nF * nF, 40), np.float32), adHost=np.zeros((nF * nF, 8, 8)),
+                   adTarget=np.zeros((nF * nF, 8, 8)), adHTdeltaF=np.zeros((nF * nF, 8), np.float32),
+                   calib_value=np.zeros(4), prior=np.zeros((nF, 8)), delta_prior=np.zeros((nF, 8)), delta=np.zeros((nF, 8)))
+        self.L.oracle_ba_get_frames(self.o, _d(out["state"]), _d(out["step"]), _f(out["frameEnergyTH"]), _f(out["precalc"]),
+                                    _d(out["adHost"]), _d(out["adTarget"]), _f(out["adHTdeltaF"]), _d(out["calib_value"]),
+                                    _d(out["prior"]), _d(out["delta_prior"]), _d(out["delta"]))
+        return out
+
+    def nullspace_projector(self):
+        n = self.n
+        P = np.zeros((n, n), np.float64, order="F")
+        self.L.oracle_ba_get_nullspace_projector(self.o, _d(P))
+        return P
+
+    def marginalize_points(self, idx, prior_fac=600.0 * 600.0):
+        idx = np.ascontiguousarray(idx, np.int32)
+        self.L.oracle_ba_marginalize_points(self.o, len(idx), idx.ctypes.data_as(c_ip), C.c_float(prior_fac))
+
+
+def make_images(color, levels, fast=False):
+    L = lib(fast)
+    h, w = color.shape
+    color = np.ascontiguousarray(color, np.float32)
+    outs = [np.zeros(((h >> l), (w >> l), 3), np.float32) for l in range(levels)]
+    arr = (c_fp * levels)(*[_f(o) for o in outs])
+    L.oracle_make_images(_f(color), w, h, levels, arr)
+    return outs
+
+
+class OracleTracker:
+    def __init__(self, pair, fast=False):
+        self.L = lib(fast)
+        self.pair = pair
+        self.levels = pair.levels
+        self.o = C.c_void_p(self.L.oracle_tracker_create(pair.w, pair.h, pair.levels))
+        K = pair.K
+        self.L.oracle_tracker_make_k(self.o, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]))
+        self._ref = [np.ascontiguousarray(p, np.float32) for p in pair.ref_pyr]
+        self._new = [np.ascontiguousarray(p, np.float32) for p in pair.new_pyr]
+        ref_arr = (c_fp * self.levels)(*[_f(p) for p in self._ref])
+        new_arr = (c_fp * self.levels)(*[_f(p) for p in self._new])
+        cpt = np.ascontiguousarray(pair.cpt, np.float32)
+        hd = np.ascontiguousarray(pair.HdiF, np.float32)
+        self.L.oracle_tracker_set_ref(self.o, ref_arr, C.c_float(pair.ref_aff[0]), C.c_float(pair.ref_aff[1]),
+                                      C.c_float(1.0), len(hd), _f(cpt), _f(hd))
+        self.L.oracle_tracker_set_new_frame(self.o, new_arr, C.c_float(1.0))
+
+    def __del__(self):
+        try:
+            self.L.oracle_tracker_destroy(self.o)
+        except Exception:
+            pass
+
+    def pc(self, lvl):
+        n = self.L.oracle_tracker_pc_n(self.o, lvl)
+        a = [np.zeros(n, np.float32) for _ in range(4)]
+        self.L.oracle_tracker_get_pc(self.o, lvl, *[_f(x) for x in a])
+        return a
+
+    def eval(self, lvl, R, t, aff_a, aff_b, cutoff, with_H=True):
+        R = np.ascontiguousarray(R, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        res = np.zeros(6)
+        H = np.zeros((8, 8))
+        b = np.zeros(8)
+        self.L.oracle_tracker_eval(self.o, lvl, _d(R), _d(t), C.c_float(aff_a), C.c_float(aff_b), C.c_float(cutoff),
+                                   _d(res), _d(H) if with_H else None, _d(b) if with_H else None)
+        return res, H, b
+
+    def track(self, R, t, aff_a, aff_b, coarsest, min_res=None):
+        R = np.array(R, np.float64, order="C")
+        t = np.array(t, np.float64)
+        a = C.c_float(aff_a)
+        b = C.c_float(aff_b)
+        mr = np.full(5, np.nan) if min_res is None else np.ascontiguousarray(min_res, np.float64)
+        lr = np.zeros(5)
+        lf = np.zeros(3)
+        ne = C.c_int()
+        ok = self.L.oracle_tracker_track(self.o, _d(R), _d(t), C.byref(a), C.byref(b), coarsest, _d(mr), _d(lr), _d(lf),
+                                         C.byref(ne))
+        return bool(ok), R, t, a.value, b.value, lr, lf, ne.value
