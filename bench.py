@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — GN-iterations/sec of the photometric BA hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA arm (N=1: 8 KF x 2000 active points)
+    torchrun ... bench.py --gpus N ...                        # points sharded over N ranks, one NCCL all-reduce/step
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one Gauss-Newton iteration (FullSystem.cc:777-831 restricted to the path): accumulate + Schur +
+stitch + 68x68 solve + resubstitute + state step + 64 frame-pair precalcs + linearize all residuals + applyRes.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GN-iters/sec, 8-KF x 2k-point window; Hessian rel-err vs SSE ref"
+PTS_PER_FRAME = 250       # per GPU: 8 KF x 250 = 2000 active points (BASELINE.json configs[1])
+NF = 8
+
+
+def algorithmic_bytes(n_res, n_pts, nF):
+    """bytes the reference's algorithm must touch once per GN iteration."""
+    n = 8 * nF + 4
+    return n_res * (384 + 12 + 12) + n_pts * (80 + 8 + 4) + nF * nF * 1164 + 4 * (n * n + n) * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path. LDSO cannot be compiled here (Eigen/glog/OpenCV/Pangolin
+    absent), so this arm times the oracle port (oracle/liboracle_fast.so, g++ -O3 -march=native like the reference's
+    Release build) with the reference's hard-wired 6 worker threads (NUM_THREADS, include/Settings.h:9)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ldso_b200 import synth
+    from tests import oracle_py
+    win = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME, seed=42)
+    o = oracle_py.OracleBA(win, threads_mode=6, fast=True)
+    o.optimize_begin()
+    for i in range(args.warmup):
+        o.gn_iteration(min(i, 3))
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o.gn_iteration(3)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GN-iters/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "8 KF x 2000 active points (14000 residuals), 640x480, seed 42", "nF": NF, "n_points": win.nP,
+                   "n_residuals": win.nR},
+        "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": "port",
+                         "sample": f"{args.steps} full GN iterations of the same window; oracle port, 6 worker threads "
+                                   f"(reference NUM_THREADS) on a {cores}-core host"},
+        "e2e": {"value": v, "unit": "GN-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+class _DevBuf:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_ours(args):
+    import torch
+    from ldso_b200 import capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: ldso_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    # weak scaling: 2000 points per GPU; the global window has 2000*N points, sharded by contiguous point blocks
+    full = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME * world, seed=42)
+    win = synth.shard_window(full, rank, world) if world > 1 else full
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(win.w, win.h, win.levels, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_synth_window(win)
+    red_t = None
+    if world > 1:
+        newest = full.nF - 1
+        counts = []
+        for r in range(world):
+            w_r = synth.shard_window(full, r, world)
+            counts.append(int(np.sum(w_r.res_target == newest)))
+        ctx.set_shard(int(np.sum(counts[:rank])), int(np.sum(counts)))
+        ptr, n = ctx.reduce_buffer()
+        red_t = torch.as_tensor(_DevBuf(ptr, n), device=f"cuda:{local_rank}")
+
+    def prologue():
+        if world > 1:
+            ctx.gn_phase_a(-1)
+            dist.all_reduce(red_t)
+            ctx.gn_phase_b()
+        else:
+            ctx.optimize_begin()
+
+    def gn_step(it):
+        if world > 1:
+            ctx.gn_phase_a(it)
+            dist.all_reduce(red_t)
+            ctx.gn_phase_b()
+        else:
+            ctx.gn_iterations(it, 1)
+
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    prologue()
+    for i in range(max(args.warmup, 3)):
+        gn_step(min(i, 3))
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+
+    # ---- timed region: K iterations, each bracketed by CUDA events on the launching stream, L2 flushed between
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(stream)
+        gn_step(3)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - launches0
+    t_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    clocks = sampler.stop()
+
+    # ---- same loop without the flush (images L2-resident, as inside a real optimize() call) — reported as extra
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        gn_step(3)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_warm_ms = e0.elapsed_time(e1)
+
+    # ---- end-to-end through the C ABI with host buffers (single GPU arm only): every step uploads the newest
+    # keyframe's raw image (device-side makeImages), the frame states and the whole window from host memory, runs
+    # one GN iteration and reads the solution, energy, point idepths/steps and residual states back.
+    e2e = None
+    if world == 1:
+        e2e = run_e2e(ctx, win, args, torch)
+
+    # max over ranks
+    if dist is not None:
+        tt = torch.tensor([t_ms, t_warm_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms, t_warm_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    n_res_rank, n_pts_rank = win.nR, win.nP
+    its_per_s = args.steps / (t_ms * 1e-3)
+    hbm_peak, peak_src = peaks()
+    b_iter = algorithmic_bytes(n_res_rank, n_pts_rank, NF)   # per GPU (each rank streams its own shard)
+    achieved = b_iter / (t_ms * 1e-3 / args.steps) / 1e9
+    line = {
+        "metric": METRIC, "value": its_per_s, "unit": "GN-iters/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"8 KF x {PTS_PER_FRAME * NF} active points per GPU ({full.nP} points, {full.nR} residuals in the window), 640x480, seed 42",
+                   "nF": NF, "n_points": full.nP, "n_residuals": full.nR, "points_per_gpu": n_pts_rank,
+                   "parallelism": f"points sharded x{world}, 1 NCCL all-reduce/step" if world > 1 else "single GPU",
+                   "l2": "192 MB flush buffer written between timed iterations (inputs 45 MB < 126 MB L2)",
+                   "timing": "per-iteration CUDA events on the launching stream, summed; max over ranks"},
+        "value_l2_warm": args.steps / (t_warm_ms * 1e-3),
+        "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": b_iter,
+                     "note": "whole GN iteration (4 kernels); the path is launch/latency-bound at 2k points, see DESIGN.md"},
+        "clocks": clocks,
+        "gpu_launches": launches,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(win)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(ctx, win, args, torch):
+    nF = win.nF
+    color = np.ascontiguousarray(win.pyramids[nF - 1][0][:, :, 0])
+    pin_color = torch.from_numpy(color).pin_memory().numpy()
+    steps = min(args.steps, 50)
+    h2d = pin_color.nbytes + nF * (9 + 3 + 10 + 10) * 8 + 8 * 8 + win.nP * (4 * 5 + 1 + 64) + (win.nP + 1) * 4 + win.nR * 4
+    n = 8 * nF + 4
+    d2h = (n + 1) * 8 + win.nP * 8 + win.nR * 2
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ctx.make_images(nF - 1, pin_color)
+        ctx.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(nF)), win.K)
+        ctx.set_window(win.pt_host, win.pt_u, win.pt_v, win.pt_idepth, win.pt_idepth_zero, win.pt_has_prior, win.pt_color,
+                       win.pt_weights, win.res_begin, win.res_target)
+        ctx.optimize_begin()
+        ctx.gn_iterations(0, 1)
+        ctx.last_solution()
+        ctx.points()
+        ctx.residuals(with_J=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": "GN-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "def": "per step: H2D newest keyframe raw image (+device makeImages), frame states, full window; "
+                   "optimize prologue + 1 GN iteration; D2H lastHS/lastbS/lastX, point arrays, residual states; wall clock"}
+
+
+def cpu_baseline(win):
+    from tests import oracle_py
+    o = oracle_py.OracleBA(win, threads_mode=6, fast=True)
+    o.optimize_begin()
+    for i in range(3):
+        o.gn_iteration(i)
+    sec = o.time_gn(40, 3)
+    return {"value": 1.0 / sec, "unit": "GN-iters/s", "cores": 6, "kind": "port",
+            "sample": f"median of 40 full GN iterations of the same 8 KF x 2000 point window; oracle port "
+                      f"(g++ -O3 -march=native), 6 worker threads = reference NUM_THREADS, host has {os.cpu_count()} cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry point launches sm_100a kernels or fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "img_kernels.cuh"
 #include "ba_k1.cuh"
 #include "ba_k2.cuh"
+#include "ba_k3.cuh"
 #include "tracker_kernels.cuh"
 
 static_assert(K1_THREADS / 32 == MAXF, "phase B maps one warp to one target frame");
@@ -61,6 +63,35 @@ struct ldso_b200_ctx {
     unsigned *trk_counter = nullptr;
     double *trk_out_dev = nullptr;
     TrkTrackOut *trk_track_out = nullptr;
+
+    // optional per-kernel CUDA-event timing of the GN loop (env LDSO_B200_KTIME=1), printed at destroy
+    bool ktime = false;
+    struct KT { const char *name; cudaEvent_t a, b; };
+    std::vector<KT> kt;
+    void kt_begin(const char *name) {
+        if (!ktime) return;
+        KT k; k.name = name;
+        cudaEventCreate(&k.a); cudaEventCreate(&k.b);
+        cudaEventRecord(k.a, stream);
+        kt.push_back(k);
+    }
+    void kt_end() { if (ktime) cudaEventRecord(kt.back().b, stream); }
+    void kt_report() {
+        if (!ktime || kt.empty()) return;
+        cudaStreamSynchronize(stream);
+        std::vector<std::string> names; std::vector<double> tot; std::vector<int> cnt;
+        for (auto &k : kt) {
+            float ms = 0; cudaEventElapsedTime(&ms, k.a, k.b);
+            size_t i = 0;
+            for (; i < names.size(); i++) if (names[i] == k.name) break;
+            if (i == names.size()) { names.push_back(k.name); tot.push_back(0); cnt.push_back(0); }
+            tot[i] += ms; cnt[i]++;
+            cudaEventDestroy(k.a); cudaEventDestroy(k.b);
+        }
+        for (size_t i = 0; i < names.size(); i++)
+            fprintf(stderr, "[ldso_b200 ktime] %-12s n=%6d avg=%8.2f us\n", names[i].c_str(), cnt[i], 1e3 * tot[i] / cnt[i]);
+        kt.clear();
+    }
 
     int fail(int code, const char *msg) { err = msg; return code; }
     int fail_cuda(cudaError_t e, const char *call, const char *file, int line) {
@@ -135,8 +166,10 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     c->sb.H_A = p; p += nn; c->sb.H_sc = p; p += nn; c->sb.HM = p; p += nn; c->sb.Pns = p; p += nn; c->sb.lastHS = p; p += nn;
     p += 2 * nn;   // spare
     c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
+    c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
     cudaFuncSetAttribute(k1_linearize_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem_bytes(64));
     cudaFuncSetAttribute(k3_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K3_SMEM_BYTES);
+    cudaFuncSetAttribute(k2b_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K2B_SMEM_BYTES);
     return c;
 }
 
@@ -150,6 +183,7 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    c->kt_report();
     free_window(c);
     for (int s = 0; s < NSLOTS; s++) for (int l = 0; l < MAXLVL; l++) if (c->img[s][l]) cudaFree(c->img[s][l]);
     for (int l = 0; l < MAXLVL; l++) for (int k = 0; k < 4; k++) if (c->trk_pc[l][k]) cudaFree(c->trk_pc[l][k]);
@@ -280,33 +314,45 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (nP > 0 && (win->res_begin[0] != 0 || win->res_begin[nP] != nR)) return c->fail(LDSO_B200_ERR_ARG, "res_begin does not cover the residual arrays");
     for (int r = 0; r < nR; r++) if (win->res_target[r] < 0 || win->res_target[r] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "res_target out of range");
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
-    free_window(c);
     DevWindow &d = c->d;
-    memset(&d, 0, sizeof(d));
-    d.nP = nP; d.nR = nR;
-    c->h_pt_host.assign(win->pt_host, win->pt_host + nP);
-    c->h_res_begin.assign(win->res_begin, win->res_begin + nP + 1);
-    if (nP == 0) c->h_res_begin.assign(1, 0);
-    c->h_res_target.assign(win->res_target, win->res_target + nR);
-
+    // same topology as the resident window (same hosts / CSR / targets): keep every allocation and the derived
+    // work-item tables, only the point values and residual states are refreshed below.
+    const bool same_topology = c->have_window && d.nP == nP && d.nR == nR && (int) c->h_pt_host.size() == nP && nP > 0 &&
+                               std::equal(win->pt_host, win->pt_host + nP, c->h_pt_host.begin()) &&
+                               std::equal(win->res_begin, win->res_begin + nP + 1, c->h_res_begin.begin()) &&
+                               std::equal(win->res_target, win->res_target + nR, c->h_res_target.begin());
     int *pt_host, *pt_res_begin, *res_point, *res_target;
     int rc = 0;
-    rc |= dev_alloc(c, &pt_host, nP); rc |= dev_alloc(c, &pt_res_begin, nP + 1);
-    rc |= dev_alloc(c, &res_point, nR); rc |= dev_alloc(c, &res_target, nR);
-    rc |= dev_alloc(c, &d.pt_u, nP); rc |= dev_alloc(c, &d.pt_v, nP); rc |= dev_alloc(c, &d.pt_idepth, nP);
-    rc |= dev_alloc(c, &d.pt_idepth_zero, nP); rc |= dev_alloc(c, &d.pt_idepth_backup, nP); rc |= dev_alloc(c, &d.pt_step, nP);
-    rc |= dev_alloc(c, &d.pt_color, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_weights, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_priorF, nP);
-    rc |= dev_alloc(c, &d.pt_HdiF, nP); rc |= dev_alloc(c, &d.pt_bdSumF, nP); rc |= dev_alloc(c, &d.pt_Hcd, (size_t) nP * 4);
-    rc |= dev_alloc(c, &d.pt_Hdd, nP); rc |= dev_alloc(c, &d.pt_bd, nP);
-    rc |= dev_alloc(c, &d.res_state, nR); rc |= dev_alloc(c, &d.res_new_state, nR); rc |= dev_alloc(c, &d.res_active, nR);
-    rc |= dev_alloc(c, &d.res_lin, nR); rc |= dev_alloc(c, &d.res_energy, nR); rc |= dev_alloc(c, &d.res_new_energy, nR);
-    rc |= dev_alloc(c, &d.res_new_energy_wo, nR); rc |= dev_alloc(c, &d.res_JpJdF, (size_t) nR * 8);
-    rc |= dev_alloc(c, &d.res_JpJdF_new, (size_t) nR * 8); rc |= dev_alloc(c, &d.res_J, (size_t) nR * 74);
-    rc |= dev_alloc(c, &d.res_proj, (size_t) nR * 16); rc |= dev_alloc(c, &d.res_cpt, (size_t) nR * 3);
-    rc |= dev_alloc(c, &d.res_toZero, (size_t) nR * 8);
-    rc |= dev_alloc(c, &c->pt_sel_dev, nP);
-    if (rc) return LDSO_B200_ERR_CUDA;
-    d.pt_host = pt_host; d.pt_res_begin = pt_res_begin; d.res_point = res_point; d.res_target = res_target;
+    if (!same_topology) {
+        free_window(c);
+        memset(&d, 0, sizeof(d));
+        d.nP = nP; d.nR = nR;
+        c->h_pt_host.assign(win->pt_host, win->pt_host + nP);
+        c->h_res_begin.assign(win->res_begin, win->res_begin + nP + 1);
+        if (nP == 0) c->h_res_begin.assign(1, 0);
+        c->h_res_target.assign(win->res_target, win->res_target + nR);
+        rc |= dev_alloc(c, &pt_host, nP); rc |= dev_alloc(c, &pt_res_begin, nP + 1);
+        rc |= dev_alloc(c, &res_point, nR); rc |= dev_alloc(c, &res_target, nR);
+        rc |= dev_alloc(c, &d.pt_u, nP); rc |= dev_alloc(c, &d.pt_v, nP); rc |= dev_alloc(c, &d.pt_idepth, nP);
+        rc |= dev_alloc(c, &d.pt_idepth_zero, nP); rc |= dev_alloc(c, &d.pt_idepth_backup, nP); rc |= dev_alloc(c, &d.pt_step, nP);
+        rc |= dev_alloc(c, &d.pt_color, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_weights, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_priorF, nP);
+        rc |= dev_alloc(c, &d.pt_HdiF, nP); rc |= dev_alloc(c, &d.pt_bdSumF, nP); rc |= dev_alloc(c, &d.pt_Hcd, (size_t) nP * 4);
+        rc |= dev_alloc(c, &d.pt_Hdd, nP); rc |= dev_alloc(c, &d.pt_bd, nP);
+        rc |= dev_alloc(c, &d.res_state, nR); rc |= dev_alloc(c, &d.res_new_state, nR); rc |= dev_alloc(c, &d.res_active, nR);
+        rc |= dev_alloc(c, &d.res_lin, nR); rc |= dev_alloc(c, &d.res_energy, nR); rc |= dev_alloc(c, &d.res_new_energy, nR);
+        rc |= dev_alloc(c, &d.res_new_energy_wo, nR); rc |= dev_alloc(c, &d.res_JpJdF, (size_t) nR * 8);
+        rc |= dev_alloc(c, &d.res_JpJdF_new, (size_t) nR * 8); rc |= dev_alloc(c, &d.res_J, (size_t) nR * 74);
+        rc |= dev_alloc(c, &d.res_proj, (size_t) nR * 16); rc |= dev_alloc(c, &d.res_cpt, (size_t) nR * 3);
+        rc |= dev_alloc(c, &d.res_toZero, (size_t) nR * 8);
+        rc |= dev_alloc(c, &c->pt_sel_dev, nP);
+        if (rc) return LDSO_B200_ERR_CUDA;
+        d.pt_host = pt_host; d.pt_res_begin = pt_res_begin; d.res_point = res_point; d.res_target = res_target;
+        d.newest_offset = 0;
+        d.newest_total = -1;   // derived
+        c->derived_dirty = true;
+    } else {
+        pt_host = (int *) d.pt_host; pt_res_begin = (int *) d.pt_res_begin; res_point = (int *) d.res_point; res_target = (int *) d.res_target;
+    }
 
     std::vector<int> h_res_point(nR);
     for (int p = 0; p < nP; p++) for (int r = c->h_res_begin[p]; r < c->h_res_begin[p + 1]; r++) h_res_point[r] = p;
@@ -317,10 +363,12 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (win->res_state) st.assign(win->res_state, win->res_state + nR);
     if (win->res_is_linearized) lin.assign(win->res_is_linearized, win->res_is_linearized + nR);
 
-    rc |= dev_upload(c, pt_host, win->pt_host, nP);
-    rc |= dev_upload(c, pt_res_begin, c->h_res_begin.data(), nP + 1);
-    rc |= dev_upload(c, res_point, h_res_point.data(), nR);
-    rc |= dev_upload(c, res_target, win->res_target, nR);
+    if (!same_topology) {
+        rc |= dev_upload(c, pt_host, win->pt_host, nP);
+        rc |= dev_upload(c, pt_res_begin, c->h_res_begin.data(), nP + 1);
+        rc |= dev_upload(c, res_point, h_res_point.data(), nR);
+        rc |= dev_upload(c, res_target, win->res_target, nR);
+    }
     rc |= dev_upload(c, d.pt_u, win->pt_u, nP); rc |= dev_upload(c, d.pt_v, win->pt_v, nP);
     rc |= dev_upload(c, d.pt_idepth, win->pt_idepth, nP); rc |= dev_upload(c, d.pt_idepth_zero, win->pt_idepth_zero, nP);
     rc |= dev_upload(c, d.pt_idepth_backup, win->pt_idepth, nP);
@@ -342,10 +390,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_JpJdF_new, 0, sizeof(float) * 8 * std::max(nR, 1), c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * std::max(nR, 1), c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // host vectors above go out of scope
-    d.newest_offset = 0;
-    d.newest_total = -1;   // derived
     c->have_window = true;
-    c->derived_dirty = true;
     return LDSO_B200_OK;
 }
 
@@ -357,8 +402,10 @@ static int build_derived(ldso_b200_ctx *c) {
     const int nP = d.nP, nR = d.nR, nF = c->nF;
     for (int p = 0; p < nP; p++) if (c->h_pt_host[p] >= nF) return c->fail(LDSO_B200_ERR_ARG, "pt_host >= nFrames");
     for (int r = 0; r < nR; r++) if (c->h_res_target[r] >= nF) return c->fail(LDSO_B200_ERR_ARG, "res_target >= nFrames");
-    int ppi = (nP + c->sm_count - 1) / std::max(c->sm_count, 1);
-    ppi = std::max(8, std::min(64, ppi));
+    // two co-resident CTAs per SM hide each other's phase latencies (K1 is a chain of short, barrier-separated phases)
+    const int target_items = 2 * std::max(c->sm_count, 1);
+    int ppi = (nP + target_items - 1) / target_items;
+    ppi = std::max(4, std::min(64, ppi));
     d.pts_per_item = ppi;
     c->k1_smem = k1_smem_bytes(ppi);
     std::vector<int4> items;
@@ -412,6 +459,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     WinState &W = *c->ws_host;
     memset(&W, 0, sizeof(W));
     const int nF = nFrames, n = 8 * nF + CPARS;
+    const int prev_nF = c->have_frames ? c->nF : -1;
     W.nF = nF; W.n = n; W.w = c->w; W.h = c->h;
     W.wM3G = (float) (c->w - 3); W.hM3G = (float) (c->h - 3);      // GlobalCalib.cc:42-43
     W.S = c->S;
@@ -519,7 +567,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     LAUNCH_CHECK(c);
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     c->have_frames = true;
-    c->derived_dirty = true;
+    if (prev_nF != nF) c->derived_dirty = true;    // work items / newest-frame slots depend on nF only
     return LDSO_B200_OK;
 }
 
@@ -548,24 +596,32 @@ extern "C" int ldso_b200_get_marg_prior(ldso_b200_ctx *c, double *HM, double *bM
 // ---------------------------------------------------------------------------------------------- launches
 static int launch_k1(ldso_b200_ctx *c, int flags, const uint8_t *sel = nullptr) {
     if (c->d.nItems == 0) return LDSO_B200_OK;
+    c->kt_begin("k1");
     k1_linearize_accumulate<<<c->d.nItems, K1_THREADS, c->k1_smem, c->stream>>>(c->d, c->ws_dev, flags, sel);
+    c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
 }
 static int launch_k2a(ldso_b200_ctx *c, int full) {
     const int nb = (MAXF * PART_USED + 255) / 256 + 1;
+    c->kt_begin("k2a");
     k2a_reduce<<<nb, 256, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
+    c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
 }
 static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select) {
     const int nb = c->nF * c->nF + c->nF + 2;
-    k2b_stitch<<<nb, K2B_THREADS, 0, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select);
+    c->kt_begin("k2b");
+    k2b_stitch<<<nb, K2B_THREADS, K2B_SMEM_BYTES, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select);
+    c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
 }
 static int launch_k3(ldso_b200_ctx *c, int flags) {
+    c->kt_begin("k3");
     k3_solve_step<<<1, K3_THREADS, K3_SMEM_BYTES, c->stream>>>(c->ws_dev, c->sb, flags, c->iteration_dev);
+    c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
 }

@@ -37,6 +37,8 @@ __device__ __forceinline__ void tri10_rc(int e, int &r, int &c) {
     c = rr + rem;
 }
 
+#define recs_dot(base, ri, k) (base)[2 * (ri) + (k)]
+
 struct K1Shared {   // offsets (in floats) inside the dynamic shared memory block
     int recs, pair, ptin, ptout, misc;
 };
@@ -46,7 +48,7 @@ __host__ __device__ inline K1Shared k1_layout(int pts_per_item) {
     L.pair = L.recs + pts_per_item * MAXF * REC;
     L.ptin = L.pair + MAXF * 32;
     L.ptout = L.ptin + pts_per_item * 8;      // u v idepth idepth_zero priorF deltaF sel pad
-    L.misc = L.ptout + pts_per_item * 8;      // HdiF bdSumF Hcd[4] w ngood
+    L.misc = L.ptout + pts_per_item * 2 * MAXF;   // phase P: HdiF bdSumF Hcd[4] w ngood (8/pt); phase R: 2 floats per residual
     return L;
 }
 #define K1_MISC_FLOATS (MAXF /*frameEnergyTH*/ + 8 /*calib*/ + MAXF * 8 /*xAd rows of host*/ + 4 /*cstep*/ + MAXF * 8 /*adHTdeltaF*/ + 4 /*cDeltaF*/ + 4)
@@ -97,32 +99,54 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         s_dHT[tid] = (t < nF) ? ws->adHTdeltaF[host + nF * t][k] : 0.f;
     }
     if (tid < 4) { s_cstep[tid] = ws->cstep[tid]; s_cD[tid] = ws->calib.cDeltaF[tid]; }
-    for (int i = tid; i < npts * MAXF * REC; i += K1_THREADS) recs[i] = 0.f;
+    for (int i = tid; i < npts * MAXF * 9; i += K1_THREADS) {     // only the active flag and JpJdF must start at zero
+        const int q = i / 9, k = i - q * 9;
+        recs[q * REC + REC_ACTIVE + k] = 0.f;
+    }
     __syncthreads();
 
-    // ---------------- phase R: resubstitute + step (thread per point), stage point inputs
+    // ---------------- phase R: resubstitute + step, stage point inputs.
+    // R1: one thread per residual computes xAd[h,t] . JpJdF_r (EnergyFunctional.cc:539-542) into shared memory;
+    // R2: one thread per point folds them in residual-list order and applies the idepth step.
+    const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
+    const int nres = rend - rbeg;
+    float *s_rdot = s_ptout;        // [nres <= pts_per_item*MAXF] reuse: s_ptout is not live before phase P
+    if (flags & K1F_APPLY_STEP) {
+        for (int ri = tid; ri < nres; ri += K1_THREADS) {
+            const int r = rbeg + ri;
+            float s = 0.f;
+            float act = 0.f;
+            if (d.res_active[r]) {
+                const float4 j0 = *(const float4 *) (d.res_JpJdF + 8 * r), j1 = *(const float4 *) (d.res_JpJdF + 8 * r + 4);
+                const float *xa = s_xAd + d.res_target[r] * 8;
+                s += xa[0] * j0.x; s += xa[1] * j0.y; s += xa[2] * j0.z; s += xa[3] * j0.w;
+                s += xa[4] * j1.x; s += xa[5] * j1.y; s += xa[6] * j1.z; s += xa[7] * j1.w;
+                act = 1.f;
+            }
+            recs_dot(s_rdot, ri, 0) = s;
+            recs_dot(s_rdot, ri, 1) = act;
+        }
+        __syncthreads();
+    }
     double my_sumNID = 0.0, my_numID = 0.0;
     if (tid < npts) {
         const int p = p0 + tid;
         float idepth = d.pt_idepth[p];
         float idepth_zero = d.pt_idepth_zero[p];
         if (flags & K1F_APPLY_STEP) {
-            const int r0 = d.pt_res_begin[p], r1 = d.pt_res_begin[p + 1];
+            const int r0 = d.pt_res_begin[p] - rbeg, r1 = d.pt_res_begin[p + 1] - rbeg;
             int ngood = 0;
             float b = d.pt_bdSumF[p];
             {
+                const float4 hc = *(const float4 *) (d.pt_Hcd + 4 * p);
                 float s = 0.f;
-                for (int i = 0; i < 4; i++) s += s_cstep[i] * d.pt_Hcd[4 * p + i];
+                s += s_cstep[0] * hc.x; s += s_cstep[1] * hc.y; s += s_cstep[2] * hc.z; s += s_cstep[3] * hc.w;
                 b -= s;
             }
-            for (int r = r0; r < r1; r++) {
-                if (!d.res_active[r]) continue;
+            for (int ri = r0; ri < r1; ri++) {
+                if (recs_dot(s_rdot, ri, 1) == 0.f) continue;
                 ngood++;
-                const float *xa = s_xAd + d.res_target[r] * 8;
-                const float *jp = d.res_JpJdF + 8 * r;
-                float s = 0.f;
-                for (int i = 0; i < 8; i++) s += xa[i] * jp[i];
-                b -= s;
+                b -= recs_dot(s_rdot, ri, 0);
             }
             float step = d.pt_step[p];
             if (ngood == 0) step = 0.f;
@@ -150,8 +174,6 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
 
     // ---------------- phase A: one 8-lane group per residual
     const int grp = tid >> 3, idx = tid & 7;
-    const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
-    const int nres = rend - rbeg;
     double my_energy = 0.0, my_nres = 0.0;
     const float fxl = s_cal[0], fyl = s_cal[1], cxl = s_cal[2], cyl = s_cal[3], fxli = s_cal[4], fyli = s_cal[5];
     const float wM3G = s_cal[6], hM3G = s_cal[7];
@@ -444,47 +466,43 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     float *part = d.partials + (size_t) item * PART_STRIDE;
 
     // ---------------- phase B: top Hessian blocks, warp <-> target (AccumulatedTopHessian.cc:78-92)
+    // 4 lane-slots of uniform entry type (no divergence): [tri 0..31] [tri 32..54] [TopRight 0..29] [BotRight 0..5]
     {
         const int t = warp;     // K1_THREADS/32 == MAXF
-        int kind[3], o1[3], o2[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int e = lane + 32 * k;
-            if (e < 55) { kind[k] = 0; tri10_rc(e, o1[k], o2[k]); }
-            else if (e < 85) { kind[k] = 1; o1[k] = (e - 55) / 3; o2[k] = (e - 55) % 3; }
-            else if (e < 91) {
-                kind[k] = 2;
-                const int b = e - 85;   // Jab2(0,0) Jab2(0,1) Jab_r[0] Jab2(1,1) Jab_r[1] rr
-                o1[k] = (b == 0) ? REC_JAB2 : (b == 1) ? REC_JAB2 + 1 : (b == 2) ? REC_JABR : (b == 3) ? REC_JAB2 + 2
-                                                                                  : (b == 4) ? REC_JABR + 1 : REC_RR;
-                o2[k] = 0;
-            } else { kind[k] = 3; o1[k] = o2[k] = 0; }
-        }
-        float acc[3] = {0.f, 0.f, 0.f};
+        int r0, c0, r1, c1;
+        tri10_rc(lane, r0, c0);
+        tri10_rc(min(32 + lane, 54), r1, c1);
+        const bool on1 = lane < 23, on2 = lane < 30, on3 = lane < 6;
+        const int tri = min(lane, 29) / 3, trk = min(lane, 29) % 3;
+        const int troff0 = (trk == 0) ? REC_JABJI + 0 : (trk == 1) ? REC_JABJI + 2 : REC_JIR + 0;
+        const int troff1 = (trk == 0) ? REC_JABJI + 1 : (trk == 1) ? REC_JABJI + 3 : REC_JIR + 1;
+        const int b3 = min(lane, 5);   // Jab2(0,0) Jab2(0,1) Jab_r[0] Jab2(1,1) Jab_r[1] rr
+        const int broff = (b3 == 0) ? REC_JAB2 : (b3 == 1) ? REC_JAB2 + 1 : (b3 == 2) ? REC_JABR : (b3 == 3) ? REC_JAB2 + 2
+                                                                          : (b3 == 4) ? REC_JABR + 1 : REC_RR;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         if (t < nF && t != host) {
             for (int pl = 0; pl < npts; pl++) {
                 const float *rec = recs + (pl * MAXF + t) * REC;
                 if (rec[REC_ACTIVE] == 0.f) continue;
                 const float a = rec[REC_A], b = rec[REC_B], c = rec[REC_C];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (kind[k] == 0) {
-                        const float xr = rec[REC_X + o1[k]], xc = rec[REC_X + o2[k]];
-                        const float yr = rec[REC_Y + o1[k]], yc = rec[REC_Y + o2[k]];
-                        acc[k] += a * xc * xr + c * yc * yr + b * (xc * yr + yc * xr);
-                    } else if (kind[k] == 1) {
-                        const float xi = rec[REC_X + o1[k]], yi = rec[REC_Y + o1[k]];
-                        const float tr0 = (o2[k] == 0) ? rec[REC_JABJI + 0] : (o2[k] == 1) ? rec[REC_JABJI + 2] : rec[REC_JIR + 0];
-                        const float tr1 = (o2[k] == 0) ? rec[REC_JABJI + 1] : (o2[k] == 1) ? rec[REC_JABJI + 3] : rec[REC_JIR + 1];
-                        acc[k] += xi * tr0 + yi * tr1;
-                    } else if (kind[k] == 2) {
-                        acc[k] += rec[o1[k]];
-                    }
+                {
+                    const float xr = rec[REC_X + r0], xc = rec[REC_X + c0], yr = rec[REC_Y + r0], yc = rec[REC_Y + c0];
+                    acc0 += a * xc * xr + c * yc * yr + b * (xc * yr + yc * xr);
                 }
+                {
+                    const float xr = rec[REC_X + r1], xc = rec[REC_X + c1], yr = rec[REC_Y + r1], yc = rec[REC_Y + c1];
+                    acc1 += a * xc * xr + c * yc * yr + b * (xc * yr + yc * xr);
+                }
+                acc2 += rec[REC_X + tri] * rec[troff0] + rec[REC_Y + tri] * rec[troff1];
+                acc3 += rec[broff];
             }
         }
-#pragma unroll
-        for (int k = 0; k < 3; k++) part[PART_TOP + t * 96 + lane + 32 * k] = acc[k];
+        float *pt = part + PART_TOP + t * 96;
+        pt[lane] = acc0;
+        if (on1) pt[32 + lane] = acc1;
+        if (on2) pt[55 + lane] = acc2;
+        if (on3) pt[85 + lane] = acc3;
+        if (lane < 5) pt[91 + lane] = 0.f;
     }
 
     // ---------------- phase P: per-point sums (AccumulatedTopHessian.cc:94-116, AccumulatedSCHessian.cc:11-29)

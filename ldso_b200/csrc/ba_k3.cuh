@@ -1,0 +1,425 @@
+// K3 — one CTA: EnergyFunctional::solveSystemF (EnergyFunctional.cc:240-351, default solver mode), the frame/calib
+// part of resubstituteF_MT (:491-507), FullSystem::backupState / doStepFromBackup (FullSystem.cc:1587-1676),
+// FrameHessian::setState, FrameFramePrecalc::Set for all nF^2 pairs and EnergyFunctional::setDeltaF.
+//
+// Everything here is a serial dependency chain on a 68x68 system, so the design goal is latency, not throughput:
+//   * the frame/calib records are staged in shared memory once (one global round trip instead of dozens);
+//   * the LDL^T is BLOCKED (8 columns per step): a step is [8x8 diagonal block by one thread, in registers] ->
+//     [panel rows, one thread per row] -> [trailing update, all threads], 3 barriers per 8 columns instead of
+//     2 barriers per column;
+//   * Eigen's LDLT pivots on the largest remaining |diagonal| of the INPUT matrix (its left-looking update never
+//     touches later diagonal entries before they are chosen), i.e. a descending-|diag| order: computed by a rank
+//     sort and applied as a symmetric permutation before the (then unpivoted) blocked factorisation.
+#pragma once
+#include "common.cuh"
+#include "se3_math.cuh"
+#include "ba_k2.cuh"
+
+#define K3F_SOLVE 1
+#define K3F_STEP 2
+#define K3F_BACKUP 4
+#define K3_THREADS 256
+#define K3_LD (MAXN + 1)
+#define K3_NB 8
+
+struct K3Frames {       // shared-memory staging of the mutable window records
+    FrameDev fr[MAXF];
+    CalibDev calib;
+};
+
+__device__ void calib_set_value(CalibDev &c, const double v[4]) {  // CalibHessian::setValue (CalibHessian.h:71-85)
+    for (int i = 0; i < 4; i++) c.value[i] = v[i];
+    c.value_scaled[0] = (double) SCALE_F * c.value[0];
+    c.value_scaled[1] = (double) SCALE_F * c.value[1];
+    c.value_scaled[2] = (double) SCALE_C * c.value[2];
+    c.value_scaled[3] = (double) SCALE_C * c.value[3];
+    c.fxl = (float) c.value_scaled[0]; c.fyl = (float) c.value_scaled[1];
+    c.cxl = (float) c.value_scaled[2]; c.cyl = (float) c.value_scaled[3];
+    c.fxli = 1.0f / c.fxl; c.fyli = 1.0f / c.fyl;
+    c.cxli = -c.cxl / c.fxl; c.cyli = -c.cyl / c.fyl;
+}
+
+__device__ void stage_in(K3Frames *S, const WinState *ws) {
+    const int nw = (int) (sizeof(FrameDev) * MAXF / 4);
+    const unsigned *src = (const unsigned *) ws->fr;
+    unsigned *dst = (unsigned *) S->fr;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    const int nc = (int) (sizeof(CalibDev) / 4);
+    const unsigned *srcc = (const unsigned *) &ws->calib;
+    unsigned *dstc = (unsigned *) &S->calib;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) dstc[i] = srcc[i];
+    __syncthreads();
+}
+__device__ void stage_out(const K3Frames *S, WinState *ws) {
+    __syncthreads();
+    const int nw = (int) (sizeof(FrameDev) * MAXF / 4);
+    unsigned *dst = (unsigned *) ws->fr;
+    const unsigned *src = (const unsigned *) S->fr;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    const int nc = (int) (sizeof(CalibDev) / 4);
+    unsigned *dstc = (unsigned *) &ws->calib;
+    const unsigned *srcc = (const unsigned *) &S->calib;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) dstc[i] = srcc[i];
+}
+
+// FrameHessian::setState (FrameHessian.h:78-91), FrameFramePrecalc::Set for all pairs (FrameFramePrecalc.cc:6-35),
+// EnergyFunctional::setDeltaF frame part (EnergyFunctional.cc:403-429). Frame records live in shared memory (S);
+// the pair records are written to global. Called by all threads of a CTA with >= 128 threads.
+__device__ void frames_refresh(K3Frames *S, WinState *ws) {
+    const int nF = ws->nF, tid = threadIdx.x;
+    if (tid < nF) {
+        FrameDev &f = S->fr[tid];
+        double ss[6];
+        for (int i = 0; i < 3; i++) ss[i] = (double) SCALE_XI_TRANS * f.state[i];
+        for (int i = 3; i < 6; i++) ss[i] = (double) SCALE_XI_ROT * f.state[i];
+        double Re[9], te[3];
+        se3_exp(ss, Re, te);
+        se3_mul(Re, te, f.evalR, f.evalT, f.preR, f.preT);
+        for (int i = 0; i < 8; i++) {
+            f.delta[i] = f.state[i] - f.state_zero[i];
+            f.delta_prior[i] = f.state[i];
+        }
+    }
+    if (tid == 64) {
+        CalibDev &c = S->calib;
+        for (int i = 0; i < 4; i++) c.cDeltaF[i] = (float) (c.value[i] - c.value_zero[i]);
+    }
+    __syncthreads();
+    if (tid < nF * nF) {
+        const int h = tid % nF, t = tid / nF;
+        const FrameDev &fh = S->fr[h], &ft = S->fr[t];
+        PairRec pc;
+        PairRecFull pf;
+        double R0[9], t0[3], R[9], tt[3];
+        se3_mul_inv(ft.evalR, ft.evalT, fh.evalR, fh.evalT, R0, t0);
+        se3_mul_inv(ft.preR, ft.preT, fh.preR, fh.preT, R, tt);
+        float Rf[9], tf[3];
+        for (int i = 0; i < 9; i++) { pc.R0[i] = (float) R0[i]; Rf[i] = (float) R[i]; pf.RTll[i] = Rf[i]; }
+        for (int i = 0; i < 3; i++) { pc.t0[i] = (float) t0[i]; tf[i] = (float) tt[i]; pf.tTll[i] = tf[i]; }
+        pc.distanceLL = (float) sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+        const CalibDev &c = S->calib;
+        float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
+        float Ki[9], tmp[9];
+        m33f_inverse(K, Ki);
+        m33f_mul(K, Rf, tmp);
+        m33f_mul(tmp, Ki, pc.KRKi);
+        for (int i = 0; i < 3; i++) {
+            float s = K[i * 3 + 0] * tf[0];
+            s += K[i * 3 + 1] * tf[1];
+            s += K[i * 3 + 2] * tf[2];
+            pc.Kt[i] = s;
+        }
+        // AffLight::fromToVecExposure (AffLight.h:27-35) with aff_g2l() = state_scaled[6..7]
+        float eF = fh.ab_exposure, eT = ft.ab_exposure;
+        if (eF == 0 || eT == 0) eT = eF = 1;
+        const float ah = (float) ((double) SCALE_A * fh.state[6]), bh = (float) ((double) SCALE_B * fh.state[7]);
+        const float at = (float) ((double) SCALE_A * ft.state[6]), bt = (float) ((double) SCALE_B * ft.state[7]);
+        const float aa = expf(at - ah) * eT / eF;
+        pc.aff[0] = aa;
+        pc.aff[1] = bt - aa * bh;
+        pc.b0 = (float) (fh.state_zero[7] * (double) SCALE_B);
+        pc.pad[0] = pc.pad[1] = pc.pad[2] = pc.pad[3] = 0.f;
+        ws->pair[h + nF * t] = pc;
+        ws->pairFull[h + nF * t] = pf;
+    }
+    // adHTdeltaF (EnergyFunctional.cc:406-414): one (pair, column) output per thread pass
+    for (int o = tid; o < nF * nF * 8; o += blockDim.x) {
+        const int q = o >> 3, j = o & 7, h = q % nF, t = q / nF;
+        const FrameDev &fh = S->fr[h], &ft = S->fr[t];
+        const float *AH = ws->adHostF[q], *AT = ws->adTargetF[q];
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < 8; i++) s1 += (float) (fh.state[i] - fh.state_zero[i]) * AH[i * 8 + j];
+        for (int i = 0; i < 8; i++) s2 += (float) (ft.state[i] - ft.state_zero[i]) * AT[i * 8 + j];
+        ws->adHTdeltaF[q][j] = s1 + s2;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
+    __shared__ K3Frames S;
+    stage_in(&S, ws);
+    frames_refresh(&S, ws);
+    stage_out(&S, ws);
+}
+
+// Factor the bs x bs diagonal block at (k0,k0) in place (lower): L below the diagonal (unit), D on it.
+// Executed by ONE WARP: lane j < 8 keeps row j of the block in registers; a step is one broadcast of the pivot,
+// one reciprocal, and 7-k shuffles of the unscaled column. (L = W * (1/d): <= 1 ulp from Eigen's W / d.)
+__device__ __forceinline__ void ldlt_diag_block_warp(double *A, int k0, int bs, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    double a[K3_NB];
+    const int row = lane & 7;
+#pragma unroll
+    for (int c = 0; c < K3_NB; c++)
+        a[c] = (row < bs && c <= row && c < bs) ? A[(k0 + row) * K3_LD + k0 + c] : ((c == row) ? 1.0 : 0.0);
+#pragma unroll
+    for (int k = 0; k < K3_NB; k++) {
+        const double dk = __shfl_sync(FULL, a[k], k);
+        const bool valid = fabs(dk) > 0.0;
+        const double inv = valid ? 1.0 / dk : 1.0;
+        const double w = a[k];                      // unscaled column entry of this lane's row (rows > k)
+        const double l = w * inv;
+#pragma unroll
+        for (int j = k + 1; j < K3_NB; j++) {
+            const double wj = __shfl_sync(FULL, w, j);
+            if (row >= j) a[j] -= l * wj;
+        }
+        if (row > k) a[k] = l;
+    }
+    if (lane < bs) {
+#pragma unroll
+        for (int c = 0; c < K3_NB; c++) if (c <= lane) A[(k0 + lane) * K3_LD + k0 + c] = a[c];
+    }
+}
+
+// z <- L11^{-1} z for the unit-lower block at (k0,k0); one warp, lane c holds z[k0+c]
+__device__ __forceinline__ void trsv_lower_warp(const double *A, double *v, int k0, int bs, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = lane & 7;
+    double Lr[K3_NB];
+#pragma unroll
+    for (int j = 0; j < K3_NB; j++) Lr[j] = (c < bs && j < c) ? A[(k0 + c) * K3_LD + k0 + j] : 0.0;
+    double z = (c < bs) ? v[k0 + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < K3_NB - 1; j++) {
+        const double zj = __shfl_sync(FULL, z, j);
+        z -= Lr[j] * zj;          // Lr[j] == 0 for j >= c
+    }
+    if (lane < bs) v[k0 + lane] = z;
+}
+// x <- L11^{-T} x
+__device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, int k0, int bs, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = lane & 7;
+    double Lc[K3_NB];
+#pragma unroll
+    for (int j = 0; j < K3_NB; j++) Lc[j] = (j < bs && c < j) ? A[(k0 + j) * K3_LD + k0 + c] : 0.0;
+    double x = (c < bs) ? v[k0 + c] : 0.0;
+#pragma unroll
+    for (int j = K3_NB - 1; j >= 1; j--) {
+        const double xj = __shfl_sync(FULL, x, j);
+        x -= Lc[j] * xj;          // Lc[j] == 0 for j <= c
+    }
+    if (lane < bs) v[k0 + lane] = x;
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
+    extern __shared__ double sm3[];
+    double *A0 = sm3;                       // [n][K3_LD] row-major assembled matrix
+    double *A = A0 + MAXN * K3_LD;          // permuted copy, factorised in place
+    double *Wp = A + MAXN * K3_LD;          // [MAXN][K3_NB] panel W = L*D of the current block step
+    double *vb = Wp + MAXN * K3_NB;         // rhs / solution
+    double *vS = vb + MAXN;                 // SVecI
+    double *vd = vS + MAXN;                 // delta / temp
+    double *vx = vd + MAXN;                 // x
+    int *perm = (int *) (vx + MAXN);        // [MAXN]
+    K3Frames *S = (K3Frames *) (perm + MAXN + 2);
+    const int nF = ws->nF, n = ws->n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int iteration = *iteration_dev;
+
+    stage_in(S, ws);
+
+    if (flags & K3F_BACKUP) {
+        if (tid < nF) for (int i = 0; i < 10; i++) S->fr[tid].state_backup[i] = S->fr[tid].state[i];
+        if (tid == 32) for (int i = 0; i < 4; i++) S->calib.value_backup[i] = S->calib.value[i];
+        __syncthreads();
+    }
+    if (flags & K3F_SOLVE) {
+        const double lambda = 1e-5;        // SOLVER_FIX_LAMBDA (EnergyFunctional.cc:243)
+        // delta = getStitchedDeltaF (EnergyFunctional.h:178-184)
+        if (tid < n) vd[tid] = (tid < CPARS) ? (double) S->calib.cDeltaF[tid] : S->fr[(tid - CPARS) >> 3].delta[(tid - CPARS) & 7];
+        __syncthreads();
+        // HFinal_top = HL + HM + HA ; lastHS = HFinal_top - H_sc ; diag *= (1+lambda) ; HFinal_top -= H_sc/(1+lambda)
+        // (:283-291)  — one pass, all loads independent
+        const double inv1l = 1.0 / (1.0 + lambda);
+        for (int e = tid; e < n * n; e += K3_THREADS) {
+            const int r = e % n, c = e / n;
+            const double hsc = sb.H_sc[e];
+            double v = sb.H_A[e] + sb.HM[e];
+            if (r == c) v += (r < CPARS) ? ws->cPrior[r] : S->fr[(r - CPARS) >> 3].prior[(r - CPARS) & 7];
+            sb.lastHS[e] = v - hsc;
+            if (r == c) v *= (1 + lambda);
+            A0[r * K3_LD + c] = v - hsc * inv1l;
+        }
+        // bFinal_top = bL + (bM + HM*delta) + bA - b_sc  (:257,284): warp per row group, coalesced over columns
+        for (int r = warp; r < n; r += K3_THREADS / 32) {
+            double s = 0.0;
+            for (int c = lane; c < n; c += 32) s += sb.HM[(size_t) c * n + r] * vd[c];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                double bl;
+                if (r < CPARS) bl = ws->cPrior[r] * (double) S->calib.cDeltaF[r];
+                else {
+                    const FrameDev &f = S->fr[(r - CPARS) >> 3];
+                    bl = f.prior[(r - CPARS) & 7] * f.delta_prior[(r - CPARS) & 7];
+                }
+                const double bf = bl + (sb.bM[r] + s) + sb.b_A[r] - sb.b_sc[r];
+                vb[r] = bf;
+                sb.lastbS[r] = bf;
+            }
+        }
+        __syncthreads();
+        // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
+        if (tid < n) vS[tid] = 1.0 / sqrt(A0[tid * K3_LD + tid] + 10.0);
+        __syncthreads();
+        if (tid < n) {
+            const double di = fabs(A0[tid * K3_LD + tid] * vS[tid] * vS[tid]);
+            int rank = 0;
+            for (int j = 0; j < n; j++) {
+                const double dj = fabs(A0[j * K3_LD + j] * vS[j] * vS[j]);
+                rank += (dj > di) || (dj == di && j < tid);
+            }
+            perm[rank] = tid;
+        }
+        __syncthreads();
+        // A = P (S A0 S) P^T, b' = P S b
+        for (int e = tid; e < n * n; e += K3_THREADS) {
+            const int r = e / n, c = e % n;
+            const int pr = perm[r], pc = perm[c];
+            A[r * K3_LD + c] = A0[pr * K3_LD + pc] * vS[pr] * vS[pc];
+        }
+        if (tid < n) vd[tid] = vb[perm[tid]] * vS[perm[tid]];
+        __syncthreads();
+        if (tid < n) vb[tid] = vd[tid];
+        __syncthreads();
+
+        // ---- blocked in-place LDL^T (lower)
+        for (int k0 = 0; k0 < n; k0 += K3_NB) {
+            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
+            if (warp == 0) ldlt_diag_block_warp(A, k0, bs, lane);
+            __syncthreads();
+            if (tid < n - m0) {      // panel row i: w = L*D (unscaled), l = L
+                const int i = m0 + tid;
+                double w[K3_NB], l[K3_NB];
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) {
+                    if (c < bs) {
+                        double s = A[i * K3_LD + k0 + c];
+#pragma unroll
+                        for (int j = 0; j < c; j++) s -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
+                        w[c] = s;
+                        const double d = A[(k0 + c) * K3_LD + k0 + c];
+                        l[c] = (fabs(d) > 0.0) ? s * (1.0 / d) : s;
+                    } else { w[c] = 0.0; l[c] = 0.0; }
+                }
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) {
+                    if (c < bs) A[i * K3_LD + k0 + c] = l[c];
+                    Wp[i * K3_NB + c] = w[c];
+                }
+            }
+            __syncthreads();
+            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= i < n
+            for (int i = m0 + (tid >> 4); i < n; i += 16) {
+                double li[K3_NB];
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) li[c] = (c < bs) ? A[i * K3_LD + k0 + c] : 0.0;
+                for (int j = m0 + (tid & 15); j <= i; j += 16) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c++) s += li[c] * Wp[j * K3_NB + c];
+                    A[i * K3_LD + j] -= s;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- forward solve L z = b (unit lower), blocked
+        for (int k0 = 0; k0 < n; k0 += K3_NB) {
+            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
+            if (warp == 0) trsv_lower_warp(A, vb, k0, bs, lane);
+            __syncthreads();
+            if (tid < n - m0) {
+                const int i = m0 + tid;
+                double s = vb[i];
+                for (int c = 0; c < bs; c++) s -= A[i * K3_LD + k0 + c] * vb[k0 + c];
+                vb[i] = s;
+            }
+            __syncthreads();
+        }
+        if (tid < n) {
+            const double dk = A[tid * K3_LD + tid];
+            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? vb[tid] / dk : 0.0;     // Eigen's pseudo-inverse of D
+        }
+        __syncthreads();
+        // ---- backward solve L^T x = z, blocked from the last block up
+        for (int k0 = ((n - 1) / K3_NB) * K3_NB; k0 >= 0; k0 -= K3_NB) {
+            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
+            // z[k0+c] -= sum_{i>=m0} L(i,k0+c) x[i] : warp c
+            if (warp < bs && m0 < n) {
+                double s = 0.0;
+                for (int i = m0 + lane; i < n; i += 32) s += A[i * K3_LD + k0 + warp] * vb[i];
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) vb[k0 + warp] -= s;
+            }
+            __syncthreads();
+            if (warp == 0) trsv_lower_t_warp(A, vb, k0, bs, lane);
+            __syncthreads();
+        }
+        if (tid < n) vx[perm[tid]] = vb[tid];
+        __syncthreads();
+        if (tid < n) vx[tid] *= vS[tid];
+        __syncthreads();
+        // orthogonalize(&x, 0) when iteration >= 2 (SOLVER_ORTHOGONALIZE_X_LATER, :339-343): x -= NNpiTS x
+        if (iteration >= 2) {
+            for (int r = warp; r < n; r += K3_THREADS / 32) {
+                double s = 0.0;
+                for (int c = lane; c < n; c += 32) s += sb.Pns[(size_t) r * n + c] * vx[c];   // NNpiTS is symmetric
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) vd[r] = s;
+            }
+            __syncthreads();
+            if (tid < n) vx[tid] -= vd[tid];
+            __syncthreads();
+        }
+        if (tid < n) sb.lastX[tid] = vx[tid];
+        // resubstituteF_MT frame part (:495-507)
+        if (tid < CPARS) {
+            S->calib.step[tid] = -vx[tid];
+            ws->cstep[tid] = (float) vx[tid];
+        }
+        if (tid >= 32 && tid < 32 + nF) {
+            const int h = tid - 32;
+            for (int i = 0; i < 8; i++) S->fr[h].step[i] = -vx[CPARS + 8 * h + i];
+            S->fr[h].step[8] = S->fr[h].step[9] = 0.0;
+        }
+        for (int o = tid; o < nF * nF * 8; o += K3_THREADS) {
+            const int q = o >> 3, j = o & 7, h = q / nF, t = q % nF;     // xAd[nFrames*h + t]
+            const float *AH = ws->adHostF[h + nF * t], *AT = ws->adTargetF[h + nF * t];
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < 8; i++) s1 += (float) vx[CPARS + 8 * h + i] * AH[i * 8 + j];
+            for (int i = 0; i < 8; i++) s2 += (float) vx[CPARS + 8 * t + i] * AT[i * 8 + j];
+            ws->xAd[nF * h + t][j] = s1 + s2;
+        }
+        __syncthreads();
+    }
+    if (flags & K3F_STEP) {
+        // doStepFromBackup(1,1,1,1,1), frame/calib part (FullSystem.cc:1588-1597,1617-1627)
+        if (tid == 0) {
+            double nv[4];
+            for (int i = 0; i < 4; i++) nv[i] = S->calib.value_backup[i] + S->calib.step[i];
+            calib_set_value(S->calib, nv);
+            float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+            for (int h = 0; h < nF; h++) {
+                const double *st = S->fr[h].step;
+                sumA += st[6] * st[6];
+                sumB += st[7] * st[7];
+                sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
+                sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
+            }
+            sumA /= nF; sumB /= nF; sumR /= nF; sumT /= nF;
+            const float sumNID = ws->sumNID / ws->numID;
+            const float thO = ws->S.thOptIterations;
+            ws->canbreak = (sqrtf(sumA) < 0.0005 * thO && sqrtf(sumB) < 0.00005 * thO && sqrtf(sumR) < 0.00005 * thO &&
+                            sqrtf(sumT) * sumNID < 0.00005 * thO) ? 1 : 0;
+        }
+        if (tid >= 32 && tid < 32 + nF) {
+            FrameDev &f = S->fr[tid - 32];
+            for (int i = 0; i < 10; i++) f.state[i] = f.state_backup[i] + f.step[i];
+        }
+        __syncthreads();
+        frames_refresh(S, ws);
+    }
+    stage_out(S, ws);
+    if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
+}
+#define K3_SMEM_BYTES ((2 * MAXN * K3_LD + MAXN * K3_NB + 4 * MAXN) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + 64)

@@ -1,0 +1,65 @@
+"""GPU parity tests of the coarse tracker (CoarseTracker::calcRes / calcGSSSE / trackNewestCoarse) through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from ldso_b200 import capi, synth
+from tests import oracle_py
+from tests.parity import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(pair):
+    ot = oracle_py.OracleTracker(pair)
+    ctx = capi.Context(pair.w, pair.h, pair.levels)
+    ctx.upload_frame(0, pair.ref_pyr)
+    ctx.upload_frame(1, pair.new_pyr)
+    ctx.tracker_make_k(*[float(x) for x in pair.K])
+    for l in range(pair.levels):
+        ctx.tracker_set_ref_level(l, *ot.pc(l))
+    ctx.tracker_set_frames(pair.ref_aff[0], pair.ref_aff[1], 1.0, 1, 1.0)
+    return ot, ctx
+
+
+@pytest.mark.parametrize("size", ["small", "cfg1"])
+def test_eval_matches_oracle(size):
+    pair = synth.make_track_pair(w=320, h=240, n_pts=400, seed=7) if size == "small" else synth.make_track_pair()
+    ot, ctx = _setup(pair)
+    for l in range(pair.levels):
+        for R, t, a, b, cut in ((np.eye(3), np.zeros(3), 0.0, 0.0, 20.0), (pair.R_true, pair.t_true, 0.01, 1.0, 20.0),
+                                (pair.R_true, pair.t_true * 3, 0.0, 0.0, 5.0)):
+            rg, Hg, bg = ctx.tracker_eval(l, R, t, a, b, cut)
+            ro, Ho, bo = ot.eval(l, R, t, a, b, cut)
+            assert rg[1] == ro[1], "numTermsInE must match exactly"
+            assert rel_err(rg, ro) < 1e-5
+            assert rel_err(Hg, Ho) < TOL and rel_err(bg, bo) < TOL
+    ctx.close()
+
+
+def test_track_matches_oracle_and_golden():
+    pair = synth.make_track_pair(w=320, h=240, n_pts=400, seed=7)
+    ot, ctx = _setup(pair)
+    okg, Rg, tg, ag, bg, lrg, lfg = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    oko, Ro, to, ao, bo, lro, lfo, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    assert okg == oko
+    assert rel_err(Rg, Ro) < 1e-5 and rel_err(tg, to) < 1e-3
+    assert abs(ag - ao) < 1e-4 and abs(bg - bo) < 1e-2
+    assert rel_err(np.nan_to_num(lrg), np.nan_to_num(lro)) < 1e-3
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tracker_small.npz"))
+    assert rel_err(tg, g["t"]) < 1e-3 and rel_err(Rg, g["R"]) < 1e-5
+    # abort path: an impossible minResForAbort makes trackNewestCoarse return false and leave the pose untouched
+    okg, Rg2, tg2, *_ = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1, min_res=np.full(5, 1e-3))
+    assert not okg and np.array_equal(Rg2, np.eye(3)) and np.all(tg2 == 0)
+    ctx.close()
+
+
+def test_track_full_size_converges():
+    pair = synth.make_track_pair()
+    ot, ctx = _setup(pair)
+    ok, R, t, a, b, lr, lf = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    assert ok
+    assert np.linalg.norm(t - pair.t_true) < 0.05 * np.linalg.norm(pair.t_true)
+    assert np.abs(R - pair.R_true).max() < 1e-3
+    ctx.close()

@@ -87,6 +87,19 @@ def run_ba(win, tag):
         cmp(f"it{it} lastHS", HS, so["lastHS"])
         cmp(f"it{it} lastbS", bS, so["lastbS"])
         cmp(f"it{it} lastX", X, so["lastX"])
+        Pn = o.nullspace_projector()
+        I = np.eye(Pn.shape[0])
+        cmp(f"it{it} lastX gauge-projected", (I - Pn) @ X, (I - Pn) @ so["lastX"])
+        # the device solver against a double-precision numpy solve of ITS OWN system (isolates K3 from input noise)
+        lam = 1e-5
+        Hf = HS + sg["Hsc"]
+        H2 = Hf.copy(); H2[np.diag_indices_from(H2)] *= (1 + lam); H2 -= sg["Hsc"] / (1 + lam)
+        Sv = 1 / np.sqrt(np.diag(H2) + 10)
+        xn = Sv * np.linalg.solve(Sv[:, None] * H2 * Sv[None, :], Sv * bS)
+        if it >= 2:
+            xn = xn - ctx.nullspace_projector() @ xn
+        cmp(f"it{it} lastX vs numpy(own system)", X, xn)
+        cmp(f"it{it} lastX vs numpy, gauge-projected", (I - Pn) @ X, (I - Pn) @ xn)
         pg, po = ctx.points(), o.points()
         for k in ("HdiF", "bdSumF", "Hcd_accAF", "Hdd_accAF", "bd_accAF"):
             cmp(f"it{it} pt.{k}", pg[k], po[k])
