@@ -286,7 +286,7 @@ def run_e2e(ctx, win, args, torch):
         ctx.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(nF)), win.K)
         ctx.set_window(win.pt_host, win.pt_u, win.pt_v, win.pt_idepth, win.pt_idepth_zero, win.pt_has_prior, win.pt_color,
                        win.pt_weights, win.res_begin, win.res_target)
-        ctx.optimize_begin()
+        ctx.optimize_begin(want_energy=False)
         ctx.gn_iterations(0, 1)
         ctx.last_solution()
         ctx.points()

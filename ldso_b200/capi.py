@@ -43,6 +43,10 @@ class FrameStateC(C.Structure):
                 ("frame_id", C.c_int32), ("image_slot", C.c_int32)]
 
 
+FRAME_DTYPE = np.dtype([("evalR", "<f8", 9), ("evalT", "<f8", 3), ("state_zero", "<f8", 10), ("state", "<f8", 10),
+                        ("ab_exposure", "<f4"), ("frameEnergyTH", "<f4"), ("frame_id", "<i4"), ("image_slot", "<i4")])
+assert FRAME_DTYPE.itemsize == C.sizeof(FrameStateC)
+
 # every symbol include/ldso_b200.h declares (tests check the shared object exports all of them)
 SYMBOLS = [
     "ldso_b200_default_settings", "ldso_b200_create", "ldso_b200_destroy", "ldso_b200_last_error", "ldso_b200_set_stream",
@@ -174,22 +178,20 @@ class Context:
     def set_frames(self, Rcw, tcw, state_zero, state, ab_exposure, frame_id, slots, K_scaled, K_zero=None,
                    frame_energy_th=None):
         nF = len(Rcw)
-        arr = (FrameStateC * nF)()
-        for i in range(nF):
-            f = arr[i]
-            f.evalR[:] = np.asarray(Rcw[i], np.float64).reshape(-1).tolist()
-            f.evalT[:] = np.asarray(tcw[i], np.float64).tolist()
-            f.state_zero[:] = np.asarray(state_zero[i], np.float64).tolist()
-            f.state[:] = np.asarray(state[i], np.float64).tolist()
-            f.ab_exposure = float(ab_exposure[i])
-            f.frameEnergyTH = float(8 * 8 * 8 if frame_energy_th is None else frame_energy_th[i])
-            f.frame_id = int(frame_id[i])
-            f.image_slot = int(slots[i])
+        arr = np.zeros(nF, FRAME_DTYPE)          # same layout as ldso_b200_frame_state
+        arr["evalR"] = np.asarray(Rcw, np.float64).reshape(nF, 9)
+        arr["evalT"] = np.asarray(tcw, np.float64).reshape(nF, 3)
+        arr["state_zero"] = np.asarray(state_zero, np.float64).reshape(nF, 10)
+        arr["state"] = np.asarray(state, np.float64).reshape(nF, 10)
+        arr["ab_exposure"] = np.asarray(ab_exposure, np.float32)
+        arr["frameEnergyTH"] = 8 * 8 * 8 if frame_energy_th is None else np.asarray(frame_energy_th, np.float32)
+        arr["frame_id"] = np.asarray(frame_id, np.int32)
+        arr["image_slot"] = np.asarray(slots, np.int32)
         Ks = np.ascontiguousarray(K_scaled, np.float64)
         if K_zero is None:   # CalibHessian ctor: value_zero = value = SCALE_*_INVERSE * value_scaled
             K_zero = Ks * np.float64(np.float32(1.0) / np.float32(50.0))
         Kz = np.ascontiguousarray(K_zero, np.float64)
-        self._chk(self.L.ldso_b200_set_frames(self.ctx, nF, arr, _d(Ks), _d(Kz)))
+        self._chk(self.L.ldso_b200_set_frames(self.ctx, nF, arr.ctypes.data_as(C.POINTER(FrameStateC)), _d(Ks), _d(Kz)))
         self.nF = nF
 
     def set_window(self, pt_host, pt_u, pt_v, pt_idepth, pt_idepth_zero, pt_has_prior, pt_color, pt_weights, res_begin,
@@ -257,7 +259,10 @@ class Context:
         return bool(cb.value)
 
     # ---- fused loop
-    def optimize_begin(self):
+    def optimize_begin(self, want_energy=True):
+        if not want_energy:     # fully asynchronous
+            self._chk(self.L.ldso_b200_optimize_begin(self.ctx, None))
+            return None
         e = C.c_double()
         self._chk(self.L.ldso_b200_optimize_begin(self.ctx, C.byref(e)))
         return e.value

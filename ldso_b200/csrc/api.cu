@@ -33,6 +33,7 @@ struct ldso_b200_ctx {
 
     float4 *img[NSLOTS][MAXLVL];
     float *scratch = nullptr;          // upload staging (w*h*3 floats)
+    cudaEvent_t copy_done = nullptr, frames_copied = nullptr;
     size_t scratch_floats = 0;
 
     // window
@@ -48,6 +49,13 @@ struct ldso_b200_ctx {
     double *solve_mem = nullptr;
     int *iteration_dev = nullptr;
     uint8_t *pt_sel_dev = nullptr;
+    char *arena_dev = nullptr, *arena_host = nullptr;
+    struct Layout {
+        size_t pt_host, pt_res_begin, res_point, res_target, topo_end, pt_u, pt_v, pt_color, pt_weights, pt_priorF, pt_idepth_backup,
+            res_lin, res_state, dl_begin, pt_idepth, pt_idepth_zero, ul_end, pt_step, pt_HdiF, pt_bdSumF, pt_Hdd, pt_bd, pt_Hcd,
+            res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, res_JpJdF, dl_end, res_JpJdF_new, total;
+    } lay;
+    bool mirror_valid = false;
     size_t k1_smem = 0;
     bool multi = false;
 
@@ -167,6 +175,7 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     p += 2 * nn;   // spare
     c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
+    cudaEventCreateWithFlags(&c->frames_copied, cudaEventDisableTiming);
     cudaFuncSetAttribute(k1_linearize_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem_bytes(64));
     cudaFuncSetAttribute(k3_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K3_SMEM_BYTES);
     cudaFuncSetAttribute(k2b_stitch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K2B_SMEM_BYTES);
@@ -176,6 +185,9 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
 static void free_window(ldso_b200_ctx *c) {
     for (void *p : c->win_allocs) cudaFree(p);
     c->win_allocs.clear();
+    if (c->arena_dev) { cudaFree(c->arena_dev); c->arena_dev = nullptr; }
+    if (c->arena_host) { cudaFreeHost(c->arena_host); c->arena_host = nullptr; }
+    c->mirror_valid = false;
     c->have_window = false;
 }
 
@@ -221,9 +233,13 @@ extern "C" int ldso_b200_synchronize(ldso_b200_ctx *c) {
 #define LAUNCH_CHECK(c)                                            \
     do {                                                           \
         (c)->launches++;                                           \
+        (c)->mirror_valid = false;                                 \
         cudaError_t e__ = cudaGetLastError();                      \
         if (e__ != cudaSuccess) return (c)->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
     } while (0)
+
+#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+#define D2H(dst, src, bytes) do { if (dst) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
 
 // ---------------------------------------------------------------------------------------------- images
 static int ensure_slot(ldso_b200_ctx *c, int slot) {
@@ -261,6 +277,8 @@ extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *co
     int rc = ensure_slot(c, slot);
     if (rc) return rc;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->scratch, color, sizeof(float) * c->w * c->h, cudaMemcpyHostToDevice, c->stream));
+    if (!c->copy_done) CUDA_CHECK_RET(c, cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+    CUDA_CHECK_RET(c, cudaEventRecord(c->copy_done, c->stream));
     for (int l = 0; l < c->levels; l++) {
         const int npx = c->lw[l] * c->lh[l];
         k_pyr_intensity<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->scratch, l == 0 ? nullptr : c->img[slot][l - 1], c->img[slot][l],
@@ -269,7 +287,8 @@ extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *co
         k_pyr_gradients<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->img[slot][l], c->lw[l], c->lh[l]);
         LAUNCH_CHECK(c);
     }
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // the caller's buffer is free once the copy has landed; the pyramid kernels keep running asynchronously
+    CUDA_CHECK_RET(c, cudaEventSynchronize(c->copy_done));
     return LDSO_B200_OK;
 }
 
@@ -288,7 +307,7 @@ extern "C" int ldso_b200_download_frame_level(ldso_b200_ctx *c, int slot, int lv
 template<typename T>
 static int dev_alloc(ldso_b200_ctx *c, T **p, size_t count) {
     void *q = nullptr;
-    CUDA_CHECK_RET(c, cudaMalloc(&q, sizeof(T) * std::max<size_t>(count, 1)));
+    CUDA_CHECK_RET(c, cudaMalloc(&q, sizeof(T) * std::max<size_t>(count, 128)));   // empty windows still get valid buffers
     c->win_allocs.push_back(q);
     *p = (T *) q;
     return 0;
@@ -298,6 +317,63 @@ static int dev_upload(ldso_b200_ctx *c, T *dst, const T *src, size_t count) {
     if (count == 0) return 0;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, sizeof(T) * count, cudaMemcpyHostToDevice, c->stream));
     return 0;
+}
+
+// Window memory: ONE device arena + ONE pinned host mirror with the same layout.
+//   [topology | inputs ......................... | pt_idepth pt_idepth_zero | results ............ ]
+//    ^ uploaded only when the CSR changes         ^---- upload range ------^
+//                                                 ^----------- download range (one D2H) ----------^
+// so a set_window is one pack + one cudaMemcpyAsync + one memset, and reading points/residuals back is one copy.
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t) 255; return o; }
+};
+
+static int alloc_window(ldso_b200_ctx *c, int nP, int nR) {
+    DevWindow &d = c->d;
+    Arena A;
+    const size_t nPs = std::max(nP, 32), nRs = std::max(nR, 32);
+    auto &L = c->lay;
+    L.pt_host = A.take(4 * nPs); L.pt_res_begin = A.take(4 * (nPs + 1)); L.res_point = A.take(4 * nRs); L.res_target = A.take(4 * nRs);
+    L.topo_end = A.off;
+    L.pt_u = A.take(4 * nPs); L.pt_v = A.take(4 * nPs); L.pt_color = A.take(32 * nPs); L.pt_weights = A.take(32 * nPs);
+    L.pt_priorF = A.take(4 * nPs); L.pt_idepth_backup = A.take(4 * nPs); L.res_lin = A.take(nRs);
+    L.res_state = A.take(nRs);
+    L.dl_begin = A.off;
+    L.pt_idepth = A.take(4 * nPs); L.pt_idepth_zero = A.take(4 * nPs);
+    L.ul_end = A.off;
+    L.pt_step = A.take(4 * nPs); L.pt_HdiF = A.take(4 * nPs); L.pt_bdSumF = A.take(4 * nPs); L.pt_Hdd = A.take(4 * nPs);
+    L.pt_bd = A.take(4 * nPs); L.pt_Hcd = A.take(16 * nPs);
+    L.res_new_state = A.take(nRs); L.res_active = A.take(nRs); L.res_energy = A.take(4 * nRs); L.res_new_energy = A.take(4 * nRs);
+    L.res_new_energy_wo = A.take(4 * nRs); L.res_JpJdF = A.take(32 * nRs);
+    L.dl_end = A.off;
+    L.res_JpJdF_new = A.take(32 * nRs);
+    L.total = A.off;
+    // res_state is both an input and a result: it sits right before dl_begin and is fetched separately (tiny)
+    CUDA_CHECK_RET(c, cudaMalloc(&c->arena_dev, L.total));
+    CUDA_CHECK_RET(c, cudaMallocHost(&c->arena_host, L.total));
+    memset(c->arena_host, 0, L.total);
+    char *B = c->arena_dev;
+    d.pt_host = (int *) (B + L.pt_host); d.pt_res_begin = (int *) (B + L.pt_res_begin);
+    d.res_point = (int *) (B + L.res_point); d.res_target = (int *) (B + L.res_target);
+    d.pt_u = (float *) (B + L.pt_u); d.pt_v = (float *) (B + L.pt_v); d.pt_color = (float *) (B + L.pt_color);
+    d.pt_weights = (float *) (B + L.pt_weights); d.pt_priorF = (float *) (B + L.pt_priorF);
+    d.pt_idepth_backup = (float *) (B + L.pt_idepth_backup); d.res_lin = (uint8_t *) (B + L.res_lin);
+    d.res_state = (uint8_t *) (B + L.res_state);
+    d.pt_idepth = (float *) (B + L.pt_idepth); d.pt_idepth_zero = (float *) (B + L.pt_idepth_zero);
+    d.pt_step = (float *) (B + L.pt_step); d.pt_HdiF = (float *) (B + L.pt_HdiF); d.pt_bdSumF = (float *) (B + L.pt_bdSumF);
+    d.pt_Hdd = (float *) (B + L.pt_Hdd); d.pt_bd = (float *) (B + L.pt_bd); d.pt_Hcd = (float *) (B + L.pt_Hcd);
+    d.res_new_state = (uint8_t *) (B + L.res_new_state); d.res_active = (uint8_t *) (B + L.res_active);
+    d.res_energy = (float *) (B + L.res_energy); d.res_new_energy = (float *) (B + L.res_new_energy);
+    d.res_new_energy_wo = (float *) (B + L.res_new_energy_wo); d.res_JpJdF = (float *) (B + L.res_JpJdF);
+    d.res_JpJdF_new = (float *) (B + L.res_JpJdF_new);
+    // big arrays only the piecewise API / tests touch
+    int rc = 0;
+    rc |= dev_alloc(c, &d.res_J, (size_t) nR * 74);
+    rc |= dev_alloc(c, &d.res_proj, (size_t) nR * 16); rc |= dev_alloc(c, &d.res_cpt, (size_t) nR * 3);
+    rc |= dev_alloc(c, &d.res_toZero, (size_t) nR * 8);
+    rc |= dev_alloc(c, &c->pt_sel_dev, nP);
+    return rc ? LDSO_B200_ERR_CUDA : LDSO_B200_OK;
 }
 
 extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *win) {
@@ -313,16 +389,13 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     }
     if (nP > 0 && (win->res_begin[0] != 0 || win->res_begin[nP] != nR)) return c->fail(LDSO_B200_ERR_ARG, "res_begin does not cover the residual arrays");
     for (int r = 0; r < nR; r++) if (win->res_target[r] < 0 || win->res_target[r] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "res_target out of range");
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));     // the pinned mirror may still be in flight
     DevWindow &d = c->d;
-    // same topology as the resident window (same hosts / CSR / targets): keep every allocation and the derived
-    // work-item tables, only the point values and residual states are refreshed below.
     const bool same_topology = c->have_window && d.nP == nP && d.nR == nR && (int) c->h_pt_host.size() == nP && nP > 0 &&
                                std::equal(win->pt_host, win->pt_host + nP, c->h_pt_host.begin()) &&
                                std::equal(win->res_begin, win->res_begin + nP + 1, c->h_res_begin.begin()) &&
                                std::equal(win->res_target, win->res_target + nR, c->h_res_target.begin());
-    int *pt_host, *pt_res_begin, *res_point, *res_target;
-    int rc = 0;
+    auto &L = c->lay;
     if (!same_topology) {
         free_window(c);
         memset(&d, 0, sizeof(d));
@@ -331,65 +404,36 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
         c->h_res_begin.assign(win->res_begin, win->res_begin + nP + 1);
         if (nP == 0) c->h_res_begin.assign(1, 0);
         c->h_res_target.assign(win->res_target, win->res_target + nR);
-        rc |= dev_alloc(c, &pt_host, nP); rc |= dev_alloc(c, &pt_res_begin, nP + 1);
-        rc |= dev_alloc(c, &res_point, nR); rc |= dev_alloc(c, &res_target, nR);
-        rc |= dev_alloc(c, &d.pt_u, nP); rc |= dev_alloc(c, &d.pt_v, nP); rc |= dev_alloc(c, &d.pt_idepth, nP);
-        rc |= dev_alloc(c, &d.pt_idepth_zero, nP); rc |= dev_alloc(c, &d.pt_idepth_backup, nP); rc |= dev_alloc(c, &d.pt_step, nP);
-        rc |= dev_alloc(c, &d.pt_color, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_weights, (size_t) nP * 8); rc |= dev_alloc(c, &d.pt_priorF, nP);
-        rc |= dev_alloc(c, &d.pt_HdiF, nP); rc |= dev_alloc(c, &d.pt_bdSumF, nP); rc |= dev_alloc(c, &d.pt_Hcd, (size_t) nP * 4);
-        rc |= dev_alloc(c, &d.pt_Hdd, nP); rc |= dev_alloc(c, &d.pt_bd, nP);
-        rc |= dev_alloc(c, &d.res_state, nR); rc |= dev_alloc(c, &d.res_new_state, nR); rc |= dev_alloc(c, &d.res_active, nR);
-        rc |= dev_alloc(c, &d.res_lin, nR); rc |= dev_alloc(c, &d.res_energy, nR); rc |= dev_alloc(c, &d.res_new_energy, nR);
-        rc |= dev_alloc(c, &d.res_new_energy_wo, nR); rc |= dev_alloc(c, &d.res_JpJdF, (size_t) nR * 8);
-        rc |= dev_alloc(c, &d.res_JpJdF_new, (size_t) nR * 8); rc |= dev_alloc(c, &d.res_J, (size_t) nR * 74);
-        rc |= dev_alloc(c, &d.res_proj, (size_t) nR * 16); rc |= dev_alloc(c, &d.res_cpt, (size_t) nR * 3);
-        rc |= dev_alloc(c, &d.res_toZero, (size_t) nR * 8);
-        rc |= dev_alloc(c, &c->pt_sel_dev, nP);
-        if (rc) return LDSO_B200_ERR_CUDA;
-        d.pt_host = pt_host; d.pt_res_begin = pt_res_begin; d.res_point = res_point; d.res_target = res_target;
+        int rc = alloc_window(c, nP, nR);
+        if (rc) return rc;
         d.newest_offset = 0;
         d.newest_total = -1;   // derived
         c->derived_dirty = true;
-    } else {
-        pt_host = (int *) d.pt_host; pt_res_begin = (int *) d.pt_res_begin; res_point = (int *) d.res_point; res_target = (int *) d.res_target;
+        char *H = c->arena_host;
+        memcpy(H + L.pt_host, win->pt_host, 4 * (size_t) nP);
+        memcpy(H + L.pt_res_begin, c->h_res_begin.data(), 4 * ((size_t) nP + 1));
+        int *rp = (int *) (H + L.res_point);
+        for (int p = 0; p < nP; p++) for (int r = c->h_res_begin[p]; r < c->h_res_begin[p + 1]; r++) rp[r] = p;
+        memcpy(H + L.res_target, win->res_target, 4 * (size_t) nR);
     }
-
-    std::vector<int> h_res_point(nR);
-    for (int p = 0; p < nP; p++) for (int r = c->h_res_begin[p]; r < c->h_res_begin[p + 1]; r++) h_res_point[r] = p;
-    std::vector<float> priorF(nP);
+    // ---- pack the per-call inputs into the pinned mirror
+    char *H = c->arena_host;
+    memcpy(H + L.pt_u, win->pt_u, 4 * (size_t) nP); memcpy(H + L.pt_v, win->pt_v, 4 * (size_t) nP);
+    memcpy(H + L.pt_color, win->pt_color, 32 * (size_t) nP); memcpy(H + L.pt_weights, win->pt_weights, 32 * (size_t) nP);
+    float *priorF = (float *) (H + L.pt_priorF);
     for (int p = 0; p < nP; p++)   // PointHessian::takeData (PointHessian.h:112-117)
         priorF[p] = (win->pt_has_prior && win->pt_has_prior[p]) ? c->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0.f;
-    std::vector<uint8_t> st(nR, (uint8_t) LDSO_B200_RES_IN), lin(nR, 0);
-    if (win->res_state) st.assign(win->res_state, win->res_state + nR);
-    if (win->res_is_linearized) lin.assign(win->res_is_linearized, win->res_is_linearized + nR);
-
-    if (!same_topology) {
-        rc |= dev_upload(c, pt_host, win->pt_host, nP);
-        rc |= dev_upload(c, pt_res_begin, c->h_res_begin.data(), nP + 1);
-        rc |= dev_upload(c, res_point, h_res_point.data(), nR);
-        rc |= dev_upload(c, res_target, win->res_target, nR);
-    }
-    rc |= dev_upload(c, d.pt_u, win->pt_u, nP); rc |= dev_upload(c, d.pt_v, win->pt_v, nP);
-    rc |= dev_upload(c, d.pt_idepth, win->pt_idepth, nP); rc |= dev_upload(c, d.pt_idepth_zero, win->pt_idepth_zero, nP);
-    rc |= dev_upload(c, d.pt_idepth_backup, win->pt_idepth, nP);
-    rc |= dev_upload(c, d.pt_color, win->pt_color, (size_t) nP * 8); rc |= dev_upload(c, d.pt_weights, win->pt_weights, (size_t) nP * 8);
-    rc |= dev_upload(c, d.pt_priorF, priorF.data(), nP);
-    rc |= dev_upload(c, d.res_state, st.data(), nR); rc |= dev_upload(c, d.res_lin, lin.data(), nR);
-    if (win->res_toZeroF) rc |= dev_upload(c, d.res_toZero, win->res_toZeroF, (size_t) nR * 8);
-    if (rc) return LDSO_B200_ERR_CUDA;
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_step, 0, sizeof(float) * std::max(nP, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_HdiF, 0, sizeof(float) * std::max(nP, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_bdSumF, 0, sizeof(float) * std::max(nP, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.pt_Hcd, 0, sizeof(float) * 4 * std::max(nP, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_active, 0, std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_state, LDSO_B200_RES_OUTLIER, std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_energy, 0, sizeof(float) * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_energy, 0, sizeof(float) * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_new_energy_wo, 0, sizeof(float) * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_JpJdF, 0, sizeof(float) * 8 * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_JpJdF_new, 0, sizeof(float) * 8 * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * std::max(nR, 1), c->stream));
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // host vectors above go out of scope
+    memcpy(H + L.pt_idepth_backup, win->pt_idepth, 4 * (size_t) nP);
+    if (win->res_is_linearized) memcpy(H + L.res_lin, win->res_is_linearized, nR); else memset(H + L.res_lin, 0, std::max(nR, 1));
+    if (win->res_state) memcpy(H + L.res_state, win->res_state, nR); else memset(H + L.res_state, LDSO_B200_RES_IN, std::max(nR, 1));
+    memcpy(H + L.pt_idepth, win->pt_idepth, 4 * (size_t) nP); memcpy(H + L.pt_idepth_zero, win->pt_idepth_zero, 4 * (size_t) nP);
+    const size_t ul_begin = same_topology ? L.topo_end : 0;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_dev + ul_begin, H + ul_begin, L.ul_end - ul_begin, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->arena_dev + L.ul_end, 0, L.total - L.ul_end, c->stream));    // all result/state arrays
+    if (win->res_toZeroF && nR > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(d.res_toZero, win->res_toZeroF, 32 * (size_t) nR, cudaMemcpyHostToDevice, c->stream));
+    if (!same_topology) CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * (size_t) std::max(nR, 1), c->stream));
+    if (win->res_toZeroF) CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // pageable source
+    c->mirror_valid = false;
     c->have_window = true;
     return LDSO_B200_OK;
 }
@@ -435,6 +479,7 @@ static int build_derived(ldso_b200_ctx *c) {
     rc |= dev_alloc(c, &d.partials, (size_t) std::max(d.nItems, 1) * PART_STRIDE);
     rc |= dev_alloc(c, &d.item_stats, (size_t) std::max(d.nItems, 1) * 4);
     rc |= dev_alloc(c, &d.red, (size_t) RED_SELECT + std::max(d.newest_total, 1) + 16);
+    rc |= dev_alloc(c, &d.dbg, 32);
     if (rc) return LDSO_B200_ERR_CUDA;
     rc |= dev_upload(c, items_dev, items.data(), items.size());
     rc |= dev_upload(c, hib_dev, hib.data(), MAXF + 1);
@@ -565,7 +610,10 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
     LAUNCH_CHECK(c);
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // P (pageable std::vector) must be consumed before it goes out of scope; ws_host is pinned and only reused
+    // after the synchronize at the top of the next call
+    CUDA_CHECK_RET(c, cudaEventRecord(c->frames_copied, c->stream));
+    CUDA_CHECK_RET(c, cudaEventSynchronize(c->frames_copied));
     c->have_frames = true;
     if (prev_nF != nF) c->derived_dirty = true;    // work items / newest-frame slots depend on nF only
     return LDSO_B200_OK;
@@ -634,7 +682,6 @@ static int clear_select(ldso_b200_ctx *c) {   // multi-GPU: slots owned by other
         CUDA_CHECK_RET(c, cudaMemsetAsync(c->d.red + RED_SELECT, 0, sizeof(double) * c->d.newest_total, c->stream));
     return LDSO_B200_OK;
 }
-#define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
 extern "C" int ldso_b200_linearize_all(ldso_b200_ctx *c, int fixLinearization, int flags, double *energy_out) {
     if (!c) return LDSO_B200_ERR_ARG;
@@ -824,15 +871,27 @@ extern "C" int ldso_b200_get_energy(ldso_b200_ctx *c, double *energy, int *canbr
 
 #define D2H(dst, src, bytes) do { if (dst) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
 
+// one D2H of the contiguous result range into the pinned mirror (valid until the next launch)
+static int refresh_mirror(ldso_b200_ctx *c) {
+    if (c->mirror_valid) return LDSO_B200_OK;
+    auto &L = c->lay;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    c->mirror_valid = true;
+    return LDSO_B200_OK;
+}
+#define FROM_MIRROR(dst, off, bytes) do { if (dst) memcpy(dst, c->arena_host + (off), (bytes)); } while (0)
+
 extern "C" int ldso_b200_get_points(ldso_b200_ctx *c, float *idepth, float *idepth_zero, float *step, float *HdiF,
                                     float *bdSumF, float *Hdd, float *bd, float *Hcd4) {
     if (!c || !c->have_window) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
+    RET_IF(refresh_mirror(c));
     const size_t nP = c->d.nP;
-    D2H(idepth, c->d.pt_idepth, 4 * nP); D2H(idepth_zero, c->d.pt_idepth_zero, 4 * nP); D2H(step, c->d.pt_step, 4 * nP);
-    D2H(HdiF, c->d.pt_HdiF, 4 * nP); D2H(bdSumF, c->d.pt_bdSumF, 4 * nP); D2H(Hdd, c->d.pt_Hdd, 4 * nP); D2H(bd, c->d.pt_bd, 4 * nP);
-    D2H(Hcd4, c->d.pt_Hcd, 16 * nP);
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    auto &L = c->lay;
+    FROM_MIRROR(idepth, L.pt_idepth, 4 * nP); FROM_MIRROR(idepth_zero, L.pt_idepth_zero, 4 * nP); FROM_MIRROR(step, L.pt_step, 4 * nP);
+    FROM_MIRROR(HdiF, L.pt_HdiF, 4 * nP); FROM_MIRROR(bdSumF, L.pt_bdSumF, 4 * nP); FROM_MIRROR(Hdd, L.pt_Hdd, 4 * nP);
+    FROM_MIRROR(bd, L.pt_bd, 4 * nP); FROM_MIRROR(Hcd4, L.pt_Hcd, 16 * nP);
     return LDSO_B200_OK;
 }
 
@@ -841,12 +900,16 @@ extern "C" int ldso_b200_get_residuals(ldso_b200_ctx *c, uint8_t *state_state, u
                                        float *JpJdF8, float *J74, float *projectedTo16, float *centerProjectedTo3) {
     if (!c || !c->have_window) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
+    RET_IF(refresh_mirror(c));
     const size_t nR = c->d.nR;
-    D2H(state_state, c->d.res_state, nR); D2H(state_NewState, c->d.res_new_state, nR); D2H(state_energy, c->d.res_energy, 4 * nR);
-    D2H(state_NewEnergy, c->d.res_new_energy, 4 * nR); D2H(state_NewEnergyWithOutlier, c->d.res_new_energy_wo, 4 * nR);
-    D2H(isActive, c->d.res_active, nR); D2H(JpJdF8, c->d.res_JpJdF, 32 * nR); D2H(J74, c->d.res_J, 296 * nR);
-    D2H(projectedTo16, c->d.res_proj, 64 * nR); D2H(centerProjectedTo3, c->d.res_cpt, 12 * nR);
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    auto &L = c->lay;
+    FROM_MIRROR(state_state, L.res_state, nR); FROM_MIRROR(state_NewState, L.res_new_state, nR); FROM_MIRROR(state_energy, L.res_energy, 4 * nR);
+    FROM_MIRROR(state_NewEnergy, L.res_new_energy, 4 * nR); FROM_MIRROR(state_NewEnergyWithOutlier, L.res_new_energy_wo, 4 * nR);
+    FROM_MIRROR(isActive, L.res_active, nR); FROM_MIRROR(JpJdF8, L.res_JpJdF, 32 * nR);
+    if (J74 || projectedTo16 || centerProjectedTo3) {
+        D2H(J74, c->d.res_J, 296 * nR); D2H(projectedTo16, c->d.res_proj, 64 * nR); D2H(centerProjectedTo3, c->d.res_cpt, 12 * nR);
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    }
     return LDSO_B200_OK;
 }
 
@@ -877,6 +940,15 @@ extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *s
         if (adHTdeltaF8) memcpy(adHTdeltaF8 + 8 * q, W.adHTdeltaF[q], 32);
     }
     if (calib_value4) memcpy(calib_value4, W.calib.value, 32);
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_debug_clocks(ldso_b200_ctx *c, long long *out32) {
+    if (!c || !out32) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out32, c->ws_dev->dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (c->d.dbg) CUDA_CHECK_RET(c, cudaMemcpyAsync(out32 + 16, c->d.dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     return LDSO_B200_OK;
 }
 

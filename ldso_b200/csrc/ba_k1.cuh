@@ -81,6 +81,9 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (flags >> K1F_MODE_SHIFT) & 3;
 
+    int dbgi = 0;
+#define K1_STAMP() do { if (tid == 0 && blockIdx.x == 0) d.dbg[dbgi] = clock64(); dbgi++; } while (0)
+    K1_STAMP();
     // ---------------- phase 0: stage per-host constants, clear records
     for (int i = tid; i < MAXF * 32; i += K1_THREADS) {
         int t = i >> 5, k = i & 31;
@@ -103,31 +106,32 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         const int q = i / 9, k = i - q * 9;
         recs[q * REC + REC_ACTIVE + k] = 0.f;
     }
-    __syncthreads();
-
-    // ---------------- phase R: resubstitute + step, stage point inputs.
-    // R1: one thread per residual computes xAd[h,t] . JpJdF_r (EnergyFunctional.cc:539-542) into shared memory;
-    // R2: one thread per point folds them in residual-list order and applies the idepth step.
     const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
     const int nres = rend - rbeg;
     float *s_rdot = s_ptout;        // [nres <= pts_per_item*MAXF] reuse: s_ptout is not live before phase P
-    if (flags & K1F_APPLY_STEP) {
+    if (flags & K1F_APPLY_STEP) {   // R1 (no dependence on the staged constants: overlaps their load latency)
         for (int ri = tid; ri < nres; ri += K1_THREADS) {
             const int r = rbeg + ri;
             float s = 0.f;
             float act = 0.f;
             if (d.res_active[r]) {
                 const float4 j0 = *(const float4 *) (d.res_JpJdF + 8 * r), j1 = *(const float4 *) (d.res_JpJdF + 8 * r + 4);
-                const float *xa = s_xAd + d.res_target[r] * 8;
-                s += xa[0] * j0.x; s += xa[1] * j0.y; s += xa[2] * j0.z; s += xa[3] * j0.w;
-                s += xa[4] * j1.x; s += xa[5] * j1.y; s += xa[6] * j1.z; s += xa[7] * j1.w;
+                const float4 *xa = (const float4 *) ws->xAd[host * nF + d.res_target[r]];
+                const float4 x0 = xa[0], x1 = xa[1];
+                s += x0.x * j0.x; s += x0.y * j0.y; s += x0.z * j0.z; s += x0.w * j0.w;
+                s += x1.x * j1.x; s += x1.y * j1.y; s += x1.z * j1.z; s += x1.w * j1.w;
                 act = 1.f;
             }
             recs_dot(s_rdot, ri, 0) = s;
             recs_dot(s_rdot, ri, 1) = act;
         }
-        __syncthreads();
     }
+    __syncthreads();
+
+    K1_STAMP();   // 1: phase 0 done
+    // ---------------- phase R: resubstitute + step, stage point inputs.
+    // R1: one thread per residual computes xAd[h,t] . JpJdF_r (EnergyFunctional.cc:539-542) into shared memory;
+    // R2: one thread per point folds them in residual-list order and applies the idepth step.
     double my_sumNID = 0.0, my_numID = 0.0;
     if (tid < npts) {
         const int p = p0 + tid;
@@ -172,6 +176,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     }
     __syncthreads();
 
+    K1_STAMP();   // 2: phase R done
     // ---------------- phase A: one 8-lane group per residual
     const int grp = tid >> 3, idx = tid & 7;
     double my_energy = 0.0, my_nres = 0.0;
@@ -444,6 +449,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         }
     }
 
+    K1_STAMP();   // 3: phase A done
     // ---------------- item statistics: energy, active residual count, sum |idepth|, point count
     {
         double v0 = my_energy, v1 = my_nres, v2 = my_sumNID, v3 = my_numID;
@@ -464,6 +470,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     if (!(flags & K1F_ACCUMULATE)) return;
 
     float *part = d.partials + (size_t) item * PART_STRIDE;
+    K1_STAMP();   // 4: stats done
 
     // ---------------- phase B: top Hessian blocks, warp <-> target (AccumulatedTopHessian.cc:78-92)
     // 4 lane-slots of uniform entry type (no divergence): [tri 0..31] [tri 32..54] [TopRight 0..29] [BotRight 0..5]
@@ -505,6 +512,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         if (lane < 5) pt[91 + lane] = 0.f;
     }
 
+    K1_STAMP();   // 5: phase B done
     // ---------------- phase P: per-point sums (AccumulatedTopHessian.cc:94-116, AccumulatedSCHessian.cc:11-29)
     if (tid < npts) {
         const int pl = tid, p = p0 + pl;
@@ -540,6 +548,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     }
     __syncthreads();
 
+    K1_STAMP();   // 6: phase P done
     // ---------------- phase C: Schur complement accumulators (AccumulatedSCHessian.cc:30-49)
     {
         const int ty = tid >> 4, tx = tid & 15;      // 16x16 threads x (4x4) tile of the 64x64 matrix D_host
@@ -581,4 +590,5 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         else if (tid < 80) part[PART_HCC + (tid - 64)] = accX;
         else if (tid < 84) part[PART_BC + (tid - 80)] = accX;
     }
+    K1_STAMP();   // 7: phase C done
 }

@@ -39,7 +39,14 @@ __global__ void __launch_bounds__(256) k2a_reduce(DevWindow d, WinState *ws, int
     if (h < nF) {
         const int i0 = d.host_item_begin[h], i1 = d.host_item_begin[h + 1];
         const float *p = d.partials + (size_t) i0 * PART_STRIDE + e;
-        for (int i = i0; i < i1; i++, p += PART_STRIDE) s += (double) *p;
+        // four independent chains keep 4+ loads in flight; the order of the final fold is fixed (deterministic)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int i = i0;
+        for (; i + 3 < i1; i += 4, p += 4 * PART_STRIDE) {
+            s0 += (double) p[0]; s1 += (double) p[PART_STRIDE]; s2 += (double) p[2 * PART_STRIDE]; s3 += (double) p[3 * PART_STRIDE];
+        }
+        for (; i < i1; i++, p += PART_STRIDE) s0 += (double) *p;
+        s = (s0 + s1) + (s2 + s3);
     }
     d.red[g] = s;
 }
@@ -226,84 +233,73 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     }
     if ((int) blockIdx.x < nBlocks + nF) {
         if (!do_stitch) return;
-        // ---- calibration rows of frame a and b segments
+        // ---- calibration rows of frame a and its b segments: 80 outputs, 8 lanes per output (lane <-> other frame),
+        // every lane issues its 32 independent loads at once, then a 3-step shuffle fold.
         const int a = blockIdx.x - nBlocks;
-        if (tid < 32) {                 // H_A[a, c]  (8x4)
-            const int r = tid >> 2, c = tid & 3;
+        for (int o8 = tid; o8 < 80 * 8; o8 += K2B_THREADS) {
+            const int o = o8 >> 3, t = o8 & 7;
             double s = 0.0;
-            for (int t = 0; t < nF; t++) {
-                if (t == a) continue;
+            if (t < nF && t != a) {
                 const double *AH = ws->adHost[a + nF * t], *AT = ws->adTarget[t + nF * a];
-                for (int i = 0; i < 8; i++) {
-                    s += AH[r * 8 + i] * top_elem(red, a, t, 4 + i, c);
-                    s += AT[r * 8 + i] * top_elem(red, t, a, 4 + i, c);
+                if (o < 32) {                 // H_A[a, c]
+                    const int r = o >> 2, c = o & 3;
+                    for (int i = 0; i < 8; i++) s += AH[r * 8 + i] * top_elem(red, a, t, 4 + i, c) + AT[r * 8 + i] * top_elem(red, t, a, 4 + i, c);
+                } else if (o < 40) {          // b_A[a]
+                    const int r = o - 32;
+                    for (int i = 0; i < 8; i++) s += AH[r * 8 + i] * top_elem(red, a, t, 4 + i, 12) + AT[r * 8 + i] * top_elem(red, t, a, 4 + i, 12);
+                } else if (o < 72) {          // H_sc[a, c]
+                    const int r = (o - 40) >> 2, c = (o - 40) & 3;
+                    const double *Eat = red + a * PART_USED + PART_E + t * 32, *Eta = red + t * PART_USED + PART_E + a * 32;
+                    for (int i = 0; i < 8; i++) s += AH[r * 8 + i] * Eat[i * 4 + c] + AT[r * 8 + i] * Eta[i * 4 + c];
+                } else {                      // b_sc[a]
+                    const int r = o - 72;
+                    const double *Bat = red + a * PART_USED + PART_EB + t * 8, *Bta = red + t * PART_USED + PART_EB + a * 8;
+                    for (int i = 0; i < 8; i++) s += AH[r * 8 + i] * Bat[i] + AT[r * 8 + i] * Bta[i];
                 }
             }
-            sb.H_A[(size_t) c * n + (CPARS + 8 * a + r)] = s;
-            sb.H_A[(size_t) (CPARS + 8 * a + r) * n + c] = s;
-        } else if (tid < 40) {          // b_A[a]
-            const int r = tid - 32;
-            double s = 0.0;
-            for (int t = 0; t < nF; t++) {
-                if (t == a) continue;
-                const double *AH = ws->adHost[a + nF * t], *AT = ws->adTarget[t + nF * a];
-                for (int i = 0; i < 8; i++) {
-                    s += AH[r * 8 + i] * top_elem(red, a, t, 4 + i, 12);
-                    s += AT[r * 8 + i] * top_elem(red, t, a, 4 + i, 12);
-                }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (t == 0) {
+                if (o < 32) {
+                    const int r = o >> 2, c = o & 3;
+                    sb.H_A[(size_t) c * n + (CPARS + 8 * a + r)] = s;
+                    sb.H_A[(size_t) (CPARS + 8 * a + r) * n + c] = s;
+                } else if (o < 40) sb.b_A[CPARS + 8 * a + (o - 32)] = s;
+                else if (o < 72) {
+                    const int r = (o - 40) >> 2, c = (o - 40) & 3;
+                    sb.H_sc[(size_t) c * n + (CPARS + 8 * a + r)] = s;
+                    sb.H_sc[(size_t) (CPARS + 8 * a + r) * n + c] = s;
+                } else sb.b_sc[CPARS + 8 * a + (o - 72)] = s;
             }
-            sb.b_A[CPARS + 8 * a + r] = s;
-        } else if (tid >= 64 && tid < 96) {   // H_sc[a, c]
-            const int r = (tid - 64) >> 2, c = (tid - 64) & 3;
-            double s = 0.0;
-            for (int j = 0; j < nF; j++) {
-                const double *AH = ws->adHost[a + nF * j], *AT = ws->adTarget[j + nF * a];
-                const double *Eaj = red + a * PART_USED + PART_E + j * 32;
-                const double *Eja = red + j * PART_USED + PART_E + a * 32;
-                for (int i = 0; i < 8; i++) {
-                    s += AH[r * 8 + i] * Eaj[i * 4 + c];
-                    s += AT[r * 8 + i] * Eja[i * 4 + c];
-                }
-            }
-            sb.H_sc[(size_t) c * n + (CPARS + 8 * a + r)] = s;
-            sb.H_sc[(size_t) (CPARS + 8 * a + r) * n + c] = s;
-        } else if (tid >= 96 && tid < 104) {  // b_sc[a]
-            const int r = tid - 96;
-            double s = 0.0;
-            for (int j = 0; j < nF; j++) {
-                const double *AH = ws->adHost[a + nF * j], *AT = ws->adTarget[j + nF * a];
-                const double *Baj = red + a * PART_USED + PART_EB + j * 8;
-                const double *Bja = red + j * PART_USED + PART_EB + a * 8;
-                for (int i = 0; i < 8; i++) {
-                    s += AH[r * 8 + i] * Baj[i];
-                    s += AT[r * 8 + i] * Bja[i];
-                }
-            }
-            sb.b_sc[CPARS + 8 * a + r] = s;
         }
         return;
     }
     if ((int) blockIdx.x == nBlocks + nF) {
         if (!do_stitch) return;
-        // ---- calibration corner
-        if (tid < 16) {
-            const int r = tid >> 2, c = tid & 3;
+        // ---- calibration corner: 20 outputs x 8 lanes (lane <-> host frame)
+        if (tid < 20 * 8) {
+            const int o = tid >> 3, h = tid & 7;
             double sA = 0.0, sS = 0.0;
-            for (int h = 0; h < nF; h++) {
-                for (int t = 0; t < nF; t++) if (t != h) sA += top_elem(red, h, t, r, c);
-                sS += red[h * PART_USED + PART_HCC + r * 4 + c];
+            if (h < nF) {
+                if (o < 16) {
+                    const int r = o >> 2, c = o & 3;
+                    for (int t = 0; t < nF; t++) if (t != h) sA += top_elem(red, h, t, r, c);
+                    sS = red[h * PART_USED + PART_HCC + r * 4 + c];
+                } else {
+                    const int r = o - 16;
+                    for (int t = 0; t < nF; t++) if (t != h) sA += top_elem(red, h, t, r, 12);
+                    sS = red[h * PART_USED + PART_BC + r];
+                }
             }
-            sb.H_A[(size_t) c * n + r] = sA;
-            sb.H_sc[(size_t) c * n + r] = sS;
-        } else if (tid < 20) {
-            const int r = tid - 16;
-            double sA = 0.0, sS = 0.0;
-            for (int h = 0; h < nF; h++) {
-                for (int t = 0; t < nF; t++) if (t != h) sA += top_elem(red, h, t, r, 12);
-                sS += red[h * PART_USED + PART_BC + r];
+            for (int m = 1; m < 8; m <<= 1) { sA += __shfl_xor_sync(0xffffffffu, sA, m); sS += __shfl_xor_sync(0xffffffffu, sS, m); }
+            if (h == 0) {
+                if (o < 16) {
+                    const int r = o >> 2, c = o & 3;
+                    sb.H_A[(size_t) c * n + r] = sA;
+                    sb.H_sc[(size_t) c * n + r] = sS;
+                } else { sb.b_A[o - 16] = sA; sb.b_sc[o - 16] = sS; }
             }
-            sb.b_A[r] = sA;
-            sb.b_sc[r] = sS;
         }
         return;
     }

@@ -18,9 +18,10 @@
 #define K3F_SOLVE 1
 #define K3F_STEP 2
 #define K3F_BACKUP 4
-#define K3_THREADS 256
+#define K3_THREADS 512
 #define K3_LD (MAXN + 1)
 #define K3_NB 8
+#define K3_WPLD (MAXN + 2)      // Wp is [K3_NB][K3_WPLD] (column of the panel major): conflict-free for consecutive rows
 
 struct K3Frames {       // shared-memory staging of the mutable window records
     FrameDev fr[MAXF];
@@ -65,7 +66,7 @@ __device__ void stage_out(const K3Frames *S, WinState *ws) {
 // FrameHessian::setState (FrameHessian.h:78-91), FrameFramePrecalc::Set for all pairs (FrameFramePrecalc.cc:6-35),
 // EnergyFunctional::setDeltaF frame part (EnergyFunctional.cc:403-429). Frame records live in shared memory (S);
 // the pair records are written to global. Called by all threads of a CTA with >= 128 threads.
-__device__ void frames_refresh(K3Frames *S, WinState *ws) {
+__device__ void frames_refresh(K3Frames *S, WinState *ws, bool full) {
     const int nF = ws->nF, tid = threadIdx.x;
     if (tid < nF) {
         FrameDev &f = S->fr[tid];
@@ -88,21 +89,29 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws) {
     if (tid < nF * nF) {
         const int h = tid % nF, t = tid / nF;
         const FrameDev &fh = S->fr[h], &ft = S->fr[t];
-        PairRec pc;
-        PairRecFull pf;
-        double R0[9], t0[3], R[9], tt[3];
-        se3_mul_inv(ft.evalR, ft.evalT, fh.evalR, fh.evalT, R0, t0);
+        PairRec &pc = ws->pair[h + nF * t];
+        PairRecFull &pf = ws->pairFull[h + nF * t];
+        if (full) {     // eval-point (FEJ) part: constant while the window's linearisation point is fixed
+            double R0[9], t0[3];
+            se3_mul_inv(ft.evalR, ft.evalT, fh.evalR, fh.evalT, R0, t0);
+            for (int i = 0; i < 9; i++) pc.R0[i] = (float) R0[i];
+            for (int i = 0; i < 3; i++) pc.t0[i] = (float) t0[i];
+            pc.b0 = (float) (fh.state_zero[7] * (double) SCALE_B);
+            pc.pad[0] = pc.pad[1] = pc.pad[2] = pc.pad[3] = 0.f;
+        }
+        double R[9], tt[3];
         se3_mul_inv(ft.preR, ft.preT, fh.preR, fh.preT, R, tt);
         float Rf[9], tf[3];
-        for (int i = 0; i < 9; i++) { pc.R0[i] = (float) R0[i]; Rf[i] = (float) R[i]; pf.RTll[i] = Rf[i]; }
-        for (int i = 0; i < 3; i++) { pc.t0[i] = (float) t0[i]; tf[i] = (float) tt[i]; pf.tTll[i] = tf[i]; }
+        for (int i = 0; i < 9; i++) { Rf[i] = (float) R[i]; pf.RTll[i] = Rf[i]; }
+        for (int i = 0; i < 3; i++) { tf[i] = (float) tt[i]; pf.tTll[i] = tf[i]; }
         pc.distanceLL = (float) sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
         const CalibDev &c = S->calib;
         float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
-        float Ki[9], tmp[9];
+        float Ki[9], tmp[9], KRKi[9];
         m33f_inverse(K, Ki);
         m33f_mul(K, Rf, tmp);
-        m33f_mul(tmp, Ki, pc.KRKi);
+        m33f_mul(tmp, Ki, KRKi);
+        for (int i = 0; i < 9; i++) pc.KRKi[i] = KRKi[i];
         for (int i = 0; i < 3; i++) {
             float s = K[i * 3 + 0] * tf[0];
             s += K[i * 3 + 1] * tf[1];
@@ -117,10 +126,6 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws) {
         const float aa = expf(at - ah) * eT / eF;
         pc.aff[0] = aa;
         pc.aff[1] = bt - aa * bh;
-        pc.b0 = (float) (fh.state_zero[7] * (double) SCALE_B);
-        pc.pad[0] = pc.pad[1] = pc.pad[2] = pc.pad[3] = 0.f;
-        ws->pair[h + nF * t] = pc;
-        ws->pairFull[h + nF * t] = pf;
     }
     // adHTdeltaF (EnergyFunctional.cc:406-414): one (pair, column) output per thread pass
     for (int o = tid; o < nF * nF * 8; o += blockDim.x) {
@@ -138,14 +143,14 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws) {
 __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
     __shared__ K3Frames S;
     stage_in(&S, ws);
-    frames_refresh(&S, ws);
+    frames_refresh(&S, ws, true);
     stage_out(&S, ws);
 }
 
 // Factor the bs x bs diagonal block at (k0,k0) in place (lower): L below the diagonal (unit), D on it.
 // Executed by ONE WARP: lane j < 8 keeps row j of the block in registers; a step is one broadcast of the pivot,
 // one reciprocal, and 7-k shuffles of the unscaled column. (L = W * (1/d): <= 1 ulp from Eigen's W / d.)
-__device__ __forceinline__ void ldlt_diag_block_warp(double *A, int k0, int bs, int lane) {
+__device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int bs, int lane) {
     const unsigned FULL = 0xffffffffu;
     double a[K3_NB];
     const int row = lane & 7;
@@ -156,7 +161,8 @@ __device__ __forceinline__ void ldlt_diag_block_warp(double *A, int k0, int bs, 
     for (int k = 0; k < K3_NB; k++) {
         const double dk = __shfl_sync(FULL, a[k], k);
         const bool valid = fabs(dk) > 0.0;
-        const double inv = valid ? 1.0 / dk : 1.0;
+        const double inv = valid ? __drcp_rn(dk) : 1.0;
+        if (lane == 0 && k < bs) vinv[k0 + k] = inv;
         const double w = a[k];                      // unscaled column entry of this lane's row (rows > k)
         const double l = w * inv;
 #pragma unroll
@@ -206,18 +212,28 @@ __device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, in
 __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
     extern __shared__ double sm3[];
     double *A0 = sm3;                       // [n][K3_LD] row-major assembled matrix
-    double *A = A0 + MAXN * K3_LD;          // permuted copy, factorised in place
-    double *Wp = A + MAXN * K3_LD;          // [MAXN][K3_NB] panel W = L*D of the current block step
-    double *vb = Wp + MAXN * K3_NB;         // rhs / solution
+    double *A = A0 + MAXN * K3_LD;          // permuted copy (+ rhs as row n), factorised in place
+    double *Wp = A + (MAXN + 1) * K3_LD;    // [K3_NB][K3_WPLD] panel W = L*D of the current block step
+    double *vinv = Wp + K3_NB * K3_WPLD;    // [MAXN] reciprocal pivots
+    double *vb = vinv + MAXN;               // rhs / solution
     double *vS = vb + MAXN;                 // SVecI
     double *vd = vS + MAXN;                 // delta / temp
     double *vx = vd + MAXN;                 // x
     int *perm = (int *) (vx + MAXN);        // [MAXN]
     K3Frames *S = (K3Frames *) (perm + MAXN + 2);
+    double *sPns = (double *) (S + 1);      // [n*n] null-space projector
     const int nF = ws->nF, n = ws->n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int iteration = *iteration_dev;
 
+    // NNpiTS is needed at the very end: start copying it into shared memory now (fire-and-forget stores, the
+    // L2 round trip overlaps the assembly and the factorisation)
+    if ((flags & K3F_SOLVE) && iteration >= 2)
+        for (int e = tid; e < n * n; e += K3_THREADS) sPns[e] = sb.Pns[e];
+    int dbgi = 0;
+#define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clock64(); dbgi++; } while (0)
+    K3_STAMP();
     stage_in(S, ws);
+    K3_STAMP();
 
     if (flags & K3F_BACKUP) {
         if (tid < nF) for (int i = 0; i < 10; i++) S->fr[tid].state_backup[i] = S->fr[tid].state[i];
@@ -232,33 +248,88 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         // HFinal_top = HL + HM + HA ; lastHS = HFinal_top - H_sc ; diag *= (1+lambda) ; HFinal_top -= H_sc/(1+lambda)
         // (:283-291)  — one pass, all loads independent
         const double inv1l = 1.0 / (1.0 + lambda);
-        for (int e = tid; e < n * n; e += K3_THREADS) {
-            const int r = e % n, c = e / n;
-            const double hsc = sb.H_sc[e];
-            double v = sb.H_A[e] + sb.HM[e];
-            if (r == c) v += (r < CPARS) ? ws->cPrior[r] : S->fr[(r - CPARS) >> 3].prior[(r - CPARS) & 7];
-            sb.lastHS[e] = v - hsc;
-            if (r == c) v *= (1 + lambda);
-            A0[r * K3_LD + c] = v - hsc * inv1l;
-        }
-        // bFinal_top = bL + (bM + HM*delta) + bA - b_sc  (:257,284): warp per row group, coalesced over columns
-        for (int r = warp; r < n; r += K3_THREADS / 32) {
-            double s = 0.0;
-            for (int c = lane; c < n; c += 32) s += sb.HM[(size_t) c * n + r] * vd[c];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) {
-                double bl;
-                if (r < CPARS) bl = ws->cPrior[r] * (double) S->calib.cDeltaF[r];
-                else {
-                    const FrameDev &f = S->fr[(r - CPARS) >> 3];
-                    bl = f.prior[(r - CPARS) & 7] * f.delta_prior[(r - CPARS) & 7];
+        {
+            // all global loads of this phase are issued before the first dependent use / global store (the stores to
+            // lastHS would otherwise fence the loads of the next column: one L2 round trip per column)
+            constexpr int NC = (MAXN + K3_THREADS / 32 - 1) / (K3_THREADS / 32), NR = (MAXN + 31) / 32;
+            // (1) bM + HM*delta: rows of HM and the b vectors
+            double hmrow[NC][NR], brow[NC][3], bsum[NC];
+#pragma unroll
+            for (int ci = 0; ci < NC; ci++) {
+                const int r = warp + ci * (K3_THREADS / 32);
+#pragma unroll
+                for (int cc = 0; cc < NR; cc++) {
+                    const int c = lane + 32 * cc;
+                    hmrow[ci][cc] = (r < n && c < n) ? sb.HM[(size_t) c * n + r] : 0.0;
                 }
-                const double bf = bl + (sb.bM[r] + s) + sb.b_A[r] - sb.b_sc[r];
-                vb[r] = bf;
-                sb.lastbS[r] = bf;
+                brow[ci][0] = (r < n) ? sb.bM[r] : 0.0;
+                brow[ci][1] = (r < n) ? sb.b_A[r] : 0.0;
+                brow[ci][2] = (r < n) ? sb.b_sc[r] : 0.0;
+            }
+#pragma unroll
+            for (int ci = 0; ci < NC; ci++) {
+                double s = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < NR; cc++) {
+                    const int c = lane + 32 * cc;
+                    if (c < n) s += hmrow[ci][cc] * vd[c];
+                }
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                bsum[ci] = s;
+            }
+            // (2) the matrices
+            double ha[NC][NR], hm[NC][NR], hs[NC][NR];
+#pragma unroll
+            for (int ci = 0; ci < NC; ci++) {
+                const int c = warp + ci * (K3_THREADS / 32);
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) {
+                    const int r = lane + 32 * rr;
+                    const bool on = (c < n && r < n);
+                    const int e = on ? c * n + r : 0;
+                    ha[ci][rr] = on ? sb.H_A[e] : 0.0;
+                    hm[ci][rr] = on ? sb.HM[e] : 0.0;
+                    hs[ci][rr] = on ? sb.H_sc[e] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int ci = 0; ci < NC; ci++) {
+                const int c = warp + ci * (K3_THREADS / 32);
+                if (c < n) {
+                    const double pc = (c < CPARS) ? ws->cPrior[c] : S->fr[(c - CPARS) >> 3].prior[(c - CPARS) & 7];
+#pragma unroll
+                    for (int rr = 0; rr < NR; rr++) {
+                        const int r = lane + 32 * rr;
+                        if (r < n) {
+                            const int e = c * n + r;
+                            double v = ha[ci][rr] + hm[ci][rr];
+                            if (r == c) v += pc;
+                            sb.lastHS[e] = v - hs[ci][rr];
+                            if (r == c) v *= (1 + lambda);
+                            A0[r * K3_LD + c] = v - hs[ci][rr] * inv1l;
+                        }
+                    }
+                }
+            }
+            // bFinal_top = bL + (bM + HM*delta) + bA - b_sc  (:257,284)
+#pragma unroll
+            for (int ci = 0; ci < NC; ci++) {
+                const int r = warp + ci * (K3_THREADS / 32);
+                if (lane == 0 && r < n) {
+                    double bl;
+                    if (r < CPARS) bl = ws->cPrior[r] * (double) S->calib.cDeltaF[r];
+                    else {
+                        const FrameDev &f = S->fr[(r - CPARS) >> 3];
+                        bl = f.prior[(r - CPARS) & 7] * f.delta_prior[(r - CPARS) & 7];
+                    }
+                    const double bf = bl + (brow[ci][0] + bsum[ci]) + brow[ci][1] - brow[ci][2];
+                    vb[r] = bf;
+                    sb.lastbS[r] = bf;
+                }
             }
         }
         __syncthreads();
+        K3_STAMP();   // 2: assembled
         // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
         if (tid < n) vS[tid] = 1.0 / sqrt(A0[tid * K3_LD + tid] + 10.0);
         __syncthreads();
@@ -273,72 +344,73 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         }
         __syncthreads();
         // A = P (S A0 S) P^T, b' = P S b
-        for (int e = tid; e < n * n; e += K3_THREADS) {
-            const int r = e / n, c = e % n;
-            const int pr = perm[r], pc = perm[c];
-            A[r * K3_LD + c] = A0[pr * K3_LD + pc] * vS[pr] * vS[pc];
+        for (int r = warp; r < n; r += K3_THREADS / 32) {
+            const int pr = perm[r];
+            const double sr = vS[pr];
+#pragma unroll
+            for (int cc = 0; cc < (MAXN + 31) / 32; cc++) {
+                const int c = lane + 32 * cc;
+                if (c < n) {
+                    const int pc = perm[c];
+                    A[r * K3_LD + c] = A0[pr * K3_LD + pc] * sr * vS[pc];
+                }
+            }
         }
         if (tid < n) vd[tid] = vb[perm[tid]] * vS[perm[tid]];
         __syncthreads();
         if (tid < n) vb[tid] = vd[tid];
         __syncthreads();
 
-        // ---- blocked in-place LDL^T (lower)
+        K3_STAMP();   // 3: scaled+permuted
+        // ---- blocked in-place LDL^T (lower) of the matrix AUGMENTED with the right-hand side as row n:
+        // the panel/trailing steps then leave D^-1 L^-1 b in that row, i.e. the forward solve comes for free.
+        if (tid < n) A[n * K3_LD + tid] = vb[tid];
+        __syncthreads();
         for (int k0 = 0; k0 < n; k0 += K3_NB) {
             const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
-            if (warp == 0) ldlt_diag_block_warp(A, k0, bs, lane);
+            if (warp == 0) ldlt_diag_block_warp(A, vinv, k0, bs, lane);
             __syncthreads();
-            if (tid < n - m0) {      // panel row i: w = L*D (unscaled), l = L
+            if (tid < n + 1 - m0) {      // panel row i (incl. the rhs row n): w = L*D (unscaled), l = L
                 const int i = m0 + tid;
-                double w[K3_NB], l[K3_NB];
+                double w[K3_NB];
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) {
                     if (c < bs) {
-                        double s = A[i * K3_LD + k0 + c];
+                        double s0 = A[i * K3_LD + k0 + c], s1 = 0.0;
 #pragma unroll
-                        for (int j = 0; j < c; j++) s -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
-                        w[c] = s;
-                        const double d = A[(k0 + c) * K3_LD + k0 + c];
-                        l[c] = (fabs(d) > 0.0) ? s * (1.0 / d) : s;
-                    } else { w[c] = 0.0; l[c] = 0.0; }
+                        for (int j = 0; j < c; j += 2) s0 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
+#pragma unroll
+                        for (int j = 1; j < c; j += 2) s1 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
+                        w[c] = s0 + s1;
+                    } else w[c] = 0.0;
                 }
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) {
-                    if (c < bs) A[i * K3_LD + k0 + c] = l[c];
-                    Wp[i * K3_NB + c] = w[c];
+                    if (c < bs) A[i * K3_LD + k0 + c] = w[c] * vinv[k0 + c];
+                    Wp[c * K3_WPLD + i] = w[c];
                 }
             }
             __syncthreads();
-            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= i < n
-            for (int i = m0 + (tid >> 4); i < n; i += 16) {
+            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= min(i, n-1), i <= n
+            for (int i = m0 + (tid >> 4); i <= n; i += K3_THREADS / 16) {
                 double li[K3_NB];
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) li[c] = (c < bs) ? A[i * K3_LD + k0 + c] : 0.0;
-                for (int j = m0 + (tid & 15); j <= i; j += 16) {
-                    double s = 0.0;
+                const int jmax = min(i, n - 1);
+                for (int j = m0 + (tid & 15); j <= jmax; j += 16) {
+                    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < K3_NB; c++) s += li[c] * Wp[j * K3_NB + c];
-                    A[i * K3_LD + j] -= s;
+                    for (int c = 0; c < K3_NB; c += 2) { s0 += li[c] * Wp[c * K3_WPLD + j]; s1 += li[c + 1] * Wp[(c + 1) * K3_WPLD + j]; }
+                    A[i * K3_LD + j] -= (s0 + s1);
                 }
             }
             __syncthreads();
         }
-        // ---- forward solve L z = b (unit lower), blocked
-        for (int k0 = 0; k0 < n; k0 += K3_NB) {
-            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
-            if (warp == 0) trsv_lower_warp(A, vb, k0, bs, lane);
-            __syncthreads();
-            if (tid < n - m0) {
-                const int i = m0 + tid;
-                double s = vb[i];
-                for (int c = 0; c < bs; c++) s -= A[i * K3_LD + k0 + c] * vb[k0 + c];
-                vb[i] = s;
-            }
-            __syncthreads();
-        }
+        K3_STAMP();   // 4: factorised
+        // row n now holds D^-1 L^-1 b (unscaled where the pivot was invalid): Eigen's solve uses the pseudo-inverse of D
         if (tid < n) {
             const double dk = A[tid * K3_LD + tid];
-            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? vb[tid] / dk : 0.0;     // Eigen's pseudo-inverse of D
+            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? A[n * K3_LD + tid] : 0.0;
         }
         __syncthreads();
         // ---- backward solve L^T x = z, blocked from the last block up
@@ -355,6 +427,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             if (warp == 0) trsv_lower_t_warp(A, vb, k0, bs, lane);
             __syncthreads();
         }
+        K3_STAMP();   // 5: back-substituted
         if (tid < n) vx[perm[tid]] = vb[tid];
         __syncthreads();
         if (tid < n) vx[tid] *= vS[tid];
@@ -363,7 +436,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         if (iteration >= 2) {
             for (int r = warp; r < n; r += K3_THREADS / 32) {
                 double s = 0.0;
-                for (int c = lane; c < n; c += 32) s += sb.Pns[(size_t) r * n + c] * vx[c];   // NNpiTS is symmetric
+                for (int c = lane; c < n; c += 32) s += sPns[r * n + c] * vx[c];      // NNpiTS is symmetric
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0) vd[r] = s;
             }
@@ -371,6 +444,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             if (tid < n) vx[tid] -= vd[tid];
             __syncthreads();
         }
+        K3_STAMP();   // 6: orthogonalised
         if (tid < n) sb.lastX[tid] = vx[tid];
         // resubstituteF_MT frame part (:495-507)
         if (tid < CPARS) {
@@ -392,6 +466,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         }
         __syncthreads();
     }
+    K3_STAMP();   // 7: xAd done
     if (flags & K3F_STEP) {
         // doStepFromBackup(1,1,1,1,1), frame/calib part (FullSystem.cc:1588-1597,1617-1627)
         if (tid == 0) {
@@ -417,9 +492,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             for (int i = 0; i < 10; i++) f.state[i] = f.state_backup[i] + f.step[i];
         }
         __syncthreads();
-        frames_refresh(S, ws);
+        frames_refresh(S, ws, false);
     }
+    K3_STAMP();   // 8: frames refreshed
     stage_out(S, ws);
+    K3_STAMP();   // 9
     if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
 }
-#define K3_SMEM_BYTES ((2 * MAXN * K3_LD + MAXN * K3_NB + 4 * MAXN) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + 64)
+#define K3_SMEM_BYTES (((2 * MAXN + 1) * K3_LD + K3_NB * K3_WPLD + 5 * MAXN) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 64)

@@ -113,10 +113,10 @@ struct WinState {
     ldso_b200_settings S;
     FrameDev fr[MAXF];
     CalibDev calib;
-    PairRec pair[MAXPAIR];            // index h + nF*t
+    alignas(16) PairRec pair[MAXPAIR];            // index h + nF*t
     PairRecFull pairFull[MAXPAIR];
-    float adHTdeltaF[MAXPAIR][8];     // index h + nF*t
-    float xAd[MAXPAIR][8];            // index h*nF + t  (EnergyFunctional.cc:503)
+    alignas(16) float adHTdeltaF[MAXPAIR][8];     // index h + nF*t
+    alignas(16) float xAd[MAXPAIR][8];            // index h*nF + t  (EnergyFunctional.cc:503)
     float cstep[4];
     double adHost[MAXPAIR][64], adTarget[MAXPAIR][64];   // index h + nF*t, 8x8 row-major
     float adHostF[MAXPAIR][64], adTargetF[MAXPAIR][64];
@@ -128,6 +128,7 @@ struct WinState {
     int canbreak;
     int iteration_count;
     float sumNID, numID;
+    long long dbg[32];               // clock64() phase stamps of the last K3 (development aid)
 };
 
 // device pointers of the flattened window
@@ -151,6 +152,7 @@ struct DevWindow {
     double *red;                  // reduced buffer (RED_* layout)
     int newest_offset, newest_total;
     int pts_per_item;
+    long long *dbg;               // clock64() phase stamps of K1's CTA 0 (development aid)
 };
 
 #define CUDA_CHECK_RET(ctx, call)                                                         \

@@ -1,0 +1,73 @@
+"""Sharded (multi-GPU) GN iteration vs the single-context result, run under torchrun (one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_check.py
+Every rank holds a point shard; one NCCL all-reduce of the reduced system per GN step. Rank 0 also runs the
+full window on its own GPU in a second context and compares. Exit code != 0 on mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ldso_b200 import capi, synth  # noqa: E402
+from tests.parity import rel_err  # noqa: E402
+
+
+class _DevBuf:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    full = synth.make_window(nF=6, pts_per_frame=120, w=320, h=240, seed=17)
+    win = synth.shard_window(full, rank, world)
+    ctx = capi.Context(win.w, win.h, win.levels, device=lr)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.load_synth_window(win)
+    counts = [int(np.sum(synth.shard_window(full, r, world).res_target == full.nF - 1)) for r in range(world)]
+    ctx.set_shard(int(np.sum(counts[:rank])), int(np.sum(counts)))
+    ptr, n = ctx.reduce_buffer()
+    red = torch.as_tensor(_DevBuf(ptr, n), device=f"cuda:{lr}")
+    sols, energies = [], []
+    for it in range(-1, 3):
+        ctx.gn_phase_a(it)
+        dist.all_reduce(red)
+        ctx.gn_phase_b()
+        if it >= 0:
+            sols.append(ctx.last_solution())
+        energies.append(ctx.energy()[0])
+    pts = ctx.points()
+    ok = True
+    if rank == 0:
+        ref = capi.Context(full.w, full.h, full.levels, device=lr)
+        ref.load_synth_window(full)
+        e_ref = [ref.optimize_begin()]
+        P = ref.nullspace_projector()
+        I = np.eye(P.shape[0])
+        for it in range(3):
+            ref.gn_iterations(it, 1)
+            s = ref.last_solution()
+            e_ref.append(ref.energy()[0])
+            eh = rel_err(sols[it]["lastHS"], s["lastHS"]); eb = rel_err(sols[it]["lastbS"], s["lastbS"])
+            ex = rel_err((I - P) @ sols[it]["lastX"], (I - P) @ s["lastX"])
+            print(f"it{it}: lastHS {eh:.2e} lastbS {eb:.2e} lastX(gauge-proj) {ex:.2e} energy {energies[it + 1]:.3f} vs {e_ref[it + 1]:.3f}")
+            if it == 0:
+                ok &= eh < 1e-6 and eb < 1e-5 and ex < 1e-4
+        ok &= abs(energies[0] - e_ref[0]) <= 1e-6 * abs(e_ref[0])
+        ok &= np.allclose(energies, e_ref, rtol=2e-3)
+        ok &= rel_err(ctx.frames()["frameEnergyTH"], ref.frames()["frameEnergyTH"]) < 1e-3
+        print("MULTI_CHECK", "OK" if ok else "FAIL", "world", world)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
