@@ -152,6 +152,13 @@ int ldso_b200_get_system(ldso_b200_ctx *ctx, double *H_A, double *b_A, double *H
 /* FullSystem::doStepFromBackup(1,1,1,1,1) + setPrecalcValues (FullSystem.cc:1587-1622); returns canbreak. */
 int ldso_b200_do_step(ldso_b200_ctx *ctx, int *canbreak);
 
+/* FullSystem::flagPointsForRemoval's re-linearisation (FullSystem.cc:1241-1249: resetOOB, linearize, applyRes(true),
+ * fixLinearizationF, Residuals.cc:216-242) of the n listed points followed by EnergyFunctional::marginalizePointsF
+ * (EnergyFunctional.cc:165-222): priorF *= prior_fac (setting_idepthFixPriorMargFac), addPoint<2> + SC addPoint(p,false),
+ * stitchDouble without priors, HM += setting_margWeightFac (M - Msc), bM likewise (read back with get_marg_prior;
+ * get_system returns M, Mb, Msc, Mbsc). The caller then removes the points from its window (removePoint). */
+int ldso_b200_marginalize_points(ldso_b200_ctx *ctx, int n, const int32_t *point_idx, float prior_fac, int *resInM);
+
 /* ---- the fused, device-resident Gauss-Newton loop ------------------------------------------------------
  * FullSystem::optimize's prologue (resetOOB + linearizeAll(false) + applyRes, FullSystem.cc:734-771). */
 int ldso_b200_optimize_begin(ldso_b200_ctx *ctx, double *energy_out);

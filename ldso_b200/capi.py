@@ -53,7 +53,7 @@ SYMBOLS = [
     "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
-    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_optimize_begin",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
@@ -258,6 +258,19 @@ class Context:
         self._chk(self.L.ldso_b200_do_step(self.ctx, C.byref(cb)))
         return bool(cb.value)
 
+    def marginalize_points(self, idx, prior_fac=600.0 * 600.0):
+        idx = np.ascontiguousarray(idx, np.int32)
+        r = C.c_int()
+        self._chk(self.L.ldso_b200_marginalize_points(self.ctx, int(idx.shape[0]), _i(idx), C.c_float(prior_fac), C.byref(r)))
+        return r.value
+
+    def marg_prior(self):
+        n = self.n
+        HM = np.zeros((n, n), np.float64, order="F")
+        bM = np.zeros(n)
+        self._chk(self.L.ldso_b200_get_marg_prior(self.ctx, _d(HM), _d(bM)))
+        return HM, bM
+
     # ---- fused loop
     def optimize_begin(self, want_energy=True):
         if not want_energy:     # fully asynchronous
@@ -355,6 +368,18 @@ class Context:
     def tracker_set_ref_level(self, lvl, u, v, idepth, color):
         a = [np.ascontiguousarray(x, np.float32) for x in (u, v, idepth, color)]
         self._chk(self.L.ldso_b200_tracker_set_ref_level(self.ctx, int(lvl), int(a[0].shape[0]), *[_f(x) for x in a]))
+
+    def tracker_make_coarse_depth(self, ref_slot, cpt, HdiF):
+        cpt = np.ascontiguousarray(cpt, np.float32)
+        hd = np.ascontiguousarray(HdiF, np.float32)
+        self._chk(self.L.ldso_b200_tracker_make_coarse_depth(self.ctx, int(ref_slot), int(hd.shape[0]), _f(cpt), _f(hd)))
+
+    def tracker_get_ref_level(self, lvl):
+        n = C.c_int()
+        self._chk(self.L.ldso_b200_tracker_get_ref_level(self.ctx, int(lvl), C.byref(n), None, None, None, None))
+        a = [np.zeros(n.value, np.float32) for _ in range(4)]
+        self._chk(self.L.ldso_b200_tracker_get_ref_level(self.ctx, int(lvl), C.byref(n), *[_f(x) for x in a]))
+        return a
 
     def tracker_set_frames(self, ref_a, ref_b, ref_exposure, new_slot, new_exposure):
         self._chk(self.L.ldso_b200_tracker_set_frames(self.ctx, C.c_float(ref_a), C.c_float(ref_b), C.c_float(ref_exposure),

@@ -67,6 +67,11 @@ struct ldso_b200_ctx {
     float trk_Ki[MAXLVL][9];
     float ref_aff_a = 0, ref_aff_b = 0, ref_exposure = 1, new_exposure = 1;
     int new_slot = -1;
+    float *cd_id[MAXLVL] = {}, *cd_ws[MAXLVL] = {}, *cd_bak[MAXLVL] = {};
+    int *cd_pos[MAXLVL] = {};
+    int *cd_rows = nullptr, *cd_tot = nullptr;
+    float *cd_in = nullptr;
+    int cd_in_cap = 0;
     float *trk_partials = nullptr;
     unsigned *trk_counter = nullptr;
     double *trk_out_dev = nullptr;
@@ -199,6 +204,10 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     free_window(c);
     for (int s = 0; s < NSLOTS; s++) for (int l = 0; l < MAXLVL; l++) if (c->img[s][l]) cudaFree(c->img[s][l]);
     for (int l = 0; l < MAXLVL; l++) for (int k = 0; k < 4; k++) if (c->trk_pc[l][k]) cudaFree(c->trk_pc[l][k]);
+    for (int l = 0; l < MAXLVL; l++) { if (c->cd_id[l]) cudaFree(c->cd_id[l]); if (c->cd_ws[l]) cudaFree(c->cd_ws[l]); if (c->cd_bak[l]) cudaFree(c->cd_bak[l]); if (c->cd_pos[l]) cudaFree(c->cd_pos[l]); }
+    if (c->cd_rows) cudaFree(c->cd_rows);
+    if (c->cd_tot) cudaFree(c->cd_tot);
+    if (c->cd_in) cudaFree(c->cd_in);
     if (c->scratch) cudaFree(c->scratch);
     if (c->ws_dev) cudaFree(c->ws_dev);
     if (c->ws_host) cudaFreeHost(c->ws_host);
@@ -782,6 +791,41 @@ extern "C" int ldso_b200_do_step(ldso_b200_ctx *c, int *canbreak) {
     return LDSO_B200_OK;
 }
 
+// FullSystem::flagPointsForRemoval's re-linearisation of the points to marginalise (FullSystem.cc:1241-1249:
+// resetOOB, linearize, applyRes(true), fixLinearizationF) followed by EnergyFunctional::marginalizePointsF
+// (EnergyFunctional.cc:165-222): priorF *= prior_fac, addPoint<2> + SC addPoint(p, false), stitchDouble without priors,
+// HM += margWeightFac (M - Msc), bM likewise. The caller then drops the points from its window.
+extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32_t *point_idx, float prior_fac, int *resInM) {
+    if (!c || n < 0 || (n > 0 && !point_idx)) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    std::vector<uint8_t> sel(std::max(c->d.nP, 1), 0);
+    for (int i = 0; i < n; i++) {
+        if (point_idx[i] < 0 || point_idx[i] >= c->d.nP) return c->fail(LDSO_B200_ERR_ARG, "point index out of range");
+        sel[point_idx[i]] = 1;
+    }
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->pt_sel_dev, sel.data(), c->d.nP, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    RET_IF(launch_k1(c, K1F_LINEARIZE | K1F_STORE_J | K1F_APPLY_RES | K1F_RESET_OOB, c->pt_sel_dev));
+    if (c->d.nR > 0) {
+        k_fix_linearization<<<(c->d.nR + 255) / 256, 256, 0, c->stream>>>(c->d, c->ws_dev, c->pt_sel_dev);
+        LAUNCH_CHECK(c);
+        k_scale_prior<<<(c->d.nP + 255) / 256, 256, 0, c->stream>>>(c->d, c->pt_sel_dev, prior_fac);
+        LAUNCH_CHECK(c);
+    }
+    RET_IF(launch_k1(c, K1F_ACCUMULATE | K1F_NO_SHIFT_PRIOR | (2 << K1F_MODE_SHIFT), c->pt_sel_dev));
+    RET_IF(launch_k2a(c, 1));
+    RET_IF(launch_k2b(c, 1, 0));
+    const int nn = c->n;
+    k_add_marg<<<(nn * nn + 255) / 256, 256, 0, c->stream>>>(c->sb, nn, (double) c->S.margWeightFac);
+    LAUNCH_CHECK(c);
+    if (resInM) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(resInM, &c->ws_dev->resInA, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    }
+    return LDSO_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- fused loop
 static const int K1_FUSED = K1F_LINEARIZE | K1F_ACCUMULATE | K1F_APPLY_RES;
 
@@ -1084,7 +1128,63 @@ extern "C" int ldso_b200_tracker_track(ldso_b200_ctx *c, double R[9], double t[3
 }
 
 extern "C" int ldso_b200_tracker_make_coarse_depth(ldso_b200_ctx *c, int ref_slot, int n, const float *centerProjectedTo3, const float *HdiF) {
-    (void) ref_slot; (void) n; (void) centerProjectedTo3; (void) HdiF;
-    if (!c) return LDSO_B200_ERR_ARG;
-    return c->fail(LDSO_B200_ERR_STATE, "tracker_make_coarse_depth: device makeCoarseDepthL0 not built yet (SURVEY §8f rank 1)");
+    if (!c || n < 0 || (n > 0 && (!centerProjectedTo3 || !HdiF))) return LDSO_B200_ERR_ARG;
+    if (ref_slot < 0 || ref_slot >= NSLOTS || !c->img[ref_slot][0]) return c->fail(LDSO_B200_ERR_ARG, "reference image slot not uploaded");
+    if (c->lh[0] > 1024) return c->fail(LDSO_B200_ERR_ARG, "image height > 1024 not supported by the row scan");
+    cudaSetDevice(c->device);
+    // buffers: idepth / weightSums / weightSums_bak / pos per level, point-cloud arrays with wl*hl capacity (CoarseTracker.cc:36-45)
+    for (int l = 0; l < c->levels; l++) {
+        const size_t npx = (size_t) c->lw[l] * c->lh[l];
+        if (!c->cd_id[l]) {
+            CUDA_CHECK_RET(c, cudaMalloc(&c->cd_id[l], 4 * npx)); CUDA_CHECK_RET(c, cudaMalloc(&c->cd_ws[l], 4 * npx));
+            CUDA_CHECK_RET(c, cudaMalloc(&c->cd_bak[l], 4 * npx)); CUDA_CHECK_RET(c, cudaMalloc(&c->cd_pos[l], 4 * npx));
+        }
+        if ((int) npx > c->trk_cap[l]) {
+            CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+            for (int k = 0; k < 4; k++) { if (c->trk_pc[l][k]) cudaFree(c->trk_pc[l][k]); CUDA_CHECK_RET(c, cudaMalloc(&c->trk_pc[l][k], 4 * npx)); }
+            c->trk_cap[l] = (int) npx;
+        }
+    }
+    if (!c->cd_rows) { CUDA_CHECK_RET(c, cudaMalloc(&c->cd_rows, sizeof(int) * 1024)); CUDA_CHECK_RET(c, cudaMalloc(&c->cd_tot, sizeof(int) * MAXLVL)); }
+    if (n > c->cd_in_cap) {
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+        if (c->cd_in) cudaFree(c->cd_in);
+        CUDA_CHECK_RET(c, cudaMalloc(&c->cd_in, sizeof(float) * 4 * (size_t) n));
+        c->cd_in_cap = n;
+    }
+    const size_t np0 = (size_t) c->lw[0] * c->lh[0];
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->cd_id[0], 0, 4 * np0, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->cd_ws[0], 0, 4 * np0, c->stream));
+    if (n > 0) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->cd_in, centerProjectedTo3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->cd_in + 3 * (size_t) n, HdiF, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+        k_cd_scatter<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->cd_in, c->cd_in + 3 * (size_t) n, c->cd_id[0], c->cd_ws[0], c->lw[0], c->lh[0]);
+        LAUNCH_CHECK(c);
+    }
+    for (int l = 1; l < c->levels; l++) {
+        const int npx = c->lw[l] * c->lh[l];
+        k_cd_down<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->cd_id[l - 1], c->cd_ws[l - 1], c->cd_id[l], c->cd_ws[l], c->lw[l], c->lh[l], c->lw[l - 1]);
+        LAUNCH_CHECK(c);
+    }
+    for (int l = 0; l < c->levels; l++) {
+        const int npx = c->lw[l] * c->lh[l];
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->cd_bak[l], c->cd_ws[l], 4 * (size_t) npx, cudaMemcpyDeviceToDevice, c->stream));
+        k_cd_dilate<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->cd_id[l], c->cd_ws[l], c->cd_bak[l], c->lw[l], c->lh[l], l < 2 ? 1 : 0);
+        LAUNCH_CHECK(c);
+    }
+    for (int l = 0; l < c->levels; l++) {
+        const int npx = c->lw[l] * c->lh[l];
+        k_cd_rowcount<<<c->lh[l], 128, 0, c->stream>>>(c->cd_id[l], c->cd_ws[l], c->img[ref_slot][l], c->lw[l], c->lh[l], c->cd_pos[l], c->cd_rows);
+        LAUNCH_CHECK(c);
+        k_cd_rowscan<<<1, 1024, 0, c->stream>>>(c->cd_rows, c->lh[l], c->cd_tot + l);
+        LAUNCH_CHECK(c);
+        k_cd_emit<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->cd_id[l], c->cd_ws[l], c->img[ref_slot][l], c->cd_pos[l], c->cd_rows, c->lw[l], c->lh[l],
+                                                             c->trk_pc[l][0], c->trk_pc[l][1], c->trk_pc[l][2], c->trk_pc[l][3]);
+        LAUNCH_CHECK(c);
+    }
+    int tot[MAXLVL];
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(tot, c->cd_tot, sizeof(int) * c->levels, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    for (int l = 0; l < c->levels; l++) c->trk[l].n = tot[l];
+    return LDSO_B200_OK;
 }

@@ -200,7 +200,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         const bool lin = d.res_lin[r] != 0;
         // FullSystem::optimize only puts non-linearized residuals into activeResiduals (:744-750): a linearized
         // residual is neither reset nor re-linearized, and mode-0 accumulation skips it.
-        const bool touch = valid && !((flags & K1F_LINEARIZE) && lin);
+        const bool touch = valid && !((flags & K1F_LINEARIZE) && lin) && (pin[6] != 0.f);   // pt_sel restricts the pass
 
         float x10[10], y10[10], Jpdd0, Jpdd1;
         float v_res, v_ji0, v_ji1, v_jab0, v_jab1;       // this lane's pixel row: resF, JIdx[0..1], JabF[0..1]

@@ -439,3 +439,40 @@ __global__ void k_sum_nid(DevWindow d, WinState *ws) {
     }
     if (threadIdx.x == 0) { ws->sumNID = sh[0]; ws->numID = (float) d.nP; }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// marginalisation helpers
+// PointFrameResidual::fixLinearizationF (Residuals.cc:216-242) on the active residuals of the selected points
+__global__ void k_fix_linearization(DevWindow d, const WinState *__restrict__ ws, const uint8_t *__restrict__ pt_sel) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.nR) return;
+    const int p = d.res_point[r];
+    if (!pt_sel[p] || !d.res_active[r]) return;
+    const int nF = ws->nF, h = d.pt_host[p], t = d.res_target[r];
+    const float *dp = ws->adHTdeltaF[h + nF * t];
+    const float *J = d.res_J + (size_t) 74 * r;
+    const float deltaF = d.pt_idepth[p] - d.pt_idepth_zero[p];
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+    for (int i = 0; i < 6; i++) { a0 += J[8 + i] * dp[i]; a1 += J[14 + i] * dp[i]; }
+    for (int i = 0; i < 4; i++) { b0 += J[20 + i] * ws->calib.cDeltaF[i]; b1 += J[24 + i] * ws->calib.cDeltaF[i]; }
+    const float dx = a0 + b0 + J[28] * deltaF, dy = a1 + b1 + J[29] * deltaF;
+    for (int i = 0; i < 8; i++) {
+        float rtz = J[i];
+        rtz = rtz - J[30 + i] * dx;
+        rtz = rtz - J[38 + i] * dy;
+        rtz = rtz - J[46 + i] * dp[6];
+        rtz = rtz - J[54 + i] * dp[7];
+        d.res_toZero[8 * r + i] = rtz;
+    }
+    d.res_lin[r] = 1;
+}
+__global__ void k_scale_prior(DevWindow d, const uint8_t *__restrict__ pt_sel, float fac) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < d.nP && pt_sel[p]) d.pt_priorF[p] *= fac;
+}
+// HM += w (M - Msc), bM += w (Mb - Mbsc)   (EnergyFunctional.cc:200-214)
+__global__ void k_add_marg(SolveBufs sb, int n, double w) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n * n) sb.HM[e] += w * (sb.H_A[e] - sb.H_sc[e]);
+    if (e < n) sb.bM[e] += w * (sb.b_A[e] - sb.b_sc[e]);
+}

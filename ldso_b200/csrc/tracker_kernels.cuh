@@ -420,3 +420,102 @@ __global__ void __launch_bounds__(TRK_TRACK_THREADS) k_trk_track(TrkTrackArgs A,
         out->n_evals = s_evals;
     }
 }
+
+// =========================================================================================================
+// Device-side CoarseTracker::makeCoarseDepthL0 (src/frontend/CoarseTracker.cc:258-438): the reference point cloud
+// of the tracker, built from the active points' projections into the newest keyframe.
+// (1) scatter idepth*weight and weight at the rounded projection (:262-283)
+__global__ void k_cd_scatter(int n, const float *__restrict__ cpt, const float *__restrict__ HdiF, float *idepth0, float *wsum0, int w0, int h0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int u = (int) (cpt[3 * k + 0] + 0.5f);
+    const int v = (int) (cpt[3 * k + 1] + 0.5f);
+    if (u < 0 || v < 0 || u >= w0 || v >= h0) return;     // the reference would write out of bounds here
+    const float new_idepth = cpt[3 * k + 2];
+    const float weight = sqrtf(1e-3 / (HdiF[k] + 1e-12));
+    atomicAdd(idepth0 + u + w0 * v, new_idepth * weight);   // >2 points on one pixel: sum order differs by ulps
+    atomicAdd(wsum0 + u + w0 * v, weight);
+}
+// (2) 2x2 sums down the pyramid (:285-310)
+__global__ void k_cd_down(const float *__restrict__ idm, const float *__restrict__ wsm, float *idl, float *wsl, int wl, int hl, int wlm1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wl * hl) return;
+    const int x = i % wl, y = i / wl;
+    const int b = 2 * x + 2 * y * wlm1;
+    idl[i] = idm[b] + idm[b + 1] + idm[b + wlm1] + idm[b + wlm1 + 1];
+    wsl[i] = wsm[b] + wsm[b + 1] + wsm[b + wlm1] + wsm[b + wlm1 + 1];
+}
+// (3) one dilation pass (:312-395): diagonal neighbours on levels 0,1, 4-neighbourhood above. Cells with weight are
+// only read, cells without are only written, so the in-place update of idepth is race-free like in the reference.
+__global__ void k_cd_dilate(float *idl, float *wsl, const float *__restrict__ wbak, int wl, int hl, int diagonal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < wl || i >= wl * hl - wl) return;
+    if (wbak[i] > 0) return;
+    int nb[4];
+    if (diagonal) { nb[0] = i + 1 + wl; nb[1] = i - 1 - wl; nb[2] = i + wl - 1; nb[3] = i - wl + 1; }
+    else { nb[0] = i + 1; nb[1] = i - 1; nb[2] = i + wl; nb[3] = i - wl; }
+    float sum = 0, num = 0, numn = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (wbak[nb[k]] > 0) { sum += idl[nb[k]]; num += wbak[nb[k]]; numn++; }
+    if (numn > 0) { idl[i] = sum / numn; wsl[i] = num / numn; }
+}
+// (4) normalise + ordered compaction (:398-437). One block per image row computes each valid pixel's rank in the row.
+__device__ __forceinline__ bool cd_valid(const float *idl, const float *wsl, const float4 *ref, int i, float &id, float &col) {
+    if (!(wsl[i] > 0)) return false;
+    id = idl[i] / wsl[i];
+    col = ref[i].x;
+    return isfinite(col) && (id > 0);
+}
+__global__ void __launch_bounds__(128) k_cd_rowcount(const float *__restrict__ idl, const float *__restrict__ wsl, const float4 *__restrict__ ref,
+                                                     int wl, int hl, int *pos, int *rowcount) {
+    const int y = blockIdx.x;
+    __shared__ int s_warp[4];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const bool rowok = (y >= 2 && y < hl - 2);
+    for (int x0 = 0; x0 < wl; x0 += 128) {
+        const int x = x0 + threadIdx.x;
+        float id, col;
+        const bool v = rowok && x >= 2 && x < wl - 2 && cd_valid(idl, wsl, ref, x + y * wl, id, col);
+        const unsigned bal = __ballot_sync(0xffffffffu, v);
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+        if (lane == 0) s_warp[wp] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wp; k++) off += s_warp[k];
+        if (v) pos[x + y * wl] = off + __popc(bal & ((1u << lane) - 1));
+        else if (x < wl) pos[x + y * wl] = -1;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowcount[y] = s_base;
+}
+__global__ void __launch_bounds__(1024) k_cd_rowscan(int *rowcount, int hl, int *total) {
+    __shared__ int s[1024];
+    const int t = threadIdx.x;
+    s[t] = (t < hl) ? rowcount[t] : 0;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (t >= o) ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    if (t < hl) rowcount[t] = s[t] - ((t < hl) ? (s[t] - (t > 0 ? s[t - 1] : 0)) : 0);   // exclusive
+    if (t == 0) *total = s[1023];
+}
+__global__ void k_cd_emit(const float *__restrict__ idl, const float *__restrict__ wsl, const float4 *__restrict__ ref, const int *__restrict__ pos,
+                          const int *__restrict__ rowoff, int wl, int hl, float *pc_u, float *pc_v, float *pc_id, float *pc_col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wl * hl) return;
+    const int p = pos[i];
+    if (p < 0) return;
+    const int x = i % wl, y = i / wl;
+    float id, col;
+    cd_valid(idl, wsl, ref, i, id, col);
+    const int dst = rowoff[y] + p;
+    pc_u[dst] = (float) x; pc_v[dst] = (float) y; pc_id[dst] = id; pc_col[dst] = col;
+}

@@ -284,3 +284,25 @@ def test_make_images_device(small_win):
     for l in range(small_win.levels):
         assert np.array_equal(ctx.download_frame_level(3, l), small_win.pyramids[1][l])
     ctx.close()
+
+
+def test_marginalize_points(small_win):
+    """flagPointsForRemoval's fixLinearizationF + EnergyFunctional::marginalizePointsF (mode-2 accumulation + SC without
+    prior shift) after two GN steps: M, Mb, Msc, Mbsc and the updated HM, bM against the oracle."""
+    win = small_win
+    o = oracle_py.OracleBA(win, threads_mode=1)
+    ctx = _ctx(win)
+    o.optimize_begin()
+    ctx.optimize_begin()
+    # both sides start the marginalisation from THEIR OWN state after the prologue (identical up to float rounding)
+    idx = np.arange(0, win.nP, 3, dtype=np.int32)[:40]
+    o.marginalize_points(idx)
+    nres = ctx.marginalize_points(idx)
+    so, sg = o.system(), ctx.system()
+    assert nres == o.res_counts()[2]
+    for k in ("HA", "bA", "Hsc", "bsc"):
+        assert rel_err(sg[k], so[k]) < TOL, k
+    HMo, bMo = o.marg_prior()
+    HMg, bMg = ctx.marg_prior()
+    assert rel_err(HMg, HMo) < TOL and rel_err(bMg, bMo) < TOL
+    ctx.close()

@@ -63,3 +63,20 @@ def test_track_full_size_converges():
     assert np.linalg.norm(t - pair.t_true) < 0.05 * np.linalg.norm(pair.t_true)
     assert np.abs(R - pair.R_true).max() < 1e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("size", ["small", "cfg1"])
+def test_make_coarse_depth_device(size):
+    """Device-side CoarseTracker::makeCoarseDepthL0: same point cloud (order, coordinates, colours, idepths) as the oracle."""
+    pair = synth.make_track_pair(w=320, h=240, n_pts=400, seed=7) if size == "small" else synth.make_track_pair()
+    ot = oracle_py.OracleTracker(pair)
+    ctx = capi.Context(pair.w, pair.h, pair.levels)
+    ctx.upload_frame(0, pair.ref_pyr)
+    ctx.tracker_make_coarse_depth(0, pair.cpt, pair.HdiF)
+    for l in range(pair.levels):
+        uo, vo, io_, co = ot.pc(l)
+        ug, vg, ig, cg = ctx.tracker_get_ref_level(l)
+        assert len(ug) == len(uo)
+        assert np.array_equal(ug, uo) and np.array_equal(vg, vo) and np.array_equal(cg, co)
+        assert rel_err(ig, io_) < 1e-6
+    ctx.close()
