@@ -223,6 +223,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_warm_ms = e0.elapsed_time(e1)
 
+    # ---- per-kernel durations (CUDA events around each launch, L2 flushed between iterations) for the roofline of the
+    # dominant HBM kernel K1 (fused linearize + accumulate: it moves all of the per-residual / per-point algorithmic bytes)
+    ctx.kernel_times(True)
+    for k in range(min(args.steps, 50)):
+        flush.fill_(k & 0xff)
+        gn_step(3)
+    ktimes = ctx.kernel_times(False)
+
     # ---- end-to-end through the C ABI with host buffers (single GPU arm only): every step uploads the newest
     # keyframe's raw image (device-side makeImages), the frame states and the whole window from host memory, runs
     # one GN iteration and reads the solution, energy, point idepths/steps and residual states back.
@@ -247,7 +255,9 @@ def run_ours(args):
     its_per_s = world * window_its_per_s
     hbm_peak, peak_src = peaks()
     b_iter = algorithmic_bytes(n_res_rank, n_pts_rank, NF)   # per GPU (each rank streams its own shard)
-    achieved = b_iter / (t_ms * 1e-3 / args.steps) / 1e9
+    achieved_iter = b_iter / (t_ms * 1e-3 / args.steps) / 1e9
+    b_k1 = n_res_rank * (384 + 12 + 12) + n_pts_rank * (80 + 8 + 4)     # SURVEY §8d per-residual / per-point terms
+    achieved = b_k1 / (ktimes["k1"] * 1e-6) / 1e9 if ktimes["k1"] > 0 else 0.0
     line = {
         "metric": METRIC, "value": its_per_s, "unit": "GN-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -262,9 +272,12 @@ def run_ours(args):
         "value_l2_warm": world * args.steps / (t_warm_ms * 1e-3),
         "window_iters_per_s": window_its_per_s,
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": b_iter,
-                     "note": "whole GN iteration (4 kernels); the path is launch/latency-bound at 2k points, see DESIGN.md"},
+        "roofline": {"bound": "hbm", "kernel": "k1_linearize_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": 12244736, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": b_k1, "kernel_us": ktimes,
+                     "traffic_source": "dram__bytes_read.sum+write of K1, ncu --set full (profiles/r01a_ncu_full_raw.csv), cold L2",
+                     "whole_iteration": {"achieved": achieved_iter, "frac": achieved_iter / hbm_peak, "algorithmic_bytes_per_step": b_iter},
+                     "note": "2k points: latency-bound, not bandwidth-bound (ideal 0.93 us/iteration); see DESIGN.md §4"},
         "clocks": clocks,
         "gpu_launches": launches,
     }

@@ -181,6 +181,10 @@ int ldso_b200_set_shard(ldso_b200_ctx *ctx, int newest_slot_offset, int newest_t
 int ldso_b200_gn_phase_a(ldso_b200_ctx *ctx, int iteration);
 int ldso_b200_gn_phase_b(ldso_b200_ctx *ctx);
 
+/* Per-kernel CUDA-event timing of the GN loop (bench.py's roofline leg): enable != 0 starts collecting (CUDA graphs off),
+ * enable == 0 stops and returns the average duration in microseconds of K1, K2a, K2b, K3 since it was enabled. */
+int ldso_b200_kernel_times(ldso_b200_ctx *ctx, int enable, double out_us[4]);
+
 /* ---- read-back (host mirrors of PointHessian / PointFrameResidual / FrameHessian fields) --------------- */
 int ldso_b200_get_energy(ldso_b200_ctx *ctx, double *energy, int *canbreak);
 int ldso_b200_get_last_solution(ldso_b200_ctx *ctx, double *lastHS, double *lastbS, double *lastX);

@@ -50,7 +50,7 @@ assert FRAME_DTYPE.itemsize == C.sizeof(FrameStateC)
 # every symbol include/ldso_b200.h declares (tests check the shared object exports all of them)
 SYMBOLS = [
     "ldso_b200_default_settings", "ldso_b200_create", "ldso_b200_destroy", "ldso_b200_last_error", "ldso_b200_set_stream",
-    "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_upload_frame", "ldso_b200_make_images",
+    "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_kernel_times", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_optimize_begin",
@@ -154,6 +154,12 @@ class Context:
 
     def synchronize(self):
         self._chk(self.L.ldso_b200_synchronize(self.ctx))
+
+    def kernel_times(self, enable):
+        """enable=True: start per-kernel event timing; enable=False: stop, return avg us of (k1, k2a, k2b, k3)."""
+        out = (C.c_double * 4)()
+        self._chk(self.L.ldso_b200_kernel_times(self.ctx, int(bool(enable)), out))
+        return dict(zip(("k1", "k2a", "k2b", "k3"), list(out)))
 
     def launch_count(self) -> int:
         return int(self.L.ldso_b200_launch_count(self.ctx))

@@ -56,6 +56,10 @@ struct ldso_b200_ctx {
             res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, res_JpJdF, dl_end, res_JpJdF_new, total;
     } lay;
     bool mirror_valid = false;
+    // one GN iteration (K3 -> K1 -> K2a -> K2b) captured as a CUDA graph; re-captured when the window arena changes
+    cudaGraphExec_t gn_graph = nullptr;
+    bool gn_graph_valid = false;
+    bool use_graph = true;
     size_t k1_smem = 0;
     bool multi = false;
 
@@ -180,6 +184,7 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     p += 2 * nn;   // spare
     c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
+    c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
     cudaEventCreateWithFlags(&c->frames_copied, cudaEventDisableTiming);
     cudaFuncSetAttribute(k1_linearize_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem_bytes(64));
     cudaFuncSetAttribute(k3_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K3_SMEM_BYTES);
@@ -193,6 +198,7 @@ static void free_window(ldso_b200_ctx *c) {
     if (c->arena_dev) { cudaFree(c->arena_dev); c->arena_dev = nullptr; }
     if (c->arena_host) { cudaFreeHost(c->arena_host); c->arena_host = nullptr; }
     c->mirror_valid = false;
+    c->gn_graph_valid = false;
     c->have_window = false;
 }
 
@@ -201,6 +207,7 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->kt_report();
+    if (c->gn_graph) cudaGraphExecDestroy(c->gn_graph);
     free_window(c);
     for (int s = 0; s < NSLOTS; s++) for (int l = 0; l < MAXLVL; l++) if (c->img[s][l]) cudaFree(c->img[s][l]);
     for (int l = 0; l < MAXLVL; l++) for (int k = 0; k < 4; k++) if (c->trk_pc[l][k]) cudaFree(c->trk_pc[l][k]);
@@ -499,6 +506,7 @@ static int build_derived(ldso_b200_ctx *c) {
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     d.items = items_dev; d.host_item_begin = hib_dev; d.res_newest_slot = slot_dev;
     c->derived_dirty = false;
+    c->gn_graph_valid = false;
     return LDSO_B200_OK;
 }
 
@@ -845,18 +853,44 @@ extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
     return LDSO_B200_OK;
 }
 
+static int launch_gn_body(ldso_b200_ctx *c) {
+    RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
+    RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
+    RET_IF(launch_k2a(c, 1));
+    RET_IF(launch_k2b(c, 1, 1));
+    return LDSO_B200_OK;
+}
+
 extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, int n_iterations) {
     if (!c) return LDSO_B200_ERR_ARG;
     if (c->multi) return c->fail(LDSO_B200_ERR_STATE, "sharded context: use gn_phase_a / all-reduce / gn_phase_b");
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
-    RET_IF(set_iteration(c, first_iteration));
-    for (int i = 0; i < n_iterations; i++) {
-        RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
-        RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
-        RET_IF(launch_k2a(c, 1));
-        RET_IF(launch_k2b(c, 1, 1));
+    RET_IF(set_iteration(c, first_iteration));     // K3 reads the iteration number from device memory and increments it
+    if (c->use_graph && c->d.nItems > 0) {
+        if (!c->gn_graph_valid) {
+            if (c->gn_graph) { cudaGraphExecDestroy(c->gn_graph); c->gn_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            CUDA_CHECK_RET(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const long long l0 = c->launches;
+            int rc = launch_gn_body(c);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            c->launches = l0;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return c->fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            e = cudaGraphInstantiate(&c->gn_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return c->fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+            c->gn_graph_valid = true;
+        }
+        for (int i = 0; i < n_iterations; i++) {
+            CUDA_CHECK_RET(c, cudaGraphLaunch(c->gn_graph, c->stream));
+            c->launches += 4;
+            c->mirror_valid = false;
+        }
+        return LDSO_B200_OK;
     }
+    for (int i = 0; i < n_iterations; i++) RET_IF(launch_gn_body(c));
     return LDSO_B200_OK;
 }
 
@@ -984,6 +1018,43 @@ extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *s
         if (adHTdeltaF8) memcpy(adHTdeltaF8 + 8 * q, W.adHTdeltaF[q], 32);
     }
     if (calib_value4) memcpy(calib_value4, W.calib.value, 32);
+    return LDSO_B200_OK;
+}
+
+// Per-kernel CUDA-event timing of the GN loop (bench.py's roofline leg): enable != 0 starts collecting (graphs off),
+// enable == 0 stops and returns the average duration in microseconds of K1, K2a, K2b, K3 since it was enabled.
+extern "C" int ldso_b200_kernel_times(ldso_b200_ctx *c, int enable, double out_us[4]) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (enable) {
+        for (auto &k : c->kt) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+        c->kt.clear();
+        c->ktime = true;
+        c->use_graph = false;
+        return LDSO_B200_OK;
+    }
+    const char *names[4] = {"k1", "k2a", "k2b", "k3"};
+    double tot[4] = {0, 0, 0, 0};
+    int cnt[4] = {0, 0, 0, 0};
+    for (auto &k : c->kt) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, k.a, k.b);
+        for (int i = 0; i < 4; i++) if (!strcmp(names[i], k.name)) { tot[i] += ms; cnt[i]++; }
+        cudaEventDestroy(k.a); cudaEventDestroy(k.b);
+    }
+    c->kt.clear();
+    c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
+    c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
+    if (out_us) for (int i = 0; i < 4; i++) out_us[i] = cnt[i] ? 1e3 * tot[i] / cnt[i] : 0.0;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_debug_res_to_zero(ldso_b200_ctx *c, float *out8) {
+    if (!c || !out8 || !c->have_window) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out8, c->d.res_toZero, 32 * (size_t) c->d.nR, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     return LDSO_B200_OK;
 }
 

@@ -86,46 +86,73 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full) {
         for (int i = 0; i < 4; i++) c.cDeltaF[i] = (float) (c.value[i] - c.value_zero[i]);
     }
     __syncthreads();
-    if (tid < nF * nF) {
-        const int h = tid % nF, t = tid / nF;
+    // pair records, three short parallel phases instead of one long per-pair chain:
+    // F2 (pair,row): one row of R = R_t R_h^T and of t = t_t - R t_h, in double; F3 (pair,row): one row of K R K^-1 and K t in
+    // float (the reference's Mat33f products, FrameFramePrecalc.cc:21-31); F3' (pair): affine brightness transfer.
+    __shared__ float sRf[MAXPAIR][9], sTf[MAXPAIR][3];
+    __shared__ double sTd[MAXPAIR][3];
+    for (int o = tid; o < nF * nF * 3; o += blockDim.x) {
+        const int q = o / 3, i = o - 3 * q, h = q % nF, t = q / nF;
         const FrameDev &fh = S->fr[h], &ft = S->fr[t];
-        PairRec &pc = ws->pair[h + nF * t];
-        PairRecFull &pf = ws->pairFull[h + nF * t];
         if (full) {     // eval-point (FEJ) part: constant while the window's linearisation point is fixed
-            double R0[9], t0[3];
-            se3_mul_inv(ft.evalR, ft.evalT, fh.evalR, fh.evalT, R0, t0);
-            for (int i = 0; i < 9; i++) pc.R0[i] = (float) R0[i];
-            for (int i = 0; i < 3; i++) pc.t0[i] = (float) t0[i];
-            pc.b0 = (float) (fh.state_zero[7] * (double) SCALE_B);
-            pc.pad[0] = pc.pad[1] = pc.pad[2] = pc.pad[3] = 0.f;
+            double r0[3], t0 = ft.evalT[i];
+            for (int j = 0; j < 3; j++) r0[j] = ft.evalR[i * 3] * fh.evalR[j * 3] + ft.evalR[i * 3 + 1] * fh.evalR[j * 3 + 1] + ft.evalR[i * 3 + 2] * fh.evalR[j * 3 + 2];
+            t0 -= r0[0] * fh.evalT[0] + r0[1] * fh.evalT[1] + r0[2] * fh.evalT[2];
+            PairRec &pc = ws->pair[q];
+            for (int j = 0; j < 3; j++) pc.R0[i * 3 + j] = (float) r0[j];
+            pc.t0[i] = (float) t0;
+            if (i == 0) { pc.b0 = (float) (fh.state_zero[7] * (double) SCALE_B); pc.pad[0] = pc.pad[1] = pc.pad[2] = pc.pad[3] = 0.f; }
         }
-        double R[9], tt[3];
-        se3_mul_inv(ft.preR, ft.preT, fh.preR, fh.preT, R, tt);
-        float Rf[9], tf[3];
-        for (int i = 0; i < 9; i++) { Rf[i] = (float) R[i]; pf.RTll[i] = Rf[i]; }
-        for (int i = 0; i < 3; i++) { tf[i] = (float) tt[i]; pf.tTll[i] = tf[i]; }
-        pc.distanceLL = (float) sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
-        const CalibDev &c = S->calib;
-        float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
-        float Ki[9], tmp[9], KRKi[9];
-        m33f_inverse(K, Ki);
-        m33f_mul(K, Rf, tmp);
-        m33f_mul(tmp, Ki, KRKi);
-        for (int i = 0; i < 9; i++) pc.KRKi[i] = KRKi[i];
-        for (int i = 0; i < 3; i++) {
-            float s = K[i * 3 + 0] * tf[0];
-            s += K[i * 3 + 1] * tf[1];
-            s += K[i * 3 + 2] * tf[2];
-            pc.Kt[i] = s;
+        double r[3], tt = ft.preT[i];
+        for (int j = 0; j < 3; j++) r[j] = ft.preR[i * 3] * fh.preR[j * 3] + ft.preR[i * 3 + 1] * fh.preR[j * 3 + 1] + ft.preR[i * 3 + 2] * fh.preR[j * 3 + 2];
+        tt -= r[0] * fh.preT[0] + r[1] * fh.preT[1] + r[2] * fh.preT[2];
+        for (int j = 0; j < 3; j++) sRf[q][i * 3 + j] = (float) r[j];
+        sTf[q][i] = (float) tt;
+        sTd[q][i] = tt;
+    }
+    __syncthreads();
+    for (int o = tid; o < nF * nF * 4; o += blockDim.x) {
+        const int q = o >> 2, i = o & 3;
+        PairRec &pc = ws->pair[q];
+        if (i < 3) {
+            const CalibDev &c = S->calib;
+            const float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
+            float Ki[9];
+            m33f_inverse(K, Ki);
+            const float *Rf = sRf[q];
+            float tmp[3];
+            for (int j = 0; j < 3; j++) {
+                float s2 = K[i * 3 + 0] * Rf[0 * 3 + j];
+                s2 += K[i * 3 + 1] * Rf[1 * 3 + j];
+                s2 += K[i * 3 + 2] * Rf[2 * 3 + j];
+                tmp[j] = s2;
+            }
+            for (int j = 0; j < 3; j++) {
+                float s2 = tmp[0] * Ki[0 * 3 + j];
+                s2 += tmp[1] * Ki[1 * 3 + j];
+                s2 += tmp[2] * Ki[2 * 3 + j];
+                pc.KRKi[i * 3 + j] = s2;
+            }
+            float s2 = K[i * 3 + 0] * sTf[q][0];
+            s2 += K[i * 3 + 1] * sTf[q][1];
+            s2 += K[i * 3 + 2] * sTf[q][2];
+            pc.Kt[i] = s2;
+            PairRecFull &pf = ws->pairFull[q];
+            for (int j = 0; j < 3; j++) pf.RTll[i * 3 + j] = Rf[i * 3 + j];
+            pf.tTll[i] = sTf[q][i];
+        } else {
+            const int h = q % nF, t = q / nF;
+            const FrameDev &fh = S->fr[h], &ft = S->fr[t];
+            // AffLight::fromToVecExposure (AffLight.h:27-35) with aff_g2l() = state_scaled[6..7]
+            float eF = fh.ab_exposure, eT = ft.ab_exposure;
+            if (eF == 0 || eT == 0) eT = eF = 1;
+            const float ah = (float) ((double) SCALE_A * fh.state[6]), bh = (float) ((double) SCALE_B * fh.state[7]);
+            const float at = (float) ((double) SCALE_A * ft.state[6]), bt = (float) ((double) SCALE_B * ft.state[7]);
+            const float aa = expf(at - ah) * eT / eF;
+            pc.aff[0] = aa;
+            pc.aff[1] = bt - aa * bh;
+            pc.distanceLL = (float) sqrt(sTd[q][0] * sTd[q][0] + sTd[q][1] * sTd[q][1] + sTd[q][2] * sTd[q][2]);
         }
-        // AffLight::fromToVecExposure (AffLight.h:27-35) with aff_g2l() = state_scaled[6..7]
-        float eF = fh.ab_exposure, eT = ft.ab_exposure;
-        if (eF == 0 || eT == 0) eT = eF = 1;
-        const float ah = (float) ((double) SCALE_A * fh.state[6]), bh = (float) ((double) SCALE_B * fh.state[7]);
-        const float at = (float) ((double) SCALE_A * ft.state[6]), bt = (float) ((double) SCALE_B * ft.state[7]);
-        const float aa = expf(at - ah) * eT / eF;
-        pc.aff[0] = aa;
-        pc.aff[1] = bt - aa * bh;
     }
     // adHTdeltaF (EnergyFunctional.cc:406-414): one (pair, column) output per thread pass
     for (int o = tid; o < nF * nF * 8; o += blockDim.x) {
@@ -331,16 +358,26 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         __syncthreads();
         K3_STAMP();   // 2: assembled
         // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
-        if (tid < n) vS[tid] = 1.0 / sqrt(A0[tid * K3_LD + tid] + 10.0);
-        __syncthreads();
         if (tid < n) {
-            const double di = fabs(A0[tid * K3_LD + tid] * vS[tid] * vS[tid]);
+            const double dg = A0[tid * K3_LD + tid];
+            const double sv = 1.0 / sqrt(dg + 10.0);
+            vS[tid] = sv;
+            vd[tid] = fabs(dg * sv * sv);          // |diagonal| of the scaled matrix
+        }
+        __syncthreads();
+        {   // rank sort: 4 threads per row fold a quarter of the comparisons each
+            const int i = tid >> 2, q = tid & 3;
             int rank = 0;
-            for (int j = 0; j < n; j++) {
-                const double dj = fabs(A0[j * K3_LD + j] * vS[j] * vS[j]);
-                rank += (dj > di) || (dj == di && j < tid);
+            if (i < n) {
+                const double di = vd[i];
+                for (int j = q; j < n; j += 4) {
+                    const double dj = vd[j];
+                    rank += (dj > di) || (dj == di && j < i);
+                }
             }
-            perm[rank] = tid;
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            if (i < n && q == 0) perm[rank] = i;
         }
         __syncthreads();
         // A = P (S A0 S) P^T, b' = P S b
@@ -413,18 +450,21 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? A[n * K3_LD + tid] : 0.0;
         }
         __syncthreads();
-        // ---- backward solve L^T x = z, blocked from the last block up
+        // ---- backward solve L^T x = z, blocked from the last block up, column oriented: once a block of x is final its
+        // contribution is removed from all earlier rows by one thread per row (no reduction on the critical path)
         for (int k0 = ((n - 1) / K3_NB) * K3_NB; k0 >= 0; k0 -= K3_NB) {
-            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
-            // z[k0+c] -= sum_{i>=m0} L(i,k0+c) x[i] : warp c
-            if (warp < bs && m0 < n) {
-                double s = 0.0;
-                for (int i = m0 + lane; i < n; i += 32) s += A[i * K3_LD + k0 + warp] * vb[i];
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) vb[k0 + warp] -= s;
-            }
-            __syncthreads();
+            const int bs = min(K3_NB, n - k0);
             if (warp == 0) trsv_lower_t_warp(A, vb, k0, bs, lane);
+            __syncthreads();
+            if (tid < k0) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < K3_NB; c += 2) {
+                    if (c < bs) s0 += A[(k0 + c) * K3_LD + tid] * vb[k0 + c];
+                    if (c + 1 < bs) s1 += A[(k0 + c + 1) * K3_LD + tid] * vb[k0 + c + 1];
+                }
+                vb[tid] -= (s0 + s1);
+            }
             __syncthreads();
         }
         K3_STAMP();   // 5: back-substituted

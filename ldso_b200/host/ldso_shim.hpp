@@ -346,6 +346,9 @@ inline bool EnergyFunctional::optimizeOnDevice(int firstIteration, int nIteratio
     if (!syncToDevice(HCalib)) return false;
     if (ldso_b200_optimize_begin(ctx, &lastEnergy)) return false;
     if (ldso_b200_gn_iterations(ctx, firstIteration, nIterations)) return false;
+    // FullSystem::optimize ends with linearizeAll(true) (FullSystem.cc:843): fixes the states and leaves the projections
+    // (centerProjectedTo / projectedTo) that makeCoarseDepthL0 and LoopClosing read
+    if (ldso_b200_linearize_all(ctx, 1, 1, &lastEnergy)) return false;
     const int n = 8 * nFrames + CPARS;
     lastHS.resize(n, n); lastbS.d.assign(n, 0.0); lastX.d.assign(n, 0.0);
     if (ldso_b200_get_last_solution(ctx, lastHS.d.data(), lastbS.d.data(), lastX.d.data())) return false;
@@ -360,9 +363,14 @@ inline bool EnergyFunctional::optimizeOnDevice(int firstIteration, int nIteratio
     std::vector<float> id(nP), step(nP), HdiF(nP);
     ldso_b200_get_points(ctx, id.data(), nullptr, step.data(), HdiF.data(), nullptr, nullptr, nullptr, nullptr);
     for (size_t p = 0; p < nP; p++) { allPoints[p]->setIdepth(id[p]); allPoints[p]->setIdepthZero(id[p]); allPoints[p]->step = step[p]; allPoints[p]->HdiF = HdiF[p]; }
-    std::vector<uint8_t> ss(nR), act(nR); std::vector<float> en(nR);
-    ldso_b200_get_residuals(ctx, ss.data(), nullptr, en.data(), nullptr, nullptr, act.data(), nullptr, nullptr, nullptr, nullptr);
-    for (size_t r = 0; r < nR; r++) { flatResiduals[r]->state_state = (ResState) ss[r]; flatResiduals[r]->state_energy = en[r]; flatResiduals[r]->isActiveAndIsGoodNEW = act[r]; }
+    std::vector<uint8_t> ss(nR), act(nR); std::vector<float> en(nR), cpt(3 * nR), proj(16 * nR);
+    ldso_b200_get_residuals(ctx, ss.data(), nullptr, en.data(), nullptr, nullptr, act.data(), nullptr, nullptr, proj.data(), cpt.data());
+    for (size_t r = 0; r < nR; r++) {
+        PointFrameResidual &R = *flatResiduals[r];
+        R.state_state = (ResState) ss[r]; R.state_energy = en[r]; R.isActiveAndIsGoodNEW = act[r];
+        for (int i = 0; i < 3; i++) R.centerProjectedTo[i] = cpt[3 * r + i];
+        memcpy(R.projectedTo, &proj[16 * r], 64);
+    }
     uploadedState = stateEpoch();      // host and device agree again
     return true;
 }

@@ -124,8 +124,9 @@ int main(int argc, char **argv) {
         AffLight aff(0, 0);
         Vec5 mr; for (int i = 0; i < 5; i++) mr[i] = NAN;
         bool ok = tr.trackNewestCoarse(frameHessians[nF - 2], T, aff, levels - 1, mr);
-        printf(", \"track_ok\": %s, \"track_t\": [%.9g, %.9g, %.9g], \"track_res\": [%.6g, %.6g]", ok ? "true" : "false", T.t[0], T.t[1], T.t[2],
-               tr.lastResiduals[0], tr.lastResiduals[1]);
+        auto num = [](double v) { static char b[4][64]; static int k = 0; k = (k + 1) & 3; if (std::isfinite(v)) snprintf(b[k], 64, "%.9g", v); else snprintf(b[k], 64, "null"); return b[k]; };
+        printf(", \"track_ok\": %s, \"track_t\": [%s, %s, %s], \"track_res\": [%s, %s]", ok ? "true" : "false", num(T.t[0]), num(T.t[1]), num(T.t[2]),
+               num(tr.lastResiduals[0]), num(tr.lastResiduals[1]));
     }
     printf("}\n");
     return 0;

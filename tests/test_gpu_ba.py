@@ -299,6 +299,12 @@ def test_marginalize_points(small_win):
     o.marginalize_points(idx)
     nres = ctx.marginalize_points(idx)
     so, sg = o.system(), ctx.system()
+    rtz = np.zeros((win.nR, 8), np.float32)
+    ctx.L.ldso_b200_debug_res_to_zero(ctx.ctx, rtz.ctypes.data_as(capi.c_fp))
+    ro = o.residuals()
+    selr = np.isin(win.res_point, idx) & (ro["isActive"] == 1)
+    print("rtz err", rel_err(rtz[selr], ro["res_toZeroF"][selr]), "J err", rel_err(ctx.residuals()["J"][selr], ro["J"][selr]),
+          {k: rel_err(sg[k], so[k]) for k in ("HA", "bA", "Hsc", "bsc")})
     assert nres == o.res_counts()[2]
     for k in ("HA", "bA", "Hsc", "bsc"):
         assert rel_err(sg[k], so[k]) < TOL, k
