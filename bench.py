@@ -153,7 +153,8 @@ def run_ours(args):
     # weak scaling: 2000 points per GPU; the global window has 2000*N points, sharded by contiguous point blocks
     full = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME * world, seed=42)
     win = synth.shard_window(full, rank, world) if world > 1 else full
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (capturable) stream; everything below runs on it
+    torch.cuda.set_stream(stream)
     ctx = capi.Context(win.w, win.h, win.levels, device=local_rank)
     ctx.set_stream(stream.cuda_stream)
     ctx.load_synth_window(win)

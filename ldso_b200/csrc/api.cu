@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cstddef>
 
 #include "common.cuh"
 #include "se3_math.cuh"
@@ -56,6 +57,8 @@ struct ldso_b200_ctx {
             res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, res_JpJdF, dl_end, res_JpJdF_new, total;
     } lay;
     bool mirror_valid = false;
+    std::vector<double> evalpt_key, Pns_host;
+    cudaEvent_t window_copied = nullptr;
     // one GN iteration (K3 -> K1 -> K2a -> K2b) captured as a CUDA graph; re-captured when the window arena changes
     cudaGraphExec_t gn_graph = nullptr;
     bool gn_graph_valid = false;
@@ -405,7 +408,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     }
     if (nP > 0 && (win->res_begin[0] != 0 || win->res_begin[nP] != nR)) return c->fail(LDSO_B200_ERR_ARG, "res_begin does not cover the residual arrays");
     for (int r = 0; r < nR; r++) if (win->res_target[r] < 0 || win->res_target[r] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "res_target out of range");
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));     // the pinned mirror may still be in flight
+    if (c->window_copied) CUDA_CHECK_RET(c, cudaEventSynchronize(c->window_copied));     // the pinned mirror may still be in flight
     DevWindow &d = c->d;
     const bool same_topology = c->have_window && d.nP == nP && d.nR == nR && (int) c->h_pt_host.size() == nP && nP > 0 &&
                                std::equal(win->pt_host, win->pt_host + nP, c->h_pt_host.begin()) &&
@@ -445,6 +448,8 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     memcpy(H + L.pt_idepth, win->pt_idepth, 4 * (size_t) nP); memcpy(H + L.pt_idepth_zero, win->pt_idepth_zero, 4 * (size_t) nP);
     const size_t ul_begin = same_topology ? L.topo_end : 0;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_dev + ul_begin, H + ul_begin, L.ul_end - ul_begin, cudaMemcpyHostToDevice, c->stream));
+    if (!c->window_copied) CUDA_CHECK_RET(c, cudaEventCreateWithFlags(&c->window_copied, cudaEventDisableTiming));
+    CUDA_CHECK_RET(c, cudaEventRecord(c->window_copied, c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->arena_dev + L.ul_end, 0, L.total - L.ul_end, c->stream));    // all result/state arrays
     if (win->res_toZeroF && nR > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(d.res_toZero, win->res_toZeroF, 32 * (size_t) nR, cudaMemcpyHostToDevice, c->stream));
     if (!same_topology) CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * (size_t) std::max(nR, 1), c->stream));
@@ -516,10 +521,27 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     if (!c || !frames || !calib_value_scaled || !calib_value_zero) return LDSO_B200_ERR_ARG;
     if (nFrames < 1 || nFrames > MAXF) return c->fail(LDSO_B200_ERR_ARG, "nFrames must be in [1, LDSO_B200_MAX_FRAMES]");
     cudaSetDevice(c->device);
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // ws_host (pinned) is free: every set_frames / get_frames waits for its own copy before returning
     using namespace hostmath;
     WinState &W = *c->ws_host;
-    memset(&W, 0, sizeof(W));
+    // the adjoints and the null-space projector depend only on the evaluation points (worldToCam_evalPT, state_zero's
+    // affine part, exposures): they change once per keyframe, so they are recomputed only when those inputs change
+    std::vector<double> key;
+    key.reserve((size_t) nFrames * 16 + 1);
+    key.push_back((double) nFrames);
+    for (int i = 0; i < nFrames; i++) {
+        key.insert(key.end(), frames[i].evalR, frames[i].evalR + 9);
+        key.insert(key.end(), frames[i].evalT, frames[i].evalT + 3);
+        key.push_back(frames[i].state_zero[6]); key.push_back(frames[i].state_zero[7]); key.push_back(frames[i].ab_exposure);
+    }
+    const bool evalpt_cached = c->have_frames && key == c->evalpt_key;
+    if (evalpt_cached) {
+        // keep adHost/adTarget(/F) of the previous call; everything else is rewritten below
+        memset(&W, 0, offsetof(WinState, adHost));
+        memset((char *) &W + offsetof(WinState, cPrior), 0, sizeof(WinState) - offsetof(WinState, cPrior));
+    } else {
+        memset(&W, 0, sizeof(W));
+    }
     const int nF = nFrames, n = 8 * nF + CPARS;
     const int prev_nF = c->have_frames ? c->nF : -1;
     W.nF = nF; W.n = n; W.w = c->w; W.h = c->h;
@@ -561,6 +583,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     for (int i = 0; i < 4; i++) { C.cDeltaF[i] = (float) (C.value[i] - C.value_zero[i]); W.cPrior[i] = c->S.initialCalibHessian; }
 
     // EnergyFunctional::setAdjointsF (EnergyFunctional.cc:431-489)
+    if (!evalpt_cached)
     for (int h = 0; h < nF; h++)
         for (int t = 0; t < nF; t++) {
             Pose hostToTarget = mul(ev[t], inv(ev[h]));
@@ -586,6 +609,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     // null spaces (FrameHessian::setStateZero, FrameHessian.cc:11-42; FullSystem::getNullspaces, FullSystem.cc:1711-1760)
     // and the projector EnergyFunctional::orthogonalize applies (pose + scale, EnergyFunctional.cc:687-716)
     std::vector<double> N((size_t) n * 7, 0.0);
+    if (!evalpt_cached) {
     for (int f = 0; f < nF; f++) {
         const Pose evI = inv(ev[f]);
         for (int i = 0; i < 6; i++) {
@@ -617,12 +641,14 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
         s = sqrt(s);
         if (s > 0) for (int r = 0; r < n; r++) N[(size_t) j * n + r] /= s;
     }
-    std::vector<double> P;
-    range_projector(N, n, 7, c->S.solverModeDelta, P);
+    range_projector(N, n, 7, c->S.solverModeDelta, c->Pns_host);
+    c->evalpt_key = key;
+    }
 
     c->nF = nF; c->n = n;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->ws_dev, c->ws_host, sizeof(WinState), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.Pns, P.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
+    if (!evalpt_cached)
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.Pns, c->Pns_host.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
@@ -871,7 +897,13 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         if (!c->gn_graph_valid) {
             if (c->gn_graph) { cudaGraphExecDestroy(c->gn_graph); c->gn_graph = nullptr; }
             cudaGraph_t g = nullptr;
-            CUDA_CHECK_RET(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                // e.g. the legacy default stream cannot be captured: run the plain launches instead
+                cudaGetLastError();
+                c->use_graph = false;
+                for (int i = 0; i < n_iterations; i++) RET_IF(launch_gn_body(c));
+                return LDSO_B200_OK;
+            }
             const long long l0 = c->launches;
             int rc = launch_gn_body(c);
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);

@@ -288,26 +288,23 @@ def test_make_images_device(small_win):
 
 def test_marginalize_points(small_win):
     """flagPointsForRemoval's fixLinearizationF + EnergyFunctional::marginalizePointsF (mode-2 accumulation + SC without
-    prior shift) after two GN steps: M, Mb, Msc, Mbsc and the updated HM, bM against the oracle."""
-    win = small_win
+    prior shift): M, Mb, Msc, Mbsc and the updated HM, bM against the oracle. As in the reference, the points are
+    re-linearised at idepth == idepth_zero (FullSystem::doStepFromBackup resets idepth_zero after every step, so
+    deltaF = 0 whenever marginalisation runs); with the synthetic window's large initial deltaF the J*delta term is as
+    large as the residual and amplifies the 1e-5 float noise of the interpolated gradients above the 1e-4 bar."""
+    import dataclasses
+    win = dataclasses.replace(small_win, pt_idepth=small_win.pt_idepth_zero.copy())
     o = oracle_py.OracleBA(win, threads_mode=1)
     ctx = _ctx(win)
     o.optimize_begin()
     ctx.optimize_begin()
-    # both sides start the marginalisation from THEIR OWN state after the prologue (identical up to float rounding)
     idx = np.arange(0, win.nP, 3, dtype=np.int32)[:40]
     o.marginalize_points(idx)
     nres = ctx.marginalize_points(idx)
     so, sg = o.system(), ctx.system()
-    rtz = np.zeros((win.nR, 8), np.float32)
-    ctx.L.ldso_b200_debug_res_to_zero(ctx.ctx, rtz.ctypes.data_as(capi.c_fp))
-    ro = o.residuals()
-    selr = np.isin(win.res_point, idx) & (ro["isActive"] == 1)
-    print("rtz err", rel_err(rtz[selr], ro["res_toZeroF"][selr]), "J err", rel_err(ctx.residuals()["J"][selr], ro["J"][selr]),
-          {k: rel_err(sg[k], so[k]) for k in ("HA", "bA", "Hsc", "bsc")})
     assert nres == o.res_counts()[2]
     for k in ("HA", "bA", "Hsc", "bsc"):
-        assert rel_err(sg[k], so[k]) < TOL, k
+        assert rel_err(sg[k], so[k]) < TOL, (k, rel_err(sg[k], so[k]))
     HMo, bMo = o.marg_prior()
     HMg, bMg = ctx.marg_prior()
     assert rel_err(HMg, HMo) < TOL and rel_err(bMg, bMo) < TOL
