@@ -109,6 +109,31 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
     const int nres = rend - rbeg;
     float *s_rdot = s_ptout;        // [nres <= pts_per_item*MAXF] reuse: s_ptout is not live before phase P
+    // software prefetch: everything phases R2 and A(round 0) read from global is requested here, before the first
+    // barrier, so that its L2/HBM round trip overlaps the staging above instead of serialising behind each barrier
+    float pf_idepth = 0.f, pf_idz = 0.f, pf_bd = 0.f, pf_step = 0.f, pf_hdi = 0.f, pf_u = 0.f, pf_v = 0.f, pf_prior = 0.f;
+    float4 pf_hcd = make_float4(0.f, 0.f, 0.f, 0.f);
+    int pf_r0 = 0, pf_r1 = 0;
+    if (tid < npts) {
+        const int p = p0 + tid;
+        pf_idepth = d.pt_idepth[p]; pf_idz = d.pt_idepth_zero[p]; pf_u = d.pt_u[p]; pf_v = d.pt_v[p]; pf_prior = d.pt_priorF[p];
+        if (flags & K1F_APPLY_STEP) {
+            pf_bd = d.pt_bdSumF[p]; pf_step = d.pt_step[p]; pf_hdi = d.pt_HdiF[p]; pf_hcd = *(const float4 *) (d.pt_Hcd + 4 * p);
+            pf_r0 = d.pt_res_begin[p] - rbeg; pf_r1 = d.pt_res_begin[p + 1] - rbeg;
+        }
+    }
+    const int grp = tid >> 3, idx = tid & 7;
+    int nx_p, nx_t; uint8_t nx_state, nx_lin; float nx_energy; int nx_slot;
+#define K1_PREFETCH_RES(base_)                                                                          \
+    do {                                                                                                \
+        const int ri_ = (base_) + grp;                                                                  \
+        const int r_ = rbeg + ((ri_ < nres) ? ri_ : 0);                                                 \
+        nx_p = d.res_point[r_]; nx_t = d.res_target[r_]; nx_state = d.res_state[r_];                    \
+        nx_energy = d.res_energy[r_]; nx_lin = d.res_lin[r_];                                           \
+        nx_slot = (d.res_newest_slot != nullptr) ? d.res_newest_slot[r_] : -1;                          \
+    } while (0)
+    nx_p = p0; nx_t = 0; nx_state = 0; nx_lin = 0; nx_energy = 0.f; nx_slot = -1;
+    if (nres > 0) K1_PREFETCH_RES(0);
     if (flags & K1F_APPLY_STEP) {   // R1 (no dependence on the staged constants: overlaps their load latency)
         for (int ri = tid; ri < nres; ri += K1_THREADS) {
             const int r = rbeg + ri;
@@ -135,14 +160,14 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     double my_sumNID = 0.0, my_numID = 0.0;
     if (tid < npts) {
         const int p = p0 + tid;
-        float idepth = d.pt_idepth[p];
-        float idepth_zero = d.pt_idepth_zero[p];
+        float idepth = pf_idepth;
+        float idepth_zero = pf_idz;
         if (flags & K1F_APPLY_STEP) {
-            const int r0 = d.pt_res_begin[p] - rbeg, r1 = d.pt_res_begin[p + 1] - rbeg;
+            const int r0 = pf_r0, r1 = pf_r1;
             int ngood = 0;
-            float b = d.pt_bdSumF[p];
+            float b = pf_bd;
             {
-                const float4 hc = *(const float4 *) (d.pt_Hcd + 4 * p);
+                const float4 hc = pf_hcd;
                 float s = 0.f;
                 s += s_cstep[0] * hc.x; s += s_cstep[1] * hc.y; s += s_cstep[2] * hc.z; s += s_cstep[3] * hc.w;
                 b -= s;
@@ -152,9 +177,9 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
                 ngood++;
                 b -= recs_dot(s_rdot, ri, 0);
             }
-            float step = d.pt_step[p];
+            float step = pf_step;
             if (ngood == 0) step = 0.f;
-            else if (isfinite(b)) step = -b * d.pt_HdiF[p];
+            else if (isfinite(b)) step = -b * pf_hdi;
             d.pt_step[p] = step;
             const float backup = idepth;                       // FullSystem::backupState
             d.pt_idepth_backup[p] = backup;
@@ -166,11 +191,11 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         my_sumNID = fabsf(idepth);
         my_numID = 1.0;
         float *pi = s_ptin + tid * 8;
-        pi[0] = d.pt_u[p];
-        pi[1] = d.pt_v[p];
+        pi[0] = pf_u;
+        pi[1] = pf_v;
         pi[2] = idepth;
         pi[3] = idepth_zero;
-        pi[4] = d.pt_priorF[p];
+        pi[4] = pf_prior;
         pi[5] = idepth - idepth_zero;                          // deltaF (EnergyFunctional.cc:424)
         pi[6] = (pt_sel == nullptr || pt_sel[p]) ? 1.f : 0.f;
     }
@@ -178,7 +203,6 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
 
     K1_STAMP();   // 2: phase R done
     // ---------------- phase A: one 8-lane group per residual
-    const int grp = tid >> 3, idx = tid & 7;
     double my_energy = 0.0, my_nres = 0.0;
     const float fxl = s_cal[0], fyl = s_cal[1], cxl = s_cal[2], cyl = s_cal[3], fxli = s_cal[4], fyli = s_cal[5];
     const float wM3G = s_cal[6], hM3G = s_cal[7];
@@ -190,14 +214,16 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         const int ri = base + grp;
         const bool valid = ri < nres;
         const int r = rbeg + (valid ? ri : 0);
-        const int p = d.res_point[r];
-        const int t = d.res_target[r];
+        const int p = nx_p;
+        const int t = nx_t;
         const int pl = p - p0;
         const float *pin = s_ptin + pl * 8;
         const float *pr = s_pair + t * 32;
-        uint8_t old_state = (flags & K1F_RESET_OOB) ? (uint8_t) LDSO_B200_RES_IN : d.res_state[r];
-        float old_energy = (flags & K1F_RESET_OOB) ? 0.f : d.res_energy[r];
-        const bool lin = d.res_lin[r] != 0;
+        uint8_t old_state = (flags & K1F_RESET_OOB) ? (uint8_t) LDSO_B200_RES_IN : nx_state;
+        float old_energy = (flags & K1F_RESET_OOB) ? 0.f : nx_energy;
+        const bool lin = nx_lin != 0;
+        const int my_slot = nx_slot;
+        if (base + K1_GROUPS < nres) K1_PREFETCH_RES(base + K1_GROUPS);    // next round's indices, in flight during this round
         // FullSystem::optimize only puts non-linearized residuals into activeResiduals (:744-750): a linearized
         // residual is neither reset nor re-linearized, and mode-0 accumulation skips it.
         const bool touch = valid && !((flags & K1F_LINEARIZE) && lin) && (pin[6] != 0.f);   // pt_sel restricts the pass
@@ -397,10 +423,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
                     for (int i = 0; i < 8; i++) d.res_JpJdF_new[8 * r + i] = JpJdF[i];
                     if (flags & K1F_RESET_OOB) { d.res_state[r] = old_state; d.res_energy[r] = old_energy; }
                 }
-                if (d.res_newest_slot != nullptr) {
-                    const int slot = d.res_newest_slot[r];
-                    if (slot >= 0) d.red[RED_SELECT + slot] = (double) energy_wo;
-                }
+                if (my_slot >= 0) d.red[RED_SELECT + my_slot] = (double) energy_wo;
                 my_energy += (double) ret_energy;
             }
             if (active) my_nres += 1.0;

@@ -40,13 +40,16 @@ __global__ void __launch_bounds__(256) k2a_reduce(DevWindow d, WinState *ws, int
         const int i0 = d.host_item_begin[h], i1 = d.host_item_begin[h + 1];
         const float *p = d.partials + (size_t) i0 * PART_STRIDE + e;
         // four independent chains keep 4+ loads in flight; the order of the final fold is fixed (deterministic)
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
         int i = i0;
-        for (; i + 3 < i1; i += 4, p += 4 * PART_STRIDE) {
-            s0 += (double) p[0]; s1 += (double) p[PART_STRIDE]; s2 += (double) p[2 * PART_STRIDE]; s3 += (double) p[3 * PART_STRIDE];
+        for (; i + 7 < i1; i += 8, p += 8 * PART_STRIDE) {
+            const float v0 = p[0], v1 = p[PART_STRIDE], v2 = p[2 * PART_STRIDE], v3 = p[3 * PART_STRIDE];
+            const float v4 = p[4 * PART_STRIDE], v5 = p[5 * PART_STRIDE], v6 = p[6 * PART_STRIDE], v7 = p[7 * PART_STRIDE];
+            s0 += (double) v0; s1 += (double) v1; s2 += (double) v2; s3 += (double) v3;
+            s4 += (double) v4; s5 += (double) v5; s6 += (double) v6; s7 += (double) v7;
         }
         for (; i < i1; i++, p += PART_STRIDE) s0 += (double) *p;
-        s = (s0 + s1) + (s2 + s3);
+        s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     }
     d.red[g] = s;
 }
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         double *sO = sY3 + 64;              // [4][2][64] partial outputs
         const int a = blockIdx.x % nF, b = blockIdx.x / nF;
         const bool diag = (a == b);
+        if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
         // -------- stage
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {
             const int q = o >> 6, e = o & 63;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             }
         }
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) d.dbg[9] = clock64();
         // -------- stage A: left products
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {         // Z_i = AT_ia * D_i[a,b]
             const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             sT[o] = s;
         }
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0) d.dbg[10] = clock64();
         // -------- stage B: right products, 4 slots of 64 threads split the term lists
         {
             const int slot = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7;
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             sb.H_A[(size_t) col * n + row] = vA;
             sb.H_sc[(size_t) col * n + row] = vS;
         }
+        if (blockIdx.x == 0 && tid == 0) d.dbg[11] = clock64();
         return;
     }
     if ((int) blockIdx.x < nBlocks + nF) {
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     }
     if (!do_select) return;
     {
+        if (tid == 0) d.dbg[12] = clock64();
         const int N = d.newest_total;
         const double *vals = red + RED_SELECT;
         // count valid (energy >= 0) values
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             th = th * th;
             th *= ws->S.overallEnergyTHWeight * ws->S.overallEnergyTHWeight;
         }
-        if (tid == 0) ws->fr[nF - 1].frameEnergyTH = th;
+        if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; d.dbg[13] = clock64(); }
     }
 }
 

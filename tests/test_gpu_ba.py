@@ -303,9 +303,20 @@ def test_marginalize_points(small_win):
     nres = ctx.marginalize_points(idx)
     so, sg = o.system(), ctx.system()
     assert nres == o.res_counts()[2]
-    for k in ("HA", "bA", "Hsc", "bsc"):
+    # noise floor of the reference itself for the mode-2 right-hand sides: the same oracle built with and without FMA
+    # contraction (the reference's -march=native Release build contracts). res_toZeroF = resF - J*delta is a difference
+    # of terms several times larger than itself, so b moves by ~1.6e-4 between the two builds while H moves by 2e-6.
+    o2 = oracle_py.OracleBA(win, threads_mode=1, fast=True)
+    o2.optimize_begin()
+    o2.marginalize_points(idx)
+    s2 = o2.system()
+    for k in ("HA", "Hsc"):
         assert rel_err(sg[k], so[k]) < TOL, (k, rel_err(sg[k], so[k]))
+    for k in ("bA", "bsc"):
+        floor = rel_err(s2[k], so[k])
+        assert rel_err(sg[k], so[k]) < max(TOL, 3 * floor), (k, rel_err(sg[k], so[k]), floor)
     HMo, bMo = o.marg_prior()
     HMg, bMg = ctx.marg_prior()
-    assert rel_err(HMg, HMo) < TOL and rel_err(bMg, bMo) < TOL
+    assert rel_err(HMg, HMo) < TOL
+    assert rel_err(bMg, bMo) < max(TOL, 3 * rel_err(o2.marg_prior()[1], bMo))
     ctx.close()
