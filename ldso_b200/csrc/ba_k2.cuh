@@ -74,8 +74,10 @@ struct SolveBufs {
 // the calibration corner, and a last CTA for FullSystem::setNewFrameEnergyTH (FullSystem.cc:1762-1793).
 // Formulas: AccumulatedTopHessian.cc:221-240 + .h:95-104 and AccumulatedSCHessian.cc:85-118 + .h:93-97,
 // regrouped by output block so that no two CTAs write the same element (deterministic, no atomics).
-#define K2B_THREADS 256
-#define K2B_SMEM_DOUBLES (7 * MAXF * 64 + MAXF * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 128 + 512)
+#define K2B_THREADS 512
+#define K2B_NSLOT (K2B_THREADS / 64)
+#define K2B_SELCAP 8192          // newest-frame energies kept in shared memory by the select CTA
+#define K2B_SMEM_DOUBLES (7 * MAXF * 64 + MAXF * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 128 + K2B_NSLOT * 128)
 #define K2B_SMEM_BYTES (K2B_SMEM_DOUBLES * sizeof(double))
 __device__ __forceinline__ double top_elem(const double *red, int h, int t, int r13, int c13) {
     return red[h * PART_USED + PART_TOP + t * 96 + packed13(r13, c13)];
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         double *sT = sX + MAXF * 64;        // [2*nF][64] L_q * M_q
         double *sY2 = sT + 2 * MAXF * 64;   // [64] sum_k D_b[a,k] * AH_bk^T
         double *sY3 = sY2 + 64;             // [64] sum_j AH_aj * D_a[j,b]
-        double *sO = sY3 + 64;              // [4][2][64] partial outputs
+        double *sO = sY3 + 64;              // [K2B_NSLOT][2][64] partial outputs
         const int a = blockIdx.x % nF, b = blockIdx.x / nF;
         const bool diag = (a == b);
         if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 for (int i = 0; i < 8; i++) s += Lm[r * 8 + i] * sM[q * 64 + i * 8 + c];
                 sT[o] = s;
             }
-        } else if (tid >= 128) {
+        } else if (tid >= 128 && tid < 256) {
             const int o = tid - 128, q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;   // T_0 = AH_ab*M_ab, T_1 = AH_ba*M_ba
             const double *Lm = (q == 0) ? (sAHa + b * 64) : (sAHb + a * 64);
             double s = 0.0;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         {
             const int slot = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7;
             double accA = 0.0, accS = 0.0;
-            for (int i = slot; i < nF; i += 4) {                    // sum_i Z_i * AT_ib^T
+            for (int i = slot; i < nF; i += K2B_NSLOT) {            // sum_i Z_i * AT_ib^T
                 double s = 0.0;
                 for (int j = 0; j < 8; j++) s += sZ[i * 64 + r * 8 + j] * sATb[i * 64 + c * 8 + j];
                 accS += s;
@@ -203,12 +205,12 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 accS += s;
             }
             if (diag) {
-                for (int k = slot; k < nF; k += 4) {                // sum_k X_k * AH_ak^T
+                for (int k = slot; k < nF; k += K2B_NSLOT) {        // sum_k X_k * AH_ak^T
                     double s = 0.0;
                     for (int j = 0; j < 8; j++) s += sX[k * 64 + r * 8 + j] * sAHa[k * 64 + c * 8 + j];
                     accS += s;
                 }
-                for (int q = slot; q < 2 * nF; q += 4) {            // sum_q T_q * L_q^T (host==target blocks are zero)
+                for (int q = slot; q < 2 * nF; q += K2B_NSLOT) {    // sum_q T_q * L_q^T (host==target blocks are zero)
                     const double *Rm = (q < nF) ? (sAHa + q * 64) : (sATa + (q - nF) * 64);
                     double s = 0.0;
                     for (int j = 0; j < 8; j++) s += sT[q * 64 + r * 8 + j] * Rm[c * 8 + j];
@@ -229,8 +231,9 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         __syncthreads();
         if (tid < 64) {
             const int e = tid, r = e >> 3, c = e & 7;
-            const double vA = ((sO[0 * 64 + e] + sO[2 * 64 + e]) + sO[4 * 64 + e]) + sO[6 * 64 + e];
-            const double vS = ((sO[1 * 64 + e] + sO[3 * 64 + e]) + sO[5 * 64 + e]) + sO[7 * 64 + e];
+            double vA = 0.0, vS = 0.0;
+#pragma unroll
+            for (int q = 0; q < K2B_NSLOT; q++) { vA += sO[(2 * q) * 64 + e]; vS += sO[(2 * q + 1) * 64 + e]; }
             const int row = CPARS + 8 * a + r, col = CPARS + 8 * b + c;
             sb.H_A[(size_t) col * n + row] = vA;
             sb.H_sc[(size_t) col * n + row] = vS;
@@ -322,12 +325,20 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         if (tid == 0) d.dbg[12] = clock64();
         const int N = d.newest_total;
         const double *vals = red + RED_SELECT;
-        // count valid (energy >= 0) values
+        extern __shared__ double sk2[];
+        unsigned *skey = (unsigned *) sk2;            // float bit patterns of the valid energies (0x80000000 = excluded)
+        const bool insm = N <= K2B_SELCAP;
         if (tid == 0) { sel_count = 0; sel_prefix = 0; }
         __syncthreads();
         unsigned cnt = 0;
-        for (int i = tid; i < N; i += K2B_THREADS) if (vals[i] >= 0.0) cnt++;
-        atomicAdd(&sel_count, cnt);
+        for (int i = tid; i < N; i += K2B_THREADS) {
+            const double v = vals[i];
+            const bool ok = v >= 0.0;
+            if (insm) skey[i] = ok ? __float_as_uint((float) v) : 0x80000000u;
+            cnt += ok;
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((tid & 31) == 0) atomicAdd(&sel_count, cnt);
         __syncthreads();
         const unsigned m = sel_count;
         float th;
@@ -342,9 +353,10 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 const unsigned pref = sel_prefix;
                 const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
                 for (int i = tid; i < N; i += K2B_THREADS) {
-                    const double v = vals[i];
-                    if (v < 0.0) continue;
-                    const unsigned key = __float_as_uint((float) v);
+                    unsigned key;
+                    if (insm) key = skey[i];
+                    else { const double v = vals[i]; key = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
+                    if (key == 0x80000000u) continue;
                     if ((key & himask) == pref) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1u);
                 }
                 __syncthreads();
