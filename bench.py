@@ -292,30 +292,23 @@ def run_ours(args):
 
 
 def run_e2e(ctx, win, args, torch):
-    nF = win.nF
-    color = np.ascontiguousarray(win.pyramids[nF - 1][0][:, :, 0])
-    pin_color = torch.from_numpy(color).pin_memory().numpy()
+    from ldso_b200 import capi
+    io = capi.StepIO(ctx, win, pinned_alloc=lambda a: torch.from_numpy(a).pin_memory().numpy())
     steps = min(args.steps, 50)
-    h2d = pin_color.nbytes + nF * (9 + 3 + 10 + 10) * 8 + 8 * 8 + win.nP * (4 * 5 + 1 + 64) + (win.nP + 1) * 4 + win.nR * 4
-    n = 8 * nF + 4
-    d2h = (n + 1) * 8 + win.nP * 8 + win.nR * 2
+    for k in range(3):
+        io.upload(); io.step(0); io.download()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(steps):
-        ctx.make_images(nF - 1, pin_color)
-        ctx.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(nF)), win.K)
-        ctx.set_window(win.pt_host, win.pt_u, win.pt_v, win.pt_idepth, win.pt_idepth_zero, win.pt_has_prior, win.pt_color,
-                       win.pt_weights, win.res_begin, win.res_target)
-        ctx.optimize_begin(want_energy=False)
-        ctx.gn_iterations(0, 1)
-        ctx.last_solution()
-        ctx.points()
-        ctx.residuals(with_J=False)
+        io.upload()
+        io.step(0)
+        io.download()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": "GN-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "def": "per step: H2D newest keyframe raw image (+device makeImages), frame states, full window; "
-                   "optimize prologue + 1 GN iteration; D2H lastHS/lastbS/lastX, point arrays, residual states; wall clock"}
+    return {"value": steps / dt, "unit": "GN-iters/s", "h2d_bytes_per_step": int(io.h2d_bytes), "d2h_bytes_per_step": int(io.d2h_bytes),
+            "def": "per step, bare C-ABI calls on persistent host buffers (capi.StepIO): H2D newest keyframe raw image from pinned "
+                   "memory (+device makeImages), frame states, full window; optimize prologue + 1 GN iteration; D2H "
+                   "lastHS/lastbS/lastX, point idepth/step/HdiF, residual states+energies; host wall clock"}
 
 
 def cpu_baseline(win):

@@ -186,6 +186,11 @@ int ldso_b200_gn_phase_b(ldso_b200_ctx *ctx);
 int ldso_b200_kernel_times(ldso_b200_ctx *ctx, int enable, double out_us[4]);
 
 /* ---- read-back (host mirrors of PointHessian / PointFrameResidual / FrameHessian fields) --------------- */
+/* Optional, non-blocking: queue the device->host copy of everything get_last_solution / get_points / get_residuals
+ * return (into the context's pinned staging memory) behind the work already on the stream. The next getter then
+ * waits for that one copy instead of issuing and synchronising its own. The reference has no counterpart (its state is
+ * host-resident); a caller that skips it gets the same values, one synchronise later. */
+int ldso_b200_prefetch_results(ldso_b200_ctx *ctx);
 int ldso_b200_get_energy(ldso_b200_ctx *ctx, double *energy, int *canbreak);
 int ldso_b200_get_last_solution(ldso_b200_ctx *ctx, double *lastHS, double *lastbS, double *lastX);
 /* any pointer may be NULL. Hcd4 is [nPoints*4]. */

@@ -55,7 +55,7 @@ SYMBOLS = [
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
-    "ldso_b200_gn_phase_b", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
+    "ldso_b200_gn_phase_b", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
     "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
@@ -351,6 +351,9 @@ class Context:
             _f(out.get("projectedTo")), _f(out.get("centerProjectedTo"))))
         return out
 
+    def prefetch_results(self):
+        self._chk(self.L.ldso_b200_prefetch_results(self.ctx))
+
     def frames(self):
         nF = self.nF
         out = dict(state=np.zeros((nF, 10)), step=np.zeros((nF, 10)), frameEnergyTH=np.zeros(nF, np.float32),
@@ -413,3 +416,74 @@ class Context:
         self._chk(self.L.ldso_b200_tracker_track(self.ctx, _d(R), _d(t), C.byref(a), C.byref(b), int(coarsest), _d(mr), _d(lr),
                                                  _d(lf), C.byref(ok)))
         return bool(ok.value), R, t, a.value, b.value, lr, lf
+
+
+class StepIO:
+    """Persistent host buffers + pre-built C argument blocks for one window, the way a C++ caller holds them: every
+    call below is the bare C-ABI call on memory allocated once (no per-call numpy allocation or dtype conversion).
+    Used by bench.py's end-to-end leg."""
+
+    def __init__(self, ctx: Context, win, pinned_alloc=None):
+        self.ctx, self.L, self.h = ctx, ctx.L, ctx.ctx
+        nF, nP, nR = win.nF, win.nP, win.nR
+        self.nF, self.nP, self.nR = nF, nP, nR
+        alloc = pinned_alloc or (lambda a: a)
+        k = self.keep = {}
+        # ---- inputs
+        k["color"] = alloc(np.ascontiguousarray(win.pyramids[nF - 1][0][:, :, 0], np.float32))
+        fr = np.zeros(nF, FRAME_DTYPE)
+        fr["evalR"] = np.asarray(win.Rcw, np.float64).reshape(nF, 9); fr["evalT"] = np.asarray(win.tcw, np.float64).reshape(nF, 3)
+        fr["state_zero"] = np.asarray(win.state_zero, np.float64).reshape(nF, 10); fr["state"] = np.asarray(win.state, np.float64).reshape(nF, 10)
+        fr["ab_exposure"] = np.asarray(win.ab_exposure, np.float32); fr["frameEnergyTH"] = 8 * 8 * 8
+        fr["frame_id"] = np.asarray(win.frame_id, np.int32); fr["image_slot"] = np.arange(nF, dtype=np.int32)
+        k["frames"] = fr
+        k["Ks"] = np.ascontiguousarray(win.K, np.float64)
+        k["Kz"] = np.ascontiguousarray(k["Ks"] * np.float64(np.float32(1.0) / np.float32(50.0)))
+        for name, dt in (("pt_host", np.int32), ("pt_u", np.float32), ("pt_v", np.float32), ("pt_idepth", np.float32),
+                         ("pt_idepth_zero", np.float32), ("pt_has_prior", np.uint8), ("pt_color", np.float32),
+                         ("pt_weights", np.float32), ("res_begin", np.int32), ("res_target", np.int32)):
+            k[name] = alloc(np.ascontiguousarray(getattr(win, name), dt))
+        w = self.w = WindowC()
+        w.nPoints, w.nResiduals = nP, nR
+        w.pt_host = _i(k["pt_host"]); w.pt_u = _f(k["pt_u"]); w.pt_v = _f(k["pt_v"]); w.pt_idepth = _f(k["pt_idepth"])
+        w.pt_idepth_zero = _f(k["pt_idepth_zero"]); w.pt_has_prior = _b(k["pt_has_prior"]); w.pt_color = _f(k["pt_color"])
+        w.pt_weights = _f(k["pt_weights"]); w.res_begin = _i(k["res_begin"]); w.res_target = _i(k["res_target"])
+        self._wref = C.byref(w)
+        self._color, self._frames = _f(k["color"]), fr.ctypes.data_as(C.POINTER(FrameStateC))
+        self._Ks, self._Kz = _d(k["Ks"]), _d(k["Kz"])
+        # ---- outputs
+        n = 8 * nF + 4
+        o = self.out = dict(lastHS=np.zeros((n, n), np.float64, order="F"), lastbS=np.zeros(n), lastX=np.zeros(n),
+                            idepth=np.zeros(nP, np.float32), step=np.zeros(nP, np.float32), HdiF=np.zeros(nP, np.float32),
+                            state_state=np.zeros(nR, np.uint8), state_NewState=np.zeros(nR, np.uint8),
+                            state_energy=np.zeros(nR, np.float32))
+        self._sol = (_d(o["lastHS"]), _d(o["lastbS"]), _d(o["lastX"]))
+        self._pts = (_f(o["idepth"]), None, _f(o["step"]), _f(o["HdiF"]), None, None, None, None)
+        self._res = (_b(o["state_state"]), _b(o["state_NewState"]), _f(o["state_energy"]), None, None, None, None, None, None, None)
+        self.h2d_bytes = (k["color"].nbytes + nF * (9 + 3 + 10 + 10) * 8 + 8 * 8 +
+                          sum(k[x].nbytes for x in ("pt_host", "pt_u", "pt_v", "pt_idepth", "pt_idepth_zero", "pt_has_prior",
+                                                    "pt_color", "pt_weights", "res_begin", "res_target")))
+        self.d2h_bytes = sum(v.nbytes for v in o.values())
+
+    def upload(self):
+        """newest keyframe's raw image (+ device makeImages), frame states, the whole window"""
+        L, h, chk = self.L, self.h, self.ctx._chk
+        chk(L.ldso_b200_make_images(h, self.nF - 1, self._color))
+        chk(L.ldso_b200_set_frames(h, self.nF, self._frames, self._Ks, self._Kz))
+        chk(L.ldso_b200_set_window(h, self._wref))
+        self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
+
+    def step(self, iteration=0):
+        """optimize() prologue + one Gauss-Newton iteration; the result read-back is queued behind it"""
+        L, h, chk = self.L, self.h, self.ctx._chk
+        chk(L.ldso_b200_optimize_begin(h, None))
+        chk(L.ldso_b200_gn_iterations(h, int(iteration), 1))
+        chk(L.ldso_b200_prefetch_results(h))
+
+    def download(self):
+        """solution (lastHS, lastbS, lastX), point idepth/step/HdiF, residual states + energies"""
+        L, h, chk = self.L, self.h, self.ctx._chk
+        chk(L.ldso_b200_get_last_solution(h, *self._sol))
+        chk(L.ldso_b200_get_points(h, *self._pts))
+        chk(L.ldso_b200_get_residuals(h, *self._res))
+        return self.out

@@ -48,6 +48,7 @@ struct ldso_b200_ctx {
     WinState *ws_host = nullptr;       // pinned staging copy
     SolveBufs sb;
     double *solve_mem = nullptr;
+    double *sol_host = nullptr;      // pinned staging for get_last_solution
     int *iteration_dev = nullptr;
     uint8_t *pt_sel_dev = nullptr;
     char *arena_dev = nullptr, *arena_host = nullptr;
@@ -57,6 +58,9 @@ struct ldso_b200_ctx {
             res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, res_JpJdF, dl_end, res_JpJdF_new, total;
     } lay;
     bool mirror_valid = false;
+    bool sol_valid = false;          // sol_host holds the current [lastHS | lastbS | lastX]
+    bool results_inflight = false;   // prefetch_results queued the read-back copies; results_ready marks their end
+    cudaEvent_t results_ready = nullptr;
     std::vector<double> evalpt_key, Pns_host;
     cudaEvent_t window_copied = nullptr;
     // one GN iteration (K3 -> K1 -> K2a -> K2b) captured as a CUDA graph; re-captured when the window arena changes
@@ -183,9 +187,13 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     cudaMemset(c->ws_dev, 0, sizeof(WinState));
     memset(c->ws_host, 0, sizeof(WinState));
     double *p = c->solve_mem;
-    c->sb.H_A = p; p += nn; c->sb.H_sc = p; p += nn; c->sb.HM = p; p += nn; c->sb.Pns = p; p += nn; c->sb.lastHS = p; p += nn;
+    c->sb.H_A = p; p += nn; c->sb.H_sc = p; p += nn; c->sb.HM = p; p += nn; c->sb.Pns = p; p += nn;
     p += 2 * nn;   // spare
-    c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
+    // lastHS | lastbS | lastX are contiguous: get_last_solution reads them back with one copy
+    c->sb.lastHS = p; p += nn; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
+    c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN;
+    ok = cudaMallocHost(&c->sol_host, sizeof(double) * (nn + 2 * MAXN)) == cudaSuccess;
+    if (!ok) { fprintf(stderr, "ldso_b200: pinned allocation failed\n"); delete c; return nullptr; }
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
     c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
     cudaEventCreateWithFlags(&c->frames_copied, cudaEventDisableTiming);
@@ -200,7 +208,7 @@ static void free_window(ldso_b200_ctx *c) {
     c->win_allocs.clear();
     if (c->arena_dev) { cudaFree(c->arena_dev); c->arena_dev = nullptr; }
     if (c->arena_host) { cudaFreeHost(c->arena_host); c->arena_host = nullptr; }
-    c->mirror_valid = false;
+    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
     c->gn_graph_valid = false;
     c->have_window = false;
 }
@@ -221,6 +229,7 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->ws_dev) cudaFree(c->ws_dev);
     if (c->ws_host) cudaFreeHost(c->ws_host);
+    if (c->sol_host) cudaFreeHost(c->sol_host);
     if (c->iteration_dev) cudaFree(c->iteration_dev);
     if (c->solve_mem) cudaFree(c->solve_mem);
     if (c->trk_partials) cudaFree(c->trk_partials);
@@ -252,7 +261,7 @@ extern "C" int ldso_b200_synchronize(ldso_b200_ctx *c) {
 #define LAUNCH_CHECK(c)                                            \
     do {                                                           \
         (c)->launches++;                                           \
-        (c)->mirror_valid = false;                                 \
+        (c)->mirror_valid = false; (c)->results_inflight = false; (c)->sol_valid = false;                                 \
         cudaError_t e__ = cudaGetLastError();                      \
         if (e__ != cudaSuccess) return (c)->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
     } while (0)
@@ -300,10 +309,8 @@ extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *co
     CUDA_CHECK_RET(c, cudaEventRecord(c->copy_done, c->stream));
     for (int l = 0; l < c->levels; l++) {
         const int npx = c->lw[l] * c->lh[l];
-        k_pyr_intensity<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->scratch, l == 0 ? nullptr : c->img[slot][l - 1], c->img[slot][l],
-                                                                    c->lw[l], c->lh[l], l == 0 ? 0 : c->lw[l - 1]);
-        LAUNCH_CHECK(c);
-        k_pyr_gradients<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->img[slot][l], c->lw[l], c->lh[l]);
+        k_pyr_level<<<(npx + 255) / 256, 256, 0, c->stream>>>(c->scratch, l == 0 ? nullptr : c->img[slot][l - 1], c->img[slot][l],
+                                                                c->lw[l], c->lh[l], l == 0 ? 0 : c->lw[l - 1]);
         LAUNCH_CHECK(c);
     }
     // the caller's buffer is free once the copy has landed; the pyramid kernels keep running asynchronously
@@ -454,7 +461,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (win->res_toZeroF && nR > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(d.res_toZero, win->res_toZeroF, 32 * (size_t) nR, cudaMemcpyHostToDevice, c->stream));
     if (!same_topology) CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * (size_t) std::max(nR, 1), c->stream));
     if (win->res_toZeroF) CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // pageable source
-    c->mirror_valid = false;
+    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
     c->have_window = true;
     return LDSO_B200_OK;
 }
@@ -521,7 +528,9 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     if (!c || !frames || !calib_value_scaled || !calib_value_zero) return LDSO_B200_ERR_ARG;
     if (nFrames < 1 || nFrames > MAXF) return c->fail(LDSO_B200_ERR_ARG, "nFrames must be in [1, LDSO_B200_MAX_FRAMES]");
     cudaSetDevice(c->device);
-    // ws_host (pinned) is free: every set_frames / get_frames waits for its own copy before returning
+    // ws_host (pinned) may still be the source of the previous call's upload: wait for that copy only (not for the
+    // kernels queued behind it), so that back-to-back calls overlap host packing with device work
+    CUDA_CHECK_RET(c, cudaEventSynchronize(c->frames_copied));
     using namespace hostmath;
     WinState &W = *c->ws_host;
     // the adjoints and the null-space projector depend only on the evaluation points (worldToCam_evalPT, state_zero's
@@ -647,16 +656,13 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
 
     c->nF = nF; c->n = n;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->ws_dev, c->ws_host, sizeof(WinState), cudaMemcpyHostToDevice, c->stream));
-    if (!evalpt_cached)
+    CUDA_CHECK_RET(c, cudaEventRecord(c->frames_copied, c->stream));
+    if (!evalpt_cached)     // pageable source: staged before the call returns
         CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.Pns, c->Pns_host.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
     LAUNCH_CHECK(c);
-    // P (pageable std::vector) must be consumed before it goes out of scope; ws_host is pinned and only reused
-    // after the synchronize at the top of the next call
-    CUDA_CHECK_RET(c, cudaEventRecord(c->frames_copied, c->stream));
-    CUDA_CHECK_RET(c, cudaEventSynchronize(c->frames_copied));
     c->have_frames = true;
     if (prev_nF != nF) c->derived_dirty = true;    // work items / newest-frame slots depend on nF only
     return LDSO_B200_OK;
@@ -783,14 +789,22 @@ extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *l
     return ldso_b200_get_last_solution(c, lastHS, lastbS, lastX);
 }
 
+static int wait_results(ldso_b200_ctx *c);
 extern "C" int ldso_b200_get_last_solution(ldso_b200_ctx *c, double *lastHS, double *lastbS, double *lastX) {
     if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
     const int n = c->n;
-    if (lastHS) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastHS, c->sb.lastHS, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
-    if (lastbS) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastbS, c->sb.lastbS, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
-    if (lastX) CUDA_CHECK_RET(c, cudaMemcpyAsync(lastX, c->sb.lastX, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // one copy of [lastHS | lastbS | lastX] into pinned staging memory, then plain memcpy into the caller's buffers
+    const size_t nn = (size_t) MAXN * MAXN;
+    RET_IF(wait_results(c));
+    if (!c->sol_valid) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sol_host, c->sb.lastHS, sizeof(double) * (nn + 2 * MAXN), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+        c->sol_valid = true;
+    }
+    if (lastHS) memcpy(lastHS, c->sol_host, sizeof(double) * n * n);
+    if (lastbS) memcpy(lastbS, c->sol_host + nn, sizeof(double) * n);
+    if (lastX) memcpy(lastX, c->sol_host + nn + MAXN, sizeof(double) * n);
     return LDSO_B200_OK;
 }
 
@@ -918,7 +932,7 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         for (int i = 0; i < n_iterations; i++) {
             CUDA_CHECK_RET(c, cudaGraphLaunch(c->gn_graph, c->stream));
             c->launches += 4;
-            c->mirror_valid = false;
+            { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
         }
         return LDSO_B200_OK;
     }
@@ -982,7 +996,34 @@ extern "C" int ldso_b200_get_energy(ldso_b200_ctx *c, double *energy, int *canbr
 #define D2H(dst, src, bytes) do { if (dst) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
 
 // one D2H of the contiguous result range into the pinned mirror (valid until the next launch)
+// Optional hint: queue the read-back of everything the getters below return (solution, point and residual arrays) into
+// pinned staging memory right behind the work already on the stream, without blocking. The next getter then only waits
+// for that one event instead of issuing its own copy + synchronize.
+extern "C" int ldso_b200_prefetch_results(ldso_b200_ctx *c) {
+    if (!c || !c->have_window || !c->have_frames) return LDSO_B200_ERR_STATE;
+    cudaSetDevice(c->device);
+    auto &L = c->lay;
+    const size_t nn = (size_t) MAXN * MAXN;
+    if (!c->mirror_valid)
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->sol_valid)
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sol_host, c->sb.lastHS, sizeof(double) * (nn + 2 * MAXN), cudaMemcpyDeviceToHost, c->stream));
+    if (!c->results_ready) CUDA_CHECK_RET(c, cudaEventCreateWithFlags(&c->results_ready, cudaEventDisableTiming));
+    CUDA_CHECK_RET(c, cudaEventRecord(c->results_ready, c->stream));
+    c->results_inflight = true;
+    return LDSO_B200_OK;
+}
+static int wait_results(ldso_b200_ctx *c) {
+    if (!c->results_inflight) return LDSO_B200_OK;
+    CUDA_CHECK_RET(c, cudaEventSynchronize(c->results_ready));
+    c->results_inflight = false;
+    c->mirror_valid = true;
+    c->sol_valid = true;
+    return LDSO_B200_OK;
+}
+
 static int refresh_mirror(ldso_b200_ctx *c) {
+    RET_IF(wait_results(c));
     if (c->mirror_valid) return LDSO_B200_OK;
     auto &L = c->lay;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));

@@ -352,12 +352,18 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 __syncthreads();
                 const unsigned pref = sel_prefix;
                 const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
-                for (int i = tid; i < N; i += K2B_THREADS) {
-                    unsigned key;
-                    if (insm) key = skey[i];
-                    else { const double v = vals[i]; key = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
-                    if (key == 0x80000000u) continue;
-                    if ((key & himask) == pref) atomicAdd(&hist[(key >> (8 * pass)) & 0xffu], 1u);
+                // energies of one frame share their leading bytes: aggregate equal bins inside the warp first
+                // (one shared-memory atomic per distinct bin per warp instead of 32 serialised ones)
+                for (int i = tid; i < ((N + 31) & ~31); i += K2B_THREADS) {
+                    unsigned key = 0x80000000u;
+                    if (i < N) {
+                        if (insm) key = skey[i];
+                        else { const double v = vals[i]; key = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
+                    }
+                    const bool act = (key != 0x80000000u) && ((key & himask) == pref);
+                    const unsigned bin = act ? ((key >> (8 * pass)) & 0xffu) : 256u;
+                    const unsigned mm = __match_any_sync(0xffffffffu, bin);
+                    if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist[bin], (unsigned) __popc(mm));
                 }
                 __syncthreads();
                 if (tid < 32) {

@@ -17,31 +17,27 @@ __global__ void k_unpack_aos3(const float4 *__restrict__ src, float *__restrict_
     dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
 }
 
-// level 0: intensity from the raw image; level l>0: 2x2 box filter of level l-1 (FrameHessian.cc:69-81)
-__global__ void k_pyr_intensity(const float *__restrict__ color, const float4 *__restrict__ prev, float4 *__restrict__ dst,
-                                int wl, int hl, int wlm1) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wl * hl) return;
-    float v;
-    if (prev == nullptr) v = color[i];
-    else {
-        const int x = i % wl, y = i / wl;
-        const float4 *b = prev + 2 * x + 2 * y * wlm1;
-        v = 0.25f * (b[0].x + b[1].x + b[wlm1].x + b[wlm1 + 1].x);
-    }
-    dst[i] = make_float4(v, 0.f, 0.f, 0.f);
+// One launch per pyramid level: intensity (raw image at level 0, 2x2 box filter of level l-1 above) and the central
+// differences of the same level over the flat index range [wl, wl*(hl-1)) (FrameHessian.cc:69-92; dx at a row border
+// reads the neighbouring row's pixel exactly like the reference's flat indexing does). The four neighbours'
+// intensities are recomputed with the same expression instead of being read back, so one launch per level suffices.
+__device__ __forceinline__ float pyr_val(const float *__restrict__ color, const float4 *__restrict__ prev, int j, int wl, int wlm1) {
+    if (prev == nullptr) return color[j];
+    const int x = j % wl, y = j / wl;
+    const float4 *b = prev + 2 * x + 2 * y * wlm1;
+    return 0.25f * (b[0].x + b[1].x + b[wlm1].x + b[wlm1 + 1].x);
 }
-
-// central differences over the flat index range [wl, wl*(hl-1)) (FrameHessian.cc:83-92); dx at a row border reads
-// the neighbouring row's pixel exactly like the reference's flat indexing does.
-__global__ void k_pyr_gradients(float4 *__restrict__ img, int wl, int hl) {
+__global__ void k_pyr_level(const float *__restrict__ color, const float4 *__restrict__ prev, float4 *__restrict__ dst,
+                            int wl, int hl, int wlm1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < wl || idx >= wl * (hl - 1)) return;
-    float dx = 0.5f * (img[idx + 1].x - img[idx - 1].x);
-    float dy = 0.5f * (img[idx + wl].x - img[idx - wl].x);
-    if (isnan(dx) || fabsf(dx) > 255.0f) dx = 0;
-    if (isnan(dy) || fabsf(dy) > 255.0f) dy = 0;
-    float *px = (float *) (img + idx);   // only dx,dy are written: neighbours read .x concurrently
-    px[1] = dx;
-    px[2] = dy;
+    if (idx >= wl * hl) return;
+    const float v = pyr_val(color, prev, idx, wl, wlm1);
+    float dx = 0.f, dy = 0.f;
+    if (idx >= wl && idx < wl * (hl - 1)) {
+        dx = 0.5f * (pyr_val(color, prev, idx + 1, wl, wlm1) - pyr_val(color, prev, idx - 1, wl, wlm1));
+        dy = 0.5f * (pyr_val(color, prev, idx + wl, wl, wlm1) - pyr_val(color, prev, idx - wl, wl, wlm1));
+        if (isnan(dx) || fabsf(dx) > 255.0f) dx = 0;
+        if (isnan(dy) || fabsf(dy) > 255.0f) dy = 0;
+    }
+    dst[idx] = make_float4(v, dx, dy, 0.f);
 }

@@ -320,3 +320,33 @@ def test_marginalize_points(small_win):
     assert rel_err(HMg, HMo) < TOL
     assert rel_err(bMg, bMo) < max(TOL, 3 * rel_err(o2.marg_prior()[1], bMo))
     ctx.close()
+
+
+def test_stepio_prefetch_matches_getters(small_win):
+    """The persistent-buffer call sequence bench.py's end-to-end leg uses (capi.StepIO: raw C-ABI calls +
+    ldso_b200_prefetch_results) returns exactly what the plain getters return, and stale prefetches are dropped."""
+    win = small_win
+    ctx = _ctx(win)
+    io = capi.StepIO(ctx, win)
+    for rep in range(2):                      # second round runs on the same-topology fast path
+        io.upload(); io.step(0)
+        out = {k: v.copy() for k, v in io.download().items()}
+        ref = capi.Context(win.w, win.h, win.levels)
+        ref.load_synth_window(win)
+        ref.optimize_begin(want_energy=False); ref.gn_iterations(0, 1)
+        sol, pts, res = ref.last_solution(), ref.points(), ref.residuals(with_J=False)
+        for k in ("lastHS", "lastbS", "lastX"):
+            assert np.array_equal(out[k], sol[k]), k
+        for k in ("idepth", "step", "HdiF"):
+            assert np.array_equal(out[k], pts[k]), k
+        for k in ("state_state", "state_NewState", "state_energy"):
+            assert np.array_equal(out[k], res[k]), k
+        ref.close()
+    # a launch after the prefetch invalidates it: the getters must return the newer state
+    io.upload(); io.step(0)
+    ctx.gn_iterations(1, 1)
+    a = ctx.last_solution()["lastX"]
+    ctx.prefetch_results()
+    b = ctx.last_solution()["lastX"]
+    assert np.array_equal(a, b) and not np.array_equal(a, out["lastX"])
+    ctx.close()

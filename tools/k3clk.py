@@ -8,6 +8,7 @@ ctx.optimize_begin(); ctx.gn_iterations(0, 30); ctx.synchronize()
 buf = (C.c_longlong*32)()
 ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
 t = np.array(buf[:10]); print("K3 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
+t = np.array(buf[10:14]); print("K3 block step k0=8 [diag, panel, trailing]:", np.diff(t))
 t = np.array(buf[16:24]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
 t = np.array(buf[24:28]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
 t = np.array(buf[28:30]); print("K2b select-CTA cycles:", np.diff(t))
