@@ -468,9 +468,10 @@ class StepIO:
     def upload(self):
         """newest keyframe's raw image (+ device makeImages), frame states, the whole window"""
         L, h, chk = self.L, self.h, self.ctx._chk
-        chk(L.ldso_b200_make_images(h, self.nF - 1, self._color))
-        chk(L.ldso_b200_set_frames(h, self.nF, self._frames, self._Ks, self._Kz))
+        # the two asynchronous uploads first; make_images blocks until the caller's image buffer has been consumed
         chk(L.ldso_b200_set_window(h, self._wref))
+        chk(L.ldso_b200_set_frames(h, self.nF, self._frames, self._Ks, self._Kz))
+        chk(L.ldso_b200_make_images(h, self.nF - 1, self._color))
         self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
 
     def step(self, iteration=0):

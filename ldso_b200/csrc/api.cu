@@ -55,9 +55,10 @@ struct ldso_b200_ctx {
     struct Layout {
         size_t pt_host, pt_res_begin, res_point, res_target, topo_end, pt_u, pt_v, pt_color, pt_weights, pt_priorF, pt_idepth_backup,
             res_lin, res_state, dl_begin, pt_idepth, pt_idepth_zero, ul_end, pt_step, pt_HdiF, pt_bdSumF, pt_Hdd, pt_bd, pt_Hcd,
-            res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, res_JpJdF, dl_end, res_JpJdF_new, total;
+            res_new_state, res_active, res_energy, res_new_energy, res_new_energy_wo, dl_light_end, res_JpJdF, dl_end, res_JpJdF_new, total;
     } lay;
-    bool mirror_valid = false;
+    bool mirror_valid = false;       // pinned mirror holds the current [res_state, dl_light_end) arrays
+    bool mirror_full_valid = false;  // ... and the bulky [dl_light_end, dl_end) tail (JpJdF) as well
     bool sol_valid = false;          // sol_host holds the current [lastHS | lastbS | lastX]
     bool results_inflight = false;   // prefetch_results queued the read-back copies; results_ready marks their end
     cudaEvent_t results_ready = nullptr;
@@ -208,7 +209,7 @@ static void free_window(ldso_b200_ctx *c) {
     c->win_allocs.clear();
     if (c->arena_dev) { cudaFree(c->arena_dev); c->arena_dev = nullptr; }
     if (c->arena_host) { cudaFreeHost(c->arena_host); c->arena_host = nullptr; }
-    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
+    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
     c->gn_graph_valid = false;
     c->have_window = false;
 }
@@ -261,13 +262,15 @@ extern "C" int ldso_b200_synchronize(ldso_b200_ctx *c) {
 #define LAUNCH_CHECK(c)                                            \
     do {                                                           \
         (c)->launches++;                                           \
-        (c)->mirror_valid = false; (c)->results_inflight = false; (c)->sol_valid = false;                                 \
+        (c)->mirror_valid = false; (c)->results_inflight = false; (c)->sol_valid = false; (c)->mirror_full_valid = false;                                 \
         cudaError_t e__ = cudaGetLastError();                      \
         if (e__ != cudaSuccess) return (c)->fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
     } while (0)
 
 #define RET_IF(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 #define D2H(dst, src, bytes) do { if (dst) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream)); } while (0)
+
+static int wait_results(ldso_b200_ctx *c);
 
 // ---------------------------------------------------------------------------------------------- images
 static int ensure_slot(ldso_b200_ctx *c, int slot) {
@@ -371,7 +374,9 @@ static int alloc_window(ldso_b200_ctx *c, int nP, int nR) {
     L.pt_step = A.take(4 * nPs); L.pt_HdiF = A.take(4 * nPs); L.pt_bdSumF = A.take(4 * nPs); L.pt_Hdd = A.take(4 * nPs);
     L.pt_bd = A.take(4 * nPs); L.pt_Hcd = A.take(16 * nPs);
     L.res_new_state = A.take(nRs); L.res_active = A.take(nRs); L.res_energy = A.take(4 * nRs); L.res_new_energy = A.take(4 * nRs);
-    L.res_new_energy_wo = A.take(4 * nRs); L.res_JpJdF = A.take(32 * nRs);
+    L.res_new_energy_wo = A.take(4 * nRs);
+    L.dl_light_end = A.off;
+    L.res_JpJdF = A.take(32 * nRs);
     L.dl_end = A.off;
     L.res_JpJdF_new = A.take(32 * nRs);
     L.total = A.off;
@@ -416,6 +421,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (nP > 0 && (win->res_begin[0] != 0 || win->res_begin[nP] != nR)) return c->fail(LDSO_B200_ERR_ARG, "res_begin does not cover the residual arrays");
     for (int r = 0; r < nR; r++) if (win->res_target[r] < 0 || win->res_target[r] >= MAXF) return c->fail(LDSO_B200_ERR_ARG, "res_target out of range");
     if (c->window_copied) CUDA_CHECK_RET(c, cudaEventSynchronize(c->window_copied));     // the pinned mirror may still be in flight
+    RET_IF(wait_results(c));                                                              // ... or be the target of a queued read-back
     DevWindow &d = c->d;
     const bool same_topology = c->have_window && d.nP == nP && d.nR == nR && (int) c->h_pt_host.size() == nP && nP > 0 &&
                                std::equal(win->pt_host, win->pt_host + nP, c->h_pt_host.begin()) &&
@@ -461,7 +467,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (win->res_toZeroF && nR > 0) CUDA_CHECK_RET(c, cudaMemcpyAsync(d.res_toZero, win->res_toZeroF, 32 * (size_t) nR, cudaMemcpyHostToDevice, c->stream));
     if (!same_topology) CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * (size_t) std::max(nR, 1), c->stream));
     if (win->res_toZeroF) CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // pageable source
-    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
+    { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
     c->have_window = true;
     return LDSO_B200_OK;
 }
@@ -507,7 +513,7 @@ static int build_derived(ldso_b200_ctx *c) {
     rc |= dev_alloc(c, &d.partials, (size_t) std::max(d.nItems, 1) * PART_STRIDE);
     rc |= dev_alloc(c, &d.item_stats, (size_t) std::max(d.nItems, 1) * 4);
     rc |= dev_alloc(c, &d.red, (size_t) RED_SELECT + std::max(d.newest_total, 1) + 16);
-    rc |= dev_alloc(c, &d.dbg, 32);
+    rc |= dev_alloc(c, &d.dbg, 32 + 3 * (size_t) std::max(d.nItems, 1));
     if (rc) return LDSO_B200_ERR_CUDA;
     rc |= dev_upload(c, items_dev, items.data(), items.size());
     rc |= dev_upload(c, hib_dev, hib.data(), MAXF + 1);
@@ -700,9 +706,9 @@ static int launch_k1(ldso_b200_ctx *c, int flags, const uint8_t *sel = nullptr) 
     return LDSO_B200_OK;
 }
 static int launch_k2a(ldso_b200_ctx *c, int full) {
-    const int nb = (MAXF * PART_USED + 255) / 256 + 1;
+    const int nb = (MAXF * PART_USED + 63) / 64 + 1;
     c->kt_begin("k2a");
-    k2a_reduce<<<nb, 256, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
+    k2a_reduce<<<nb, K2A_THREADS, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
     c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
@@ -789,7 +795,6 @@ extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *l
     return ldso_b200_get_last_solution(c, lastHS, lastbS, lastX);
 }
 
-static int wait_results(ldso_b200_ctx *c);
 extern "C" int ldso_b200_get_last_solution(ldso_b200_ctx *c, double *lastHS, double *lastbS, double *lastX) {
     if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
@@ -932,7 +937,7 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         for (int i = 0; i < n_iterations; i++) {
             CUDA_CHECK_RET(c, cudaGraphLaunch(c->gn_graph, c->stream));
             c->launches += 4;
-            { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; }
+            { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
         }
         return LDSO_B200_OK;
     }
@@ -1005,7 +1010,7 @@ extern "C" int ldso_b200_prefetch_results(ldso_b200_ctx *c) {
     auto &L = c->lay;
     const size_t nn = (size_t) MAXN * MAXN;
     if (!c->mirror_valid)
-        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_light_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
     if (!c->sol_valid)
         CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sol_host, c->sb.lastHS, sizeof(double) * (nn + 2 * MAXN), cudaMemcpyDeviceToHost, c->stream));
     if (!c->results_ready) CUDA_CHECK_RET(c, cudaEventCreateWithFlags(&c->results_ready, cudaEventDisableTiming));
@@ -1022,13 +1027,21 @@ static int wait_results(ldso_b200_ctx *c) {
     return LDSO_B200_OK;
 }
 
-static int refresh_mirror(ldso_b200_ctx *c) {
+static int refresh_mirror(ldso_b200_ctx *c, bool full = false) {
     RET_IF(wait_results(c));
-    if (c->mirror_valid) return LDSO_B200_OK;
     auto &L = c->lay;
-    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    bool copied = false;
+    if (!c->mirror_valid) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.res_state, c->arena_dev + L.res_state, L.dl_light_end - L.res_state, cudaMemcpyDeviceToHost, c->stream));
+        copied = true;
+    }
+    if (full && !c->mirror_full_valid) {
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->arena_host + L.dl_light_end, c->arena_dev + L.dl_light_end, L.dl_end - L.dl_light_end, cudaMemcpyDeviceToHost, c->stream));
+        copied = true;
+    }
+    if (copied) CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     c->mirror_valid = true;
+    if (full) c->mirror_full_valid = true;
     return LDSO_B200_OK;
 }
 #define FROM_MIRROR(dst, off, bytes) do { if (dst) memcpy(dst, c->arena_host + (off), (bytes)); } while (0)
@@ -1051,7 +1064,7 @@ extern "C" int ldso_b200_get_residuals(ldso_b200_ctx *c, uint8_t *state_state, u
                                        float *JpJdF8, float *J74, float *projectedTo16, float *centerProjectedTo3) {
     if (!c || !c->have_window) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
-    RET_IF(refresh_mirror(c));
+    RET_IF(refresh_mirror(c, JpJdF8 != nullptr));
     const size_t nR = c->d.nR;
     auto &L = c->lay;
     FROM_MIRROR(state_state, L.res_state, nR); FROM_MIRROR(state_NewState, L.res_new_state, nR); FROM_MIRROR(state_energy, L.res_energy, 4 * nR);
@@ -1138,6 +1151,15 @@ extern "C" int ldso_b200_debug_clocks(ldso_b200_ctx *c, long long *out32) {
     if (c->d.dbg) CUDA_CHECK_RET(c, cudaMemcpyAsync(out32 + 16, c->d.dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_debug_cta_spans(ldso_b200_ctx *c, long long *out, int cap_items) {
+    if (!c || !out || !c->d.dbg) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int n = std::min(cap_items, c->d.nItems);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out, c->d.dbg + 32, sizeof(long long) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return n;
 }
 
 extern "C" int ldso_b200_get_nullspace_projector(ldso_b200_ctx *c, double *P) {

@@ -84,6 +84,13 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     int dbgi = 0;
 #define K1_STAMP() do { if (tid == 0 && blockIdx.x == 0) d.dbg[dbgi] = clock64(); dbgi++; } while (0)
     K1_STAMP();
+    if (tid == 0) {          // per-CTA wall-clock span (development aid, 3 stores per CTA)
+        unsigned long long gt; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        d.dbg[32 + 3 * blockIdx.x] = (long long) gt;
+        d.dbg[32 + 3 * blockIdx.x + 2] = smid;
+    }
     // ---------------- phase 0: stage per-host constants, clear records
     for (int i = tid; i < MAXF * 32; i += K1_THREADS) {
         int t = i >> 5, k = i & 31;
@@ -614,4 +621,9 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         else if (tid < 84) part[PART_BC + (tid - 80)] = accX;
     }
     K1_STAMP();   // 7: phase C done
+    if (tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        d.dbg[32 + 3 * blockIdx.x + 1] = (long long) gt;
+    }
 }

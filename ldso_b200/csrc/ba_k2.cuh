@@ -10,7 +10,9 @@
 // (the reference casts its per-thread float accumulators to double before summing them,
 //  AccumulatedTopHessian.cc:215-219, AccumulatedSCHessian.cc:78-83,101-105).
 // The last block folds the per-item scalar statistics.
-__global__ void __launch_bounds__(256) k2a_reduce(DevWindow d, WinState *ws, int full, int multi) {
+#define K2A_THREADS 512
+#define K2A_SLICES (K2A_THREADS / 64)     // 8 threads share one output element, each folds every 8th work item
+__global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState *ws, int full, int multi) {
     const int nF = ws->nF;
     if (blockIdx.x == gridDim.x - 1) {
         // stats: warp w (<4) reduces stat w over all items
@@ -32,26 +34,39 @@ __global__ void __launch_bounds__(256) k2a_reduce(DevWindow d, WinState *ws, int
         return;
     }
     if (!full) return;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= MAXF * PART_USED) return;
-    const int h = g / PART_USED, e = g - h * PART_USED;
+    // 64 consecutive output elements per CTA; slice q of 8 folds items i0+q, i0+q+8, ... with all of its loads in
+    // flight at once (the fold is a chain of L2 round trips otherwise); the 8 slice sums are added in a fixed order.
+    __shared__ double part[K2A_SLICES][64];
+    const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int g = blockIdx.x * 64 + el;
     double s = 0.0;
-    if (h < nF) {
-        const int i0 = d.host_item_begin[h], i1 = d.host_item_begin[h + 1];
-        const float *p = d.partials + (size_t) i0 * PART_STRIDE + e;
-        // four independent chains keep 4+ loads in flight; the order of the final fold is fixed (deterministic)
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
-        int i = i0;
-        for (; i + 7 < i1; i += 8, p += 8 * PART_STRIDE) {
-            const float v0 = p[0], v1 = p[PART_STRIDE], v2 = p[2 * PART_STRIDE], v3 = p[3 * PART_STRIDE];
-            const float v4 = p[4 * PART_STRIDE], v5 = p[5 * PART_STRIDE], v6 = p[6 * PART_STRIDE], v7 = p[7 * PART_STRIDE];
-            s0 += (double) v0; s1 += (double) v1; s2 += (double) v2; s3 += (double) v3;
-            s4 += (double) v4; s5 += (double) v5; s6 += (double) v6; s7 += (double) v7;
+    if (g < MAXF * PART_USED) {
+        const int h = g / PART_USED, e = g - h * PART_USED;
+        if (h < nF) {
+            const int i0 = d.host_item_begin[h], i1 = d.host_item_begin[h + 1];
+            const float *p = d.partials + (size_t) (i0 + q) * PART_STRIDE + e;
+            int i = i0 + q;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (; i + 3 * K2A_SLICES < i1; i += 4 * K2A_SLICES, p += 4 * K2A_SLICES * PART_STRIDE) {
+                const float v0 = p[0], v1 = p[K2A_SLICES * PART_STRIDE], v2 = p[2 * K2A_SLICES * PART_STRIDE], v3 = p[3 * K2A_SLICES * PART_STRIDE];
+                s0 += (double) v0; s1 += (double) v1; s2 += (double) v2; s3 += (double) v3;
+            }
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (i < i1) v0 = p[0];
+            if (i + K2A_SLICES < i1) v1 = p[K2A_SLICES * PART_STRIDE];
+            if (i + 2 * K2A_SLICES < i1) v2 = p[2 * K2A_SLICES * PART_STRIDE];
+            s0 += (double) v0; s1 += (double) v1; s2 += (double) v2;
+            s = (s0 + s1) + (s2 + s3);
         }
-        for (; i < i1; i++, p += PART_STRIDE) s0 += (double) *p;
-        s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     }
-    d.red[g] = s;
+    part[q][el] = s;
+    __syncthreads();
+    if (q == 0 && g < MAXF * PART_USED) {
+        double t = part[0][el];
+#pragma unroll
+        for (int k = 1; k < K2A_SLICES; k++) t += part[k][el];
+        d.red[g] = t;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -77,7 +92,14 @@ struct SolveBufs {
 #define K2B_THREADS 512
 #define K2B_NSLOT (K2B_THREADS / 64)
 #define K2B_SELCAP 8192          // newest-frame energies kept in shared memory by the select CTA
-#define K2B_SMEM_DOUBLES (7 * MAXF * 64 + MAXF * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 2 * MAXF * 64 + 128 + K2B_NSLOT * 128)
+// staged 8x8 matrices use a row stride of 10 doubles: rows then start 20 banks apart, so both the "one row per lane
+// group" and the "transposed operand" access patterns of the triple products are bank-conflict free and stay 16-byte
+// aligned (with the natural stride of 8 every other row maps to the same banks: 4-way conflicts on every operand load)
+#define K2B_RS 10
+#define K2B_MS (8 * K2B_RS)
+#define K2B_M(q, r, c) ((q) * K2B_MS + (r) * K2B_RS + (c))
+#define K2B_NMAT (7 * MAXF + MAXF * MAXF + 2 * MAXF + MAXF + MAXF + 2 * MAXF + 2)
+#define K2B_SMEM_DOUBLES (K2B_NMAT * K2B_MS + 2 * MAXF * 64 + K2B_NSLOT * 128)
 #define K2B_SMEM_BYTES (K2B_SMEM_DOUBLES * sizeof(double))
 __device__ __forceinline__ double top_elem(const double *red, int h, int t, int r13, int c13) {
     return red[h * PART_USED + PART_TOP + t * 96 + packed13(r13, c13)];
@@ -96,133 +118,164 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         // ---- 8x8 frame block (a,b) of H_A and H_sc. All operands (adjoints, D blocks, top blocks) are first staged
         // in shared memory with one burst of independent loads; the triple products then run from shared memory.
         extern __shared__ double sk2[];
-        double *sAHa = sk2;                 // [nF][64] adHost[a + nF*j]
-        double *sATa = sAHa + MAXF * 64;    // [nF][64] adTarget[i + nF*a]
-        double *sATb = sATa + MAXF * 64;    // [nF][64] adTarget[i + nF*b]
-        double *sAHb = sATb + MAXF * 64;    // [nF][64] adHost[b + nF*k]
-        double *sD1 = sAHb + MAXF * 64;     // [nF][64] D_i[a,b]
-        double *sD2 = sD1 + MAXF * 64;      // [nF][64] D_b[a,k]
-        double *sD3 = sD2 + MAXF * 64;      // [nF][64] D_a[j,b]
-        double *sD4 = sD3 + MAXF * 64;      // [nF*nF][64] D_a[j,k]  (a == b only)
-        double *sM = sD4 + MAXF * MAXF * 64;   // [2*nF][64] top blocks
-        double *sZ = sM + 2 * MAXF * 64;    // [nF][64]  AT_ia * D_i[a,b]
-        double *sX = sZ + MAXF * 64;        // [nF][64]  sum_j AH_aj * D_a[j,k]
-        double *sT = sX + MAXF * 64;        // [2*nF][64] L_q * M_q
-        double *sY2 = sT + 2 * MAXF * 64;   // [64] sum_k D_b[a,k] * AH_bk^T
-        double *sY3 = sY2 + 64;             // [64] sum_j AH_aj * D_a[j,b]
-        double *sO = sY3 + 64;              // [K2B_NSLOT][2][64] partial outputs
+        double *sAHa = sk2;                    // [nF] adHost[a + nF*j]
+        double *sATa = sAHa + MAXF * K2B_MS;   // [nF] adTarget[i + nF*a]
+        double *sATb = sATa + MAXF * K2B_MS;   // [nF] adTarget[i + nF*b]
+        double *sAHb = sATb + MAXF * K2B_MS;   // [nF] adHost[b + nF*k]
+        double *sD1 = sAHb + MAXF * K2B_MS;    // [nF] D_i[a,b]
+        double *sD2 = sD1 + MAXF * K2B_MS;     // [nF] D_b[a,k]
+        double *sD3 = sD2 + MAXF * K2B_MS;     // [nF] D_a[j,b]
+        double *sD4 = sD3 + MAXF * K2B_MS;     // [nF*nF] D_a[j,k]  (a == b only)
+        double *sM = sD4 + MAXF * MAXF * K2B_MS;   // [2*nF] top blocks
+        double *sZ = sM + 2 * MAXF * K2B_MS;   // [nF]  AT_ia * D_i[a,b]
+        double *sX = sZ + MAXF * K2B_MS;       // [nF]  sum_j AH_aj * D_a[j,k]
+        double *sT = sX + MAXF * K2B_MS;       // [2*nF] L_q * M_q
+        double *sY2 = sT + 2 * MAXF * K2B_MS;  // sum_k D_b[a,k] * AH_bk^T
+        double *sY3 = sY2 + K2B_MS;            // sum_j AH_aj * D_a[j,b]
+        double *sP = sY3 + K2B_MS;             // [2][MAXF][64] per-frame partial products of Y2 / Y3
+        double *sO = sP + 2 * MAXF * 64;       // [K2B_NSLOT][2][64] partial outputs
         const int a = blockIdx.x % nF, b = blockIdx.x / nF;
         const bool diag = (a == b);
         if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
         // -------- stage
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {
-            const int q = o >> 6, e = o & 63;
-            sAHa[o] = ws->adHost[a + nF * q][e];
-            sATa[o] = ws->adTarget[q + nF * a][e];
-            sATb[o] = ws->adTarget[q + nF * b][e];
-            sAHb[o] = ws->adHost[b + nF * q][e];
-            sD1[o] = red[q * PART_USED + PART_D + (a * MAXF + b) * 64 + e];
-            sD2[o] = red[b * PART_USED + PART_D + (a * MAXF + q) * 64 + e];
-            sD3[o] = red[a * PART_USED + PART_D + (q * MAXF + b) * 64 + e];
+            const int q = o >> 6, e = o & 63, m = K2B_M(q, e >> 3, e & 7);
+            sAHa[m] = ws->adHost[a + nF * q][e];
+            sATa[m] = ws->adTarget[q + nF * a][e];
+            sATb[m] = ws->adTarget[q + nF * b][e];
+            sAHb[m] = ws->adHost[b + nF * q][e];
+            sD1[m] = red[q * PART_USED + PART_D + (a * MAXF + b) * 64 + e];
+            sD2[m] = red[b * PART_USED + PART_D + (a * MAXF + q) * 64 + e];
+            sD3[m] = red[a * PART_USED + PART_D + (q * MAXF + b) * 64 + e];
         }
         if (diag) {
             for (int o = tid; o < nF * nF * 64; o += K2B_THREADS) {
                 const int jk = o >> 6, e = o & 63, j = jk % nF, k = jk / nF;
-                sD4[o] = red[a * PART_USED + PART_D + (j * MAXF + k) * 64 + e];
+                sD4[K2B_M(jk, e >> 3, e & 7)] = red[a * PART_USED + PART_D + (j * MAXF + k) * 64 + e];
             }
             for (int o = tid; o < 2 * nF * 64; o += K2B_THREADS) {
                 const int q = o >> 6, e = o & 63, i = e >> 3, c = e & 7;
-                sM[o] = (q < nF) ? top_elem(red, a, q, 4 + i, 4 + c) : top_elem(red, q - nF, a, 4 + i, 4 + c);
+                sM[K2B_M(q, i, c)] = (q < nF) ? top_elem(red, a, q, 4 + i, 4 + c) : top_elem(red, q - nF, a, 4 + i, 4 + c);
             }
         } else {
             for (int o = tid; o < 2 * 64; o += K2B_THREADS) {
                 const int q = o >> 6, e = o & 63, i = e >> 3, c = e & 7;
-                sM[o] = (q == 0) ? top_elem(red, a, b, 4 + i, 4 + c) : top_elem(red, b, a, 4 + i, 4 + c);
+                sM[K2B_M(q, i, c)] = (q == 0) ? top_elem(red, a, b, 4 + i, 4 + c) : top_elem(red, b, a, 4 + i, 4 + c);
             }
         }
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0) d.dbg[9] = clock64();
-        // -------- stage A: left products
+        // -------- stage A: left products. Every thread runs short (8-term) chains only; sums over frames are kept as
+        // independent partial chains and folded in a fixed order.
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {         // Z_i = AT_ia * D_i[a,b]
             const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
             double s = 0.0;
-            for (int i = 0; i < 8; i++) s += sATa[q * 64 + r * 8 + i] * sD1[q * 64 + i * 8 + c];
-            sZ[o] = s;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s += sATa[K2B_M(q, r, i)] * sD1[K2B_M(q, i, c)];
+            sZ[K2B_M(q, r, c)] = s;
         }
-        if (tid < 64) {                                              // Y2 = sum_k D_b[a,k] * AH_bk^T
-            const int r = tid >> 3, c = tid & 7;
+        for (int u = tid; u < 2 * MAXF * 64; u += K2B_THREADS) {   // per-frame terms of Y2 and Y3
+            const int which = u / (MAXF * 64), k = (u >> 6) & (MAXF - 1), e = u & 63, r = e >> 3, c = e & 7;
             double s = 0.0;
-            for (int k = 0; k < nF; k++)
-                for (int j = 0; j < 8; j++) s += sD2[k * 64 + r * 8 + j] * sAHb[k * 64 + c * 8 + j];
-            sY2[tid] = s;
-        } else if (tid < 128) {                                      // Y3 = sum_j AH_aj * D_a[j,b]
-            const int e = tid - 64, r = e >> 3, c = e & 7;
-            double s = 0.0;
-            for (int j = 0; j < nF; j++)
-                for (int i = 0; i < 8; i++) s += sAHa[j * 64 + r * 8 + i] * sD3[j * 64 + i * 8 + c];
-            sY3[e] = s;
+            if (k < nF) {
+                if (which == 0) {                                    // D_b[a,k] * AH_bk^T
+#pragma unroll
+                    for (int j = 0; j < 8; j++) s += sD2[K2B_M(k, r, j)] * sAHb[K2B_M(k, c, j)];
+                } else {                                             // AH_ak * D_a[k,b]
+#pragma unroll
+                    for (int i = 0; i < 8; i++) s += sAHa[K2B_M(k, r, i)] * sD3[K2B_M(k, i, c)];
+                }
+            }
+            sP[u] = s;
         }
         if (diag) {
             for (int o = tid; o < nF * 64; o += K2B_THREADS) {     // X_k = sum_j AH_aj * D_a[j,k]
                 const int k = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
-                double s = 0.0;
-                for (int j = 0; j < nF; j++)
-                    for (int i = 0; i < 8; i++) s += sAHa[j * 64 + r * 8 + i] * sD4[(j + nF * k) * 64 + i * 8 + c];
-                sX[o] = s;
+                double acc[MAXF];
+#pragma unroll
+                for (int j = 0; j < MAXF; j++) {
+                    double s = 0.0;
+                    if (j < nF) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) s += sAHa[K2B_M(j, r, i)] * sD4[K2B_M(j + nF * k, i, c)];
+                    }
+                    acc[j] = s;
+                }
+                double s = acc[0];
+#pragma unroll
+                for (int j = 1; j < MAXF; j++) s += acc[j];
+                sX[K2B_M(k, r, c)] = s;
             }
             for (int o = tid; o < 2 * nF * 64; o += K2B_THREADS) { // T_q = L_q * M_q, L = AH_aq (q<nF) or AT_(q-nF)a
                 const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
-                const double *Lm = (q < nF) ? (sAHa + q * 64) : (sATa + (q - nF) * 64);
+                const double *Lm = (q < nF) ? (sAHa + q * K2B_MS) : (sATa + (q - nF) * K2B_MS);
                 double s = 0.0;
-                for (int i = 0; i < 8; i++) s += Lm[r * 8 + i] * sM[q * 64 + i * 8 + c];
-                sT[o] = s;
+#pragma unroll
+                for (int i = 0; i < 8; i++) s += Lm[r * K2B_RS + i] * sM[K2B_M(q, i, c)];
+                sT[K2B_M(q, r, c)] = s;
             }
         } else if (tid >= 128 && tid < 256) {
             const int o = tid - 128, q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;   // T_0 = AH_ab*M_ab, T_1 = AH_ba*M_ba
-            const double *Lm = (q == 0) ? (sAHa + b * 64) : (sAHb + a * 64);
+            const double *Lm = (q == 0) ? (sAHa + b * K2B_MS) : (sAHb + a * K2B_MS);
             double s = 0.0;
-            for (int i = 0; i < 8; i++) s += Lm[r * 8 + i] * sM[q * 64 + i * 8 + c];
-            sT[o] = s;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s += Lm[r * K2B_RS + i] * sM[K2B_M(q, i, c)];
+            sT[K2B_M(q, r, c)] = s;
+        }
+        __syncthreads();
+        if (tid < 128) {                                             // fold the per-frame terms of Y2 / Y3
+            const int which = tid >> 6, e = tid & 63;
+            double s = sP[which * MAXF * 64 + e];
+#pragma unroll
+            for (int k = 1; k < MAXF; k++) s += sP[which * MAXF * 64 + k * 64 + e];
+            (which ? sY3 : sY2)[K2B_M(0, e >> 3, e & 7)] = s;
         }
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0) d.dbg[10] = clock64();
-        // -------- stage B: right products, 4 slots of 64 threads split the term lists
+        // -------- stage B: right products, K2B_NSLOT slots of 64 threads split the term lists
         {
             const int slot = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7;
             double accA = 0.0, accS = 0.0;
             for (int i = slot; i < nF; i += K2B_NSLOT) {            // sum_i Z_i * AT_ib^T
                 double s = 0.0;
-                for (int j = 0; j < 8; j++) s += sZ[i * 64 + r * 8 + j] * sATb[i * 64 + c * 8 + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += sZ[K2B_M(i, r, j)] * sATb[K2B_M(i, c, j)];
                 accS += s;
             }
             if (slot == 0) {                                         // AT_ba * Y2
                 double s = 0.0;
-                for (int j = 0; j < 8; j++) s += sATa[b * 64 + r * 8 + j] * sY2[j * 8 + c];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += sATa[K2B_M(b, r, j)] * sY2[K2B_M(0, j, c)];
                 accS += s;
             } else if (slot == 1) {                                  // Y3 * AT_ab^T
                 double s = 0.0;
-                for (int j = 0; j < 8; j++) s += sY3[r * 8 + j] * sATb[a * 64 + c * 8 + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += sY3[K2B_M(0, r, j)] * sATb[K2B_M(a, c, j)];
                 accS += s;
             }
             if (diag) {
                 for (int k = slot; k < nF; k += K2B_NSLOT) {        // sum_k X_k * AH_ak^T
                     double s = 0.0;
-                    for (int j = 0; j < 8; j++) s += sX[k * 64 + r * 8 + j] * sAHa[k * 64 + c * 8 + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) s += sX[K2B_M(k, r, j)] * sAHa[K2B_M(k, c, j)];
                     accS += s;
                 }
                 for (int q = slot; q < 2 * nF; q += K2B_NSLOT) {    // sum_q T_q * L_q^T (host==target blocks are zero)
-                    const double *Rm = (q < nF) ? (sAHa + q * 64) : (sATa + (q - nF) * 64);
+                    const double *Rm = (q < nF) ? (sAHa + q * K2B_MS) : (sATa + (q - nF) * K2B_MS);
                     double s = 0.0;
-                    for (int j = 0; j < 8; j++) s += sT[q * 64 + r * 8 + j] * Rm[c * 8 + j];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) s += sT[K2B_M(q, r, j)] * Rm[c * K2B_RS + j];
                     accA += s;
                 }
             } else if (slot == 2) {                                  // (AH_ab M_ab) AT_ab^T
                 double s = 0.0;
-                for (int j = 0; j < 8; j++) s += sT[r * 8 + j] * sATb[a * 64 + c * 8 + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += sT[K2B_M(0, r, j)] * sATb[K2B_M(a, c, j)];
                 accA += s;
             } else if (slot == 3) {                                  // ((AH_ba M_ba) AT_ba^T)^T
                 double s = 0.0;
-                for (int j = 0; j < 8; j++) s += sT[64 + c * 8 + j] * sATa[b * 64 + r * 8 + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s += sT[K2B_M(1, c, j)] * sATa[K2B_M(b, r, j)];
                 accA += s;
             }
             sO[(slot * 2 + 0) * 64 + e] = accA;

@@ -403,10 +403,13 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         // the panel/trailing steps then leave D^-1 L^-1 b in that row, i.e. the forward solve comes for free.
         if (tid < n) A[n * K3_LD + tid] = vb[tid];
         __syncthreads();
+        // Look-ahead schedule: while warps 1.. apply block step k to the rows below the NEXT diagonal block, warp 0
+        // applies it to that block and factorises it right away, so the serial 8-pivot chain of step k+1 is hidden
+        // behind the trailing update of step k (two barriers per step instead of three).
+        if (warp == 0) ldlt_diag_block_warp(A, vinv, 0, min(K3_NB, n), lane);
+        __syncthreads();
         for (int k0 = 0; k0 < n; k0 += K3_NB) {
             const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
-            if (warp == 0) ldlt_diag_block_warp(A, vinv, k0, bs, lane);
-            __syncthreads();
             if (tid < n + 1 - m0) {      // panel row i (incl. the rhs row n): w = L*D (unscaled), l = L
                 const int i = m0 + tid;
                 double w[K3_NB];
@@ -429,16 +432,40 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             }
             __syncthreads();
             // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= min(i, n-1), i <= n
-            for (int i = m0 + (tid >> 4); i <= n; i += K3_THREADS / 16) {
-                double li[K3_NB];
+            const int bs2 = min(K3_NB, n - m0);           // size of the next diagonal block (<= 0: none)
+            if (warp == 0) {
+                if (bs2 > 0) {
 #pragma unroll
-                for (int c = 0; c < K3_NB; c++) li[c] = (c < bs) ? A[i * K3_LD + k0 + c] : 0.0;
-                const int jmax = min(i, n - 1);
-                for (int j = m0 + (tid & 15); j <= jmax; j += 16) {
-                    double s0 = 0.0, s1 = 0.0;
+                    for (int h = 0; h < 2; h++) {
+                        const int e = lane + 32 * h, r = e >> 3, cc = e & 7;
+                        if (cc <= r && r < bs2) {
+                            const int i = m0 + r, j = m0 + cc;
+                            double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < K3_NB; c += 2) { s0 += li[c] * Wp[c * K3_WPLD + j]; s1 += li[c + 1] * Wp[(c + 1) * K3_WPLD + j]; }
-                    A[i * K3_LD + j] -= (s0 + s1);
+                            for (int c = 0; c < K3_NB; c += 2) {
+                                if (c < bs) s0 += A[i * K3_LD + k0 + c] * Wp[c * K3_WPLD + j];
+                                if (c + 1 < bs) s1 += A[i * K3_LD + k0 + c + 1] * Wp[(c + 1) * K3_WPLD + j];
+                            }
+                            A[i * K3_LD + j] -= (s0 + s1);
+                        }
+                    }
+                    __syncwarp();
+                    ldlt_diag_block_warp(A, vinv, m0, bs2, lane);
+                }
+            } else {
+                const int t = tid - 32;
+                for (int i = m0 + max(bs2, 0) + (t >> 4); i <= n; i += (K3_THREADS - 32) / 16) {
+                    double li[K3_NB];
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c++) li[c] = (c < bs) ? A[i * K3_LD + k0 + c] : 0.0;
+                    const int jmax = min(i, n - 1);
+#pragma unroll 2
+                    for (int j = m0 + (t & 15); j <= jmax; j += 16) {
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < K3_NB; c += 2) { s0 += li[c] * Wp[c * K3_WPLD + j]; s1 += li[c + 1] * Wp[(c + 1) * K3_WPLD + j]; }
+                        A[i * K3_LD + j] -= (s0 + s1);
+                    }
                 }
             }
             __syncthreads();
