@@ -10,9 +10,16 @@
 // (the reference casts its per-thread float accumulators to double before summing them,
 //  AccumulatedTopHessian.cc:215-219, AccumulatedSCHessian.cc:78-83,101-105).
 // The last block folds the per-item scalar statistics.
+__device__ __forceinline__ void dbg_span(long long *slot_min_max, bool end) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    if (!end) atomicMin((unsigned long long *) slot_min_max, gt);
+    else atomicMax((unsigned long long *) (slot_min_max + 1), gt);
+}
 #define K2A_THREADS 512
 #define K2A_SLICES (K2A_THREADS / 64)     // 8 threads share one output element, each folds every 8th work item
 __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState *ws, int full, int multi) {
+    if (threadIdx.x == 0) dbg_span(&ws->dbg[16], false);
     const int nF = ws->nF;
     if (blockIdx.x == gridDim.x - 1) {
         // stats: warp w (<4) reduces stat w over all items
@@ -31,7 +38,7 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
                 }
             }
         }
-        return;
+        { if (threadIdx.x == 0) dbg_span(&ws->dbg[16], true); return; }
     }
     if (!full) return;
     // 64 consecutive output elements per CTA; slice q of 8 folds items i0+q, i0+q+8, ... with all of its loads in
@@ -67,6 +74,7 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
         for (int k = 1; k < K2A_SLICES; k++) t += part[k][el];
         d.red[g] = t;
     }
+    if (threadIdx.x == 0) dbg_span(&ws->dbg[16], true);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -108,6 +116,7 @@ __device__ __forceinline__ double top_elem(const double *red, int h, int t, int 
 __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState *ws, SolveBufs sb, int do_stitch, int do_select) {
     const int nF = ws->nF, n = ws->n;
     const int tid = threadIdx.x;
+    if (tid == 0) dbg_span(&ws->dbg[18], false);
     const double *red = d.red;
     const int nBlocks = nF * nF;
     __shared__ unsigned hist[256];
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             sb.H_sc[(size_t) col * n + row] = vS;
         }
         if (blockIdx.x == 0 && tid == 0) d.dbg[11] = clock64();
-        return;
+        { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
     }
     if ((int) blockIdx.x < nBlocks + nF) {
         if (!do_stitch) return;
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 } else sb.b_sc[CPARS + 8 * a + (o - 72)] = s;
             }
         }
-        return;
+        { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
     }
     if ((int) blockIdx.x == nBlocks + nF) {
         if (!do_stitch) return;
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 } else { sb.b_A[o - 16] = sA; sb.b_sc[o - 16] = sS; }
             }
         }
-        return;
+        { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
     }
     // ---- last CTA: exact k-th order statistic of the newest frame's residual energies (radix select)
     if (tid == 0) {   // publish the (all-reduced) scalar statistics
@@ -452,6 +461,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         }
         if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; d.dbg[13] = clock64(); }
     }
+    if (tid == 0) dbg_span(&ws->dbg[18], true);
 }
 
 // ---------------------------------------------------------------------------------------------------------

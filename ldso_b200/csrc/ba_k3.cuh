@@ -259,6 +259,12 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     int dbgi = 0;
 #define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clock64(); dbgi++; } while (0)
     K3_STAMP();
+    if (tid == 0) {      // wall-clock timeline of one iteration (development aid): K3 span here, K2a/K2b spans by atomics
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        ws->dbg[14] = (long long) gt;
+        ws->dbg[16] = 0x7fffffffffffffffLL; ws->dbg[17] = 0; ws->dbg[18] = 0x7fffffffffffffffLL; ws->dbg[19] = 0;
+    }
     stage_in(S, ws);
     K3_STAMP();
 
@@ -564,6 +570,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     K3_STAMP();   // 8: frames refreshed
     stage_out(S, ws);
     K3_STAMP();   // 9
+    if (tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        ws->dbg[15] = (long long) gt;
+    }
     if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
 }
 #define K3_SMEM_BYTES (((2 * MAXN + 1) * K3_LD + K3_NB * K3_WPLD + 5 * MAXN) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 64)

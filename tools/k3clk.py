@@ -5,13 +5,12 @@ from ldso_b200 import capi, synth
 win = synth.make_window(nF=8, pts_per_frame=250, seed=42)
 ctx = capi.Context(win.w, win.h, win.levels); ctx.load_synth_window(win)
 ctx.optimize_begin(); ctx.gn_iterations(0, 30); ctx.synchronize()
-buf = (C.c_longlong*32)()
+buf = (C.c_longlong*48)()
 ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
 t = np.array(buf[:10]); print("K3 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
-t = np.array(buf[10:14]); print("K3 block step k0=8 [diag, panel, trailing]:", np.diff(t))
-t = np.array(buf[16:24]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
-t = np.array(buf[24:28]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
-t = np.array(buf[28:30]); print("K2b select-CTA cycles:", np.diff(t))
+t = np.array(buf[32:40]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
+t = np.array(buf[40:44]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
+t = np.array(buf[44:46]); print("K2b select-CTA cycles:", np.diff(t))
 cap = 1024
 sp = (C.c_longlong * (3 * cap))()
 n = ctx.L.ldso_b200_debug_cta_spans(ctx.ctx, sp, cap)
@@ -23,3 +22,28 @@ dur = en - st
 print(f"   duration p0/p50/p90/p100 = {dur.min()}/{int(np.median(dur))}/{int(np.percentile(dur, 90))}/{dur.max()}  distinct SMs {len(set(sm.tolist()))}  max CTAs/SM {np.bincount(sm.astype(int)).max()}")
 order = np.argsort(en)[-6:]
 print("   last finishers (cta, start, end, dur, sm):", [(int(i), int(st[i]), int(en[i]), int(dur[i]), int(sm[i])) for i in order])
+
+# one-iteration wall-clock timeline (graph launch): K3 -> K1 -> K2a -> K2b, relative to K3's start
+k3s, k3e, k2as, k2ae, k2bs, k2be = buf[14], buf[15], buf[16], buf[17], buf[18], buf[19]
+k1s, k1e = int(a[:, 0].min()), int(a[:, 1].max())
+print("timeline ns rel. K3 start: K3 [0, %d]  K1 [%d, %d]  K2a [%d, %d]  K2b [%d, %d]" %
+      (k3e - k3s, k1s - k3s, k1e - k3s, k2as - k3s, k2ae - k3s, k2bs - k3s, k2be - k3s))
+
+def timeline(tag):
+    ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
+    n = ctx.L.ldso_b200_debug_cta_spans(ctx.ctx, sp, cap)
+    a = np.array(sp[:3 * n]).reshape(n, 3)
+    k3s = buf[14]
+    print("%s timeline ns rel. K3 start: K3 [0, %d]  K1 [%d, %d]  K2a [%d, %d]  K2b [%d, %d]" %
+          (tag, buf[15] - k3s, int(a[:, 0].min()) - k3s, int(a[:, 1].max()) - k3s, buf[16] - k3s, buf[17] - k3s, buf[18] - k3s, buf[19] - k3s))
+    d = a[:, 1] - a[:, 0]
+    print("   K1 CTA duration p50/p100 %d/%d ns; K3 stamps %s" % (int(np.median(d)), d.max(), np.diff(np.array(buf[:10]))))
+
+import torch
+flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+for rep in range(3):
+    flush.fill_(rep); torch.cuda.synchronize()
+    ctx.gn_iterations(3, 1); ctx.synchronize()
+    timeline("L2-cold")
+ctx.gn_iterations(3, 3); ctx.synchronize()
+timeline("L2-warm")
