@@ -49,6 +49,10 @@ struct ldso_b200_ctx {
     SolveBufs sb;
     double *solve_mem = nullptr;
     double *sol_host = nullptr;      // pinned staging for get_last_solution
+    // K2b(do_assemble) has produced the system K3 solves and nothing it depends on changed since
+    bool solve_ready = false;
+    // the reduced accumulators still describe the current window state (a re-stitch is enough to get solve_ready back)
+    bool restitch_ok = false;
     int *iteration_dev = nullptr;
     uint8_t *pt_sel_dev = nullptr;
     char *arena_dev = nullptr, *arena_host = nullptr;
@@ -189,10 +193,11 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     memset(c->ws_host, 0, sizeof(WinState));
     double *p = c->solve_mem;
     c->sb.H_A = p; p += nn; c->sb.H_sc = p; p += nn; c->sb.HM = p; p += nn; c->sb.Pns = p; p += nn;
-    p += 2 * nn;   // spare
+    c->sb.A0g = p; p += nn; c->sb.HSg = p; p += nn;     // assembled system handed from K2b to K3
     // lastHS | lastbS | lastX are contiguous: get_last_solution reads them back with one copy
     c->sb.lastHS = p; p += nn; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
     c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN;
+    c->sb.dg = p; p += MAXN; c->sb.bFg = p; p += MAXN;
     ok = cudaMallocHost(&c->sol_host, sizeof(double) * (nn + 2 * MAXN)) == cudaSuccess;
     if (!ok) { fprintf(stderr, "ldso_b200: pinned allocation failed\n"); delete c; return nullptr; }
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
@@ -468,6 +473,7 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
     if (!same_topology) CUDA_CHECK_RET(c, cudaMemsetAsync(d.res_J, 0, sizeof(float) * 74 * (size_t) std::max(nR, 1), c->stream));
     if (win->res_toZeroF) CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));   // pageable source
     { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
+    c->solve_ready = false; c->restitch_ok = false;
     c->have_window = true;
     return LDSO_B200_OK;
 }
@@ -669,6 +675,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
     LAUNCH_CHECK(c);
+    c->solve_ready = false; c->restitch_ok = false;
     c->have_frames = true;
     if (prev_nF != nF) c->derived_dirty = true;    // work items / newest-frame slots depend on nF only
     return LDSO_B200_OK;
@@ -683,6 +690,7 @@ extern "C" int ldso_b200_set_marg_prior(ldso_b200_ctx *c, const double *HM, cons
     if (bM) CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.bM, bM, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     else CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    c->solve_ready = false;      // HM/bM enter the assembled system
     return LDSO_B200_OK;
 }
 
@@ -711,15 +719,23 @@ static int launch_k2a(ldso_b200_ctx *c, int full) {
     k2a_reduce<<<nb, K2A_THREADS, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
     c->kt_end();
     LAUNCH_CHECK(c);
+    if (full) { c->restitch_ok = true; c->solve_ready = false; }
     return LDSO_B200_OK;
 }
-static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select) {
+static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select, int do_assemble) {
     const int nb = c->nF * c->nF + c->nF + 2;
     c->kt_begin("k2b");
-    k2b_stitch<<<nb, K2B_THREADS, K2B_SMEM_BYTES, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select);
+    k2b_stitch<<<nb, K2B_THREADS, K2B_SMEM_BYTES, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select, do_stitch && do_assemble);
     c->kt_end();
     LAUNCH_CHECK(c);
+    if (do_stitch) c->solve_ready = do_assemble != 0;
     return LDSO_B200_OK;
+}
+// K3(SOLVE) consumes what K2b(do_assemble) left behind; re-stitch if only the prior changed in between
+static int ensure_solve_ready(ldso_b200_ctx *c) {
+    if (c->solve_ready) return LDSO_B200_OK;
+    if (!c->restitch_ok) return c->fail(LDSO_B200_ERR_STATE, "no stitched system for the current window state: call optimize_begin / solve_system first");
+    return launch_k2b(c, 1, 0, 1);
 }
 static int launch_k3(ldso_b200_ctx *c, int flags) {
     c->kt_begin("k3");
@@ -748,7 +764,7 @@ extern "C" int ldso_b200_linearize_all(ldso_b200_ctx *c, int fixLinearization, i
     RET_IF(clear_select(c));
     RET_IF(launch_k1(c, f));
     RET_IF(launch_k2a(c, 0));
-    RET_IF(launch_k2b(c, 0, 1));
+    RET_IF(launch_k2b(c, 0, 1, 0));
     if (energy_out) {
         CUDA_CHECK_RET(c, cudaMemcpyAsync(energy_out, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
@@ -785,7 +801,7 @@ extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *l
     RET_IF(build_derived(c));
     RET_IF(launch_k1(c, K1F_ACCUMULATE));                 // mode 0 records from the stored Jacobians
     RET_IF(launch_k2a(c, 1));
-    RET_IF(launch_k2b(c, 1, 0));
+    RET_IF(launch_k2b(c, 1, 0, 1));
     RET_IF(set_iteration(c, iteration));
     RET_IF(launch_k3(c, K3F_SOLVE));
     if (c->d.nP > 0) {
@@ -868,7 +884,8 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
     }
     RET_IF(launch_k1(c, K1F_ACCUMULATE | K1F_NO_SHIFT_PRIOR | (2 << K1F_MODE_SHIFT), c->pt_sel_dev));
     RET_IF(launch_k2a(c, 1));
-    RET_IF(launch_k2b(c, 1, 0));
+    RET_IF(launch_k2b(c, 1, 0, 0));
+    c->restitch_ok = false;      // the reduced buffer now holds the mode-2 (marginalisation) accumulators
     const int nn = c->n;
     k_add_marg<<<(nn * nn + 255) / 256, 256, 0, c->stream>>>(c->sb, nn, (double) c->S.margWeightFac);
     LAUNCH_CHECK(c);
@@ -890,7 +907,7 @@ extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
     RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
     RET_IF(launch_k2a(c, 1));
     if (c->multi) return LDSO_B200_OK;     // caller all-reduces, then gn_phase_b
-    RET_IF(launch_k2b(c, 1, 1));
+    RET_IF(launch_k2b(c, 1, 1, 1));
     if (energy_out) {
         CUDA_CHECK_RET(c, cudaMemcpyAsync(energy_out, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
@@ -902,7 +919,7 @@ static int launch_gn_body(ldso_b200_ctx *c) {
     RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
     RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
     RET_IF(launch_k2a(c, 1));
-    RET_IF(launch_k2b(c, 1, 1));
+    RET_IF(launch_k2b(c, 1, 1, 1));
     return LDSO_B200_OK;
 }
 
@@ -911,6 +928,7 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
     if (c->multi) return c->fail(LDSO_B200_ERR_STATE, "sharded context: use gn_phase_a / all-reduce / gn_phase_b");
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
+    RET_IF(ensure_solve_ready(c));
     RET_IF(set_iteration(c, first_iteration));     // K3 reads the iteration number from device memory and increments it
     if (c->use_graph && c->d.nItems > 0) {
         if (!c->gn_graph_valid) {
@@ -972,6 +990,7 @@ extern "C" int ldso_b200_gn_phase_a(ldso_b200_ctx *c, int iteration) {
     if (iteration < 0) {
         RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
     } else {
+        if (!c->solve_ready) return c->fail(LDSO_B200_ERR_STATE, "gn_phase_a(iteration >= 0) needs a preceding gn_phase_b");
         RET_IF(set_iteration(c, iteration));
         RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
         RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
@@ -984,7 +1003,7 @@ extern "C" int ldso_b200_gn_phase_b(ldso_b200_ctx *c) {
     if (!c) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
-    RET_IF(launch_k2b(c, 1, 1));
+    RET_IF(launch_k2b(c, 1, 1, 1));
     return LDSO_B200_OK;
 }
 

@@ -91,6 +91,9 @@ struct SolveBufs {
     double *HM, *bM;                      // marginalisation prior
     double *Pns;                          // null-space projector (n x n, col-major)
     double *lastHS, *lastbS, *lastX;
+    // assembled system handed from K2b to K3 (EnergyFunctional.cc:257,283-291): HFinal_top (column-major) and its
+    // diagonal, HFinal_top - H_sc (becomes lastHS once solved), bFinal_top (becomes lastbS)
+    double *A0g, *dg, *HSg, *bFg;
 };
 
 // K2b: one CTA per 8x8 output block (a,b) of H_A and H_sc, nF CTAs for the calibration rows + b, one CTA for
@@ -113,7 +116,11 @@ __device__ __forceinline__ double top_elem(const double *red, int h, int t, int 
     return red[h * PART_USED + PART_TOP + t * 96 + packed13(r13, c13)];
 }
 
-__global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState *ws, SolveBufs sb, int do_stitch, int do_select) {
+#define K2B_LAMBDA 1e-5        // SOLVER_FIX_LAMBDA (EnergyFunctional.cc:243)
+__device__ __forceinline__ double k2b_delta(const WinState *ws, int c) {      // getStitchedDeltaF (EnergyFunctional.h:178-184)
+    return (c < CPARS) ? (double) ws->calib.cDeltaF[c] : ws->fr[(c - CPARS) >> 3].delta[(c - CPARS) & 7];
+}
+__global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState *ws, SolveBufs sb, int do_stitch, int do_select, int do_assemble) {
     const int nF = ws->nF, n = ws->n;
     const int tid = threadIdx.x;
     if (tid == 0) dbg_span(&ws->dbg[18], false);
@@ -145,6 +152,9 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         double *sO = sP + 2 * MAXF * 64;       // [K2B_NSLOT][2][64] partial outputs
         const int a = blockIdx.x % nF, b = blockIdx.x / nF;
         const bool diag = (a == b);
+        // the marginalisation-prior element this thread will add in the epilogue: issue the load now
+        double hm_pre = 0.0;
+        if (do_assemble && tid < 64) hm_pre = sb.HM[(size_t) (CPARS + 8 * b + (tid & 7)) * n + CPARS + 8 * a + (tid >> 3)];
         if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
         // -------- stage
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {
@@ -299,6 +309,15 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             const int row = CPARS + 8 * a + r, col = CPARS + 8 * b + c;
             sb.H_A[(size_t) col * n + row] = vA;
             sb.H_sc[(size_t) col * n + row] = vS;
+            if (do_assemble) {       // HFinal_top = HL + HM + HA, lastHS, damping, Schur part (EnergyFunctional.cc:283-291)
+                double v = vA + hm_pre;
+                if (row == col) v += ws->fr[a].prior[r];
+                sb.HSg[(size_t) col * n + row] = v - vS;
+                if (row == col) v *= (1.0 + K2B_LAMBDA);
+                const double a0 = v - vS * (1.0 / (1.0 + K2B_LAMBDA));
+                sb.A0g[(size_t) col * n + row] = a0;
+                if (row == col) sb.dg[row] = a0;
+            }
         }
         if (blockIdx.x == 0 && tid == 0) d.dbg[11] = clock64();
         { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
@@ -308,6 +327,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         // ---- calibration rows of frame a and its b segments: 80 outputs, 8 lanes per output (lane <-> other frame),
         // every lane issues its 32 independent loads at once, then a 3-step shuffle fold.
         const int a = blockIdx.x - nBlocks;
+        __shared__ double s_cal[80];
         for (int o8 = tid; o8 < 80 * 8; o8 += K2B_THREADS) {
             const int o = o8 >> 3, t = o8 & 7;
             double s = 0.0;
@@ -333,6 +353,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
             if (t == 0) {
+                s_cal[o] = s;
                 if (o < 32) {
                     const int r = o >> 2, c = o & 3;
                     sb.H_A[(size_t) c * n + (CPARS + 8 * a + r)] = s;
@@ -343,6 +364,30 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                     sb.H_sc[(size_t) c * n + (CPARS + 8 * a + r)] = s;
                     sb.H_sc[(size_t) (CPARS + 8 * a + r) * n + c] = s;
                 } else sb.b_sc[CPARS + 8 * a + (o - 72)] = s;
+            }
+        }
+        if (do_assemble) {
+            __syncthreads();
+            if (tid < 32) {                    // the two mirrored elements (R,c) and (c,R): no diagonal here
+                const int r = tid >> 2, c = tid & 3, R = CPARS + 8 * a + r;
+                const double sA = s_cal[tid], sS = s_cal[40 + tid];
+                const double v1 = sA + sb.HM[(size_t) c * n + R], v2 = sA + sb.HM[(size_t) R * n + c];
+                sb.HSg[(size_t) c * n + R] = v1 - sS;
+                sb.HSg[(size_t) R * n + c] = v2 - sS;
+                sb.A0g[(size_t) c * n + R] = v1 - sS * (1.0 / (1.0 + K2B_LAMBDA));
+                sb.A0g[(size_t) R * n + c] = v2 - sS * (1.0 / (1.0 + K2B_LAMBDA));
+            } else if (tid >= 64 && tid < 128) {   // bFinal_top = bL + (bM + HM*delta) + bA - b_sc (:257,284), 8 lanes per row
+                const int r = (tid - 64) >> 3, t = tid & 7, R = CPARS + 8 * a + r;
+                double hd = 0.0;
+                for (int c = t; c < n; c += 8) hd += sb.HM[(size_t) c * n + R] * k2b_delta(ws, c);
+                hd += __shfl_xor_sync(0xffffffffu, hd, 1);
+                hd += __shfl_xor_sync(0xffffffffu, hd, 2);
+                hd += __shfl_xor_sync(0xffffffffu, hd, 4);
+                if (t == 0) {
+                    const FrameDev &f = ws->fr[a];
+                    const double bl = f.prior[r] * f.delta_prior[r];
+                    sb.bFg[R] = bl + (sb.bM[R] + hd) + s_cal[32 + r] - s_cal[72 + r];
+                }
             }
         }
         { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
@@ -365,12 +410,32 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 }
             }
             for (int m = 1; m < 8; m <<= 1) { sA += __shfl_xor_sync(0xffffffffu, sA, m); sS += __shfl_xor_sync(0xffffffffu, sS, m); }
+            double hd = 0.0;
+            if (do_assemble && o >= 16)      // (HM*delta)[r], the 8 lanes split the columns
+                for (int c = h; c < n; c += 8) hd += sb.HM[(size_t) c * n + (o - 16)] * k2b_delta(ws, c);
+            for (int m = 1; m < 8; m <<= 1) hd += __shfl_xor_sync(0xffffffffu, hd, m);
             if (h == 0) {
                 if (o < 16) {
                     const int r = o >> 2, c = o & 3;
                     sb.H_A[(size_t) c * n + r] = sA;
                     sb.H_sc[(size_t) c * n + r] = sS;
-                } else { sb.b_A[o - 16] = sA; sb.b_sc[o - 16] = sS; }
+                    if (do_assemble) {
+                        double v = sA + sb.HM[(size_t) c * n + r];
+                        if (r == c) v += ws->cPrior[r];
+                        sb.HSg[(size_t) c * n + r] = v - sS;
+                        if (r == c) v *= (1.0 + K2B_LAMBDA);
+                        const double a0 = v - sS * (1.0 / (1.0 + K2B_LAMBDA));
+                        sb.A0g[(size_t) c * n + r] = a0;
+                        if (r == c) sb.dg[r] = a0;
+                    }
+                } else {
+                    const int r = o - 16;
+                    sb.b_A[r] = sA; sb.b_sc[r] = sS;
+                    if (do_assemble) {
+                        const double bl = ws->cPrior[r] * (double) ws->calib.cDeltaF[r];
+                        sb.bFg[r] = bl + (sb.bM[r] + hd) + sA - sS;
+                    }
+                }
             }
         }
         { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }

@@ -236,6 +236,12 @@ __device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, in
     if (lane < bs) v[k0 + lane] = x;
 }
 
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
     extern __shared__ double sm3[];
     double *A0 = sm3;                       // [n][K3_LD] row-major assembled matrix
@@ -254,8 +260,25 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
 
     // NNpiTS is needed at the very end: start copying it into shared memory now (fire-and-forget stores, the
     // L2 round trip overlaps the assembly and the factorisation)
-    if ((flags & K3F_SOLVE) && iteration >= 2)
-        for (int e = tid; e < n * n; e += K3_THREADS) sPns[e] = sb.Pns[e];
+    constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
+    double b_pre = 0.0, dg_pre = 0.0, hs_pre[K3_HSCOPY];
+    if (flags & K3F_SOLVE) {
+        // asynchronous global->shared copies (LDGSTS): the assembled system the stitch kernel left behind (HFinal_top,
+        // column-major -> row-major) and, from iteration 2 on, the null-space projector. They land while the frame state
+        // is staged; nothing below waits for them until cp_async_wait_all().
+        for (int e = tid; e < n * n; e += K3_THREADS) {
+            const int c = e / n, r = e - c * n;
+            cp_async8(A0 + r * K3_LD + c, sb.A0g + e);
+        }
+        if (iteration >= 2)
+            for (int e = tid; e < n * n; e += K3_THREADS) cp_async8(sPns + e, sb.Pns + e);
+        if (tid < n) { dg_pre = sb.dg[tid]; b_pre = sb.bFg[tid]; }
+#pragma unroll
+        for (int k = 0; k < K3_HSCOPY; k++) {
+            const int e = tid + k * K3_THREADS;
+            hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
+        }
+    }
     int dbgi = 0;
 #define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clock64(); dbgi++; } while (0)
     K3_STAMP();
@@ -274,101 +297,21 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         __syncthreads();
     }
     if (flags & K3F_SOLVE) {
-        const double lambda = 1e-5;        // SOLVER_FIX_LAMBDA (EnergyFunctional.cc:243)
-        // delta = getStitchedDeltaF (EnergyFunctional.h:178-184)
-        if (tid < n) vd[tid] = (tid < CPARS) ? (double) S->calib.cDeltaF[tid] : S->fr[(tid - CPARS) >> 3].delta[(tid - CPARS) & 7];
-        __syncthreads();
-        // HFinal_top = HL + HM + HA ; lastHS = HFinal_top - H_sc ; diag *= (1+lambda) ; HFinal_top -= H_sc/(1+lambda)
-        // (:283-291)  — one pass, all loads independent
-        const double inv1l = 1.0 / (1.0 + lambda);
-        {
-            // all global loads of this phase are issued before the first dependent use / global store (the stores to
-            // lastHS would otherwise fence the loads of the next column: one L2 round trip per column)
-            constexpr int NC = (MAXN + K3_THREADS / 32 - 1) / (K3_THREADS / 32), NR = (MAXN + 31) / 32;
-            // (1) bM + HM*delta: rows of HM and the b vectors
-            double hmrow[NC][NR], brow[NC][3], bsum[NC];
+        // The stitch kernel (k2b_stitch, do_assemble) already produced HFinal_top, bFinal_top (= lastbS), lastHS, SVecI and
+        // the pivot order (EnergyFunctional.cc:257,283-291,326-327); the copies were issued at kernel entry.
+        // The system being solved now becomes the public lastHS / lastbS (EnergyFunctional.cc:285,:335).
 #pragma unroll
-            for (int ci = 0; ci < NC; ci++) {
-                const int r = warp + ci * (K3_THREADS / 32);
-#pragma unroll
-                for (int cc = 0; cc < NR; cc++) {
-                    const int c = lane + 32 * cc;
-                    hmrow[ci][cc] = (r < n && c < n) ? sb.HM[(size_t) c * n + r] : 0.0;
-                }
-                brow[ci][0] = (r < n) ? sb.bM[r] : 0.0;
-                brow[ci][1] = (r < n) ? sb.b_A[r] : 0.0;
-                brow[ci][2] = (r < n) ? sb.b_sc[r] : 0.0;
-            }
-#pragma unroll
-            for (int ci = 0; ci < NC; ci++) {
-                double s = 0.0;
-#pragma unroll
-                for (int cc = 0; cc < NR; cc++) {
-                    const int c = lane + 32 * cc;
-                    if (c < n) s += hmrow[ci][cc] * vd[c];
-                }
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                bsum[ci] = s;
-            }
-            // (2) the matrices
-            double ha[NC][NR], hm[NC][NR], hs[NC][NR];
-#pragma unroll
-            for (int ci = 0; ci < NC; ci++) {
-                const int c = warp + ci * (K3_THREADS / 32);
-#pragma unroll
-                for (int rr = 0; rr < NR; rr++) {
-                    const int r = lane + 32 * rr;
-                    const bool on = (c < n && r < n);
-                    const int e = on ? c * n + r : 0;
-                    ha[ci][rr] = on ? sb.H_A[e] : 0.0;
-                    hm[ci][rr] = on ? sb.HM[e] : 0.0;
-                    hs[ci][rr] = on ? sb.H_sc[e] : 0.0;
-                }
-            }
-#pragma unroll
-            for (int ci = 0; ci < NC; ci++) {
-                const int c = warp + ci * (K3_THREADS / 32);
-                if (c < n) {
-                    const double pc = (c < CPARS) ? ws->cPrior[c] : S->fr[(c - CPARS) >> 3].prior[(c - CPARS) & 7];
-#pragma unroll
-                    for (int rr = 0; rr < NR; rr++) {
-                        const int r = lane + 32 * rr;
-                        if (r < n) {
-                            const int e = c * n + r;
-                            double v = ha[ci][rr] + hm[ci][rr];
-                            if (r == c) v += pc;
-                            sb.lastHS[e] = v - hs[ci][rr];
-                            if (r == c) v *= (1 + lambda);
-                            A0[r * K3_LD + c] = v - hs[ci][rr] * inv1l;
-                        }
-                    }
-                }
-            }
-            // bFinal_top = bL + (bM + HM*delta) + bA - b_sc  (:257,284)
-#pragma unroll
-            for (int ci = 0; ci < NC; ci++) {
-                const int r = warp + ci * (K3_THREADS / 32);
-                if (lane == 0 && r < n) {
-                    double bl;
-                    if (r < CPARS) bl = ws->cPrior[r] * (double) S->calib.cDeltaF[r];
-                    else {
-                        const FrameDev &f = S->fr[(r - CPARS) >> 3];
-                        bl = f.prior[(r - CPARS) & 7] * f.delta_prior[(r - CPARS) & 7];
-                    }
-                    const double bf = bl + (brow[ci][0] + bsum[ci]) + brow[ci][1] - brow[ci][2];
-                    vb[r] = bf;
-                    sb.lastbS[r] = bf;
-                }
-            }
+        for (int k = 0; k < K3_HSCOPY; k++) {
+            const int e = tid + k * K3_THREADS;
+            if (e < n * n) sb.lastHS[e] = hs_pre[k];
         }
-        __syncthreads();
-        K3_STAMP();   // 2: assembled
         // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
         if (tid < n) {
-            const double dg = A0[tid * K3_LD + tid];
-            const double sv = 1.0 / sqrt(dg + 10.0);
+            const double sv = 1.0 / sqrt(dg_pre + 10.0);
             vS[tid] = sv;
-            vd[tid] = fabs(dg * sv * sv);          // |diagonal| of the scaled matrix
+            vd[tid] = fabs(dg_pre * sv * sv);          // |diagonal| of the scaled matrix
+            vb[tid] = b_pre;
+            sb.lastbS[tid] = b_pre;
         }
         __syncthreads();
         {   // rank sort: 4 threads per row fold a quarter of the comparisons each
@@ -385,7 +328,9 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             rank += __shfl_xor_sync(0xffffffffu, rank, 2);
             if (i < n && q == 0) perm[rank] = i;
         }
+        cp_async_wait_all();
         __syncthreads();
+        K3_STAMP();   // 2: assembled system loaded
         // A = P (S A0 S) P^T, b' = P S b
         for (int r = warp; r < n; r += K3_THREADS / 32) {
             const int pr = perm[r];

@@ -350,3 +350,36 @@ def test_stepio_prefetch_matches_getters(small_win):
     b = ctx.last_solution()["lastX"]
     assert np.array_equal(a, b) and not np.array_equal(a, out["lastX"])
     ctx.close()
+
+
+def test_prior_change_between_stitch_and_solve(small_win):
+    """The stitch kernel hands the assembled system (HFinal_top, bFinal_top, pivot order) to the solver kernel. A
+    marginalisation prior set AFTER optimize_begin must still enter the next solve (the library re-stitches), and a
+    solve without any stitched system for the current state is an error, not a stale answer."""
+    win = small_win
+    n = 8 * win.nF + 4
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((n, n)) * 30.0
+    HM = B @ B.T
+    bM = rng.standard_normal(n) * 10.0
+    a = _ctx(win)
+    a.set_marg_prior(HM, bM)
+    a.optimize_begin(); a.gn_iterations(0, 1)
+    sa = a.last_solution()
+    b = _ctx(win)
+    b.optimize_begin()
+    b.set_marg_prior(HM, bM)          # after the stitch
+    b.gn_iterations(0, 1)
+    sb = b.last_solution()
+    for k in ("lastHS", "lastbS", "lastX"):
+        assert np.array_equal(sa[k], sb[k]), k
+    o = oracle_py.OracleBA(win, threads_mode=1)
+    o.set_marg_prior(HM, bM)
+    o.optimize_begin(); o.gn_iteration(0)
+    ref = o.system()
+    assert rel_err(sa["lastHS"], ref["lastHS"]) < TOL and rel_err(sa["lastbS"], ref["lastbS"]) < TOL
+    # new frame states invalidate the accumulators: solving without re-linearising must fail loudly
+    b.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(win.nF)), win.K)
+    with pytest.raises(capi.Error):
+        b.gn_iterations(0, 1)
+    a.close(); b.close()
