@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libldso_b200.so")
+# development aid: LDSO_B200_CFLAGS adds nvcc flags (e.g. -DK3V_...=0), LDSO_B200_LIB redirects the output / the library capi loads
+EXTRA = os.environ.get("LDSO_B200_CFLAGS", "").split()
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -33,9 +35,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "api.cu"), "-o", LIB]
+    out = os.environ.get("LDSO_B200_LIB", LIB)
+    cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "api.cu"), "-o", out]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

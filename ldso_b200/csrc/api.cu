@@ -1166,9 +1166,9 @@ extern "C" int ldso_b200_debug_res_to_zero(ldso_b200_ctx *c, float *out8) {
 extern "C" int ldso_b200_debug_clocks(ldso_b200_ctx *c, long long *out32) {
     if (!c || !out32) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
-    // out: 48 values = WinState::dbg[0..31] then DevWindow::dbg[0..15]
-    CUDA_CHECK_RET(c, cudaMemcpyAsync(out32, c->ws_dev->dbg, sizeof(long long) * 32, cudaMemcpyDeviceToHost, c->stream));
-    if (c->d.dbg) CUDA_CHECK_RET(c, cudaMemcpyAsync(out32 + 32, c->d.dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->stream));
+    // out: 80 values = WinState::dbg[0..63] then DevWindow::dbg[0..15]
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(out32, c->ws_dev->dbg, sizeof(long long) * 64, cudaMemcpyDeviceToHost, c->stream));
+    if (c->d.dbg) CUDA_CHECK_RET(c, cudaMemcpyAsync(out32 + 64, c->d.dbg, sizeof(long long) * 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     return LDSO_B200_OK;
 }

@@ -19,9 +19,16 @@
 #define K3F_STEP 2
 #define K3F_BACKUP 4
 #define K3_THREADS 512
-#define K3_LD (MAXN + 1)
+#ifndef K3V_SHFL_EARLY
+#define K3V_SHFL_EARLY 1
+#endif
+#ifndef K3V_PANEL_HOIST
+#define K3V_PANEL_HOIST 1
+#endif
+#define K3_NP ((MAXN + 7) & ~7)     // system dimension padded to whole 8x8 blocks (identity padding)
+#define K3_LD (K3_NP + 1)
 #define K3_NB 8
-#define K3_WPLD (MAXN + 2)      // Wp is [K3_NB][K3_WPLD] (column of the panel major): conflict-free for consecutive rows
+#define K3_WPLD (K3_NP + 2)      // Wp is [K3_NB][K3_WPLD] (column of the panel major): conflict-free for consecutive rows
 
 struct K3Frames {       // shared-memory staging of the mutable window records
     FrameDev fr[MAXF];
@@ -174,23 +181,41 @@ __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
     stage_out(&S, ws);
 }
 
-// Factor the bs x bs diagonal block at (k0,k0) in place (lower): L below the diagonal (unit), D on it.
+// Factor the 8x8 diagonal block at (k0,k0) in place (lower): L below the diagonal (unit), D on it. The matrix is
+// padded to whole blocks, so there is no partial-block predicate anywhere on this serial path.
 // Executed by ONE WARP: lane j < 8 keeps row j of the block in registers; a step is one broadcast of the pivot,
 // one reciprocal, and 7-k shuffles of the unscaled column. (L = W * (1/d): <= 1 ulp from Eigen's W / d.)
-__device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int bs, int lane) {
+__device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int lane) {
     const unsigned FULL = 0xffffffffu;
     double a[K3_NB];
     const int row = lane & 7;
 #pragma unroll
-    for (int c = 0; c < K3_NB; c++)
-        a[c] = (row < bs && c <= row && c < bs) ? A[(k0 + row) * K3_LD + k0 + c] : ((c == row) ? 1.0 : 0.0);
+    for (int c = 0; c < K3_NB; c++) a[c] = A[(k0 + row) * K3_LD + k0 + c];
 #pragma unroll
+#if K3V_SHFL_EARLY
+    for (int k = 0; k < K3_NB; k++) {
+        const double w = a[k];                      // unscaled column entry of this lane's row (rows >= k)
+        // all exchanges of this step are issued before the reciprocal: only rcp -> mul -> fma stays on the chain
+        const double dk = __shfl_sync(FULL, w, k);
+        double wj[K3_NB];
+#pragma unroll
+        for (int j = k + 1; j < K3_NB; j++) wj[j] = __shfl_sync(FULL, w, j);
+        const bool valid = fabs(dk) > 0.0;
+        const double inv = valid ? __drcp_rn(dk) : 1.0;
+        const double l = w * inv;
+#pragma unroll
+        for (int j = k + 1; j < K3_NB; j++)
+            if (row >= j) a[j] -= l * wj[j];
+        if (row > k) a[k] = l;
+        if (lane == 0) vinv[k0 + k] = inv;
+    }
+#else
     for (int k = 0; k < K3_NB; k++) {
         const double dk = __shfl_sync(FULL, a[k], k);
         const bool valid = fabs(dk) > 0.0;
         const double inv = valid ? __drcp_rn(dk) : 1.0;
-        if (lane == 0 && k < bs) vinv[k0 + k] = inv;
-        const double w = a[k];                      // unscaled column entry of this lane's row (rows > k)
+        if (lane == 0) vinv[k0 + k] = inv;
+        const double w = a[k];
         const double l = w * inv;
 #pragma unroll
         for (int j = k + 1; j < K3_NB; j++) {
@@ -199,7 +224,8 @@ __device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, in
         }
         if (row > k) a[k] = l;
     }
-    if (lane < bs) {
+#endif
+    if (lane < K3_NB) {
 #pragma unroll
         for (int c = 0; c < K3_NB; c++) if (c <= lane) A[(k0 + lane) * K3_LD + k0 + c] = a[c];
     }
@@ -236,6 +262,16 @@ __device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, in
     if (lane < bs) v[k0 + lane] = x;
 }
 
+// Clock read that the compiler cannot move across memory operations, and that the hardware cannot execute before a
+// preceding barrier has completed: BAR.SYNC.DEFER_BLOCKING lets a warp run ahead until its next memory instruction,
+// so the dependent shared-memory load in front pins the read to "after the barrier released this warp".
+__device__ __forceinline__ long long clk_fenced() {
+    long long t;
+    unsigned sink;
+    asm volatile("{ .reg .u32 a; mov.u32 a, 0; ld.volatile.shared.u32 %1, [a]; }\n\tmov.u64 %0, %%clock64;" : "=l"(t), "=r"(sink)::"memory");
+    if (sink == 0x7f123456u) t ^= 1;      // makes the clock read depend on the load's completion
+    return t;
+}
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
@@ -246,9 +282,9 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     extern __shared__ double sm3[];
     double *A0 = sm3;                       // [n][K3_LD] row-major assembled matrix
     double *A = A0 + MAXN * K3_LD;          // permuted copy (+ rhs as row n), factorised in place
-    double *Wp = A + (MAXN + 1) * K3_LD;    // [K3_NB][K3_WPLD] panel W = L*D of the current block step
-    double *vinv = Wp + K3_NB * K3_WPLD;    // [MAXN] reciprocal pivots
-    double *vb = vinv + MAXN;               // rhs / solution
+    double *Wp = A + (K3_NP + 1) * K3_LD;    // [K3_NB][K3_WPLD] panel W = L*D of the current block step
+    double *vinv = Wp + K3_NB * K3_WPLD;    // [K3_NP] reciprocal pivots
+    double *vb = vinv + K3_NP;               // rhs / solution
     double *vS = vb + MAXN;                 // SVecI
     double *vd = vS + MAXN;                 // delta / temp
     double *vx = vd + MAXN;                 // x
@@ -280,7 +316,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         }
     }
     int dbgi = 0;
-#define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clock64(); dbgi++; } while (0)
+#define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clk_fenced(); dbgi++; } while (0)
     K3_STAMP();
     if (tid == 0) {      // wall-clock timeline of one iteration (development aid): K3 span here, K2a/K2b spans by atomics
         unsigned long long gt;
@@ -332,84 +368,109 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         __syncthreads();
         K3_STAMP();   // 2: assembled system loaded
         // A = P (S A0 S) P^T, b' = P S b
-        for (int r = warp; r < n; r += K3_THREADS / 32) {
-            const int pr = perm[r];
+        const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole blocks; the rhs is row npad
+        for (int r = warp; r < npad; r += K3_THREADS / 32) {
+            const int pr = (r < n) ? perm[r] : 0;
             const double sr = vS[pr];
 #pragma unroll
-            for (int cc = 0; cc < (MAXN + 31) / 32; cc++) {
+            for (int cc = 0; cc < (K3_NP + 31) / 32; cc++) {
                 const int c = lane + 32 * cc;
-                if (c < n) {
-                    const int pc = perm[c];
-                    A[r * K3_LD + c] = A0[pr * K3_LD + pc] * sr * vS[pc];
+                if (c < npad) {
+                    double v = (r == c) ? 1.0 : 0.0;
+                    if (r < n && c < n) { const int pc = perm[c]; v = A0[pr * K3_LD + pc] * sr * vS[pc]; }
+                    A[r * K3_LD + c] = v;
                 }
             }
         }
-        if (tid < n) vd[tid] = vb[perm[tid]] * vS[perm[tid]];
-        __syncthreads();
-        if (tid < n) vb[tid] = vd[tid];
+        if (tid < npad) A[npad * K3_LD + tid] = (tid < n) ? vb[perm[tid]] * vS[perm[tid]] : 0.0;
         __syncthreads();
 
         K3_STAMP();   // 3: scaled+permuted
         // ---- blocked in-place LDL^T (lower) of the matrix AUGMENTED with the right-hand side as row n:
         // the panel/trailing steps then leave D^-1 L^-1 b in that row, i.e. the forward solve comes for free.
-        if (tid < n) A[n * K3_LD + tid] = vb[tid];
-        __syncthreads();
         // Look-ahead schedule: while warps 1.. apply block step k to the rows below the NEXT diagonal block, warp 0
         // applies it to that block and factorises it right away, so the serial 8-pivot chain of step k+1 is hidden
-        // behind the trailing update of step k (two barriers per step instead of three).
-        if (warp == 0) ldlt_diag_block_warp(A, vinv, 0, min(K3_NB, n), lane);
-        __syncthreads();
-        for (int k0 = 0; k0 < n; k0 += K3_NB) {
-            const int bs = min(K3_NB, n - k0), m0 = k0 + bs;
-            if (tid < n + 1 - m0) {      // panel row i (incl. the rhs row n): w = L*D (unscaled), l = L
+        // behind the trailing update of step k (two barriers per step).
+        long long tp = 0, tw = 0, tb1 = 0, tb2 = 0, tq;     // this thread's clocks in panel / barrier / trailing(+diag) / barrier (development aid)
+        // (the loop starts one block early: that pass only factorises diagonal block 0, so the serial pivot code exists
+        // once -- a second inlined copy in front of the loop costs ~19 k cycles of cold instruction fetch per launch)
+        for (int k0 = -K3_NB; k0 < npad; k0 += K3_NB) {
+            const int m0 = k0 + K3_NB;
+            tq = clk_fenced();
+            if (tid == 0) ws->dbg[33 + (k0 >> 3)] = tq;
+            if (k0 >= 0 && tid < npad + 1 - m0) {      // panel row i (incl. the rhs row npad): w = L*D (unscaled), l = L
                 const int i = m0 + tid;
+#if K3V_PANEL_HOIST
+                // all operands first (the 28 entries of L11 are warp-uniform broadcasts), then the 8-step substitution
+                double a[K3_NB], iv[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2], w[K3_NB];
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) { a[c] = A[i * K3_LD + k0 + c]; iv[c] = vinv[k0 + c]; }
+#pragma unroll
+                for (int c = 1; c < K3_NB; c++)
+#pragma unroll
+                    for (int j = 0; j < c; j++) Lb[c * (c - 1) / 2 + j] = A[(k0 + c) * K3_LD + k0 + j];
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) {
+                    double s0 = a[c], s1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < c; j += 2) s0 -= w[j] * Lb[c * (c - 1) / 2 + j];
+#pragma unroll
+                    for (int j = 1; j < c; j += 2) s1 -= w[j] * Lb[c * (c - 1) / 2 + j];
+                    w[c] = s0 + s1;
+                }
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) {
+                    A[i * K3_LD + k0 + c] = w[c] * iv[c];
+                    Wp[c * K3_WPLD + i] = w[c];
+                }
+#else
                 double w[K3_NB];
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) {
-                    if (c < bs) {
-                        double s0 = A[i * K3_LD + k0 + c], s1 = 0.0;
+                    double s0 = A[i * K3_LD + k0 + c], s1 = 0.0;
 #pragma unroll
-                        for (int j = 0; j < c; j += 2) s0 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
+                    for (int j = 0; j < c; j += 2) s0 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
 #pragma unroll
-                        for (int j = 1; j < c; j += 2) s1 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
-                        w[c] = s0 + s1;
-                    } else w[c] = 0.0;
+                    for (int j = 1; j < c; j += 2) s1 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
+                    w[c] = s0 + s1;
                 }
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) {
-                    if (c < bs) A[i * K3_LD + k0 + c] = w[c] * vinv[k0 + c];
+                    A[i * K3_LD + k0 + c] = w[c] * vinv[k0 + c];
                     Wp[c * K3_WPLD + i] = w[c];
                 }
+#endif
             }
+            { const long long t1 = clk_fenced(); tp += t1 - tq; tq = t1; }
             __syncthreads();
-            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= min(i, n-1), i <= n
-            const int bs2 = min(K3_NB, n - m0);           // size of the next diagonal block (<= 0: none)
+            { const long long t1 = clk_fenced(); tb1 += t1 - tq; tq = t1; }
+            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= min(i, npad-1), i <= npad
             if (warp == 0) {
-                if (bs2 > 0) {
+                if (m0 < npad) {
+                    if (k0 >= 0) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int e = lane + 32 * h, r = e >> 3, cc = e & 7;
-                        if (cc <= r && r < bs2) {
+                        for (int h = 0; h < 2; h++) {
+                            const int e = lane + 32 * h, r = e >> 3, cc = e & 7;
                             const int i = m0 + r, j = m0 + cc;
                             double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                             for (int c = 0; c < K3_NB; c += 2) {
-                                if (c < bs) s0 += A[i * K3_LD + k0 + c] * Wp[c * K3_WPLD + j];
-                                if (c + 1 < bs) s1 += A[i * K3_LD + k0 + c + 1] * Wp[(c + 1) * K3_WPLD + j];
+                                s0 += A[i * K3_LD + k0 + c] * Wp[c * K3_WPLD + j];
+                                s1 += A[i * K3_LD + k0 + c + 1] * Wp[(c + 1) * K3_WPLD + j];
                             }
-                            A[i * K3_LD + j] -= (s0 + s1);
+                            if (cc <= r) A[i * K3_LD + j] -= (s0 + s1);
                         }
                     }
                     __syncwarp();
-                    ldlt_diag_block_warp(A, vinv, m0, bs2, lane);
+                    ldlt_diag_block_warp(A, vinv, m0, lane);
                 }
-            } else {
+            } else if (k0 >= 0) {
                 const int t = tid - 32;
-                for (int i = m0 + max(bs2, 0) + (t >> 4); i <= n; i += (K3_THREADS - 32) / 16) {
+                for (int i = m0 + K3_NB + (t >> 4); i <= npad; i += (K3_THREADS - 32) / 16) {
                     double li[K3_NB];
 #pragma unroll
-                    for (int c = 0; c < K3_NB; c++) li[c] = (c < bs) ? A[i * K3_LD + k0 + c] : 0.0;
-                    const int jmax = min(i, n - 1);
+                    for (int c = 0; c < K3_NB; c++) li[c] = A[i * K3_LD + k0 + c];
+                    const int jmax = min(i, npad - 1);
 #pragma unroll 2
                     for (int j = m0 + (t & 15); j <= jmax; j += 16) {
                         double s0 = 0.0, s1 = 0.0;
@@ -419,13 +480,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
                     }
                 }
             }
+            { const long long t1 = clk_fenced(); tw += t1 - tq; tq = t1; }
             __syncthreads();
+            tb2 += clk_fenced() - tq;
         }
+        if (tid == 0) { ws->dbg[20] = tp; ws->dbg[21] = tb1; ws->dbg[22] = tw; ws->dbg[23] = tb2; ws->dbg[33 + 9] = clk_fenced(); }
+        if (tid == 32) { ws->dbg[24] = tp; ws->dbg[25] = tb1; ws->dbg[26] = tw; ws->dbg[27] = tb2; }
+        if (tid == 496) { ws->dbg[28] = tp; ws->dbg[29] = tb1; ws->dbg[30] = tw; ws->dbg[31] = tb2; }
         K3_STAMP();   // 4: factorised
         // row n now holds D^-1 L^-1 b (unscaled where the pivot was invalid): Eigen's solve uses the pseudo-inverse of D
         if (tid < n) {
             const double dk = A[tid * K3_LD + tid];
-            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? A[n * K3_LD + tid] : 0.0;
+            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? A[npad * K3_LD + tid] : 0.0;
         }
         __syncthreads();
         // ---- backward solve L^T x = z, blocked from the last block up, column oriented: once a block of x is final its
@@ -522,4 +588,4 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     }
     if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
 }
-#define K3_SMEM_BYTES (((2 * MAXN + 1) * K3_LD + K3_NB * K3_WPLD + 5 * MAXN) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 64)
+#define K3_SMEM_BYTES (((MAXN + K3_NP + 1) * K3_LD + K3_NB * K3_WPLD + 4 * MAXN + K3_NP) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 64)

@@ -128,7 +128,7 @@ struct WinState {
     int canbreak;
     int iteration_count;
     float sumNID, numID;
-    long long dbg[32];               // clock64() phase stamps of the last K3 (development aid)
+    long long dbg[64];               // clock64() phase stamps of the last K3 (development aid)
 };
 
 // device pointers of the flattened window

@@ -5,12 +5,14 @@ from ldso_b200 import capi, synth
 win = synth.make_window(nF=8, pts_per_frame=250, seed=42)
 ctx = capi.Context(win.w, win.h, win.levels); ctx.load_synth_window(win)
 ctx.optimize_begin(); ctx.gn_iterations(0, 30); ctx.synchronize()
-buf = (C.c_longlong*48)()
+buf = (C.c_longlong*80)()
 ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
 t = np.array(buf[:10]); print("K3 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
-t = np.array(buf[32:40]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
-t = np.array(buf[40:44]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
-t = np.array(buf[44:46]); print("K2b select-CTA cycles:", np.diff(t))
+print("K3 stamp3 -> step tops -> loop end:", [int(buf[32+i] - buf[3]) for i in range(11)], "stamp4 at", int(buf[4]-buf[3]))
+print("K3 factorisation clocks [panel, barrier, trailing/diag, barrier]: tid0", list(buf[20:24]), "tid32", list(buf[24:28]), "tid496", list(buf[28:32]))
+t = np.array(buf[64:72]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
+t = np.array(buf[72:76]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
+t = np.array(buf[76:78]); print("K2b select-CTA cycles:", np.diff(t))
 cap = 1024
 sp = (C.c_longlong * (3 * cap))()
 n = ctx.L.ldso_b200_debug_cta_spans(ctx.ctx, sp, cap)
