@@ -158,6 +158,13 @@ int ldso_b200_do_step(ldso_b200_ctx *ctx, int *canbreak);
  * stitchDouble without priors, HM += setting_margWeightFac (M - Msc), bM likewise (read back with get_marg_prior;
  * get_system returns M, Mb, Msc, Mbsc). The caller then removes the points from its window (removePoint). */
 int ldso_b200_marginalize_points(ldso_b200_ctx *ctx, int n, const int32_t *point_idx, float prior_fac, int *resInM);
+/* EnergyFunctional::marginalizeFrame (EnergyFunctional.cc:72-129), the HM/bM algebra, on the device-resident prior:
+ * the frame's block is moved to the end, its own prior added, and the 8 variables are eliminated by a scaled Schur
+ * complement. HM, bM shrink to 8(nF-1)+4 (returned in *new_dim; get_marg_prior returns that size) until the next
+ * set_frames. set_frames then KEEPS the prior when it is called with the remaining nF-1 frames, and extends it with a
+ * zero block when one keyframe is appended (EnergyFunctional::insertFrame, :38-44); any other dimension clears it.
+ * The bookkeeping half of the reference function (frame list, makeIDX, :131-150) is the caller's set_frames/set_window. */
+int ldso_b200_marginalize_frame(ldso_b200_ctx *ctx, int frame_idx, int *new_dim);
 
 /* ---- the fused, device-resident Gauss-Newton loop ------------------------------------------------------
  * FullSystem::optimize's prologue (resetOOB + linearizeAll(false) + applyRes, FullSystem.cc:734-771). */

@@ -53,7 +53,7 @@ SYMBOLS = [
     "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_kernel_times", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
-    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_optimize_begin",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
@@ -270,8 +270,14 @@ class Context:
         self._chk(self.L.ldso_b200_marginalize_points(self.ctx, int(idx.shape[0]), _i(idx), C.c_float(prior_fac), C.byref(r)))
         return r.value
 
-    def marg_prior(self):
-        n = self.n
+    def marginalize_frame(self, idx):
+        """EnergyFunctional::marginalizeFrame's prior algebra on the device; returns the shrunken (HM, bM)."""
+        nd = C.c_int()
+        self._chk(self.L.ldso_b200_marginalize_frame(self.ctx, int(idx), C.byref(nd)))
+        return self.marg_prior(nd.value)
+
+    def marg_prior(self, n=None):
+        n = self.n if n is None else n
         HM = np.zeros((n, n), np.float64, order="F")
         bM = np.zeros(n)
         self._chk(self.L.ldso_b200_get_marg_prior(self.ctx, _d(HM), _d(bM)))

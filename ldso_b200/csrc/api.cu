@@ -51,6 +51,9 @@ struct ldso_b200_ctx {
     double *sol_host = nullptr;      // pinned staging for get_last_solution
     // K2b(do_assemble) has produced the system K3 solves and nothing it depends on changed since
     bool solve_ready = false;
+    // dimension of the device-resident marginalisation prior HM, bM (0 = all zero, any dimension): set_marg_prior,
+    // marginalize_points -> n; marginalize_frame -> n - 8; set_frames keeps / grows / clears it accordingly
+    int prior_dim = 0;
     // the reduced accumulators still describe the current window state (a re-stitch is enough to get solve_ready back)
     bool restitch_ok = false;
     int *iteration_dev = nullptr;
@@ -671,8 +674,19 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     CUDA_CHECK_RET(c, cudaEventRecord(c->frames_copied, c->stream));
     if (!evalpt_cached)     // pageable source: staged before the call returns
         CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.Pns, c->Pns_host.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
-    CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
+    if (c->prior_dim == n) {
+        // same frames as the prior describes (a repeated set_frames, or the window after marginalize_frame + insertFrame)
+    } else if (c->prior_dim > 0 && c->prior_dim == n - 8) {
+        // one keyframe appended since the prior was last touched: EnergyFunctional::insertFrame (EnergyFunctional.cc:38-44)
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sb.A0g, c->sb.HM, sizeof(double) * (n - 8) * (n - 8), cudaMemcpyDeviceToDevice, c->stream));
+        k_grow_prior<<<(n * n + 255) / 256, 256, 0, c->stream>>>(c->sb, c->sb.A0g, n);
+        LAUNCH_CHECK(c);
+        c->prior_dim = n;
+    } else {
+        CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
+        CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
+        c->prior_dim = 0;
+    }
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
     LAUNCH_CHECK(c);
     c->solve_ready = false; c->restitch_ok = false;
@@ -691,13 +705,14 @@ extern "C" int ldso_b200_set_marg_prior(ldso_b200_ctx *c, const double *HM, cons
     else CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     c->solve_ready = false;      // HM/bM enter the assembled system
+    c->prior_dim = (HM || bM) ? n : 0;
     return LDSO_B200_OK;
 }
 
 extern "C" int ldso_b200_get_marg_prior(ldso_b200_ctx *c, double *HM, double *bM) {
     if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
-    const int n = c->n;
+    const int n = (c->prior_dim > 0) ? c->prior_dim : c->n;      // n - 8 between marginalize_frame and the next set_frames
     if (HM) CUDA_CHECK_RET(c, cudaMemcpyAsync(HM, c->sb.HM, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
     if (bM) CUDA_CHECK_RET(c, cudaMemcpyAsync(bM, c->sb.bM, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
@@ -723,6 +738,8 @@ static int launch_k2a(ldso_b200_ctx *c, int full) {
     return LDSO_B200_OK;
 }
 static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select, int do_assemble) {
+    if (do_stitch && do_assemble && c->prior_dim != 0 && c->prior_dim != c->n)
+        return c->fail(LDSO_B200_ERR_STATE, "the marginalisation prior has a different dimension than the frames (marginalize_frame): call set_frames with the remaining frames first");
     const int nb = c->nF * c->nF + c->nF + 2;
     c->kt_begin("k2b");
     k2b_stitch<<<nb, K2B_THREADS, K2B_SMEM_BYTES, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select, do_stitch && do_assemble);
@@ -886,6 +903,7 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
     RET_IF(launch_k2a(c, 1));
     RET_IF(launch_k2b(c, 1, 0, 0));
     c->restitch_ok = false;      // the reduced buffer now holds the mode-2 (marginalisation) accumulators
+    c->prior_dim = c->n;
     const int nn = c->n;
     k_add_marg<<<(nn * nn + 255) / 256, 256, 0, c->stream>>>(c->sb, nn, (double) c->S.margWeightFac);
     LAUNCH_CHECK(c);
@@ -893,6 +911,25 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
         CUDA_CHECK_RET(c, cudaMemcpyAsync(resInM, &c->ws_dev->resInA, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     }
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_marginalize_frame(ldso_b200_ctx *c, int frame_idx, int *new_dim) {
+    if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
+    if (frame_idx < 0 || frame_idx >= c->nF) return c->fail(LDSO_B200_ERR_ARG, "frame index out of range");
+    if (c->nF < 2) return c->fail(LDSO_B200_ERR_STATE, "cannot marginalise the only frame");
+    if (c->prior_dim != 0 && c->prior_dim != c->n) return c->fail(LDSO_B200_ERR_STATE, "prior dimension does not match the frames: call set_frames first");
+    cudaSetDevice(c->device);
+    const int n = c->n;
+    if (c->prior_dim == 0) {     // an all-zero prior of the current dimension
+        CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.HM, 0, sizeof(double) * n * n, c->stream));
+        CUDA_CHECK_RET(c, cudaMemsetAsync(c->sb.bM, 0, sizeof(double) * n, c->stream));
+    }
+    k_marginalize_frame<<<1, KMF_THREADS, KMF_SMEM_BYTES(n), c->stream>>>(c->sb, c->ws_dev, n, frame_idx);
+    LAUNCH_CHECK(c);
+    c->prior_dim = n - 8;
+    c->solve_ready = false; c->restitch_ok = false;
+    if (new_dim) *new_dim = n - 8;
     return LDSO_B200_OK;
 }
 

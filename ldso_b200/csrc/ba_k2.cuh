@@ -630,3 +630,118 @@ __global__ void k_add_marg(SolveBufs sb, int n, double w) {
     if (e < n * n) sb.HM[e] += w * (sb.H_A[e] - sb.H_sc[e]);
     if (e < n) sb.bM[e] += w * (sb.b_A[e] - sb.b_sc[e]);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// EnergyFunctional::marginalizeFrame, the prior algebra (EnergyFunctional.cc:72-129), on the device-resident HM, bM:
+// move the frame's 8 rows/columns to the end (:81-99), add its own prior (:103-104), scale by (|diag|+10)^1/2 (:106-111),
+// invert the 8x8 block (partial-pivot LU like Eigen's fixed-size inverse(), :114-117), Schur complement (:120-122),
+// unscale (:125-126), symmetrise (:129). Output is written with the NEW leading dimension n-8. One CTA.
+#define KMF_THREADS 256
+__global__ void __launch_bounds__(KMF_THREADS) k_marginalize_frame(SolveBufs sb, const WinState *ws, int n, int fidx) {
+    extern __shared__ double smf[];
+    const int ndim = n - 8, io = CPARS + 8 * fidx, tid = threadIdx.x;
+    double *H = smf;                 // [n*n] column-major, frame block moved to the end
+    double *b = H + n * n;           // [n]
+    double *SV = b + n;              // [n]
+    double *bli = SV + n;            // [ndim][8]
+    double *hp = bli + ndim * 8;     // [8][8] row-major inverse
+    double *lu = hp + 64;            // [8][8] row-major LU
+    __shared__ int piv[8];
+    auto pold = [&](int i) { return (i < io) ? i : ((i < ndim) ? i + 8 : io + (i - ndim)); };
+    for (int e = tid; e < n * n; e += KMF_THREADS) {
+        const int j = e / n, i = e - j * n;
+        H[e] = sb.HM[(size_t) pold(j) * n + pold(i)];
+    }
+    if (tid < n) b[tid] = sb.bM[pold(tid)];
+    __syncthreads();
+    if (tid < 8) {
+        const FrameDev &f = ws->fr[fidx];
+        H[(ndim + tid) * n + ndim + tid] += f.prior[tid];
+        b[ndim + tid] += f.prior[tid] * f.delta_prior[tid];
+    }
+    __syncthreads();
+    if (tid < n) SV[tid] = sqrt(fabs(H[tid * n + tid]) + 10.0);
+    __syncthreads();
+    for (int e = tid; e < n * n; e += KMF_THREADS) {
+        const int j = e / n, i = e - j * n;
+        H[e] = ((1.0 / SV[i]) * H[e]) * (1.0 / SV[j]);
+    }
+    __syncthreads();            // (b is scaled after the matrix: its entries feed nothing before the next barrier)
+    if (tid < n) b[tid] = (1.0 / SV[tid]) * b[tid];
+    if (tid < 64) { const int r = tid >> 3, c = tid & 7; lu[tid] = 0.5f * (H[(ndim + c) * n + ndim + r] + H[(ndim + c) * n + ndim + r]); }
+    __syncthreads();
+    if (tid == 0) {             // unblocked partial-pivot LU of the 8x8 block (a few hundred flops, serial)
+        int p[8];
+        for (int i = 0; i < 8; i++) p[i] = i;
+        for (int k = 0; k < 8; k++) {
+            int pv = k;
+            double best = fabs(lu[k * 8 + k]);
+            for (int i = k + 1; i < 8; i++) if (fabs(lu[i * 8 + k]) > best) { best = fabs(lu[i * 8 + k]); pv = i; }
+            if (pv != k) {
+                for (int j = 0; j < 8; j++) { const double t = lu[k * 8 + j]; lu[k * 8 + j] = lu[pv * 8 + j]; lu[pv * 8 + j] = t; }
+                const int t = p[k]; p[k] = p[pv]; p[pv] = t;
+            }
+            if (lu[k * 8 + k] != 0.0) {
+                const double dd = lu[k * 8 + k];
+                for (int i = k + 1; i < 8; i++) lu[i * 8 + k] /= dd;
+            }
+            for (int j = k + 1; j < 8; j++)
+                for (int i = k + 1; i < 8; i++) lu[i * 8 + j] -= lu[i * 8 + k] * lu[k * 8 + j];
+        }
+        for (int i = 0; i < 8; i++) piv[i] = p[i];
+    }
+    __syncthreads();
+    if (tid < 8) {              // column tid of the inverse: solve L U x = P e_c
+        double x[8];
+        for (int i = 0; i < 8; i++) x[i] = (piv[i] == tid) ? 1.0 : 0.0;
+        for (int i = 0; i < 8; i++) for (int j = 0; j < i; j++) x[i] -= lu[i * 8 + j] * x[j];
+        for (int i = 7; i >= 0; i--) {
+            for (int j = i + 1; j < 8; j++) x[i] -= lu[i * 8 + j] * x[j];
+            x[i] /= lu[i * 8 + i];
+        }
+        for (int i = 0; i < 8; i++) hp[i * 8 + tid] = 0.5f * (x[i] + x[i]);
+    }
+    __syncthreads();
+    for (int e = tid; e < ndim * 8; e += KMF_THREADS) {     // bli = bottomLeft^T * hpi
+        const int i = e >> 3, k = e & 7;
+        double s = 0.0;
+        for (int m = 0; m < 8; m++) s += H[i * n + ndim + m] * hp[m * 8 + k];
+        bli[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < ndim * ndim; e += KMF_THREADS) {  // topLeft -= bli * bottomLeft (rows >= ndim are read-only here)
+        const int j = e / ndim, i = e - j * ndim;
+        double s = 0.0;
+        for (int k = 0; k < 8; k++) s += bli[i * 8 + k] * H[j * n + ndim + k];
+        H[j * n + i] -= s;
+    }
+    if (tid < ndim) {
+        double s = 0.0;
+        for (int k = 0; k < 8; k++) s += bli[tid * 8 + k] * b[ndim + k];
+        b[tid] -= s;
+    }
+    __syncthreads();
+    for (int e = tid; e < ndim * ndim; e += KMF_THREADS) {
+        const int j = e / ndim, i = e - j * ndim;
+        H[j * n + i] = (SV[i] * H[j * n + i]) * SV[j];
+    }
+    if (tid < ndim) b[tid] = SV[tid] * b[tid];
+    __syncthreads();
+    for (int e = tid; e < ndim * ndim; e += KMF_THREADS) {
+        const int j = e / ndim, i = e - j * ndim;
+        sb.HM[(size_t) j * ndim + i] = 0.5 * (H[j * n + i] + H[i * n + j]);
+    }
+    if (tid < ndim) sb.bM[tid] = b[tid];
+}
+#define KMF_SMEM_BYTES(n) ((size_t) ((n) * (n) + 2 * (n) + ((n) - 8) * 8 + 128) * sizeof(double))
+
+// EnergyFunctional::insertFrame's resize of HM, bM (EnergyFunctional.cc:38-44): re-lay the (n-8)^2 prior out with the new
+// leading dimension n and zero the new frame's rows/columns. src = copy of the old HM.
+__global__ void k_grow_prior(SolveBufs sb, const double *src, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, od = n - 8;
+    if (e < n * n) {
+        const int j = e / n, i = e - j * n;
+        sb.HM[e] = (i < od && j < od) ? src[(size_t) j * od + i] : 0.0;
+    }
+    if (e >= od && e < n) sb.bM[e] = 0.0;
+}

@@ -247,7 +247,9 @@ inline bool EnergyFunctional::syncToDevice(shared_ptr<CalibHessian> &HCalib) {
         fs[i].ab_exposure = f.ab_exposure; fs[i].frameEnergyTH = f.frameEnergyTH; fs[i].frame_id = f.frame->id; fs[i].image_slot = f.imageSlot;
     }
     if (ldso_b200_set_frames(ctx, (int) frames.size(), fs.data(), HCalib->value_scaled.v, HCalib->value_zero.v)) return false;
+    // the host mirror owns HM, bM in this shim: push them (or an explicit zero prior) after every set_frames
     if (HM.r == 8 * nFrames + CPARS) ldso_b200_set_marg_prior(ctx, HM.d.data(), bM.d.data());
+    else ldso_b200_set_marg_prior(ctx, nullptr, nullptr);
     // flatten allPoints / residuals (EnergyFunctional::makeIDX order)
     const int nP = (int) allPoints.size();
     std::vector<int32_t> host(nP), rb(nP + 1, 0), tgt;

@@ -1509,6 +1509,59 @@ void Window::marginalizePointsF(const std::vector<int> &pointIdx) {
     last_HA = M; last_bA = Mb; last_Hsc = Msc; last_bsc = Mbsc;
 }
 
+// EnergyFunctional::marginalizeFrame — :72-129, the prior algebra: move the frame's 8 rows/columns of HM, bM to the end,
+// add its own prior there, scale by (|diag| + 10)^1/2, Schur-complement the 8x8 block out, unscale, symmetrise.
+// HM, bM shrink by 8. (The bookkeeping half, :131-150, belongs to the caller, who rebuilds the window without the frame.)
+void Window::marginalizeFramePrior(int idx) {
+    const int odim = nFrames * 8 + CPARS, ndim = odim - 8;
+    const Frame &fh = frames[idx];
+    std::vector<int> p(odim);                       // new position -> old position (the block moves of :81-99)
+    const int io = idx * 8 + CPARS;
+    for (int i = 0; i < io; i++) p[i] = i;
+    for (int i = io; i < ndim; i++) p[i] = i + 8;
+    for (int k = 0; k < 8; k++) p[ndim + k] = io + k;
+    MatX H(odim, odim);
+    VecXd b(odim);
+    for (int j = 0; j < odim; j++) { b[j] = bM[p[j]]; for (int i = 0; i < odim; i++) H(i, j) = HM(p[i], p[j]); }
+    for (int k = 0; k < 8; k++) {                   // :103-104
+        H(ndim + k, ndim + k) += fh.prior[k];
+        b[ndim + k] += fh.prior[k] * fh.delta_prior[k];
+    }
+    VecXd SVec(odim), SVecI(odim);                  // :106-107
+    for (int i = 0; i < odim; i++) { SVec[i] = std::sqrt(std::fabs(H(i, i)) + 10.0); SVecI[i] = 1.0 / SVec[i]; }
+    MatX Hs(odim, odim);                            // :110-111
+    VecXd bs(odim);
+    for (int j = 0; j < odim; j++) { bs[j] = SVecI[j] * b[j]; for (int i = 0; i < odim; i++) Hs(i, j) = (SVecI[i] * H(i, j)) * SVecI[j]; }
+    MatX hpi(8, 8);                                 // :114-117 (the two 0.5f*(hpi+hpi) statements are exact no-ops)
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) hpi(i, j) = 0.5f * (Hs(ndim + i, ndim + j) + Hs(ndim + i, ndim + j));
+    hpi = inverse_partial_piv_lu(hpi);
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) hpi(i, j) = 0.5f * (hpi(i, j) + hpi(i, j));
+    MatX bli(ndim, 8);                              // :120  bli = bottomLeft^T * hpi
+    for (int i = 0; i < ndim; i++)
+        for (int k = 0; k < 8; k++) {
+            double s = 0.0;
+            for (int m = 0; m < 8; m++) s += Hs(ndim + m, i) * hpi(m, k);
+            bli(i, k) = s;
+        }
+    for (int j = 0; j < ndim; j++)                  // :121-122
+        for (int i = 0; i < ndim; i++) {
+            double s = 0.0;
+            for (int k = 0; k < 8; k++) s += bli(i, k) * Hs(ndim + k, j);
+            Hs(i, j) -= s;
+        }
+    for (int i = 0; i < ndim; i++) {
+        double s = 0.0;
+        for (int k = 0; k < 8; k++) s += bli(i, k) * bs[ndim + k];
+        bs[i] -= s;
+    }
+    for (int j = 0; j < odim; j++) { bs[j] = SVec[j] * bs[j]; for (int i = 0; i < odim; i++) Hs(i, j) = (SVec[i] * Hs(i, j)) * SVec[j]; }   // :125-126
+    MatX Hn(ndim, ndim);                            // :129-130
+    VecXd bn(ndim);
+    for (int j = 0; j < ndim; j++) { bn[j] = bs[j]; for (int i = 0; i < ndim; i++) Hn(i, j) = 0.5 * (Hs(i, j) + Hs(j, i)); }
+    HM = Hn;
+    bM = bn;
+}
+
 template void Window::topAddPoint<0>(AccumulatedTopHessianSSE &, Point &, int);
 template void Window::topAddPoint<1>(AccumulatedTopHessianSSE &, Point &, int);
 template void Window::topAddPoint<2>(AccumulatedTopHessianSSE &, Point &, int);

@@ -305,6 +305,7 @@ struct Window {
 
     // marginalisation algebra
     void marginalizePointsF(const std::vector<int> &pointIdx);   // EnergyFunctional.cc:165-222
+    void marginalizeFramePrior(int idx);                         // EnergyFunctional.cc:72-129 (HM, bM algebra only)
 };
 
 // bilinear sampler, GlobalFuncs.h:89-103

@@ -133,6 +133,14 @@ void oracle_ba_marginalize_points(void *o, int n, const int *pointIdx, float pri
     W->marginalizePointsF(idx);
 }
 
+// EnergyFunctional::marginalizeFrame's prior algebra for frame idx; HM, bM shrink to 8(nF-1)+4 (get_marg_prior then
+// returns that size). Returns the new dimension.
+int oracle_ba_marginalize_frame(void *o, int idx) {
+    Window *W = (Window *) o;
+    W->marginalizeFramePrior(idx);
+    return W->HM.r;
+}
+
 int oracle_ba_dims(void *o, int *nFrames, int *nPoints, int *nResiduals) {
     Window *W = (Window *) o;
     *nFrames = (int) W->frames.size();

@@ -52,6 +52,43 @@ inline MatX transpose(const MatX &A) {
 // ------------------------------------------------------------------------------------------
 // Eigen::LDLT<MatXX>::compute + solve restated (lower, unblocked, left-looking, with the
 // diagonal pivot search Eigen performs at each step). x = A^{-1} b. A is n x n col-major.
+// Inverse of a small dense matrix the way Eigen computes MatrixBase::inverse() for fixed sizes > 4: PartialPivLU
+// (unblocked: pivot = largest |entry| of the column at/below the diagonal, rows swapped, multipliers = column / pivot,
+// rank-1 update) followed by solve(Identity) (permute, unit-lower forward substitution, upper back substitution).
+inline MatX inverse_partial_piv_lu(const MatX &A_in) {
+    const int n = A_in.r;
+    MatX lu = A_in;
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double best = std::fabs(lu(k, k));
+        for (int i = k + 1; i < n; i++) if (std::fabs(lu(i, k)) > best) { best = std::fabs(lu(i, k)); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < n; j++) std::swap(lu(k, j), lu(piv, j));
+            std::swap(perm[k], perm[piv]);
+        }
+        if (lu(k, k) != 0.0) {
+            const double d = lu(k, k);
+            for (int i = k + 1; i < n; i++) lu(i, k) /= d;
+        }
+        for (int j = k + 1; j < n; j++)
+            for (int i = k + 1; i < n; i++) lu(i, j) -= lu(i, k) * lu(k, j);
+    }
+    MatX inv(n, n);
+    for (int c = 0; c < n; c++) {
+        std::vector<double> x(n);
+        for (int i = 0; i < n; i++) x[i] = (perm[i] == c) ? 1.0 : 0.0;       // P * e_c
+        for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) x[i] -= lu(i, j) * x[j];
+        for (int i = n - 1; i >= 0; i--) {
+            for (int j = i + 1; j < n; j++) x[i] -= lu(i, j) * x[j];
+            x[i] /= lu(i, i);
+        }
+        for (int i = 0; i < n; i++) inv(i, c) = x[i];
+    }
+    return inv;
+}
+
 inline VecXd ldlt_solve(const MatX &A_in, const VecXd &b) {
     const int n = A_in.r;
     MatX m = A_in;

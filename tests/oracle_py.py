@@ -134,12 +134,17 @@ class OracleBA:
         out.update(vecs)
         return out
 
-    def marg_prior(self):
-        n = self.n
+    def marg_prior(self, n=None):
+        n = self.n if n is None else n
         HM = np.zeros((n, n), np.float64, order="F")
         bM = np.zeros(n, np.float64)
         self.L.oracle_ba_get_marg_prior(self.o, _d(HM), _d(bM))
         return HM, bM
+
+    def marginalize_frame(self, idx):
+        """EnergyFunctional::marginalizeFrame's HM/bM algebra; returns the shrunken (HM, bM)."""
+        nd = int(self.L.oracle_ba_marginalize_frame(self.o, int(idx)))
+        return self.marg_prior(nd)
 
     def res_counts(self):
         a, l, m = C.c_int(), C.c_int(), C.c_int()

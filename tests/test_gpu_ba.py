@@ -383,3 +383,86 @@ def test_prior_change_between_stitch_and_solve(small_win):
     with pytest.raises(capi.Error):
         b.gn_iterations(0, 1)
     a.close(); b.close()
+
+
+KITTI_K = (718.856, 718.856, 607.1928, 185.2157)      # examples/Kitti/Kitti00-02.txt:1-4, cropped to 1232x368
+
+
+def test_kitti_geometry_window():
+    """BASELINE config 4's image geometry (1232x368, 5 pyramid levels, KITTI intrinsics): one linearizeAll and one
+    Gauss-Newton solve against the oracle; device makeImages bit-equal to the host pyramid at this size."""
+    win = synth.make_window(nF=4, pts_per_frame=120, w=1232, h=368, seed=11, K=np.array(KITTI_K))
+    assert win.levels == 5
+    ctx = _ctx(win)
+    ctx.make_images(7, win.pyramids[2][0][:, :, 0])
+    for l in range(win.levels):
+        assert np.array_equal(ctx.download_frame_level(7, l), win.pyramids[2][l])
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    eo = o.optimize_begin()
+    eg = ctx.linearize_all(False)
+    assert abs(eg - eo) <= 1e-5 * abs(eo)
+    rg, ro = ctx.residuals(with_J=False), o.residuals()
+    assert int(np.sum(rg["state_NewState"].astype(int) != ro["state_NewState"].astype(int))) <= 1
+    ctx.apply_res(); ctx.backup_state()
+    _check_solve(ctx, o, 0)
+    ctx.close()
+
+
+def test_config3_size_single_gpu():
+    """BASELINE config 3's window (8 KF x 20 000 points, 140 000 residuals) on ONE GPU: the stitched system and the
+    solve against the oracle at full size, plus run-to-run bit-reproducibility of the fused loop."""
+    win = synth.make_window(nF=8, pts_per_frame=2500, seed=42)
+    assert win.nP == 20000
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    ctx = _ctx(win)
+    eo = o.optimize_begin()
+    eg = ctx.linearize_all(False)
+    assert abs(eg - eo) <= 1e-5 * abs(eo)
+    ctx.apply_res(); ctx.backup_state()
+    _check_solve(ctx, o, 0)
+    ctx.close()
+    outs = []
+    for rep in range(2):
+        c2 = _ctx(win)
+        c2.optimize_begin(); c2.gn_iterations(0, 3)
+        outs.append((c2.last_solution()["lastX"], c2.points()["idepth"], c2.energy()[0]))
+        c2.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_marginalize_frame_and_prior_persistence(small_win):
+    """EnergyFunctional::marginalizeFrame's HM/bM algebra on the device-resident prior against the oracle, for the first,
+    a middle and the last frame; then the prior's life across set_frames: kept for the remaining frames, extended by a
+    zero block when a keyframe is appended (insertFrame), cleared for any other dimension."""
+    win = small_win
+    n = 8 * win.nF + 4
+    rng = np.random.default_rng(17)
+    B = rng.standard_normal((n, n)) * np.exp(rng.uniform(0, 6, n))[:, None]
+    HM = B @ B.T + np.diag(rng.uniform(1, 100, n))
+    bM = rng.standard_normal(n) * 100.0
+    for idx in (0, 2, win.nF - 1):
+        o = oracle_py.OracleBA(win, threads_mode=1)
+        o.set_marg_prior(HM, bM)
+        Ho, bo = o.marginalize_frame(idx)
+        ctx = _ctx(win)
+        ctx.set_marg_prior(HM, bM)
+        Hg, bg = ctx.marginalize_frame(idx)
+        assert Hg.shape == (n - 8, n - 8)
+        assert rel_err(Hg, Ho) < 1e-9 and rel_err(bg, bo) < 1e-9
+        assert np.array_equal(Hg, Hg.T)
+        # the solver refuses to run until the frame list matches the prior again
+        with pytest.raises(capi.Error):
+            ctx.optimize_begin(); ctx.gn_iterations(0, 1)
+        keep = [i for i in range(win.nF) if i != idx]
+        sub = lambda a: [a[i] for i in keep]
+        ctx.set_frames(sub(win.Rcw), sub(win.tcw), sub(win.state_zero), sub(win.state), sub(win.ab_exposure), sub(win.frame_id), keep, win.K)
+        H2, b2 = ctx.marg_prior()
+        assert np.array_equal(H2, Hg) and np.array_equal(b2, bg)                      # kept
+        ctx.set_frames(win.Rcw, win.tcw, win.state_zero, win.state, win.ab_exposure, win.frame_id, list(range(win.nF)), win.K)
+        H3, b3 = ctx.marg_prior()                                                      # one frame appended: zero block
+        assert np.array_equal(H3[:n - 8, :n - 8], Hg) and not H3[n - 8:, :].any() and not H3[:, n - 8:].any()
+        assert np.array_equal(b3[:n - 8], bg) and not b3[n - 8:].any()
+        ctx.set_frames(win.Rcw[:2], win.tcw[:2], win.state_zero[:2], win.state[:2], win.ab_exposure[:2], win.frame_id[:2], [0, 1], win.K)
+        H4, b4 = ctx.marg_prior()                                                      # unrelated dimension: cleared
+        assert not H4.any() and not b4.any()
+        ctx.close()

@@ -80,3 +80,21 @@ def test_make_coarse_depth_device(size):
         assert np.array_equal(ug, uo) and np.array_equal(vg, vo) and np.array_equal(cg, co)
         assert rel_err(ig, io_) < 1e-6
     ctx.close()
+
+
+def test_kitti_geometry_tracker():
+    """Config 4's image geometry (1232x368, 5 levels, KITTI intrinsics): calcRes/calcGSSSE on every level and the whole
+    trackNewestCoarse against the oracle."""
+    pair = synth.make_track_pair(w=1232, h=368, n_pts=1500, seed=9, K=np.array([718.856, 718.856, 607.1928, 185.2157]))
+    assert pair.levels == 5
+    ot, ctx = _setup(pair)
+    for l in range(pair.levels):
+        rg, Hg, bg = ctx.tracker_eval(l, pair.R_true, pair.t_true, 0.0, 0.0, 20.0)
+        ro, Ho, bo = ot.eval(l, pair.R_true, pair.t_true, 0.0, 0.0, 20.0)
+        assert rg[1] == ro[1] and rel_err(rg, ro) < 1e-5
+        assert rel_err(Hg, Ho) < TOL and rel_err(bg, bo) < TOL
+    okg, Rg, tg, ag, bg_, lrg, lfg = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    oko, Ro, to, ao, bo_, lro, lfo, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    assert okg == oko
+    assert rel_err(Rg, Ro) < 1e-5 and rel_err(tg, to) < 1e-3
+    ctx.close()

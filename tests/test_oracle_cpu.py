@@ -223,3 +223,40 @@ def test_tracker_converges_to_truth():
     assert rel_err(t, g["t"]) < 1e-9 and rel_err(R, g["R"]) < 1e-9
     res, H, bb = ot.eval(0, np.eye(3), np.zeros(3), 0.0, 0.0, 20.0)
     assert rel_err(H, g["H0"]) < 1e-9 and rel_err(bb, g["b0"]) < 1e-9 and rel_err(res, g["res0"]) < 1e-9
+
+
+def test_marginalize_frame_prior():
+    """EnergyFunctional::marginalizeFrame's HM/bM algebra (EnergyFunctional.cc:72-129) against an independent numpy
+    derivation, and the defining property of a Schur complement: the kept variables of the full solution solve the
+    reduced system."""
+    win = synth.make_window(nF=5, pts_per_frame=40, w=320, h=240, seed=3)
+    n = 8 * win.nF + 4
+    rng = np.random.default_rng(17)
+    B = rng.standard_normal((n, n)) * np.exp(rng.uniform(0, 6, n))[:, None]
+    HM = B @ B.T + np.diag(rng.uniform(1, 100, n))
+    bM = rng.standard_normal(n) * 100.0
+    for idx in (0, 2, win.nF - 1):
+        o = oracle_py.OracleBA(win, threads_mode=1)
+        o.set_marg_prior(HM, bM)
+        fr = o.frames()
+        prior, dprior = fr["prior"][idx], fr["delta_prior"][idx]
+        Hn, bn = o.marginalize_frame(idx)
+        nd = n - 8
+        assert Hn.shape == (nd, nd)
+        io = 4 + 8 * idx
+        keep = np.r_[0:io, io + 8:n]
+        p = np.r_[keep, io:io + 8]
+        H = HM[np.ix_(p, p)].copy(); b = bM[p].copy()
+        H[nd:, nd:] += np.diag(prior); b[nd:] += prior * dprior
+        S = np.sqrt(np.abs(np.diag(H)) + 10.0)
+        Hs = H / S[:, None] / S[None, :]; bs = b / S
+        hpi = np.linalg.inv(Hs[nd:, nd:])
+        bli = Hs[nd:, :nd].T @ hpi
+        Ht = Hs[:nd, :nd] - bli @ Hs[nd:, :nd]
+        bt = bs[:nd] - bli @ bs[nd:]
+        Ht = Ht * S[:nd, None] * S[None, :nd]; bt = bt * S[:nd]
+        Ht = 0.5 * (Ht + Ht.T)
+        assert rel_err(Hn, Ht) < 1e-9 and rel_err(bn, bt) < 1e-9
+        assert np.array_equal(Hn, Hn.T)
+        x_full = np.linalg.solve(H, b)
+        assert rel_err(np.linalg.solve(Hn, bn), x_full[:nd]) < 1e-6
