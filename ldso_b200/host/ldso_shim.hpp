@@ -191,6 +191,22 @@ public:
         if (h) for (size_t i = 0; i < h->pointHessians.size(); i++) if (h->pointHessians[i] == ph) { h->pointHessians.erase(h->pointHessians.begin() + i); break; }
         nPoints--; topologyEpoch++;
     }
+    // EnergyFunctional::marginalizeFrame (EnergyFunctional.cc:72-150): the HM/bM algebra runs on the device-resident prior
+    // (ldso_b200_marginalize_frame), the frame-list bookkeeping (:131-150) here. Points/residuals of the frame must
+    // already have been dropped or marginalised by the caller, as FullSystem::marginalizeFrame does.
+    bool marginalizeFrame(shared_ptr<FrameHessian> fh) {
+        if (!lastCalib || !syncToDevice(lastCalib)) return false;       // current states, delta_prior and HM on the device
+        int nd = 0;
+        if (ldso_b200_marginalize_frame(ctx, fh->idx, &nd)) return false;
+        HM.resize(nd, nd); bM.d.assign(nd, 0.0);
+        if (ldso_b200_get_marg_prior(ctx, HM.d.data(), bM.d.data())) return false;
+        for (size_t i = fh->idx; i + 1 < frames.size(); i++) { frames[i] = frames[i + 1]; frames[i]->idx = (int) i; }
+        frames.pop_back();
+        nFrames--;
+        makeIDX();
+        stateEpoch()++;
+        return true;
+    }
     void makeIDX() {            // EnergyFunctional.cc:385-401
         for (size_t i = 0; i < frames.size(); i++) frames[i]->idx = (int) i;
         allPoints.clear();
@@ -225,6 +241,7 @@ public:
         if (ldso_b200_upload_frame(ctx, slot, fh->dIp, L) == 0) fh->imageSlot = slot;
     }
     std::vector<shared_ptr<PointHessian>> allPoints;
+    shared_ptr<CalibHessian> lastCalib;          // the CalibHessian of the last sync (marginalizeFrame has no such argument)
     std::vector<shared_ptr<PointFrameResidual>> flatResiduals;
     unsigned long topologyEpoch = 1, uploadedTopology = 0, uploadedState = 0, linearizedState = 0;
     bool applyPending = false;
@@ -238,6 +255,7 @@ private:
 // ---------------------------------------------------------------------------------------------------------
 inline bool EnergyFunctional::syncToDevice(shared_ptr<CalibHessian> &HCalib) {
     if (!ctx) return false;
+    lastCalib = HCalib;
     if (uploadedState == stateEpoch() && uploadedTopology == topologyEpoch) return true;
     std::vector<ldso_b200_frame_state> fs(frames.size());
     for (size_t i = 0; i < frames.size(); i++) {

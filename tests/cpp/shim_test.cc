@@ -106,6 +106,31 @@ int main(int argc, char **argv) {
         bool ok = ef->optimizeOnDevice(0, 3, HCalib);
         printf("\"ok\": %s, \"energy\": [%.9g]", ok ? "true" : "false", ef->lastEnergy);
     }
+    if (argc > 2 && std::string(argv[2]) == "margframe") {
+        // EnergyFunctional::marginalizeFrame on a synthetic prior: HM = diag(50 + 3i) + v v^T, v_i = 20 sin(i+1), bM_i = 10 cos(i)
+        const int n = 8 * nF + 4;
+        ef->HM.resize(n, n); ef->bM.d.assign(n, 0.0);
+        for (int j = 0; j < n; j++) {
+            ef->bM.d[j] = 10.0 * std::cos((double) j);
+            for (int i = 0; i < n; i++) ef->HM(i, j) = 20.0 * std::sin(i + 1.0) * 20.0 * std::sin(j + 1.0) + (i == j ? 50.0 + 3.0 * i : 0.0);
+        }
+        ldso::internal::stateEpoch()++;
+        // the frame's points/residuals leave the window first (FullSystem::marginalizeFrame drops them)
+        auto victim = frameHessians[1];
+        for (auto &fh : frameHessians) for (auto &ph : fh->pointHessians) {
+            std::vector<shared_ptr<PointFrameResidual>> keep;
+            for (auto &r : ph->residuals) if (r->target.lock() != victim && r->host.lock() != victim) keep.push_back(r);
+            ph->residuals = keep;
+        }
+        victim->pointHessians.clear();
+        bool ok = ef->marginalizeFrame(victim);
+        printf(", \"marg_ok\": %s, \"marg_n\": %d, \"marg_nframes\": %d, \"HM\": [", ok ? "true" : "false", ef->HM.r, ef->nFrames);
+        for (size_t i = 0; i < ef->HM.d.size(); i++) printf("%s%.15g", i ? ", " : "", ef->HM.d[i]);
+        printf("], \"bM\": [");
+        for (size_t i = 0; i < ef->bM.d.size(); i++) printf("%s%.15g", i ? ", " : "", ef->bM.d[i]);
+        printf("]}\n");
+        return 0;
+    }
     int nIn = 0, nOob = 0, nAct = 0;
     for (auto &r : activeResiduals) { nIn += r->state_state == ResState::IN; nOob += r->state_state == ResState::OOB; nAct += r->isActive(); }
     printf(", \"nIn\": %d, \"nOOB\": %d, \"nActive\": %d, \"idepth\": [", nIn, nOob, nAct);

@@ -68,3 +68,25 @@ def test_fused_entry_point(win):
         o.gn_iteration(it)
     assert abs(out["energy"][0] - o.L.oracle_ba_last_energy(o.o)) <= 2e-3 * out["energy"][0]
     assert rel_err(out["idepth"], o.points()["idepth"]) < 2e-3
+
+
+def test_marginalize_frame_through_shim(win):
+    """EnergyFunctional::marginalizeFrame with the reference's signature (shim) on a synthetic prior against the oracle."""
+    out = _run(win, "margframe")
+    assert out["marg_ok"] is True and out["marg_nframes"] == win.nF - 1
+    n = 8 * win.nF + 4
+    i = np.arange(n, dtype=np.float64)
+    v = 20.0 * np.sin(i + 1.0)
+    HM = np.outer(v, v) + np.diag(50.0 + 3.0 * i)
+    bM = 10.0 * np.cos(i)
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    o.optimize_begin()
+    for it in range(3):
+        o.gn_iteration(it)              # same states as the shim after its fused 3 iterations
+    o.set_marg_prior(HM, bM)
+    Ho, bo = o.marginalize_frame(1)
+    nd = out["marg_n"]
+    assert nd == n - 8
+    Hg = np.array(out["HM"]).reshape(nd, nd, order="F")
+    assert rel_err(Hg, Ho) < 1e-9            # HM does not depend on the states
+    assert rel_err(np.array(out["bM"]), bo) < 2e-3   # bM carries prior * delta_prior of the 3-iteration states (same bar as idepth above)
