@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("LDSO_B200_LIB", os.path.join(_HERE, "lib", "libldso_b200.so"))   # env override: development A/B builds
+LIB_PATH = os.environ.get("LDSO_B200_LIB") or os.path.join(_HERE, "lib", "libldso_b200.so")   # env override: development A/B builds
 
 MAX_FRAMES = 8
 RES_IN, RES_OOB, RES_OUTLIER = 0, 1, 2

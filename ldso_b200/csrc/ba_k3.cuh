@@ -19,12 +19,6 @@
 #define K3F_STEP 2
 #define K3F_BACKUP 4
 #define K3_THREADS 512
-#ifndef K3V_SHFL_EARLY
-#define K3V_SHFL_EARLY 1
-#endif
-#ifndef K3V_PANEL_HOIST
-#define K3V_PANEL_HOIST 1
-#endif
 #define K3_NP ((MAXN + 7) & ~7)     // system dimension padded to whole 8x8 blocks (identity padding)
 #define K3_LD (K3_NP + 1)
 #define K3_NB 8
@@ -73,7 +67,7 @@ __device__ void stage_out(const K3Frames *S, WinState *ws) {
 // FrameHessian::setState (FrameHessian.h:78-91), FrameFramePrecalc::Set for all pairs (FrameFramePrecalc.cc:6-35),
 // EnergyFunctional::setDeltaF frame part (EnergyFunctional.cc:403-429). Frame records live in shared memory (S);
 // the pair records are written to global. Called by all threads of a CTA with >= 128 threads.
-__device__ void frames_refresh(K3Frames *S, WinState *ws, bool full) {
+__device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float *adHF, const float *adTF) {
     const int nF = ws->nF, tid = threadIdx.x;
     if (tid < nF) {
         FrameDev &f = S->fr[tid];
@@ -165,7 +159,7 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full) {
     for (int o = tid; o < nF * nF * 8; o += blockDim.x) {
         const int q = o >> 3, j = o & 7, h = q % nF, t = q / nF;
         const FrameDev &fh = S->fr[h], &ft = S->fr[t];
-        const float *AH = ws->adHostF[q], *AT = ws->adTargetF[q];
+        const float *AH = adHF + q * 64, *AT = adTF + q * 64;
         float s1 = 0.f, s2 = 0.f;
         for (int i = 0; i < 8; i++) s1 += (float) (fh.state[i] - fh.state_zero[i]) * AH[i * 8 + j];
         for (int i = 0; i < 8; i++) s2 += (float) (ft.state[i] - ft.state_zero[i]) * AT[i * 8 + j];
@@ -177,7 +171,7 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full) {
 __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
     __shared__ K3Frames S;
     stage_in(&S, ws);
-    frames_refresh(&S, ws, true);
+    frames_refresh(&S, ws, true, &ws->adHostF[0][0], &ws->adTargetF[0][0]);
     stage_out(&S, ws);
 }
 
@@ -185,6 +179,12 @@ __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
 // padded to whole blocks, so there is no partial-block predicate anywhere on this serial path.
 // Executed by ONE WARP: lane j < 8 keeps row j of the block in registers; a step is one broadcast of the pivot,
 // one reciprocal, and 7-k shuffles of the unscaled column. (L = W * (1/d): <= 1 ulp from Eigen's W / d.)
+__device__ __forceinline__ double shfl_f64(double v, int src) {      // low word first: lands in an aligned register pair
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
 __device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int lane) {
     const unsigned FULL = 0xffffffffu;
     double a[K3_NB];
@@ -192,39 +192,22 @@ __device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, in
 #pragma unroll
     for (int c = 0; c < K3_NB; c++) a[c] = A[(k0 + row) * K3_LD + k0 + c];
 #pragma unroll
-#if K3V_SHFL_EARLY
     for (int k = 0; k < K3_NB; k++) {
         const double w = a[k];                      // unscaled column entry of this lane's row (rows >= k)
         // all exchanges of this step are issued before the reciprocal: only rcp -> mul -> fma stays on the chain
-        const double dk = __shfl_sync(FULL, w, k);
+        const double dk = shfl_f64(w, k);
         double wj[K3_NB];
 #pragma unroll
-        for (int j = k + 1; j < K3_NB; j++) wj[j] = __shfl_sync(FULL, w, j);
+        for (int j = k + 1; j < K3_NB; j++) wj[j] = shfl_f64(w, j);
         const bool valid = fabs(dk) > 0.0;
         const double inv = valid ? __drcp_rn(dk) : 1.0;
         const double l = w * inv;
+        // unconditional: for row < j this touches only the (never read, never stored) upper part of the lane's row
 #pragma unroll
-        for (int j = k + 1; j < K3_NB; j++)
-            if (row >= j) a[j] -= l * wj[j];
+        for (int j = k + 1; j < K3_NB; j++) a[j] -= l * wj[j];
         if (row > k) a[k] = l;
         if (lane == 0) vinv[k0 + k] = inv;
     }
-#else
-    for (int k = 0; k < K3_NB; k++) {
-        const double dk = __shfl_sync(FULL, a[k], k);
-        const bool valid = fabs(dk) > 0.0;
-        const double inv = valid ? __drcp_rn(dk) : 1.0;
-        if (lane == 0) vinv[k0 + k] = inv;
-        const double w = a[k];
-        const double l = w * inv;
-#pragma unroll
-        for (int j = k + 1; j < K3_NB; j++) {
-            const double wj = __shfl_sync(FULL, w, j);
-            if (row >= j) a[j] -= l * wj;
-        }
-        if (row > k) a[k] = l;
-    }
-#endif
     if (lane < K3_NB) {
 #pragma unroll
         for (int c = 0; c < K3_NB; c++) if (c <= lane) A[(k0 + lane) * K3_LD + k0 + c] = a[c];
@@ -241,7 +224,7 @@ __device__ __forceinline__ void trsv_lower_warp(const double *A, double *v, int 
     double z = (c < bs) ? v[k0 + c] : 0.0;
 #pragma unroll
     for (int j = 0; j < K3_NB - 1; j++) {
-        const double zj = __shfl_sync(FULL, z, j);
+        const double zj = shfl_f64(z, j);
         z -= Lr[j] * zj;          // Lr[j] == 0 for j >= c
     }
     if (lane < bs) v[k0 + lane] = z;
@@ -256,7 +239,7 @@ __device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, in
     double x = (c < bs) ? v[k0 + c] : 0.0;
 #pragma unroll
     for (int j = K3_NB - 1; j >= 1; j--) {
-        const double xj = __shfl_sync(FULL, x, j);
+        const double xj = shfl_f64(x, j);
         x -= Lc[j] * xj;          // Lc[j] == 0 for j <= c
     }
     if (lane < bs) v[k0 + lane] = x;
@@ -276,12 +259,15 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
     extern __shared__ double sm3[];
-    double *A0 = sm3;                       // [n][K3_LD] row-major assembled matrix
-    double *A = A0 + MAXN * K3_LD;          // permuted copy (+ rhs as row n), factorised in place
+    double *A = sm3;                        // [(K3_NP + 1)][K3_LD] permuted, scaled, padded system (+ rhs as row npad), factorised in place
     double *Wp = A + (K3_NP + 1) * K3_LD;    // [K3_NB][K3_WPLD] panel W = L*D of the current block step
     double *vinv = Wp + K3_NB * K3_WPLD;    // [K3_NP] reciprocal pivots
     double *vb = vinv + K3_NP;               // rhs / solution
@@ -291,6 +277,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     int *perm = (int *) (vx + MAXN);        // [MAXN]
     K3Frames *S = (K3Frames *) (perm + MAXN + 2);
     double *sPns = (double *) (S + 1);      // [n*n] null-space projector
+    float *sAdH = (float *) (sPns + MAXN * MAXN);   // [MAXPAIR][64] adHostF, adTargetF (index h + nF*t): staged once per launch
+    float *sAdT = sAdH + MAXPAIR * 64;
     const int nF = ws->nF, n = ws->n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int iteration = *iteration_dev;
 
@@ -298,21 +286,61 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     // L2 round trip overlaps the assembly and the factorisation)
     constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
     double b_pre = 0.0, dg_pre = 0.0, hs_pre[K3_HSCOPY];
+    const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole 8x8 blocks; the rhs is row npad
+    // the f32 adjoints feed xAd (solve) and adHTdeltaF (step) at the very end: asynchronous copies, 16 bytes each
+    for (int e = tid; e < nF * nF * 16; e += K3_THREADS) {
+        cp_async16(sAdH + 4 * e, &ws->adHostF[0][0] + 4 * e);
+        cp_async16(sAdT + 4 * e, &ws->adTargetF[0][0] + 4 * e);
+    }
+    float nid_pre = 0.f, num_pre = 1.f, tho_pre = 0.f;      // doStepFromBackup's canbreak inputs (thread 0 only)
+    if (tid == 0) { nid_pre = ws->sumNID; num_pre = ws->numID; tho_pre = ws->S.thOptIterations; }
     if (flags & K3F_SOLVE) {
-        // asynchronous global->shared copies (LDGSTS): the assembled system the stitch kernel left behind (HFinal_top,
-        // column-major -> row-major) and, from iteration 2 on, the null-space projector. They land while the frame state
-        // is staged; nothing below waits for them until cp_async_wait_all().
-        for (int e = tid; e < n * n; e += K3_THREADS) {
-            const int c = e / n, r = e - c * n;
-            cp_async8(A0 + r * K3_LD + c, sb.A0g + e);
-        }
-        if (iteration >= 2)
-            for (int e = tid; e < n * n; e += K3_THREADS) cp_async8(sPns + e, sb.Pns + e);
+        // What the stitch kernel left behind (k2b_stitch, do_assemble; EnergyFunctional.cc:257,283-291): HFinal_top and its
+        // diagonal, HFinal_top - H_sc (lastHS once solved), bFinal_top (lastbS). The diagonal comes first: it fixes SVecI
+        // and the pivot order, and with those the matrix is gathered straight into its permuted place by asynchronous
+        // global->shared copies (LDGSTS) that land while the frame state is staged.
         if (tid < n) { dg_pre = sb.dg[tid]; b_pre = sb.bFg[tid]; }
 #pragma unroll
         for (int k = 0; k < K3_HSCOPY; k++) {
             const int e = tid + k * K3_THREADS;
             hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
+        }
+        if (iteration >= 2)
+            for (int e = tid; e < n * n; e += K3_THREADS) cp_async8(sPns + e, sb.Pns + e);
+        // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
+        if (tid < n) {
+            const double sv = 1.0 / sqrt(dg_pre + 10.0);
+            vS[tid] = sv;
+            vd[tid] = fabs(dg_pre * sv * sv);          // |diagonal| of the scaled matrix
+            vb[tid] = b_pre;
+        }
+        __syncthreads();
+        {   // rank sort: 4 threads per row fold a quarter of the comparisons each
+            const int i = tid >> 2, q = tid & 3;
+            int rank = 0;
+            if (i < n) {
+                const double di = vd[i];
+                for (int j = q; j < n; j += 4) {
+                    const double dj = vd[j];
+                    rank += (dj > di) || (dj == di && j < i);
+                }
+            }
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            if (i < n && q == 0) perm[rank] = i;
+        }
+        __syncthreads();
+        // lower triangle (+ the whole diagonal blocks) of P A0 P^T; padding = identity
+        for (int r = warp; r < npad; r += K3_THREADS / 32) {
+            const int pr = (r < n) ? perm[r] : 0;
+#pragma unroll
+            for (int cc = 0; cc < (K3_NP + 31) / 32; cc++) {
+                const int c = lane + 32 * cc;
+                if (c < npad && (c <= r || (c >> 3) == (r >> 3))) {
+                    if (r < n && c < n) cp_async8(A + r * K3_LD + c, sb.A0g + (size_t) perm[c] * n + pr);
+                    else A[r * K3_LD + c] = (r == c) ? 1.0 : 0.0;
+                }
+            }
         }
     }
     int dbgi = 0;
@@ -333,53 +361,22 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         __syncthreads();
     }
     if (flags & K3F_SOLVE) {
-        // The stitch kernel (k2b_stitch, do_assemble) already produced HFinal_top, bFinal_top (= lastbS), lastHS, SVecI and
-        // the pivot order (EnergyFunctional.cc:257,283-291,326-327); the copies were issued at kernel entry.
         // The system being solved now becomes the public lastHS / lastbS (EnergyFunctional.cc:285,:335).
 #pragma unroll
         for (int k = 0; k < K3_HSCOPY; k++) {
             const int e = tid + k * K3_THREADS;
             if (e < n * n) sb.lastHS[e] = hs_pre[k];
         }
-        // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
-        if (tid < n) {
-            const double sv = 1.0 / sqrt(dg_pre + 10.0);
-            vS[tid] = sv;
-            vd[tid] = fabs(dg_pre * sv * sv);          // |diagonal| of the scaled matrix
-            vb[tid] = b_pre;
-            sb.lastbS[tid] = b_pre;
-        }
-        __syncthreads();
-        {   // rank sort: 4 threads per row fold a quarter of the comparisons each
-            const int i = tid >> 2, q = tid & 3;
-            int rank = 0;
-            if (i < n) {
-                const double di = vd[i];
-                for (int j = q; j < n; j += 4) {
-                    const double dj = vd[j];
-                    rank += (dj > di) || (dj == di && j < i);
-                }
-            }
-            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-            if (i < n && q == 0) perm[rank] = i;
-        }
+        if (tid < n) sb.lastbS[tid] = b_pre;
+        K3_STAMP();   // 2
+        // A = P (S A0 S) P^T: every thread scales the elements it copied itself (visible to it after the wait); b' = P S b
         cp_async_wait_all();
-        __syncthreads();
-        K3_STAMP();   // 2: assembled system loaded
-        // A = P (S A0 S) P^T, b' = P S b
-        const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole blocks; the rhs is row npad
-        for (int r = warp; r < npad; r += K3_THREADS / 32) {
-            const int pr = (r < n) ? perm[r] : 0;
-            const double sr = vS[pr];
+        for (int r = warp; r < n; r += K3_THREADS / 32) {
+            const double sr = vS[perm[r]];
 #pragma unroll
             for (int cc = 0; cc < (K3_NP + 31) / 32; cc++) {
                 const int c = lane + 32 * cc;
-                if (c < npad) {
-                    double v = (r == c) ? 1.0 : 0.0;
-                    if (r < n && c < n) { const int pc = perm[c]; v = A0[pr * K3_LD + pc] * sr * vS[pc]; }
-                    A[r * K3_LD + c] = v;
-                }
+                if (c < n && (c <= r || (c >> 3) == (r >> 3))) A[r * K3_LD + c] = A[r * K3_LD + c] * sr * vS[perm[c]];
             }
         }
         if (tid < npad) A[npad * K3_LD + tid] = (tid < n) ? vb[perm[tid]] * vS[perm[tid]] : 0.0;
@@ -400,7 +397,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             if (tid == 0) ws->dbg[33 + (k0 >> 3)] = tq;
             if (k0 >= 0 && tid < npad + 1 - m0) {      // panel row i (incl. the rhs row npad): w = L*D (unscaled), l = L
                 const int i = m0 + tid;
-#if K3V_PANEL_HOIST
                 // all operands first (the 28 entries of L11 are warp-uniform broadcasts), then the 8-step substitution
                 double a[K3_NB], iv[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2], w[K3_NB];
 #pragma unroll
@@ -423,23 +419,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
                     A[i * K3_LD + k0 + c] = w[c] * iv[c];
                     Wp[c * K3_WPLD + i] = w[c];
                 }
-#else
-                double w[K3_NB];
-#pragma unroll
-                for (int c = 0; c < K3_NB; c++) {
-                    double s0 = A[i * K3_LD + k0 + c], s1 = 0.0;
-#pragma unroll
-                    for (int j = 0; j < c; j += 2) s0 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
-#pragma unroll
-                    for (int j = 1; j < c; j += 2) s1 -= w[j] * A[(k0 + c) * K3_LD + k0 + j];
-                    w[c] = s0 + s1;
-                }
-#pragma unroll
-                for (int c = 0; c < K3_NB; c++) {
-                    A[i * K3_LD + k0 + c] = w[c] * vinv[k0 + c];
-                    Wp[c * K3_WPLD + i] = w[c];
-                }
-#endif
             }
             { const long long t1 = clk_fenced(); tp += t1 - tq; tq = t1; }
             __syncthreads();
@@ -542,7 +521,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         }
         for (int o = tid; o < nF * nF * 8; o += K3_THREADS) {
             const int q = o >> 3, j = o & 7, h = q / nF, t = q % nF;     // xAd[nFrames*h + t]
-            const float *AH = ws->adHostF[h + nF * t], *AT = ws->adTargetF[h + nF * t];
+            const float *AH = sAdH + (h + nF * t) * 64, *AT = sAdT + (h + nF * t) * 64;
             float s1 = 0.f, s2 = 0.f;
             for (int i = 0; i < 8; i++) s1 += (float) vx[CPARS + 8 * h + i] * AH[i * 8 + j];
             for (int i = 0; i < 8; i++) s2 += (float) vx[CPARS + 8 * t + i] * AT[i * 8 + j];
@@ -552,6 +531,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     }
     K3_STAMP();   // 7: xAd done
     if (flags & K3F_STEP) {
+        if (!(flags & K3F_SOLVE)) { cp_async_wait_all(); __syncthreads(); }     // the staged adjoints (the solve path waited already)
         // doStepFromBackup(1,1,1,1,1), frame/calib part (FullSystem.cc:1588-1597,1617-1627)
         if (tid == 0) {
             double nv[4];
@@ -566,8 +546,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
                 sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
             }
             sumA /= nF; sumB /= nF; sumR /= nF; sumT /= nF;
-            const float sumNID = ws->sumNID / ws->numID;
-            const float thO = ws->S.thOptIterations;
+            const float sumNID = nid_pre / num_pre;
+            const float thO = tho_pre;
             ws->canbreak = (sqrtf(sumA) < 0.0005 * thO && sqrtf(sumB) < 0.00005 * thO && sqrtf(sumR) < 0.00005 * thO &&
                             sqrtf(sumT) * sumNID < 0.00005 * thO) ? 1 : 0;
         }
@@ -576,7 +556,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             for (int i = 0; i < 10; i++) f.state[i] = f.state_backup[i] + f.step[i];
         }
         __syncthreads();
-        frames_refresh(S, ws, false);
+        frames_refresh(S, ws, false, sAdH, sAdT);
     }
     K3_STAMP();   // 8: frames refreshed
     stage_out(S, ws);
@@ -588,4 +568,4 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     }
     if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
 }
-#define K3_SMEM_BYTES (((MAXN + K3_NP + 1) * K3_LD + K3_NB * K3_WPLD + 4 * MAXN + K3_NP) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 64)
+#define K3_SMEM_BYTES (((K3_NP + 1) * K3_LD + K3_NB * K3_WPLD + 4 * MAXN + K3_NP) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 2 * MAXPAIR * 64 * sizeof(float) + 64)
