@@ -75,6 +75,8 @@ struct ldso_b200_ctx {
     cudaGraphExec_t gn_graph = nullptr;
     bool gn_graph_valid = false;
     bool use_graph = true;
+    bool use_pdl = true;             // programmatic dependent launch inside the GN iteration (env LDSO_B200_NO_PDL disables)
+    bool pdl_now = false;            // set while launch_gn_body issues its four kernels
     size_t k1_smem = 0;
     bool multi = false;
 
@@ -205,6 +207,7 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     if (!ok) { fprintf(stderr, "ldso_b200: pinned allocation failed\n"); delete c; return nullptr; }
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
     c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
+    c->use_pdl = getenv("LDSO_B200_NO_PDL") == nullptr;
     cudaEventCreateWithFlags(&c->frames_copied, cudaEventDisableTiming);
     cudaFuncSetAttribute(k1_linearize_accumulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k1_smem_bytes(64));
     cudaFuncSetAttribute(k3_solve_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) K3_SMEM_BYTES);
@@ -720,10 +723,26 @@ extern "C" int ldso_b200_get_marg_prior(ldso_b200_ctx *c, double *HM, double *bM
 }
 
 // ---------------------------------------------------------------------------------------------- launches
+// One launch path for the loop kernels: inside launch_gn_body the kernel is allowed to start (and run its constant-data
+// prologue up to pdl_wait()) while its predecessor on the stream is still executing.
+template<typename... KArgs, typename... Args>
+static cudaError_t launch_loop_kernel(ldso_b200_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    memset(at, 0, sizeof(at));
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (c->pdl_now && c->use_pdl && !c->ktime) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int launch_k1(ldso_b200_ctx *c, int flags, const uint8_t *sel = nullptr) {
     if (c->d.nItems == 0) return LDSO_B200_OK;
     c->kt_begin("k1");
-    k1_linearize_accumulate<<<c->d.nItems, K1_THREADS, c->k1_smem, c->stream>>>(c->d, c->ws_dev, flags, sel);
+    launch_loop_kernel(c, k1_linearize_accumulate, dim3(c->d.nItems), dim3(K1_THREADS), c->k1_smem, c->d, (const WinState *) c->ws_dev, flags, sel);
     c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
@@ -731,7 +750,7 @@ static int launch_k1(ldso_b200_ctx *c, int flags, const uint8_t *sel = nullptr) 
 static int launch_k2a(ldso_b200_ctx *c, int full) {
     const int nb = (MAXF * PART_USED + 63) / 64 + 1;
     c->kt_begin("k2a");
-    k2a_reduce<<<nb, K2A_THREADS, 0, c->stream>>>(c->d, c->ws_dev, full, c->multi ? 1 : 0);
+    launch_loop_kernel(c, k2a_reduce, dim3(nb), dim3(K2A_THREADS), 0, c->d, c->ws_dev, full, c->multi ? 1 : 0);
     c->kt_end();
     LAUNCH_CHECK(c);
     if (full) { c->restitch_ok = true; c->solve_ready = false; }
@@ -742,7 +761,7 @@ static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select, int do_ass
         return c->fail(LDSO_B200_ERR_STATE, "the marginalisation prior has a different dimension than the frames (marginalize_frame): call set_frames with the remaining frames first");
     const int nb = c->nF * c->nF + c->nF + 2;
     c->kt_begin("k2b");
-    k2b_stitch<<<nb, K2B_THREADS, K2B_SMEM_BYTES, c->stream>>>(c->d, c->ws_dev, c->sb, do_stitch, do_select, do_stitch && do_assemble);
+    launch_loop_kernel(c, k2b_stitch, dim3(nb), dim3(K2B_THREADS), K2B_SMEM_BYTES, c->d, c->ws_dev, c->sb, do_stitch, do_select, (int) (do_stitch && do_assemble));
     c->kt_end();
     LAUNCH_CHECK(c);
     if (do_stitch) c->solve_ready = do_assemble != 0;
@@ -756,7 +775,7 @@ static int ensure_solve_ready(ldso_b200_ctx *c) {
 }
 static int launch_k3(ldso_b200_ctx *c, int flags) {
     c->kt_begin("k3");
-    k3_solve_step<<<1, K3_THREADS, K3_SMEM_BYTES, c->stream>>>(c->ws_dev, c->sb, flags, c->iteration_dev);
+    launch_loop_kernel(c, k3_solve_step, dim3(1), dim3(K3_THREADS), K3_SMEM_BYTES, c->ws_dev, c->sb, flags, c->iteration_dev);
     c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
@@ -953,6 +972,7 @@ extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
 }
 
 static int launch_gn_body(ldso_b200_ctx *c) {
+    struct Scope { ldso_b200_ctx *c; Scope(ldso_b200_ctx *c_) : c(c_) { c->pdl_now = true; } ~Scope() { c->pdl_now = false; } } scope(c);
     RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
     RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
     RET_IF(launch_k2a(c, 1));
@@ -982,11 +1002,20 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
             int rc = launch_gn_body(c);
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             c->launches = l0;
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            if (e != cudaSuccess) return c->fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-            e = cudaGraphInstantiate(&c->gn_graph, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return c->fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+            if (rc == 0 && e == cudaSuccess) {
+                e = cudaGraphInstantiate(&c->gn_graph, g, 0);
+                if (e != cudaSuccess) c->gn_graph = nullptr;
+            }
+            if (g) cudaGraphDestroy(g);
+            if (rc || e != cudaSuccess) {
+                cudaGetLastError();
+                if (c->use_pdl) {        // programmatic edges not capturable here: same graph with full dependencies
+                    c->use_pdl = false;
+                    return ldso_b200_gn_iterations(c, first_iteration, n_iterations);
+                }
+                if (rc) return rc;
+                return c->fail_cuda(e, "CUDA graph capture of the GN iteration", __FILE__, __LINE__);
+            }
             c->gn_graph_valid = true;
         }
         for (int i = 0; i < n_iterations; i++) {

@@ -91,7 +91,53 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         d.dbg[32 + 3 * blockIdx.x] = (long long) gt;
         d.dbg[32 + 3 * blockIdx.x + 2] = smid;
     }
-    // ---------------- phase 0: stage per-host constants, clear records
+    // ---------------- phase 0a (before pdl_wait: iteration-constant data only): clear records, request the point scalars
+    // and the first round of residual records
+    pdl_launch_dependents();
+    for (int i = tid; i < npts * MAXF * 9; i += K1_THREADS) {     // only the active flag and JpJdF must start at zero
+        const int q = i / 9, k = i - q * 9;
+        recs[q * REC + REC_ACTIVE + k] = 0.f;
+    }
+    const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
+    const int nres = rend - rbeg;
+    float *s_rdot = s_ptout;        // [nres <= pts_per_item*MAXF] reuse: s_ptout is not live before phase P
+    // software prefetch: everything phases R2 and A(round 0) read from global is requested here, before the first
+    // barrier, so that its L2/HBM round trip overlaps the staging above instead of serialising behind each barrier
+    float pf_idepth = 0.f, pf_idz = 0.f, pf_bd = 0.f, pf_step = 0.f, pf_hdi = 0.f, pf_u = 0.f, pf_v = 0.f, pf_prior = 0.f;
+    float4 pf_hcd = make_float4(0.f, 0.f, 0.f, 0.f);
+    int pf_r0 = 0, pf_r1 = 0;
+    if (tid < npts) {        // window inputs that no kernel writes
+        const int p = p0 + tid;
+        pf_u = d.pt_u[p]; pf_v = d.pt_v[p]; pf_prior = d.pt_priorF[p];
+        if (flags & K1F_APPLY_STEP) { pf_r0 = d.pt_res_begin[p] - rbeg; pf_r1 = d.pt_res_begin[p + 1] - rbeg; }
+    }
+    const int grp = tid >> 3, idx = tid & 7;
+    int nx_p, nx_t; uint8_t nx_state, nx_lin; float nx_energy; int nx_slot;
+    // topology (constant) and state (written by the previous iteration's K1) of the residual a lane group handles next
+#define K1_PREFETCH_RES_TOPO(base_)                                                                     \
+    do {                                                                                                \
+        const int ri_ = (base_) + grp;                                                                  \
+        const int r_ = rbeg + ((ri_ < nres) ? ri_ : 0);                                                 \
+        nx_p = d.res_point[r_]; nx_t = d.res_target[r_];                                                \
+        nx_slot = (d.res_newest_slot != nullptr) ? d.res_newest_slot[r_] : -1;                          \
+    } while (0)
+#define K1_PREFETCH_RES_STATE(base_)                                                                    \
+    do {                                                                                                \
+        const int ri_ = (base_) + grp;                                                                  \
+        const int r_ = rbeg + ((ri_ < nres) ? ri_ : 0);                                                 \
+        nx_state = d.res_state[r_]; nx_energy = d.res_energy[r_]; nx_lin = d.res_lin[r_];               \
+    } while (0)
+#define K1_PREFETCH_RES(base_) do { K1_PREFETCH_RES_TOPO(base_); K1_PREFETCH_RES_STATE(base_); } while (0)
+    nx_p = p0; nx_t = 0; nx_state = 0; nx_lin = 0; nx_energy = 0.f; nx_slot = -1;
+    if (nres > 0) K1_PREFETCH_RES_TOPO(0);
+    // ---------------- phase 0b: everything the solver kernel produced (pair records, xAd, calibration, thresholds)
+    pdl_wait();
+    if (tid < npts) {        // point state written by the previous iteration's K1
+        const int p = p0 + tid;
+        pf_idepth = d.pt_idepth[p]; pf_idz = d.pt_idepth_zero[p];
+        if (flags & K1F_APPLY_STEP) { pf_bd = d.pt_bdSumF[p]; pf_step = d.pt_step[p]; pf_hdi = d.pt_HdiF[p]; pf_hcd = *(const float4 *) (d.pt_Hcd + 4 * p); }
+    }
+    if (nres > 0) K1_PREFETCH_RES_STATE(0);
     for (int i = tid; i < MAXF * 32; i += K1_THREADS) {
         int t = i >> 5, k = i & 31;
         s_pair[i] = (t < nF) ? ((const float *) &ws->pair[host + nF * t])[k] : 0.f;
@@ -109,38 +155,6 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         s_dHT[tid] = (t < nF) ? ws->adHTdeltaF[host + nF * t][k] : 0.f;
     }
     if (tid < 4) { s_cstep[tid] = ws->cstep[tid]; s_cD[tid] = ws->calib.cDeltaF[tid]; }
-    for (int i = tid; i < npts * MAXF * 9; i += K1_THREADS) {     // only the active flag and JpJdF must start at zero
-        const int q = i / 9, k = i - q * 9;
-        recs[q * REC + REC_ACTIVE + k] = 0.f;
-    }
-    const int rbeg = d.pt_res_begin[p0], rend = d.pt_res_begin[p1];
-    const int nres = rend - rbeg;
-    float *s_rdot = s_ptout;        // [nres <= pts_per_item*MAXF] reuse: s_ptout is not live before phase P
-    // software prefetch: everything phases R2 and A(round 0) read from global is requested here, before the first
-    // barrier, so that its L2/HBM round trip overlaps the staging above instead of serialising behind each barrier
-    float pf_idepth = 0.f, pf_idz = 0.f, pf_bd = 0.f, pf_step = 0.f, pf_hdi = 0.f, pf_u = 0.f, pf_v = 0.f, pf_prior = 0.f;
-    float4 pf_hcd = make_float4(0.f, 0.f, 0.f, 0.f);
-    int pf_r0 = 0, pf_r1 = 0;
-    if (tid < npts) {
-        const int p = p0 + tid;
-        pf_idepth = d.pt_idepth[p]; pf_idz = d.pt_idepth_zero[p]; pf_u = d.pt_u[p]; pf_v = d.pt_v[p]; pf_prior = d.pt_priorF[p];
-        if (flags & K1F_APPLY_STEP) {
-            pf_bd = d.pt_bdSumF[p]; pf_step = d.pt_step[p]; pf_hdi = d.pt_HdiF[p]; pf_hcd = *(const float4 *) (d.pt_Hcd + 4 * p);
-            pf_r0 = d.pt_res_begin[p] - rbeg; pf_r1 = d.pt_res_begin[p + 1] - rbeg;
-        }
-    }
-    const int grp = tid >> 3, idx = tid & 7;
-    int nx_p, nx_t; uint8_t nx_state, nx_lin; float nx_energy; int nx_slot;
-#define K1_PREFETCH_RES(base_)                                                                          \
-    do {                                                                                                \
-        const int ri_ = (base_) + grp;                                                                  \
-        const int r_ = rbeg + ((ri_ < nres) ? ri_ : 0);                                                 \
-        nx_p = d.res_point[r_]; nx_t = d.res_target[r_]; nx_state = d.res_state[r_];                    \
-        nx_energy = d.res_energy[r_]; nx_lin = d.res_lin[r_];                                           \
-        nx_slot = (d.res_newest_slot != nullptr) ? d.res_newest_slot[r_] : -1;                          \
-    } while (0)
-    nx_p = p0; nx_t = 0; nx_state = 0; nx_lin = 0; nx_energy = 0.f; nx_slot = -1;
-    if (nres > 0) K1_PREFETCH_RES(0);
     if (flags & K1F_APPLY_STEP) {   // R1 (no dependence on the staged constants: overlaps their load latency)
         for (int ri = tid; ri < nres; ri += K1_THREADS) {
             const int r = rbeg + ri;

@@ -19,6 +19,8 @@ __device__ __forceinline__ void dbg_span(long long *slot_min_max, bool end) {
 #define K2A_THREADS 512
 #define K2A_SLICES (K2A_THREADS / 64)     // 8 threads share one output element, each folds every 8th work item
 __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState *ws, int full, int multi) {
+    pdl_launch_dependents();
+    pdl_wait();                      // everything below reads what K1 just wrote
     if (threadIdx.x == 0) dbg_span(&ws->dbg[16], false);
     const int nF = ws->nF;
     if (blockIdx.x == gridDim.x - 1) {
@@ -121,9 +123,9 @@ __device__ __forceinline__ double k2b_delta(const WinState *ws, int c) {      //
     return (c < CPARS) ? (double) ws->calib.cDeltaF[c] : ws->fr[(c - CPARS) >> 3].delta[(c - CPARS) & 7];
 }
 __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState *ws, SolveBufs sb, int do_stitch, int do_select, int do_assemble) {
+    pdl_launch_dependents();
     const int nF = ws->nF, n = ws->n;
     const int tid = threadIdx.x;
-    if (tid == 0) dbg_span(&ws->dbg[18], false);
     const double *red = d.red;
     const int nBlocks = nF * nF;
     __shared__ unsigned hist[256];
@@ -157,12 +159,17 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         if (do_assemble && tid < 64) hm_pre = sb.HM[(size_t) (CPARS + 8 * b + (tid & 7)) * n + CPARS + 8 * a + (tid >> 3)];
         if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
         // -------- stage
-        for (int o = tid; o < nF * 64; o += K2B_THREADS) {
+        for (int o = tid; o < nF * 64; o += K2B_THREADS) {      // adjoints: constant for the window, staged before pdl_wait
             const int q = o >> 6, e = o & 63, m = K2B_M(q, e >> 3, e & 7);
             sAHa[m] = ws->adHost[a + nF * q][e];
             sATa[m] = ws->adTarget[q + nF * a][e];
             sATb[m] = ws->adTarget[q + nF * b][e];
             sAHb[m] = ws->adHost[b + nF * q][e];
+        }
+        pdl_wait();
+        if (tid == 0) dbg_span(&ws->dbg[18], false);
+        for (int o = tid; o < nF * 64; o += K2B_THREADS) {
+            const int q = o >> 6, e = o & 63, m = K2B_M(q, e >> 3, e & 7);
             sD1[m] = red[q * PART_USED + PART_D + (a * MAXF + b) * 64 + e];
             sD2[m] = red[b * PART_USED + PART_D + (a * MAXF + q) * 64 + e];
             sD3[m] = red[a * PART_USED + PART_D + (q * MAXF + b) * 64 + e];
@@ -328,6 +335,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         // every lane issues its 32 independent loads at once, then a 3-step shuffle fold.
         const int a = blockIdx.x - nBlocks;
         __shared__ double s_cal[80];
+        pdl_wait();
+        if (tid == 0) dbg_span(&ws->dbg[18], false);
         for (int o8 = tid; o8 < 80 * 8; o8 += K2B_THREADS) {
             const int o = o8 >> 3, t = o8 & 7;
             double s = 0.0;
@@ -395,6 +404,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     if ((int) blockIdx.x == nBlocks + nF) {
         if (!do_stitch) return;
         // ---- calibration corner: 20 outputs x 8 lanes (lane <-> host frame)
+        pdl_wait();
+        if (tid == 0) dbg_span(&ws->dbg[18], false);
         if (tid < 20 * 8) {
             const int o = tid >> 3, h = tid & 7;
             double sA = 0.0, sS = 0.0;
@@ -441,6 +452,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
     }
     // ---- last CTA: exact k-th order statistic of the newest frame's residual energies (radix select)
+    pdl_wait();
+    if (tid == 0) dbg_span(&ws->dbg[18], false);
     if (tid == 0) {   // publish the (all-reduced) scalar statistics
         ws->energy = red[RED_STATS + 0];
         ws->resInA = (int) (red[RED_STATS + 1] + 0.5);

@@ -280,18 +280,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     float *sAdH = (float *) (sPns + MAXN * MAXN);   // [MAXPAIR][64] adHostF, adTargetF (index h + nF*t): staged once per launch
     float *sAdT = sAdH + MAXPAIR * 64;
     const int nF = ws->nF, n = ws->n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int iteration = *iteration_dev;
-
-    // NNpiTS is needed at the very end: start copying it into shared memory now (fire-and-forget stores, the
-    // L2 round trip overlaps the assembly and the factorisation)
+    pdl_launch_dependents();
     constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
     double b_pre = 0.0, dg_pre = 0.0, hs_pre[K3_HSCOPY];
     const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole 8x8 blocks; the rhs is row npad
-    // the f32 adjoints feed xAd (solve) and adHTdeltaF (step) at the very end: asynchronous copies, 16 bytes each
+    // the f32 adjoints (constant for the window) feed xAd (solve) and adHTdeltaF (step) at the very end: asynchronous
+    // copies, 16 bytes each, issued before pdl_wait
     for (int e = tid; e < nF * nF * 16; e += K3_THREADS) {
         cp_async16(sAdH + 4 * e, &ws->adHostF[0][0] + 4 * e);
         cp_async16(sAdT + 4 * e, &ws->adTargetF[0][0] + 4 * e);
     }
+    pdl_wait();
+    const int iteration = *iteration_dev;
     float nid_pre = 0.f, num_pre = 1.f, tho_pre = 0.f;      // doStepFromBackup's canbreak inputs (thread 0 only)
     if (tid == 0) { nid_pre = ws->sumNID; num_pre = ws->numID; tho_pre = ws->S.thOptIterations; }
     if (flags & K3F_SOLVE) {

@@ -155,6 +155,15 @@ struct DevWindow {
     long long *dbg;               // clock64() phase stamps of K1's CTA 0 (development aid)
 };
 
+// Programmatic dependent launch (sm_90+): the four kernels of a Gauss-Newton iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N+1 may become resident and run its prologue while
+// kernel N is still executing. RULE: before pdl_wait() a kernel may only read data that is constant for the whole
+// iteration (window inputs, set_frames constants, settings) and may not write global memory; everything produced by
+// an earlier kernel of the chain is touched only after pdl_wait() (which returns once all prerequisite grids have
+// completed and flushed). Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #define CUDA_CHECK_RET(ctx, call)                                                         \
     do {                                                                                  \
         cudaError_t e__ = (call);                                                         \

@@ -49,3 +49,4 @@ for rep in range(3):
     timeline("L2-cold")
 ctx.gn_iterations(3, 3); ctx.synchronize()
 timeline("L2-warm")
+print("use_pdl/use_graph probe: launches per gn_iterations(3,1):", (lambda a: (ctx.gn_iterations(3, 1), ctx.launch_count() - a)[1])(ctx.launch_count()))
