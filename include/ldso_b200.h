@@ -185,12 +185,23 @@ int ldso_b200_gn_iterations(ldso_b200_ctx *ctx, int first_iteration, int n_itera
  * context to sharded mode; call it before the first launch. */
 int ldso_b200_reduce_buffer(ldso_b200_ctx *ctx, void **buf_dev, size_t *n_doubles);
 int ldso_b200_set_shard(ldso_b200_ctx *ctx, int newest_slot_offset, int newest_total);
+/* Device-side exchange instead of the caller's all-reduce: ONE kernel (k2r_peer_allreduce) sums the ranks' reduced buffers
+ * over NVLink peer memory (CUDA IPC mappings; every rank pushes its values, tagged with the exchange number, into the peers'
+ * inboxes and polls its own; fixed rank order = identical bits on every rank), so a sharded iteration is K3 -> K1 -> K2a -> K2r -> K2b on the device, captured in one CUDA graph, with no NCCL call
+ * and no host round trip. Setup, once per window topology, one process per GPU on one node:
+ *   set_shard(...); peer_export(handle64);  <all-gather the 64-byte handles, e.g. torch.distributed>;
+ *   peer_connect(rank, world, handles);     then optimize_begin / gn_iterations exactly as on a single GPU.
+ * A peer that never arrives does not hang the GPU: the wait is bounded and peer_error() then reports 1. */
+int ldso_b200_peer_export(ldso_b200_ctx *ctx, void *ipc_handle_64);
+int ldso_b200_peer_connect(ldso_b200_ctx *ctx, int rank, int world, const void *ipc_handles_64_each);
+int ldso_b200_peer_error(ldso_b200_ctx *ctx, int *error);
 int ldso_b200_gn_phase_a(ldso_b200_ctx *ctx, int iteration);
 int ldso_b200_gn_phase_b(ldso_b200_ctx *ctx);
 
 /* Per-kernel CUDA-event timing of the GN loop (bench.py's roofline leg): enable != 0 starts collecting (CUDA graphs off),
- * enable == 0 stops and returns the average duration in microseconds of K1, K2a, K2b, K3 since it was enabled. */
-int ldso_b200_kernel_times(ldso_b200_ctx *ctx, int enable, double out_us[4]);
+ * enable == 0 stops and returns the average duration in microseconds of K1, K2a, K2b, K3, K2r (peer exchange; 0 on a
+ * single GPU) since it was enabled. */
+int ldso_b200_kernel_times(ldso_b200_ctx *ctx, int enable, double out_us[5]);
 
 /* ---- read-back (host mirrors of PointHessian / PointFrameResidual / FrameHessian fields) --------------- */
 /* Optional, non-blocking: queue the device->host copy of everything get_last_solution / get_points / get_residuals

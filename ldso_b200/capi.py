@@ -55,7 +55,7 @@ SYMBOLS = [
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
-    "ldso_b200_gn_phase_b", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
+    "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
     "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
@@ -156,10 +156,10 @@ class Context:
         self._chk(self.L.ldso_b200_synchronize(self.ctx))
 
     def kernel_times(self, enable):
-        """enable=True: start per-kernel event timing; enable=False: stop, return avg us of (k1, k2a, k2b, k3)."""
-        out = (C.c_double * 4)()
+        """enable=True: start per-kernel event timing; enable=False: stop, return avg us of (k1, k2a, k2b, k3, k2r)."""
+        out = (C.c_double * 5)()
         self._chk(self.L.ldso_b200_kernel_times(self.ctx, int(bool(enable)), out))
-        return dict(zip(("k1", "k2a", "k2b", "k3"), list(out)))
+        return dict(zip(("k1", "k2a", "k2b", "k3", "k2r"), list(out)))
 
     def launch_count(self) -> int:
         return int(self.L.ldso_b200_launch_count(self.ctx))
@@ -303,6 +303,23 @@ class Context:
 
     def set_shard(self, offset, total):
         self._chk(self.L.ldso_b200_set_shard(self.ctx, int(offset), int(total)))
+
+    def peer_export(self) -> bytes:
+        h = (C.c_ubyte * 64)()
+        self._chk(self.L.ldso_b200_peer_export(self.ctx, h))
+        return bytes(h)
+
+    def peer_connect(self, rank, world, handles):
+        """handles: list of `world` 64-byte IPC handles (peer_export of every rank, in rank order)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._chk(self.L.ldso_b200_peer_connect(self.ctx, int(rank), int(world), buf))
+
+    def peer_error(self) -> int:
+        e = C.c_int()
+        self._chk(self.L.ldso_b200_peer_error(self.ctx, C.byref(e)))
+        return e.value
 
     def gn_phase_a(self, iteration):
         self._chk(self.L.ldso_b200_gn_phase_a(self.ctx, int(iteration)))

@@ -79,6 +79,14 @@ struct ldso_b200_ctx {
     bool pdl_now = false;            // set while launch_gn_body issues its four kernels
     size_t k1_smem = 0;
     bool multi = false;
+    // peer-memory exchange (k2r_peer_allreduce): this rank's exported inbox, the peers' mapped inboxes, and the local
+    // epoch / completion / error words
+    char *peer_local = nullptr;
+    void *peer_opened[K2R_MAX_PEERS] = {};
+    int *peer_words = nullptr;       // [0] epoch, [1] done, [2] error
+    double *red_sum = nullptr;
+    PeerExchange px;
+    bool peers_connected = false;
 
     // tracker
     TrkLevel trk[MAXLVL];
@@ -242,6 +250,10 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     if (c->ws_dev) cudaFree(c->ws_dev);
     if (c->ws_host) cudaFreeHost(c->ws_host);
     if (c->sol_host) cudaFreeHost(c->sol_host);
+    for (int r = 0; r < K2R_MAX_PEERS; r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
+    if (c->peer_local) cudaFree(c->peer_local);
+    if (c->peer_words) cudaFree(c->peer_words);
+    if (c->red_sum) cudaFree(c->red_sum);
     if (c->iteration_dev) cudaFree(c->iteration_dev);
     if (c->solve_mem) cudaFree(c->solve_mem);
     if (c->trk_partials) cudaFree(c->trk_partials);
@@ -534,6 +546,8 @@ static int build_derived(ldso_b200_ctx *c) {
     CUDA_CHECK_RET(c, cudaMemsetAsync(d.red, 0, sizeof(double) * ((size_t) RED_SELECT + std::max(d.newest_total, 1) + 16), c->stream));
     CUDA_CHECK_RET(c, cudaMemsetAsync(d.partials, 0, sizeof(float) * (size_t) std::max(d.nItems, 1) * PART_STRIDE, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (c->peers_connected && c->px.n_doubles != RED_SELECT + std::max(d.newest_total, 0))
+        return c->fail(LDSO_B200_ERR_STATE, "the window's newest-frame residual count changed: the peer exchange buffers must be re-exported");
     d.items = items_dev; d.host_item_begin = hib_dev; d.res_newest_slot = slot_dev;
     c->derived_dirty = false;
     c->gn_graph_valid = false;
@@ -761,10 +775,19 @@ static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select, int do_ass
         return c->fail(LDSO_B200_ERR_STATE, "the marginalisation prior has a different dimension than the frames (marginalize_frame): call set_frames with the remaining frames first");
     const int nb = c->nF * c->nF + c->nF + 2;
     c->kt_begin("k2b");
-    launch_loop_kernel(c, k2b_stitch, dim3(nb), dim3(K2B_THREADS), K2B_SMEM_BYTES, c->d, c->ws_dev, c->sb, do_stitch, do_select, (int) (do_stitch && do_assemble));
+    DevWindow dw = c->d;
+    if (c->peers_connected) dw.red = c->red_sum;      // the stitch reads the all-reduced accumulators
+    launch_loop_kernel(c, k2b_stitch, dim3(nb), dim3(K2B_THREADS), K2B_SMEM_BYTES, dw, c->ws_dev, c->sb, do_stitch, do_select, (int) (do_stitch && do_assemble));
     c->kt_end();
     LAUNCH_CHECK(c);
     if (do_stitch) c->solve_ready = do_assemble != 0;
+    return LDSO_B200_OK;
+}
+static int launch_k2r(ldso_b200_ctx *c) {
+    c->kt_begin("k2r");
+    launch_loop_kernel(c, k2r_peer_allreduce, dim3(c->px.n_chunks), dim3(K2R_THREADS), 0, c->d, c->px);
+    c->kt_end();
+    LAUNCH_CHECK(c);
     return LDSO_B200_OK;
 }
 // K3(SOLVE) consumes what K2b(do_assemble) left behind; re-stitch if only the prior changed in between
@@ -962,7 +985,8 @@ extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
     RET_IF(clear_select(c));
     RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
     RET_IF(launch_k2a(c, 1));
-    if (c->multi) return LDSO_B200_OK;     // caller all-reduces, then gn_phase_b
+    if (c->multi && !c->peers_connected) return LDSO_B200_OK;     // caller all-reduces, then gn_phase_b
+    if (c->peers_connected) RET_IF(launch_k2r(c));
     RET_IF(launch_k2b(c, 1, 1, 1));
     if (energy_out) {
         CUDA_CHECK_RET(c, cudaMemcpyAsync(energy_out, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -976,13 +1000,14 @@ static int launch_gn_body(ldso_b200_ctx *c) {
     RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
     RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
     RET_IF(launch_k2a(c, 1));
+    if (c->peers_connected) RET_IF(launch_k2r(c));
     RET_IF(launch_k2b(c, 1, 1, 1));
     return LDSO_B200_OK;
 }
 
 extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, int n_iterations) {
     if (!c) return LDSO_B200_ERR_ARG;
-    if (c->multi) return c->fail(LDSO_B200_ERR_STATE, "sharded context: use gn_phase_a / all-reduce / gn_phase_b");
+    if (c->multi && !c->peers_connected) return c->fail(LDSO_B200_ERR_STATE, "sharded context without peer exchange: use gn_phase_a / all-reduce / gn_phase_b, or peer_export + peer_connect");
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
     RET_IF(ensure_solve_ready(c));
@@ -1020,7 +1045,7 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         }
         for (int i = 0; i < n_iterations; i++) {
             CUDA_CHECK_RET(c, cudaGraphLaunch(c->gn_graph, c->stream));
-            c->launches += 4;
+            c->launches += c->peers_connected ? 5 : 4;
             { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
         }
         return LDSO_B200_OK;
@@ -1047,6 +1072,66 @@ extern "C" int ldso_b200_set_shard(ldso_b200_ctx *c, int newest_slot_offset, int
     c->derived_dirty = true;
     return LDSO_B200_OK;
 }
+
+// ---- peer-memory exchange: export this rank's block, map the peers', then gn_iterations / optimize_begin run the whole
+// sharded iteration on the device (K3 -> K1 -> K2a -> K2r -> K2b) with no NCCL call and no host round trip
+extern "C" int ldso_b200_peer_export(ldso_b200_ctx *c, void *ipc_handle_64) {
+    if (!c || !ipc_handle_64) return LDSO_B200_ERR_ARG;
+    if (!c->multi) return c->fail(LDSO_B200_ERR_STATE, "peer_export needs set_shard first");
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const int n = RED_SELECT + std::max(c->d.newest_total, 0);
+    const int nch = (n + K2R_THREADS - 1) / K2R_THREADS;
+    if (c->peers_connected || c->peer_local) return c->fail(LDSO_B200_ERR_STATE, "peer exchange already set up for this context");
+    const size_t bytes = sizeof(uint4) * 2 * K2R_MAX_PEERS * (size_t) n;      // the inbox: [2 parities][8 senders][n] 16-byte slots
+    CUDA_CHECK_RET(c, cudaMalloc(&c->peer_local, bytes));
+    CUDA_CHECK_RET(c, cudaMemset(c->peer_local, 0, bytes));
+    CUDA_CHECK_RET(c, cudaMalloc(&c->peer_words, sizeof(int) * 4));
+    CUDA_CHECK_RET(c, cudaMemset(c->peer_words, 0, sizeof(int) * 4));
+    CUDA_CHECK_RET(c, cudaMalloc(&c->red_sum, sizeof(double) * ((size_t) n + 16)));
+    CUDA_CHECK_RET(c, cudaMemset(c->red_sum, 0, sizeof(double) * ((size_t) n + 16)));
+    memset(&c->px, 0, sizeof(c->px));
+    c->px.n_doubles = n; c->px.n_chunks = nch;
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK_RET(c, cudaIpcGetMemHandle(&h, c->peer_local));
+    memcpy(ipc_handle_64, &h, 64);
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_peer_connect(ldso_b200_ctx *c, int rank, int world, const void *ipc_handles_64_each) {
+    if (!c || !ipc_handles_64_each) return LDSO_B200_ERR_ARG;
+    if (!c->peer_local) return c->fail(LDSO_B200_ERR_STATE, "peer_connect needs peer_export first");
+    if (world < 1 || world > K2R_MAX_PEERS || rank < 0 || rank >= world) return c->fail(LDSO_B200_ERR_ARG, "rank/world out of range (max 8 peers)");
+    cudaSetDevice(c->device);
+    for (int r = 0; r < world; r++) {
+        char *base = c->peer_local;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *) ipc_handles_64_each + 64 * r, 64);
+            void *p = nullptr;
+            CUDA_CHECK_RET(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_opened[r] = p;
+            base = (char *) p;
+        }
+        c->px.inbox[r] = (uint4 *) base;
+    }
+    c->px.rank = rank; c->px.world = world;
+    c->px.epoch = c->peer_words; c->px.done = (unsigned *) (c->peer_words + 1); c->px.error = c->peer_words + 2;
+    c->px.out = c->red_sum;
+    c->peers_connected = true;
+    c->gn_graph_valid = false;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_peer_error(ldso_b200_ctx *c, int *error) {
+    if (!c || !error || !c->peer_words) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(error, c->peer_words + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
 
 extern "C" int ldso_b200_gn_phase_a(ldso_b200_ctx *c, int iteration) {
     if (!c) return LDSO_B200_ERR_ARG;
@@ -1194,7 +1279,7 @@ extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *s
 
 // Per-kernel CUDA-event timing of the GN loop (bench.py's roofline leg): enable != 0 starts collecting (graphs off),
 // enable == 0 stops and returns the average duration in microseconds of K1, K2a, K2b, K3 since it was enabled.
-extern "C" int ldso_b200_kernel_times(ldso_b200_ctx *c, int enable, double out_us[4]) {
+extern "C" int ldso_b200_kernel_times(ldso_b200_ctx *c, int enable, double out_us[5]) {
     if (!c) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
@@ -1205,19 +1290,19 @@ extern "C" int ldso_b200_kernel_times(ldso_b200_ctx *c, int enable, double out_u
         c->use_graph = false;
         return LDSO_B200_OK;
     }
-    const char *names[4] = {"k1", "k2a", "k2b", "k3"};
-    double tot[4] = {0, 0, 0, 0};
-    int cnt[4] = {0, 0, 0, 0};
+    const char *names[5] = {"k1", "k2a", "k2b", "k3", "k2r"};
+    double tot[5] = {0, 0, 0, 0, 0};
+    int cnt[5] = {0, 0, 0, 0, 0};
     for (auto &k : c->kt) {
         float ms = 0;
         cudaEventElapsedTime(&ms, k.a, k.b);
-        for (int i = 0; i < 4; i++) if (!strcmp(names[i], k.name)) { tot[i] += ms; cnt[i]++; }
+        for (int i = 0; i < 5; i++) if (!strcmp(names[i], k.name)) { tot[i] += ms; cnt[i]++; }
         cudaEventDestroy(k.a); cudaEventDestroy(k.b);
     }
     c->kt.clear();
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
     c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
-    if (out_us) for (int i = 0; i < 4; i++) out_us[i] = cnt[i] ? 1e3 * tot[i] / cnt[i] : 0.0;
+    if (out_us) for (int i = 0; i < 5; i++) out_us[i] = cnt[i] ? 1e3 * tot[i] / cnt[i] : 0.0;
     return LDSO_B200_OK;
 }
 

@@ -80,6 +80,71 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K2r: the exchange step of the sharded Gauss-Newton iteration as ONE kernel over NVLink peer memory (no NCCL call, no host
+// round trip): a push-based one-shot all-reduce of the reduced buffer with flag-in-data slots. Every rank owns an inbox
+// [2 parities][8 senders][n] of 16-byte slots {lo32, tag, hi32, tag}. The thread that owns element g (1) writes its value,
+// tagged with the exchange number, straight into the inbox of every peer (two 8-byte stores per slot, each atomic over
+// NVLink -- no fence, no separate flag), then (2) polls its OWN inbox (local memory) until the slots of all peers carry
+// this exchange's tag, and (3) adds the contributions in RANK ORDER (identical bits on every rank) into the buffer the
+// stitch kernel reads. Cost: one one-way NVLink store latency plus local polling. The inbox is double-buffered by parity:
+// a sender reuses a slot two exchanges later, which it cannot reach before this rank has sent the exchange in between,
+// i.e. after this rank finished reading the current one.
+#define K2R_THREADS 256
+#define K2R_MAX_PEERS 8
+struct PeerExchange {
+    int rank, world, n_doubles, n_chunks;
+    uint4 *inbox[K2R_MAX_PEERS];          // rank r's inbox (peer-mapped for r != rank): [2][K2R_MAX_PEERS][n_doubles]
+    int *epoch;                           // local: number of exchanges completed
+    unsigned *done;                       // local: CTAs finished in this launch
+    int *error;                           // local: set when a peer's data never arrived (bounded spin)
+    double *out;                          // local: the summed buffer
+};
+__global__ void __launch_bounds__(K2R_THREADS) k2r_peer_allreduce(DevWindow d, PeerExchange px) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int s_epoch;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_epoch = *((volatile int *) px.epoch) + 1;
+    __syncthreads();
+    const unsigned e = (unsigned) s_epoch;
+    const int par = (int) (e & 1u);
+    const int g = blockIdx.x * K2R_THREADS + tid;
+    if (g < px.n_doubles) {
+        const double mine = d.red[g];
+        const unsigned lo = (unsigned) __double2loint(mine), hi = (unsigned) __double2hiint(mine);
+        for (int p = 0; p < px.world; p++) {
+            if (p == px.rank) continue;
+            uint4 *dst = px.inbox[p] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * px.n_doubles + g);
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(lo), "r"(e) : "memory");
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"((char *) dst + 8), "r"(hi), "r"(e) : "memory");
+        }
+        double s = 0.0;
+        bool late = false;
+        for (int r = 0; r < px.world; r++) {
+            double v = mine;
+            if (r != px.rank) {
+                const uint4 *src = px.inbox[px.rank] + ((size_t) (par * K2R_MAX_PEERS + r) * px.n_doubles + g);
+                unsigned a, f0, c, f1;
+                int spins = 0;
+                do {
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f0), "=r"(c), "=r"(f1) : "l"(src) : "memory");
+                } while ((f0 != e || f1 != e) && ++spins < (1 << 24));          // ~ seconds; never hang the GPU
+                if (f0 != e || f1 != e) late = true;
+                v = __hiloint2double((int) c, (int) a);
+            }
+            s += v;
+        }
+        px.out[g] = s;
+        if (late) *px.error = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(px.done, 1u) == gridDim.x - 1) { *px.done = 0u; *px.epoch = (int) e; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // packed index of element (r,c) of the symmetric 13x13 AccumulatorApprox block [C(4)|xi(6)|ab(2)|r(1)]
 __device__ __forceinline__ int packed13(int r, int c) {
     if (r > c) { int t = r; r = c; c = t; }

@@ -44,6 +44,32 @@ def main():
         energies.append(ctx.energy()[0])
     pts = ctx.points()
     ok = True
+    # ---- the same iterations with the device-side exchange (k2r_peer_allreduce over NVLink peer memory): no NCCL call in the loop
+    ctx2 = capi.Context(win.w, win.h, win.levels, device=lr)
+    ctx2.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx2.load_synth_window(win)
+    ctx2.set_shard(int(np.sum(counts[:rank])), int(np.sum(counts)))
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx2.peer_export())
+    ctx2.peer_connect(rank, world, handles)
+    dist.barrier()
+    e2 = [ctx2.optimize_begin()]
+    sols2 = []
+    for it in range(3):
+        ctx2.gn_iterations(it, 1)
+        sols2.append(ctx2.last_solution())
+        e2.append(ctx2.energy()[0])
+    ok &= ctx2.peer_error() == 0
+    for it in range(3):
+        for k in ("lastHS", "lastbS", "lastX"):
+            same = np.array_equal(sols2[it][k], sols[it][k]) if world == 2 else rel_err(sols2[it][k], sols[it][k]) < 1e-9
+            if not same:
+                print(f"rank {rank}: peer path differs from the NCCL path at it{it} {k}: {rel_err(sols2[it][k], sols[it][k]):.3e}")
+                ok = False
+    ok &= bool(np.allclose(e2, energies, rtol=1e-12))
+    if rank == 0:
+        print("peer-exchange path: energies", [round(x, 3) for x in e2])
+    torch.cuda.synchronize(); dist.barrier()
     if rank == 0:
         ref = capi.Context(full.w, full.h, full.levels, device=lr)
         ref.load_synth_window(full)
