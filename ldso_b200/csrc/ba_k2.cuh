@@ -169,7 +169,7 @@ struct SolveBufs {
 // regrouped by output block so that no two CTAs write the same element (deterministic, no atomics).
 #define K2B_THREADS 512
 #define K2B_NSLOT (K2B_THREADS / 64)
-#define K2B_SELCAP 8192          // newest-frame energies kept in shared memory by the select CTA
+#define K2B_SELCAP 30720         // newest-frame energies kept in shared memory by the select CTA (120 KB of the CTA's dynamic smem)
 // staged 8x8 matrices use a row stride of 10 doubles: rows then start 20 banks apart, so both the "one row per lane
 // group" and the "transposed operand" access patterns of the triple products are bank-conflict free and stay 16-byte
 // aligned (with the natural stride of 8 every other row maps to the same banks: 4-way conflicts on every operand load)
@@ -529,6 +529,9 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     {
         if (tid == 0) d.dbg[12] = clock64();
         const int N = d.newest_total;
+        // settings (constant): requested now, consumed after the passes
+        const float set_thn = ws->S.frameEnergyTHN, set_fac = ws->S.frameEnergyTHFacMedian, set_cw = ws->S.frameEnergyTHConstWeight,
+                    set_ow = ws->S.overallEnergyTHWeight;
         const double *vals = red + RED_SELECT;
         extern __shared__ double sk2[];
         unsigned *skey = (unsigned *) sk2;            // float bit patterns of the valid energies (0x80000000 = excluded)
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         if (m == 0) {
             th = 12 * 12 * LDSO_B200_PATTERN;
         } else {
-            if (tid == 0) sel_k = (unsigned) (int) (ws->S.frameEnergyTHN * (float) m);
+            if (tid == 0) sel_k = (unsigned) (int) (set_thn * (float) m);
             __syncthreads();
             for (int pass = 3; pass >= 0; pass--) {
                 for (int i = tid; i < 256; i += K2B_THREADS) hist[i] = 0;
@@ -559,22 +562,31 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
                 // energies of one frame share their leading bytes: aggregate equal bins inside the warp first
                 // (one shared-memory atomic per distinct bin per warp instead of 32 serialised ones)
-                for (int i = tid; i < ((N + 31) & ~31); i += K2B_THREADS) {
-                    unsigned key = 0x80000000u;
-                    if (i < N) {
-                        if (insm) key = skey[i];
-                        else { const double v = vals[i]; key = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
+                for (int i0 = tid; i0 < ((N + 31) & ~31); i0 += 4 * K2B_THREADS) {     // 4 independent keys per trip
+                    unsigned key[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * K2B_THREADS;
+                        key[u] = 0x80000000u;
+                        if (i < N) {
+                            if (insm) key[u] = skey[i];
+                            else { const double v = vals[i]; key[u] = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
+                        }
                     }
-                    const bool act = (key != 0x80000000u) && ((key & himask) == pref);
-                    const unsigned bin = act ? ((key >> (8 * pass)) & 0xffu) : 256u;
-                    const unsigned mm = __match_any_sync(0xffffffffu, bin);
-                    if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist[bin], (unsigned) __popc(mm));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const bool act = (key[u] != 0x80000000u) && ((key[u] & himask) == pref);
+                        const unsigned bin = act ? ((key[u] >> (8 * pass)) & 0xffu) : 256u;
+                        const unsigned mm = __match_any_sync(0xffffffffu, bin);
+                        if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist[bin], (unsigned) __popc(mm));
+                    }
                 }
                 __syncthreads();
                 if (tid < 32) {
                     // warp 0: lane owns 8 consecutive bins; find the bin holding rank sel_k
-                    unsigned loc = 0;
-                    for (int q = 0; q < 8; q++) loc += hist[8 * tid + q];
+                    unsigned hq[8], loc = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { hq[q] = hist[8 * tid + q]; loc += hq[q]; }
                     unsigned incl = loc;
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -586,9 +598,13 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                     __syncwarp();
                     if (mine) {
                         unsigned k = k0 - excl, bin = 8 * tid;
-                        for (int q = 0; q < 8; q++, bin++) {
-                            if (k < hist[bin]) break;
-                            k -= hist[bin];
+                        bool found = false;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (!found) {
+                                if (k < hq[q]) found = true;
+                                else { k -= hq[q]; bin++; }
+                            }
                         }
                         sel_k = k;
                         sel_prefix = pref | (bin << (8 * pass));
@@ -597,10 +613,10 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 __syncthreads();
             }
             const float nthElement = sqrtf(__uint_as_float(sel_prefix));
-            th = nthElement * ws->S.frameEnergyTHFacMedian;
-            th = 26.0f * ws->S.frameEnergyTHConstWeight + th * (1 - ws->S.frameEnergyTHConstWeight);
+            th = nthElement * set_fac;
+            th = 26.0f * set_cw + th * (1 - set_cw);
             th = th * th;
-            th *= ws->S.overallEnergyTHWeight * ws->S.overallEnergyTHWeight;
+            th *= set_ow * set_ow;
         }
         if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; d.dbg[13] = clock64(); }
     }
