@@ -59,6 +59,16 @@ typedef struct ldso_b200_settings {
     float thOptIterations;            /* :37 */
     double solverModeDelta;           /* :24 */
     float margWeightFac;              /* setting_margWeightFac           :45 */
+    /* immature-point tracing (ImmaturePoint::traceOn) */
+    float maxPixSearch;               /* setting_maxPixSearch            :28 */
+    float outlierTH;                  /* setting_outlierTH               :39 */
+    float trace_stepsize;             /* :89 */
+    float trace_GNThreshold;          /* :91 */
+    float trace_extraSlackOnTH;       /* :92 */
+    float trace_slackInterval;        /* :93 */
+    float trace_minImprovementFactor; /* :94 */
+    int32_t minTraceTestRadius;       /* :52 */
+    int32_t trace_GNIterations;       /* :90 */
 } ldso_b200_settings;
 
 void ldso_b200_default_settings(ldso_b200_settings *s);
@@ -225,6 +235,33 @@ int ldso_b200_get_residuals(ldso_b200_ctx *ctx, uint8_t *state_state, uint8_t *s
 int ldso_b200_get_frames(ldso_b200_ctx *ctx, double *state10, double *step10, float *frameEnergyTH, float *precalc40,
                          double *adHost64, double *adTarget64, float *adHTdeltaF8, double *calib_value4);
 int ldso_b200_get_nullspace_projector(ldso_b200_ctx *ctx, double *P);
+
+/* ---- immature points (src/internal/ImmaturePoint.cc) -------------------------------
+ * Candidate points whose inverse depth is still an interval [idepth_min, idepth_max]; SoA mirror of the ImmaturePoint fields
+ * (include/internal/ImmaturePoint.h:103-121). status = ImmaturePointStatus (0 GOOD, 1 OOB, 2 OUTLIER, 3 SKIPPED,
+ * 4 BADCONDITION, 5 UNINITIALIZED). */
+typedef struct ldso_b200_immature {
+    int n;
+    const float *u, *v;                 /* [n] feature->uv on the host keyframe */
+    const int32_t *host;                /* [n] index into the per-host KRKi/Kt/aff arrays of trace_immature */
+    const float *color8, *weights8;     /* [n*8] color[], weights[] */
+    const float *gradH4;                /* [n*4] gradH row-major */
+    const float *energyTH;              /* [n] */
+    float *idepth_min, *idepth_max;     /* [n] in/out */
+    float *quality;                     /* [n] in/out */
+    int32_t *lastTraceStatus;           /* [n] in/out */
+    float *lastTraceUV2;                /* [n*2] out */
+    float *lastTracePixelInterval;      /* [n] out */
+} ldso_b200_immature;
+/* ImmaturePoint::ImmaturePoint (ImmaturePoint.cc:14-38) for n candidates of the keyframe in image slot host_slot:
+ * fills color8, weights8, gradH4, energyTH (NaN where a pattern pixel is not finite). */
+int ldso_b200_immature_init(ldso_b200_ctx *ctx, int host_slot, int n, const float *u, const float *v, float *color8,
+                            float *weights8, float *gradH4, float *energyTH);
+/* One FullSystem::traceNewCoarse pass (FullSystem.cc:1012-1050): ImmaturePoint::traceOn (ImmaturePoint.cc:46-314) of every
+ * candidate on the frame in image slot new_slot. KRKi9 (row-major 3x3), Kt3, aff2 per host keyframe, computed by the caller
+ * exactly as FullSystem.cc:1027-1032 does. One warp per candidate. */
+int ldso_b200_trace_immature(ldso_b200_ctx *ctx, int new_slot, const ldso_b200_immature *pts, int n_hosts, const float *KRKi9,
+                             const float *Kt3, const float *aff2);
 
 /* ---- coarse tracker (src/frontend/CoarseTracker.cc) ---------------------------------------------------- */
 /* CoarseTracker::makeK (:219-246) */

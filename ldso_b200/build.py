@@ -36,7 +36,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.environ.get("LDSO_B200_LIB", LIB)
-    cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "api.cu"), "-o", out]
+    # trace.cu (immature-point trace) keeps separate multiply/add roundings: its own object, built with -fmad=false
+    trace_o = os.path.join(LIBDIR, "trace.o")
+    base = [f for f in FLAGS if f != "-shared"]
+    subprocess.check_call([NVCC] + base + EXTRA + ["-fmad=false", "-c", os.path.join(CSRC, "trace.cu"), "-o", trace_o])
+    cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "api.cu"), trace_o, "-o", out]
     subprocess.check_call(cmd)
     return out
 

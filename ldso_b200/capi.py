@@ -27,7 +27,9 @@ class Settings(C.Structure):
         "huberTH", "outlierTHSumComponent", "affineOptModeA", "affineOptModeB", "idepthFixPrior", "initialTransPrior",
         "initialRotPrior", "initialAffAPrior", "initialAffBPrior", "initialCalibHessian", "frameEnergyTHN",
         "frameEnergyTHFacMedian", "frameEnergyTHConstWeight", "overallEnergyTHWeight", "coarseCutoffTH",
-        "thOptIterations")] + [("solverModeDelta", C.c_double), ("margWeightFac", C.c_float)]
+        "thOptIterations")] + [("solverModeDelta", C.c_double), ("margWeightFac", C.c_float)] + [(n, C.c_float) for n in (
+        "maxPixSearch", "outlierTH", "trace_stepsize", "trace_GNThreshold", "trace_extraSlackOnTH", "trace_slackInterval",
+        "trace_minImprovementFactor")] + [("minTraceTestRadius", C.c_int32), ("trace_GNIterations", C.c_int32)]
 
 
 class WindowC(C.Structure):
@@ -35,6 +37,12 @@ class WindowC(C.Structure):
                 ("pt_idepth", c_fp), ("pt_idepth_zero", c_fp), ("pt_has_prior", c_bp), ("pt_color", c_fp),
                 ("pt_weights", c_fp), ("res_begin", c_ip), ("res_target", c_ip), ("res_state", c_bp),
                 ("res_is_linearized", c_bp), ("res_toZeroF", c_fp)]
+
+
+class ImmatureC(C.Structure):
+    _fields_ = [("n", C.c_int), ("u", c_fp), ("v", c_fp), ("host", c_ip), ("color8", c_fp), ("weights8", c_fp), ("gradH4", c_fp),
+                ("energyTH", c_fp), ("idepth_min", c_fp), ("idepth_max", c_fp), ("quality", c_fp), ("lastTraceStatus", c_ip),
+                ("lastTraceUV2", c_fp), ("lastTracePixelInterval", c_fp)]
 
 
 class FrameStateC(C.Structure):
@@ -56,7 +64,8 @@ SYMBOLS = [
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
-    "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_tracker_make_k",
+    "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
+    "ldso_b200_trace_immature", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
     "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
 ]
@@ -394,6 +403,36 @@ class Context:
         return P
 
     # ---- tracker
+    # ---- immature points
+    def immature_init(self, host_slot, u, v):
+        """ImmaturePoint's constructor for candidates (u, v) of the keyframe in image slot host_slot."""
+        u = np.ascontiguousarray(u, np.float32); v = np.ascontiguousarray(v, np.float32)
+        n = u.shape[0]
+        out = dict(color=np.zeros((n, 8), np.float32), weights=np.zeros((n, 8), np.float32), gradH=np.zeros((n, 4), np.float32),
+                   energyTH=np.zeros(n, np.float32))
+        self._chk(self.L.ldso_b200_immature_init(self.ctx, int(host_slot), n, _f(u), _f(v), _f(out["color"]), _f(out["weights"]),
+                                                 _f(out["gradH"]), _f(out["energyTH"])))
+        return out
+
+    def trace_immature(self, new_slot, pts: dict, KRKi, Kt, aff):
+        """One traceNewCoarse pass. pts: dict of arrays u, v, host, color, weights, gradH, energyTH, idepth_min, idepth_max, quality,
+        status, uv, interval (the last six are updated in place). KRKi (nH,3,3), Kt (nH,3), aff (nH,2) per host."""
+        f32 = lambda k: np.ascontiguousarray(pts[k], np.float32)
+        for k in ("idepth_min", "idepth_max", "quality", "uv", "interval"):
+            assert pts[k].dtype == np.float32 and pts[k].flags.c_contiguous
+        assert pts["status"].dtype == np.int32 and pts["status"].flags.c_contiguous
+        keep = dict(u=f32("u"), v=f32("v"), host=np.ascontiguousarray(pts["host"], np.int32), color=f32("color"), weights=f32("weights"),
+                    gradH=f32("gradH"), energyTH=f32("energyTH"), K=np.ascontiguousarray(KRKi, np.float32),
+                    t=np.ascontiguousarray(Kt, np.float32), a=np.ascontiguousarray(aff, np.float32))
+        p = ImmatureC()
+        p.n = int(keep["u"].shape[0])
+        p.u = _f(keep["u"]); p.v = _f(keep["v"]); p.host = _i(keep["host"]); p.color8 = _f(keep["color"]); p.weights8 = _f(keep["weights"])
+        p.gradH4 = _f(keep["gradH"]); p.energyTH = _f(keep["energyTH"]); p.idepth_min = _f(pts["idepth_min"]); p.idepth_max = _f(pts["idepth_max"])
+        p.quality = _f(pts["quality"]); p.lastTraceStatus = _i(pts["status"]); p.lastTraceUV2 = _f(pts["uv"])
+        p.lastTracePixelInterval = _f(pts["interval"])
+        self._chk(self.L.ldso_b200_trace_immature(self.ctx, int(new_slot), C.byref(p), int(keep["K"].shape[0]), _f(keep["K"]), _f(keep["t"]),
+                                                  _f(keep["a"])))
+
     def tracker_make_k(self, fx, fy, cx, cy):
         self._chk(self.L.ldso_b200_tracker_make_k(self.ctx, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))
 

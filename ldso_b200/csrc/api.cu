@@ -17,6 +17,7 @@
 #include "ba_k2.cuh"
 #include "ba_k3.cuh"
 #include "tracker_kernels.cuh"
+#include "trace_types.h"
 
 static_assert(K1_THREADS / 32 == MAXF, "phase B maps one warp to one target frame");
 
@@ -78,6 +79,8 @@ struct ldso_b200_ctx {
     bool use_pdl = true;             // programmatic dependent launch inside the GN iteration (env LDSO_B200_NO_PDL disables)
     bool pdl_now = false;            // set while launch_gn_body issues its four kernels
     size_t k1_smem = 0;
+    char *trace_buf = nullptr;       // device scratch of immature_init / trace_immature
+    size_t trace_cap = 0;
     bool multi = false;
     // peer-memory exchange (k2r_peer_allreduce): this rank's exported inbox, the peers' mapped inboxes, and the local
     // epoch / completion / error words
@@ -163,6 +166,15 @@ extern "C" void ldso_b200_default_settings(ldso_b200_settings *s) {
     s->thOptIterations = 1.2f;
     s->solverModeDelta = 0.00001;
     s->margWeightFac = 0.5f * 0.5f;
+    s->maxPixSearch = 0.027f;
+    s->outlierTH = 12 * 12;
+    s->trace_stepsize = 1.0f;
+    s->trace_GNThreshold = 0.1f;
+    s->trace_extraSlackOnTH = 1.2f;
+    s->trace_slackInterval = 1.5f;
+    s->trace_minImprovementFactor = 2;
+    s->minTraceTestRadius = 2;
+    s->trace_GNIterations = 3;
 }
 
 extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_levels, const ldso_b200_settings *settings) {
@@ -250,6 +262,7 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     if (c->ws_dev) cudaFree(c->ws_dev);
     if (c->ws_host) cudaFreeHost(c->ws_host);
     if (c->sol_host) cudaFreeHost(c->sol_host);
+    if (c->trace_buf) cudaFree(c->trace_buf);
     for (int r = 0; r < K2R_MAX_PEERS; r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
     if (c->peer_local) cudaFree(c->peer_local);
     if (c->peer_words) cudaFree(c->peer_words);
@@ -972,6 +985,85 @@ extern "C" int ldso_b200_marginalize_frame(ldso_b200_ctx *c, int frame_idx, int 
     c->prior_dim = n - 8;
     c->solve_ready = false; c->restitch_ok = false;
     if (new_dim) *new_dim = n - 8;
+    return LDSO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- immature points
+static TraceSettingsDev trace_settings(const ldso_b200_ctx *c) {
+    TraceSettingsDev T;
+    T.maxPixSearch = c->S.maxPixSearch; T.outlierTH = c->S.outlierTH; T.outlierTHSumComponent = c->S.outlierTHSumComponent;
+    T.huberTH = c->S.huberTH; T.overallEnergyTHWeight = c->S.overallEnergyTHWeight;
+    T.minTraceTestRadius = c->S.minTraceTestRadius; T.trace_GNIterations = c->S.trace_GNIterations;
+    T.trace_stepsize = c->S.trace_stepsize; T.trace_GNThreshold = c->S.trace_GNThreshold;
+    T.trace_extraSlackOnTH = c->S.trace_extraSlackOnTH; T.trace_slackInterval = c->S.trace_slackInterval;
+    T.trace_minImprovementFactor = c->S.trace_minImprovementFactor;
+    return T;
+}
+static int trace_reserve(ldso_b200_ctx *c, size_t bytes) {
+    if (bytes <= c->trace_cap) return LDSO_B200_OK;
+    if (c->trace_buf) cudaFree(c->trace_buf);
+    c->trace_buf = nullptr; c->trace_cap = 0;
+    CUDA_CHECK_RET(c, cudaMalloc(&c->trace_buf, bytes));
+    c->trace_cap = bytes;
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_immature_init(ldso_b200_ctx *c, int host_slot, int n, const float *u, const float *v, float *color8,
+                                       float *weights8, float *gradH4, float *energyTH) {
+    if (!c || n < 0 || (n > 0 && (!u || !v || !color8 || !weights8 || !gradH4 || !energyTH))) return LDSO_B200_ERR_ARG;
+    if (host_slot < 0 || host_slot >= NSLOTS || !c->img[host_slot][0]) return c->fail(LDSO_B200_ERR_ARG, "host image slot not uploaded");
+    if (n == 0) return LDSO_B200_OK;
+    cudaSetDevice(c->device);
+    const size_t N = (size_t) n;
+    RET_IF(trace_reserve(c, sizeof(float) * N * 23));
+    float *du = (float *) c->trace_buf, *dv = du + N, *dc = dv + N, *dw = dc + 8 * N, *dg = dw + 8 * N, *de = dg + 4 * N;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(du, u, 4 * N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(dv, v, 4 * N, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(dc, 0, sizeof(float) * N * 21, c->stream));
+    launch_immature_init(n, c->img[host_slot][0], c->w, du, dv, trace_settings(c), dc, dw, dg, de, c->stream);
+    LAUNCH_CHECK(c);
+    D2H(color8, dc, 32 * N); D2H(weights8, dw, 32 * N); D2H(gradH4, dg, 16 * N); D2H(energyTH, de, 4 * N);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_trace_immature(ldso_b200_ctx *c, int new_slot, const ldso_b200_immature *p, int n_hosts, const float *KRKi9,
+                                        const float *Kt3, const float *aff2) {
+    if (!c || !p || !KRKi9 || !Kt3 || !aff2 || n_hosts < 1) return LDSO_B200_ERR_ARG;
+    if (new_slot < 0 || new_slot >= NSLOTS || !c->img[new_slot][0]) return c->fail(LDSO_B200_ERR_ARG, "image slot of the traced frame not uploaded");
+    const int n = p->n;
+    if (n < 0) return c->fail(LDSO_B200_ERR_ARG, "negative candidate count");
+    if (n == 0) return LDSO_B200_OK;
+    if (!p->u || !p->v || !p->host || !p->color8 || !p->weights8 || !p->gradH4 || !p->energyTH || !p->idepth_min || !p->idepth_max ||
+        !p->quality || !p->lastTraceStatus || !p->lastTraceUV2 || !p->lastTracePixelInterval) return c->fail(LDSO_B200_ERR_ARG, "null candidate array");
+    for (int i = 0; i < n; i++) if (p->host[i] < 0 || p->host[i] >= n_hosts) return c->fail(LDSO_B200_ERR_ARG, "candidate host index out of range");
+    cudaSetDevice(c->device);
+    const size_t N = (size_t) n, H = (size_t) n_hosts;
+    // layout (floats): u v color8 weights8 gradH4 energyTH | idmin idmax quality uv2 interval | host status (ints) | KRKi Kt aff
+    const size_t nf = N * (2 + 8 + 8 + 4 + 1) + N * (3 + 2 + 1) + 2 * N + H * 14;
+    RET_IF(trace_reserve(c, sizeof(float) * nf));
+    float *q = (float *) c->trace_buf;
+    TraceArgs A;
+    A.n = n; A.w = c->w; A.h = c->h; A.img = c->img[new_slot][0]; A.S = trace_settings(c);
+    float *du = q; q += N; float *dv = q; q += N; float *dc = q; q += 8 * N; float *dw = q; q += 8 * N; float *dg = q; q += 4 * N; float *de = q; q += N;
+    float *dmin = q; q += N; float *dmax = q; q += N; float *dq = q; q += N; float *duv = q; q += 2 * N; float *div = q; q += N;
+    int *dh = (int *) q; q += N; int *ds = (int *) q; q += N;
+    float *dK = q; q += 9 * H; float *dt = q; q += 3 * H; float *da = q; q += 2 * H;
+#define TR_H2D(dst, src, bytes) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream))
+    TR_H2D(du, p->u, 4 * N); TR_H2D(dv, p->v, 4 * N); TR_H2D(dc, p->color8, 32 * N); TR_H2D(dw, p->weights8, 32 * N);
+    TR_H2D(dg, p->gradH4, 16 * N); TR_H2D(de, p->energyTH, 4 * N); TR_H2D(dmin, p->idepth_min, 4 * N); TR_H2D(dmax, p->idepth_max, 4 * N);
+    TR_H2D(dq, p->quality, 4 * N); TR_H2D(duv, p->lastTraceUV2, 8 * N); TR_H2D(div, p->lastTracePixelInterval, 4 * N);
+    TR_H2D(dh, p->host, 4 * N); TR_H2D(ds, p->lastTraceStatus, 4 * N);
+    TR_H2D(dK, KRKi9, 36 * H); TR_H2D(dt, Kt3, 12 * H); TR_H2D(da, aff2, 8 * H);
+#undef TR_H2D
+    A.u = du; A.v = dv; A.color8 = dc; A.weights8 = dw; A.gradH4 = dg; A.energyTH = de; A.host = dh;
+    A.KRKi9 = dK; A.Kt3 = dt; A.aff2 = da;
+    A.idepth_min = dmin; A.idepth_max = dmax; A.quality = dq; A.status = ds; A.uv2 = duv; A.interval = div;
+    launch_trace_on(A, c->stream);
+    LAUNCH_CHECK(c);
+    D2H(p->idepth_min, dmin, 4 * N); D2H(p->idepth_max, dmax, 4 * N); D2H(p->quality, dq, 4 * N); D2H(p->lastTraceStatus, ds, 4 * N);
+    D2H(p->lastTraceUV2, duv, 8 * N); D2H(p->lastTracePixelInterval, div, 4 * N);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     return LDSO_B200_OK;
 }
 

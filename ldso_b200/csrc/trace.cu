@@ -1,0 +1,10 @@
+// Immature-point kernels: separate translation unit, compiled with -fmad=false (see trace_types.h).
+#include "trace_kernels.cuh"
+
+void launch_immature_init(int n, const float4 *img, int w, const float *u, const float *v, const TraceSettingsDev &S, float *color8,
+                          float *weights8, float *gradH4, float *energyTH, cudaStream_t stream) {
+    k_immature_init<<<(n + 127) / 128, 128, 0, stream>>>(n, img, w, u, v, S, color8, weights8, gradH4, energyTH);
+}
+void launch_trace_on(const TraceArgs &A, cudaStream_t stream) {
+    k_trace_on<<<(A.n + KTR_WARPS - 1) / KTR_WARPS, 32 * KTR_WARPS, 0, stream>>>(A);
+}

@@ -1,0 +1,250 @@
+// Immature-point candidates on the device: ImmaturePoint's constructor and ImmaturePoint::traceOn
+// (src/internal/ImmaturePoint.cc:14-38, :46-314), driven like FullSystem::traceNewCoarse drives them (FullSystem.cc:1012-1050).
+// One WARP per candidate. The discrete epipolar search runs 32 steps at a time (lane = step; every lane re-creates the
+// reference's running `ptx += dx` by repeated addition so the sample positions are bit-identical, and adds its 8 pattern
+// residuals in the reference's order); the 1-D Gauss-Newton refinement evaluates the 8 pattern pixels on lanes 0..7 and
+// accumulates them in pattern order. All control flow is warp-uniform (every lane carries the same scalars).
+#pragma once
+#include "trace_types.h"
+
+__constant__ int c_trace_pattern[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
+
+// getInterpolatedElement31 / 33 (GlobalFuncs.h:145-159, :89-103); samples outside the image count as non-finite (the reference
+// would read out of bounds there)
+__device__ __forceinline__ float trace_tap1(const float4 *img, int w, int h, float x, float y) {
+    const int ix = (int) x, iy = (int) y;
+    if (!(x >= 0.f && y >= 0.f && ix < w - 1 && iy < h - 1)) return NAN;
+    const float dx = x - ix, dy = y - iy, dxdy = dx * dy;
+    const float4 *bp = img + ix + iy * w;
+    return dxdy * bp[1 + w].x + (dy - dxdy) * bp[w].x + (dx - dxdy) * bp[1].x + (1 - dx - dy + dxdy) * bp[0].x;
+}
+__device__ __forceinline__ float3 trace_tap3(const float4 *img, int w, int h, float x, float y) {
+    const int ix = (int) x, iy = (int) y;
+    if (!(x >= 0.f && y >= 0.f && ix < w - 1 && iy < h - 1)) return make_float3(NAN, 0.f, 0.f);
+    const float dx = x - ix, dy = y - iy, dxdy = dx * dy;
+    const float4 *bp = img + ix + iy * w;
+    const float4 p11 = bp[1 + w], p01 = bp[w], p10 = bp[1], p00 = bp[0];
+    const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+    return make_float3(w11 * p11.x + w01 * p01.x + w10 * p10.x + w00 * p00.x, w11 * p11.y + w01 * p01.y + w10 * p10.y + w00 * p00.y,
+                       w11 * p11.z + w01 * p01.z + w10 * p10.z + w00 * p00.z);
+}
+
+// ImmaturePoint::ImmaturePoint (:14-38): one thread per candidate on its host keyframe
+__global__ void k_immature_init(int n, const float4 *img, int w, const float *u, const float *v, TraceSettingsDev S, float *color8,
+                                float *weights8, float *gradH4, float *energyTH) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g00 = 0, g01 = 0, g10 = 0, g11 = 0;
+    bool bad = false;
+    for (int idx = 0; idx < 8 && !bad; idx++) {
+        const float x = u[i] + c_trace_pattern[idx][0], y = v[i] + c_trace_pattern[idx][1];
+        // getInterpolatedElement33BiLin (GlobalFuncs.h:185-207)
+        const int ix = (int) x, iy = (int) y;
+        const float4 *bp = img + ix + iy * w;
+        const float tl = bp[0].x, tr = bp[1].x, bl = bp[w].x, br = bp[w + 1].x;
+        const float dx = x - ix, dy = y - iy;
+        const float topInt = dx * tr + (1 - dx) * tl, botInt = dx * br + (1 - dx) * bl;
+        const float leftInt = dy * bl + (1 - dy) * tl, rightInt = dy * br + (1 - dy) * tr;
+        const float c = dx * rightInt + (1 - dx) * leftInt, gx = rightInt - leftInt, gy = botInt - topInt;
+        color8[8 * i + idx] = c;
+        if (!isfinite(c)) { bad = true; break; }
+        g00 += gx * gx; g01 += gx * gy; g10 += gy * gx; g11 += gy * gy;
+        weights8[8 * i + idx] = sqrtf(S.outlierTHSumComponent / (S.outlierTHSumComponent + (gx * gx + gy * gy)));
+    }
+    gradH4[4 * i] = g00; gradH4[4 * i + 1] = g01; gradH4[4 * i + 2] = g10; gradH4[4 * i + 3] = g11;
+    float e = 8 * S.outlierTH;
+    e *= S.overallEnergyTHWeight * S.overallEnergyTHWeight;
+    energyTH[i] = bad ? NAN : e;
+}
+
+#define KTR_WARPS 8
+__global__ void __launch_bounds__(32 * KTR_WARPS) k_trace_on(TraceArgs A) {
+    __shared__ float s_err[KTR_WARPS][100];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * KTR_WARPS + wib;
+    if (i >= A.n) return;
+    const unsigned FULL = 0xffffffffu;
+    const TraceSettingsDev &S = A.S;
+    int st = A.status[i];
+    if (st == IPS_OOB) return;                                                   // :52
+    const int w = A.w, h = A.h;
+    const float pu = A.u[i], pv = A.v[i];
+    float idmin = A.idepth_min[i], idmax = A.idepth_max[i], quality = A.quality[i];
+    const float *KRKi = A.KRKi9 + 9 * A.host[i], *Kt = A.Kt3 + 3 * A.host[i], *aff = A.aff2 + 2 * A.host[i];
+    const float maxPixSearch = (w + h) * S.maxPixSearch;
+    float uvx = -1.f, uvy = -1.f, interval = 0.f;
+    int result = -1;          // >= 0: finished with this status
+#define TR_RETURN(status_, ux_, uy_, iv_) do { result = (status_); uvx = (ux_); uvy = (uy_); interval = (iv_); } while (0)
+
+    float pr[3], ptpMin[3], ptpMax[3];
+    for (int k = 0; k < 3; k++) pr[k] = KRKi[k * 3 + 0] * pu + KRKi[k * 3 + 1] * pv + KRKi[k * 3 + 2] * 1.0f;
+    for (int k = 0; k < 3; k++) ptpMin[k] = pr[k] + Kt[k] * idmin;
+    float uMin = ptpMin[0] / ptpMin[2], vMin = ptpMin[1] / ptpMin[2];
+    float dist = 0.f, uMax = 0.f, vMax = 0.f;
+    if (!(uMin > 4 && vMin > 4 && uMin < w - 5 && vMin < h - 5)) TR_RETURN(IPS_OOB, -1.f, -1.f, 0.f);
+    if (result < 0) {
+        if (isfinite(idmax)) {                                                   // :77-98
+            for (int k = 0; k < 3; k++) ptpMax[k] = pr[k] + Kt[k] * idmax;
+            uMax = ptpMax[0] / ptpMax[2]; vMax = ptpMax[1] / ptpMax[2];
+            if (!(uMax > 4 && vMax > 4 && uMax < w - 5 && vMax < h - 5)) TR_RETURN(IPS_OOB, -1.f, -1.f, 0.f);
+            else {
+                dist = (uMin - uMax) * (uMin - uMax) + (vMin - vMax) * (vMin - vMax);
+                dist = sqrtf(dist);
+                if (dist < S.trace_slackInterval) TR_RETURN(IPS_SKIPPED, (uMax + uMin) * 0.5f, (vMax + vMin) * 0.5f, dist);
+            }
+        } else {                                                                 // :99-124
+            dist = maxPixSearch;
+            for (int k = 0; k < 3; k++) ptpMax[k] = pr[k] + Kt[k] * 0.01f;
+            uMax = ptpMax[0] / ptpMax[2]; vMax = ptpMax[1] / ptpMax[2];
+            const float ddx = uMax - uMin, ddy = vMax - vMin;
+            const float d = 1.0f / sqrtf(ddx * ddx + ddy * ddy);
+            uMax = uMin + dist * ddx * d;
+            vMax = vMin + dist * ddy * d;
+            if (!(uMax > 4 && vMax > 4 && uMax < w - 5 && vMax < h - 5)) TR_RETURN(IPS_OOB, -1.f, -1.f, 0.f);
+        }
+    }
+    if (result < 0 && !(idmin < 0 || (ptpMin[2] > 0.75f && ptpMin[2] < 1.5f))) TR_RETURN(IPS_OOB, -1.f, -1.f, 0.f);   // :127-131
+
+    float dx = 0.f, dy = 0.f, errorInPixel = 0.f;
+    if (result < 0) {                                                            // :134-148
+        const float *G = A.gradH4 + 4 * i;
+        dx = S.trace_stepsize * (uMax - uMin);
+        dy = S.trace_stepsize * (vMax - vMin);
+        const float a = (dx * G[0] + dy * G[2]) * dx + (dx * G[1] + dy * G[3]) * dy;
+        const float b = (dy * G[0] + (-dx) * G[2]) * dy + (dy * G[1] + (-dx) * G[3]) * (-dx);
+        errorInPixel = 0.2f + 0.2f * (a + b) / a;
+        if (errorInPixel * S.trace_minImprovementFactor > dist && isfinite(idmax)) TR_RETURN(IPS_BADCONDITION, (uMax + uMin) * 0.5f, (vMax + vMin) * 0.5f, dist);
+        if (errorInPixel > 10) errorInPixel = 10;
+    }
+    float bestU = 0.f, bestV = 0.f, bestEnergy = 1e10f;
+    float rx = 0.f, ry = 0.f, col = 0.f, wgt = 0.f;        // lane < 8: rotated pattern offset, colour, weight of pattern pixel `lane`
+    if (result < 0) {                                                            // :151-217 discrete search
+        dx /= dist;
+        dy /= dist;
+        if (dist > maxPixSearch) {
+            uMax = uMin + maxPixSearch * dx;
+            vMax = vMin + maxPixSearch * dy;
+            dist = maxPixSearch;
+        }
+        int numSteps = 1.9999f + dist / S.trace_stepsize;
+        const float randShift = uMin * 1000 - floorf(uMin * 1000);
+        const float ptx0 = uMin - randShift * dx, pty0 = vMin - randShift * dy;
+        if (!isfinite(dx) || !isfinite(dy)) TR_RETURN(IPS_OOB, -1.f, -1.f, 0.f);
+        else {
+            if (lane < 8) {
+                rx = KRKi[0] * c_trace_pattern[lane][0] + KRKi[1] * c_trace_pattern[lane][1];
+                ry = KRKi[3] * c_trace_pattern[lane][0] + KRKi[4] * c_trace_pattern[lane][1];
+                col = A.color8[8 * i + lane]; wgt = A.weights8[8 * i + lane];
+            }
+            if (numSteps >= 100) numSteps = 99;
+            // every lane needs all 8 pattern offsets / colours for its own steps
+            float prx[8], pry[8], pcol[8];
+#pragma unroll
+            for (int idx = 0; idx < 8; idx++) { prx[idx] = __shfl_sync(FULL, rx, idx); pry[idx] = __shfl_sync(FULL, ry, idx); pcol[idx] = __shfl_sync(FULL, col, idx); }
+            float ptx = ptx0, pty = pty0;
+            for (int k = 0; k < lane; k++) { ptx += dx; pty += dy; }             // the reference's running sum, replayed
+            float myBestE = 1e10f, myBestU = 0.f, myBestV = 0.f;
+            int myBestI = 1 << 30;
+            for (int s0 = 0; s0 < numSteps; s0 += 32) {
+                const int si = s0 + lane;
+                if (si < numSteps) {
+                    float energy = 0;
+#pragma unroll
+                    for (int idx = 0; idx < 8; idx++) {
+                        const float hit = trace_tap1(A.img, w, h, ptx + prx[idx], pty + pry[idx]);
+                        if (!isfinite(hit)) { energy += 1e5f; continue; }
+                        const float residual = hit - (aff[0] * pcol[idx] + aff[1]);
+                        const float hw = fabsf(residual) < S.huberTH ? 1 : S.huberTH / fabsf(residual);
+                        energy += hw * residual * residual * (2 - hw);
+                    }
+                    s_err[wib][si] = energy;
+                    if (energy < myBestE) { myBestE = energy; myBestU = ptx; myBestV = pty; myBestI = si; }
+                }
+                for (int k = 0; k < 32; k++) { ptx += dx; pty += dy; }
+            }
+            // first index of the minimum (the reference's strict `<` scan)
+            float be = myBestE; int bi = myBestI;
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oe = __shfl_xor_sync(FULL, be, o); const int oi = __shfl_xor_sync(FULL, bi, o);
+                if (oe < be || (oe == be && oi < bi)) { be = oe; bi = oi; }
+            }
+            const int src = bi & 31;        // lane that evaluated step bi (bi = 1<<30 only if no step beat 1e10: src 0, bestIdx -1)
+            int bestIdx = (bi == (1 << 30)) ? -1 : bi;
+            bestEnergy = (bestIdx < 0) ? 1e10f : be;
+            bestU = __shfl_sync(FULL, (myBestI == bi) ? myBestU : 0.f, src);
+            bestV = __shfl_sync(FULL, (myBestI == bi) ? myBestV : 0.f, src);
+            if (bestIdx < 0) { bestU = 0.f; bestV = 0.f; }
+            __syncwarp();
+            float second = 1e10f;                                                // :220-227
+            for (int si = lane; si < numSteps; si += 32)
+                if ((si < bestIdx - S.minTraceTestRadius || si > bestIdx + S.minTraceTestRadius) && s_err[wib][si] < second) second = s_err[wib][si];
+            for (int o = 16; o > 0; o >>= 1) second = fminf(second, __shfl_xor_sync(FULL, second, o));
+            const float newQuality = second / bestEnergy;
+            if (newQuality < quality || numSteps > 10) quality = newQuality;
+        }
+    }
+    if (result < 0) {                                                            // :231-278 GN optimisation
+        float uBak = bestU, vBak = bestV, stepBack = 0;
+        const float gnstepsize = 1;
+        if (S.trace_GNIterations > 0) bestEnergy = 1e5f;
+        for (int it = 0; it < S.trace_GNIterations; it++) {
+            float tH = 0.f, tb = 0.f, te = 0.f;
+            int valid = 0;
+            if (lane < 8) {
+                const float3 hit = trace_tap3(A.img, w, h, bestU + rx, bestV + ry);
+                if (isfinite(hit.x)) {
+                    valid = 1;
+                    const float residual = hit.x - (aff[0] * col + aff[1]);
+                    const float dResdDist = dx * hit.y + dy * hit.z;
+                    const float hw = fabsf(residual) < S.huberTH ? 1 : S.huberTH / fabsf(residual);
+                    tH = hw * dResdDist * dResdDist;
+                    tb = hw * residual * dResdDist;
+                    te = wgt * wgt * hw * residual * residual * (2 - hw);
+                }
+            }
+            float H = 1, b = 0, energy = 0;
+#pragma unroll
+            for (int idx = 0; idx < 8; idx++) {
+                const int vd = __shfl_sync(FULL, valid, idx);
+                const float xH = __shfl_sync(FULL, tH, idx), xb = __shfl_sync(FULL, tb, idx), xe = __shfl_sync(FULL, te, idx);
+                if (!vd) { energy += 1e5f; continue; }
+                H += xH; b += xb; energy += xe;
+            }
+            if (energy > bestEnergy) {
+                stepBack *= 0.5f;
+                bestU = uBak + stepBack * dx;
+                bestV = vBak + stepBack * dy;
+            } else {
+                float step = -gnstepsize * b / H;
+                if (step < -0.5f) step = -0.5f;
+                else if (step > 0.5f) step = 0.5f;
+                if (!isfinite(step)) step = 0;
+                uBak = bestU; vBak = bestV; stepBack = step;
+                bestU += step * dx;
+                bestV += step * dy;
+                bestEnergy = energy;
+            }
+            if (fabsf(stepBack) < S.trace_GNThreshold) break;
+        }
+        if (!(bestEnergy < A.energyTH[i] * S.trace_extraSlackOnTH)) {            // :281-288
+            TR_RETURN((st == IPS_OUTLIER) ? IPS_OOB : IPS_OUTLIER, -1.f, -1.f, 0.f);
+        } else {                                                                 // :291-313
+            if (dx * dx > dy * dy) {
+                idmin = (pr[2] * (bestU - errorInPixel * dx) - pr[0]) / (Kt[0] - Kt[2] * (bestU - errorInPixel * dx));
+                idmax = (pr[2] * (bestU + errorInPixel * dx) - pr[0]) / (Kt[0] - Kt[2] * (bestU + errorInPixel * dx));
+            } else {
+                idmin = (pr[2] * (bestV - errorInPixel * dy) - pr[1]) / (Kt[1] - Kt[2] * (bestV - errorInPixel * dy));
+                idmax = (pr[2] * (bestV + errorInPixel * dy) - pr[1]) / (Kt[1] - Kt[2] * (bestV + errorInPixel * dy));
+            }
+            if (idmin > idmax) { const float t = idmin; idmin = idmax; idmax = t; }
+            if (!isfinite(idmin) || !isfinite(idmax) || (idmax < 0)) TR_RETURN(IPS_OUTLIER, -1.f, -1.f, 0.f);
+            else TR_RETURN(IPS_GOOD, bestU, bestV, 2 * errorInPixel);
+        }
+    }
+#undef TR_RETURN
+    if (lane == 0) {
+        A.status[i] = result;
+        A.idepth_min[i] = idmin; A.idepth_max[i] = idmax; A.quality[i] = quality;
+        A.uv2[2 * i] = uvx; A.uv2[2 * i + 1] = uvy; A.interval[i] = interval;
+    }
+}

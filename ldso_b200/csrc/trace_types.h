@@ -1,0 +1,28 @@
+// Types and launchers of the immature-point kernels (trace.cu). trace.cu is its own translation unit because it is compiled
+// with -fmad=false: ImmaturePoint::traceOn takes discrete decisions (best epipolar step, status thresholds) on float sums, so
+// the kernel keeps the reference's separate multiply / add roundings instead of nvcc's contracted FMAs.
+#pragma once
+#include "common.cuh"
+
+struct TraceSettingsDev {      // Setting.cc:28,39,41,52,76,81,89-94
+    float maxPixSearch, outlierTH, outlierTHSumComponent, huberTH, overallEnergyTHWeight;
+    int minTraceTestRadius, trace_GNIterations;
+    float trace_stepsize, trace_GNThreshold, trace_extraSlackOnTH, trace_slackInterval, trace_minImprovementFactor;
+};
+enum { IPS_GOOD = 0, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED };   // ImmaturePoint.h:31-38
+
+struct TraceArgs {
+    int n, w, h;
+    const float4 *img;                 // level 0 of the frame traced on: (I, dx, dy, 0)
+    const float *u, *v, *color8, *weights8, *gradH4, *energyTH;
+    const int *host;
+    const float *KRKi9, *Kt3, *aff2;   // per host keyframe
+    float *idepth_min, *idepth_max, *quality;
+    int *status;
+    float *uv2, *interval;
+    TraceSettingsDev S;
+};
+
+void launch_immature_init(int n, const float4 *img, int w, const float *u, const float *v, const TraceSettingsDev &S, float *color8,
+                          float *weights8, float *gradH4, float *energyTH, cudaStream_t stream);
+void launch_trace_on(const TraceArgs &A, cudaStream_t stream);

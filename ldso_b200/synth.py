@@ -302,3 +302,43 @@ def make_track_pair(w=640, h=480, n_pts=2000, seed=7, K=None) -> TrackPair:
     HdiF = rng.uniform(1e-4, 1e-2, n_pts).astype(np.float32)
     return TrackPair(w=w, h=h, levels=levels, K=K, ref_pyr=make_images(ref, levels), new_pyr=make_images(new, levels),
                      ref_aff=ref_aff, new_aff_true=new_aff, R_true=R_rn, t_true=t_rn, cpt=cpt, HdiF=HdiF)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# immature-point tracing: FullSystem::traceNewCoarse's inputs for a synthetic window
+@dataclasses.dataclass
+class TraceCase:
+    w: int
+    h: int
+    n: int
+    u: np.ndarray            # (n,) f32 candidate pixels on their host keyframes (integer positions like the pixel selector's)
+    v: np.ndarray
+    host: np.ndarray         # (n,) i32 host keyframe index
+    KRKi: np.ndarray         # (nF, nF, 3, 3) f32: KRKi[new, host]  (FullSystem.cc:1027-1029)
+    Kt: np.ndarray           # (nF, nF, 3) f32
+    aff: np.ndarray          # (nF, nF, 2) f32  AffLight::fromToVecExposure(host, new) with exposures 1
+
+
+def make_trace_case(win: Window, n_per_host=200, seed=5, hosts=None) -> TraceCase:
+    rng = np.random.default_rng(seed)
+    nF = win.nF
+    hosts = list(range(nF - 2)) if hosts is None else list(hosts)
+    K32 = np.array([[win.K[0], 0, win.K[2]], [0, win.K[1], win.K[3]], [0, 0, 1]], np.float32)
+    Ki32 = np.linalg.inv(K32.astype(np.float64)).astype(np.float32)
+    ab = np.stack([win.state_zero[:, 6] * SCALE_A, win.state_zero[:, 7] * SCALE_B], axis=1)
+    KRKi = np.zeros((nF, nF, 3, 3), np.float32); Kt = np.zeros((nF, nF, 3), np.float32); aff = np.zeros((nF, nF, 2), np.float32)
+    for new in range(nF):
+        for h in range(nF):
+            R = (win.Rcw[new] @ win.Rcw[h].T)
+            t = win.tcw[new] - R @ win.tcw[h]
+            KRKi[new, h] = (K32 @ R.astype(np.float32)) @ Ki32
+            Kt[new, h] = K32 @ t.astype(np.float32)
+            a = np.exp(ab[new, 0] - ab[h, 0])
+            aff[new, h] = [a, ab[new, 1] - a * ab[h, 1]]
+    us, vs, hs = [], [], []
+    for h in hosts:
+        us.append(rng.integers(20, win.w - 20, n_per_host).astype(np.float32))
+        vs.append(rng.integers(20, win.h - 20, n_per_host).astype(np.float32))
+        hs.append(np.full(n_per_host, h, np.int32))
+    return TraceCase(w=win.w, h=win.h, n=n_per_host * len(hosts), u=np.concatenate(us), v=np.concatenate(vs), host=np.concatenate(hs),
+                     KRKi=KRKi, Kt=Kt, aff=aff)

@@ -3,6 +3,7 @@
 // bench.py's cpu_baseline / --impl reference legs can drive it. Nothing in ldso_b200/ may load this.
 #include "ba.h"
 #include "tracker.h"
+#include "trace.h"
 #include <chrono>
 
 using namespace oracle;
@@ -358,6 +359,38 @@ int oracle_tracker_track(void *o, double R[9], double t[3], float *aff_a, float 
     memcpy(lastFlowIndicators, T->lastFlowIndicators, 24);
     if (n_evals) *n_evals = T->lm_iterations_total;
     return ok ? 1 : 0;
+}
+
+// ---- immature-point trace (ImmaturePoint ctor + traceOn, FullSystem::traceNewCoarse's loop) ----------------------------
+// candidate construction on the host keyframe: colour[8], weights[8], gradH[4], energyTH per point
+void oracle_trace_init(const float *dI_host, int w, int n, const float *u, const float *v, float *color8, float *weights8,
+                       float *gradH4, float *energyTH) {
+    TraceSettings S;
+    for (int i = 0; i < n; i++) {
+        ImmaturePt p;
+        immature_init(p, dI_host, w, u[i], v[i], S);
+        memcpy(color8 + 8 * i, p.color, 32); memcpy(weights8 + 8 * i, p.weights, 32); memcpy(gradH4 + 4 * i, p.gradH, 16);
+        energyTH[i] = p.energyTH;
+    }
+}
+// one traceNewCoarse pass over n candidates; KRKi9/Kt3/aff2 are per host keyframe (row-major 3x3). In/out: idepth_min,
+// idepth_max, quality, status; out: lastTraceUV[2], lastTracePixelInterval.
+void oracle_trace_on(const float *dI, int w, int h, int n, const float *u, const float *v, const float *color8, const float *weights8,
+                     const float *gradH4, const float *energyTH, const int *host, const float *KRKi9, const float *Kt3,
+                     const float *aff2, float *idepth_min, float *idepth_max, float *quality, int *status, float *uv2, float *interval) {
+    TraceSettings S;
+    for (int i = 0; i < n; i++) {
+        ImmaturePt p;
+        p.u = u[i]; p.v = v[i];
+        memcpy(p.color, color8 + 8 * i, 32); memcpy(p.weights, weights8 + 8 * i, 32); memcpy(p.gradH, gradH4 + 4 * i, 16);
+        p.energyTH = energyTH[i]; p.quality = quality[i]; p.idepth_min = idepth_min[i]; p.idepth_max = idepth_max[i];
+        p.lastTraceStatus = status[i];
+        p.lastTraceUV[0] = uv2[2 * i]; p.lastTraceUV[1] = uv2[2 * i + 1]; p.lastTracePixelInterval = interval[i];
+        const int hh = host[i];
+        trace_on(p, dI, w, h, KRKi9 + 9 * hh, Kt3 + 3 * hh, aff2 + 2 * hh, S);
+        idepth_min[i] = p.idepth_min; idepth_max[i] = p.idepth_max; quality[i] = p.quality; status[i] = p.lastTraceStatus;
+        uv2[2 * i] = p.lastTraceUV[0]; uv2[2 * i + 1] = p.lastTraceUV[1]; interval[i] = p.lastTracePixelInterval;
+    }
 }
 
 }  // extern "C"

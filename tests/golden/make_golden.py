@@ -36,6 +36,16 @@ def main():
     ok, R, t, a, bb, lr, lf, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
     np.savez_compressed(os.path.join(HERE, "tracker_small.npz"), res0=res, H0=H, b0=b, R=R, t=t, aff=np.array([a, bb]), lastResiduals=lr,
                         lastFlow=lf, n_evals=ne)
+    # immature-point trace: two traceNewCoarse passes over 150 candidates per host keyframe
+    wt = synth.make_window(nF=6, pts_per_frame=10, w=320, h=240, seed=3)
+    case = synth.make_trace_case(wt, 150, seed=5)
+    tr = oracle_py.OracleTrace(wt, case)
+    st1 = tr.trace_on(wt.nF - 2)
+    imin1, imax1 = tr.idepth_min.copy(), tr.idepth_max.copy()
+    st2 = tr.trace_on(wt.nF - 1)
+    np.savez_compressed(os.path.join(HERE, "trace_small.npz"), color=tr.color, weights=tr.weights, gradH=tr.gradH, status1=st1, status2=st2,
+                        idepth_min1=imin1, idepth_max1=imax1, idepth_min2=tr.idepth_min, idepth_max2=tr.idepth_max, quality=tr.quality,
+                        uv=tr.uv, interval=tr.interval)
     print("golden written")
 
 

@@ -260,3 +260,38 @@ class OracleTracker:
         ok = self.L.oracle_tracker_track(self.o, _d(R), _d(t), C.byref(a), C.byref(b), coarsest, _d(mr), _d(lr), _d(lf),
                                          C.byref(ne))
         return bool(ok), R, t, a.value, b.value, lr, lf, ne.value
+
+
+# ---- immature-point trace (oracle/trace.cc) -------------------------------------------------------------
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
+class OracleTrace:
+    """ImmaturePoint candidates of a synth.TraceCase and FullSystem::traceNewCoarse passes over them."""
+
+    def __init__(self, win, case):
+        self.L = lib()
+        self.win, self.case = win, case
+        n = case.n
+        self.color = np.zeros((n, 8), np.float32); self.weights = np.zeros((n, 8), np.float32)
+        self.gradH = np.zeros((n, 4), np.float32); self.energyTH = np.zeros(n, np.float32)
+        for h in np.unique(case.host):
+            m = np.nonzero(case.host == h)[0]
+            dI = np.ascontiguousarray(win.pyramids[h][0], np.float32)
+            u = np.ascontiguousarray(case.u[m]); v = np.ascontiguousarray(case.v[m])
+            c = np.zeros((len(m), 8), np.float32); wt = np.zeros((len(m), 8), np.float32); g = np.zeros((len(m), 4), np.float32)
+            e = np.zeros(len(m), np.float32)
+            self.L.oracle_trace_init(_f(dI), win.w, len(m), _f(u), _f(v), _f(c), _f(wt), _f(g), _f(e))
+            self.color[m], self.weights[m], self.gradH[m], self.energyTH[m] = c, wt, g, e
+        self.idepth_min = np.zeros(n, np.float32); self.idepth_max = np.full(n, np.nan, np.float32)
+        self.quality = np.full(n, 10000.0, np.float32); self.status = np.full(n, IPS_UNINITIALIZED, np.int32)
+        self.uv = np.zeros((n, 2), np.float32); self.interval = np.zeros(n, np.float32)
+
+    def trace_on(self, new):
+        c, win = self.case, self.win
+        dI = np.ascontiguousarray(win.pyramids[new][0], np.float32)
+        KRKi = np.ascontiguousarray(c.KRKi[new]); Kt = np.ascontiguousarray(c.Kt[new]); aff = np.ascontiguousarray(c.aff[new])
+        self.L.oracle_trace_on(_f(dI), win.w, win.h, c.n, _f(c.u), _f(c.v), _f(self.color), _f(self.weights), _f(self.gradH),
+                               _f(self.energyTH), c.host.ctypes.data_as(c_ip), _f(KRKi), _f(Kt), _f(aff), _f(self.idepth_min),
+                               _f(self.idepth_max), _f(self.quality), self.status.ctypes.data_as(c_ip), _f(self.uv), _f(self.interval))
+        return self.status.copy()

@@ -260,3 +260,31 @@ def test_marginalize_frame_prior():
         assert np.array_equal(Hn, Hn.T)
         x_full = np.linalg.solve(H, b)
         assert rel_err(np.linalg.solve(Hn, bn), x_full[:nd]) < 1e-6
+
+
+def test_trace_immature_oracle():
+    """ImmaturePoint construction + traceOn (oracle/trace.cc): frozen outputs, and what the search is for — after two traces the
+    true inverse depth of a well-traced candidate lies inside its [idepth_min, idepth_max] interval."""
+    win = synth.make_window(nF=6, pts_per_frame=10, w=320, h=240, seed=3)
+    case = synth.make_trace_case(win, 150, seed=5)
+    tr = oracle_py.OracleTrace(win, case)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_small.npz"))
+    assert np.array_equal(tr.color, g["color"]) and np.array_equal(tr.gradH, g["gradH"])
+    st1 = tr.trace_on(win.nF - 2)
+    assert np.array_equal(st1, g["status1"])
+    assert np.array_equal(tr.idepth_min, g["idepth_min1"]) and np.array_equal(tr.idepth_max, g["idepth_max1"], equal_nan=True)
+    st2 = tr.trace_on(win.nF - 1)
+    assert np.array_equal(st2, g["status2"]) and np.array_equal(tr.idepth_max, g["idepth_max2"], equal_nan=True)
+    good = st2 == oracle_py.IPS_GOOD
+    assert good.sum() > 0.4 * case.n
+    idt = np.zeros(case.n)
+    for h in np.unique(case.host):
+        m = case.host == h
+        _, _, depth, _ = synth.scene_depth(win.Rcw[h], win.tcw[h], win.K, case.u[m].astype(float), case.v[m].astype(float))
+        idt[m] = 1.0 / depth
+    inside = (tr.idepth_min <= idt) & (idt <= tr.idepth_max)
+    assert inside[good].mean() > 0.8
+    # a candidate that left the image stays out
+    oob = st2 == oracle_py.IPS_OOB
+    st3 = tr.trace_on(win.nF - 1)
+    assert np.all(st3[oob] == oracle_py.IPS_OOB)
