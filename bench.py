@@ -251,6 +251,9 @@ def run_ours(args):
     if world == 1:
         e2e = run_e2e(ctx, win, args, torch)
 
+    trace_extra = None
+    if world == 1:
+        trace_extra = run_trace(ctx, win)
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
     # max over ranks
@@ -298,6 +301,8 @@ def run_ours(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if trace_extra is not None:
+        line["extra_trace_immature"] = trace_extra
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(win)
     print(json.dumps(line), flush=True)
@@ -325,6 +330,42 @@ def run_e2e(ctx, win, args, torch):
                    "lastHS/lastbS/lastX, point idepth/step/HdiF, residual states+energies; host wall clock"}
 
 
+def _trace_inputs(win):
+    from ldso_b200 import synth
+    case = synth.make_trace_case(win, 250, seed=5, hosts=range(win.nF - 2))          # 1500 candidates, what LDSO keeps per frame
+    return case
+
+
+def run_trace(ctx, win):
+    """SURVEY 8f rank 2 (not the headline metric): one FullSystem::traceNewCoarse pass = ImmaturePoint::traceOn of 1500 candidates on
+    the newest keyframe, through the C ABI from host arrays (uploads, kernel, read-back inside the timed region)."""
+    case = _trace_inputs(win)
+    init = {k: [] for k in ("color", "weights", "gradH", "energyTH")}
+    for h in range(win.nF - 2):
+        m = case.host == h
+        r = ctx.immature_init(h, case.u[m], case.v[m])
+        for k in init:
+            init[k].append(r[k])
+    init = {k: np.concatenate(v) for k, v in init.items()}
+    n = case.n
+    new = win.nF - 1
+
+    def fresh():
+        return dict(u=case.u, v=case.v, host=case.host, **init, idepth_min=np.zeros(n, np.float32), idepth_max=np.full(n, np.nan, np.float32),
+                    quality=np.full(n, 10000.0, np.float32), status=np.full(n, 5, np.int32), uv=np.zeros((n, 2), np.float32),
+                    interval=np.zeros(n, np.float32))
+    for _ in range(3):
+        ctx.trace_immature(new, fresh(), case.KRKi[new], case.Kt[new], case.aff[new])
+    reps = 20
+    states = [fresh() for _ in range(reps)]
+    t0 = time.perf_counter()
+    for p in states:
+        ctx.trace_immature(new, p, case.KRKi[new], case.Kt[new], case.aff[new])
+    dt = (time.perf_counter() - t0) / reps
+    return {"candidates": n, "ms_per_pass": 1e3 * dt, "candidates_per_s": n / dt, "good": int((states[-1]["status"] == 0).sum()),
+            "def": "ImmaturePoint::traceOn of 1500 fresh candidates (unbounded idepth interval: full epipolar search) on one frame, host arrays in/out"}
+
+
 def cpu_baseline(win):
     from tests import oracle_py
     o = oracle_py.OracleBA(win, threads_mode=6, fast=True)
@@ -332,7 +373,13 @@ def cpu_baseline(win):
     for i in range(3):
         o.gn_iteration(i)
     sec = o.time_gn(40, 3)
-    return {"value": 1.0 / sec, "unit": "GN-iters/s", "cores": 6, "kind": "port",
+    case = _trace_inputs(win)
+    tr = oracle_py.OracleTrace(win, case)
+    t0 = time.perf_counter()
+    tr.trace_on(win.nF - 1)
+    trace_ms = 1e3 * (time.perf_counter() - t0)
+    return {"trace_immature_ms_per_pass_1core": trace_ms,
+            "value": 1.0 / sec, "unit": "GN-iters/s", "cores": 6, "kind": "port",
             "sample": f"median of 40 full GN iterations of the same 8 KF x 2000 point window; oracle port "
                       f"(g++ -O3 -march=native), 6 worker threads = reference NUM_THREADS, host has {os.cpu_count()} cores"}
 
