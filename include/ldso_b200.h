@@ -263,6 +263,16 @@ int ldso_b200_immature_init(ldso_b200_ctx *ctx, int host_slot, int n, const floa
 int ldso_b200_trace_immature(ldso_b200_ctx *ctx, int new_slot, const ldso_b200_immature *pts, int n_hosts, const float *KRKi9,
                              const float *Kt3, const float *aff2);
 
+/* FullSystem::optimizeImmaturePoint (FullSystem.cc:892-978, with ImmaturePoint::linearizeResidual, ImmaturePoint.cc:316-383) for n
+ * candidates against the device-resident window (set_frames: frame states, calibration, images; the candidates' hosts index
+ * those frames): Levenberg-Marquardt on the inverse depth starting from (idepth_min + idepth_max)/2. ok[i] != 0 means the
+ * reference would have created the PointHessian (finite depth, Hdd >= setting_minIdepthH_act, >= min_obs residuals IN);
+ * idepth[i] is its idepth (= idepth_zero); res_state[i*nFrames + t] is the final ResState of the residual to frame t (0 IN, 1 OOB,
+ * 2 OUTLIER; 255 for the host itself) - every residual left IN becomes a PointFrameResidual (:995-1008). */
+int ldso_b200_optimize_immature(ldso_b200_ctx *ctx, int n, const float *u, const float *v, const int32_t *host, const float *idepth_min,
+                                const float *idepth_max, const float *color8, const float *weights8, const float *energyTH, int min_obs,
+                                int32_t *ok, float *idepth, uint8_t *res_state);
+
 /* ---- coarse tracker (src/frontend/CoarseTracker.cc) ---------------------------------------------------- */
 /* CoarseTracker::makeK (:219-246) */
 int ldso_b200_tracker_make_k(ldso_b200_ctx *ctx, float fx, float fy, float cx, float cy);

@@ -65,7 +65,7 @@ SYMBOLS = [
     "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
-    "ldso_b200_trace_immature", "ldso_b200_tracker_make_k",
+    "ldso_b200_trace_immature", "ldso_b200_optimize_immature", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
     "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
 ]
@@ -432,6 +432,17 @@ class Context:
         p.lastTracePixelInterval = _f(pts["interval"])
         self._chk(self.L.ldso_b200_trace_immature(self.ctx, int(new_slot), C.byref(p), int(keep["K"].shape[0]), _f(keep["K"]), _f(keep["t"]),
                                                   _f(keep["a"])))
+
+    def optimize_immature(self, u, v, host, idepth_min, idepth_max, color, weights, energyTH, min_obs=1):
+        """FullSystem::optimizeImmaturePoint for every candidate against the device-resident frames: (ok, idepth, res_state[n, nF])."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        u, v, imin, imax, col, wts, eth = map(f32, (u, v, idepth_min, idepth_max, color, weights, energyTH))
+        host = np.ascontiguousarray(host, np.int32)
+        n = u.shape[0]
+        ok = np.zeros(n, np.int32); idepth = np.zeros(n, np.float32); states = np.zeros((n, max(self.nF, 1)), np.uint8)
+        self._chk(self.L.ldso_b200_optimize_immature(self.ctx, n, _f(u), _f(v), _i(host), _f(imin), _f(imax), _f(col), _f(wts), _f(eth), int(min_obs),
+                                                     _i(ok), _f(idepth), _b(states)))
+        return ok, idepth, states
 
     def tracker_make_k(self, fx, fy, cx, cy):
         self._chk(self.L.ldso_b200_tracker_make_k(self.ctx, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))

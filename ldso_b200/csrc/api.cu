@@ -1067,6 +1067,35 @@ extern "C" int ldso_b200_trace_immature(ldso_b200_ctx *c, int new_slot, const ld
     return LDSO_B200_OK;
 }
 
+extern "C" int ldso_b200_optimize_immature(ldso_b200_ctx *c, int n, const float *u, const float *v, const int32_t *host, const float *idepth_min,
+                                           const float *idepth_max, const float *color8, const float *weights8, const float *energyTH,
+                                           int min_obs, int32_t *ok, float *idepth, uint8_t *res_state) {
+    if (!c || n < 0) return LDSO_B200_ERR_ARG;
+    if (!c->have_frames) return c->fail(LDSO_B200_ERR_STATE, "optimize_immature needs set_frames first");
+    if (n == 0) return LDSO_B200_OK;
+    if (!u || !v || !host || !idepth_min || !idepth_max || !color8 || !weights8 || !energyTH || !ok || !idepth || !res_state)
+        return c->fail(LDSO_B200_ERR_ARG, "null candidate array");
+    const int nF = c->nF;
+    if (nF < 2) return c->fail(LDSO_B200_ERR_STATE, "optimize_immature needs at least two frames");
+    for (int i = 0; i < n; i++) if (host[i] < 0 || host[i] >= nF) return c->fail(LDSO_B200_ERR_ARG, "candidate host index out of range");
+    cudaSetDevice(c->device);
+    const size_t N = (size_t) n;
+    const size_t nf = N * (2 + 2 + 8 + 8 + 1) + N /*host*/ + N /*ok*/ + N /*idepth*/ + (N * nF + 3) / 4 + 4;
+    RET_IF(trace_reserve(c, sizeof(float) * nf));
+    float *q = (float *) c->trace_buf;
+    float *du = q; q += N; float *dv = q; q += N; float *dmin = q; q += N; float *dmax = q; q += N; float *dc = q; q += 8 * N; float *dw = q; q += 8 * N;
+    float *de = q; q += N; int *dh = (int *) q; q += N; int *dok = (int *) q; q += N; float *did = q; q += N; unsigned char *dst = (unsigned char *) q;
+#define TR_H2D(dst_, src_, bytes_) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst_, src_, bytes_, cudaMemcpyHostToDevice, c->stream))
+    TR_H2D(du, u, 4 * N); TR_H2D(dv, v, 4 * N); TR_H2D(dmin, idepth_min, 4 * N); TR_H2D(dmax, idepth_max, 4 * N); TR_H2D(dc, color8, 32 * N);
+    TR_H2D(dw, weights8, 32 * N); TR_H2D(de, energyTH, 4 * N); TR_H2D(dh, host, 4 * N);
+#undef TR_H2D
+    launch_optimize_immature(n, c->ws_dev, du, dv, dh, dmin, dmax, dc, dw, de, min_obs, dok, did, dst, c->stream);
+    LAUNCH_CHECK(c);
+    D2H(ok, dok, 4 * N); D2H(idepth, did, 4 * N); D2H(res_state, dst, N * nF);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- fused loop
 static const int K1_FUSED = K1F_LINEARIZE | K1F_ACCUMULATE | K1F_APPLY_RES;
 

@@ -8,3 +8,9 @@ void launch_immature_init(int n, const float4 *img, int w, const float *u, const
 void launch_trace_on(const TraceArgs &A, cudaStream_t stream) {
     k_trace_on<<<(A.n + KTR_WARPS - 1) / KTR_WARPS, 32 * KTR_WARPS, 0, stream>>>(A);
 }
+void launch_optimize_immature(int n, const WinState *ws, const float *u, const float *v, const int *host, const float *idmin, const float *idmax,
+                              const float *color8, const float *weights8, const float *energyTH, int minObs, int *ok, float *idepth,
+                              unsigned char *res_state, cudaStream_t stream) {
+    k_optimize_immature<<<(n + KTR_WARPS - 1) / KTR_WARPS, 32 * KTR_WARPS, 0, stream>>>(n, ws, u, v, host, idmin, idmax, color8, weights8, energyTH,
+                                                                                      minObs, ok, idepth, res_state);
+}

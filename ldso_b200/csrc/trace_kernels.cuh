@@ -248,3 +248,152 @@ __global__ void __launch_bounds__(32 * KTR_WARPS) k_trace_on(TraceArgs A) {
         A.uv2[2 * i] = uvx; A.uv2[2 * i + 1] = uvy; A.interval[i] = interval;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// FullSystem::optimizeImmaturePoint (src/frontend/FullSystem.cc:892-978) with ImmaturePoint::linearizeResidual
+// (ImmaturePoint.cc:316-383): Levenberg-Marquardt on the inverse depth of a candidate over its residuals to all other
+// keyframes of the device-resident window (frame-pair records, calibration and images as the GN loop left them).
+// One warp per candidate: lane = (residual, pattern pixel) in two rounds of 32; the per-pixel terms are then folded by all
+// lanes in the reference's order (residual by residual, pixel by pixel, stopping a residual at its first out-of-bounds pixel
+// exactly like the early return of linearizeResidual, partial Hdd/bd contributions included).
+#define RS_IN_ 0
+#define RS_OOB_ 1
+#define RS_OUTLIER_ 2
+struct ImmatureEval { float E, H, B; int ns[MAXF - 1]; float ne[MAXF - 1]; };
+
+__device__ __forceinline__ void immature_eval(const WinState *ws, int nF, int host, float pu, float pv, const float *col8, const float *w8,
+                                              float energyTH, float idepth, float slack, const int *st, const float *en, ImmatureEval &R) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, nres = nF - 1;
+    int okp[2]; float ep[2], hp[2], bp[2];
+    const CalibDev &C = ws->calib;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        const int q = 32 * pass + lane, r = q >> 3, idx = q & 7;
+        okp[pass] = 0; ep[pass] = 0.f; hp[pass] = 0.f; bp[pass] = 0.f;
+        if (r < nres) {
+            const int t = (r < host) ? r : r + 1;
+            const PairRecFull &pf = ws->pairFull[host + nF * t];
+            const float *aff = ws->pair[host + nF * t].aff;
+            const int dx = c_trace_pattern[idx][0], dy = c_trace_pattern[idx][1];
+            // projectPoint (ResidualProjections.h:57-84)
+            const float k0 = (pu + dx - C.cxl) * C.fxli, k1 = (pv + dy - C.cyl) * C.fyli, k2 = 1;
+            float ptp[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                float s = pf.RTll[a * 3 + 0] * k0;
+                s += pf.RTll[a * 3 + 1] * k1;
+                s += pf.RTll[a * 3 + 2] * k2;
+                ptp[a] = s + pf.tTll[a] * idepth;
+            }
+            const float drescale = 1.0f / ptp[2];
+            if (drescale > 0) {
+                const float uu = ptp[0] * drescale, vv = ptp[1] * drescale;
+                const float Ku = uu * C.fxl + C.cxl, Kv = vv * C.fyl + C.cyl;
+                if (Ku > 1.1f && Kv > 1.1f && Ku < ws->wM3G && Kv < ws->hM3G) {
+                    const float3 hit = trace_tap3(ws->img0[t], ws->w, ws->h, Ku, Kv);
+                    if (isfinite(hit.x)) {
+                        const float residual = hit.x - (aff[0] * col8[idx] + aff[1]);
+                        float hw = fabsf(residual) < ws->S.huberTH ? 1 : ws->S.huberTH / fabsf(residual);
+                        ep[pass] = w8[idx] * w8[idx] * hw * residual * residual * (2 - hw);
+                        const float dxInterp = hit.y * C.fxl, dyInterp = hit.z * C.fyl;
+                        const float d_idepth = (dxInterp * drescale * (pf.tTll[0] - pf.tTll[2] * uu) + dyInterp * drescale * (pf.tTll[1] - pf.tTll[2] * vv)) * SCALE_IDEPTH;
+                        hw *= w8[idx] * w8[idx];
+                        hp[pass] = (hw * d_idepth) * d_idepth;
+                        bp[pass] = (hw * residual) * d_idepth;
+                        okp[pass] = 1;
+                    }
+                }
+            }
+        }
+    }
+    R.E = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAXF - 1; r++) {
+        float el = 0.f;
+        bool broke = false;
+#pragma unroll
+        for (int idx = 0; idx < 8; idx++) {
+            const int q = r * 8 + idx, src = q & 31, pass = q >> 5;         // compile-time
+            const int ok = __shfl_sync(FULL, okp[pass], src);
+            const float e = __shfl_sync(FULL, ep[pass], src), hd = __shfl_sync(FULL, hp[pass], src), bd = __shfl_sync(FULL, bp[pass], src);
+            if (r < nres && st[r] != RS_OOB_ && !broke) {
+                if (!ok) broke = true;
+                else { el += e; R.H += hd; R.B += bd; }
+            }
+        }
+        if (r < nres) {
+            float ret;
+            if (st[r] == RS_OOB_ || broke) { R.ns[r] = RS_OOB_; R.ne[r] = en[r]; ret = en[r]; }     // state_NewEnergy untouched on these paths
+            else {
+                if (el > energyTH * slack) { el = energyTH * slack; R.ns[r] = RS_OUTLIER_; }
+                else R.ns[r] = RS_IN_;
+                R.ne[r] = el;
+                ret = el;
+            }
+            R.E += ret;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * KTR_WARPS) k_optimize_immature(int n, const WinState *ws, const float *u, const float *v, const int *host,
+                                                                      const float *idmin, const float *idmax, const float *color8,
+                                                                      const float *weights8, const float *energyTH, int minObs, int *ok_out,
+                                                                      float *idepth_out, unsigned char *res_state) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * KTR_WARPS + wib;
+    if (i >= n) return;
+    const int nF = ws->nF, nres = nF - 1, h = host[i];
+    const float setting_minIdepthH_act = 100;          // Setting.cc:25
+    const int setting_GNItsOnPointActivation = 3;      // Setting.cc:47
+    float col8[8], w8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { col8[k] = color8[8 * i + k]; w8[k] = weights8[8 * i + k]; }
+    const float pu = u[i], pv = v[i], eTH = energyTH[i];
+    int st[MAXF - 1]; float en[MAXF - 1];
+#pragma unroll
+    for (int r = 0; r < MAXF - 1; r++) { st[r] = RS_IN_; en[r] = 0.f; }
+    float currentIdepth = (idmax[i] + idmin[i]) * 0.5f;
+    ImmatureEval R;
+    R.H = 0.f; R.B = 0.f;
+    immature_eval(ws, nF, h, pu, pv, col8, w8, eTH, currentIdepth, 1000.f, st, en, R);
+    float lastEnergy = R.E, lastHdd = R.H, lastbd = R.B;
+#pragma unroll
+    for (int r = 0; r < MAXF - 1; r++) if (r < nres) { st[r] = R.ns[r]; en[r] = R.ne[r]; }
+    bool success = true;
+    if (!isfinite(lastEnergy) || lastHdd < setting_minIdepthH_act) success = false;
+    if (success) {
+        float lambda = 0.1f;
+        for (int iteration = 0; iteration < setting_GNItsOnPointActivation; iteration++) {
+            float H = lastHdd;
+            H *= 1 + lambda;
+            const float step = (float) ((1.0 / (double) H) * (double) lastbd);
+            const float newIdepth = currentIdepth - step;
+            R.H = 0.f; R.B = 0.f;
+            immature_eval(ws, nF, h, pu, pv, col8, w8, eTH, newIdepth, 1.f, st, en, R);
+            if (!isfinite(lastEnergy) || R.H < setting_minIdepthH_act) { success = false; break; }
+            if (R.E < lastEnergy) {
+                currentIdepth = newIdepth;
+                lastHdd = R.H; lastbd = R.B; lastEnergy = R.E;
+#pragma unroll
+                for (int r = 0; r < MAXF - 1; r++) if (r < nres) { st[r] = R.ns[r]; en[r] = R.ne[r]; }
+                lambda = (float) ((double) lambda * 0.5);
+            } else {
+                lambda *= 5;
+            }
+            if ((double) fabsf(step) < 0.0001 * (double) currentIdepth) break;
+        }
+    }
+    if (success && !isfinite(currentIdepth)) success = false;
+    int numGoodRes = 0;
+#pragma unroll
+    for (int r = 0; r < MAXF - 1; r++) if (r < nres && st[r] == RS_IN_) numGoodRes++;
+    if (success && numGoodRes < minObs) success = false;
+    if (lane == 0) {
+        ok_out[i] = success ? 1 : 0;
+        idepth_out[i] = currentIdepth;
+        for (int t = 0; t < nF; t++) res_state[(size_t) i * nF + t] = 255;
+#pragma unroll
+        for (int r = 0; r < MAXF - 1; r++) if (r < nres) res_state[(size_t) i * nF + ((r < h) ? r : r + 1)] = (unsigned char) st[r];
+    }
+}

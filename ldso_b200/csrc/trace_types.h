@@ -26,3 +26,6 @@ struct TraceArgs {
 void launch_immature_init(int n, const float4 *img, int w, const float *u, const float *v, const TraceSettingsDev &S, float *color8,
                           float *weights8, float *gradH4, float *energyTH, cudaStream_t stream);
 void launch_trace_on(const TraceArgs &A, cudaStream_t stream);
+void launch_optimize_immature(int n, const WinState *ws, const float *u, const float *v, const int *host, const float *idmin, const float *idmax,
+                              const float *color8, const float *weights8, const float *energyTH, int minObs, int *ok, float *idepth,
+                              unsigned char *res_state, cudaStream_t stream);

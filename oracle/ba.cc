@@ -1562,6 +1562,102 @@ void Window::marginalizeFramePrior(int idx) {
     bM = bn;
 }
 
+// ImmaturePoint::linearizeResidual — src/internal/ImmaturePoint.cc:316-383 (the temporary residual is (state, energy, newState, newEnergy))
+namespace {
+struct TmpRes { int state_state, state_NewState; float state_energy, state_NewEnergy; };
+}
+static double immatureLinearizeResidual(const Window &W, const Window::ImmatureCand &c, int target, float outlierTHSlack, TmpRes &tr,
+                                        float &Hdd, float &bd, float idepth) {
+    if (tr.state_state == RS_OOB) { tr.state_NewState = RS_OOB; return tr.state_energy; }
+    const FramePrecalc &pc = W.frames[c.host].targetPrecalc[target];
+    const float *dIl = W.frames[target].dI;
+    float energyLeft = 0;
+    const float *affLL = pc.PRE_aff_mode;
+    for (int idx = 0; idx < patternNum; idx++) {
+        int dx = patternP[idx][0], dy = patternP[idx][1];
+        float drescale, u, v, new_idepth, Ku, Kv, KliP[3];
+        if (!projectPointB(c.u, c.v, idepth, dx, dy, W.HCalib, pc.PRE_RTll, pc.PRE_tTll, W.wM3G, W.hM3G, drescale, u, v, Ku, Kv, KliP, new_idepth)) {
+            tr.state_NewState = RS_OOB;
+            return tr.state_energy;
+        }
+        float hitColor[3];
+        getInterpolatedElement33(dIl, Ku, Kv, W.frames[target].w, hitColor);
+        if (!std::isfinite((float) hitColor[0])) { tr.state_NewState = RS_OOB; return tr.state_energy; }
+        float residual = hitColor[0] - (affLL[0] * c.color[idx] + affLL[1]);
+        float hw = fabsf(residual) < W.S.huberTH ? 1 : W.S.huberTH / fabsf(residual);
+        energyLeft += c.weights[idx] * c.weights[idx] * hw * residual * residual * (2 - hw);
+        // depth derivatives (derive_idepth, ResidualProjections.h:12-18)
+        float dxInterp = hitColor[1] * W.HCalib.fxl();
+        float dyInterp = hitColor[2] * W.HCalib.fyl();
+        float d_idepth = (dxInterp * drescale * (pc.PRE_tTll[0] - pc.PRE_tTll[2] * u) + dyInterp * drescale * (pc.PRE_tTll[1] - pc.PRE_tTll[2] * v)) * SCALE_IDEPTH;
+        hw *= c.weights[idx] * c.weights[idx];
+        Hdd += (hw * d_idepth) * d_idepth;
+        bd += (hw * residual) * d_idepth;
+    }
+    if (energyLeft > c.energyTH * outlierTHSlack) {
+        energyLeft = c.energyTH * outlierTHSlack;
+        tr.state_NewState = RS_OUTLIER;
+    } else {
+        tr.state_NewState = RS_IN;
+    }
+    tr.state_NewEnergy = energyLeft;
+    return energyLeft;
+}
+
+// FullSystem::optimizeImmaturePoint — src/frontend/FullSystem.cc:892-978 (the part that decides; building the PointHessian and its
+// residual objects, :980-1009, is the caller's bookkeeping: every residual left IN becomes a PointFrameResidual)
+bool Window::optimizeImmaturePoint(const ImmatureCand &c, int minObs, float &idepth_out, unsigned char *res_state) {
+    const float setting_minIdepthH_act = 100;          // Setting.cc:25
+    const int setting_GNItsOnPointActivation = 3;      // Setting.cc:47
+    const int nFr = (int) frames.size();
+    std::vector<TmpRes> residuals;
+    std::vector<int> targets;
+    for (int t = 0; t < nFr; t++) {
+        res_state[t] = 255;
+        if (t != c.host) { residuals.push_back({RS_IN, RS_OUTLIER, 0.f, 0.f}); targets.push_back(t); }
+    }
+    const int nres = (int) residuals.size();
+    auto publish = [&]() { for (int i = 0; i < nres; i++) res_state[targets[i]] = (unsigned char) residuals[i].state_state; };
+    float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+    float currentIdepth = (c.idepth_max + c.idepth_min) * 0.5f;
+    for (int i = 0; i < nres; i++) {
+        lastEnergy += immatureLinearizeResidual(*this, c, targets[i], 1000, residuals[i], lastHdd, lastbd, currentIdepth);
+        residuals[i].state_state = residuals[i].state_NewState;
+        residuals[i].state_energy = residuals[i].state_NewEnergy;
+    }
+    idepth_out = currentIdepth;
+    if (!std::isfinite(lastEnergy) || lastHdd < setting_minIdepthH_act) { publish(); return false; }
+    float lambda = 0.1;
+    for (int iteration = 0; iteration < setting_GNItsOnPointActivation; iteration++) {
+        float H = lastHdd;
+        H *= 1 + lambda;
+        float step = (1.0 / H) * lastbd;
+        float newIdepth = currentIdepth - step;
+        float newHdd = 0, newbd = 0, newEnergy = 0;
+        for (int i = 0; i < nres; i++)
+            newEnergy += immatureLinearizeResidual(*this, c, targets[i], 1, residuals[i], newHdd, newbd, newIdepth);
+        if (!std::isfinite(lastEnergy) || newHdd < setting_minIdepthH_act) { idepth_out = currentIdepth; publish(); return false; }
+        if (newEnergy < lastEnergy) {
+            currentIdepth = newIdepth;
+            lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+            for (int i = 0; i < nres; i++) {
+                residuals[i].state_state = residuals[i].state_NewState;
+                residuals[i].state_energy = residuals[i].state_NewEnergy;
+            }
+            lambda *= 0.5;
+        } else {
+            lambda *= 5;
+        }
+        if (fabsf(step) < 0.0001 * currentIdepth) break;
+    }
+    idepth_out = currentIdepth;
+    publish();
+    if (!std::isfinite(currentIdepth)) return false;
+    int numGoodRes = 0;
+    for (int i = 0; i < nres; i++) if (residuals[i].state_state == RS_IN) numGoodRes++;
+    return numGoodRes >= minObs;
+}
+
 template void Window::topAddPoint<0>(AccumulatedTopHessianSSE &, Point &, int);
 template void Window::topAddPoint<1>(AccumulatedTopHessianSSE &, Point &, int);
 template void Window::topAddPoint<2>(AccumulatedTopHessianSSE &, Point &, int);

@@ -306,6 +306,10 @@ struct Window {
     // marginalisation algebra
     void marginalizePointsF(const std::vector<int> &pointIdx);   // EnergyFunctional.cc:165-222
     void marginalizeFramePrior(int idx);                         // EnergyFunctional.cc:72-129 (HM, bM algebra only)
+    // immature-point activation: ImmaturePoint::linearizeResidual (ImmaturePoint.cc:316-383) and
+    // FullSystem::optimizeImmaturePoint (FullSystem.cc:892-978). res_state: one entry per frame (255 for the host itself).
+    struct ImmatureCand { float u, v, idepth_min, idepth_max, energyTH; float color[8], weights[8]; int host; };
+    bool optimizeImmaturePoint(const ImmatureCand &c, int minObs, float &idepth_out, unsigned char *res_state);
 };
 
 // bilinear sampler, GlobalFuncs.h:89-103

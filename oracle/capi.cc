@@ -393,4 +393,19 @@ void oracle_trace_on(const float *dI, int w, int h, int n, const float *u, const
     }
 }
 
+// FullSystem::optimizeImmaturePoint for n candidates against the window's frames (current states). ok[n], idepth[n],
+// res_state[n * nFrames] (ResState per target frame, 255 for the host).
+void oracle_ba_optimize_immature(void *o, int n, const float *u, const float *v, const int *host, const float *idepth_min,
+                                 const float *idepth_max, const float *color8, const float *weights8, const float *energyTH, int minObs,
+                                 int *ok, float *idepth, unsigned char *res_state) {
+    Window *W = (Window *) o;
+    const int nF = (int) W->frames.size();
+    for (int i = 0; i < n; i++) {
+        Window::ImmatureCand c;
+        c.u = u[i]; c.v = v[i]; c.host = host[i]; c.idepth_min = idepth_min[i]; c.idepth_max = idepth_max[i]; c.energyTH = energyTH[i];
+        memcpy(c.color, color8 + 8 * i, 32); memcpy(c.weights, weights8 + 8 * i, 32);
+        ok[i] = W->optimizeImmaturePoint(c, minObs, idepth[i], res_state + (size_t) i * nF) ? 1 : 0;
+    }
+}
+
 }  // extern "C"

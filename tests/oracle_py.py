@@ -141,6 +141,17 @@ class OracleBA:
         self.L.oracle_ba_get_marg_prior(self.o, _d(HM), _d(bM))
         return HM, bM
 
+    def optimize_immature(self, u, v, host, idepth_min, idepth_max, color, weights, energyTH, min_obs=1):
+        """FullSystem::optimizeImmaturePoint for every candidate against the window's current frame states."""
+        n = len(u)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        u, v, imin, imax, col, wts, eth = map(f32, (u, v, idepth_min, idepth_max, color, weights, energyTH))
+        host = np.ascontiguousarray(host, np.int32)
+        ok = np.zeros(n, np.int32); idepth = np.zeros(n, np.float32); states = np.zeros((n, self.win.nF), np.uint8)
+        self.L.oracle_ba_optimize_immature(self.o, n, _f(u), _f(v), host.ctypes.data_as(c_ip), _f(imin), _f(imax), _f(col), _f(wts), _f(eth),
+                                           int(min_obs), ok.ctypes.data_as(c_ip), _f(idepth), states.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return ok, idepth, states
+
     def marginalize_frame(self, idx):
         """EnergyFunctional::marginalizeFrame's HM/bM algebra; returns the shrunken (HM, bM)."""
         nd = int(self.L.oracle_ba_marginalize_frame(self.o, int(idx)))

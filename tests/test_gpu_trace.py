@@ -106,3 +106,39 @@ def test_trace_golden_and_edges():
     with pytest.raises(capi.Error):
         ctx.trace_immature(win.nF - 1, pts, case.KRKi[0][:1], case.Kt[0][:1], case.aff[0][:1])
     ctx.close()
+
+
+@pytest.mark.parametrize("geom", ["small", "vga"])
+def test_optimize_immature_matches_oracle(geom):
+    """FullSystem::optimizeImmaturePoint (activation LM on the inverse depth) for the candidates two traces left GOOD, against the
+    oracle on the same window state: activation decision equal for >= 99 %, idepth within 1e-4 relative and residual states equal
+    where the decision agrees."""
+    if geom == "small":
+        win = synth.make_window(nF=6, pts_per_frame=10, w=320, h=240, seed=3); per_host = 150
+    else:
+        win = synth.make_window(nF=8, pts_per_frame=10, seed=42); per_host = 250
+    case = synth.make_trace_case(win, per_host, seed=5)
+    tr = oracle_py.OracleTrace(win, case)
+    tr.trace_on(win.nF - 2); tr.trace_on(win.nF - 1)
+    m = np.isin(tr.status, [oracle_py.IPS_GOOD, oracle_py.IPS_SKIPPED, oracle_py.IPS_BADCONDITION]) & np.isfinite(tr.idepth_max)
+    args = (case.u[m], case.v[m], case.host[m], tr.idepth_min[m], tr.idepth_max[m], tr.color[m], tr.weights[m], tr.energyTH[m])
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    ctx = capi.Context(win.w, win.h, win.levels)
+    ctx.load_synth_window(win)
+    for min_obs in (1, 3):
+        oko, ido, sto = o.optimize_immature(*args, min_obs=min_obs)
+        okg, idg, stg = ctx.optimize_immature(*args, min_obs=min_obs)
+        same = okg == oko
+        assert same.mean() >= 0.99, (geom, min_obs, okg.sum(), oko.sum())
+        act = same & (oko == 1)
+        assert act.sum() > 0.5 * m.sum()
+        d = np.abs(idg[act] - ido[act]) / np.abs(ido[act])
+        assert np.median(d) < 1e-6 and np.quantile(d, 0.99) < 1e-4, (np.median(d), np.quantile(d, 0.99))
+        assert (stg[act] == sto[act]).mean() >= 0.999
+    # edge cases: empty batch; host index out of range
+    ok0, _, _ = ctx.optimize_immature(*(a[:0] for a in args))
+    assert ok0.shape == (0,)
+    bad = list(args); bad[2] = np.full_like(args[2], win.nF)
+    with pytest.raises(capi.Error):
+        ctx.optimize_immature(*bad)
+    ctx.close()
