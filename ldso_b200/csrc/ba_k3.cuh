@@ -186,7 +186,6 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {      // low word
     return __hiloint2double(hi, lo);
 }
 __device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int lane) {
-    const unsigned FULL = 0xffffffffu;
     double a[K3_NB];
     const int row = lane & 7;
 #pragma unroll
@@ -216,7 +215,6 @@ __device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, in
 
 // z <- L11^{-1} z for the unit-lower block at (k0,k0); one warp, lane c holds z[k0+c]
 __device__ __forceinline__ void trsv_lower_warp(const double *A, double *v, int k0, int bs, int lane) {
-    const unsigned FULL = 0xffffffffu;
     const int c = lane & 7;
     double Lr[K3_NB];
 #pragma unroll
@@ -231,7 +229,6 @@ __device__ __forceinline__ void trsv_lower_warp(const double *A, double *v, int 
 }
 // x <- L11^{-T} x
 __device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, int k0, int bs, int lane) {
-    const unsigned FULL = 0xffffffffu;
     const int c = lane & 7;
     double Lc[K3_NB];
 #pragma unroll

@@ -466,3 +466,9 @@ def test_marginalize_frame_and_prior_persistence(small_win):
         H4, b4 = ctx.marg_prior()                                                      # unrelated dimension: cleared
         assert not H4.any() and not b4.any()
         ctx.close()
+
+
+def test_graft_entry_smoke():
+    """The driver's smoke() entry point (one small window through the fused path, checked against the oracle)."""
+    import __graft_entry__
+    __graft_entry__.smoke()
