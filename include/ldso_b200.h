@@ -184,6 +184,29 @@ int ldso_b200_optimize_begin(ldso_b200_ctx *ctx, double *energy_out);
  * first_iteration.. are passed to solveSystemF (orthogonalize from iteration 2). Asynchronous on the
  * context's stream; results are fetched with the getters below (which synchronise). */
 int ldso_b200_gn_iterations(ldso_b200_ctx *ctx, int first_iteration, int n_iterations);
+/* ---- one call per keyframe optimisation, from host buffers ------------------------------------------------
+ * What FullSystem::optimize does around the loop, as ONE call: (optionally) the newest keyframe's raw image -> device
+ * makeImages, set_frames, set_window, the optimize() prologue, n_iterations Gauss-Newton iterations, and the read-back of the
+ * results. The library orders the work itself: the image copy is queued first and travels while the host packs the
+ * window; nothing blocks before the final wait. Inputs must stay valid until the call returns (they always do: it
+ * returns after the read-back). Any output pointer may be NULL. Equivalent to the individual calls in that order. */
+typedef struct ldso_b200_fused_io {
+    int image_slot;                 /* slot of `image` (ignored when image == NULL) */
+    const float *image;             /* w*h raw irradiance of the newest keyframe (pinned memory copies fastest), or NULL */
+    int nFrames;
+    const ldso_b200_frame_state *frames;
+    const double *calib_value_scaled, *calib_value_zero;    /* [4] each */
+    const ldso_b200_window *window;
+    int first_iteration, n_iterations;
+    /* outputs */
+    double *lastHS, *lastbS, *lastX;                 /* (8nF+4)^2 column-major, 8nF+4, 8nF+4 */
+    double *energy; int *canbreak;                   /* lastEnergyP of the final linearisation, canbreak of the last step */
+    float *pt_idepth, *pt_step, *pt_HdiF;            /* [nPoints] */
+    uint8_t *res_state, *res_new_state;              /* [nResiduals] */
+    float *res_energy;                               /* [nResiduals] */
+} ldso_b200_fused_io;
+int ldso_b200_optimize_from_host(ldso_b200_ctx *ctx, const ldso_b200_fused_io *io);
+
 /* Multi-GPU: points are sharded over ranks (one context per GPU), frames/images replicated. A GN
  * iteration is split around the ONE collective: gn_phase_a(iteration) runs [solve + frame step of `iteration`
  * (skipped when iteration < 0 = the optimize() prologue)] + resubstitute/linearize/accumulate on this rank's

@@ -45,6 +45,13 @@ class ImmatureC(C.Structure):
                 ("lastTraceUV2", c_fp), ("lastTracePixelInterval", c_fp)]
 
 
+class FusedIOC(C.Structure):
+    _fields_ = [("image_slot", C.c_int), ("image", c_fp), ("nFrames", C.c_int), ("frames", C.c_void_p), ("calib_value_scaled", c_dp),
+                ("calib_value_zero", c_dp), ("window", C.c_void_p), ("first_iteration", C.c_int), ("n_iterations", C.c_int),
+                ("lastHS", c_dp), ("lastbS", c_dp), ("lastX", c_dp), ("energy", c_dp), ("canbreak", c_ip), ("pt_idepth", c_fp),
+                ("pt_step", c_fp), ("pt_HdiF", c_fp), ("res_state", c_bp), ("res_new_state", c_bp), ("res_energy", c_fp)]
+
+
 class FrameStateC(C.Structure):
     _fields_ = [("evalR", C.c_double * 9), ("evalT", C.c_double * 3), ("state_zero", C.c_double * 10),
                 ("state", C.c_double * 10), ("ab_exposure", C.c_float), ("frameEnergyTH", C.c_float),
@@ -62,7 +69,7 @@ SYMBOLS = [
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_optimize_begin",
-    "ldso_b200_gn_iterations", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
+    "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
     "ldso_b200_trace_immature", "ldso_b200_optimize_immature", "ldso_b200_tracker_make_k",
@@ -537,6 +544,24 @@ class StepIO:
                           sum(k[x].nbytes for x in ("pt_host", "pt_u", "pt_v", "pt_idepth", "pt_idepth_zero", "pt_has_prior",
                                                     "pt_color", "pt_weights", "res_begin", "res_target")))
         self.d2h_bytes = sum(v.nbytes for v in o.values())
+
+    def fused(self, iteration=0, n_iterations=1):
+        """The same step as upload() + step() + download(), as ONE C-ABI call (ldso_b200_optimize_from_host)."""
+        if not hasattr(self, "_io"):
+            io = self._io = FusedIOC()
+            o = self.out
+            self._scal = (np.zeros(1), np.zeros(1, np.int32))
+            io.image_slot = self.nF - 1; io.image = self._color; io.nFrames = self.nF
+            io.frames = C.cast(self._frames, C.c_void_p); io.calib_value_scaled = self._Ks; io.calib_value_zero = self._Kz
+            io.window = C.cast(C.pointer(self.w), C.c_void_p)
+            io.lastHS, io.lastbS, io.lastX = self._sol
+            io.energy = _d(self._scal[0]); io.canbreak = _i(self._scal[1])
+            io.pt_idepth = _f(o["idepth"]); io.pt_step = _f(o["step"]); io.pt_HdiF = _f(o["HdiF"])
+            io.res_state = _b(o["state_state"]); io.res_new_state = _b(o["state_NewState"]); io.res_energy = _f(o["state_energy"])
+        self._io.first_iteration = int(iteration); self._io.n_iterations = int(n_iterations)
+        self.ctx._chk(self.L.ldso_b200_optimize_from_host(self.h, C.byref(self._io)))
+        self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
+        return self.out
 
     def upload(self):
         """newest keyframe's raw image (+ device makeImages), frame states, the whole window"""

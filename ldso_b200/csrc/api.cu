@@ -338,7 +338,7 @@ extern "C" int ldso_b200_upload_frame(ldso_b200_ctx *c, int slot, const float *c
     return LDSO_B200_OK;
 }
 
-extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *color) {
+static int make_images_impl(ldso_b200_ctx *c, int slot, const float *color, bool wait_copy) {
     if (!c || !color) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
     int rc = ensure_slot(c, slot);
@@ -353,9 +353,10 @@ extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *co
         LAUNCH_CHECK(c);
     }
     // the caller's buffer is free once the copy has landed; the pyramid kernels keep running asynchronously
-    CUDA_CHECK_RET(c, cudaEventSynchronize(c->copy_done));
+    if (wait_copy) CUDA_CHECK_RET(c, cudaEventSynchronize(c->copy_done));
     return LDSO_B200_OK;
 }
+extern "C" int ldso_b200_make_images(ldso_b200_ctx *c, int slot, const float *color) { return make_images_impl(c, slot, color, true); }
 
 extern "C" int ldso_b200_download_frame_level(ldso_b200_ctx *c, int slot, int lvl, float *out) {
     if (!c || !out || slot < 0 || slot >= NSLOTS || lvl < 0 || lvl >= c->levels || !c->img[slot][lvl]) return LDSO_B200_ERR_ARG;
@@ -1172,6 +1173,35 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         return LDSO_B200_OK;
     }
     for (int i = 0; i < n_iterations; i++) RET_IF(launch_gn_body(c));
+    return LDSO_B200_OK;
+}
+
+static int wait_results(ldso_b200_ctx *c);
+extern "C" int ldso_b200_prefetch_results(ldso_b200_ctx *c);
+extern "C" int ldso_b200_get_points(ldso_b200_ctx *c, float *idepth, float *idepth_zero, float *step, float *HdiF, float *bdSumF, float *Hdd,
+                                    float *bd, float *Hcd4);
+extern "C" int ldso_b200_get_residuals(ldso_b200_ctx *c, uint8_t *state_state, uint8_t *state_NewState, float *state_energy,
+                                       float *state_NewEnergy, float *state_NewEnergyWithOutlier, uint8_t *isActive, float *JpJdF8, float *J74,
+                                       float *projectedTo16, float *centerProjectedTo3);
+extern "C" int ldso_b200_optimize_from_host(ldso_b200_ctx *c, const ldso_b200_fused_io *io) {
+    if (!c || !io || !io->frames || !io->window || !io->calib_value_scaled || !io->calib_value_zero) return LDSO_B200_ERR_ARG;
+    if (io->n_iterations < 0) return c->fail(LDSO_B200_ERR_ARG, "negative iteration count");
+    // the image first: 1.2 MB over PCIe, in flight while the host packs the frame states and the window
+    if (io->image) RET_IF(make_images_impl(c, io->image_slot, io->image, false));
+    RET_IF(ldso_b200_set_frames(c, io->nFrames, io->frames, io->calib_value_scaled, io->calib_value_zero));
+    RET_IF(ldso_b200_set_window(c, io->window));
+    RET_IF(ldso_b200_optimize_begin(c, nullptr));
+    if (io->n_iterations > 0) RET_IF(ldso_b200_gn_iterations(c, io->first_iteration, io->n_iterations));
+    RET_IF(ldso_b200_prefetch_results(c));
+    // the two scalars ride behind the prefetch; one wait covers everything (and frees the caller's image buffer)
+    if (io->energy) CUDA_CHECK_RET(c, cudaMemcpyAsync(io->energy, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (io->canbreak) CUDA_CHECK_RET(c, cudaMemcpyAsync(io->canbreak, &c->ws_dev->canbreak, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (io->lastHS || io->lastbS || io->lastX) RET_IF(ldso_b200_get_last_solution(c, io->lastHS, io->lastbS, io->lastX));
+    if (io->pt_idepth || io->pt_step || io->pt_HdiF)
+        RET_IF(ldso_b200_get_points(c, io->pt_idepth, nullptr, io->pt_step, io->pt_HdiF, nullptr, nullptr, nullptr, nullptr));
+    if (io->res_state || io->res_new_state || io->res_energy)
+        RET_IF(ldso_b200_get_residuals(c, io->res_state, io->res_new_state, io->res_energy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
     return LDSO_B200_OK;
 }
 

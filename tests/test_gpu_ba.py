@@ -342,6 +342,10 @@ def test_stepio_prefetch_matches_getters(small_win):
         for k in ("state_state", "state_NewState", "state_energy"):
             assert np.array_equal(out[k], res[k]), k
         ref.close()
+    # the single-call form (ldso_b200_optimize_from_host) returns the same bits
+    fused = {k: v.copy() for k, v in io.fused(0, 1).items()}
+    for k in out:
+        assert np.array_equal(fused[k], out[k]), k
     # a launch after the prefetch invalidates it: the getters must return the newer state
     io.upload(); io.step(0)
     ctx.gn_iterations(1, 1)
