@@ -252,8 +252,10 @@ def run_ours(args):
         e2e = run_e2e(ctx, win, args, torch)
 
     trace_extra = None
+    big_extra = None
     if world == 1:
         trace_extra = run_trace(ctx, win)
+        big_extra = run_config3(args, torch, stream, flush)
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
     # max over ranks
@@ -303,6 +305,8 @@ def run_ours(args):
         line["e2e"] = e2e
     if trace_extra is not None:
         line["extra_trace_immature"] = trace_extra
+    if big_extra is not None:
+        line["extra_config3_single_gpu"] = big_extra
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(win)
     print(json.dumps(line), flush=True)
@@ -334,6 +338,38 @@ def run_e2e(ctx, win, args, torch):
                    "pinned memory (+device makeImages), frame states, full window; optimize prologue + 1 GN iteration; D2H "
                    "lastHS/lastbS/lastX, energy, point idepth/step/HdiF, residual states+energies; host wall clock. "
                    "value_separate_calls = the same step issued as nine individual C-ABI calls (capi.StepIO.upload/step/download)"}
+
+
+def run_config3(args, torch, stream, flush):
+    """Not the headline: BASELINE configs[2]'s window (8 KF x 20 000 points, 140 000 residuals) on ONE GPU, to show how the same
+    kernels sit against the HBM roofline once the problem is large enough to leave the launch-latency regime."""
+    from ldso_b200 import capi, synth
+    win = synth.make_window(nF=NF, pts_per_frame=2500, seed=42)
+    ctx = capi.Context(win.w, win.h, win.levels, device=torch.cuda.current_device())
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_synth_window(win)
+    ctx.optimize_begin(want_energy=False)
+    for i in range(5):
+        ctx.gn_iterations(min(i, 3), 1)
+    torch.cuda.synchronize()
+    steps = 30
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(stream); ctx.gn_iterations(3, 1); ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    t_ms = float(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    ctx.kernel_times(True)
+    for k in range(20):
+        flush.fill_(k & 0xff)
+        ctx.gn_iterations(3, 1)
+    kt = ctx.kernel_times(False)
+    hbm_peak, _ = peaks()
+    b_k1 = win.nR * (384 + 12 + 12) + win.nP * (80 + 8 + 4)
+    ach = b_k1 / (kt["k1"] * 1e-6) / 1e9 if kt["k1"] > 0 else 0.0
+    ctx.close()
+    return {"n_points": win.nP, "n_residuals": win.nR, "ms_per_step": t_ms, "gn_iters_per_s": 1e3 / t_ms, "kernel_us": kt,
+            "k1_algorithmic_bytes": b_k1, "k1_achieved_GBs": ach, "k1_roofline_frac": ach / hbm_peak}
 
 
 def _trace_inputs(win):

@@ -519,7 +519,11 @@ static int build_derived(ldso_b200_ctx *c) {
     for (int p = 0; p < nP; p++) if (c->h_pt_host[p] >= nF) return c->fail(LDSO_B200_ERR_ARG, "pt_host >= nFrames");
     for (int r = 0; r < nR; r++) if (c->h_res_target[r] >= nF) return c->fail(LDSO_B200_ERR_ARG, "res_target >= nFrames");
     // two co-resident CTAs per SM hide each other's phase latencies (K1 is a chain of short, barrier-separated phases)
-    const int target_items = 2 * std::max(c->sm_count, 1);
+    // ... and large windows are cut into whole waves of 2*SMs items (at most 64 points each: the records of an item live in
+    // shared memory), so that the last wave is as full as the first
+    const int slots = 2 * std::max(c->sm_count, 1);
+    const int waves = std::max(1, (nP + 64 * slots - 1) / (64 * slots));
+    const int target_items = waves * slots;
     int ppi = (nP + target_items - 1) / target_items;
     ppi = std::max(4, std::min(64, ppi));
     d.pts_per_item = ppi;

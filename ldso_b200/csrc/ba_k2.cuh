@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     const double *red = d.red;
     const int nBlocks = nF * nF;
     __shared__ unsigned hist[256];
+    __shared__ unsigned hist_w[K2B_THREADS / 32][256];     // per-warp histograms of the select CTA (no cross-warp contention on the hot bins)
     __shared__ unsigned sel_prefix, sel_k, sel_count;
 
     if ((int) blockIdx.x < nBlocks) {
@@ -539,11 +540,17 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         if (tid == 0) { sel_count = 0; sel_prefix = 0; }
         __syncthreads();
         unsigned cnt = 0;
-        for (int i = tid; i < N; i += K2B_THREADS) {
-            const double v = vals[i];
-            const bool ok = v >= 0.0;
-            if (insm) skey[i] = ok ? __float_as_uint((float) v) : 0x80000000u;
-            cnt += ok;
+        for (int i0 = tid; i0 < N; i0 += 8 * K2B_THREADS) {      // 8 independent loads per trip (the values come from L2 / HBM)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * K2B_THREADS; v[u] = (i < N) ? vals[i] : -1.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * K2B_THREADS;
+                const bool ok = v[u] >= 0.0;
+                if (insm && i < N) skey[i] = ok ? __float_as_uint((float) v[u]) : 0x80000000u;
+                cnt += ok;
+            }
         }
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if ((tid & 31) == 0) atomicAdd(&sel_count, cnt);
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             if (tid == 0) sel_k = (unsigned) (int) (set_thn * (float) m);
             __syncthreads();
             for (int pass = 3; pass >= 0; pass--) {
-                for (int i = tid; i < 256; i += K2B_THREADS) hist[i] = 0;
+                for (int i = tid; i < 256 * (K2B_THREADS / 32); i += K2B_THREADS) (&hist_w[0][0])[i] = 0;
                 __syncthreads();
                 const unsigned pref = sel_prefix;
                 const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
@@ -577,9 +584,17 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                     for (int u = 0; u < 4; u++) {
                         const bool act = (key[u] != 0x80000000u) && ((key[u] & himask) == pref);
                         const unsigned bin = act ? ((key[u] >> (8 * pass)) & 0xffu) : 256u;
+                        // equal bins are aggregated inside the warp first (one atomic per distinct bin), on the warp's own histogram
                         const unsigned mm = __match_any_sync(0xffffffffu, bin);
-                        if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist[bin], (unsigned) __popc(mm));
+                        if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist_w[tid >> 5][bin], (unsigned) __popc(mm));
                     }
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned t = 0;
+#pragma unroll
+                    for (int wv = 0; wv < K2B_THREADS / 32; wv++) t += hist_w[wv][tid];
+                    hist[tid] = t;
                 }
                 __syncthreads();
                 if (tid < 32) {
