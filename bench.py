@@ -118,7 +118,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "8 KF x 2000 active points (14000 residuals), 640x480, seed 42", "nF": NF, "n_points": win.nP,
-                   "n_residuals": win.nR},
+                   "n_residuals": win.nR,
+                   "value_unit_note": "iterations/s of ONE 2000-point window on the host CPU; the GPU arm's value at N GPUs counts N such "
+                                      "2000-point shards per step, so both arms are in 2000-point-window iterations per second"},
         "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": "port",
                          "sample": f"{args.steps} full GN iterations of the same window; oracle port, 6 worker threads "
                                    f"(reference NUM_THREADS) on a {cores}-core host"},
