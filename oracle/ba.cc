@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
 // CPU restatement of the reference's windowed photometric bundle-adjustment path.
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 #include "ba.h"
@@ -325,44 +325,7 @@ void Window::setPrecalcValues() {
 }
 
 // ------------------------------------------------------------------------------------------
-// projectPoint (pattern) — include/internal/ResidualProjections.h:24-33
-static inline bool projectPointA(float u_pt, float v_pt, float idepth, const float *KRKi, const float *Kt,
-                                 float wM3G, float hM3G, float &Ku, float &Kv) {
-    float ptp[3];
-    for (int i = 0; i < 3; i++) {
-        float s = KRKi[i * 3 + 0] * u_pt;
-        s += KRKi[i * 3 + 1] * v_pt;
-        s += KRKi[i * 3 + 2] * 1.0f;
-        ptp[i] = s + Kt[i] * idepth;
-    }
-    Ku = ptp[0] / ptp[2];
-    Kv = ptp[1] / ptp[2];
-    return Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
-}
-// projectPoint (centre, eval point) — ResidualProjections.h:57-84
-static inline bool projectPointB(float u_pt, float v_pt, float idepth, int dx, int dy, const Calib &HCalib,
-                                 const float *R, const float *t, float wM3G, float hM3G,
-                                 float &drescale, float &u, float &v, float &Ku, float &Kv, float KliP[3],
-                                 float &new_idepth) {
-    KliP[0] = (u_pt + dx - HCalib.cxl()) * HCalib.fxli();
-    KliP[1] = (v_pt + dy - HCalib.cyl()) * HCalib.fyli();
-    KliP[2] = 1;
-    float ptp[3];
-    for (int i = 0; i < 3; i++) {
-        float s = R[i * 3 + 0] * KliP[0];
-        s += R[i * 3 + 1] * KliP[1];
-        s += R[i * 3 + 2] * KliP[2];
-        ptp[i] = s + t[i] * idepth;
-    }
-    drescale = 1.0f / ptp[2];
-    new_idepth = idepth * drescale;
-    if (!(drescale > 0)) return false;
-    u = ptp[0] * drescale;
-    v = ptp[1] * drescale;
-    Ku = u * HCalib.fxl() + HCalib.cxl();
-    Kv = v * HCalib.fyl() + HCalib.cyl();
-    return Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
-}
+// projectPointA / projectPointB (ResidualProjections.h:24-33, :57-84) live in ba.h (also used by oracle/ref_pin)
 
 // PointFrameResidual::linearize — src/internal/Residuals.cc:13-214
 double Window::linearize(Residual &r) {
@@ -1589,7 +1552,7 @@ static double immatureLinearizeResidual(const Window &W, const Window::ImmatureC
         // depth derivatives (derive_idepth, ResidualProjections.h:12-18)
         float dxInterp = hitColor[1] * W.HCalib.fxl();
         float dyInterp = hitColor[2] * W.HCalib.fyl();
-        float d_idepth = (dxInterp * drescale * (pc.PRE_tTll[0] - pc.PRE_tTll[2] * u) + dyInterp * drescale * (pc.PRE_tTll[1] - pc.PRE_tTll[2] * v)) * SCALE_IDEPTH;
+        float d_idepth = derive_idepth(pc.PRE_tTll, u, v, dx, dy, dxInterp, dyInterp, drescale);
         hw *= c.weights[idx] * c.weights[idx];
         Hdd += (hw * d_idepth) * d_idepth;
         bd += (hw * residual) * d_idepth;

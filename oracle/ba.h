@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
 // Data records of the windowed photometric BA, restated from the reference without the
 // shared_ptr graph (indices instead):
 //   RawResidualJacobian   include/internal/RawResidualJacobian.h:13-39
@@ -311,6 +311,51 @@ struct Window {
     struct ImmatureCand { float u, v, idepth_min, idepth_max, energyTH; float color[8], weights[8]; int host; };
     bool optimizeImmaturePoint(const ImmatureCand &c, int minObs, float &idepth_out, unsigned char *res_state);
 };
+
+// projectPoint (pattern) — include/internal/ResidualProjections.h:24-33
+inline bool projectPointA(float u_pt, float v_pt, float idepth, const float *KRKi, const float *Kt,
+                                 float wM3G, float hM3G, float &Ku, float &Kv) {
+    float ptp[3];
+    for (int i = 0; i < 3; i++) {
+        float s = KRKi[i * 3 + 0] * u_pt;
+        s += KRKi[i * 3 + 1] * v_pt;
+        s += KRKi[i * 3 + 2] * 1.0f;
+        ptp[i] = s + Kt[i] * idepth;
+    }
+    Ku = ptp[0] / ptp[2];
+    Kv = ptp[1] / ptp[2];
+    return Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
+}
+// projectPoint (centre, eval point) — ResidualProjections.h:57-84
+inline bool projectPointB(float u_pt, float v_pt, float idepth, int dx, int dy, const Calib &HCalib,
+                                 const float *R, const float *t, float wM3G, float hM3G,
+                                 float &drescale, float &u, float &v, float &Ku, float &Kv, float KliP[3],
+                                 float &new_idepth) {
+    KliP[0] = (u_pt + dx - HCalib.cxl()) * HCalib.fxli();
+    KliP[1] = (v_pt + dy - HCalib.cyl()) * HCalib.fyli();
+    KliP[2] = 1;
+    float ptp[3];
+    for (int i = 0; i < 3; i++) {
+        float s = R[i * 3 + 0] * KliP[0];
+        s += R[i * 3 + 1] * KliP[1];
+        s += R[i * 3 + 2] * KliP[2];
+        ptp[i] = s + t[i] * idepth;
+    }
+    drescale = 1.0f / ptp[2];
+    new_idepth = idepth * drescale;
+    if (!(drescale > 0)) return false;
+    u = ptp[0] * drescale;
+    v = ptp[1] * drescale;
+    Ku = u * HCalib.fxl() + HCalib.cxl();
+    Kv = v * HCalib.fyl() + HCalib.cyl();
+    return Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
+}
+
+// derive_idepth — ResidualProjections.h:12-18
+inline float derive_idepth(const float t[3], float u, float v, int dx, int dy, float dxInterp, float dyInterp, float drescale) {
+    (void) dx; (void) dy;
+    return (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * SCALE_IDEPTH;
+}
 
 // bilinear sampler, GlobalFuncs.h:89-103
 inline void getInterpolatedElement33(const float *mat, float x, float y, int width, float out[3]) {

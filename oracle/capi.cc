@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
 // Flat extern "C" surface over the oracle so tests/ (ctypes), __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs can drive it. Nothing in ldso_b200/ may load this.
 #include "ba.h"

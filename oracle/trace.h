@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/ba.h). PARITY UNPINNED: the reference ships no golden vectors for this path.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/ba.h). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
 // CPU restatement of the immature-point epipolar trace of tum-vision/LDSO:
 //   ImmaturePoint::ImmaturePoint   src/internal/ImmaturePoint.cc:14-38   (colour, weights, gradH, energyTH of a candidate)
 //   ImmaturePoint::traceOn         src/internal/ImmaturePoint.cc:46-314  (epipolar search + 1-D Gauss-Newton refinement)

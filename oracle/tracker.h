@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
 // CPU restatement of the reference's coarse direct tracker:
 //   include/frontend/CoarseTracker.h:17-127, src/frontend/CoarseTracker.cc:61-246,258-632
 #pragma once
