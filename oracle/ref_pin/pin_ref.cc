@@ -4,6 +4,7 @@
 //   include/internal/OptimizationBackend/MatrixAccumulators.h   AccumulatorApprox, Accumulator9, Accumulator11, AccumulatorXX, AccumulatorX
 //   include/internal/GlobalFuncs.h                              getInterpolatedElement33 / 31 / 33BiLin
 //   include/AffLight.h                                          AffLight::fromToVecExposure
+//   src/internal/Residuals.cc (+ Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h)   PointFrameResidual::linearize, fixLinearizationF, applyRes/takeData
 //   include/internal/ResidualProjections.h                      projectPoint (both overloads), derive_idepth
 //   src/Setting.cc (+ include/Settings.h)                       every setting_* constant and the residual pattern the path reads
 // compiled UNMODIFIED against oracle/ref_shim/NumTypes.h (a stand-in for the Eigen types those headers use; Eigen3, Sophus, glog,
@@ -22,17 +23,10 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "AffLight.h"
 #include "internal/GlobalFuncs.h"
 #include "internal/OptimizationBackend/MatrixAccumulators.h"
-// ResidualProjections.h expects CalibHessian to be complete (the reference's includers pull in internal/CalibHessian.h, which drags
-// in the camera/frame classes): the accessors it calls are all it needs. The globals of GlobalCalib.h are defined below.
-namespace ldso { namespace internal {
-struct CalibHessian {
-    float fx, fy, cx, cy, fxi, fyi;
-    float fxl() const { return fx; } float fyl() const { return fy; } float cxl() const { return cx; } float cyl() const { return cy; }
-    float fxli() const { return fxi; } float fyli() const { return fyi; }
-};
-} }
+#include "../ref_shim/ref_classes.h"      // stand-ins for FrameHessian / PointHessian / CalibHessian / EnergyFunctional
+#include "internal/Residuals.h"           // the reference's own PointFrameResidual (its linearize lives in src/internal/Residuals.cc)
 #include "internal/ResidualProjections.h"
-namespace ldso { namespace internal { float wM3G, hM3G; } }
+namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
 
 static unsigned long long rng_state = 88172645463325252ull;
 static inline float frand(float lo, float hi) {
@@ -191,6 +185,143 @@ static void pin_projections() {
     CHECK(okA, "projectPoint (pattern, KRKi/Kt form)"); CHECK(okB, "projectPoint (centre, R/t/K^-1 form)"); CHECK(okD, "derive_idepth");
 }
 
+// ---- PointFrameResidual::linearize / applyRes+takeData / fixLinearizationF: the reference's src/internal/Residuals.cc itself
+extern "C" {
+void *oracle_ba_create(int w, int h, int threads_mode);
+void oracle_ba_destroy(void *o);
+void oracle_ba_set_calib(void *o, const double value_scaled[4]);
+void oracle_ba_set_calib_delta(void *o, const double delta[4]);
+int oracle_ba_add_frame(void *o, const double R[9], const double t[3], const double state_zero[10], const double state[10], float ab_exposure,
+                        int frame_id, const float *dI);
+int oracle_ba_add_point(void *o, int host, float u, float v, float idepth_zero, float idepth, int hasDepthPrior, const float color[8],
+                        const float weights[8]);
+int oracle_ba_add_residual(void *o, int point, int target);
+void oracle_ba_set_frame_energy_th(void *o, int frame, float th);
+void oracle_ba_finalize(void *o);
+}
+static void pin_linearize() {
+    using namespace ldso::internal;
+    const int w = 160, h = 120, nF = 4, nPper = 150;
+    // images: smooth texture + central-difference gradients, (I, dx, dy) AoS like FrameHessian::dI
+    std::vector<std::vector<float>> imgs(nF, std::vector<float>(3 * w * h));
+    for (int f = 0; f < nF; f++) {
+        std::vector<float> I(w * h);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++)
+            I[y * w + x] = 128.f + 60.f * sinf(0.11f * x) * cosf(0.07f * y) + 30.f * sinf(0.05f * (x + 2 * y)) + 0.3f * f;   // same scene, tiny brightness offset
+        for (int i = 0; i < w * h; i++) {
+            imgs[f][3 * i] = I[i];
+            const int x = i % w, y = i / w;
+            imgs[f][3 * i + 1] = (x > 0 && x < w - 1) ? 0.5f * (I[i + 1] - I[i - 1]) : 0.f;
+            imgs[f][3 * i + 2] = (y > 0 && y < h - 1) ? 0.5f * (I[i + w] - I[i - w]) : 0.f;
+        }
+    }
+    void *o = oracle_ba_create(w, h, 0);
+    oracle::Window *W = (oracle::Window *) o;
+    const double K[4] = {110.0, 112.0, 79.5, 59.5};
+    oracle_ba_set_calib(o, K);
+    const double cd[4] = {1e-4, -2e-4, 3e-4, 1e-4};
+    oracle_ba_set_calib_delta(o, cd);
+    for (int f = 0; f < nF; f++) {
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0.004 * f, 0.001 * f, 0.0005 * f}, sz[10] = {0}, st[10] = {0};
+        const double a = 0.002 * f;      // small rotation about y
+        R[0] = cos(a); R[2] = sin(a); R[6] = -sin(a); R[8] = cos(a);
+        sz[6] = 0.002 * f; sz[7] = 0.001 * f;
+        for (int i = 0; i < 10; i++) st[i] = sz[i];
+        for (int i = 0; i < 6; i++) st[i] += (f ? 1e-3 : 0.0) * (i + 1) * (f % 2 ? 1 : -1);
+        st[6] += f ? 1e-4 : 0; st[7] -= f ? 2e-4 : 0;
+        oracle_ba_add_frame(o, R, t, sz, st, 1.0f, f, imgs[f].data());
+        oracle_ba_set_frame_energy_th(o, f, (f == 2) ? 2000.f : 8 * 8 * 8);
+    }
+    for (int f = 0; f < nF; f++)
+        for (int k = 0; k < nPper; k++) {
+            float col[8], wt[8];
+            const float u = (float) (int) frand(3, w - 3), v = (float) (int) frand(3, h - 3);
+            for (int i = 0; i < 8; i++) {       // colour / weight of the pattern pixel on the host image (ImmaturePoint.cc:21-35), a few perturbed
+                float c3[3];
+                oracle::getInterpolatedElement33BiLin(imgs[f].data(), u + oracle_pattern(i, 0), v + oracle_pattern(i, 1), w, c3);
+                col[i] = c3[0] + ((k % 9 == 0) ? frand(-40, 40) : 0.f);
+                wt[i] = sqrtf(2500.f / (2500.f + c3[1] * c3[1] + c3[2] * c3[2]));
+            }
+            const float idz = frand(0.2f, 1.5f);
+            const int p = oracle_ba_add_point(o, f, u, v, idz, idz + frand(-0.02f, 0.02f), 0, col, wt);
+            for (int t = 0; t < nF; t++) if (t != f) oracle_ba_add_residual(o, p, t);
+        }
+    oracle_ba_finalize(o);
+    // the reference-side mirror of the window
+    wG[0] = w; hG[0] = h; wM3G = w - 3; hM3G = h - 3;
+    auto HC = std::make_shared<CalibHessian>();
+    HC->fx = W->HCalib.fxl(); HC->fy = W->HCalib.fyl(); HC->cx = W->HCalib.cxl(); HC->cy = W->HCalib.cyl();
+    HC->fxi = W->HCalib.fxli(); HC->fyi = W->HCalib.fyli();
+    std::vector<shared_ptr<FrameHessian>> FH(nF);
+    for (int f = 0; f < nF; f++) {
+        FH[f] = std::make_shared<FrameHessian>();
+        FH[f]->idx = f; FH[f]->dI = (Eigen::Vector3f *) imgs[f].data(); FH[f]->frameEnergyTH = W->frames[f].frameEnergyTH;
+        FH[f]->targetPrecalc.resize(nF);
+        for (int t = 0; t < nF; t++) {
+            const oracle::FramePrecalc &s = W->frames[f].targetPrecalc[t];
+            FrameFramePrecalc &d = FH[f]->targetPrecalc[t];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+                d.PRE_RTll(i, j) = s.PRE_RTll[i * 3 + j]; d.PRE_RTll_0(i, j) = s.PRE_RTll_0[i * 3 + j];
+                d.PRE_KRKiTll(i, j) = s.PRE_KRKiTll[i * 3 + j]; d.PRE_RKiTll(i, j) = s.PRE_RKiTll[i * 3 + j];
+            }
+            for (int i = 0; i < 3; i++) { d.PRE_tTll[i] = s.PRE_tTll[i]; d.PRE_tTll_0[i] = s.PRE_tTll_0[i]; d.PRE_KtTll[i] = s.PRE_KtTll[i]; }
+            d.PRE_aff_mode[0] = s.PRE_aff_mode[0]; d.PRE_aff_mode[1] = s.PRE_aff_mode[1]; d.PRE_b0_mode = s.PRE_b0_mode; d.distanceLL = s.distanceLL;
+        }
+    }
+    auto EF = std::make_shared<EnergyFunctional>();
+    EF->nFrames = nF;
+    std::vector<Mat18f> adHT(nF * nF);
+    for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) adHT[q][i] = W->adHTdeltaF[8 * q + i];
+    EF->adHTdeltaF = adHT.data();
+    for (int i = 0; i < 4; i++) EF->cDeltaF[i] = W->cDeltaF[i];
+    bool okRet = true, okState = true, okJ = true, okProj = true, okTake = true, okFix = true;
+    int nIn = 0, nOob = 0, nOut = 0;
+    for (size_t ri = 0; ri < W->residuals.size(); ri++) {
+        oracle::Residual &orr = W->residuals[ri];
+        const oracle::Point &op = W->points[orr.point];
+        auto PH = std::make_shared<PointHessian>();
+        PH->u = op.u; PH->v = op.v; PH->idepth_scaled = op.idepth_scaled; PH->idepth_zero_scaled = op.idepth_zero_scaled; PH->deltaF = op.deltaF;
+        memcpy(PH->color, op.color, 32); memcpy(PH->weights, op.weights, 32);
+        PointFrameResidual R(PH, FH[orr.host], FH[orr.target]);
+        R.hostIDX = orr.host; R.targetIDX = orr.target;
+        orr.hostIDX = orr.host; orr.targetIDX = orr.target;
+        const double er = R.linearize(HC);            // the reference's own code
+        const double eo = W->linearize(orr);          // the restatement
+        okRet &= memcmp(&er, &eo, 8) == 0;
+        okState &= (int) R.state_NewState == (int) orr.state_NewState && memcmp(&R.state_NewEnergy, &orr.state_NewEnergy, 8) == 0 &&
+                   memcmp(&R.state_NewEnergyWithOutlier, &orr.state_NewEnergyWithOutlier, 8) == 0;
+        nIn += R.state_NewState == ResState::IN; nOob += R.state_NewState == ResState::OOB; nOut += R.state_NewState == ResState::OUTLIER;
+        if (R.state_NewState != ResState::OOB) {
+            const RawResidualJacobian &a = *R.J; const oracle::RawResidualJacobian &b = orr.J;
+            bool j = memcmp(a.resF.d, b.resF, 32) == 0;
+            for (int k = 0; k < 2; k++) j &= memcmp(a.Jpdxi[k].d, b.Jpdxi[k], 24) == 0 && memcmp(a.Jpdc[k].d, b.Jpdc[k], 16) == 0 &&
+                                             memcmp(a.JIdx[k].d, b.JIdx[k], 32) == 0 && memcmp(a.JabF[k].d, b.JabF[k], 32) == 0;
+            j &= memcmp(a.Jpdd.d, b.Jpdd, 8) == 0;
+            const float i2[4] = {a.JIdx2(0, 0), a.JIdx2(0, 1), a.JIdx2(1, 0), a.JIdx2(1, 1)}, ji[4] = {a.JabJIdx(0, 0), a.JabJIdx(0, 1), a.JabJIdx(1, 0), a.JabJIdx(1, 1)},
+                        a2[4] = {a.Jab2(0, 0), a.Jab2(0, 1), a.Jab2(1, 0), a.Jab2(1, 1)};
+            j &= memcmp(i2, b.JIdx2, 16) == 0 && memcmp(ji, b.JabJIdx, 16) == 0 && memcmp(a2, b.Jab2, 16) == 0;
+            okJ &= j;
+            bool pj = memcmp(R.centerProjectedTo.d, orr.centerProjectedTo, 12) == 0;
+            for (int k = 0; k < 8; k++) pj &= memcmp(R.projectedTo[k].d, orr.projectedTo[k], 8) == 0;
+            okProj &= pj;
+            // applyRes(true) -> takeData, then fixLinearizationF
+            R.applyRes(true); W->applyRes(orr, true);
+            okTake &= R.isActive() == orr.isActive() && (int) R.state_state == (int) orr.state_state;
+            if (R.isActive()) {
+                okTake &= memcmp(R.JpJdF.d, orr.JpJdF, 32) == 0;
+                R.fixLinearizationF(EF); W->fixLinearizationF(orr);
+                okFix &= memcmp(R.res_toZeroF.d, orr.res_toZeroF, 32) == 0 && R.isLinearized == orr.isLinearized;
+            }
+        }
+    }
+    printf("  linearize pin: %zu residuals (%d IN, %d OUTLIER, %d OOB)\n", W->residuals.size(), nIn, nOut, nOob);
+    CHECK(nIn > 300 && nOob > 0 && nOut > 50, "linearize scenario exercises the IN, OUTLIER and OOB branches");
+    CHECK(okRet, "PointFrameResidual::linearize return value"); CHECK(okState, "linearize state_NewState / state_NewEnergy / state_NewEnergyWithOutlier");
+    CHECK(okJ, "linearize RawResidualJacobian (all 74 floats)"); CHECK(okProj, "linearize projectedTo / centerProjectedTo");
+    CHECK(okTake, "applyRes(true) + takeData (JpJdF, isActive)"); CHECK(okFix, "fixLinearizationF (res_toZeroF)");
+    oracle_ba_destroy(o);
+}
+
 static void pin_settings() {
     using namespace ldso;
     oracle::Settings S; oracle::TraceSettings T;
@@ -229,8 +360,9 @@ int main() {
     pin_samplers();
     pin_afflight();
     pin_projections();
+    pin_linearize();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc and Residuals.cc\n", checks);
     return 0;
 }

@@ -9,6 +9,7 @@
 // the reference's own NumTypes.h sits next to AffLight.h and would win the quoted-include lookup: claim its include guard
 #define LDSO_NUM_TYPES_H_
 #include <cassert>
+#include <immintrin.h>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -28,8 +29,10 @@ namespace Eigen {
 template<typename T, int R, int C> struct Matrix;
 template<typename T, int N> struct RowView { const Matrix<T, N, 1> *v; };
 
+// Eigen aligns fixed-size objects whose size is a multiple of 16 bytes to 16 bytes (SSE build); the reference's _mm_load_ps on
+// RawResidualJacobian members relies on the struct layout that follows from it
 template<typename T, int R, int C>
-struct Matrix {
+struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     T d[R * C];        // column-major like Eigen's default
     Matrix() {}
     Matrix(T a, T b) { static_assert(R * C == 2, "size"); d[0] = a; d[1] = b; }
@@ -41,6 +44,17 @@ struct Matrix {
     const T &operator[](int i) const { return d[i]; }
     void setZero() { for (int i = 0; i < R * C; i++) d[i] = T(0); }
     Matrix &operator+=(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] += o.d[i]; return *this; }
+    static Matrix Zero() { Matrix m; m.setZero(); return m; }
+    // Eigen lets a 1xN row initialise an Nx1 column (vector <- vector): EnergyFunctional::adHTdeltaF is Mat18f, read as Vec8f
+    template<int R2, int C2> Matrix(const Matrix<T, R2, C2> &o) { static_assert(R2 * C2 == R * C && (R2 == 1 || C2 == 1) && (R == 1 || C == 1), "vector copy"); for (int i = 0; i < R * C; i++) d[i] = o.d[i]; }
+    Matrix(const Matrix &) = default;
+    Matrix &operator=(const Matrix &) = default;
+    T dot(const Matrix &o) const { T s = d[0] * o.d[0]; for (int i = 1; i < R * C; i++) s += d[i] * o.d[i]; return s; }
+    template<int N> Matrix<T, N, 1> tail() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[R * C - N + i]; return o; }
+    T squaredNorm() const { T s = d[0] * d[0]; for (int i = 1; i < R * C; i++) s += d[i] * d[i]; return s; }
+    template<int N> Matrix<T, N, 1> head() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[i]; return o; }
+    template<int N> struct Seg { T *p; Seg &operator=(const Matrix<T, N, 1> &v) { for (int i = 0; i < N; i++) p[i] = v.d[i]; return *this; } };
+    template<int N> Seg<N> segment(int i0) { return Seg<N>{d + i0}; }
     RowView<T, R> transpose() const { static_assert(C == 1, "only column vectors are transposed here"); return RowView<T, R>{this}; }
 };
 template<typename T, int R, int C> inline Matrix<T, R, C> operator*(T s, const Matrix<T, R, C> &m) {
@@ -75,6 +89,13 @@ typedef Eigen::Matrix<float, 2, 1> Vec2f;
 typedef Eigen::Matrix<float, 3, 1> Vec3f;
 typedef Eigen::Matrix<unsigned char, 3, 1> Vec3b;
 typedef Eigen::Matrix<float, 3, 3> Mat33f;
+typedef Eigen::Matrix<float, 2, 2> Mat22f;
+typedef Eigen::Matrix<float, 1, 8> Mat18f;
+typedef Eigen::Matrix<float, 4, 1> Vec4f;
+typedef Eigen::Matrix<float, 6, 1> Vec6f;
+typedef Eigen::Matrix<float, 8, 1> Vec8f;
+typedef Eigen::Matrix<float, CPARS, 1> VecCf;
+typedef Eigen::Matrix<float, MAX_RES_PER_POINT, 1> VecNRf;
 typedef Eigen::Matrix<float, 9, 1> Vec9f;
 typedef Eigen::Matrix<float, 14, 1> Vec14f;
 typedef Eigen::Matrix<float, 9, 9> Mat99f;

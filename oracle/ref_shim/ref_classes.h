@@ -1,0 +1,42 @@
+// STAND-INS for the reference classes PointFrameResidual::linearize / fixLinearizationF reach into — TEST INFRASTRUCTURE ONLY
+// (see NumTypes.h in this directory). The reference's own Residuals.cc, Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h,
+// ResidualProjections.h, GlobalFuncs.h and Setting.cc are compiled UNMODIFIED; the four classes below replace
+// internal/FrameHessian.h, PointHessian.h, CalibHessian.h and OptimizationBackend/EnergyFunctional.h (whose real definitions pull
+// in OpenCV-backed Frame, Sophus, IndexThreadReduce ...) with the members those two functions read, same names and types.
+#pragma once
+#include "NumTypes.h"
+#define LDSO_FRAME_HESSIAN_H_
+#define LDSO_POINT_HESSIAN_H_
+#define LDSO_CALIB_HESSIAN_H_
+#define LDSO_ENERGY_FUNCTIONAL_H_
+namespace ldso { namespace internal {
+class FrameHessian;
+class CalibHessian;
+} }
+#include "internal/FrameFramePrecalc.h"      // the reference's own struct (PRE_* members)
+namespace ldso { namespace internal {
+class CalibHessian {          // include/internal/CalibHessian.h:39-69 (accessors only)
+public:
+    float fx = 0, fy = 0, cx = 0, cy = 0, fxi = 0, fyi = 0;
+    float fxl() const { return fx; } float fyl() const { return fy; } float cxl() const { return cx; } float cyl() const { return cy; }
+    float fxli() const { return fxi; } float fyli() const { return fyi; }
+};
+class FrameHessian {          // include/internal/FrameHessian.h:163-201 (members read by linearize)
+public:
+    int idx = 0;
+    Eigen::Vector3f *dI = nullptr;
+    std::vector<FrameFramePrecalc> targetPrecalc;
+    float frameEnergyTH = 8 * 8 * 8;
+};
+class PointHessian {          // include/internal/PointHessian.h:83-107
+public:
+    float u = 0, v = 0, idepth_scaled = 0, idepth_zero_scaled = 0, deltaF = 0;
+    float color[MAX_RES_PER_POINT], weights[MAX_RES_PER_POINT];
+};
+class EnergyFunctional {      // include/internal/OptimizationBackend/EnergyFunctional.h:152,213,222
+public:
+    int nFrames = 0;
+    Mat18f *adHTdeltaF = nullptr;
+    VecCf cDeltaF;
+};
+} }
