@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin compiles the reference's own Residuals.cc, ImmaturePoint.cc, MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc and checks linearize, traceOn, the accumulators, samplers, projections and constants bit for bit; what needs dynamic Eigen / Sophus - stitching, solve, tracker loop - is restated from the cited lines and unpinned).
 // CPU restatement of the reference's windowed photometric bundle-adjustment path.
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
 #include "ba.h"
@@ -1526,11 +1526,8 @@ void Window::marginalizeFramePrior(int idx) {
 }
 
 // ImmaturePoint::linearizeResidual — src/internal/ImmaturePoint.cc:316-383 (the temporary residual is (state, energy, newState, newEnergy))
-namespace {
-struct TmpRes { int state_state, state_NewState; float state_energy, state_NewEnergy; };
-}
-static double immatureLinearizeResidual(const Window &W, const Window::ImmatureCand &c, int target, float outlierTHSlack, TmpRes &tr,
-                                        float &Hdd, float &bd, float idepth) {
+double immatureLinearizeResidual(const Window &W, const Window::ImmatureCand &c, int target, float outlierTHSlack, TmpRes &tr,
+                                 float &Hdd, float &bd, float idepth) {
     if (tr.state_state == RS_OOB) { tr.state_NewState = RS_OOB; return tr.state_energy; }
     const FramePrecalc &pc = W.frames[c.host].targetPrecalc[target];
     const float *dIl = W.frames[target].dI;

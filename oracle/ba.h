@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin compiles the reference's own Residuals.cc, ImmaturePoint.cc, MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc and checks linearize, traceOn, the accumulators, samplers, projections and constants bit for bit; what needs dynamic Eigen / Sophus - stitching, solve, tracker loop - is restated from the cited lines and unpinned).
 // Data records of the windowed photometric BA, restated from the reference without the
 // shared_ptr graph (indices instead):
 //   RawResidualJacobian   include/internal/RawResidualJacobian.h:13-39
@@ -356,6 +356,11 @@ inline float derive_idepth(const float t[3], float u, float v, int dx, int dy, f
     (void) dx; (void) dy;
     return (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * SCALE_IDEPTH;
 }
+
+// ImmaturePointTemporaryResidual (ImmaturePoint.h:17-27) and ImmaturePoint::linearizeResidual (ImmaturePoint.cc:316-383)
+struct TmpRes { int state_state, state_NewState; float state_energy, state_NewEnergy; };
+double immatureLinearizeResidual(const Window &W, const Window::ImmatureCand &c, int target, float outlierTHSlack, TmpRes &tr,
+                                 float &Hdd, float &bd, float idepth);
 
 // bilinear sampler, GlobalFuncs.h:89-103
 inline void getInterpolatedElement33(const float *mat, float x, float y, int width, float out[3]) {

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PARTLY PINNED (oracle/ref_pin compiles the reference's own Residuals.cc, ImmaturePoint.cc, MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc and checks linearize, traceOn, the accumulators, samplers, projections and constants bit for bit; what needs dynamic Eigen / Sophus - stitching, solve, tracker loop - is restated from the cited lines and unpinned).
 // Flat extern "C" surface over the oracle so tests/ (ctypes), __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs can drive it. Nothing in ldso_b200/ may load this.
 #include "ba.h"

@@ -2,7 +2,7 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may build, load or execute anything under oracle/.
 //
-// PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned): the reference (tum-vision/LDSO) ships no golden vectors or tests for
+// PARITY PARTLY PINNED (oracle/ref_pin compiles the reference's own Residuals.cc, ImmaturePoint.cc, MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc and checks linearize, traceOn, the accumulators, samplers, projections and constants bit for bit; what needs dynamic Eigen / Sophus - stitching, solve, tracker loop - is restated from the cited lines and unpinned): the reference (tum-vision/LDSO) ships no golden vectors or tests for
 // this path and cannot be compiled here (Eigen3/glog/OpenCV/Pangolin absent). This file is a
 // dependency-free CPU restatement of the small dense-math pieces the reference takes from
 // Eigen / Sophus:

@@ -5,6 +5,7 @@
 //   include/internal/GlobalFuncs.h                              getInterpolatedElement33 / 31 / 33BiLin
 //   include/AffLight.h                                          AffLight::fromToVecExposure
 //   src/internal/Residuals.cc (+ Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h)   PointFrameResidual::linearize, fixLinearizationF, applyRes/takeData
+//   src/internal/ImmaturePoint.cc (+ ImmaturePoint.h, Feature.h)   ImmaturePoint::ImmaturePoint, traceOn, linearizeResidual
 //   include/internal/ResidualProjections.h                      projectPoint (both overloads), derive_idepth
 //   src/Setting.cc (+ include/Settings.h)                       every setting_* constant and the residual pattern the path reads
 // compiled UNMODIFIED against oracle/ref_shim/NumTypes.h (a stand-in for the Eigen types those headers use; Eigen3, Sophus, glog,
@@ -25,6 +26,7 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "internal/OptimizationBackend/MatrixAccumulators.h"
 #include "../ref_shim/ref_classes.h"      // stand-ins for FrameHessian / PointHessian / CalibHessian / EnergyFunctional
 #include "internal/Residuals.h"           // the reference's own PointFrameResidual (its linearize lives in src/internal/Residuals.cc)
+#include "internal/ImmaturePoint.h"       // the reference's own ImmaturePoint (+ Feature.h); bodies in src/internal/ImmaturePoint.cc
 #include "internal/ResidualProjections.h"
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
 
@@ -319,6 +321,66 @@ static void pin_linearize() {
     CHECK(okRet, "PointFrameResidual::linearize return value"); CHECK(okState, "linearize state_NewState / state_NewEnergy / state_NewEnergyWithOutlier");
     CHECK(okJ, "linearize RawResidualJacobian (all 74 floats)"); CHECK(okProj, "linearize projectedTo / centerProjectedTo");
     CHECK(okTake, "applyRes(true) + takeData (JpJdF, isActive)"); CHECK(okFix, "fixLinearizationF (res_toZeroF)");
+
+    // ---- ImmaturePoint: constructor, traceOn (twice, on two frames), linearizeResidual — the reference's src/internal/ImmaturePoint.cc
+    {
+        oracle::TraceSettings TS;
+        std::vector<shared_ptr<ldso::Frame>> FR(nF);
+        for (int f = 0; f < nF; f++) { FR[f] = std::make_shared<ldso::Frame>(); FR[f]->frameHessian = FH[f]; }
+        bool okCtor = true, okTrace = true, okLin = true;
+        int hist[6] = {0, 0, 0, 0, 0, 0}, nLin = 0, nLinOob = 0;
+        for (int k = 0; k < 1200; k++) {
+            const int hst = k % (nF - 1);
+            const float u = (float) (int) frand(6, w - 6), v = (float) (int) frand(6, h - 6);
+            auto feat = std::make_shared<ldso::Feature>(u, v, FR[hst]);
+            shared_ptr<CalibHessian> HCc = HC;
+            ImmaturePoint ip(FR[hst], feat, 1, HCc);                          // the reference's constructor
+            oracle::ImmaturePt op;
+            oracle::immature_init(op, imgs[hst].data(), w, u, v, TS);
+            const float g[4] = {ip.gradH(0, 0), ip.gradH(0, 1), ip.gradH(1, 0), ip.gradH(1, 1)};
+            okCtor &= memcmp(ip.color, op.color, 32) == 0 && memcmp(ip.weights, op.weights, 32) == 0 && memcmp(g, op.gradH, 16) == 0 &&
+                      memcmp(&ip.energyTH, &op.energyTH, 4) == 0;
+            if (k % 5 == 0) { ip.idepth_min = op.idepth_min = frand(0.1f, 0.6f); ip.idepth_max = op.idepth_max = ip.idepth_min + frand(0.05f, 1.2f); }
+            for (int pass = 0; pass < 2; pass++) {
+                const int nw = (pass == 0) ? nF - 1 : (hst + 1) % nF;
+                if (nw == hst) continue;
+                const oracle::FramePrecalc &pc = W->frames[hst].targetPrecalc[nw];     // host -> traced frame, as FullSystem.cc:1027-1032 builds it
+                Mat33f KRKi; Vec3f Kt; Vec2f aff(pc.PRE_aff_mode[0], pc.PRE_aff_mode[1]);
+                for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) KRKi(i, j) = pc.PRE_KRKiTll[i * 3 + j]; Kt[i] = pc.PRE_KtTll[i] * ((k % 3) ? 1.f : 40.f); }
+                float kt[3] = {Kt[0], Kt[1], Kt[2]};
+                const int sr = (int) ip.traceOn(FH[nw], KRKi, Kt, aff, HC);
+                const int so = oracle::trace_on(op, imgs[nw].data(), w, h, pc.PRE_KRKiTll, kt, pc.PRE_aff_mode, TS);
+                hist[sr]++;
+                okTrace &= sr == so && (int) ip.lastTraceStatus == op.lastTraceStatus && memcmp(&ip.idepth_min, &op.idepth_min, 4) == 0 &&
+                           memcmp(&ip.idepth_max, &op.idepth_max, 4) == 0 && memcmp(&ip.quality, &op.quality, 4) == 0;
+                if (sr != IPS_OOB || pass == 0)
+                    okTrace &= memcmp(ip.lastTraceUV.d, op.lastTraceUV, 8) == 0 && memcmp(&ip.lastTracePixelInterval, &op.lastTracePixelInterval, 4) == 0;
+            }
+            // linearizeResidual against every other frame at a few depths
+            oracle::Window::ImmatureCand c;
+            c.u = u; c.v = v; c.host = hst; c.energyTH = op.energyTH; c.idepth_min = 0; c.idepth_max = 0;
+            memcpy(c.color, op.color, 32); memcpy(c.weights, op.weights, 32);
+            for (int t = 0; t < nF; t++) {
+                if (t == hst) continue;
+                auto tr = std::make_shared<ImmaturePointTemporaryResidual>();
+                tr->state_state = ResState::IN; tr->state_energy = 0; tr->state_NewState = ResState::OUTLIER; tr->state_NewEnergy = 0; tr->target = FH[t];
+                oracle::TmpRes ot = {oracle::RS_IN, oracle::RS_OUTLIER, 0.f, 0.f};
+                const float idp = (k % 4 == 0) ? frand(-0.5f, 6.f) : frand(0.2f, 1.5f), slack = (k % 2) ? 1.f : 1000.f;
+                float Hr = 0.5f, br = -0.25f, Ho = 0.5f, bo = -0.25f;
+                const double er = ip.linearizeResidual(HC, slack, tr, Hr, br, idp);
+                const double eo = oracle::immatureLinearizeResidual(*W, c, t, slack, ot, Ho, bo, idp);
+                nLin++; nLinOob += tr->state_NewState == ResState::OOB;
+                okLin &= memcmp(&er, &eo, 8) == 0 && memcmp(&Hr, &Ho, 4) == 0 && memcmp(&br, &bo, 4) == 0 && (int) tr->state_NewState == ot.state_NewState &&
+                         (float) tr->state_NewEnergy == ot.state_NewEnergy;
+            }
+        }
+        printf("  immature pin: traceOn statuses GOOD %d OOB %d OUTLIER %d SKIPPED %d BADCONDITION %d; linearizeResidual %d calls (%d OOB)\n",
+               hist[0], hist[1], hist[2], hist[3], hist[4], nLin, nLinOob);
+        CHECK(hist[0] > 100 && hist[1] > 10 && (hist[3] + hist[4]) > 10 && nLinOob > 5, "immature scenario exercises GOOD, OOB, SKIPPED/BADCONDITION and the OOB early return");
+        CHECK(okCtor, "ImmaturePoint constructor (color, weights, gradH, energyTH)");
+        CHECK(okTrace, "ImmaturePoint::traceOn (status, idepth interval, quality, lastTraceUV, lastTracePixelInterval)");
+        CHECK(okLin, "ImmaturePoint::linearizeResidual (energy, Hdd, bd, state)");
+    }
     oracle_ba_destroy(o);
 }
 
@@ -363,6 +425,6 @@ int main() {
     pin_linearize();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc and Residuals.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc and ImmaturePoint.cc\n", checks);
     return 0;
 }

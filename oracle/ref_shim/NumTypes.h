@@ -9,11 +9,13 @@
 // the reference's own NumTypes.h sits next to AffLight.h and would win the quoted-include lookup: claim its include guard
 #define LDSO_NUM_TYPES_H_
 #include <cassert>
+#include <type_traits>
 #include <immintrin.h>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <string>
 #include <vector>
@@ -50,6 +52,8 @@ struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     Matrix(const Matrix &) = default;
     Matrix &operator=(const Matrix &) = default;
     T dot(const Matrix &o) const { T s = d[0] * o.d[0]; for (int i = 1; i < R * C; i++) s += d[i] * o.d[i]; return s; }
+    template<int R1 = R, int C1 = C, typename = typename std::enable_if<R1 * C1 == 1>::type> operator T() const { return d[0]; }      // 1x1 -> scalar
+    template<int R2, int C2> Matrix<T, R2, C2> topLeftCorner() const { Matrix<T, R2, C2> o; for (int c = 0; c < C2; c++) for (int r = 0; r < R2; r++) o.d[c * R2 + r] = d[c * R + r]; return o; }
     template<int N> Matrix<T, N, 1> tail() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[R * C - N + i]; return o; }
     T squaredNorm() const { T s = d[0] * d[0]; for (int i = 1; i < R * C; i++) s += d[i] * d[i]; return s; }
     template<int N> Matrix<T, N, 1> head() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[i]; return o; }
@@ -66,8 +70,16 @@ template<typename T, int R, int C> inline Matrix<T, R, C> operator+(const Matrix
 template<typename T, int R, int C> inline Matrix<T, R, C> operator*(const Matrix<T, R, 1> &col, const RowView<T, C> &row) {
     Matrix<T, R, C> o; for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) o.d[c * R + r] = col.d[r] * row.v->d[c]; return o;
 }
-template<typename T, int R, int C> inline Matrix<T, R, C> operator*(const Matrix<T, R, C> &m, T s) {
+template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+inline Matrix<T, R, C> operator*(const Matrix<T, R, C> &m, S s_) {
+    const T s = (T) s_;     // Eigen converts the scalar to the matrix's scalar type first
     Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = m.d[i] * s; return o;
+}
+// row^T * matrix -> row (entries accumulated left to right)
+template<typename T, int R, int C> inline Matrix<T, 1, C> operator*(const RowView<T, R> &row, const Matrix<T, R, C> &M) {
+    Matrix<T, 1, C> o;
+    for (int c = 0; c < C; c++) { T s = row.v->d[0] * M(0, c); for (int r = 1; r < R; r++) s += row.v->d[r] * M(r, c); o.d[c] = s; }
+    return o;
 }
 // small fixed matrix * vector: each entry is the row-times-column sum accumulated left to right (what Eigen's unrolled
 // coefficient-based product gives for these sizes)

@@ -1,7 +1,7 @@
-// STAND-INS for the reference classes PointFrameResidual::linearize / fixLinearizationF reach into — TEST INFRASTRUCTURE ONLY
+// STAND-INS for the reference classes PointFrameResidual::linearize / fixLinearizationF and ImmaturePoint::* reach into — TEST INFRASTRUCTURE ONLY
 // (see NumTypes.h in this directory). The reference's own Residuals.cc, Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h,
-// ResidualProjections.h, GlobalFuncs.h and Setting.cc are compiled UNMODIFIED; the four classes below replace
-// internal/FrameHessian.h, PointHessian.h, CalibHessian.h and OptimizationBackend/EnergyFunctional.h (whose real definitions pull
+// ResidualProjections.h, GlobalFuncs.h, ImmaturePoint.cc/.h, Feature.h and Setting.cc are compiled UNMODIFIED; the classes below
+// replace Frame.h, internal/FrameHessian.h, PointHessian.h, CalibHessian.h and OptimizationBackend/EnergyFunctional.h (whose real definitions pull
 // in OpenCV-backed Frame, Sophus, IndexThreadReduce ...) with the members those two functions read, same names and types.
 #pragma once
 #include "NumTypes.h"
@@ -9,6 +9,7 @@
 #define LDSO_POINT_HESSIAN_H_
 #define LDSO_CALIB_HESSIAN_H_
 #define LDSO_ENERGY_FUNCTIONAL_H_
+#define LDSO_FRAME_H_
 namespace ldso { namespace internal {
 class FrameHessian;
 class CalibHessian;
@@ -40,3 +41,8 @@ public:
     VecCf cDeltaF;
 };
 } }
+namespace ldso {
+struct Frame {                // include/Frame.h (the one member ImmaturePoint.cc reads)
+    shared_ptr<internal::FrameHessian> frameHessian;
+};
+}

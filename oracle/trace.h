@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/ba.h). PARITY PARTLY PINNED (oracle/ref_pin: accumulators, samplers, projections, affine transfer and all constants are checked bit for bit against the reference's own sources; the control flow around them is restated from the cited lines and unpinned).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/ba.h). PARITY PARTLY PINNED (oracle/ref_pin compiles the reference's own Residuals.cc, ImmaturePoint.cc, MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc and checks linearize, traceOn, the accumulators, samplers, projections and constants bit for bit; what needs dynamic Eigen / Sophus - stitching, solve, tracker loop - is restated from the cited lines and unpinned).
 // CPU restatement of the immature-point epipolar trace of tum-vision/LDSO:
 //   ImmaturePoint::ImmaturePoint   src/internal/ImmaturePoint.cc:14-38   (colour, weights, gradH, energyTH of a candidate)
 //   ImmaturePoint::traceOn         src/internal/ImmaturePoint.cc:46-314  (epipolar search + 1-D Gauss-Newton refinement)
