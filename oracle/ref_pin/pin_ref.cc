@@ -7,6 +7,7 @@
 //   src/internal/Residuals.cc (+ Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h)   PointFrameResidual::linearize, fixLinearizationF, applyRes/takeData
 //   src/internal/ImmaturePoint.cc (+ ImmaturePoint.h, Feature.h)   ImmaturePoint::ImmaturePoint, traceOn, linearizeResidual
 //   include/internal/ResidualProjections.h                      projectPoint (both overloads), derive_idepth
+//   src/frontend/CoarseTracker.cc (+ CoarseTracker.h, Feature.h, Point.h)   CoarseTracker::makeK, setCoarseTrackingRef / makeCoarseDepthL0, calcRes, calcGSSSE, trackNewestCoarse
 //   src/Setting.cc (+ include/Settings.h)                       every setting_* constant and the residual pattern the path reads
 // compiled UNMODIFIED against oracle/ref_shim/NumTypes.h (a stand-in for the Eigen types those headers use; Eigen3, Sophus, glog,
 // DBoW3 are not in this image). Every comparison is bit-exact (memcmp). Exit code 0 and "PIN OK" on success.
@@ -17,6 +18,7 @@
 #include "../accumulators.h"
 #include "../ba.h"
 #include "../trace.h"
+#include "../tracker.h"
 static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; }
 // the reference's own sources, unmodified, from /root/reference (their `#include "NumTypes.h"` is satisfied by the stand-in)
 #include "../ref_shim/NumTypes.h"
@@ -28,6 +30,9 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "internal/Residuals.h"           // the reference's own PointFrameResidual (its linearize lives in src/internal/Residuals.cc)
 #include "internal/ImmaturePoint.h"       // the reference's own ImmaturePoint (+ Feature.h); bodies in src/internal/ImmaturePoint.cc
 #include "internal/ResidualProjections.h"
+#define private public                    // CoarseTracker.cc is compiled with -Dprivate=public too (Makefile): calcRes / calcGSSSE / buffers
+#include "frontend/CoarseTracker.h"       // the reference's own CoarseTracker; bodies in src/frontend/CoarseTracker.cc
+#undef private
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
 
 static unsigned long long rng_state = 88172645463325252ull;
@@ -384,6 +389,179 @@ static void pin_linearize() {
     oracle_ba_destroy(o);
 }
 
+
+// Eigen::LDLT<Mat88 / 77 / 66>::solve as the stand-in forwards it: the oracle's restatement (omath.h) on both sides of the pin
+extern "C" void ref_shim_ldlt_solve(int n, const double *A, const double *b, double *x) {
+    oracle::MatX M(n, n); oracle::VecXd v(n);
+    for (int i = 0; i < n * n; i++) M.d[i] = A[i];
+    for (int i = 0; i < n; i++) v[i] = b[i];
+    const oracle::VecXd r = oracle::ldlt_solve(M, v);
+    for (int i = 0; i < n; i++) x[i] = r[i];
+}
+
+// src/Point.cc (not compiled here: it reaches into Frame / ImmaturePoint) only numbers the point in this constructor
+ldso::Point::Point() {}
+
+// ---- CoarseTracker: the reference's src/frontend/CoarseTracker.cc against oracle/tracker.cc
+static void pin_tracker() {
+    using namespace ldso; using namespace ldso::internal;
+    const int w = 640, h = 480, L = 4;
+    pyrLevelsUsed = L;
+    for (int l = 0; l < L; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+    wM3G = w - 3; hM3G = h - 3;
+    // a fronto-parallel textured plane at inverse depth id0 seen from two cameras a small x/y translation apart: the new image is the
+    // reference image shifted by (fx*tx*id0, fy*ty*id0) pixels, plus an affine brightness change
+    const float fxl = 520.f, fyl = 522.f, cxl = 318.3f, cyl = 241.1f, id0 = 0.8f;
+    const float shx = 2.6f, shy = -1.3f;
+    auto tex = [](float x, float y) {
+        return 120.f + 40.f * sinf(0.013f * x + 0.3f) * cosf(0.017f * y) + 25.f * sinf(0.045f * (x + 0.6f * y)) + 14.f * cosf(0.11f * x - 0.07f * y) +
+               9.f * sinf(0.31f * x) * sinf(0.27f * y);
+    };
+    std::vector<float> colRef(w * h), colNew(w * h);
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+        colRef[y * w + x] = tex(x, y);
+        colNew[y * w + x] = 1.04f * tex(x - shx, y - shy) + 3.f;
+    }
+    std::vector<std::vector<float>> pyrRef(L), pyrNew(L);
+    float *pr[PYR_LEVELS] = {}, *pn[PYR_LEVELS] = {};
+    for (int l = 0; l < L; l++) { pyrRef[l].assign(3 * (w >> l) * (h >> l), 0.f); pyrNew[l].assign(3 * (w >> l) * (h >> l), 0.f); pr[l] = pyrRef[l].data(); pn[l] = pyrNew[l].data(); }
+    oracle::makeImages(colRef.data(), w, h, L, pr);
+    oracle::makeImages(colNew.data(), w, h, L, pn);
+
+    // reference side: frames, features, points, their newest residual
+    auto HC = std::make_shared<CalibHessian>();
+    HC->fx = fxl; HC->fy = fyl; HC->cx = cxl; HC->cy = cyl;
+    const int nKF = 3, nPer = 900;
+    std::vector<shared_ptr<FrameHessian>> FH(nKF);
+    std::vector<shared_ptr<Frame>> FR(nKF);
+    for (int f = 0; f < nKF; f++) {
+        FH[f] = std::make_shared<FrameHessian>(); FR[f] = std::make_shared<Frame>();
+        FH[f]->frame = FR[f]; FR[f]->frameHessian = FH[f]; FR[f]->id = 10 + f; FH[f]->idx = f;
+    }
+    auto lastRef = FH[nKF - 1];
+    for (int l = 0; l < L; l++) lastRef->dIp[l] = (Vec3f *) pr[l];
+    lastRef->dI = lastRef->dIp[0]; lastRef->ab_exposure = 0.9f; lastRef->aff = AffLight(0.02f, -1.5f);
+    auto newFH = std::make_shared<FrameHessian>();
+    for (int l = 0; l < L; l++) newFH->dIp[l] = (Vec3f *) pn[l];
+    newFH->dI = newFH->dIp[0]; newFH->ab_exposure = 1.1f;
+    std::vector<float> cpt, hdi;            // the oracle's input: the contributions in the order the reference visits them
+    std::vector<shared_ptr<PointFrameResidual>> keep;
+    int nSkipped = 0;
+    for (int f = 0; f < nKF; f++)
+        for (int k = 0; k < nPer; k++) {
+            auto feat = std::make_shared<Feature>(0.f, 0.f, FR[f]);
+            auto pt = std::make_shared<Point>();
+            auto ph = std::make_shared<PointHessian>();
+            feat->point = pt; pt->mpPH = ph; feat->status = Feature::FeatureStatus::VALID; pt->status = Point::PointStatus::ACTIVE;
+            auto r = std::make_shared<PointFrameResidual>(ph, FH[f], lastRef);
+            r->isActiveAndIsGoodNEW = true;
+            // projected position in lastRef; every 11th point lands on the pixel of the previous one (accumulation), a band is left empty (dilation)
+            float u = frand(1.f, w - 2.f), v = frand(1.f, h - 2.f);
+            if (v > 200 && v < 260 && u > 100 && u < 400) v += 70;
+            if (k % 11 == 0 && !cpt.empty()) { u = cpt[cpt.size() - 3]; v = cpt[cpt.size() - 2]; }
+            r->centerProjectedTo = Vec3f(u, v, id0 * (1.f + frand(-0.02f, 0.02f)));
+            ph->HdiF = frand(0.5f, 400.f);
+            ph->lastResiduals[0] = std::make_pair(r, (int) ResState::IN);
+            int skip = 0;
+            if (k % 17 == 3) { feat->status = Feature::FeatureStatus::OUTLIER; skip = 1; }
+            if (k % 19 == 4) { pt->status = Point::PointStatus::MARGINALIZED; skip = 1; }
+            if (k % 23 == 5) { ph->lastResiduals[0].second = (int) ResState::OOB; skip = 1; }
+            if (k % 29 == 6) { ph->lastResiduals[0].first = nullptr; skip = 1; }
+            FR[f]->features.push_back(feat); keep.push_back(r);
+            if (skip) { nSkipped++; continue; }
+            cpt.push_back(r->centerProjectedTo[0]); cpt.push_back(r->centerProjectedTo[1]); cpt.push_back(r->centerProjectedTo[2]);
+            hdi.push_back(ph->HdiF);
+        }
+    CoarseTracker R(w, h);
+    R.makeK(HC);
+    R.setCoarseTrackingRef(FH);
+    oracle::CoarseTracker O(w, h, L);
+    O.makeK(fxl, fyl, cxl, cyl);
+    for (int l = 0; l < L; l++) { O.refDIp[l] = pr[l]; O.newDIp[l] = pn[l]; }
+    O.lastRef_aff_a = lastRef->aff.a; O.lastRef_aff_b = lastRef->aff.b; O.lastRef_ab_exposure = lastRef->ab_exposure; O.newFrame_ab_exposure = newFH->ab_exposure;
+    O.makeCoarseDepthL0((int) hdi.size(), cpt.data(), hdi.data());
+
+    bool okK = true, okPc = true, okMap = true;
+    for (int l = 0; l < L; l++) {
+        okK &= R.w[l] == O.w[l] && R.h[l] == O.h[l] && memcmp(&R.fx[l], &O.fx[l], 4) == 0 && memcmp(&R.fy[l], &O.fy[l], 4) == 0 && memcmp(&R.cx[l], &O.cx[l], 4) == 0 &&
+               memcmp(&R.cy[l], &O.cy[l], 4) == 0 && memcmp(&R.fxi[l], &O.fxi[l], 4) == 0 && memcmp(&R.fyi[l], &O.fyi[l], 4) == 0 && memcmp(&R.cxi[l], &O.cxi[l], 4) == 0 &&
+               memcmp(&R.cyi[l], &O.cyi[l], 4) == 0;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) okK &= memcmp(&R.K[l](i, j), &O.K[l][i * 3 + j], 4) == 0 && memcmp(&R.Ki[l](i, j), &O.Ki[l][i * 3 + j], 4) == 0;
+        okPc &= R.pc_n[l] == O.pc_n[l];
+        if (R.pc_n[l] == O.pc_n[l]) {
+            const size_t nb = 4 * (size_t) R.pc_n[l];
+            okPc &= memcmp(R.pc_u[l], O.pc_u[l].data(), nb) == 0 && memcmp(R.pc_v[l], O.pc_v[l].data(), nb) == 0 && memcmp(R.pc_idepth[l], O.pc_idepth[l].data(), nb) == 0 &&
+                    memcmp(R.pc_color[l], O.pc_color[l].data(), nb) == 0;
+        }
+        const size_t nm = 4 * (size_t) R.w[l] * R.h[l];
+        okMap &= memcmp(R.idepth[l], O.idepth[l].data(), nm) == 0 && memcmp(R.weightSums[l], O.weightSums[l].data(), nm) == 0;
+    }
+    printf("  tracker pin: %zu contributing points (%d filtered), pc_n = %d %d %d %d\n", hdi.size(), nSkipped, R.pc_n[0], R.pc_n[1], R.pc_n[2], R.pc_n[3]);
+    CHECK(okK, "CoarseTracker::makeK (w, h, fx.., K, Ki per level)");
+    CHECK(R.pc_n[0] > 1500 && R.pc_n[0] < R.pc_n[1] + 100000 && nSkipped > 100, "tracker scenario: enough points, filters exercised");
+    CHECK(okPc, "setCoarseTrackingRef / makeCoarseDepthL0: pc_n, pc_u, pc_v, pc_idepth, pc_color on every level");
+    CHECK(okMap, "makeCoarseDepthL0: idepth and weightSums maps on every level");
+    CHECK(R.refFrameID == 10 + nKF - 1 && R.lastRef_aff_g2l.a == lastRef->aff.a, "setCoarseTrackingRef bookkeeping");
+
+    // calcRes / calcGSSSE at several poses, brightness parameters, cutoffs and levels
+    R.newFrame = newFH;
+    bool okRes = true, okBuf = true, okH = true; int nSat = 0, nEval = 0;
+    for (int trial = 0; trial < 12; trial++) {
+        Vec6 xi; double xia[6];
+        for (int i = 0; i < 6; i++) { xia[i] = (trial == 0) ? 0.0 : frand(-1.f, 1.f) * (i < 3 ? 0.01 : 0.004) * (1 + trial % 3); xi[i] = xia[i]; }
+        const SE3 Tr = SE3::exp(xi); const oracle::SE3 To = oracle::SE3::exp(xia);
+        const AffLight aff(frand(-0.05f, 0.08f), frand(-4.f, 4.f));
+        const float cutoff = (trial % 4 == 1) ? 6.f : (trial % 4 == 2 ? 40.f : 20.f);
+        for (int l = L - 1; l >= 0; l--) {
+            const Vec6 rr = R.calcRes(l, Tr, aff, cutoff);
+            double ro[6]; O.calcRes(l, To, aff.a, aff.b, cutoff, ro);
+#ifdef PIN_SELFTEST_BREAK
+            if (trial == 3 && l == 1) ro[0] = std::nextafter(ro[0], 1e30);
+#endif
+            okRes &= memcmp(rr.d, ro, 48) == 0;
+            okBuf &= R.buf_warped_n == O.buf_warped_n;
+            if (R.buf_warped_n == O.buf_warped_n) {
+                const size_t nb = 4 * (size_t) R.buf_warped_n;
+                okBuf &= memcmp(R.buf_warped_idepth, O.buf_warped_idepth.data(), nb) == 0 && memcmp(R.buf_warped_u, O.buf_warped_u.data(), nb) == 0 &&
+                         memcmp(R.buf_warped_v, O.buf_warped_v.data(), nb) == 0 && memcmp(R.buf_warped_dx, O.buf_warped_dx.data(), nb) == 0 &&
+                         memcmp(R.buf_warped_dy, O.buf_warped_dy.data(), nb) == 0 && memcmp(R.buf_warped_residual, O.buf_warped_residual.data(), nb) == 0 &&
+                         memcmp(R.buf_warped_weight, O.buf_warped_weight.data(), nb) == 0 && memcmp(R.buf_warped_refColor, O.buf_warped_refColor.data(), nb) == 0;
+            }
+            nSat += rr[5] > 0; nEval++;
+            Mat88 Hr; Vec8 br; R.calcGSSSE(l, Hr, br, Tr, aff);
+            double Ho[64], bo[8]; O.calcGSSSE(l, Ho, bo, To, aff.a, aff.b);
+            for (int i = 0; i < 8; i++) { okH &= memcmp(&br[i], &bo[i], 8) == 0; for (int j = 0; j < 8; j++) okH &= memcmp(&Hr(i, j), &Ho[i * 8 + j], 8) == 0; }
+        }
+    }
+    CHECK(nSat > 0 && nSat < nEval, "calcRes scenario exercises the saturated (cutoff) branch on some evaluations");
+    CHECK(okRes, "CoarseTracker::calcRes return vector (E, count, flow indicators, saturated ratio)");
+    CHECK(okBuf, "calcRes warped buffers (idepth, u, v, dx, dy, residual, weight, refColor, padded count)");
+    CHECK(okH, "CoarseTracker::calcGSSSE H (8x8) and b after the SCALE_* rescale");
+
+    // the whole coarse-to-fine LM loop, from three starts (identity; a start that is too far and fails the residual check; wrong brightness)
+    bool okTrack = true; int nTrue = 0, nFalse = 0, its = 0;
+    for (int run = 0; run < 4; run++) {
+        Vec6 xi; double xia[6] = {0, 0, 0, 0, 0, 0};
+        if (run == 1) { xia[0] = 0.004; xia[4] = -0.003; }
+        if (run == 2) { xia[0] = 0.25; xia[1] = -0.2; xia[5] = 0.3; }
+        for (int i = 0; i < 6; i++) xi[i] = xia[i];
+        SE3 Tr = SE3::exp(xi); oracle::SE3 To = oracle::SE3::exp(xia);
+        AffLight aff(run == 3 ? 0.3f : 0.f, run == 3 ? 20.f : 0.f); float oa = aff.a, ob = aff.b;
+        Vec5 minRes; double minResO[5];
+        for (int i = 0; i < 5; i++) { minRes[i] = minResO[i] = (run == 2) ? 1.0 : NAN; }
+        const bool gr = R.trackNewestCoarse(newFH, Tr, aff, L - 1, minRes);
+        const bool go = O.trackNewestCoarse(To, oa, ob, L - 1, minResO);
+        nTrue += gr; nFalse += !gr; its += O.lm_iterations_total;
+        bool same = gr == go && memcmp(&aff.a, &oa, 4) == 0 && memcmp(&aff.b, &ob, 4) == 0 && memcmp(&Tr.s.q, &To.q, sizeof(To.q)) == 0 && memcmp(&Tr.s.t, &To.t, sizeof(To.t)) == 0;
+        same &= memcmp(R.lastResiduals.d, O.lastResiduals, 40) == 0 && memcmp(R.lastFlowIndicators.d, O.lastFlowIndicators, 24) == 0;
+        okTrack &= same;
+        printf("  tracker pin: track run %d -> %s, t = (%.5f %.5f %.5f) (true %.5f %.5f 0), a = %.4f b = %.3f, %d calcRes evaluations\n", run, gr ? "good" : "lost",
+                             Tr.s.t[0], Tr.s.t[1], Tr.s.t[2], shx / (fxl * id0), shy / (fyl * id0), aff.a, aff.b, O.lm_iterations_total);
+    }
+    CHECK(nTrue >= 2 && nFalse >= 1, "trackNewestCoarse scenario has converging and aborting runs");
+    CHECK(okTrack, "CoarseTracker::trackNewestCoarse: return value, pose, affine brightness, lastResiduals, lastFlowIndicators");
+}
+
 static void pin_settings() {
     using namespace ldso;
     oracle::Settings S; oracle::TraceSettings T;
@@ -423,8 +601,9 @@ int main() {
     pin_afflight();
     pin_projections();
     pin_linearize();
+    pin_tracker();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc and ImmaturePoint.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc and CoarseTracker.cc\n", checks);
     return 0;
 }

@@ -1,10 +1,12 @@
-// STAND-IN for the reference's include/NumTypes.h — TEST INFRASTRUCTURE ONLY, used by oracle/ref_pin to compile a few of the
-// reference's OWN headers where they lie under /root/reference (MatrixAccumulators.h, GlobalFuncs.h, AffLight.h) plus its
-// src/Setting.cc, so that the oracle restatement can be pinned against the reference's own code for those pieces.
-// The real NumTypes.h pulls in Eigen3, Sophus, glog and DBoW3, none of which exist in this image. The three headers above use
-// only: fixed-size Eigen::Matrix storage with operator()/operator[], setZero, +=, scalar*vector, vector+vector and one
-// column * row^T outer product — that is all this file provides (eager, entry by entry, in the operand order written at the
-// call site, which is also what Eigen's expression templates evaluate to for these expressions).
+// STAND-IN for the reference's include/NumTypes.h — TEST INFRASTRUCTURE ONLY, used by oracle/ref_pin to compile parts of the
+// reference's OWN sources where they lie under /root/reference (Residuals.cc, ImmaturePoint.cc, CoarseTracker.cc, MatrixAccumulators.h,
+// GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc), so that the oracle restatement can be pinned against the reference's own
+// code. The real NumTypes.h pulls in Eigen3, Sophus, glog and DBoW3, none of which exist in this image. Those sources use a small
+// part of Eigen: fixed-size matrices with element access, +, -, scalar and matrix products, dot / norm / sum, head / tail / segment /
+// block views, cast, a 3x3 inverse, the comma initialiser and (in the tracker's LM loop only) ldlt().solve(). This file provides
+// exactly that, evaluated eagerly, entry by entry, sums accumulated left to right in the operand order written at the call site —
+// which is what Eigen's expression templates evaluate to for these fixed small sizes. ldlt().solve() and Sophus::SE3d are forwarded
+// to the oracle's own restatements (omath.h), i.e. those two pieces are NOT pinned by anything compiled against this header.
 #pragma once
 // the reference's own NumTypes.h sits next to AffLight.h and would win the quoted-include lookup: claim its include guard
 #define LDSO_NUM_TYPES_H_
@@ -27,9 +29,21 @@ using namespace std;
 #define EIGEN_ALWAYS_INLINE inline
 #define EIGEN_STRONG_INLINE inline
 
+// implemented by the pin harness with the oracle's restatement of Eigen::LDLT (oracle/omath.h)
+extern "C" void ref_shim_ldlt_solve(int n, const double *A_colmajor, const double *b, double *x);
+
 namespace Eigen {
 template<typename T, int R, int C> struct Matrix;
+template<typename T, int R, int C> struct Block;
 template<typename T, int N> struct RowView { const Matrix<T, N, 1> *v; };
+template<typename T, int R, int C> struct CommaInit {
+    Matrix<T, R, C> *m; int k;
+    template<typename S> CommaInit &operator,(S v) { m->d[(k % C) * R + (k / C)] = (T) v; k++; return *this; }     // row by row
+};
+template<typename T, int N> struct LDLTOf {
+    Matrix<T, N, N> A;
+    Matrix<T, N, 1> solve(const Matrix<T, N, 1> &b) const;
+};
 
 // Eigen aligns fixed-size objects whose size is a multiple of 16 bytes to 16 bytes (SSE build); the reference's _mm_load_ps on
 // RawResidualJacobian members relies on the struct layout that follows from it
@@ -40,40 +54,94 @@ struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     Matrix(T a, T b) { static_assert(R * C == 2, "size"); d[0] = a; d[1] = b; }
     Matrix(T a, T b, T c) { static_assert(R * C == 3, "size"); d[0] = a; d[1] = b; d[2] = c; }
     Matrix(T a, T b, T c, T e) { static_assert(R * C == 4, "size"); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
+    // Eigen lets a 1xN row initialise an Nx1 column (vector <- vector): EnergyFunctional::adHTdeltaF is Mat18f, read as Vec8f
+    template<int R2, int C2, typename = typename std::enable_if<(R2 != R || C2 != C) && R2 * C2 == R * C && (R2 == 1 || C2 == 1) && (R == 1 || C == 1)>::type>
+    Matrix(const Matrix<T, R2, C2> &o) { for (int i = 0; i < R * C; i++) d[i] = o.d[i]; }
+    Matrix(const Matrix &) = default;
+    Matrix &operator=(const Matrix &) = default;
     T &operator()(int r, int c) { return d[c * R + r]; }
     const T &operator()(int r, int c) const { return d[c * R + r]; }
     T &operator[](int i) { return d[i]; }
     const T &operator[](int i) const { return d[i]; }
     void setZero() { for (int i = 0; i < R * C; i++) d[i] = T(0); }
-    Matrix &operator+=(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] += o.d[i]; return *this; }
+    void setIdentity() { setZero(); for (int i = 0; i < (R < C ? R : C); i++) d[i * R + i] = T(1); }
     static Matrix Zero() { Matrix m; m.setZero(); return m; }
-    // Eigen lets a 1xN row initialise an Nx1 column (vector <- vector): EnergyFunctional::adHTdeltaF is Mat18f, read as Vec8f
-    template<int R2, int C2> Matrix(const Matrix<T, R2, C2> &o) { static_assert(R2 * C2 == R * C && (R2 == 1 || C2 == 1) && (R == 1 || C == 1), "vector copy"); for (int i = 0; i < R * C; i++) d[i] = o.d[i]; }
-    Matrix(const Matrix &) = default;
-    Matrix &operator=(const Matrix &) = default;
-    T dot(const Matrix &o) const { T s = d[0] * o.d[0]; for (int i = 1; i < R * C; i++) s += d[i] * o.d[i]; return s; }
+    static Matrix Identity() { Matrix m; m.setIdentity(); return m; }
+    static Matrix Constant(T v) { Matrix m; for (int i = 0; i < R * C; i++) m.d[i] = v; return m; }
+    void setConstant(T v) { for (int i = 0; i < R * C; i++) d[i] = v; }
+    Matrix &operator+=(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] += o.d[i]; return *this; }
+    Matrix &operator-=(const Matrix &o) { for (int i = 0; i < R * C; i++) d[i] -= o.d[i]; return *this; }
+    template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    Matrix &operator*=(S s_) { const T s = (T) s_; for (int i = 0; i < R * C; i++) d[i] *= s; return *this; }
+    Matrix operator-() const { Matrix o; for (int i = 0; i < R * C; i++) o.d[i] = -d[i]; return o; }
+    template<typename U> Matrix<U, R, C> cast() const { Matrix<U, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = (U) d[i]; return o; }
     template<int R1 = R, int C1 = C, typename = typename std::enable_if<R1 * C1 == 1>::type> operator T() const { return d[0]; }      // 1x1 -> scalar
-    template<int R2, int C2> Matrix<T, R2, C2> topLeftCorner() const { Matrix<T, R2, C2> o; for (int c = 0; c < C2; c++) for (int r = 0; r < R2; r++) o.d[c * R2 + r] = d[c * R + r]; return o; }
-    template<int N> Matrix<T, N, 1> tail() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[R * C - N + i]; return o; }
+    T dot(const Matrix &o) const { T s = d[0] * o.d[0]; for (int i = 1; i < R * C; i++) s += d[i] * o.d[i]; return s; }
     T squaredNorm() const { T s = d[0] * d[0]; for (int i = 1; i < R * C; i++) s += d[i] * d[i]; return s; }
-    template<int N> Matrix<T, N, 1> head() const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[i]; return o; }
-    template<int N> struct Seg { T *p; Seg &operator=(const Matrix<T, N, 1> &v) { for (int i = 0; i < N; i++) p[i] = v.d[i]; return *this; } };
-    template<int N> Seg<N> segment(int i0) { return Seg<N>{d + i0}; }
+    T norm() const { return std::sqrt(squaredNorm()); }
+    T sum() const { T s = d[0]; for (int i = 1; i < R * C; i++) s += d[i]; return s; }
     RowView<T, R> transpose() const { static_assert(C == 1, "only column vectors are transposed here"); return RowView<T, R>{this}; }
+    CommaInit<T, R, C> operator<<(T v) { d[0] = v; return CommaInit<T, R, C>{this, 1}; }
+    LDLTOf<T, R> ldlt() const { static_assert(R == C, "square"); return LDLTOf<T, R>{*this}; }
+    // 3x3 inverse by cofactors / determinant (Eigen's compute_inverse for size 3)
+    Matrix inverse() const {
+        static_assert(R == 3 && C == 3, "only the 3x3 inverse is used");
+        const Matrix &m = *this; Matrix o;
+        const T c00 = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1), c10 = m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2), c20 = m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0);
+        const T invdet = T(1) / (m(0, 0) * c00 + m(0, 1) * c10 + m(0, 2) * c20);
+        o(0, 0) = c00 * invdet; o(1, 0) = c10 * invdet; o(2, 0) = c20 * invdet;
+        o(0, 1) = (m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2)) * invdet; o(1, 1) = (m(0, 0) * m(2, 2) - m(0, 2) * m(2, 0)) * invdet; o(2, 1) = (m(2, 0) * m(0, 1) - m(0, 0) * m(2, 1)) * invdet;
+        o(0, 2) = (m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1)) * invdet; o(1, 2) = (m(1, 0) * m(0, 2) - m(0, 0) * m(1, 2)) * invdet; o(2, 2) = (m(0, 0) * m(1, 1) - m(1, 0) * m(0, 1)) * invdet;
+        return o;
+    }
+    // views: on a non-const object a Block (a value that also writes through on =, *=, setZero), on a const object a value
+    template<int BR, int BC> Block<T, BR, BC> block(int r, int c) { return Block<T, BR, BC>(d + c * R + r, R); }
+    template<int BR, int BC> Matrix<T, BR, BC> block(int r, int c) const { return Block<T, BR, BC>(const_cast<T *>(d) + c * R + r, R); }
+    template<int BR, int BC> Block<T, BR, BC> topLeftCorner() { return block<BR, BC>(0, 0); }
+    template<int BR, int BC> Matrix<T, BR, BC> topLeftCorner() const { return block<BR, BC>(0, 0); }
+    template<int BR, int BC> Block<T, BR, BC> topRightCorner() { return block<BR, BC>(0, C - BC); }
+    template<int BR, int BC> Matrix<T, BR, BC> topRightCorner() const { return block<BR, BC>(0, C - BC); }
+    Block<T, R, 1> col(int c) { return Block<T, R, 1>(d + c * R, R); }
+    Block<T, 1, C> row(int r) { return Block<T, 1, C>(d + r, R); }
+    template<int N> Block<T, N, 1> segment(int i0) { static_assert(C == 1 || R == 1, "vector"); return Block<T, N, 1>(d + i0, N); }
+    template<int N> Matrix<T, N, 1> segment(int i0) const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[i0 + i]; return o; }
+    template<int N> Block<T, N, 1> head() { return segment<N>(0); }
+    template<int N> Matrix<T, N, 1> head() const { return segment<N>(0); }
+    template<int N> Block<T, N, 1> tail() { return segment<N>(R * C - N); }
+    template<int N> Matrix<T, N, 1> tail() const { return segment<N>(R * C - N); }
 };
-template<typename T, int R, int C> inline Matrix<T, R, C> operator*(T s, const Matrix<T, R, C> &m) {
+
+template<typename T, int BR, int BC>
+struct Block : Matrix<T, BR, BC> {
+    T *p; int ld;      // top-left element of the viewed region and the column stride of its matrix
+    Block(T *p_, int ld_) : p(p_), ld(ld_) { for (int c = 0; c < BC; c++) for (int r = 0; r < BR; r++) this->d[c * BR + r] = p[c * ld + r]; }
+    void push() { for (int c = 0; c < BC; c++) for (int r = 0; r < BR; r++) p[c * ld + r] = this->d[c * BR + r]; }
+    Block &operator=(const Matrix<T, BR, BC> &m) { for (int i = 0; i < BR * BC; i++) this->d[i] = m.d[i]; push(); return *this; }
+    Block &operator=(const Block &m) { return *this = static_cast<const Matrix<T, BR, BC> &>(m); }
+    template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    Block &operator*=(S s) { Matrix<T, BR, BC>::operator*=(s); push(); return *this; }
+    void setZero() { Matrix<T, BR, BC>::setZero(); push(); }
+};
+
+template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+inline Matrix<T, R, C> operator*(S s_, const Matrix<T, R, C> &m) {
+    const T s = (T) s_;     // Eigen converts the scalar to the matrix's scalar type first
     Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = s * m.d[i]; return o;
+}
+template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+inline Matrix<T, R, C> operator*(const Matrix<T, R, C> &m, S s_) {
+    const T s = (T) s_;
+    Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = m.d[i] * s; return o;
 }
 template<typename T, int R, int C> inline Matrix<T, R, C> operator+(const Matrix<T, R, C> &a, const Matrix<T, R, C> &b) {
     Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = a.d[i] + b.d[i]; return o;
 }
+template<typename T, int R, int C> inline Matrix<T, R, C> operator-(const Matrix<T, R, C> &a, const Matrix<T, R, C> &b) {
+    Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = a.d[i] - b.d[i]; return o;
+}
+// column * row^T (outer product)
 template<typename T, int R, int C> inline Matrix<T, R, C> operator*(const Matrix<T, R, 1> &col, const RowView<T, C> &row) {
     Matrix<T, R, C> o; for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) o.d[c * R + r] = col.d[r] * row.v->d[c]; return o;
-}
-template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
-inline Matrix<T, R, C> operator*(const Matrix<T, R, C> &m, S s_) {
-    const T s = (T) s_;     // Eigen converts the scalar to the matrix's scalar type first
-    Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = m.d[i] * s; return o;
 }
 // row^T * matrix -> row (entries accumulated left to right)
 template<typename T, int R, int C> inline Matrix<T, 1, C> operator*(const RowView<T, R> &row, const Matrix<T, R, C> &M) {
@@ -81,22 +149,35 @@ template<typename T, int R, int C> inline Matrix<T, 1, C> operator*(const RowVie
     for (int c = 0; c < C; c++) { T s = row.v->d[0] * M(0, c); for (int r = 1; r < R; r++) s += row.v->d[r] * M(r, c); o.d[c] = s; }
     return o;
 }
-// small fixed matrix * vector: each entry is the row-times-column sum accumulated left to right (what Eigen's unrolled
+// small fixed matrix * matrix / vector: each entry is the row-times-column sum accumulated left to right (what Eigen's unrolled
 // coefficient-based product gives for these sizes)
-template<typename T, int R, int K> inline Matrix<T, R, 1> operator*(const Matrix<T, R, K> &A, const Matrix<T, K, 1> &x) {
-    Matrix<T, R, 1> o;
-    for (int r = 0; r < R; r++) { T s = A(r, 0) * x.d[0]; for (int k = 1; k < K; k++) s += A(r, k) * x.d[k]; o.d[r] = s; }
+template<typename T, int R, int K, int C> inline Matrix<T, R, C> operator*(const Matrix<T, R, K> &A, const Matrix<T, K, C> &B) {
+    Matrix<T, R, C> o;
+    for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) { T s = A(r, 0) * B(0, c); for (int k = 1; k < K; k++) s += A(r, k) * B(k, c); o(r, c) = s; }
     return o;
+}
+template<typename T, int N> inline Matrix<T, N, 1> LDLTOf<T, N>::solve(const Matrix<T, N, 1> &b) const {
+    static_assert(std::is_same<T, double>::value, "only double systems are solved");
+    Matrix<T, N, 1> x; ref_shim_ldlt_solve(N, A.d, b.d, x.d); return x;
 }
 typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 4, 1> Vector4f;
+typedef Matrix<int, 2, 1> Vector2i;
 }  // namespace Eigen
 
 const int CPARS = 4;
 const int MAX_RES_PER_POINT = 8;
 typedef Eigen::Matrix<double, 2, 1> Vec2;
+typedef Eigen::Matrix<double, 3, 1> Vec3;
+typedef Eigen::Matrix<double, 5, 1> Vec5;
+typedef Eigen::Matrix<double, 6, 1> Vec6;
+typedef Eigen::Matrix<double, 7, 1> Vec7;
+typedef Eigen::Matrix<double, 8, 1> Vec8;
+typedef Eigen::Matrix<double, 10, 1> Vec10;
+typedef Eigen::Matrix<double, 3, 3> Mat33;
+typedef Eigen::Matrix<double, 8, 8> Mat88;
 typedef Eigen::Matrix<float, 2, 1> Vec2f;
 typedef Eigen::Matrix<float, 3, 1> Vec3f;
 typedef Eigen::Matrix<unsigned char, 3, 1> Vec3b;
@@ -113,6 +194,22 @@ typedef Eigen::Matrix<float, 14, 1> Vec14f;
 typedef Eigen::Matrix<float, 9, 9> Mat99f;
 typedef Eigen::Matrix<float, 13, 13> Mat1313f;
 typedef Eigen::Matrix<float, 14, 14> Mat1414f;
+// Sophus::SE3d as the tracker uses it (exp, *, inverse, rotationMatrix, translation): forwarded to the oracle's restatement of
+// Sophus (oracle/omath.h) — so the SE(3) algebra is shared by both sides of the pin and is NOT itself pinned
+#include "../omath.h"
+namespace Sophus {
+class SE3d {
+public:
+    oracle::SE3 s;
+    SE3d() {}
+    Mat33 rotationMatrix() const { const oracle::M3 R = s.rotationMatrix(); Mat33 o; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o(i, j) = R(i, j); return o; }
+    Vec3 translation() const { return Vec3(s.t[0], s.t[1], s.t[2]); }
+    static SE3d exp(const Vec6 &a) { SE3d r; r.s = oracle::SE3::exp(a.d); return r; }
+    SE3d operator*(const SE3d &o) const { SE3d r; r.s = s * o.s; return r; }
+    SE3d inverse() const { SE3d r; r.s = s.inverse(); return r; }
+};
+}
+typedef Sophus::SE3d SE3;
 // GlobalFuncs.h's eigenTestNan(const MatXX&) only needs rows(), cols() and operator(); it is not called by the pin
 struct MatXX {
     int r = 0, c = 0;

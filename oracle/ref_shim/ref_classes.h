@@ -15,6 +15,13 @@ class FrameHessian;
 class CalibHessian;
 } }
 #include "internal/FrameFramePrecalc.h"      // the reference's own struct (PRE_* members)
+#include "Settings.h"
+#include "AffLight.h"
+#include "Feature.h"                         // the reference's own Feature and Point structs (plain data; their .cc files are not needed)
+#include "Point.h"
+namespace ldso { namespace internal {
+class PointFrameResidual;
+} }
 namespace ldso { namespace internal {
 class CalibHessian {          // include/internal/CalibHessian.h:39-69 (accessors only)
 public:
@@ -28,11 +35,20 @@ public:
     Eigen::Vector3f *dI = nullptr;
     std::vector<FrameFramePrecalc> targetPrecalc;
     float frameEnergyTH = 8 * 8 * 8;
+    // read by CoarseTracker.cc (FrameHessian.h:32,68,169,179,200-201)
+    shared_ptr<Frame> frame;
+    Vec3f *dIp[PYR_LEVELS] = {};
+    float ab_exposure = 0;
+    AffLight aff;
+    AffLight aff_g2l() { return aff; }
+    SE3 PRE_worldToCam, PRE_camToWorld;
 };
 class PointHessian {          // include/internal/PointHessian.h:83-107
 public:
     float u = 0, v = 0, idepth_scaled = 0, idepth_zero_scaled = 0, deltaF = 0;
     float color[MAX_RES_PER_POINT], weights[MAX_RES_PER_POINT];
+    std::pair<shared_ptr<PointFrameResidual>, int /*ResState*/> lastResiduals[2];      // PointHessian.h:103 (ResState is a plain enum: compares with int)
+    float HdiF = 0;                                                                     // PointHessian.h:124
 };
 class EnergyFunctional {      // include/internal/OptimizationBackend/EnergyFunctional.h:152,213,222
 public:
@@ -42,7 +58,9 @@ public:
 };
 } }
 namespace ldso {
-struct Frame {                // include/Frame.h (the one member ImmaturePoint.cc reads)
+struct Frame {                // include/Frame.h (the members ImmaturePoint.cc and CoarseTracker.cc read)
     shared_ptr<internal::FrameHessian> frameHessian;
+    unsigned long id = 0;
+    std::vector<shared_ptr<Feature>> features;
 };
 }
