@@ -942,13 +942,15 @@ static inline void addABAt(MatX &H, int r0, int c0, const double *A, const doubl
 
 // AccumulatedTopHessianSSE::stitchDoubleInternal — AccumulatedTopHessian.cc:193-255
 void Window::topStitchDoubleInternal(AccumulatedTopHessianSSE &A, MatX *H, VecXd *b, bool usePrior, int min, int max,
-                                     int tid) {
+                                     int tid, bool hostOuter) {
     int toAggregate = NUM_THREADS;
     if (tid == -1) { toAggregate = 1; tid = 0; }
     if (min == max) return;
     int nf = A.nframes[0];
     for (int k = min; k < max; k++) {
-        int h = k % nf, t = k / nf;
+        // stitchDoubleInternal walks the pairs target-major (k = h + nf*t); the single-accumulator stitchDouble (.cc:133-134) walks
+        // them host-major (for h, for t), which changes the order the diagonal blocks receive their terms
+        int h = hostOuter ? k / nf : k % nf, t = hostOuter ? k % nf : k / nf;
         int hIdx = CPARS + h * 8, tIdx = CPARS + t * 8;
         int aidx = h + nf * t;
         double accH[13 * 13];
@@ -1037,7 +1039,7 @@ void Window::topStitchDouble(AccumulatedTopHessianSSE &A, MatX &H, VecXd &b, boo
     // identical block algebra to stitchDoubleInternal with toAggregate == 1
     int save = A.nframes[0];
     A.nframes[0] = nf;
-    topStitchDoubleInternal(A, &H, &b, usePrior, 0, nf * nf, -1);
+    topStitchDoubleInternal(A, &H, &b, usePrior, 0, nf * nf, -1, true);
     A.nframes[0] = save;
     for (int h = 0; h < nf; h++) {
         int hIdx = CPARS + h * 8;
@@ -1090,7 +1092,7 @@ void Window::scAddPoint(Point &p, bool shiftPriorToZero, int tid) {
 }
 
 // AccumulatedSCHessianSSE::stitchDoubleInternal — AccumulatedSCHessian.cc:53-119
-void Window::scStitchDoubleInternal(MatX *H, VecXd *b, int min, int max, int tid) {
+void Window::scStitchDoubleInternal(MatX *H, VecXd *b, int min, int max, int tid, bool hostOuter) {
     AccumulatedSCHessianSSE &B = accSSE_bot;
     int toAggregate = NUM_THREADS;
     if (tid == -1) { toAggregate = 1; tid = 0; }
@@ -1098,7 +1100,8 @@ void Window::scStitchDoubleInternal(MatX *H, VecXd *b, int min, int max, int tid
     int nf = B.nframes[0];
     int nframes2 = nf * nf;
     for (int k = min; k < max; k++) {
-        int i = k % nf, j = k / nf;
+        // same remark as the top stitch: stitchDouble (.cc:130-131) walks (i, j) with i outermost
+        int i = hostOuter ? k / nf : k % nf, j = hostOuter ? k % nf : k / nf;
         int iIdx = CPARS + i * 8, jIdx = CPARS + j * 8;
         int ijIdx = i + nf * j;
         double Hpc[32], bp[8];  // Hpc 8x4 row-major
@@ -1183,7 +1186,7 @@ void Window::scStitchDouble(MatX &H, VecXd &b, int tid) {
     int n = nf * 8 + CPARS;
     H = MatX(n, n);
     b.assign(n, 0.0);
-    scStitchDoubleInternal(&H, &b, 0, nf * nf, -1);
+    scStitchDoubleInternal(&H, &b, 0, nf * nf, -1, true);
     for (int h = 0; h < nf; h++) {
         int hIdx = CPARS + h * 8;
         for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) H(i, hIdx + j) = H(hIdx + j, i);

@@ -295,11 +295,11 @@ struct Window {
 
     // accumulators
     template<int mode> void topAddPoint(AccumulatedTopHessianSSE &A, Point &p, int tid);  // AccumulatedTopHessian.cc:9-118
-    void topStitchDoubleInternal(AccumulatedTopHessianSSE &A, MatX *H, VecXd *b, bool usePrior, int min, int max, int tid);  // :193-255
+    void topStitchDoubleInternal(AccumulatedTopHessianSSE &A, MatX *H, VecXd *b, bool usePrior, int min, int max, int tid, bool hostOuter = false);  // :193-255
     void topStitchDoubleMT(AccumulatedTopHessianSSE &A, MatX &H, VecXd &b, bool usePrior, bool MT);  // .h:64-105
     void topStitchDouble(AccumulatedTopHessianSSE &A, MatX &H, VecXd &b, bool usePrior, int tid = 0);  // .cc:129-191
     void scAddPoint(Point &p, bool shiftPriorToZero, int tid);  // AccumulatedSCHessian.cc:9-51
-    void scStitchDoubleInternal(MatX *H, VecXd *b, int min, int max, int tid);  // :53-119
+    void scStitchDoubleInternal(MatX *H, VecXd *b, int min, int max, int tid, bool hostOuter = false);  // :53-119
     void scStitchDoubleMT(MatX &H, VecXd &b, bool MT);  // .h:64-98
     void scStitchDouble(MatX &H, VecXd &b, int tid = 0);  // .cc:121-177
 

@@ -7,6 +7,7 @@
 //   src/internal/Residuals.cc (+ Residuals.h, RawResidualJacobian.h, FrameFramePrecalc.h)   PointFrameResidual::linearize, fixLinearizationF, applyRes/takeData
 //   src/internal/ImmaturePoint.cc (+ ImmaturePoint.h, Feature.h)   ImmaturePoint::ImmaturePoint, traceOn, linearizeResidual
 //   include/internal/ResidualProjections.h                      projectPoint (both overloads), derive_idepth
+//   src/internal/OptimizationBackend/AccumulatedTopHessian.cc, AccumulatedSCHessian.cc (+ their headers)   addPoint<0,1,2>, SC addPoint, stitchDouble, stitchDoubleMT, stitchDoubleInternal
 //   src/frontend/CoarseTracker.cc (+ CoarseTracker.h, Feature.h, Point.h)   CoarseTracker::makeK, setCoarseTrackingRef / makeCoarseDepthL0, calcRes, calcGSSSE, trackNewestCoarse
 //   src/Setting.cc (+ include/Settings.h)                       every setting_* constant and the residual pattern the path reads
 // compiled UNMODIFIED against oracle/ref_shim/NumTypes.h (a stand-in for the Eigen types those headers use; Eigen3, Sophus, glog,
@@ -32,6 +33,8 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "internal/ResidualProjections.h"
 #define private public                    // CoarseTracker.cc is compiled with -Dprivate=public too (Makefile): calcRes / calcGSSSE / buffers
 #include "frontend/CoarseTracker.h"       // the reference's own CoarseTracker; bodies in src/frontend/CoarseTracker.cc
+#include "internal/OptimizationBackend/AccumulatedTopHessian.h"     // the reference's own accumulators; bodies in AccumulatedTopHessian.cc / AccumulatedSCHessian.cc
+#include "internal/OptimizationBackend/AccumulatedSCHessian.h"
 #undef private
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
 
@@ -206,11 +209,25 @@ int oracle_ba_add_residual(void *o, int point, int target);
 void oracle_ba_set_frame_energy_th(void *o, int frame, float th);
 void oracle_ba_finalize(void *o);
 }
-static void pin_linearize() {
+// a small window (oracle side) and its reference-side mirror, shared by pin_linearize and pin_hessians
+struct Scene {
+    int w, h, nF;
+    std::vector<std::vector<float>> imgs;
+    void *o; oracle::Window *W;
+    shared_ptr<ldso::internal::CalibHessian> HC;
+    std::vector<shared_ptr<ldso::internal::FrameHessian>> FH;
+    shared_ptr<ldso::internal::EnergyFunctional> EF;
+    std::vector<Mat18f> adHT;
+    std::vector<Mat88> adHost, adTarget;
+};
+static Scene *make_scene(int nPper) {
     using namespace ldso::internal;
-    const int w = 160, h = 120, nF = 4, nPper = 150;
+    Scene *S = new Scene();
+    const int w = 160, h = 120, nF = 4;
+    S->w = w; S->h = h; S->nF = nF;
     // images: smooth texture + central-difference gradients, (I, dx, dy) AoS like FrameHessian::dI
-    std::vector<std::vector<float>> imgs(nF, std::vector<float>(3 * w * h));
+    std::vector<std::vector<float>> &imgs = S->imgs;
+    imgs.assign(nF, std::vector<float>(3 * w * h));
     for (int f = 0; f < nF; f++) {
         std::vector<float> I(w * h);
         for (int y = 0; y < h; y++) for (int x = 0; x < w; x++)
@@ -224,6 +241,7 @@ static void pin_linearize() {
     }
     void *o = oracle_ba_create(w, h, 0);
     oracle::Window *W = (oracle::Window *) o;
+    S->o = o; S->W = W;
     const double K[4] = {110.0, 112.0, 79.5, 59.5};
     oracle_ba_set_calib(o, K);
     const double cd[4] = {1e-4, -2e-4, 3e-4, 1e-4};
@@ -256,10 +274,12 @@ static void pin_linearize() {
     oracle_ba_finalize(o);
     // the reference-side mirror of the window
     wG[0] = w; hG[0] = h; wM3G = w - 3; hM3G = h - 3;
-    auto HC = std::make_shared<CalibHessian>();
+    S->HC = std::make_shared<CalibHessian>();
+    auto HC = S->HC;
     HC->fx = W->HCalib.fxl(); HC->fy = W->HCalib.fyl(); HC->cx = W->HCalib.cxl(); HC->cy = W->HCalib.cyl();
     HC->fxi = W->HCalib.fxli(); HC->fyi = W->HCalib.fyli();
-    std::vector<shared_ptr<FrameHessian>> FH(nF);
+    std::vector<shared_ptr<FrameHessian>> &FH = S->FH;
+    FH.resize(nF);
     for (int f = 0; f < nF; f++) {
         FH[f] = std::make_shared<FrameHessian>();
         FH[f]->idx = f; FH[f]->dI = (Eigen::Vector3f *) imgs[f].data(); FH[f]->frameEnergyTH = W->frames[f].frameEnergyTH;
@@ -275,12 +295,34 @@ static void pin_linearize() {
             d.PRE_aff_mode[0] = s.PRE_aff_mode[0]; d.PRE_aff_mode[1] = s.PRE_aff_mode[1]; d.PRE_b0_mode = s.PRE_b0_mode; d.distanceLL = s.distanceLL;
         }
     }
-    auto EF = std::make_shared<EnergyFunctional>();
+    S->EF = std::make_shared<EnergyFunctional>();
+    auto EF = S->EF;
     EF->nFrames = nF;
-    std::vector<Mat18f> adHT(nF * nF);
+    std::vector<Mat18f> &adHT = S->adHT;
+    adHT.resize(nF * nF);
     for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) adHT[q][i] = W->adHTdeltaF[8 * q + i];
     EF->adHTdeltaF = adHT.data();
     for (int i = 0; i < 4; i++) EF->cDeltaF[i] = W->cDeltaF[i];
+    // adjoints, calibration prior and frame priors for the stitching (EnergyFunctional::setAdjointsF, FrameHessian::takeData)
+    S->adHost.resize(nF * nF); S->adTarget.resize(nF * nF);
+    for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) {
+        S->adHost[q](i, j) = W->adHost[64 * q + 8 * i + j]; S->adTarget[q](i, j) = W->adTarget[64 * q + 8 * i + j];
+    }
+    EF->adHost = S->adHost.data(); EF->adTarget = S->adTarget.data();
+    for (int i = 0; i < 4; i++) EF->cPrior[i] = W->cPrior[i];
+    EF->frames = FH;
+    for (int f = 0; f < nF; f++) for (int i = 0; i < 8; i++) { FH[f]->prior[i] = W->frames[f].prior[i]; FH[f]->delta_prior[i] = W->frames[f].delta_prior[i]; }
+    return S;
+}
+
+static void pin_linearize() {
+    using namespace ldso::internal;
+    Scene *S = make_scene(150);
+    oracle::Window *W = S->W;
+    auto HC = S->HC; auto EF = S->EF;
+    std::vector<shared_ptr<FrameHessian>> &FH = S->FH;
+    std::vector<std::vector<float>> &imgs = S->imgs;
+    const int nF = S->nF, w = S->w, h = S->h; (void) w; (void) h;
     bool okRet = true, okState = true, okJ = true, okProj = true, okTake = true, okFix = true;
     int nIn = 0, nOob = 0, nOut = 0;
     for (size_t ri = 0; ri < W->residuals.size(); ri++) {
@@ -386,9 +428,160 @@ static void pin_linearize() {
         CHECK(okTrace, "ImmaturePoint::traceOn (status, idepth interval, quality, lastTraceUV, lastTracePixelInterval)");
         CHECK(okLin, "ImmaturePoint::linearizeResidual (energy, Hdd, bd, state)");
     }
-    oracle_ba_destroy(o);
+    oracle_ba_destroy(S->o); delete S;
 }
 
+
+
+// ---- AccumulatedTopHessianSSE / AccumulatedSCHessianSSE: the reference's own addPoint<mode> and stitching against oracle/ba.cc.
+// addPoint is float SSE / scalar code with an explicit order: bit-exact pin. The stitching is written in Eigen expressions; compiled
+// against the stand-in their 8x8 products are row-times-column sums accumulated left to right and A*B*C^T is (A*B)*C^T, which is what the
+// restatement assumes too, so equality here pins the block / index / ordering structure of the stitch, not Eigen's
+// own product kernels.
+static bool same_dyn(const MatXX &A, const oracle::MatX &B) { return A.r == B.r && A.c == B.c && memcmp(A.d.data(), B.d.data(), 8 * A.d.size()) == 0; }
+static bool same_dyn(const VecX &a, const oracle::VecXd &b) { return a.d.size() == b.size() && memcmp(a.d.data(), b.data(), 8 * b.size()) == 0; }
+static void pin_hessians() {
+    using namespace ldso::internal;
+    Scene *S = make_scene(150);
+    oracle::Window *W = S->W;
+    auto HC = S->HC; auto EF = S->EF;
+    const int nF = S->nF, nP = (int) W->points.size();
+    std::vector<shared_ptr<PointHessian>> PH(nP);
+    int nLin = 0, nAct = 0;
+    for (int pi = 0; pi < nP; pi++) {
+        oracle::Point &op = W->points[pi];
+        if (pi % 5 == 0) op.priorF = frand(1.f, 2000.f);
+        PH[pi] = std::make_shared<PointHessian>();
+        auto ph = PH[pi];
+        ph->u = op.u; ph->v = op.v; ph->idepth_scaled = op.idepth_scaled; ph->idepth_zero_scaled = op.idepth_zero_scaled; ph->deltaF = op.deltaF; ph->priorF = op.priorF;
+        memcpy(ph->color, op.color, 32); memcpy(ph->weights, op.weights, 32);
+        int k = 0;
+        for (int ri : op.residuals) {
+            oracle::Residual &orr = W->residuals[ri];
+            auto r = std::make_shared<PointFrameResidual>(ph, S->FH[orr.host], S->FH[orr.target]);
+            r->hostIDX = orr.hostIDX = orr.host; r->targetIDX = orr.targetIDX = orr.target;
+            r->linearize(HC); W->linearize(orr);
+            r->applyRes(true); W->applyRes(orr, true);
+            // every 4th point has all its active residuals linearised (a marginalisation candidate), the others two out of three
+            if (r->isActive() && (pi % 4 == 0 || k % 3 != 0)) { r->fixLinearizationF(EF); W->fixLinearizationF(orr); nLin++; }
+            nAct += r->isActive();
+            ph->residuals.push_back(r); k++;
+        }
+    }
+    printf("  hessian pin: %d points, %d active residuals, %d of them linearised\n", nP, nAct, nLin);
+    CHECK(nAct > 800 && nLin > 300 && nLin < nAct, "hessian scenario has active, linearised and inactive residuals");
+    auto same_top_acc = [&](AccumulatedTopHessianSSE &R, oracle::AccumulatedTopHessianSSE &O, int tid) {
+        bool ok = R.nres[tid] == O.nres[tid];
+        for (int q = 0; q < nF * nF; q++) {
+            ok &= R.acc[tid][q].num == O.acc[tid][q].num;
+            for (int r = 0; r < 13; r++) for (int c = 0; c < 13; c++) ok &= memcmp(&R.acc[tid][q].H(r, c), &O.acc[tid][q].H[r * 13 + c], 4) == 0;
+        }
+        return ok;
+    };
+    auto same_point_acc = [&](bool L) {
+        bool ok = true;
+        for (int pi = 0; pi < nP; pi++) {
+            const oracle::Point &op = W->points[pi]; const PointHessian &ph = *PH[pi];
+            if (L) ok &= memcmp(&ph.Hdd_accLF, &op.Hdd_accLF, 4) == 0 && memcmp(&ph.bd_accLF, &op.bd_accLF, 4) == 0 && memcmp(ph.Hcd_accLF.d, op.Hcd_accLF, 16) == 0;
+            else ok &= memcmp(&ph.Hdd_accAF, &op.Hdd_accAF, 4) == 0 && memcmp(&ph.bd_accAF, &op.bd_accAF, 4) == 0 && memcmp(ph.Hcd_accAF.d, op.Hcd_accAF, 16) == 0;
+        }
+        return ok;
+    };
+    MatXX Hr; VecX br; oracle::MatX Ho; oracle::VecXd bo;
+    // active residuals: addPoint<0>, stitchDouble and stitchDoubleMT(MT = false), no prior
+    AccumulatedTopHessianSSE RA; oracle::AccumulatedTopHessianSSE OA;
+    RA.setZero(nF); OA.setZero(nF, 0);
+    for (int pi = 0; pi < nP; pi++) { RA.addPoint<0>(PH[pi], EF.get()); W->topAddPoint<0>(OA, W->points[pi], 0); }
+    CHECK(same_point_acc(false), "AccumulatedTopHessianSSE::addPoint<0>: Hdd_accAF, bd_accAF, Hcd_accAF of every point");
+    RA.stitchDouble(Hr, br, EF.get(), false, false); W->topStitchDouble(OA, Ho, bo, false);
+    CHECK(same_top_acc(RA, OA, 0), "addPoint<0>: all nF*nF 13x13 AccumulatorApprox blocks after finish, nres");
+    if (!same_dyn(Hr, Ho)) { int nb = 0; double mx = 0; for (size_t i = 0; i < Hr.d.size(); i++) if (Hr.d[i] != Ho.d[i]) { if (nb < 5) printf("   H[%zu,%zu] ref %.17g oracle %.17g\n", i % Hr.r, i / Hr.r, Hr.d[i], Ho.d[i]); nb++; mx = std::max(mx, fabs(Hr.d[i] - Ho.d[i])); } printf("   %d entries differ, max abs %.3g\n", nb, mx); }
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "AccumulatedTopHessianSSE::stitchDouble (active, no prior): H, b");
+    RA.stitchDoubleMT(nullptr, Hr, br, EF.get(), false, false); W->topStitchDoubleMT(OA, Ho, bo, false, false);
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "AccumulatedTopHessianSSE::stitchDoubleMT(MT = false) (active): H, b");
+    // linearised residuals: addPoint<1>, with the frame / calibration priors
+    AccumulatedTopHessianSSE RL; oracle::AccumulatedTopHessianSSE OL;
+    RL.setZero(nF); OL.setZero(nF, 0);
+    for (int pi = 0; pi < nP; pi++) { RL.addPoint<1>(PH[pi], EF.get()); W->topAddPoint<1>(OL, W->points[pi], 0); }
+    CHECK(same_point_acc(true), "AccumulatedTopHessianSSE::addPoint<1>: Hdd_accLF, bd_accLF, Hcd_accLF of every point");
+    RL.stitchDoubleMT(nullptr, Hr, br, EF.get(), true, false); W->topStitchDoubleMT(OL, Ho, bo, true, false);
+    CHECK(same_top_acc(RL, OL, 0), "addPoint<1>: all AccumulatorApprox blocks after finish, nres");
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "stitchDoubleMT(MT = false) (linearised, usePrior): H, b");
+    RL.stitchDouble(Hr, br, EF.get(), true, true); W->topStitchDouble(OL, Ho, bo, true);
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "stitchDouble (linearised, usePrior): H, b");
+    // Schur complement accumulator: addPoint(shiftPriorToZero = true) over all points
+    AccumulatedSCHessianSSE RS; oracle::AccumulatedSCHessianSSE &OS = W->accSSE_bot;
+    RS.setZero(nF); OS.setZero(nF, 0);
+    for (int pi = 0; pi < nP; pi++) { RS.addPoint(PH[pi], true); W->scAddPoint(W->points[pi], true, 0); }
+    {
+        bool ok = true;
+        for (int pi = 0; pi < nP; pi++) {
+            const oracle::Point &op = W->points[pi]; const PointHessian &ph = *PH[pi];
+            ok &= memcmp(&ph.HdiF, &op.HdiF, 4) == 0 && memcmp(&ph.bdSumF, &op.bdSumF, 4) == 0 && memcmp(&ph.idepth_hessian, &op.idepth_hessian, 4) == 0;
+        }
+        CHECK(ok, "AccumulatedSCHessianSSE::addPoint: HdiF, bdSumF, idepth_hessian of every point");
+    }
+    RS.stitchDouble(Hr, br, EF.get()); W->scStitchDouble(Ho, bo);
+    {
+        bool ok = true;
+        for (int q = 0; q < nF * nF; q++) {
+            ok &= RS.accE[0][q].num == OS.accE[0][q].num && RS.accEB[0][q].num == OS.accEB[0][q].num;
+            ok &= memcmp(RS.accEB[0][q].A1m.d, OS.accEB[0][q].A1m, 32) == 0 && memcmp(RS.accE[0][q].A1m.d, OS.accE[0][q].A1m, 128) == 0;      // both column-major
+        }
+        for (int q = 0; q < nF * nF * nF; q++) {
+            ok &= RS.accD[0][q].num == OS.accD[0][q].num;
+            ok &= memcmp(RS.accD[0][q].A1m.d, OS.accD[0][q].A1m, 256) == 0;
+        }
+        ok &= memcmp(RS.accbc[0].A1m.d, OS.accbc[0].A1m, 16) == 0 && memcmp(RS.accHcc[0].A1m.d, OS.accHcc[0].A1m, 64) == 0;
+        CHECK(ok, "SC addPoint: accE, accEB, accD, accHcc, accbc after finish");
+    }
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "AccumulatedSCHessianSSE::stitchDouble: H_sc, b_sc");
+    RS.stitchDoubleMT(nullptr, Hr, br, EF.get(), false); W->scStitchDoubleMT(Ho, bo, false);
+    CHECK(same_dyn(Hr, Ho) && same_dyn(br, bo), "AccumulatedSCHessianSSE::stitchDoubleMT(MT = false): H_sc, b_sc");
+    // marginalisation: addPoint<2> + SC addPoint(false) on the points whose active residuals are all linearised (marginalizePointsF)
+    {
+        AccumulatedTopHessianSSE RM; oracle::AccumulatedTopHessianSSE OM;
+        RM.setZero(nF); OM.setZero(nF, 0); RS.setZero(nF); OS.setZero(nF, 0);
+        int nM = 0;
+        for (int pi = 0; pi < nP; pi += 4) { RM.addPoint<2>(PH[pi], EF.get()); W->topAddPoint<2>(OM, W->points[pi], 0); RS.addPoint(PH[pi], false); W->scAddPoint(W->points[pi], false, 0); nM++; }
+        bool ok = same_point_acc(true) && same_point_acc(false);
+        RM.stitchDouble(Hr, br, EF.get(), false, false); W->topStitchDouble(OM, Ho, bo, false);
+        ok &= same_top_acc(RM, OM, 0) && same_dyn(Hr, Ho) && same_dyn(br, bo);
+        RS.stitchDouble(Hr, br, EF.get()); W->scStitchDouble(Ho, bo);
+        ok &= same_dyn(Hr, Ho) && same_dyn(br, bo);
+        CHECK(ok && nM > 100, "addPoint<2> + SC addPoint(shiftPriorToZero = false) + both stitchDouble on the marginalisation subset");
+    }
+    // the multi-threaded layout, driven by hand with a fixed chunk -> thread assignment (the reference's worker threads grab chunks
+    // dynamically, so its own MT result depends on scheduling): addPoint into acc[tid], stitchDoubleInternal(min, max, tid) aggregating
+    // over the NUM_THREADS accumulators
+    {
+        AccumulatedTopHessianSSE RT; oracle::AccumulatedTopHessianSSE OT;
+        const int per = (nP + NUM_THREADS - 1) / NUM_THREADS;
+        for (int tid = 0; tid < NUM_THREADS; tid++) {
+            RT.setZero(nF, 0, 0, 0, tid); OT.setZero(nF, tid); RS.setZero(nF, 0, 0, 0, tid); OS.setZero(nF, tid);
+            for (int pi = tid * per; pi < std::min(nP, (tid + 1) * per); pi++) {
+                RT.addPoint<0>(PH[pi], EF.get(), tid); W->topAddPoint<0>(OT, W->points[pi], tid);
+                RS.addPoint(PH[pi], true, tid); W->scAddPoint(W->points[pi], true, tid);
+            }
+        }
+        const int n = nF * 8 + CPARS, nk = nF * nF, kper = (nk + NUM_THREADS - 1) / NUM_THREADS;
+        MatXX Hs[NUM_THREADS], Hc[NUM_THREADS]; VecX bs[NUM_THREADS], bc[NUM_THREADS];
+        oracle::MatX Hso[NUM_THREADS], Hco[NUM_THREADS]; oracle::VecXd bso[NUM_THREADS], bco[NUM_THREADS];
+        for (int i = 0; i < NUM_THREADS; i++) {
+            Hs[i] = MatXX::Zero(n, n); bs[i] = VecX::Zero(n); Hc[i] = MatXX::Zero(n, n); bc[i] = VecX::Zero(n);
+            Hso[i] = oracle::MatX(n, n); bso[i].assign(n, 0.0); Hco[i] = oracle::MatX(n, n); bco[i].assign(n, 0.0);
+        }
+        bool ok = true;
+        for (int tid = 0; tid < NUM_THREADS; tid++) {
+            const int mn = std::min(nk, tid * kper), mx = std::min(nk, (tid + 1) * kper);
+            RT.stitchDoubleInternal(Hs, bs, EF.get(), true, mn, mx, nullptr, tid); W->topStitchDoubleInternal(OT, Hso, bso, true, mn, mx, tid);
+            RS.stitchDoubleInternal(Hc, bc, EF.get(), mn, mx, nullptr, tid); W->scStitchDoubleInternal(Hco, bco, mn, mx, tid);
+        }
+        for (int tid = 0; tid < NUM_THREADS; tid++) ok &= same_dyn(Hs[tid], Hso[tid]) && same_dyn(bs[tid], bso[tid]) && same_dyn(Hc[tid], Hco[tid]) && same_dyn(bc[tid], bco[tid]);
+        CHECK(ok, "stitchDoubleInternal (top with prior, and SC) aggregating NUM_THREADS accumulators, per-thread partial H / b");
+    }
+    oracle_ba_destroy(S->o); delete S;
+}
 
 // Eigen::LDLT<Mat88 / 77 / 66>::solve as the stand-in forwards it: the oracle's restatement (omath.h) on both sides of the pin
 extern "C" void ref_shim_ldlt_solve(int n, const double *A, const double *b, double *x) {
@@ -440,10 +633,10 @@ static void pin_tracker() {
     }
     auto lastRef = FH[nKF - 1];
     for (int l = 0; l < L; l++) lastRef->dIp[l] = (Vec3f *) pr[l];
-    lastRef->dI = lastRef->dIp[0]; lastRef->ab_exposure = 0.9f; lastRef->aff = AffLight(0.02f, -1.5f);
+    lastRef->dI = lastRef->dIp[0]; lastRef->ab_exposure = 1.0f; lastRef->aff = AffLight(0.02f, -1.5f);
     auto newFH = std::make_shared<FrameHessian>();
     for (int l = 0; l < L; l++) newFH->dIp[l] = (Vec3f *) pn[l];
-    newFH->dI = newFH->dIp[0]; newFH->ab_exposure = 1.1f;
+    newFH->dI = newFH->dIp[0]; newFH->ab_exposure = 1.061f;     // so that the affine brightness (0, 0) is close to the truth (gain 1.04)
     std::vector<float> cpt, hdi;            // the oracle's input: the contributions in the order the reference visits them
     std::vector<shared_ptr<PointFrameResidual>> keep;
     int nSkipped = 0;
@@ -510,7 +703,7 @@ static void pin_tracker() {
         Vec6 xi; double xia[6];
         for (int i = 0; i < 6; i++) { xia[i] = (trial == 0) ? 0.0 : frand(-1.f, 1.f) * (i < 3 ? 0.01 : 0.004) * (1 + trial % 3); xi[i] = xia[i]; }
         const SE3 Tr = SE3::exp(xi); const oracle::SE3 To = oracle::SE3::exp(xia);
-        const AffLight aff(frand(-0.05f, 0.08f), frand(-4.f, 4.f));
+        const AffLight aff(frand(-0.03f, 0.03f), frand(-4.f, 4.f));
         const float cutoff = (trial % 4 == 1) ? 6.f : (trial % 4 == 2 ? 40.f : 20.f);
         for (int l = L - 1; l >= 0; l--) {
             const Vec6 rr = R.calcRes(l, Tr, aff, cutoff);
@@ -533,6 +726,7 @@ static void pin_tracker() {
             for (int i = 0; i < 8; i++) { okH &= memcmp(&br[i], &bo[i], 8) == 0; for (int j = 0; j < 8; j++) okH &= memcmp(&Hr(i, j), &Ho[i * 8 + j], 8) == 0; }
         }
     }
+    printf("  tracker pin: %d of %d calcRes evaluations had saturated residuals\n", nSat, nEval);
     CHECK(nSat > 0 && nSat < nEval, "calcRes scenario exercises the saturated (cutoff) branch on some evaluations");
     CHECK(okRes, "CoarseTracker::calcRes return vector (E, count, flow indicators, saturated ratio)");
     CHECK(okBuf, "calcRes warped buffers (idepth, u, v, dx, dy, residual, weight, refColor, padded count)");
@@ -601,9 +795,10 @@ int main() {
     pin_afflight();
     pin_projections();
     pin_linearize();
+    pin_hessians();
     pin_tracker();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc and CoarseTracker.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc and CoarseTracker.cc\n", checks);
     return 0;
 }

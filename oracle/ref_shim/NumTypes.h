@@ -80,7 +80,14 @@ struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     T squaredNorm() const { T s = d[0] * d[0]; for (int i = 1; i < R * C; i++) s += d[i] * d[i]; return s; }
     T norm() const { return std::sqrt(squaredNorm()); }
     T sum() const { T s = d[0]; for (int i = 1; i < R * C; i++) s += d[i]; return s; }
-    RowView<T, R> transpose() const { static_assert(C == 1, "only column vectors are transposed here"); return RowView<T, R>{this}; }
+    // a column vector's transpose stays a view (row * matrix, column * row products below); any other shape transposes by value
+    template<int C1 = C> typename std::enable_if<C1 == 1, RowView<T, R>>::type transpose() const { return RowView<T, R>{this}; }
+    template<int C1 = C> typename std::enable_if<C1 != 1, Matrix<T, C, R>>::type transpose() const {
+        Matrix<T, C, R> o; for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) o(c, r) = (*this)(r, c); return o;
+    }
+    T *data() { return d; }
+    const T *data() const { return d; }
+    Matrix cwiseProduct(const Matrix &o) const { Matrix m; for (int i = 0; i < R * C; i++) m.d[i] = d[i] * o.d[i]; return m; }
     CommaInit<T, R, C> operator<<(T v) { d[0] = v; return CommaInit<T, R, C>{this, 1}; }
     LDLTOf<T, R> ldlt() const { static_assert(R == C, "square"); return LDLTOf<T, R>{*this}; }
     // 3x3 inverse by cofactors / determinant (Eigen's compute_inverse for size 3)
@@ -121,6 +128,47 @@ struct Block : Matrix<T, BR, BC> {
     template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
     Block &operator*=(S s) { Matrix<T, BR, BC>::operator*=(s); push(); return *this; }
     void setZero() { Matrix<T, BR, BC>::setZero(); push(); }
+    Block &noalias() { return *this; }
+    Block &operator+=(const Matrix<T, BR, BC> &m) { Matrix<T, BR, BC>::operator+=(m); push(); return *this; }
+    Block &operator-=(const Matrix<T, BR, BC> &m) { Matrix<T, BR, BC>::operator-=(m); push(); return *this; }
+};
+// N consecutive diagonal entries of a dynamic matrix (H.diagonal().segment<8>(i) += v)
+template<int N> struct DiagSeg {
+    double *p; int stride;
+    DiagSeg &operator+=(const Matrix<double, N, 1> &v) { for (int i = 0; i < N; i++) p[(size_t) i * stride] += v.d[i]; return *this; }
+};
+struct DiagView {
+    double *p; int stride;
+    template<int N> DiagSeg<N> segment(int i0) { return DiagSeg<N>{p + (size_t) i0 * stride, stride}; }
+    template<int N> DiagSeg<N> head() { return segment<N>(0); }
+};
+// Matrix<double, Dynamic, Dynamic> and Matrix<double, Dynamic, 1> as the Hessian stitching uses them: zero-initialised storage,
+// fixed-size block views, whole-matrix +=
+struct DynMat {
+    int r = 0, c = 0;
+    std::vector<double> d;       // column-major
+    static DynMat Zero(int r_, int c_) { DynMat m; m.r = r_; m.c = c_; m.d.assign((size_t) r_ * c_, 0.0); return m; }
+    int rows() const { return r; }
+    int cols() const { return c; }
+    double &operator()(int i, int j) { return d[(size_t) j * r + i]; }
+    double operator()(int i, int j) const { return d[(size_t) j * r + i]; }
+    template<int BR, int BC> Block<double, BR, BC> block(int i, int j) { return Block<double, BR, BC>(&d[(size_t) j * r + i], r); }
+    template<int BR, int BC> Block<double, BR, BC> topLeftCorner() { return block<BR, BC>(0, 0); }
+    DiagView diagonal() { return DiagView{d.data(), r + 1}; }
+    DynMat &noalias() { return *this; }
+    DynMat &operator+=(const DynMat &o) { for (size_t i = 0; i < d.size(); i++) d[i] += o.d[i]; return *this; }
+};
+struct DynVec {
+    std::vector<double> d;
+    static DynVec Zero(int n) { DynVec v; v.d.assign(n, 0.0); return v; }
+    int size() const { return (int) d.size(); }
+    int rows() const { return (int) d.size(); }
+    double &operator[](int i) { return d[i]; }
+    double operator[](int i) const { return d[i]; }
+    template<int N> Block<double, N, 1> segment(int i0) { return Block<double, N, 1>(&d[i0], N); }
+    template<int N> Block<double, N, 1> head() { return segment<N>(0); }
+    DynVec &noalias() { return *this; }
+    DynVec &operator+=(const DynVec &o) { for (size_t i = 0; i < d.size(); i++) d[i] += o.d[i]; return *this; }
 };
 
 template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
@@ -177,7 +225,15 @@ typedef Eigen::Matrix<double, 7, 1> Vec7;
 typedef Eigen::Matrix<double, 8, 1> Vec8;
 typedef Eigen::Matrix<double, 10, 1> Vec10;
 typedef Eigen::Matrix<double, 3, 3> Mat33;
+typedef Eigen::Matrix<double, 6, 6> Mat66;
 typedef Eigen::Matrix<double, 8, 8> Mat88;
+typedef Eigen::Matrix<float, 8, 8> Mat88f;
+typedef Eigen::Matrix<double, 8, CPARS> Mat8C;
+typedef Eigen::Matrix<double, CPARS, CPARS> MatCC;
+typedef Eigen::Matrix<double, 8 + CPARS + 1, 8 + CPARS + 1> MatPCPC;
+typedef Eigen::Matrix<double, CPARS, 1> VecC;
+typedef Eigen::DynMat MatXX;
+typedef Eigen::DynVec VecX;
 typedef Eigen::Matrix<float, 2, 1> Vec2f;
 typedef Eigen::Matrix<float, 3, 1> Vec3f;
 typedef Eigen::Matrix<unsigned char, 3, 1> Vec3b;
@@ -210,11 +266,3 @@ public:
 };
 }
 typedef Sophus::SE3d SE3;
-// GlobalFuncs.h's eigenTestNan(const MatXX&) only needs rows(), cols() and operator(); it is not called by the pin
-struct MatXX {
-    int r = 0, c = 0;
-    std::vector<double> d;
-    int rows() const { return r; }
-    int cols() const { return c; }
-    double operator()(int i, int j) const { return d[(size_t) j * r + i]; }
-};

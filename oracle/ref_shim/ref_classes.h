@@ -42,6 +42,8 @@ public:
     AffLight aff;
     AffLight aff_g2l() { return aff; }
     SE3 PRE_worldToCam, PRE_camToWorld;
+    // read by AccumulatedTopHessianSSE::stitchDouble* (FrameHessian.h: prior, delta_prior, set by takeData())
+    Vec8 prior = Vec8::Zero(), delta_prior = Vec8::Zero();
 };
 class PointHessian {          // include/internal/PointHessian.h:83-107
 public:
@@ -49,12 +51,21 @@ public:
     float color[MAX_RES_PER_POINT], weights[MAX_RES_PER_POINT];
     std::pair<shared_ptr<PointFrameResidual>, int /*ResState*/> lastResiduals[2];      // PointHessian.h:103 (ResState is a plain enum: compares with int)
     float HdiF = 0;                                                                     // PointHessian.h:124
+    // read / written by AccumulatedTopHessianSSE::addPoint and AccumulatedSCHessianSSE::addPoint (PointHessian.h:100,110-131)
+    std::vector<shared_ptr<PointFrameResidual>> residuals;
+    float priorF = 0, bdSumF = 0, idepth_hessian = 0, maxRelBaseline = 0;
+    float Hdd_accLF = 0, bd_accLF = 0, Hdd_accAF = 0, bd_accAF = 0;
+    VecCf Hcd_accLF = VecCf::Zero(), Hcd_accAF = VecCf::Zero();
 };
 class EnergyFunctional {      // include/internal/OptimizationBackend/EnergyFunctional.h:152,213,222
 public:
     int nFrames = 0;
     Mat18f *adHTdeltaF = nullptr;
     VecCf cDeltaF;
+    // read by the stitchDouble* functions (EnergyFunctional.h: adHost, adTarget, cPrior, frames)
+    Mat88 *adHost = nullptr, *adTarget = nullptr;
+    VecC cPrior;
+    std::vector<shared_ptr<FrameHessian>> frames;
 };
 } }
 namespace ldso {
@@ -64,3 +75,5 @@ struct Frame {                // include/Frame.h (the members ImmaturePoint.cc a
     std::vector<shared_ptr<Feature>> features;
 };
 }
+// the real PointHessian.h pulls in the residual class: the reference's own Residuals.h (+ RawResidualJacobian.h), unmodified
+#include "internal/Residuals.h"
