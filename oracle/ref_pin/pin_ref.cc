@@ -27,7 +27,8 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "AffLight.h"
 #include "internal/GlobalFuncs.h"
 #include "internal/OptimizationBackend/MatrixAccumulators.h"
-#include "../ref_shim/ref_classes.h"      // stand-ins for FrameHessian / PointHessian / CalibHessian / EnergyFunctional
+#include "../ref_shim/ref_classes.h"      // Frame stand-in + the reference's own FrameHessian / PointHessian / CalibHessian headers
+#include "internal/OptimizationBackend/EnergyFunctional.h"
 #include "internal/Residuals.h"           // the reference's own PointFrameResidual (its linearize lives in src/internal/Residuals.cc)
 #include "internal/ImmaturePoint.h"       // the reference's own ImmaturePoint (+ Feature.h); bodies in src/internal/ImmaturePoint.cc
 #include "internal/ResidualProjections.h"
@@ -37,6 +38,23 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "internal/OptimizationBackend/AccumulatedSCHessian.h"
 #undef private
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
+
+// src/Camera.cc and src/Point.cc are not compiled (they reach into the front end); these are their plain constructors
+ldso::Camera::Camera(double fx_, double fy_, double cx_, double cy_) { fx = fx_; fy = fy_; cx = cx_; cy = cy_; }
+ldso::Point::Point() {}
+static shared_ptr<ldso::internal::CalibHessian> make_calib(double fx, double fy, double cx, double cy) {
+    return std::make_shared<ldso::internal::CalibHessian>(std::make_shared<ldso::Camera>(fx, fy, cx, cy));
+}
+// FrameHessian's destructor frees the pyramids makeImages() allocated; frames whose pyramids point into harness buffers drop them first
+static shared_ptr<ldso::internal::FrameHessian> make_fh(shared_ptr<ldso::Frame> fr, bool ownsPyramid = false) {
+    auto *p = new ldso::internal::FrameHessian(fr);
+    for (int i = 0; i < PYR_LEVELS; i++) { p->dIp[i] = nullptr; p->absSquaredGrad[i] = nullptr; }
+    if (ownsPyramid) return shared_ptr<ldso::internal::FrameHessian>(p);
+    return shared_ptr<ldso::internal::FrameHessian>(p, [](ldso::internal::FrameHessian *q) {
+        for (int i = 0; i < PYR_LEVELS; i++) { q->dIp[i] = nullptr; q->absSquaredGrad[i] = nullptr; }
+        delete q;
+    });
+}
 
 static unsigned long long rng_state = 88172645463325252ull;
 static inline float frand(float lo, float hi) {
@@ -162,8 +180,8 @@ static void pin_projections() {
     oracle::Calib OC;
     OC.value_scaledf[0] = 400.25f; OC.value_scaledf[1] = 401.5f; OC.value_scaledf[2] = 319.5f; OC.value_scaledf[3] = 239.5f;
     OC.value_scaledi[0] = 1.0f / OC.value_scaledf[0]; OC.value_scaledi[1] = 1.0f / OC.value_scaledf[1];
-    auto HC = std::make_shared<CalibHessian>();
-    HC->fx = OC.fxl(); HC->fy = OC.fyl(); HC->cx = OC.cxl(); HC->cy = OC.cyl(); HC->fxi = OC.fxli(); HC->fyi = OC.fyli();
+    auto HC = make_calib(400.25, 401.5, 319.5, 239.5);
+    if (memcmp(HC->value_scaledf.d, OC.value_scaledf, 16) != 0 || HC->fxli() != OC.fxli() || HC->fyli() != OC.fyli()) { printf("PIN MISMATCH: CalibHessian constructor\n"); fails++; }
     wM3G = 640 - 3; hM3G = 480 - 3;
     bool okA = true, okB = true, okD = true;
     for (int k = 0; k < 20000; k++) {
@@ -217,8 +235,6 @@ struct Scene {
     shared_ptr<ldso::internal::CalibHessian> HC;
     std::vector<shared_ptr<ldso::internal::FrameHessian>> FH;
     shared_ptr<ldso::internal::EnergyFunctional> EF;
-    std::vector<Mat18f> adHT;
-    std::vector<Mat88> adHost, adTarget;
 };
 static Scene *make_scene(int nPper) {
     using namespace ldso::internal;
@@ -274,14 +290,16 @@ static Scene *make_scene(int nPper) {
     oracle_ba_finalize(o);
     // the reference-side mirror of the window
     wG[0] = w; hG[0] = h; wM3G = w - 3; hM3G = h - 3;
-    S->HC = std::make_shared<CalibHessian>();
+    S->HC = make_calib(K[0], K[1], K[2], K[3]);
     auto HC = S->HC;
-    HC->fx = W->HCalib.fxl(); HC->fy = W->HCalib.fyl(); HC->cx = W->HCalib.cxl(); HC->cy = W->HCalib.cyl();
-    HC->fxi = W->HCalib.fxli(); HC->fyi = W->HCalib.fyli();
+    for (int i = 0; i < 4; i++) {       // mirror the oracle's calibration state (value, zero point, float copies)
+        HC->value_zero[i] = W->HCalib.value_zero[i]; HC->value[i] = W->HCalib.value[i]; HC->value_scaled[i] = W->HCalib.value_scaled[i];
+        HC->value_minus_value_zero[i] = W->HCalib.value_minus_value_zero[i]; HC->value_scaledf[i] = W->HCalib.value_scaledf[i]; HC->value_scaledi[i] = W->HCalib.value_scaledi[i];
+    }
     std::vector<shared_ptr<FrameHessian>> &FH = S->FH;
     FH.resize(nF);
     for (int f = 0; f < nF; f++) {
-        FH[f] = std::make_shared<FrameHessian>();
+        FH[f] = make_fh(nullptr);
         FH[f]->idx = f; FH[f]->dI = (Eigen::Vector3f *) imgs[f].data(); FH[f]->frameEnergyTH = W->frames[f].frameEnergyTH;
         FH[f]->targetPrecalc.resize(nF);
         for (int t = 0; t < nF; t++) {
@@ -298,17 +316,14 @@ static Scene *make_scene(int nPper) {
     S->EF = std::make_shared<EnergyFunctional>();
     auto EF = S->EF;
     EF->nFrames = nF;
-    std::vector<Mat18f> &adHT = S->adHT;
-    adHT.resize(nF * nF);
-    for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) adHT[q][i] = W->adHTdeltaF[8 * q + i];
-    EF->adHTdeltaF = adHT.data();
+    EF->adHTdeltaF = new Mat18f[nF * nF];        // owned (delete[]d) by the reference's EnergyFunctional
+    for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) EF->adHTdeltaF[q][i] = W->adHTdeltaF[8 * q + i];
     for (int i = 0; i < 4; i++) EF->cDeltaF[i] = W->cDeltaF[i];
     // adjoints, calibration prior and frame priors for the stitching (EnergyFunctional::setAdjointsF, FrameHessian::takeData)
-    S->adHost.resize(nF * nF); S->adTarget.resize(nF * nF);
+    EF->adHost = new Mat88[nF * nF]; EF->adTarget = new Mat88[nF * nF];
     for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) {
-        S->adHost[q](i, j) = W->adHost[64 * q + 8 * i + j]; S->adTarget[q](i, j) = W->adTarget[64 * q + 8 * i + j];
+        EF->adHost[q](i, j) = W->adHost[64 * q + 8 * i + j]; EF->adTarget[q](i, j) = W->adTarget[64 * q + 8 * i + j];
     }
-    EF->adHost = S->adHost.data(); EF->adTarget = S->adTarget.data();
     for (int i = 0; i < 4; i++) EF->cPrior[i] = W->cPrior[i];
     EF->frames = FH;
     for (int f = 0; f < nF; f++) for (int i = 0; i < 8; i++) { FH[f]->prior[i] = W->frames[f].prior[i]; FH[f]->delta_prior[i] = W->frames[f].delta_prior[i]; }
@@ -592,8 +607,19 @@ extern "C" void ref_shim_ldlt_solve(int n, const double *A, const double *b, dou
     for (int i = 0; i < n; i++) x[i] = r[i];
 }
 
-// src/Point.cc (not compiled here: it reaches into Frame / ImmaturePoint) only numbers the point in this constructor
-ldso::Point::Point() {}
+// Eigen's PartialPivLU inverse (Mat88::inverse() in marginalizeFrame) and JacobiSVD (orthogonalize), forwarded likewise
+extern "C" void ref_shim_inverse_lu(int n, const double *A, double *out) {
+    oracle::MatX M(n, n);
+    for (int i = 0; i < n * n; i++) M.d[i] = A[i];
+    const oracle::MatX I = oracle::inverse_partial_piv_lu(M);
+    for (int i = 0; i < n * n; i++) out[i] = I.d[i];
+}
+extern "C" void ref_shim_jacobi_svd(int m, int n, const double *A, double *U, double *S, double *V) {
+    oracle::MatX M(m, n), Uo, Vo; oracle::VecXd So;
+    for (int i = 0; i < m * n; i++) M.d[i] = A[i];
+    oracle::jacobi_svd(M, Uo, So, Vo);
+    memcpy(U, Uo.d.data(), 8 * Uo.d.size()); memcpy(V, Vo.d.data(), 8 * Vo.d.size()); memcpy(S, So.data(), 8 * So.size());
+}
 
 // ---- CoarseTracker: the reference's src/frontend/CoarseTracker.cc against oracle/tracker.cc
 static void pin_tracker() {
@@ -622,19 +648,18 @@ static void pin_tracker() {
     oracle::makeImages(colNew.data(), w, h, L, pn);
 
     // reference side: frames, features, points, their newest residual
-    auto HC = std::make_shared<CalibHessian>();
-    HC->fx = fxl; HC->fy = fyl; HC->cx = cxl; HC->cy = cyl;
+    auto HC = make_calib(fxl, fyl, cxl, cyl);
     const int nKF = 3, nPer = 900;
     std::vector<shared_ptr<FrameHessian>> FH(nKF);
     std::vector<shared_ptr<Frame>> FR(nKF);
     for (int f = 0; f < nKF; f++) {
-        FH[f] = std::make_shared<FrameHessian>(); FR[f] = std::make_shared<Frame>();
-        FH[f]->frame = FR[f]; FR[f]->frameHessian = FH[f]; FR[f]->id = 10 + f; FH[f]->idx = f;
+        FR[f] = std::make_shared<Frame>(); FH[f] = make_fh(FR[f]);
+        FR[f]->frameHessian = FH[f]; FR[f]->id = 10 + f; FH[f]->idx = f;
     }
     auto lastRef = FH[nKF - 1];
     for (int l = 0; l < L; l++) lastRef->dIp[l] = (Vec3f *) pr[l];
-    lastRef->dI = lastRef->dIp[0]; lastRef->ab_exposure = 1.0f; lastRef->aff = AffLight(0.02f, -1.5f);
-    auto newFH = std::make_shared<FrameHessian>();
+    lastRef->dI = lastRef->dIp[0]; lastRef->ab_exposure = 1.0f; lastRef->setEvalPT_scaled(SE3(), AffLight(0.02f, -1.5f));
+    auto newFH = make_fh(nullptr);
     for (int l = 0; l < L; l++) newFH->dIp[l] = (Vec3f *) pn[l];
     newFH->dI = newFH->dIp[0]; newFH->ab_exposure = 1.061f;     // so that the affine brightness (0, 0) is close to the truth (gain 1.04)
     std::vector<float> cpt, hdi;            // the oracle's input: the contributions in the order the reference visits them
@@ -654,11 +679,11 @@ static void pin_tracker() {
             if (k % 11 == 0 && !cpt.empty()) { u = cpt[cpt.size() - 3]; v = cpt[cpt.size() - 2]; }
             r->centerProjectedTo = Vec3f(u, v, id0 * (1.f + frand(-0.02f, 0.02f)));
             ph->HdiF = frand(0.5f, 400.f);
-            ph->lastResiduals[0] = std::make_pair(r, (int) ResState::IN);
+            ph->lastResiduals[0] = std::make_pair(r, ResState::IN);
             int skip = 0;
             if (k % 17 == 3) { feat->status = Feature::FeatureStatus::OUTLIER; skip = 1; }
             if (k % 19 == 4) { pt->status = Point::PointStatus::MARGINALIZED; skip = 1; }
-            if (k % 23 == 5) { ph->lastResiduals[0].second = (int) ResState::OOB; skip = 1; }
+            if (k % 23 == 5) { ph->lastResiduals[0].second = ResState::OOB; skip = 1; }
             if (k % 29 == 6) { ph->lastResiduals[0].first = nullptr; skip = 1; }
             FR[f]->features.push_back(feat); keep.push_back(r);
             if (skip) { nSkipped++; continue; }
@@ -671,7 +696,7 @@ static void pin_tracker() {
     oracle::CoarseTracker O(w, h, L);
     O.makeK(fxl, fyl, cxl, cyl);
     for (int l = 0; l < L; l++) { O.refDIp[l] = pr[l]; O.newDIp[l] = pn[l]; }
-    O.lastRef_aff_a = lastRef->aff.a; O.lastRef_aff_b = lastRef->aff.b; O.lastRef_ab_exposure = lastRef->ab_exposure; O.newFrame_ab_exposure = newFH->ab_exposure;
+    O.lastRef_aff_a = lastRef->aff_g2l().a; O.lastRef_aff_b = lastRef->aff_g2l().b; O.lastRef_ab_exposure = lastRef->ab_exposure; O.newFrame_ab_exposure = newFH->ab_exposure;
     O.makeCoarseDepthL0((int) hdi.size(), cpt.data(), hdi.data());
 
     bool okK = true, okPc = true, okMap = true;
@@ -694,7 +719,7 @@ static void pin_tracker() {
     CHECK(R.pc_n[0] > 1500 && R.pc_n[0] < R.pc_n[1] + 100000 && nSkipped > 100, "tracker scenario: enough points, filters exercised");
     CHECK(okPc, "setCoarseTrackingRef / makeCoarseDepthL0: pc_n, pc_u, pc_v, pc_idepth, pc_color on every level");
     CHECK(okMap, "makeCoarseDepthL0: idepth and weightSums maps on every level");
-    CHECK(R.refFrameID == 10 + nKF - 1 && R.lastRef_aff_g2l.a == lastRef->aff.a, "setCoarseTrackingRef bookkeeping");
+    CHECK(R.refFrameID == 10 + nKF - 1 && R.lastRef_aff_g2l.a == lastRef->aff_g2l().a, "setCoarseTrackingRef bookkeeping");
 
     // calcRes / calcGSSSE at several poses, brightness parameters, cutoffs and levels
     R.newFrame = newFH;
@@ -746,11 +771,11 @@ static void pin_tracker() {
         const bool gr = R.trackNewestCoarse(newFH, Tr, aff, L - 1, minRes);
         const bool go = O.trackNewestCoarse(To, oa, ob, L - 1, minResO);
         nTrue += gr; nFalse += !gr; its += O.lm_iterations_total;
-        bool same = gr == go && memcmp(&aff.a, &oa, 4) == 0 && memcmp(&aff.b, &ob, 4) == 0 && memcmp(&Tr.s.q, &To.q, sizeof(To.q)) == 0 && memcmp(&Tr.s.t, &To.t, sizeof(To.t)) == 0;
+        bool same = gr == go && memcmp(&aff.a, &oa, 4) == 0 && memcmp(&aff.b, &ob, 4) == 0 && memcmp(&Tr.q, &To.q, sizeof(To.q)) == 0 && memcmp(Tr.t.d, &To.t, 24) == 0;
         same &= memcmp(R.lastResiduals.d, O.lastResiduals, 40) == 0 && memcmp(R.lastFlowIndicators.d, O.lastFlowIndicators, 24) == 0;
         okTrack &= same;
         printf("  tracker pin: track run %d -> %s, t = (%.5f %.5f %.5f) (true %.5f %.5f 0), a = %.4f b = %.3f, %d calcRes evaluations\n", run, gr ? "good" : "lost",
-                             Tr.s.t[0], Tr.s.t[1], Tr.s.t[2], shx / (fxl * id0), shy / (fyl * id0), aff.a, aff.b, O.lm_iterations_total);
+                             Tr.t[0], Tr.t[1], Tr.t[2], shx / (fxl * id0), shy / (fyl * id0), aff.a, aff.b, O.lm_iterations_total);
     }
     CHECK(nTrue >= 2 && nFalse >= 1, "trackNewestCoarse scenario has converging and aborting runs");
     CHECK(okTrack, "CoarseTracker::trackNewestCoarse: return value, pose, affine brightness, lastResiduals, lastFlowIndicators");

@@ -17,6 +17,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <map>
+#include <iostream>
 #include <fstream>
 #include <memory>
 #include <string>
@@ -31,6 +34,8 @@ using namespace std;
 
 // implemented by the pin harness with the oracle's restatement of Eigen::LDLT (oracle/omath.h)
 extern "C" void ref_shim_ldlt_solve(int n, const double *A_colmajor, const double *b, double *x);
+extern "C" void ref_shim_inverse_lu(int n, const double *A_colmajor, double *Ainv_colmajor);      // Eigen PartialPivLU inverse (sizes > 4)
+extern "C" void ref_shim_jacobi_svd(int m, int n, const double *A_colmajor, double *U, double *S, double *V);
 
 namespace Eigen {
 template<typename T, int R, int C> struct Matrix;
@@ -74,6 +79,10 @@ struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
     Matrix &operator*=(S s_) { const T s = (T) s_; for (int i = 0; i < R * C; i++) d[i] *= s; return *this; }
     Matrix operator-() const { Matrix o; for (int i = 0; i < R * C; i++) o.d[i] = -d[i]; return o; }
+    template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    Matrix &operator/=(S s_) { const T s = (T) s_; for (int i = 0; i < R * C; i++) d[i] /= s; return *this; }
+    template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    Matrix operator/(S s_) const { Matrix o = *this; o /= s_; return o; }
     template<typename U> Matrix<U, R, C> cast() const { Matrix<U, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = (U) d[i]; return o; }
     template<int R1 = R, int C1 = C, typename = typename std::enable_if<R1 * C1 == 1>::type> operator T() const { return d[0]; }      // 1x1 -> scalar
     T dot(const Matrix &o) const { T s = d[0] * o.d[0]; for (int i = 1; i < R * C; i++) s += d[i] * o.d[i]; return s; }
@@ -91,8 +100,11 @@ struct alignas((sizeof(T) * R * C) % 16 == 0 ? 16 : alignof(T)) Matrix {
     CommaInit<T, R, C> operator<<(T v) { d[0] = v; return CommaInit<T, R, C>{this, 1}; }
     LDLTOf<T, R> ldlt() const { static_assert(R == C, "square"); return LDLTOf<T, R>{*this}; }
     // 3x3 inverse by cofactors / determinant (Eigen's compute_inverse for size 3)
-    Matrix inverse() const {
-        static_assert(R == 3 && C == 3, "only the 3x3 inverse is used");
+    template<int R1 = R> typename std::enable_if<(R1 > 4), Matrix>::type inverse() const {       // PartialPivLU path
+        static_assert(R == C && std::is_same<T, double>::value, "square double"); Matrix o; ref_shim_inverse_lu(R, d, o.d); return o;
+    }
+    template<int R1 = R> typename std::enable_if<(R1 <= 4), Matrix>::type inverse() const {
+        static_assert(R == 3 && C == 3, "only the 3x3 cofactor inverse is used");
         const Matrix &m = *this; Matrix o;
         const T c00 = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1), c10 = m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2), c20 = m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0);
         const T invdet = T(1) / (m(0, 0) * c00 + m(0, 1) * c10 + m(0, 2) * c20);
@@ -129,48 +141,170 @@ struct Block : Matrix<T, BR, BC> {
     Block &operator*=(S s) { Matrix<T, BR, BC>::operator*=(s); push(); return *this; }
     void setZero() { Matrix<T, BR, BC>::setZero(); push(); }
     Block &noalias() { return *this; }
+    struct Diag { Block *b; Diag &operator+=(const Matrix<T, BR, 1> &v) { for (int i = 0; i < BR; i++) b->d[i * BR + i] += v.d[i]; b->push(); return *this; } };
+    Diag diagonal() { static_assert(BR == BC, "square"); return Diag{this}; }
     Block &operator+=(const Matrix<T, BR, BC> &m) { Matrix<T, BR, BC>::operator+=(m); push(); return *this; }
     Block &operator-=(const Matrix<T, BR, BC> &m) { Matrix<T, BR, BC>::operator-=(m); push(); return *this; }
 };
+// ---- dynamic-size vectors and matrices (VecX, VecXf, MatXX) as EnergyFunctional.cc and the Hessian stitchers use them. Everything is
+// evaluated eagerly into values; products are row-times-column sums accumulated from 0 in increasing index order.
+template<typename T> struct DynVecT;
+struct DynMat;
+template<typename T> struct DynSeg {        // v.head(n) / v.tail(n) / v.segment(i, n): a view that assigns through
+    DynVecT<T> *v; int i0, n;
+    operator DynVecT<T>() const;
+    DynSeg &operator=(const DynVecT<T> &o);
+    DynSeg &operator=(const DynSeg &o) { return *this = (DynVecT<T>) o; }
+    DynSeg &noalias() { return *this; }
+    DynSeg &operator-=(const DynVecT<T> &o);
+};
+template<typename T> struct DiagWrap { const DynVecT<T> *v; };      // v.asDiagonal()
+template<typename T> struct DynVecT {
+    std::vector<T> d;
+    DynVecT() {}
+    explicit DynVecT(int n) : d((size_t) n, T(0)) {}
+    template<int N> DynVecT(const Matrix<T, N, 1> &m) : d(m.d, m.d + N) {}
+    static DynVecT Zero(int n) { return DynVecT(n); }
+    static DynVecT Constant(int n, T v) { DynVecT o(n); for (auto &x : o.d) x = v; return o; }
+    int size() const { return (int) d.size(); }
+    int rows() const { return (int) d.size(); }
+    T &operator[](int i) { return d[i]; }
+    const T &operator[](int i) const { return d[i]; }
+    T &operator()(int i) { return d[i]; }
+    const T &operator()(int i) const { return d[i]; }
+    void conservativeResize(int n) { d.resize((size_t) n, T(0)); }
+    template<int N> Block<T, N, 1> segment(int i0) { return Block<T, N, 1>(&d[i0], N); }
+    template<int N> Matrix<T, N, 1> segment(int i0) const { Matrix<T, N, 1> o; for (int i = 0; i < N; i++) o.d[i] = d[i0 + i]; return o; }
+    template<int N> Block<T, N, 1> head() { return segment<N>(0); }
+    template<int N> Matrix<T, N, 1> head() const { return segment<N>(0); }
+    template<int N> Block<T, N, 1> tail() { return segment<N>((int) d.size() - N); }
+    template<int N> Matrix<T, N, 1> tail() const { return segment<N>((int) d.size() - N); }
+    DynSeg<T> segment(int i0, int n) { return DynSeg<T>{this, i0, n}; }
+    DynSeg<T> head(int n) { return DynSeg<T>{this, 0, n}; }
+    DynSeg<T> tail(int n) { return DynSeg<T>{this, (int) d.size() - n, n}; }
+    DynVecT &noalias() { return *this; }
+    DynVecT &operator+=(const DynVecT &o) { for (size_t i = 0; i < d.size(); i++) d[i] += o.d[i]; return *this; }
+    DynVecT &operator-=(const DynVecT &o) { for (size_t i = 0; i < d.size(); i++) d[i] -= o.d[i]; return *this; }
+    DynVecT operator-() const { DynVecT o = *this; for (auto &x : o.d) x = -x; return o; }
+    T dot(const DynVecT &o) const { T s = T(0); for (size_t i = 0; i < d.size(); i++) s += d[i] * o.d[i]; return s; }
+    T norm() const { return std::sqrt(dot(*this)); }
+    DynVecT normalized() const { const T n = norm(); DynVecT o = *this; for (auto &x : o.d) x = x / n; return o; }
+    DynVecT cwiseAbs() const { DynVecT o = *this; for (auto &x : o.d) x = std::fabs(x); return o; }
+    DynVecT cwiseSqrt() const { DynVecT o = *this; for (auto &x : o.d) x = std::sqrt(x); return o; }
+    DynVecT cwiseInverse() const { DynVecT o = *this; for (auto &x : o.d) x = T(1) / x; return o; }
+    template<typename U> DynVecT<U> cast() const { DynVecT<U> o((int) d.size()); for (size_t i = 0; i < d.size(); i++) o.d[i] = (U) d[i]; return o; }
+    DiagWrap<T> asDiagonal() const { return DiagWrap<T>{this}; }
+};
+template<typename T> DynSeg<T>::operator DynVecT<T>() const { DynVecT<T> o(n); for (int i = 0; i < n; i++) o.d[i] = v->d[i0 + i]; return o; }
+template<typename T> DynSeg<T> &DynSeg<T>::operator=(const DynVecT<T> &o) { for (int i = 0; i < n; i++) v->d[i0 + i] = o.d[i]; return *this; }
+template<typename T> DynSeg<T> &DynSeg<T>::operator-=(const DynVecT<T> &o) { for (int i = 0; i < n; i++) v->d[i0 + i] -= o.d[i]; return *this; }
+typedef DynVecT<double> DynVec;
+inline DynVec operator+(const DynVec &a, const DynVec &b) { DynVec o = a; o += b; return o; }
+inline DynVec operator-(const DynVec &a, const DynVec &b) { DynVec o = a; o -= b; return o; }
+inline DynVec operator*(double s, const DynVec &a) { DynVec o = a; for (auto &x : o.d) x = s * x; return o; }
+inline DynVec operator*(const DiagWrap<double> &D, const DynVec &a) { DynVec o = a; for (size_t i = 0; i < o.d.size(); i++) o.d[i] = D.v->d[i] * a.d[i]; return o; }
+
 // N consecutive diagonal entries of a dynamic matrix (H.diagonal().segment<8>(i) += v)
 template<int N> struct DiagSeg {
     double *p; int stride;
     DiagSeg &operator+=(const Matrix<double, N, 1> &v) { for (int i = 0; i < N; i++) p[(size_t) i * stride] += v.d[i]; return *this; }
 };
 struct DiagView {
-    double *p; int stride;
+    double *p; int stride, n;
     template<int N> DiagSeg<N> segment(int i0) { return DiagSeg<N>{p + (size_t) i0 * stride, stride}; }
     template<int N> DiagSeg<N> head() { return segment<N>(0); }
+    operator DynVec() const { DynVec o(n); for (int i = 0; i < n; i++) o.d[i] = p[(size_t) i * stride]; return o; }
+    DynVec cwiseAbs() const { return ((DynVec) *this).cwiseAbs(); }
+    DynVec cwiseSqrt() const { return ((DynVec) *this).cwiseSqrt(); }
 };
-// Matrix<double, Dynamic, Dynamic> and Matrix<double, Dynamic, 1> as the Hessian stitching uses them: zero-initialised storage,
-// fixed-size block views, whole-matrix +=
+struct DynBlk {          // M.block(i, j, r, c) and the corner / rows / cols variants: a view that assigns through
+    DynMat *m; int i0, j0, r, c;
+    operator DynMat() const;
+    DynBlk &operator=(const DynMat &o);
+    DynBlk &operator=(const DynBlk &o);
+    DynBlk &noalias() { return *this; }
+    DynBlk &operator-=(const DynMat &o);
+    DynMat transpose() const;
+    void setZero();
+};
+struct DynCol { DynMat *m; int j; DynCol &operator=(const DynVec &v); };
+struct DynLDLT;
 struct DynMat {
     int r = 0, c = 0;
     std::vector<double> d;       // column-major
-    static DynMat Zero(int r_, int c_) { DynMat m; m.r = r_; m.c = c_; m.d.assign((size_t) r_ * c_, 0.0); return m; }
+    DynMat() {}
+    template<typename I1, typename I2, typename = typename std::enable_if<std::is_integral<I1>::value && std::is_integral<I2>::value>::type>
+    DynMat(I1 r_, I2 c_) : r((int) r_), c((int) c_), d((size_t) r_ * (size_t) c_, 0.0) {}
+    template<int R, int C, typename = typename std::enable_if<(C > 1)>::type> DynMat(const Matrix<double, R, C> &m) : r(R), c(C), d(m.d, m.d + R * C) {}
+    static DynMat Zero(int r_, int c_) { return DynMat(r_, c_); }
     int rows() const { return r; }
     int cols() const { return c; }
     double &operator()(int i, int j) { return d[(size_t) j * r + i]; }
     double operator()(int i, int j) const { return d[(size_t) j * r + i]; }
+    void conservativeResize(int nr, int nc) {
+        DynMat o(nr, nc);
+        for (int j = 0; j < std::min(c, nc); j++) for (int i = 0; i < std::min(r, nr); i++) o(i, j) = (*this)(i, j);
+        *this = o;
+    }
     template<int BR, int BC> Block<double, BR, BC> block(int i, int j) { return Block<double, BR, BC>(&d[(size_t) j * r + i], r); }
     template<int BR, int BC> Block<double, BR, BC> topLeftCorner() { return block<BR, BC>(0, 0); }
-    DiagView diagonal() { return DiagView{d.data(), r + 1}; }
+    template<int BR, int BC> Block<double, BR, BC> bottomRightCorner() { return block<BR, BC>(r - BR, c - BC); }
+    template<int N> DynBlk rightCols() { return DynBlk{this, 0, c - N, r, N}; }
+    template<int N> DynBlk bottomRows() { return DynBlk{this, r - N, 0, N, c}; }
+    DynBlk block(int i, int j, int br, int bc) { return DynBlk{this, i, j, br, bc}; }
+    DynBlk topLeftCorner(int br, int bc) { return DynBlk{this, 0, 0, br, bc}; }
+    DynBlk bottomLeftCorner(int br, int bc) { return DynBlk{this, r - br, 0, br, bc}; }
+    DynBlk rightCols(int n) { return DynBlk{this, 0, c - n, r, n}; }
+    DynBlk bottomRows(int n) { return DynBlk{this, r - n, 0, n, c}; }
+    DynCol col(int j) { return DynCol{this, j}; }
+    DiagView diagonal() { return DiagView{d.data(), r + 1, std::min(r, c)}; }
     DynMat &noalias() { return *this; }
     DynMat &operator+=(const DynMat &o) { for (size_t i = 0; i < d.size(); i++) d[i] += o.d[i]; return *this; }
+    DynMat &operator-=(const DynMat &o) { for (size_t i = 0; i < d.size(); i++) d[i] -= o.d[i]; return *this; }
+    DynMat transpose() const { DynMat o(c, r); for (int j = 0; j < c; j++) for (int i = 0; i < r; i++) o(j, i) = (*this)(i, j); return o; }
+    inline DynLDLT ldlt() const;
 };
-struct DynVec {
-    std::vector<double> d;
-    static DynVec Zero(int n) { DynVec v; v.d.assign(n, 0.0); return v; }
-    int size() const { return (int) d.size(); }
-    int rows() const { return (int) d.size(); }
-    double &operator[](int i) { return d[i]; }
-    double operator[](int i) const { return d[i]; }
-    template<int N> Block<double, N, 1> segment(int i0) { return Block<double, N, 1>(&d[i0], N); }
-    template<int N> Block<double, N, 1> head() { return segment<N>(0); }
-    DynVec &noalias() { return *this; }
-    DynVec &operator+=(const DynVec &o) { for (size_t i = 0; i < d.size(); i++) d[i] += o.d[i]; return *this; }
+inline DynBlk::operator DynMat() const { DynMat o(r, c); for (int j = 0; j < c; j++) for (int i = 0; i < r; i++) o(i, j) = (*m)(i0 + i, j0 + j); return o; }
+inline DynBlk &DynBlk::operator=(const DynMat &o) { for (int j = 0; j < c; j++) for (int i = 0; i < r; i++) (*m)(i0 + i, j0 + j) = o(i, j); return *this; }
+inline DynBlk &DynBlk::operator=(const DynBlk &o) { return *this = (DynMat) o; }
+inline DynBlk &DynBlk::operator-=(const DynMat &o) { for (int j = 0; j < c; j++) for (int i = 0; i < r; i++) (*m)(i0 + i, j0 + j) -= o(i, j); return *this; }
+inline DynMat DynBlk::transpose() const { return ((DynMat) *this).transpose(); }
+inline void DynBlk::setZero() { for (int j = 0; j < c; j++) for (int i = 0; i < r; i++) (*m)(i0 + i, j0 + j) = 0.0; }
+inline DynCol &DynCol::operator=(const DynVec &v) { for (int i = 0; i < m->r; i++) (*m)(i, j) = v.d[i]; return *this; }
+inline DynMat operator+(const DynMat &a, const DynMat &b) { DynMat o = a; o += b; return o; }
+inline DynMat operator-(const DynMat &a, const DynMat &b) { DynMat o = a; o -= b; return o; }
+template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+inline DynMat operator*(S s_, const DynMat &a) { const double s = (double) s_; DynMat o = a; for (auto &x : o.d) x = s * x; return o; }
+template<typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+inline DynMat operator*(const DynMat &a, S s_) { const double s = (double) s_; DynMat o = a; for (auto &x : o.d) x = x * s; return o; }
+inline DynMat operator*(const DynMat &A, const DynMat &B) {
+    DynMat C(A.r, B.c);
+    for (int j = 0; j < B.c; j++) for (int i = 0; i < A.r; i++) { double s = 0.0; for (int k = 0; k < A.c; k++) s += A(i, k) * B(k, j); C(i, j) = s; }
+    return C;
+}
+inline DynVec operator*(const DynMat &A, const DynVec &v) {
+    DynVec o(A.r);
+    for (int i = 0; i < A.r; i++) { double s = 0.0; for (int k = 0; k < A.c; k++) s += A(i, k) * v.d[k]; o.d[i] = s; }
+    return o;
+}
+inline DynMat operator*(const DiagWrap<double> &D, const DynMat &A) { DynMat o = A; for (int j = 0; j < A.c; j++) for (int i = 0; i < A.r; i++) o(i, j) = D.v->d[i] * A(i, j); return o; }
+inline DynMat operator*(const DynMat &A, const DiagWrap<double> &D) { DynMat o = A; for (int j = 0; j < A.c; j++) for (int i = 0; i < A.r; i++) o(i, j) = A(i, j) * D.v->d[j]; return o; }
+struct DynLDLT { DynMat A; DynVec solve(const DynVec &b) const { DynVec x(A.r); ref_shim_ldlt_solve(A.r, A.d.data(), b.d.data(), x.d.data()); return x; } };
+inline DynLDLT DynMat::ldlt() const { return DynLDLT{*this}; }
+// Eigen::JacobiSVD<MatXX>(M, ComputeThinU | ComputeThinV): forwarded to the oracle's restatement (omath.h jacobi_svd) by the harness
+enum { ComputeThinU = 1, ComputeThinV = 2 };
+template<typename M> struct JacobiSVD {
+    DynMat U, V; DynVec S;
+    JacobiSVD(const DynMat &A, unsigned) {
+        const int k = std::min(A.r, A.c);
+        U = DynMat(A.r, k); V = DynMat(A.c, k); S = DynVec(k);
+        ref_shim_jacobi_svd(A.r, A.c, A.d.data(), U.d.data(), S.d.data(), V.d.data());
+    }
+    const DynVec &singularValues() const { return S; }
+    const DynMat &matrixU() const { return U; }
+    const DynMat &matrixV() const { return V; }
 };
-
+template<typename T> using aligned_allocator = std::allocator<T>;
 template<typename T, int R, int C, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
 inline Matrix<T, R, C> operator*(S s_, const Matrix<T, R, C> &m) {
     const T s = (T) s_;     // Eigen converts the scalar to the matrix's scalar type first
@@ -187,6 +321,8 @@ template<typename T, int R, int C> inline Matrix<T, R, C> operator+(const Matrix
 template<typename T, int R, int C> inline Matrix<T, R, C> operator-(const Matrix<T, R, C> &a, const Matrix<T, R, C> &b) {
     Matrix<T, R, C> o; for (int i = 0; i < R * C; i++) o.d[i] = a.d[i] - b.d[i]; return o;
 }
+template<typename T> inline T &operator-=(T &a, const Matrix<T, 1, 1> &m) { a -= m.d[0]; return a; }      // scalar -= (row * column)
+template<typename T> inline T &operator+=(T &a, const Matrix<T, 1, 1> &m) { a += m.d[0]; return a; }
 // column * row^T (outer product)
 template<typename T, int R, int C> inline Matrix<T, R, C> operator*(const Matrix<T, R, 1> &col, const RowView<T, C> &row) {
     Matrix<T, R, C> o; for (int c = 0; c < C; c++) for (int r = 0; r < R; r++) o.d[c * R + r] = col.d[r] * row.v->d[c]; return o;
@@ -226,6 +362,8 @@ typedef Eigen::Matrix<double, 8, 1> Vec8;
 typedef Eigen::Matrix<double, 10, 1> Vec10;
 typedef Eigen::Matrix<double, 3, 3> Mat33;
 typedef Eigen::Matrix<double, 6, 6> Mat66;
+typedef Eigen::Matrix<double, 4, 2> Mat42;
+typedef Eigen::Matrix<double, 7, 7> Mat77;
 typedef Eigen::Matrix<double, 8, 8> Mat88;
 typedef Eigen::Matrix<float, 8, 8> Mat88f;
 typedef Eigen::Matrix<double, 8, CPARS> Mat8C;
@@ -234,6 +372,7 @@ typedef Eigen::Matrix<double, 8 + CPARS + 1, 8 + CPARS + 1> MatPCPC;
 typedef Eigen::Matrix<double, CPARS, 1> VecC;
 typedef Eigen::DynMat MatXX;
 typedef Eigen::DynVec VecX;
+typedef Eigen::DynVecT<float> VecXf;
 typedef Eigen::Matrix<float, 2, 1> Vec2f;
 typedef Eigen::Matrix<float, 3, 1> Vec3f;
 typedef Eigen::Matrix<unsigned char, 3, 1> Vec3b;
@@ -256,13 +395,19 @@ typedef Eigen::Matrix<float, 14, 14> Mat1414f;
 namespace Sophus {
 class SE3d {
 public:
-    oracle::SE3 s;
+    oracle::Quat q;       // unit quaternion (w, x, y, z)
+    Vec3 t = Vec3(0, 0, 0);
     SE3d() {}
-    Mat33 rotationMatrix() const { const oracle::M3 R = s.rotationMatrix(); Mat33 o; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o(i, j) = R(i, j); return o; }
-    Vec3 translation() const { return Vec3(s.t[0], s.t[1], s.t[2]); }
-    static SE3d exp(const Vec6 &a) { SE3d r; r.s = oracle::SE3::exp(a.d); return r; }
-    SE3d operator*(const SE3d &o) const { SE3d r; r.s = s * o.s; return r; }
-    SE3d inverse() const { SE3d r; r.s = s.inverse(); return r; }
+    explicit SE3d(const oracle::SE3 &s) : q(s.q), t(s.t[0], s.t[1], s.t[2]) {}
+    oracle::SE3 o() const { oracle::SE3 s; s.q = q; s.t = oracle::V3{{t[0], t[1], t[2]}}; return s; }
+    Mat33 rotationMatrix() const { const oracle::M3 R = oracle::qmat(q); Mat33 m; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = R(i, j); return m; }
+    Vec3 &translation() { return t; }
+    const Vec3 &translation() const { return t; }
+    static SE3d exp(const Vec6 &a) { return SE3d(oracle::SE3::exp(a.d)); }
+    Vec6 log() const { Vec6 v; o().log(v.d); return v; }
+    Mat66 Adj() const { double A[36]; o().Adj(A); Mat66 m; for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) m(i, j) = A[i * 6 + j]; return m; }
+    SE3d operator*(const SE3d &b) const { return SE3d(o() * b.o()); }
+    SE3d inverse() const { return SE3d(o().inverse()); }
 };
 }
 typedef Sophus::SE3d SE3;
