@@ -226,6 +226,7 @@ int oracle_ba_add_point(void *o, int host, float u, float v, float idepth_zero, 
 int oracle_ba_add_residual(void *o, int point, int target);
 void oracle_ba_set_frame_energy_th(void *o, int frame, float th);
 void oracle_ba_finalize(void *o);
+void oracle_ba_set_marg_prior(void *o, const double *HM_colmajor, const double *bM);
 }
 // a small window (oracle side) and its reference-side mirror, shared by pin_linearize and pin_hessians
 struct Scene {
@@ -236,7 +237,7 @@ struct Scene {
     std::vector<shared_ptr<ldso::internal::FrameHessian>> FH;
     shared_ptr<ldso::internal::EnergyFunctional> EF;
 };
-static Scene *make_scene(int nPper) {
+static Scene *make_scene(int nPper, int threads_mode = 0, bool depthPriors = false) {
     using namespace ldso::internal;
     Scene *S = new Scene();
     const int w = 160, h = 120, nF = 4;
@@ -255,7 +256,7 @@ static Scene *make_scene(int nPper) {
             imgs[f][3 * i + 2] = (y > 0 && y < h - 1) ? 0.5f * (I[i + w] - I[i - w]) : 0.f;
         }
     }
-    void *o = oracle_ba_create(w, h, 0);
+    void *o = oracle_ba_create(w, h, threads_mode);
     oracle::Window *W = (oracle::Window *) o;
     S->o = o; S->W = W;
     const double K[4] = {110.0, 112.0, 79.5, 59.5};
@@ -284,7 +285,7 @@ static Scene *make_scene(int nPper) {
                 wt[i] = sqrtf(2500.f / (2500.f + c3[1] * c3[1] + c3[2] * c3[2]));
             }
             const float idz = frand(0.2f, 1.5f);
-            const int p = oracle_ba_add_point(o, f, u, v, idz, idz + frand(-0.02f, 0.02f), 0, col, wt);
+            const int p = oracle_ba_add_point(o, f, u, v, idz, idz + frand(-0.02f, 0.02f), (depthPriors && k % 5 == 0) ? 1 : 0, col, wt);
             for (int t = 0; t < nF; t++) if (t != f) oracle_ba_add_residual(o, p, t);
         }
     oracle_ba_finalize(o);
@@ -607,6 +608,182 @@ extern "C" void ref_shim_ldlt_solve(int n, const double *A, const double *b, dou
     for (int i = 0; i < n; i++) x[i] = r[i];
 }
 
+
+// ---- the back end as a whole: the reference's own FrameHessian.cc, FrameFramePrecalc.cc, PointHessian.h and EnergyFunctional.cc driven
+// through the calls FullSystem makes (FullSystem.cc itself needs the whole front end and is not compiled), against oracle/ba.cc.
+// Single-threaded mode (multiThreading = false): the reference's worker threads pick chunks dynamically, so its 6-thread sums are not
+// reproducible run to run. Dynamic-size Eigen expressions (HM * delta, the diagonal scalings, the Schur complement of marginalizeFrame,
+// orthogonalize) are evaluated by the stand-in as plain left-to-right sums, LDLT / PartialPivLU / JacobiSVD / SE3 by the oracle's own
+// restatements: equality pins the STRUCTURE of these functions (what is added where, in which order, with which scaling, permutation and
+// sign), not Eigen's kernels.
+static bool same_se3(const SE3 &a, const oracle::SE3 &b) { return memcmp(&a.q, &b.q, sizeof(b.q)) == 0 && memcmp(a.t.d, &b.t, 24) == 0; }
+static void pin_backend() {
+    using namespace ldso; using namespace ldso::internal;
+    Scene *S = make_scene(150, 1, true);
+    oracle::Window *W = S->W;
+    const int nF = S->nF, nP = (int) W->points.size();
+    multiThreading = false;
+    // calibration: the reference's own CalibHessian constructor + setValue
+    const double K[4] = {110.0, 112.0, 79.5, 59.5}, cd[4] = {1e-4, -2e-4, 3e-4, 1e-4};
+    auto HC = make_calib(K[0], K[1], K[2], K[3]);
+    { VecC v; for (int i = 0; i < 4; i++) v[i] = HC->value_zero[i] + cd[i]; HC->setValue(v); }
+    {
+        bool ok = memcmp(HC->value.d, W->HCalib.value, 32) == 0 && memcmp(HC->value_zero.d, W->HCalib.value_zero, 32) == 0 && memcmp(HC->value_scaled.d, W->HCalib.value_scaled, 32) == 0 &&
+                  memcmp(HC->value_minus_value_zero.d, W->HCalib.value_minus_value_zero, 32) == 0 && memcmp(HC->value_scaledf.d, W->HCalib.value_scaledf, 16) == 0 &&
+                  memcmp(HC->value_scaledi.d, W->HCalib.value_scaledi, 16) == 0;
+        CHECK(ok, "CalibHessian constructor / setValue: value, value_zero, value_scaled, value_minus_value_zero, float copies");
+    }
+    // frames: setState / setStateZero (nullspaces) / setState as FrameHessian::setEvalPT + setState do
+    std::vector<shared_ptr<Frame>> FR(nF); std::vector<shared_ptr<FrameHessian>> FH(nF);
+    bool okState = true, okNull = true;
+    for (int f = 0; f < nF; f++) {
+        const oracle::Frame &of = W->frames[f];
+        FR[f] = std::make_shared<Frame>(); FR[f]->id = of.id;
+        FH[f] = make_fh(FR[f]); FR[f]->frameHessian = FH[f];
+        FH[f]->frameID = of.frameID; FH[f]->ab_exposure = of.ab_exposure; FH[f]->frameEnergyTH = of.frameEnergyTH;
+        FH[f]->dI = (Vec3f *) S->imgs[f].data();
+        Vec10 sz, st; for (int i = 0; i < 10; i++) { sz[i] = of.state_zero[i]; st[i] = of.state[i]; }
+        FH[f]->setEvalPT(SE3(of.worldToCam_evalPT), sz);
+        FH[f]->setState(st);
+        okState &= memcmp(FH[f]->state.d, of.state, 80) == 0 && memcmp(FH[f]->state_scaled.d, of.state_scaled, 80) == 0 && memcmp(FH[f]->state_zero.d, of.state_zero, 80) == 0 &&
+                   same_se3(FH[f]->PRE_worldToCam, of.PRE_worldToCam) && same_se3(FH[f]->PRE_camToWorld, of.PRE_camToWorld);
+        for (int r = 0; r < 6; r++) { okNull &= memcmp(&FH[f]->nullspaces_scale[r], &of.nullspaces_scale[r], 8) == 0; for (int c = 0; c < 6; c++) okNull &= memcmp(&FH[f]->nullspaces_pose(r, c), &of.nullspaces_pose[r][c], 8) == 0; }
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 2; c++) okNull &= memcmp(&FH[f]->nullspaces_affine(r, c), &of.nullspaces_affine[r][c], 8) == 0;
+    }
+    CHECK(okState, "FrameHessian::setEvalPT / setState: state, state_scaled, state_zero, PRE_worldToCam, PRE_camToWorld");
+    CHECK(okNull, "FrameHessian::setStateZero: nullspaces_pose, nullspaces_scale, nullspaces_affine");
+    // points and residuals behind the frames' features, the way makeIDX / setDeltaF / accumulate*_MT reach them
+    std::vector<shared_ptr<PointHessian>> PH(nP); std::vector<shared_ptr<Point>> PT(nP);
+    bool okPt = true;
+    for (int pi = 0; pi < nP; pi++) {
+        const oracle::Point &op = W->points[pi];
+        auto feat = std::make_shared<Feature>(op.u, op.v, FR[op.host]); feat->status = Feature::FeatureStatus::VALID;
+        PT[pi] = std::make_shared<Point>(); PT[pi]->status = Point::PointStatus::ACTIVE; PT[pi]->mHostFeature = feat; feat->point = PT[pi];
+        PH[pi] = std::make_shared<PointHessian>(); PT[pi]->mpPH = PH[pi]; PH[pi]->point = PT[pi];
+        auto ph = PH[pi];
+        ph->u = op.u; ph->v = op.v; ph->hasDepthPrior = op.hasDepthPrior;
+        ph->setIdepthZero(op.idepth_zero); ph->setIdepth(op.idepth);
+        memcpy(ph->color, op.color, 32); memcpy(ph->weights, op.weights, 32);
+        ph->takeData();
+        okPt &= memcmp(&ph->idepth_scaled, &op.idepth_scaled, 4) == 0 && memcmp(&ph->idepth_zero_scaled, &op.idepth_zero_scaled, 4) == 0 && memcmp(&ph->nullspaces_scale, &op.nullspaces_scale, 4) == 0 &&
+                memcmp(&ph->priorF, &op.priorF, 4) == 0 && memcmp(&ph->deltaF, &op.deltaF, 4) == 0;
+        FR[op.host]->features.push_back(feat);
+        for (int ri : op.residuals) {
+            const oracle::Residual &orr = W->residuals[ri];
+            ph->residuals.push_back(std::make_shared<PointFrameResidual>(ph, FH[orr.host], FH[orr.target]));
+        }
+    }
+    CHECK(okPt, "PointHessian::setIdepthZero / setIdepth / takeData: scaled idepths, nullspaces_scale, priorF, deltaF");
+    // EnergyFunctional::insertFrame (takeData, setAdjointsF, makeIDX)
+    auto EF = std::make_shared<EnergyFunctional>();
+    EF->red = new IndexThreadReduce<Vec10>();
+    for (int f = 0; f < nF; f++) EF->insertFrame(FH[f], HC);
+    {
+        bool ok = EF->nFrames == nF && (int) EF->allPoints.size() == nP;
+        for (int f = 0; f < nF; f++) ok &= memcmp(FH[f]->prior.d, W->frames[f].prior, 64) == 0 && memcmp(FH[f]->delta.d, W->frames[f].delta, 64) == 0 && memcmp(FH[f]->delta_prior.d, W->frames[f].delta_prior, 64) == 0 && FH[f]->idx == f;
+        CHECK(ok, "insertFrame: FrameHessian::takeData / getPrior (prior, delta, delta_prior), makeIDX");
+        bool ad = true;
+        for (int q = 0; q < nF * nF; q++) for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) {
+            ad &= memcmp(&EF->adHost[q](i, j), &W->adHost[64 * q + 8 * i + j], 8) == 0 && memcmp(&EF->adTarget[q](i, j), &W->adTarget[64 * q + 8 * i + j], 8) == 0;
+            ad &= memcmp(&EF->adHostF[q](i, j), &W->adHostF[64 * q + 8 * i + j], 4) == 0 && memcmp(&EF->adTargetF[q](i, j), &W->adTargetF[64 * q + 8 * i + j], 4) == 0;
+        }
+        ad &= memcmp(EF->cPrior.d, W->cPrior, 32) == 0 && memcmp(EF->cPriorF.d, W->cPriorF, 16) == 0;
+        CHECK(ad, "EnergyFunctional::setAdjointsF: adHost, adTarget (double and float), cPrior");
+    }
+    // FullSystem::setPrecalcValues: FrameFramePrecalc::Set for every pair, then setDeltaF
+    {
+        bool ok = true;
+        for (int f = 0; f < nF; f++) {
+            FH[f]->targetPrecalc.resize(nF);
+            for (int t = 0; t < nF; t++) {
+                FH[f]->targetPrecalc[t].Set(FH[f], FH[t], HC);
+                const FrameFramePrecalc &d = FH[f]->targetPrecalc[t]; const oracle::FramePrecalc &o = W->frames[f].targetPrecalc[t];
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+                    ok &= memcmp(&d.PRE_RTll(i, j), &o.PRE_RTll[i * 3 + j], 4) == 0 && memcmp(&d.PRE_RTll_0(i, j), &o.PRE_RTll_0[i * 3 + j], 4) == 0 &&
+                          memcmp(&d.PRE_KRKiTll(i, j), &o.PRE_KRKiTll[i * 3 + j], 4) == 0 && memcmp(&d.PRE_RKiTll(i, j), &o.PRE_RKiTll[i * 3 + j], 4) == 0;
+                ok &= memcmp(d.PRE_tTll.d, o.PRE_tTll, 12) == 0 && memcmp(d.PRE_tTll_0.d, o.PRE_tTll_0, 12) == 0 && memcmp(d.PRE_KtTll.d, o.PRE_KtTll, 12) == 0 &&
+                      memcmp(d.PRE_aff_mode.d, o.PRE_aff_mode, 8) == 0 && memcmp(&d.PRE_b0_mode, &o.PRE_b0_mode, 4) == 0 && memcmp(&d.distanceLL, &o.distanceLL, 4) == 0;
+            }
+        }
+        CHECK(ok, "FrameFramePrecalc::Set for all frame pairs (R, t, K R K^-1, R K^-1, K t, affine mode, distance)");
+        EF->setDeltaF(HC);
+        bool dl = memcmp(EF->cDeltaF.d, W->cDeltaF, 16) == 0;
+        for (int q = 0; q < nF * nF; q++) dl &= memcmp(EF->adHTdeltaF[q].d, &W->adHTdeltaF[8 * q], 32) == 0;
+        CHECK(dl, "EnergyFunctional::setDeltaF: adHTdeltaF, cDeltaF");
+    }
+    // linearise everything (pinned separately), fix a part
+    int nAct = 0;
+    for (int pi = 0; pi < nP; pi++) {
+        int k = 0;
+        for (int ri : W->points[pi].residuals) {
+            oracle::Residual &orr = W->residuals[ri]; auto r = PH[pi]->residuals[k];
+            r->linearize(HC); W->linearize(orr);
+            r->applyRes(true); W->applyRes(orr, true);
+            if (r->isActive() && (pi % 4 == 0 || k % 3 != 0)) { r->fixLinearizationF(EF); W->fixLinearizationF(orr); }
+            nAct += r->isActive(); k++;
+        }
+    }
+    // a marginalisation prior HM, bM (symmetric, diagonally dominant) and the gauge nullspaces FullSystem::getNullspaces builds
+    const int n = 8 * nF + CPARS;
+    {
+        std::vector<double> HMc((size_t) n * n), bMc(n);
+        for (int j = 0; j < n; j++) { bMc[j] = frand(-50, 50); for (int i = 0; i <= j; i++) { const double v = (i == j) ? frand(2000, 9000) : frand(-30, 30); HMc[(size_t) j * n + i] = HMc[(size_t) i * n + j] = v; } }
+        oracle_ba_set_marg_prior(S->o, HMc.data(), bMc.data());
+        EF->HM = MatXX::Zero(n, n); EF->bM = VecX::Zero(n);
+        for (int i = 0; i < n * n; i++) EF->HM.d[i] = HMc[i];
+        for (int i = 0; i < n; i++) EF->bM[i] = bMc[i];
+        W->getNullspaces();
+        auto cp = [&](const std::vector<oracle::VecXd> &src, std::vector<VecX> &dst) { dst.clear(); for (auto &v : src) { VecX x = VecX::Zero((int) v.size()); for (size_t i = 0; i < v.size(); i++) x[i] = v[i]; dst.push_back(x); } };
+        cp(W->lastNullspaces_pose, EF->lastNullspaces_pose); cp(W->lastNullspaces_scale, EF->lastNullspaces_scale);
+        cp(W->lastNullspaces_affA, EF->lastNullspaces_affA); cp(W->lastNullspaces_affB, EF->lastNullspaces_affB);
+    }
+    // solveSystemF: iteration 0 (no orthogonalisation of x) and iteration 2 (SOLVER_ORTHOGONALIZE_X_LATER)
+    for (int it = 0; it <= 2; it += 2) {
+        EF->solveSystemF(it, 1e-4, HC); W->solveSystemF(it, 1e-4);
+        bool ok = same_dyn(EF->lastHS, W->lastHS) && same_dyn(EF->lastbS, W->lastbS);
+        CHECK(ok, it == 0 ? "solveSystemF(0): lastHS, lastbS (accumulate*_MT single-threaded, prior shift HM * delta, assembly)" : "solveSystemF(2): lastHS, lastbS");
+        if (!same_dyn(EF->lastX, W->lastX)) { double mx = 0; for (int i = 0; i < n; i++) mx = std::max(mx, fabs(EF->lastX[i] - W->lastX[i])); printf("   lastX max abs diff %.3g\n", mx); }
+        CHECK(same_dyn(EF->lastX, W->lastX), it == 0 ? "solveSystemF(0): lastX (scaling, LDLT hand-off, unscaling)" : "solveSystemF(2): lastX after orthogonalize(&x, 0)");
+        bool st = memcmp(HC->step.d, W->HCalib.step, 32) == 0;
+        for (int f = 0; f < nF; f++) st &= memcmp(FH[f]->step.d, W->frames[f].step, 80) == 0;
+        for (int pi = 0; pi < nP; pi++) st &= memcmp(&PH[pi]->step, &W->points[pi].step, 4) == 0;
+        CHECK(st, it == 0 ? "resubstituteF_MT / resubstituteFPt (0): calibration, frame and point steps" : "resubstituteF_MT / resubstituteFPt (2): steps");
+        CHECK(EF->resInA == W->resInA && EF->resInL == W->resInL, "solveSystemF: resInA, resInL");
+    }
+    // orthogonalize on a vector and a matrix (SOLVER_ORTHOGONALIZE_SYSTEM / POINTMARG code path), energies
+    {
+        VecX b = EF->lastbS; MatXX H = EF->lastHS; oracle::VecXd bo = W->lastbS; oracle::MatX Ho = W->lastHS;
+        EF->orthogonalize(&b, &H); W->orthogonalize(&bo, &Ho);
+        CHECK(same_dyn(b, bo) && same_dyn(H, Ho), "EnergyFunctional::orthogonalize(b, H)");
+        const double mr = EF->calcMEnergyF(), mo = W->calcMEnergyF();
+        CHECK(memcmp(&mr, &mo, 8) == 0, "calcMEnergyF");
+        Vec10 sr; sr.setZero(); double so[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        EF->calcLEnergyPt(0, nP, &sr, 0); W->calcLEnergyPt(0, nP, so, 0);
+        CHECK(memcmp(&sr[0], &so[0], 8) == 0, "calcLEnergyPt over all points");
+        const double lr = EF->calcLEnergyF_MT(), lo = W->calcLEnergyF_MT();       // the reference adds the per-chunk results in thread completion order
+        CHECK(fabs(lr - lo) <= 1e-9 * fabs(lo), "calcLEnergyF_MT (to 1e-9: chunk sums arrive in thread order)");
+    }
+    // marginalizePointsF on the points whose active residuals are all linearised, then marginalizeFrame of frame 1
+    {
+        std::vector<int> idx;
+        for (int pi = 0; pi < nP; pi += 4) { idx.push_back(pi); PT[pi]->status = Point::PointStatus::MARGINALIZED; W->points[pi].priorF *= setting_idepthFixPriorMargFac; }
+        EF->marginalizePointsF(); W->marginalizePointsF(idx);
+        CHECK(same_dyn(EF->HM, W->HM) && same_dyn(EF->bM, W->bM), "EnergyFunctional::marginalizePointsF: HM, bM");
+        CHECK(EF->resInM == W->resInM && (int) EF->allPoints.size() == nP - (int) idx.size(), "marginalizePointsF: resInM, remaining points");
+#ifdef PIN_SELFTEST_BREAK
+        W->HM(9, 20) = std::nextafter(W->HM(9, 20), 1e300);
+#endif
+        EF->marginalizeFrame(FH[1]); W->marginalizeFramePrior(1);
+        if (!same_dyn(EF->HM, W->HM)) { double mx = 0; for (size_t i = 0; i < EF->HM.d.size() && i < W->HM.d.size(); i++) mx = std::max(mx, fabs(EF->HM.d[i] - W->HM.d[i])); printf("   marginalizeFrame HM %dx%d vs %dx%d max abs diff %.3g\n", EF->HM.r, EF->HM.c, W->HM.r, W->HM.c, mx); }
+        CHECK(same_dyn(EF->HM, W->HM) && same_dyn(EF->bM, W->bM), "EnergyFunctional::marginalizeFrame (a middle frame): HM, bM");
+        CHECK(EF->nFrames == nF - 1 && FH[2]->idx == 1 && FH[3]->idx == 2, "marginalizeFrame bookkeeping");
+    }
+    { double nx = 0, nh = 0; for (int i = 0; i < n; i++) nx += EF->lastX[i] * EF->lastX[i]; for (double v : EF->HM.d) nh += v * v;
+      printf("  backend pin: %d frames, %d points, %d active residuals, system size %d; |lastX| = %.6g, |HM after marginalizeFrame| = %.6g (%dx%d)\n", nF, nP, nAct, n, sqrt(nx), sqrt(nh), EF->HM.r, EF->HM.c); }
+    delete EF->red; EF->red = nullptr;
+    oracle_ba_destroy(S->o); delete S;
+}
+
 // Eigen's PartialPivLU inverse (Mat88::inverse() in marginalizeFrame) and JacobiSVD (orthogonalize), forwarded likewise
 extern "C" void ref_shim_inverse_lu(int n, const double *A, double *out) {
     oracle::MatX M(n, n);
@@ -646,6 +823,15 @@ static void pin_tracker() {
     for (int l = 0; l < L; l++) { pyrRef[l].assign(3 * (w >> l) * (h >> l), 0.f); pyrNew[l].assign(3 * (w >> l) * (h >> l), 0.f); pr[l] = pyrRef[l].data(); pn[l] = pyrNew[l].data(); }
     oracle::makeImages(colRef.data(), w, h, L, pr);
     oracle::makeImages(colNew.data(), w, h, L, pn);
+    {   // FrameHessian::makeImages, the reference's own (src/internal/FrameHessian.cc:44-100), against the oracle's pyramid
+        auto fhI = make_fh(nullptr, true);
+        fhI->makeImages(colRef.data(), make_calib(520, 522, 318.3, 241.1));
+        bool ok = fhI->dI == fhI->dIp[0];
+        // the reference leaves the first and last image row's gradients uninitialised beyond its byte-count memset; compare the rows it writes
+        for (int l = 0; l < L; l++) { const int wl = w >> l, hl = h >> l; for (int i = wl; i < wl * (hl - 1); i++) ok &= memcmp(fhI->dIp[l][i].d, pr[l] + 3 * i, 12) == 0;
+                                      for (int i = 0; i < wl * hl; i++) ok &= memcmp(&fhI->dIp[l][i][0], pr[l] + 3 * i, 4) == 0; }
+        CHECK(ok, "FrameHessian::makeImages: intensity pyramid and gradients on every level");
+    }
 
     // reference side: frames, features, points, their newest residual
     auto HC = make_calib(fxl, fyl, cxl, cyl);
@@ -821,9 +1007,10 @@ int main() {
     pin_projections();
     pin_linearize();
     pin_hessians();
+    pin_backend();
     pin_tracker();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc and CoarseTracker.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc, EnergyFunctional.cc and CoarseTracker.cc\n", checks);
     return 0;
 }
