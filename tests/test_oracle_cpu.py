@@ -1,9 +1,10 @@
 """CPU tests of the oracle (the parity checker) and of the synthetic-input builder. No GPU needed.
 
-The reference ships no golden vectors for this path and its build cannot run here. What pins the oracle: (0) the reference's own
-Residuals.cc (linearize), ImmaturePoint.cc (traceOn), accumulators, samplers, projections, affine transfer and constants are compiled
-from its sources and compared bit for bit (oracle/ref_pin, test_oracle_pinned_against_reference_sources); for the control
-flow around them (1) independent re-derivations of the same algebra in double-precision numpy, (2) invariants the algorithm must
+The reference ships no golden vectors for this path and its build cannot run here. What pins the oracle: (0) nine of the reference's
+own translation units (Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc,
+AccumulatedSCHessian.cc, EnergyFunctional.cc, CoarseTracker.cc) and their headers are compiled from its sources against stand-in
+Eigen / Sophus headers and compared bit for bit (oracle/ref_pin, test_oracle_pinned_against_reference_sources); for Eigen / Sophus
+themselves and the FullSystem driver loop (1) independent re-derivations of the same algebra in double-precision numpy, (2) invariants the algorithm must
 satisfy, (3) frozen outputs in tests/golden/.
 """
 import os
@@ -297,11 +298,14 @@ REFERENCE = "/root/reference"
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "include", "internal")), reason="the reference tree is only mounted in the build container")
 def test_oracle_pinned_against_reference_sources():
-    """oracle/ref_pin: the reference's OWN src/internal/Residuals.cc (PointFrameResidual::linearize, applyRes/takeData,
-    fixLinearizationF), src/internal/ImmaturePoint.cc (constructor, traceOn, linearizeResidual), MatrixAccumulators.h, GlobalFuncs.h,
-    ResidualProjections.h, AffLight.h and src/Setting.cc, compiled unmodified where they lie (against oracle/ref_shim: stand-ins for
-    the Eigen types and the five classes they reach into), agree bit for bit with the oracle on thousands of generated cases; the
-    negative control (one operand scaled by 1 + 2e-7 on the oracle side) is detected."""
+    """oracle/ref_pin: the reference's OWN Residuals.cc (linearize, applyRes/takeData, fixLinearizationF), AccumulatedTopHessian.cc /
+    AccumulatedSCHessian.cc (addPoint<0,1,2>, SC addPoint, the stitchers), EnergyFunctional.cc (insertFrame, setAdjointsF, setDeltaF,
+    solveSystemF, resubstitute, orthogonalize, energies, marginalizePointsF, marginalizeFrame), FrameHessian.cc, FrameFramePrecalc.cc,
+    PointHessian.cc, CoarseTracker.cc (makeK, makeCoarseDepthL0, calcRes, calcGSSSE, trackNewestCoarse), ImmaturePoint.cc (constructor,
+    traceOn, linearizeResidual), MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc, compiled
+    unmodified where they lie (against oracle/ref_shim: stand-ins for Eigen / Sophus / Frame.h / OpenCV / glog), agree bit for bit
+    with the oracle on 98 checks; the negative controls (an operand scaled by 1 + 2e-7, two results moved by one ulp on the oracle
+    side) are detected."""
     import subprocess
     odir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
     subprocess.check_call(["make", "-C", odir, "-s", "ref_pin", "REF=" + REFERENCE])
