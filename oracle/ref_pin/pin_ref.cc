@@ -907,6 +907,54 @@ static void pin_tracker() {
     CHECK(okMap, "makeCoarseDepthL0: idepth and weightSums maps on every level");
     CHECK(R.refFrameID == 10 + nKF - 1 && R.lastRef_aff_g2l.a == lastRef->aff_g2l().a, "setCoarseTrackingRef bookkeeping");
 
+
+    // ---- CoarseDistanceMap (same file): makeK, makeDistanceMap (projection of the ACTIVE points of the other keyframes + BFS), addIntoDistFinal
+    {
+        const int nH = 3, nPts = 700;
+        std::vector<shared_ptr<FrameHessian>> DF(nH + 1); std::vector<shared_ptr<Frame>> DR(nH + 1);
+        CoarseDistanceMap RD(w, h); oracle::CoarseDistanceMap OD(w, h, L);
+        RD.makeK(HC); OD.makeK(fxl, fyl, cxl, cyl);
+        for (int f = 0; f <= nH; f++) {
+            DR[f] = std::make_shared<Frame>(); DF[f] = make_fh(DR[f]); DR[f]->frameHessian = DF[f];
+            Vec6 xi; for (int i = 0; i < 6; i++) xi[i] = frand(-1.f, 1.f) * (i < 3 ? 0.05 : 0.02);
+            DF[f]->PRE_worldToCam = SE3::exp(xi); DF[f]->PRE_camToWorld = DF[f]->PRE_worldToCam.inverse();
+        }
+        auto newest = DF[nH];
+        OD.beginDistanceMap();
+        for (int f = 0; f < nH; f++) {
+            std::vector<float> pu, pv, pid;
+            for (int k = 0; k < nPts; k++) {
+                auto feat = std::make_shared<Feature>(0.f, 0.f, DR[f]); auto pt = std::make_shared<Point>(); auto ph = std::make_shared<PointHessian>();
+                feat->point = pt; pt->mpPH = ph; pt->status = (k % 13 == 5) ? Point::PointStatus::OUTLIER : Point::PointStatus::ACTIVE;
+                ph->u = frand(-20.f, w + 20.f); ph->v = frand(-20.f, h + 20.f); ph->idepth_scaled = frand(0.05f, 2.5f);
+                if (k < 40) { ph->u = frand(0.f, 3.f); ph->v = frand(0.f, h - 1.f); }       // some land on the left border column of level 1
+                DR[f]->features.push_back(feat);
+                if (k % 17 == 3) feat->point = nullptr;
+                else if (pt->status == Point::PointStatus::ACTIVE) { pu.push_back(ph->u); pv.push_back(ph->v); pid.push_back(ph->idepth_scaled); }
+            }
+            const SE3 fhToNew = newest->PRE_worldToCam * DF[f]->PRE_camToWorld;
+            const Mat33f Rf = fhToNew.rotationMatrix().cast<float>(); const Vec3f tf = fhToNew.translation().cast<float>();
+            float Rr[9], tr[3]; for (int i = 0; i < 3; i++) { tr[i] = tf[i]; for (int j = 0; j < 3; j++) Rr[i * 3 + j] = Rf(i, j); }
+            OD.addFramePoints(Rr, tr, (int) pu.size(), pu.data(), pv.data(), pid.data());
+        }
+        OD.finishDistanceMap();
+        RD.makeDistanceMap(DF, newest);
+        const size_t nb = 4 * (size_t) RD.w[1] * RD.h[1];
+        int nz = 0, nfar = 0; for (int i = 0; i < RD.w[1] * RD.h[1]; i++) { nz += RD.fwdWarpedIDDistFinal[i] == 0; nfar += RD.fwdWarpedIDDistFinal[i] > 5; }
+        bool okK2 = true; for (int l = 0; l < L; l++) for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) okK2 &= memcmp(&RD.K[l](i, j), &OD.K[l][i * 3 + j], 4) == 0 && memcmp(&RD.Ki[l](i, j), &OD.Ki[l][i * 3 + j], 4) == 0;
+        CHECK(okK2 && RD.w[1] == OD.w[1] && RD.h[1] == OD.h[1], "CoarseDistanceMap::makeK");
+        CHECK(nz > 800 && nfar > 500, "distance map scenario: many seeds, regions farther than 5");
+        CHECK(memcmp(RD.fwdWarpedIDDistFinal, OD.fwdWarpedIDDistFinal.data(), nb) == 0, "CoarseDistanceMap::makeDistanceMap: the level-1 distance map");
+        bool okAdd = true;
+        for (int k = 0; k < 400; k++) {
+            const int u = 1 + (int) frand(0.f, RD.w[1] - 2.f), v = 1 + (int) frand(0.f, RD.h[1] - 2.f);
+            RD.addIntoDistFinal(u, v); OD.addIntoDistFinal(u, v);
+            if (k % 50 == 49) okAdd &= memcmp(RD.fwdWarpedIDDistFinal, OD.fwdWarpedIDDistFinal.data(), nb) == 0;
+        }
+        CHECK(okAdd, "CoarseDistanceMap::addIntoDistFinal x400 (incremental BFS)");
+        printf("  distance map pin: %d seed cells, %d cells farther than 5 before the incremental adds\n", nz, nfar);
+    }
+
     // calcRes / calcGSSSE at several poses, brightness parameters, cutoffs and levels
     R.newFrame = newFH;
     bool okRes = true, okBuf = true, okH = true; int nSat = 0, nEval = 0;

@@ -455,4 +455,157 @@ bool CoarseTracker::trackNewestCoarse(SE3 &lastToNew_out, float &aff_a_out, floa
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// CoarseDistanceMap — CoarseTracker.cc:634-870
+CoarseDistanceMap::CoarseDistanceMap(int ww, int hh, int levels) {
+    pyrLevelsUsed = levels;
+    fwdWarpedIDDistFinal.assign((size_t) ww * hh / 4, 0.f);
+    bfsList1.assign((size_t) ww * hh / 4 * 2, 0);
+    bfsList2.assign((size_t) ww * hh / 4 * 2, 0);
+    for (int l = 0; l < PYR_LEVELS; l++) w[l] = h[l] = 0;
+    w[0] = ww; h[0] = hh;       // the reference takes them from wG / hG in makeK
+}
+
+void CoarseDistanceMap::makeK(float fxl, float fyl, float cxl, float cyl) {   // :657-685 (same arithmetic as CoarseTracker::makeK)
+    fx[0] = fxl; fy[0] = fyl; cx[0] = cxl; cy[0] = cyl;
+    for (int level = 1; level < pyrLevelsUsed; ++level) {
+        w[level] = w[0] >> level;
+        h[level] = h[0] >> level;
+        fx[level] = fx[level - 1] * 0.5;
+        fy[level] = fy[level - 1] * 0.5;
+        cx[level] = (cx[0] + 0.5) / ((int) 1 << level) - 0.5;
+        cy[level] = (cy[0] + 0.5) / ((int) 1 << level) - 0.5;
+    }
+    for (int level = 0; level < pyrLevelsUsed; ++level) {
+        float *Kl = K[level];
+        Kl[0] = fx[level]; Kl[1] = 0; Kl[2] = cx[level];
+        Kl[3] = 0; Kl[4] = fy[level]; Kl[5] = cy[level];
+        Kl[6] = 0; Kl[7] = 0; Kl[8] = 1;
+        m33f_inverse_t(Kl, Ki[level]);
+    }
+}
+
+static void m33f_mul_t(const float *a, const float *b, float *c) {   // 3x3 float product, row . column accumulated left to right
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float s = a[i * 3 + 0] * b[0 * 3 + j];
+            s += a[i * 3 + 1] * b[1 * 3 + j];
+            s += a[i * 3 + 2] * b[2 * 3 + j];
+            c[i * 3 + j] = s;
+        }
+}
+
+// KRKi = K[1] * R * Ki[0], Kt = K[1] * t (CoarseTracker.cc:705-706, FullSystem.cc:1093-1094)
+void CoarseDistanceMap::hostToNewest(const float R[9], const float t[3], float KRKi[9], float Kt[3]) const {
+    float KR[9];
+    m33f_mul_t(K[1], R, KR);
+    m33f_mul_t(KR, Ki[0], KRKi);
+    for (int i = 0; i < 3; i++) {
+        float s = K[1][i * 3 + 0] * t[0];
+        s += K[1][i * 3 + 1] * t[1];
+        s += K[1][i * 3 + 2] * t[2];
+        Kt[i] = s;
+    }
+}
+
+void CoarseDistanceMap::beginDistanceMap() {   // :690-698
+    int wh1 = w[1] * h[1];
+    for (int i = 0; i < wh1; i++) fwdWarpedIDDistFinal[i] = 1000;
+    numItems = 0;
+}
+
+void CoarseDistanceMap::addFramePoints(const float R[9], const float t[3], int n, const float *u_, const float *v_, const float *idepth_scaled) {   // :701-722
+    float KRKi[9], Kt[3];
+    hostToNewest(R, t, KRKi, Kt);
+    int w1 = w[1];
+    for (int i = 0; i < n; i++) {
+        float ptp[3];
+        for (int r = 0; r < 3; r++) {
+            float s = KRKi[r * 3 + 0] * u_[i];
+            s += KRKi[r * 3 + 1] * v_[i];
+            s += KRKi[r * 3 + 2] * 1.0f;
+            ptp[r] = s + Kt[r] * idepth_scaled[i];
+        }
+        int u = ptp[0] / ptp[2] + 0.5f;
+        int v = ptp[1] / ptp[2] + 0.5f;
+        if (!(u > 0 && v > 0 && u < w[1] && v < h[1])) continue;
+        fwdWarpedIDDistFinal[u + w1 * v] = 0;
+        bfsList1[2 * numItems] = u; bfsList1[2 * numItems + 1] = v;
+        numItems++;
+    }
+}
+
+void CoarseDistanceMap::growDistBFS(int bfsNum) {   // :728-812
+    int w1 = w[1], h1 = h[1];
+    float *D = fwdWarpedIDDistFinal.data();
+    for (int k = 1; k < 40; k++) {
+        int bfsNum2 = bfsNum;
+        std::swap(bfsList1, bfsList2);
+        bfsNum = 0;
+        const int n4[4] = {1, -1, w1, -w1}, dx4[4] = {1, -1, 0, 0}, dy4[4] = {0, 0, 1, -1};
+        const int n8[4] = {1 + w1, -1 + w1, -1 - w1, 1 - w1}, dx8[4] = {1, -1, -1, 1}, dy8[4] = {1, 1, -1, -1};
+        for (int i = 0; i < bfsNum2; i++) {
+            int x = bfsList2[2 * i], y = bfsList2[2 * i + 1];
+            if (x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1) continue;
+            int idx = x + y * w1;
+            for (int q = 0; q < 4; q++)
+                if (D[idx + n4[q]] > k) {
+                    D[idx + n4[q]] = k;
+                    bfsList1[2 * bfsNum] = x + dx4[q]; bfsList1[2 * bfsNum + 1] = y + dy4[q];
+                    bfsNum++;
+                }
+            if (k % 2 != 0)      // odd steps also grow diagonally
+                for (int q = 0; q < 4; q++)
+                    if (D[idx + n8[q]] > k) {
+                        D[idx + n8[q]] = k;
+                        bfsList1[2 * bfsNum] = x + dx8[q]; bfsList1[2 * bfsNum + 1] = y + dy8[q];
+                        bfsNum++;
+                    }
+        }
+    }
+}
+
+void CoarseDistanceMap::addIntoDistFinal(int u, int v) {   // :814-819
+    if (w[0] == 0) return;
+    bfsList1[0] = u; bfsList1[1] = v;
+    fwdWarpedIDDistFinal[u + w[1] * v] = 0;
+    growDistBFS(1);
+}
+
+// FullSystem::activatePointsMT — FullSystem.cc:1097-1150 (the body of the loop over one host keyframe's immature features)
+void selectActivation(CoarseDistanceMap &M, const float R[9], const float t[3], bool hostFlaggedForMarginalization, float currentMinActDist,
+                      float minTraceQuality, int n, const ActivationCand *c, unsigned char *action) {
+    float KRKi[9], Kt[3];
+    M.hostToNewest(R, t, KRKi, Kt);
+    const int w1 = M.w[1], h1 = M.h[1];
+    for (int i = 0; i < n; i++) {
+        const ActivationCand &ph = c[i];
+        if (!std::isfinite(ph.idepth_max) || ph.lastTraceStatus == 2 /*IPS_OUTLIER*/) { action[i] = 2; continue; }          // :1103-1107
+        bool canActivate = (ph.lastTraceStatus == 0 /*GOOD*/ || ph.lastTraceStatus == 3 /*SKIPPED*/ || ph.lastTraceStatus == 4 /*BADCONDITION*/ ||
+                            ph.lastTraceStatus == 1 /*OOB*/)
+                           && ph.lastTracePixelInterval < 8 && ph.quality > minTraceQuality && (ph.idepth_max + ph.idepth_min) > 0;   // :1109-1115
+        if (!canActivate) {                                                                                                 // :1117-1125
+            action[i] = (hostFlaggedForMarginalization || ph.lastTraceStatus == 1) ? 2 : 0;
+            continue;
+        }
+        float ptp[3];                                                                                                       // :1128-1131
+        const float idm = 0.5f * (ph.idepth_max + ph.idepth_min);
+        for (int r = 0; r < 3; r++) {
+            float s = KRKi[r * 3 + 0] * ph.u;
+            s += KRKi[r * 3 + 1] * ph.v;
+            s += KRKi[r * 3 + 2] * 1.0f;
+            ptp[r] = s + Kt[r] * idm;
+        }
+        int u = ptp[0] / ptp[2] + 0.5f;
+        int v = ptp[1] / ptp[2] + 0.5f;
+        if (u > 0 && v > 0 && u < w1 && v < h1) {                                                                           // :1133-1143
+            float dist = M.fwdWarpedIDDistFinal[u + w1 * v] + (ptp[0] - floorf((float) (ptp[0])));
+            if (dist >= currentMinActDist * ph.my_type) {
+                M.addIntoDistFinal(u, v);
+                action[i] = 1;
+            } else action[i] = 0;
+        } else action[i] = 2;                                                                                               // :1144-1148
+    }
+}
+
 }  // namespace oracle

@@ -48,4 +48,32 @@ struct CoarseTracker {
                            const double minResForAbort[5]);                          // :61-217
 };
 
+// CoarseDistanceMap — include/frontend/CoarseTracker.h:128-170, src/frontend/CoarseTracker.cc:634-870: for every pixel of pyramid
+// level 1 of the newest keyframe, the (alternating 4-/8-neighbourhood) distance to the nearest projected ACTIVE point, capped at 40.
+struct CoarseDistanceMap {
+    int pyrLevelsUsed = 0;
+    int w[PYR_LEVELS], h[PYR_LEVELS];
+    float fx[PYR_LEVELS], fy[PYR_LEVELS], cx[PYR_LEVELS], cy[PYR_LEVELS];
+    float K[PYR_LEVELS][9], Ki[PYR_LEVELS][9];
+    std::vector<float> fwdWarpedIDDistFinal;     // w[1] * h[1]
+    std::vector<int> bfsList1, bfsList2;         // (x, y) pairs
+    int numItems = 0;
+    CoarseDistanceMap(int ww, int hh, int levels);                                 // :637-647
+    void makeK(float fxl, float fyl, float cxl, float cyl);                        // :657-685
+    // makeDistanceMap (:687-726) in three parts: reset, the points of one host keyframe (R, t = rotation / translation of
+    // newest.PRE_worldToCam * host.PRE_camToWorld cast to float, as :704-706 does), grow
+    void beginDistanceMap();
+    void addFramePoints(const float R[9], const float t[3], int n, const float *u, const float *v, const float *idepth_scaled);
+    void finishDistanceMap() { growDistBFS(numItems); }
+    void growDistBFS(int bfsNum);                                                  // :728-812
+    void addIntoDistFinal(int u, int v);                                           // :814-819
+    void hostToNewest(const float R[9], const float t[3], float KRKi[9], float Kt[3]) const;   // :705-706, FullSystem.cc:1093-1094
+};
+
+// The selection loop of FullSystem::activatePointsMT (FullSystem.cc:1088-1150) over candidates of one host keyframe, in order.
+// action: 0 = stays immature, 1 = goes to optimizeImmaturePoint (and was added to the distance map), 2 = deleted.
+struct ActivationCand { float u, v, idepth_min, idepth_max, quality, lastTracePixelInterval, my_type; int lastTraceStatus; };
+void selectActivation(CoarseDistanceMap &M, const float R[9], const float t[3], bool hostFlaggedForMarginalization, float currentMinActDist,
+                      float minTraceQuality, int n, const ActivationCand *c, unsigned char *action);
+
 }  // namespace oracle
