@@ -257,6 +257,10 @@ def run_ours(args):
     big_extra = None
     if world == 1:
         trace_extra = run_trace(ctx, win)
+        try:
+            trace_extra["activation_select"] = run_select(ctx, win)
+        except Exception as e:      # an extra, never the headline
+            trace_extra["activation_select"] = {"error": repr(e)}
         big_extra = run_config3(args, torch, stream, flush)
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
@@ -408,6 +412,34 @@ def run_trace(ctx, win):
     dt = (time.perf_counter() - t0) / reps
     return {"candidates": n, "ms_per_pass": 1e3 * dt, "candidates_per_s": n / dt, "good": int((states[-1]["status"] == 0).sum()),
             "def": "ImmaturePoint::traceOn of 1500 fresh candidates (unbounded idepth interval: full epipolar search) on one frame, host arrays in/out"}
+
+
+def run_select(ctx, win):
+    """SURVEY 8f rank 2, last piece: FullSystem::activatePointsMT's selection (CoarseDistanceMap + the order-dependent greedy pass) for
+    the traced candidates of the bench window, through the C ABI from host arrays; the oracle port's time beside it."""
+    from tests import oracle_py
+    case = _trace_inputs(win)
+    tr = oracle_py.OracleTrace(win, case)
+    tr.trace_on(win.nF - 2); tr.trace_on(win.nF - 1)
+    newest = win.nF - 1
+    m = case.host != newest
+    n = int(m.sum())
+    quality = np.where(np.isfinite(tr.quality[m]), tr.quality[m], 0).astype(np.float32)
+    a = (case.u[m], case.v[m], case.host[m], tr.idepth_min[m], tr.idepth_max[m], tr.status[m], tr.interval[m], quality, np.ones(n, np.float32))
+    for _ in range(3):
+        act = ctx.select_activation(newest, 2.0, *a)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        act = ctx.select_activation(newest, 2.0, *a)
+    dt = (time.perf_counter() - t0) / reps
+    o = oracle_py.OracleBA(win, threads_mode=1, fast=True)
+    t0 = time.perf_counter()
+    ao, _ = o.select_activation(newest, 2.0, *a)
+    dto = time.perf_counter() - t0
+    return {"candidates": n, "window_points": int(win.nP), "ms_per_call": 1e3 * dt, "cpu_port_ms_per_call_1core": 1e3 * dto, "selected": int((act == 1).sum()),
+            "identical_to_cpu_port": bool(np.array_equal(act, ao)),
+            "def": "distance map of the window's points at level 1 + greedy accept/keep/delete pass, currentMinActDist = 2, host arrays in/out"}
 
 
 def cpu_baseline(win):

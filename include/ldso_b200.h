@@ -296,6 +296,20 @@ int ldso_b200_optimize_immature(ldso_b200_ctx *ctx, int n, const float *u, const
                                 const float *idepth_max, const float *color8, const float *weights8, const float *energyTH, int min_obs,
                                 int32_t *ok, float *idepth, uint8_t *res_state);
 
+/* The selection loop of FullSystem::activatePointsMT (FullSystem.cc:1076-1150) with CoarseDistanceMap::makeK / makeDistanceMap /
+ * addIntoDistFinal (src/frontend/CoarseTracker.cc:657-819), against the device-resident window (set_frames + set_window: the
+ * window's points are the ACTIVE points that seed the distance map, projected into pyramid level 1 of frame newest_frame).
+ * Candidates are visited in the order given (the reference walks the keyframes in window order and each keyframe's features in
+ * index order); host[i] must not be newest_frame. current_min_act_dist = FullSystem::currentMinActDist after its update
+ * (:1054-1074), min_trace_quality = setting_minTraceQuality (Setting.cc:51), frame_flagged[f] = flaggedForMarginalization.
+ * action[i]: 0 = stays immature, 1 = selected (pass it to ldso_b200_optimize_immature; it is already in the distance map),
+ * 2 = the reference deletes it (never traced / outlier / cannot activate and leaving / projects outside). dist_map (optional,
+ * (w/2)*(h/2) floats) receives fwdWarpedIDDistFinal as the loop leaves it. */
+int ldso_b200_select_activation(ldso_b200_ctx *ctx, int newest_frame, float current_min_act_dist, float min_trace_quality, int n,
+                                const float *u, const float *v, const int32_t *host, const float *idepth_min, const float *idepth_max,
+                                const int32_t *lastTraceStatus, const float *lastTracePixelInterval, const float *quality,
+                                const float *my_type, const uint8_t *frame_flagged, uint8_t *action, float *dist_map);
+
 /* ---- coarse tracker (src/frontend/CoarseTracker.cc) ---------------------------------------------------- */
 /* CoarseTracker::makeK (:219-246) */
 int ldso_b200_tracker_make_k(ldso_b200_ctx *ctx, float fx, float fy, float cx, float cy);

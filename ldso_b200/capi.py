@@ -68,7 +68,7 @@ SYMBOLS = [
     "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_kernel_times", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
-    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_optimize_begin",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_select_activation", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
@@ -450,6 +450,22 @@ class Context:
         self._chk(self.L.ldso_b200_optimize_immature(self.ctx, n, _f(u), _f(v), _i(host), _f(imin), _f(imax), _f(col), _f(wts), _f(eth), int(min_obs),
                                                      _i(ok), _f(idepth), _b(states)))
         return ok, idepth, states
+
+    def select_activation(self, newest, current_min_act_dist, u, v, host, idepth_min, idepth_max, status, interval, quality, my_type,
+                          frame_flagged=None, min_trace_quality=3.0, want_map=False):
+        """FullSystem::activatePointsMT's selection loop over the device-resident window: action per candidate (0 stays immature,
+        1 activate, 2 delete) and, if asked, the level-1 distance map as the loop leaves it."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        u, v, imin, imax, itv, q, mt = map(f32, (u, v, idepth_min, idepth_max, interval, quality, my_type))
+        host = np.ascontiguousarray(host, np.int32); status = np.ascontiguousarray(status, np.int32)
+        n = u.shape[0]
+        flagged = np.zeros(max(self.nF, 1), np.uint8) if frame_flagged is None else np.ascontiguousarray(frame_flagged, np.uint8)
+        action = np.zeros(n, np.uint8)
+        dmap = np.zeros((self.h >> 1, self.w >> 1), np.float32) if want_map else None
+        self._chk(self.L.ldso_b200_select_activation(self.ctx, int(newest), C.c_float(current_min_act_dist), C.c_float(min_trace_quality), n, _f(u), _f(v),
+                                                     _i(host), _f(imin), _f(imax), _i(status), _f(itv), _f(q), _f(mt), _b(flagged), _b(action),
+                                                     _f(dmap) if want_map else None))
+        return (action, dmap) if want_map else action
 
     def tracker_make_k(self, fx, fy, cx, cy):
         self._chk(self.L.ldso_b200_tracker_make_k(self.ctx, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))

@@ -42,6 +42,7 @@ struct ldso_b200_ctx {
     DevWindow d;
     std::vector<void *> win_allocs;
     bool have_window = false, have_frames = false, derived_dirty = true;
+    std::vector<unsigned char> h_scratch_bytes;     // select_activation's map read-back
     std::vector<int> h_pt_host, h_res_begin, h_res_target;
     int nF = 0, n = 0;
     int slots[MAXF];
@@ -1098,6 +1099,64 @@ extern "C" int ldso_b200_optimize_immature(ldso_b200_ctx *c, int n, const float 
     LAUNCH_CHECK(c);
     D2H(ok, dok, 4 * N); D2H(idepth, did, 4 * N); D2H(res_state, dst, N * nF);
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    return LDSO_B200_OK;
+}
+
+// FullSystem::activatePointsMT's selection (FullSystem.cc:1076-1150): distance map of the window's points in the newest keyframe,
+// then the greedy pass over the candidates. One kernel, one CTA (the pass is order-dependent by construction).
+extern "C" int ldso_b200_select_activation(ldso_b200_ctx *c, int newest_frame, float current_min_act_dist, float min_trace_quality, int n,
+                                           const float *u, const float *v, const int32_t *host, const float *idepth_min, const float *idepth_max,
+                                           const int32_t *lastTraceStatus, const float *lastTracePixelInterval, const float *quality,
+                                           const float *my_type, const uint8_t *frame_flagged, uint8_t *action, float *dist_map) {
+    if (!c || n < 0) return LDSO_B200_ERR_ARG;
+    if (!c->have_frames || !c->have_window) return c->fail(LDSO_B200_ERR_STATE, "select_activation needs set_frames and set_window first");
+    const int nF = c->nF;
+    if (newest_frame < 0 || newest_frame >= nF) return c->fail(LDSO_B200_ERR_ARG, "newest_frame out of range");
+    if (n > 0 && (!u || !v || !host || !idepth_min || !idepth_max || !lastTraceStatus || !lastTracePixelInterval || !quality || !my_type || !action))
+        return c->fail(LDSO_B200_ERR_ARG, "null candidate array");
+    if (!frame_flagged) return c->fail(LDSO_B200_ERR_ARG, "frame_flagged must hold one byte per frame");
+    for (int i = 0; i < n; i++) if (host[i] < 0 || host[i] >= nF || host[i] == newest_frame) return c->fail(LDSO_B200_ERR_ARG, "candidate host must be a window frame other than the newest");
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    const int w1 = c->w >> 1, h1 = c->h >> 1;
+    const size_t N = (size_t) std::max(n, 1), cells = (size_t) w1 * h1, map_bytes = (cells + 3) & ~(size_t) 3;
+    // layout of the scratch buffer (4-byte units first, bytes last)
+    const size_t words = 2 * cells /*frontiers*/ + 12 * N /*7 float + 2 int inputs, 3 scratch*/;
+    RET_IF(trace_reserve(c, 4 * words + map_bytes + N + MAXF + 16));
+    int *q = (int *) c->trace_buf;
+    ActSelArgs A;
+    A.ws = c->ws_dev; A.newest = newest_frame; A.w1 = w1; A.h1 = h1;
+    A.nP = c->d.nP; A.pt_host = c->d.pt_host; A.pt_u = c->d.pt_u; A.pt_v = c->d.pt_v; A.pt_idepth = c->d.pt_idepth;
+    A.n = n;
+    A.front0 = q; q += cells; A.front1 = q; q += cells;
+    float *du = (float *) q; q += N; float *dv = (float *) q; q += N; float *dmin = (float *) q; q += N; float *dmax = (float *) q; q += N;
+    float *dq = (float *) q; q += N; float *di = (float *) q; q += N; float *dt = (float *) q; q += N; int *ds = q; q += N; int *dh = q; q += N;
+    A.pre_idx = q; q += N; A.pre_frac = (float *) q; q += N; A.pre_thresh = (float *) q; q += N;
+    unsigned char *b = (unsigned char *) q;
+    A.map = b; b += map_bytes; A.action = b; b += N; unsigned char *dflag = b;
+    A.map_bytes = (int) map_bytes;
+    A.u = du; A.v = dv; A.idmin = dmin; A.idmax = dmax; A.quality = dq; A.interval = di; A.my_type = dt; A.status = ds; A.host = dh; A.flagged = dflag;
+    A.currentMinActDist = current_min_act_dist; A.minTraceQuality = min_trace_quality;
+    A.use_smem = map_bytes <= 200 * 1024 ? 1 : 0;
+#define AS_H2D(dst_, src_, bytes_) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst_, src_, bytes_, cudaMemcpyHostToDevice, c->stream))
+    if (n > 0) {
+        AS_H2D(du, u, 4 * (size_t) n); AS_H2D(dv, v, 4 * (size_t) n); AS_H2D(dmin, idepth_min, 4 * (size_t) n); AS_H2D(dmax, idepth_max, 4 * (size_t) n);
+        AS_H2D(dq, quality, 4 * (size_t) n); AS_H2D(di, lastTracePixelInterval, 4 * (size_t) n); AS_H2D(dt, my_type, 4 * (size_t) n);
+        AS_H2D(ds, lastTraceStatus, 4 * (size_t) n); AS_H2D(dh, host, 4 * (size_t) n);
+    }
+    AS_H2D(dflag, frame_flagged, (size_t) nF);
+#undef AS_H2D
+    c->kt_begin("actsel");
+    launch_activation_select(A, c->stream);
+    c->kt_end();
+    LAUNCH_CHECK(c);
+    if (n > 0) D2H(action, A.action, (size_t) n);
+    if (dist_map) {
+        c->h_scratch_bytes.resize(map_bytes);
+        D2H(c->h_scratch_bytes.data(), A.map, map_bytes);
+    }
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (dist_map) for (size_t i = 0; i < cells; i++) dist_map[i] = c->h_scratch_bytes[i] == 255 ? 1000.f : (float) c->h_scratch_bytes[i];   // fwdWarpedIDDistFinal's values
     return LDSO_B200_OK;
 }
 

@@ -14,3 +14,10 @@ void launch_optimize_immature(int n, const WinState *ws, const float *u, const f
     k_optimize_immature<<<(n + KTR_WARPS - 1) / KTR_WARPS, 32 * KTR_WARPS, 0, stream>>>(n, ws, u, v, host, idmin, idmax, color8, weights8, energyTH,
                                                                                       minObs, ok, idepth, res_state);
 }
+size_t actsel_smem_bytes(const ActSelArgs &A) { return A.use_smem ? (size_t) A.map_bytes : 0; }
+void launch_activation_select(const ActSelArgs &A, cudaStream_t stream) {
+    const size_t smem = actsel_smem_bytes(A);
+    static size_t configured = 0;
+    if (smem > configured) { cudaFuncSetAttribute(k_activation_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); configured = smem; }
+    k_activation_select<<<1, ACTSEL_THREADS, smem, stream>>>(A);
+}

@@ -397,3 +397,196 @@ __global__ void __launch_bounds__(32 * KTR_WARPS) k_optimize_immature(int n, con
         for (int r = 0; r < MAXF - 1; r++) if (r < nres) res_state[(size_t) i * nF + ((r < h) ? r : r + 1)] = (unsigned char) st[r];
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Which immature points become active points: FullSystem::activatePointsMT's selection loop (FullSystem.cc:1088-1150) over the
+// CoarseDistanceMap (CoarseTracker.cc:634-870). The loop is a greedy, order-dependent pass — every accepted candidate is added
+// to the distance map before the next one is tested — so ONE CTA owns the map (one byte per level-1 pixel, in shared memory when
+// it fits: 75 KB for 640x480): all 1024 threads build it (projection of the window's points, then the 39-step alternating
+// 4-/8-neighbourhood BFS as a frontier expansion, each cell claimed once by a byte-wide compare-and-swap), all threads
+// precompute each candidate's static test (status gates, projection, sub-pixel term, threshold), then one warp replays the
+// reference's sequential pass, growing the map from every accepted point with a warp-wide frontier BFS that stops when
+// nothing improves. Float arithmetic as in the reference (this TU is compiled with -fmad=false).
+__device__ __forceinline__ bool actsel_improve(unsigned char *map, int idx, unsigned k) {      // map[idx] = k if map[idx] > k; true for the one winner
+    unsigned *wp = (unsigned *) (map + (idx & ~3));
+    const int sh = (idx & 3) * 8;
+    unsigned old = *(volatile unsigned *) wp;
+    while (true) {
+        if (((old >> sh) & 255u) <= k) return false;
+        const unsigned nw = (old & ~(255u << sh)) | (k << sh);
+        const unsigned prev = atomicCAS(wp, old, nw);
+        if (prev == old) return true;
+        old = prev;
+    }
+}
+__device__ __forceinline__ int actsel_neighbour(int q, int w1) {     // growDistBFS's visiting order (:747-806)
+    switch (q) { case 0: return 1; case 1: return -1; case 2: return w1; case 3: return -w1; case 4: return 1 + w1; case 5: return -1 + w1; case 6: return -1 - w1; default: return 1 - w1; }
+}
+__device__ __forceinline__ void actsel_m33_mul(const float *a, const float *b, float *c) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float s = a[i * 3 + 0] * b[0 * 3 + j];
+            s += a[i * 3 + 1] * b[1 * 3 + j];
+            s += a[i * 3 + 2] * b[2 * 3 + j];
+            c[i * 3 + j] = s;
+        }
+}
+
+__global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelArgs A) {
+    extern __shared__ __align__(16) unsigned char actsel_smem[];
+    __shared__ float sKRKi[MAXF][9], sKt[MAXF][3];
+    __shared__ int sCnt[2];
+    __shared__ int sLocal[2][ACTSEL_LOCAL_CAP];
+    const int tid = threadIdx.x, w1 = A.w1, h1 = A.h1, nF = A.ws->nF;
+    unsigned char *map = A.use_smem ? actsel_smem : A.map;
+
+    // CoarseDistanceMap::makeK (:657-685) for levels 0 and 1, then K[1] * R * Ki[0] and K[1] * t per host keyframe (:705-706)
+    if (tid < nF && tid != A.newest) {
+        const CalibDev &cal = A.ws->calib;
+        const float fx0 = cal.fxl, fy0 = cal.fyl, cx0 = cal.cxl, cy0 = cal.cyl;
+        const float fx1 = fx0 * 0.5, fy1 = fy0 * 0.5;
+        const float cx1 = (cx0 + 0.5) / ((int) 1 << 1) - 0.5, cy1 = (cy0 + 0.5) / ((int) 1 << 1) - 0.5;
+        const float K1[9] = {fx1, 0, cx1, 0, fy1, cy1, 0, 0, 1}, m[9] = {fx0, 0, cx0, 0, fy0, cy0, 0, 0, 1};
+        float inv[9];                                  // Eigen's 3x3 inverse: cofactors * (1 / det)
+        const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+        const float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+        const float invdet = 1.0f / det;
+        inv[0] = c00 * invdet; inv[3] = c01 * invdet; inv[6] = c02 * invdet;
+        inv[1] = (m[2] * m[7] - m[1] * m[8]) * invdet; inv[4] = (m[0] * m[8] - m[2] * m[6]) * invdet; inv[7] = (m[1] * m[6] - m[0] * m[7]) * invdet;
+        inv[2] = (m[1] * m[5] - m[2] * m[4]) * invdet; inv[5] = (m[2] * m[3] - m[0] * m[5]) * invdet; inv[8] = (m[0] * m[4] - m[1] * m[3]) * invdet;
+        const PairRecFull &pf = A.ws->pairFull[tid + nF * A.newest];
+        float KR[9];
+        actsel_m33_mul(K1, pf.RTll, KR);
+        actsel_m33_mul(KR, inv, sKRKi[tid]);
+        for (int i = 0; i < 3; i++) {
+            float s = K1[i * 3 + 0] * pf.tTll[0];
+            s += K1[i * 3 + 1] * pf.tTll[1];
+            s += K1[i * 3 + 2] * pf.tTll[2];
+            sKt[tid][i] = s;
+        }
+    }
+    for (int i = tid; i < A.map_bytes / 4; i += ACTSEL_THREADS) ((unsigned *) map)[i] = 0xffffffffu;      // :690-692 (1000 everywhere)
+    if (tid < 2) sCnt[tid] = 0;
+    __syncthreads();
+
+    // makeDistanceMap :699-722 — seeds: the ACTIVE points of the other keyframes projected into level 1 of the newest
+    for (int p = tid; p < A.nP; p += ACTSEL_THREADS) {
+        const int hst = A.pt_host[p];
+        if (hst == A.newest) continue;
+        const float *KRKi = sKRKi[hst], *Kt = sKt[hst];
+        const float pu = A.pt_u[p], pv = A.pt_v[p], pid = A.pt_idepth[p];
+        float ptp[3];
+        for (int r = 0; r < 3; r++) {
+            float s = KRKi[r * 3 + 0] * pu;
+            s += KRKi[r * 3 + 1] * pv;
+            s += KRKi[r * 3 + 2] * 1.0f;
+            ptp[r] = s + Kt[r] * pid;
+        }
+        const int u = (int) (ptp[0] / ptp[2] + 0.5f), v = (int) (ptp[1] / ptp[2] + 0.5f);
+        if (!(u > 0 && v > 0 && u < w1 && v < h1)) continue;
+        if (actsel_improve(map, u + w1 * v, 0u)) A.front0[atomicAdd(&sCnt[0], 1)] = u + w1 * v;
+    }
+    __syncthreads();
+
+    // growDistBFS (:728-812): step k claims every cell > k next to a cell claimed at step k-1; even steps 4-neighbourhood, odd steps 8
+    {
+        int *fin = A.front0, *fout = A.front1;
+        int cur = 0;
+        for (int k = 1; k < 40; k++) {
+            const int nin = sCnt[cur], NN = (k % 2 == 0) ? 4 : 8;
+            if (nin == 0) break;
+            for (int t = tid; t < nin * NN; t += ACTSEL_THREADS) {
+                const int cell = fin[t / NN], x = cell % w1, y = cell / w1;
+                if (x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1) continue;
+                const int nidx = cell + actsel_neighbour(t % NN, w1);
+                if (actsel_improve(map, nidx, (unsigned) k)) fout[atomicAdd(&sCnt[cur ^ 1], 1)] = nidx;
+            }
+            __syncthreads();
+            if (tid == 0) sCnt[cur] = 0;
+            cur ^= 1;
+            int *tmp = fin; fin = fout; fout = tmp;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // the static part of every candidate's test (FullSystem.cc:1103-1131, :1144-1148)
+    for (int i = tid; i < A.n; i += ACTSEL_THREADS) {
+        const int st = A.status[i], hst = A.host[i];
+        const float idmax = A.idmax[i], idmin = A.idmin[i];
+        unsigned char act;
+        int cell = -1; float frac = 0.f;
+        if (!isfinite(idmax) || st == IPS_OUTLIER) act = 2;
+        else {
+            const bool canActivate = (st == IPS_GOOD || st == IPS_SKIPPED || st == IPS_BADCONDITION || st == IPS_OOB) && A.interval[i] < 8 &&
+                                     A.quality[i] > A.minTraceQuality && (idmax + idmin) > 0;
+            if (!canActivate) act = (A.flagged[hst] || st == IPS_OOB) ? 2 : 0;
+            else {
+                const float *KRKi = sKRKi[hst], *Kt = sKt[hst];
+                const float idm = 0.5f * (idmax + idmin), cu = A.u[i], cv = A.v[i];
+                float ptp[3];
+                for (int r = 0; r < 3; r++) {
+                    float s = KRKi[r * 3 + 0] * cu;
+                    s += KRKi[r * 3 + 1] * cv;
+                    s += KRKi[r * 3 + 2] * 1.0f;
+                    ptp[r] = s + Kt[r] * idm;
+                }
+                const int u = (int) (ptp[0] / ptp[2] + 0.5f), v = (int) (ptp[1] / ptp[2] + 0.5f);
+                if (u > 0 && v > 0 && u < w1 && v < h1) { act = 3; cell = u + w1 * v; frac = ptp[0] - floorf(ptp[0]); }
+                else act = 2;
+            }
+        }
+        A.action[i] = act;                 // 3 = decided by the sequential pass below
+        A.pre_idx[i] = cell; A.pre_frac[i] = frac; A.pre_thresh[i] = A.currentMinActDist * A.my_type[i];
+    }
+    __syncthreads();
+
+    // the sequential pass (:1133-1143), one warp; 32 candidates' precomputed terms are fetched at a time
+    if (tid < 32) {
+        const int lane = tid;
+        for (int base = 0; base < A.n; base += 32) {
+            const int i = base + lane;
+            unsigned char myAct = 0; int myCell = -1; float myFrac = 0.f, myTh = 0.f;
+            if (i < A.n) { myAct = A.action[i]; myCell = A.pre_idx[i]; myFrac = A.pre_frac[i]; myTh = A.pre_thresh[i]; }
+            const int cnt = min(32, A.n - base);
+            for (int j = 0; j < cnt; j++) {
+                const int act = __shfl_sync(0xffffffffu, (int) myAct, j);
+                if (act != 3) continue;
+                const int cell = __shfl_sync(0xffffffffu, myCell, j);
+                const float frac = __shfl_sync(0xffffffffu, myFrac, j), th = __shfl_sync(0xffffffffu, myTh, j);
+                const unsigned char b = map[cell];
+                const float dist = (b == 255 ? 1000.f : (float) b) + frac;
+                const bool accept = dist >= th;
+                if (lane == j) myAct = accept ? 1 : 0;
+                if (!accept) continue;
+                // addIntoDistFinal (:814-819): the cell becomes 0 and the map grows from it
+                if (lane == 0) { map[cell] = 0; sLocal[0][0] = cell; }
+                __syncwarp();
+                int nin = 1, cur = 0;
+                for (int k = 1; k < 40 && nin > 0; k++) {
+                    const int NN = (k % 2 == 0) ? 4 : 8;
+                    int nout = 0;
+                    for (int t0 = 0; t0 < nin * NN; t0 += 32) {
+                        const int t = t0 + lane;
+                        bool won = false; int nidx = 0;
+                        if (t < nin * NN) {
+                            const int c0 = sLocal[cur][t / NN], x = c0 % w1, y = c0 / w1;
+                            if (!(x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1)) {
+                                nidx = c0 + actsel_neighbour(t % NN, w1);
+                                won = actsel_improve(map, nidx, (unsigned) k);
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, won);
+                        if (won) sLocal[cur ^ 1][nout + __popc(m & ((1u << lane) - 1u))] = nidx;
+                        nout += __popc(m);
+                    }
+                    __syncwarp();
+                    nin = nout; cur ^= 1;
+                }
+            }
+            if (i < A.n) A.action[i] = myAct;
+        }
+    }
+    __syncthreads();
+    if (A.use_smem) for (int i = tid; i < A.map_bytes / 4; i += ACTSEL_THREADS) ((unsigned *) A.map)[i] = ((unsigned *) map)[i];
+}

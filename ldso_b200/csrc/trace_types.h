@@ -29,3 +29,24 @@ void launch_trace_on(const TraceArgs &A, cudaStream_t stream);
 void launch_optimize_immature(int n, const WinState *ws, const float *u, const float *v, const int *host, const float *idmin, const float *idmax,
                               const float *color8, const float *weights8, const float *energyTH, int minObs, int *ok, float *idepth,
                               unsigned char *res_state, cudaStream_t stream);
+
+// Activation selection (FullSystem::activatePointsMT, FullSystem.cc:1076-1150, with CoarseDistanceMap, CoarseTracker.cc:634-870)
+struct ActSelArgs {
+    const WinState *ws; int newest;            // index of the newest keyframe in the window
+    int w1, h1;                                // size of pyramid level 1
+    int nP; const int *pt_host; const float *pt_u, *pt_v, *pt_idepth;       // ACTIVE points of the window: distance-map seeds
+    int n;                                     // candidates, in the order the reference visits them
+    const float *u, *v, *idmin, *idmax, *quality, *interval, *my_type; const int *status, *host;
+    const unsigned char *flagged;              // [nFrames] FrameHessian::flaggedForMarginalization
+    float currentMinActDist, minTraceQuality;
+    unsigned char *action;                     // [n] out: 0 stays immature, 1 activate, 2 delete
+    unsigned char *map;                        // [map_bytes] distance map, one byte per level-1 pixel (255 = the reference's 1000)
+    int map_bytes;                             // w1*h1 rounded up to a multiple of 4
+    int *front0, *front1;                      // [w1*h1] BFS frontiers of the initial (multi-source) growth
+    int *pre_idx; float *pre_frac, *pre_thresh;   // [n] scratch
+    int use_smem;                              // the map fits in shared memory
+};
+#define ACTSEL_THREADS 1024
+#define ACTSEL_LOCAL_CAP 512                   // one seed improves at most 8k cells at step k <= 39
+size_t actsel_smem_bytes(const ActSelArgs &A);
+void launch_activation_select(const ActSelArgs &A, cudaStream_t stream);

@@ -408,4 +408,36 @@ void oracle_ba_optimize_immature(void *o, int n, const float *u, const float *v,
     }
 }
 
+// FullSystem::activatePointsMT's selection over the window's frames and points: distance map of the ACTIVE points (all points of the
+// window whose host is not `newest`) in the newest keyframe, then the greedy pass over the candidates in the order given.
+// action[n] (0 stays, 1 activate, 2 delete), dist_map[(w/2)*(h/2)] (optional).
+void oracle_ba_select_activation(void *o, int levels, int newest, float currentMinActDist, float minTraceQuality, int n, const float *u, const float *v,
+                                 const int *host, const float *idepth_min, const float *idepth_max, const int *status, const float *interval,
+                                 const float *quality, const float *my_type, const unsigned char *flagged, unsigned char *action, float *dist_map) {
+    Window *W = (Window *) o;
+    const int nF = (int) W->frames.size();
+    CoarseDistanceMap M(W->wG0, W->hG0, levels);
+    M.makeK(W->HCalib.fxl(), W->HCalib.fyl(), W->HCalib.cxl(), W->HCalib.cyl());
+    std::vector<float> R(9 * nF), T(3 * nF);
+    for (int f = 0; f < nF; f++) {       // fhToNew = newest.PRE_worldToCam * host.PRE_camToWorld, cast to float (CoarseTracker.cc:704-706)
+        SE3 fhToNew = W->frames[newest].PRE_worldToCam * W->frames[f].PRE_camToWorld;
+        M3 Rd = fhToNew.rotationMatrix();
+        for (int i = 0; i < 9; i++) R[9 * f + i] = (float) Rd.m[i];
+        for (int i = 0; i < 3; i++) T[3 * f + i] = (float) fhToNew.t[i];
+    }
+    M.beginDistanceMap();
+    for (int f = 0; f < nF; f++) {
+        if (f == newest) continue;
+        std::vector<float> pu, pv, pid;
+        for (const Point &p : W->points) if (p.host == f) { pu.push_back(p.u); pv.push_back(p.v); pid.push_back(p.idepth_scaled); }
+        M.addFramePoints(&R[9 * f], &T[3 * f], (int) pu.size(), pu.data(), pv.data(), pid.data());
+    }
+    M.finishDistanceMap();
+    for (int i = 0; i < n; i++) {        // one call per candidate keeps the caller's order whatever the host sequence is
+        ActivationCand c{u[i], v[i], idepth_min[i], idepth_max[i], quality[i], interval[i], my_type[i], status[i]};
+        selectActivation(M, &R[9 * host[i]], &T[3 * host[i]], flagged[host[i]] != 0, currentMinActDist, minTraceQuality, 1, &c, action + i);
+    }
+    if (dist_map) memcpy(dist_map, M.fwdWarpedIDDistFinal.data(), sizeof(float) * (size_t) M.w[1] * M.h[1]);
+}
+
 }  // extern "C"

@@ -152,6 +152,22 @@ class OracleBA:
                                            int(min_obs), ok.ctypes.data_as(c_ip), _f(idepth), states.ctypes.data_as(C.POINTER(C.c_ubyte)))
         return ok, idepth, states
 
+    def select_activation(self, newest, current_min_act_dist, u, v, host, idepth_min, idepth_max, status, interval, quality, my_type,
+                          frame_flagged=None, min_trace_quality=3.0, levels=None):
+        """FullSystem::activatePointsMT's selection loop (CoarseDistanceMap + the greedy pass): (action[n], dist_map[h/2, w/2])."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        u, v, imin, imax, itv, q, mt = map(f32, (u, v, idepth_min, idepth_max, interval, quality, my_type))
+        host = np.ascontiguousarray(host, np.int32); status = np.ascontiguousarray(status, np.int32)
+        n = u.shape[0]
+        flagged = np.zeros(self.win.nF, np.uint8) if frame_flagged is None else np.ascontiguousarray(frame_flagged, np.uint8)
+        action = np.zeros(n, np.uint8)
+        dmap = np.zeros((self.win.h >> 1, self.win.w >> 1), np.float32)
+        ub = C.POINTER(C.c_ubyte)
+        self.L.oracle_ba_select_activation(self.o, int(levels or self.win.levels), int(newest), C.c_float(current_min_act_dist), C.c_float(min_trace_quality), n,
+                                           _f(u), _f(v), host.ctypes.data_as(c_ip), _f(imin), _f(imax), status.ctypes.data_as(c_ip), _f(itv), _f(q), _f(mt),
+                                           flagged.ctypes.data_as(ub), action.ctypes.data_as(ub), _f(dmap))
+        return action, dmap
+
     def marginalize_frame(self, idx):
         """EnergyFunctional::marginalizeFrame's HM/bM algebra; returns the shrunken (HM, bM)."""
         nd = int(self.L.oracle_ba_marginalize_frame(self.o, int(idx)))

@@ -142,3 +142,49 @@ def test_optimize_immature_matches_oracle(geom):
     with pytest.raises(capi.Error):
         ctx.optimize_immature(*bad)
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", ["small", "vga", "kitti"])
+def test_select_activation_matches_oracle(geom):
+    """FullSystem::activatePointsMT's selection loop (FullSystem.cc:1076-1150) with CoarseDistanceMap (CoarseTracker.cc:634-870): the
+    level-1 distance map of the window's points and the order-dependent accept / keep / delete decision of every traced candidate
+    are integer work - bit-exact against the oracle (which is pinned against the reference's own CoarseDistanceMap)."""
+    if geom == "small":
+        win = synth.make_window(nF=6, pts_per_frame=40, w=320, h=240, seed=3); per_host = 300
+    elif geom == "vga":
+        win = synth.make_window(nF=8, pts_per_frame=250, seed=42); per_host = 400
+    else:
+        win = synth.make_window(nF=7, pts_per_frame=150, w=1240, h=376, seed=9); per_host = 400
+    case = synth.make_trace_case(win, per_host, seed=5)
+    tr = oracle_py.OracleTrace(win, case)
+    tr.trace_on(win.nF - 2); tr.trace_on(win.nF - 1)
+    newest = win.nF - 1
+    m = case.host != newest
+    rng = np.random.default_rng(11)
+    n = int(m.sum())
+    my_type = rng.choice(np.array([1.0, 2.0, 4.0], np.float32), n)
+    quality = np.where(np.isfinite(tr.quality[m]), tr.quality[m], 0).astype(np.float32)
+    flagged = np.zeros(win.nF, np.uint8); flagged[0] = 1
+    args = (case.u[m], case.v[m], case.host[m], tr.idepth_min[m], tr.idepth_max[m], tr.status[m], tr.interval[m], quality, my_type)
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    ctx = capi.Context(win.w, win.h, win.levels)
+    ctx.load_synth_window(win)
+    seen = set()
+    for dist in (0.0, 1.3, 2.0, 4.0):
+        ao, mo = o.select_activation(newest, dist, *args, frame_flagged=flagged)
+        ag, mg = ctx.select_activation(newest, dist, *args, frame_flagged=flagged, want_map=True)
+        assert np.array_equal(mg, mo), (geom, dist, int((mg != mo).sum()))
+        assert np.array_equal(ag, ao), (geom, dist, int((ag != ao).sum()))
+        seen |= set(np.unique(ao).tolist())
+        assert (mo == 0).sum() > 100 and mo.max() >= 5
+    assert seen == {0, 1, 2}, seen
+    # the map without candidates = CoarseDistanceMap::makeDistanceMap alone; an empty candidate list is fine
+    a0, m0 = ctx.select_activation(newest, 2.0, *(a[:0] for a in args), frame_flagged=flagged, want_map=True)
+    _, mo0 = o.select_activation(newest, 2.0, *(a[:0] for a in args), frame_flagged=flagged)
+    assert a0.shape == (0,) and np.array_equal(m0, mo0)
+    # a candidate hosted by the newest keyframe is a caller error (the reference skips that keyframe)
+    bad = list(args); bad[2] = np.full_like(args[2], newest)
+    with pytest.raises(capi.Error):
+        ctx.select_activation(newest, 2.0, *bad, frame_flagged=flagged)
+    ctx.close()

@@ -313,3 +313,32 @@ def test_oracle_pinned_against_reference_sources():
     assert r.returncode == 0 and "PIN OK" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([os.path.join(odir, "_ref", "pin_ref_break")], capture_output=True, text=True)
     assert r.returncode != 0 and "PIN MISMATCH" in r.stdout
+
+
+def test_select_activation_oracle():
+    """CoarseDistanceMap + activatePointsMT's selection (oracle): invariants of the greedy pass. (The map code itself is pinned against
+    the reference's CoarseDistanceMap by oracle/ref_pin.)"""
+    win = synth.make_window(nF=6, pts_per_frame=40, w=320, h=240, seed=3)
+    case = synth.make_trace_case(win, 300, seed=5)
+    tr = oracle_py.OracleTrace(win, case)
+    tr.trace_on(win.nF - 2); tr.trace_on(win.nF - 1)
+    newest = win.nF - 1
+    m = case.host != newest
+    n = int(m.sum())
+    quality = np.where(np.isfinite(tr.quality[m]), tr.quality[m], 0).astype(np.float32)
+    args = (case.u[m], case.v[m], case.host[m], tr.idepth_min[m], tr.idepth_max[m], tr.status[m], tr.interval[m], quality, np.ones(n, np.float32))
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    _, base = o.select_activation(newest, 2.0, *(a[:0] for a in args))          # makeDistanceMap alone
+    assert set(np.unique(base).tolist()) <= set(range(40)) | {1000} and (base == 0).sum() > 50
+    prev = None
+    for dist in (0.0, 1.0, 2.0, 4.0):
+        act, dmap = o.select_activation(newest, dist, *args)
+        assert set(np.unique(act).tolist()) <= {0, 1, 2}
+        assert (dmap <= base).all()                                              # accepted points only ever shrink distances
+        assert (dmap == 0).sum() - (base == 0).sum() <= (act == 1).sum()          # every new zero is an accepted candidate
+        never = ~np.isfinite(tr.idepth_max[m]) | (tr.status[m] == oracle_py.IPS_OUTLIER)
+        assert (act[never] == 2).all()
+        if prev is not None:
+            assert (act == 1).sum() <= prev                                       # a larger minimum distance accepts fewer
+        prev = (act == 1).sum()
+    assert prev > 0
