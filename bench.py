@@ -433,10 +433,11 @@ def run_select(ctx, win):
     for _ in range(reps):
         act = ctx.select_activation(newest, 2.0, *a)
     dt = (time.perf_counter() - t0) / reps
-    o = oracle_py.OracleBA(win, threads_mode=1, fast=True)
+    o = oracle_py.OracleBA(win, threads_mode=1, fast=True)      # -O3 -march=native: the timing build (its FMA contraction may move a projection across a pixel boundary)
     t0 = time.perf_counter()
-    ao, _ = o.select_activation(newest, 2.0, *a)
+    o.select_activation(newest, 2.0, *a)
     dto = time.perf_counter() - t0
+    ao, _ = oracle_py.OracleBA(win, threads_mode=1).select_activation(newest, 2.0, *a)      # the bit-reproducible build: the checker
     return {"candidates": n, "window_points": int(win.nP), "ms_per_call": 1e3 * dt, "cpu_port_ms_per_call_1core": 1e3 * dto, "selected": int((act == 1).sum()),
             "identical_to_cpu_port": bool(np.array_equal(act, ao)),
             "def": "distance map of the window's points at level 1 + greedy accept/keep/delete pass, currentMinActDist = 2, host arrays in/out"}

@@ -43,6 +43,7 @@ struct ldso_b200_ctx {
     std::vector<void *> win_allocs;
     bool have_window = false, have_frames = false, derived_dirty = true;
     std::vector<unsigned char> h_scratch_bytes;     // select_activation's map read-back
+    unsigned char *actsel_pin = nullptr; size_t actsel_pin_cap = 0;      // its pinned staging block
     std::vector<int> h_pt_host, h_res_begin, h_res_target;
     int nF = 0, n = 0;
     int slots[MAXF];
@@ -263,6 +264,7 @@ extern "C" void ldso_b200_destroy(ldso_b200_ctx *c) {
     if (c->ws_dev) cudaFree(c->ws_dev);
     if (c->ws_host) cudaFreeHost(c->ws_host);
     if (c->sol_host) cudaFreeHost(c->sol_host);
+    if (c->actsel_pin) cudaFreeHost(c->actsel_pin);
     if (c->trace_buf) cudaFree(c->trace_buf);
     for (int r = 0; r < K2R_MAX_PEERS; r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
     if (c->peer_local) cudaFree(c->peer_local);
@@ -1122,7 +1124,7 @@ extern "C" int ldso_b200_select_activation(ldso_b200_ctx *c, int newest_frame, f
     const size_t N = (size_t) std::max(n, 1), cells = (size_t) w1 * h1, map_bytes = (cells + 3) & ~(size_t) 3;
     // layout of the scratch buffer (4-byte units first, bytes last)
     const size_t words = 2 * cells /*frontiers*/ + 12 * N /*7 float + 2 int inputs, 3 scratch*/;
-    RET_IF(trace_reserve(c, 4 * words + map_bytes + N + MAXF + 16));
+    RET_IF(trace_reserve(c, 4 * words + map_bytes + N + MAXF + 64));
     int *q = (int *) c->trace_buf;
     ActSelArgs A;
     A.ws = c->ws_dev; A.newest = newest_frame; A.w1 = w1; A.h1 = h1;
@@ -1138,24 +1140,40 @@ extern "C" int ldso_b200_select_activation(ldso_b200_ctx *c, int newest_frame, f
     A.u = du; A.v = dv; A.idmin = dmin; A.idmax = dmax; A.quality = dq; A.interval = di; A.my_type = dt; A.status = ds; A.host = dh; A.flagged = dflag;
     A.currentMinActDist = current_min_act_dist; A.minTraceQuality = min_trace_quality;
     A.use_smem = map_bytes <= 200 * 1024 ? 1 : 0;
-#define AS_H2D(dst_, src_, bytes_) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst_, src_, bytes_, cudaMemcpyHostToDevice, c->stream))
-    if (n > 0) {
-        AS_H2D(du, u, 4 * (size_t) n); AS_H2D(dv, v, 4 * (size_t) n); AS_H2D(dmin, idepth_min, 4 * (size_t) n); AS_H2D(dmax, idepth_max, 4 * (size_t) n);
-        AS_H2D(dq, quality, 4 * (size_t) n); AS_H2D(di, lastTracePixelInterval, 4 * (size_t) n); AS_H2D(dt, my_type, 4 * (size_t) n);
-        AS_H2D(ds, lastTraceStatus, 4 * (size_t) n); AS_H2D(dh, host, 4 * (size_t) n);
+    // the nine candidate arrays and the frame flags travel as ONE pinned staging block laid out like the device block
+    const size_t in_words = 9 * N, in_bytes = 4 * in_words, stage_bytes = in_bytes + N + MAXF + 16;
+    if (stage_bytes > c->actsel_pin_cap) {
+        if (c->actsel_pin) cudaFreeHost(c->actsel_pin);
+        c->actsel_pin = nullptr; c->actsel_pin_cap = 0;
+        CUDA_CHECK_RET(c, cudaHostAlloc((void **) &c->actsel_pin, stage_bytes * 2, cudaHostAllocDefault));
+        c->actsel_pin_cap = stage_bytes * 2;
     }
-    AS_H2D(dflag, frame_flagged, (size_t) nF);
-#undef AS_H2D
+    {
+        unsigned char *hp = c->actsel_pin;
+        const void *src[9] = {u, v, idepth_min, idepth_max, quality, lastTracePixelInterval, my_type, lastTraceStatus, host};
+        for (int k = 0; k < 9; k++) if (n > 0) memcpy(hp + 4 * N * k, src[k], 4 * (size_t) n);
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(du, hp, in_bytes, cudaMemcpyHostToDevice, c->stream));      // du .. dh are contiguous
+        memcpy(hp + in_bytes, frame_flagged, (size_t) nF);
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(dflag, hp + in_bytes, (size_t) nF, cudaMemcpyHostToDevice, c->stream));
+    }
+    A.dbg = c->ktime ? (long long *) (dflag + MAXF) : nullptr;      // 8-byte aligned below
+    if (A.dbg) A.dbg = (long long *) (((uintptr_t) A.dbg + 7) & ~(uintptr_t) 7);
     c->kt_begin("actsel");
     launch_activation_select(A, c->stream);
     c->kt_end();
     LAUNCH_CHECK(c);
-    if (n > 0) D2H(action, A.action, (size_t) n);
+    unsigned char *hact = c->actsel_pin + in_bytes + MAXF + 8;
+    if (n > 0) D2H(hact, A.action, (size_t) n);
     if (dist_map) {
         c->h_scratch_bytes.resize(map_bytes);
         D2H(c->h_scratch_bytes.data(), A.map, map_bytes);
     }
+    long long stamps[4] = {0, 0, 0, 0};
+    if (A.dbg) D2H(stamps, A.dbg, sizeof(stamps));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (n > 0) memcpy(action, hact, (size_t) n);
+    if (A.dbg) fprintf(stderr, "[ldso_b200 actsel] cycles: map+seeds+grow %lld, candidate terms %lld, sequential pass %lld\n", stamps[1] - stamps[0],
+                       stamps[2] - stamps[1], stamps[3] - stamps[2]);
     if (dist_map) for (size_t i = 0; i < cells; i++) dist_map[i] = c->h_scratch_bytes[i] == 255 ? 1000.f : (float) c->h_scratch_bytes[i];   // fwdWarpedIDDistFinal's values
     return LDSO_B200_OK;
 }

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(32 * KTR_WARPS) k_optimize_immature(int n, con
 // reference's sequential pass, growing the map from every accepted point with a warp-wide frontier BFS that stops when
 // nothing improves. Float arithmetic as in the reference (this TU is compiled with -fmad=false).
 __device__ __forceinline__ bool actsel_improve(unsigned char *map, int idx, unsigned k) {      // map[idx] = k if map[idx] > k; true for the one winner
+    if (((volatile unsigned char *) map)[idx] <= k) return false;          // most probes fail: settle them with a byte load
     unsigned *wp = (unsigned *) (map + (idx & ~3));
     const int sh = (idx & 3) * 8;
     unsigned old = *(volatile unsigned *) wp;
@@ -419,9 +420,9 @@ __device__ __forceinline__ bool actsel_improve(unsigned char *map, int idx, unsi
         old = prev;
     }
 }
-__device__ __forceinline__ int actsel_neighbour(int q, int w1) {     // growDistBFS's visiting order (:747-806)
-    switch (q) { case 0: return 1; case 1: return -1; case 2: return w1; case 3: return -w1; case 4: return 1 + w1; case 5: return -1 + w1; case 6: return -1 - w1; default: return 1 - w1; }
-}
+// frontier entries are (x | y << 16); neighbour q in growDistBFS's visiting order (:747-806): +x, -x, +y, -y, then the four diagonals
+__device__ __forceinline__ int actsel_dx(int q) { return (int) ((0x8252u >> (2 * q)) & 3u) - 1; }      // 1,-1,0,0,1,-1,-1,1
+__device__ __forceinline__ int actsel_dy(int q) { return (int) ((0x0a25u >> (2 * q)) & 3u) - 1; }      // 0,0,1,-1,1,1,-1,-1
 __device__ __forceinline__ void actsel_m33_mul(const float *a, const float *b, float *c) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) {
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
             sKt[tid][i] = s;
         }
     }
+    if (tid == 0 && A.dbg) A.dbg[0] = clock64();
     for (int i = tid; i < A.map_bytes / 4; i += ACTSEL_THREADS) ((unsigned *) map)[i] = 0xffffffffu;      // :690-692 (1000 everywhere)
     if (tid < 2) sCnt[tid] = 0;
     __syncthreads();
@@ -484,7 +486,7 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
         }
         const int u = (int) (ptp[0] / ptp[2] + 0.5f), v = (int) (ptp[1] / ptp[2] + 0.5f);
         if (!(u > 0 && v > 0 && u < w1 && v < h1)) continue;
-        if (actsel_improve(map, u + w1 * v, 0u)) A.front0[atomicAdd(&sCnt[0], 1)] = u + w1 * v;
+        if (actsel_improve(map, u + w1 * v, 0u)) A.front0[atomicAdd(&sCnt[0], 1)] = u | (v << 16);
     }
     __syncthreads();
 
@@ -493,13 +495,13 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
         int *fin = A.front0, *fout = A.front1;
         int cur = 0;
         for (int k = 1; k < 40; k++) {
-            const int nin = sCnt[cur], NN = (k % 2 == 0) ? 4 : 8;
+            const int nin = sCnt[cur], lg = (k % 2 == 0) ? 2 : 3;
             if (nin == 0) break;
-            for (int t = tid; t < nin * NN; t += ACTSEL_THREADS) {
-                const int cell = fin[t / NN], x = cell % w1, y = cell / w1;
+            for (int t = tid; t < (nin << lg); t += ACTSEL_THREADS) {
+                const int xy = fin[t >> lg], x = xy & 0xffff, y = xy >> 16, q = t & ((1 << lg) - 1);
                 if (x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1) continue;
-                const int nidx = cell + actsel_neighbour(t % NN, w1);
-                if (actsel_improve(map, nidx, (unsigned) k)) fout[atomicAdd(&sCnt[cur ^ 1], 1)] = nidx;
+                const int nx = x + actsel_dx(q), ny = y + actsel_dy(q);
+                if (actsel_improve(map, nx + ny * w1, (unsigned) k)) fout[atomicAdd(&sCnt[cur ^ 1], 1)] = nx | (ny << 16);
             }
             __syncthreads();
             if (tid == 0) sCnt[cur] = 0;
@@ -510,6 +512,7 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
     }
     __syncthreads();
 
+    if (tid == 0 && A.dbg) A.dbg[1] = clock64();
     // the static part of every candidate's test (FullSystem.cc:1103-1131, :1144-1148)
     for (int i = tid; i < A.n; i += ACTSEL_THREADS) {
         const int st = A.status[i], hst = A.host[i];
@@ -537,10 +540,11 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
             }
         }
         A.action[i] = act;                 // 3 = decided by the sequential pass below
-        A.pre_idx[i] = cell; A.pre_frac[i] = frac; A.pre_thresh[i] = A.currentMinActDist * A.my_type[i];
+        A.pre_idx[i] = cell < 0 ? -1 : ((cell % w1) | ((cell / w1) << 16)); A.pre_frac[i] = frac; A.pre_thresh[i] = A.currentMinActDist * A.my_type[i];
     }
     __syncthreads();
 
+    if (tid == 0 && A.dbg) A.dbg[2] = clock64();
     // the sequential pass (:1133-1143), one warp; 32 candidates' precomputed terms are fetched at a time
     if (tid < 32) {
         const int lane = tid;
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
             for (int j = 0; j < cnt; j++) {
                 const int act = __shfl_sync(0xffffffffu, (int) myAct, j);
                 if (act != 3) continue;
-                const int cell = __shfl_sync(0xffffffffu, myCell, j);
+                const int cxy = __shfl_sync(0xffffffffu, myCell, j), cell = (cxy & 0xffff) + (cxy >> 16) * w1;
                 const float frac = __shfl_sync(0xffffffffu, myFrac, j), th = __shfl_sync(0xffffffffu, myTh, j);
                 const unsigned char b = map[cell];
                 const float dist = (b == 255 ? 1000.f : (float) b) + frac;
@@ -560,24 +564,25 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
                 if (lane == j) myAct = accept ? 1 : 0;
                 if (!accept) continue;
                 // addIntoDistFinal (:814-819): the cell becomes 0 and the map grows from it
-                if (lane == 0) { map[cell] = 0; sLocal[0][0] = cell; }
+                if (lane == 0) { map[cell] = 0; sLocal[0][0] = cxy; }
                 __syncwarp();
                 int nin = 1, cur = 0;
                 for (int k = 1; k < 40 && nin > 0; k++) {
-                    const int NN = (k % 2 == 0) ? 4 : 8;
+                    const int lg = (k % 2 == 0) ? 2 : 3;
                     int nout = 0;
-                    for (int t0 = 0; t0 < nin * NN; t0 += 32) {
+                    for (int t0 = 0; t0 < (nin << lg); t0 += 32) {
                         const int t = t0 + lane;
-                        bool won = false; int nidx = 0;
-                        if (t < nin * NN) {
-                            const int c0 = sLocal[cur][t / NN], x = c0 % w1, y = c0 / w1;
+                        bool won = false; int nxy = 0;
+                        if (t < (nin << lg)) {
+                            const int xy = sLocal[cur][t >> lg], x = xy & 0xffff, y = xy >> 16, q = t & ((1 << lg) - 1);
                             if (!(x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1)) {
-                                nidx = c0 + actsel_neighbour(t % NN, w1);
-                                won = actsel_improve(map, nidx, (unsigned) k);
+                                const int nx = x + actsel_dx(q), ny = y + actsel_dy(q);
+                                nxy = nx | (ny << 16);
+                                won = actsel_improve(map, nx + ny * w1, (unsigned) k);
                             }
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, won);
-                        if (won) sLocal[cur ^ 1][nout + __popc(m & ((1u << lane) - 1u))] = nidx;
+                        if (won) sLocal[cur ^ 1][nout + __popc(m & ((1u << lane) - 1u))] = nxy;
                         nout += __popc(m);
                     }
                     __syncwarp();
@@ -588,5 +593,6 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
         }
     }
     __syncthreads();
+    if (tid == 0 && A.dbg) A.dbg[3] = clock64();
     if (A.use_smem) for (int i = tid; i < A.map_bytes / 4; i += ACTSEL_THREADS) ((unsigned *) A.map)[i] = ((unsigned *) map)[i];
 }

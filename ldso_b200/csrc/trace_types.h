@@ -45,6 +45,7 @@ struct ActSelArgs {
     int *front0, *front1;                      // [w1*h1] BFS frontiers of the initial (multi-source) growth
     int *pre_idx; float *pre_frac, *pre_thresh;   // [n] scratch
     int use_smem;                              // the map fits in shared memory
+    long long *dbg;                            // clock64() phase stamps (development aid; null = off)
 };
 #define ACTSEL_THREADS 1024
 #define ACTSEL_LOCAL_CAP 512                   // one seed improves at most 8k cells at step k <= 39
