@@ -418,6 +418,9 @@ def run_select(ctx, win):
     """SURVEY 8f rank 2, last piece: FullSystem::activatePointsMT's selection (CoarseDistanceMap + the order-dependent greedy pass) for
     the traced candidates of the bench window, through the C ABI from host arrays; the oracle port's time beside it."""
     from tests import oracle_py
+    from ldso_b200 import capi
+    ctx = capi.Context(win.w, win.h, win.levels)       # a fresh context: the bench context's window has been optimised, the oracle's has not
+    ctx.load_synth_window(win)
     case = _trace_inputs(win)
     tr = oracle_py.OracleTrace(win, case)
     tr.trace_on(win.nF - 2); tr.trace_on(win.nF - 1)
@@ -438,6 +441,7 @@ def run_select(ctx, win):
     o.select_activation(newest, 2.0, *a)
     dto = time.perf_counter() - t0
     ao, _ = oracle_py.OracleBA(win, threads_mode=1).select_activation(newest, 2.0, *a)      # the bit-reproducible build: the checker
+    ctx.close()
     return {"candidates": n, "window_points": int(win.nP), "ms_per_call": 1e3 * dt, "cpu_port_ms_per_call_1core": 1e3 * dto, "selected": int((act == 1).sum()),
             "identical_to_cpu_port": bool(np.array_equal(act, ao)),
             "def": "distance map of the window's points at level 1 + greedy accept/keep/delete pass, currentMinActDist = 2, host arrays in/out"}
