@@ -93,37 +93,75 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
+def _ref_arm_seconds_per_iter(steps, warmup):
+    """Seconds per GN iteration of the REFERENCE'S OWN back end (oracle/_ref/libref_ba.so: the reference's translation units compiled
+    unmodified against stand-in Eigen headers, its own 6-thread IndexThreadReduce; oracle/ref_pin/ref_bench.cc) on the bench window, or
+    None when that library is not there or does not run on this host. A child process: a library built with -march=native elsewhere
+    must not be able to take the bench down."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    if not os.path.exists(os.path.join(here, "oracle", "_ref", "libref_ba.so")):
+        return None
+    code = ("import time\nfrom ldso_b200 import synth\nfrom tests import oracle_py\n"
+            f"win = synth.make_window(nF={NF}, pts_per_frame={PTS_PER_FRAME}, seed=42)\n"
+            "r = oracle_py.RefBA(win, multithreaded=True)\nr.optimize_begin()\n"
+            f"[r.gn_iteration(min(i, 3)) for i in range({int(warmup)})]\n"
+            f"t0 = time.perf_counter()\n[r.gn_iteration(3) for _ in range({int(steps)})]\n"
+            f"print('REFARM', (time.perf_counter() - t0) / {int(steps)})\n")
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, "-c", code], cwd=here, capture_output=True, text=True, timeout=900)
+    except Exception:
+        return None
+    for ln in r.stdout.splitlines():
+        if ln.startswith("REFARM "):
+            return float(ln.split()[1])
+    return None
+
+
+def _port_seconds_per_iter(win, steps, warmup):
+    from tests import oracle_py
+    o = oracle_py.OracleBA(win, threads_mode=6, fast=True)
+    o.optimize_begin()
+    for i in range(warmup):
+        o.gn_iteration(min(i, 3))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        o.gn_iteration(3)
+    return (time.perf_counter() - t0) / steps
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path. LDSO cannot be compiled here (Eigen/glog/OpenCV/Pangolin
-    absent), so this arm times the oracle port (oracle/liboracle_fast.so, g++ -O3 -march=native like the reference's
-    Release build) with the reference's hard-wired 6 worker threads (NUM_THREADS, include/Settings.h:9)."""
+    """The reference's own CPU implementation of the path, on the host cores, with the reference's hard-wired 6 worker threads
+    (NUM_THREADS, include/Settings.h:9). LDSO's build cannot run here (Eigen / glog / OpenCV / Pangolin absent), but its back-end
+    translation units compile unmodified against stand-in Eigen headers: oracle/_ref/libref_ba.so (kind "reference": linearize, both
+    addPoint's, the stitchers, solveSystemF, resubstituteF and IndexThreadReduce are the reference's code; FullSystem.cc's driver loop
+    around them is restated in oracle/ref_pin/ref_bench.cc; the 68x68 dense algebra runs through the stand-in). When that library is not
+    there, the oracle port (oracle/liboracle_fast.so, kind "port"). The port's rate is reported beside it either way."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from ldso_b200 import synth
-    from tests import oracle_py
     win = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME, seed=42)
-    o = oracle_py.OracleBA(win, threads_mode=6, fast=True)
-    o.optimize_begin()
-    for i in range(args.warmup):
-        o.gn_iteration(min(i, 3))
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        o.gn_iteration(3)
-    dt = time.perf_counter() - t0
-    v = args.steps / dt
+    sec_port = _port_seconds_per_iter(win, args.steps, args.warmup)
+    sec_ref = _ref_arm_seconds_per_iter(args.steps, args.warmup)
+    kind = "reference" if sec_ref else "port"
+    sec = sec_ref if sec_ref else sec_port
+    v = 1.0 / sec
     cores = os.cpu_count()
+    what = ("the reference's own Residuals.cc / AccumulatedTopHessian.cc / AccumulatedSCHessian.cc / EnergyFunctional.cc / FrameHessian.cc / "
+            "FrameFramePrecalc.cc compiled -O3 -march=native against stand-in Eigen headers (oracle/_ref/libref_ba.so), its own IndexThreadReduce"
+            if sec_ref else "oracle port (g++ -O3 -march=native)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GN-iters/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "8 KF x 2000 active points (14000 residuals), 640x480, seed 42", "nF": NF, "n_points": win.nP,
                    "n_residuals": win.nR,
                    "value_unit_note": "iterations/s of ONE 2000-point window on the host CPU; the GPU arm's value at N GPUs counts N such "
                                       "2000-point shards per step, so both arms are in 2000-point-window iterations per second"},
-        "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": "port",
-                         "sample": f"{args.steps} full GN iterations of the same window; oracle port, 6 worker threads "
-                                   f"(reference NUM_THREADS) on a {cores}-core host"},
+        "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": kind, "port_value": 1.0 / sec_port,
+                         "sample": f"{args.steps} full GN iterations of the same window; {what}, 6 worker threads "
+                                   f"(reference NUM_THREADS) on a {cores}-core host; port_value = the oracle port on the same sample"},
         "e2e": {"value": v, "unit": "GN-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -459,6 +497,14 @@ def cpu_baseline(win):
     t0 = time.perf_counter()
     tr.trace_on(win.nF - 1)
     trace_ms = 1e3 * (time.perf_counter() - t0)
+    sec_ref = _ref_arm_seconds_per_iter(40, 6)
+    if sec_ref:
+        return {"trace_immature_ms_per_pass_1core": trace_ms,
+                "value": 1.0 / sec_ref, "unit": "GN-iters/s", "cores": 6, "kind": "reference", "port_value": 1.0 / sec,
+                "sample": f"40 full GN iterations of the same 8 KF x 2000 point window by the reference's own back-end translation units "
+                          f"(oracle/_ref/libref_ba.so: compiled -O3 -march=native against stand-in Eigen headers, FullSystem's driver loop "
+                          f"restated), 6 worker threads = reference NUM_THREADS, host has {os.cpu_count()} cores; port_value = median of 40 by "
+                          f"the oracle port"}
     return {"trace_immature_ms_per_pass_1core": trace_ms,
             "value": 1.0 / sec, "unit": "GN-iters/s", "cores": 6, "kind": "port",
             "sample": f"median of 40 full GN iterations of the same 8 KF x 2000 point window; oracle port "

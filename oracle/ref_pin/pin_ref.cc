@@ -599,15 +599,7 @@ static void pin_hessians() {
     oracle_ba_destroy(S->o); delete S;
 }
 
-// Eigen::LDLT<Mat88 / 77 / 66>::solve as the stand-in forwards it: the oracle's restatement (omath.h) on both sides of the pin
-extern "C" void ref_shim_ldlt_solve(int n, const double *A, const double *b, double *x) {
-    oracle::MatX M(n, n); oracle::VecXd v(n);
-    for (int i = 0; i < n * n; i++) M.d[i] = A[i];
-    for (int i = 0; i < n; i++) v[i] = b[i];
-    const oracle::VecXd r = oracle::ldlt_solve(M, v);
-    for (int i = 0; i < n; i++) x[i] = r[i];
-}
-
+#include "ref_hooks.h"      // LDLT / PartialPivLU / JacobiSVD hand-offs of the stand-in, implemented with the oracle's omath.h
 
 // ---- the back end as a whole: the reference's own FrameHessian.cc, FrameFramePrecalc.cc, PointHessian.h and EnergyFunctional.cc driven
 // through the calls FullSystem makes (FullSystem.cc itself needs the whole front end and is not compiled), against oracle/ba.cc.
@@ -782,20 +774,6 @@ static void pin_backend() {
       printf("  backend pin: %d frames, %d points, %d active residuals, system size %d; |lastX| = %.6g, |HM after marginalizeFrame| = %.6g (%dx%d)\n", nF, nP, nAct, n, sqrt(nx), sqrt(nh), EF->HM.r, EF->HM.c); }
     delete EF->red; EF->red = nullptr;
     oracle_ba_destroy(S->o); delete S;
-}
-
-// Eigen's PartialPivLU inverse (Mat88::inverse() in marginalizeFrame) and JacobiSVD (orthogonalize), forwarded likewise
-extern "C" void ref_shim_inverse_lu(int n, const double *A, double *out) {
-    oracle::MatX M(n, n);
-    for (int i = 0; i < n * n; i++) M.d[i] = A[i];
-    const oracle::MatX I = oracle::inverse_partial_piv_lu(M);
-    for (int i = 0; i < n * n; i++) out[i] = I.d[i];
-}
-extern "C" void ref_shim_jacobi_svd(int m, int n, const double *A, double *U, double *S, double *V) {
-    oracle::MatX M(m, n), Uo, Vo; oracle::VecXd So;
-    for (int i = 0; i < m * n; i++) M.d[i] = A[i];
-    oracle::jacobi_svd(M, Uo, So, Vo);
-    memcpy(U, Uo.d.data(), 8 * Uo.d.size()); memcpy(V, Vo.d.data(), 8 * Vo.d.size()); memcpy(S, So.data(), 8 * So.size());
 }
 
 // ---- CoarseTracker: the reference's src/frontend/CoarseTracker.cc against oracle/tracker.cc

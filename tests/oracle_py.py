@@ -58,6 +58,75 @@ def _d(a):
     return a.ctypes.data_as(c_dp)
 
 
+REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_ba.so")
+
+
+def ref_lib():
+    """oracle/_ref/libref_ba.so: the reference's own back-end translation units behind a C interface (oracle/ref_pin/ref_bench.cc).
+    Built by `make -C oracle ref_pin` where /root/reference is mounted; None where it is not there (the built file travels)."""
+    if not os.path.exists(REF_LIB):
+        return None
+    L = C.CDLL(REF_LIB)
+    L.ref_ba_create.restype = C.c_void_p
+    for f in ("ref_ba_optimize_begin", "ref_ba_energy", "ref_ba_time_gn"):
+        getattr(L, f).restype = C.c_double
+    return L
+
+
+class RefBA:
+    """The same window as OracleBA, held by the REFERENCE'S own classes (FrameHessian, PointHessian, PointFrameResidual,
+    EnergyFunctional, IndexThreadReduce) compiled from /root/reference; only FullSystem.cc's driver loop is restated around them."""
+
+    def __init__(self, win, multithreaded=True, calib_delta=None):
+        self.L = ref_lib()
+        if self.L is None:
+            raise RuntimeError("oracle/_ref/libref_ba.so is not built (needs the reference tree: make -C oracle ref_pin)")
+        self.win = win
+        self.o = C.c_void_p(self.L.ref_ba_create(win.w, win.h, int(bool(multithreaded))))
+        self._keep = []
+        K = np.ascontiguousarray(win.K, np.float64)
+        cd = None if calib_delta is None else np.ascontiguousarray(calib_delta, np.float64)
+        self.L.ref_ba_set_calib(self.o, _d(K), None if cd is None else _d(cd))
+        for i in range(win.nF):
+            dI = np.ascontiguousarray(win.pyramids[i][0], np.float32)
+            self._keep.append(dI)
+            self.L.ref_ba_add_frame(self.o, _d(np.ascontiguousarray(win.Rcw[i], np.float64)), _d(np.ascontiguousarray(win.tcw[i], np.float64)),
+                                    _d(np.ascontiguousarray(win.state_zero[i], np.float64)), _d(np.ascontiguousarray(win.state[i], np.float64)),
+                                    C.c_float(float(win.ab_exposure[i])), int(win.frame_id[i]), _f(dI))
+        col = np.ascontiguousarray(win.pt_color, np.float32)
+        wts = np.ascontiguousarray(win.pt_weights, np.float32)
+        for p in range(win.nP):
+            self.L.ref_ba_add_point(self.o, int(win.pt_host[p]), C.c_float(float(win.pt_u[p])), C.c_float(float(win.pt_v[p])),
+                                    C.c_float(float(win.pt_idepth_zero[p])), C.c_float(float(win.pt_idepth[p])), int(win.pt_has_prior[p]),
+                                    _f(col[p]), _f(wts[p]))
+        for r in range(win.nR):
+            self.L.ref_ba_add_residual(self.o, int(win.res_point[r]), int(win.res_target[r]))
+        self.L.ref_ba_finalize(self.o)
+        self.n = 8 * win.nF + 4
+
+    def optimize_begin(self):
+        return self.L.ref_ba_optimize_begin(self.o)
+
+    def gn_iteration(self, it):
+        return bool(self.L.ref_ba_gn_iteration(self.o, it))
+
+    def energy(self):
+        return self.L.ref_ba_energy(self.o)
+
+    def time_gn(self, iters, warmup):
+        return self.L.ref_ba_time_gn(self.o, iters, warmup)
+
+    def last_x(self):
+        x = np.zeros(self.n, np.float64)
+        self.L.ref_ba_last_x(self.o, _d(x))
+        return x
+
+    def idepths(self):
+        a = np.zeros(self.win.nP, np.float32)
+        self.L.ref_ba_point_idepths(self.o, _f(a))
+        return a
+
+
 class OracleBA:
     """One oracle window built from a ldso_b200.synth.Window."""
 
@@ -108,6 +177,10 @@ class OracleBA:
 
     def gn_iteration(self, it):
         return bool(self.L.oracle_ba_gn_iteration(self.o, it))
+
+    def energy(self):
+        """lastEnergyP of the last linearizeAll."""
+        return self.L.oracle_ba_last_energy(self.o)
 
     def linearize_all(self, fix=False):
         return self.L.oracle_ba_linearize_all(self.o, int(fix))
