@@ -304,7 +304,8 @@ int ldso_b200_optimize_immature(ldso_b200_ctx *ctx, int n, const float *u, const
  * (:1054-1074), min_trace_quality = setting_minTraceQuality (Setting.cc:51), frame_flagged[f] = flaggedForMarginalization.
  * action[i]: 0 = stays immature, 1 = selected (pass it to ldso_b200_optimize_immature; it is already in the distance map),
  * 2 = the reference deletes it (never traced / outlier / cannot activate and leaving / projects outside). dist_map (optional,
- * (w/2)*(h/2) floats) receives fwdWarpedIDDistFinal as the loop leaves it. */
+ * (w/2)*(h/2) floats) receives fwdWarpedIDDistFinal as the loop leaves it. Limit: (w/2)*(h/2) <= 204800 pixels (the map lives in
+ * shared memory, one byte per pixel); larger images return LDSO_B200_ERR_ARG. */
 int ldso_b200_select_activation(ldso_b200_ctx *ctx, int newest_frame, float current_min_act_dist, float min_trace_quality, int n,
                                 const float *u, const float *v, const int32_t *host, const float *idepth_min, const float *idepth_max,
                                 const int32_t *lastTraceStatus, const float *lastTracePixelInterval, const float *quality,

@@ -1139,7 +1139,10 @@ extern "C" int ldso_b200_select_activation(ldso_b200_ctx *c, int newest_frame, f
     A.map_bytes = (int) map_bytes;
     A.u = du; A.v = dv; A.idmin = dmin; A.idmax = dmax; A.quality = dq; A.interval = di; A.my_type = dt; A.status = ds; A.host = dh; A.flagged = dflag;
     A.currentMinActDist = current_min_act_dist; A.minTraceQuality = min_trace_quality;
-    A.use_smem = map_bytes <= 200 * 1024 ? 1 : 0;
+    // the kernel also has a global-memory map path (use_smem = 0) for larger images; it has not been exercised on hardware yet, so
+    // larger images are refused rather than served by an unvalidated path (level 1 of 1240x376 needs 114 KB)
+    if (map_bytes > 200 * 1024) return c->fail(LDSO_B200_ERR_ARG, "select_activation: level-1 image larger than 200 KB (one byte per pixel must fit in shared memory)");
+    A.use_smem = 1;
     // the nine candidate arrays and the frame flags travel as ONE pinned staging block laid out like the device block
     const size_t in_words = 9 * N, in_bytes = 4 * in_words, stage_bytes = in_bytes + N + MAXF + 16;
     if (stage_bytes > c->actsel_pin_cap) {
