@@ -46,7 +46,37 @@ def main():
     np.savez_compressed(os.path.join(HERE, "trace_small.npz"), color=tr.color, weights=tr.weights, gradH=tr.gradH, status1=st1, status2=st2,
                         idepth_min1=imin1, idepth_max1=imax1, idepth_min2=tr.idepth_min, idepth_max2=tr.idepth_max, quality=tr.quality,
                         uv=tr.uv, interval=tr.interval)
+    make_select()
     print("golden written")
+
+
+def select_case():
+    """The activation-selection case shared by make_select() and the tests: window, traced candidates, arguments."""
+    win = synth.make_window(nF=6, pts_per_frame=40, w=320, h=240, seed=3)
+    case = synth.make_trace_case(win, 300, seed=5)
+    tr = oracle_py.OracleTrace(win, case)
+    tr.trace_on(win.nF - 2)
+    tr.trace_on(win.nF - 1)
+    newest = win.nF - 1
+    m = case.host != newest
+    n = int(m.sum())
+    my_type = np.random.default_rng(11).choice(np.array([1.0, 2.0, 4.0], np.float32), n)
+    quality = np.where(np.isfinite(tr.quality[m]), tr.quality[m], 0).astype(np.float32)
+    flagged = np.zeros(win.nF, np.uint8)
+    flagged[0] = 1
+    args = (case.u[m], case.v[m], case.host[m], tr.idepth_min[m], tr.idepth_max[m], tr.status[m], tr.interval[m], quality, my_type)
+    return win, newest, args, flagged
+
+
+def make_select():
+    # activatePointsMT's selection: actions and the level-1 distance map for two minimum distances
+    win, newest, args, flagged = select_case()
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    a13, m13 = o.select_activation(newest, 1.3, *args, frame_flagged=flagged)
+    a20, m20 = o.select_activation(newest, 2.0, *args, frame_flagged=flagged)
+    _, m0 = o.select_activation(newest, 2.0, *(x[:0] for x in args), frame_flagged=flagged)
+    np.savez_compressed(os.path.join(HERE, "select_small.npz"), action13=a13, map13=m13.astype(np.uint16), action20=a20, map20=m20.astype(np.uint16),
+                        map_seed_only=m0.astype(np.uint16))
 
 
 if __name__ == "__main__":

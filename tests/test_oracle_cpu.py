@@ -365,3 +365,19 @@ def test_reference_arm_matches_oracle():
     assert abs(r6.optimize_begin() - e_o) <= 1e-5 * e_o
     r6.gn_iteration(0)
     assert np.isfinite(r6.energy()) and r6.energy() < e_o
+
+
+def test_select_activation_golden():
+    """The frozen selection case (tests/golden/select_small.npz, written by tests/golden/make_golden.py from the pinned oracle)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    win, newest, args, flagged = mg.select_case()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "select_small.npz"))
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    for key, dist in (("13", 1.3), ("20", 2.0)):
+        act, dmap = o.select_activation(newest, dist, *args, frame_flagged=flagged)
+        assert np.array_equal(act, g["action" + key]) and np.array_equal(dmap.astype(np.uint16), g["map" + key])
+    _, m0 = o.select_activation(newest, 2.0, *(a[:0] for a in args), frame_flagged=flagged)
+    assert np.array_equal(m0.astype(np.uint16), g["map_seed_only"])
