@@ -299,6 +299,10 @@ def run_ours(args):
             trace_extra["activation_select"] = run_select(ctx, win)
         except Exception as e:      # an extra, never the headline
             trace_extra["activation_select"] = {"error": repr(e)}
+        try:
+            trace_extra["coarse_tracker"] = run_tracker()
+        except Exception as e:
+            trace_extra["coarse_tracker"] = {"error": repr(e)}
         big_extra = run_config3(args, torch, stream, flush)
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
@@ -450,6 +454,39 @@ def run_trace(ctx, win):
     dt = (time.perf_counter() - t0) / reps
     return {"candidates": n, "ms_per_pass": 1e3 * dt, "candidates_per_s": n / dt, "good": int((states[-1]["status"] == 0).sum()),
             "def": "ImmaturePoint::traceOn of 1500 fresh candidates (unbounded idepth interval: full epipolar search) on one frame, host arrays in/out"}
+
+
+def run_tracker():
+    """SURVEY 8 rows b1-b4 (not the headline metric): one CoarseTracker::trackNewestCoarse (coarse-to-fine LM over all pyramid levels,
+    calcRes + calcGSSSE per evaluation) of a 640x480 frame against a reference keyframe, through the C ABI, images resident; the oracle
+    port on one host core beside it (the reference's tracker is single-threaded)."""
+    from tests import oracle_py
+    from ldso_b200 import capi, synth
+    pair = synth.make_track_pair()
+    ot = oracle_py.OracleTracker(pair, fast=True)
+    ctx = capi.Context(pair.w, pair.h, pair.levels)
+    ctx.upload_frame(0, pair.ref_pyr)
+    ctx.upload_frame(1, pair.new_pyr)
+    ctx.tracker_make_k(*[float(x) for x in pair.K])
+    for l in range(pair.levels):
+        ctx.tracker_set_ref_level(l, *ot.pc(l))
+    ctx.tracker_set_frames(pair.ref_aff[0], pair.ref_aff[1], 1.0, 1, 1.0)
+    I, z = np.eye(3), np.zeros(3)
+    for _ in range(3):
+        r = ctx.tracker_track(I, z, 0.0, 0.0, pair.levels - 1)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = ctx.tracker_track(I, z, 0.0, 0.0, pair.levels - 1)
+    dt = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    ro = ot.track(I, z, 0.0, 0.0, pair.levels - 1)
+    dto = time.perf_counter() - t0
+    ctx.close()
+    return {"ms_per_track": 1e3 * dt, "tracks_per_s": 1.0 / dt, "cpu_port_ms_per_track_1core": 1e3 * dto, "calcRes_evaluations": int(ro[-1]),
+            "converged": bool(r[0]), "same_outcome_as_cpu_port": bool(r[0] == ro[0]),
+            "translation_err_rel": float(np.linalg.norm(r[2] - pair.t_true) / max(np.linalg.norm(pair.t_true), 1e-12)),
+            "def": "trackNewestCoarse from the identity on synth.make_track_pair() (640x480, all levels), pose in / pose out through the C ABI"}
 
 
 def run_select(ctx, win):
