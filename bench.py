@@ -483,7 +483,14 @@ def run_tracker():
     ro = ot.track(I, z, 0.0, 0.0, pair.levels - 1)
     dto = time.perf_counter() - t0
     ctx.close()
-    return {"ms_per_track": 1e3 * dt, "tracks_per_s": 1.0 / dt, "cpu_port_ms_per_track_1core": 1e3 * dto, "calcRes_evaluations": int(ro[-1]),
+    ref_ms = None
+    try:                                   # the reference's own CoarseTracker.cc (oracle/_ref/libref_ba.so), when it is there
+        if oracle_py.ref_lib() is not None:
+            ref_ms = 1e3 * oracle_py.RefTracker(pair).track(I, z, 0.0, 0.0, pair.levels - 1, reps=10)[5]
+    except Exception:
+        ref_ms = None
+    return {"ms_per_track": 1e3 * dt, "tracks_per_s": 1.0 / dt, "reference_ms_per_track_1core": ref_ms, "cpu_port_ms_per_track_1core": 1e3 * dto,
+            "calcRes_evaluations": int(ro[-1]),
             "converged": bool(r[0]), "same_outcome_as_cpu_port": bool(r[0] == ro[0]),
             "translation_err_rel": float(np.linalg.norm(r[2] - pair.t_true) / max(np.linalg.norm(pair.t_true), 1e-12)),
             "def": "trackNewestCoarse from the identity on synth.make_track_pair() (640x480, all levels), pose in / pose out through the C ABI"}

@@ -18,6 +18,7 @@
 #include "../ref_shim/ref_classes.h"
 #include "internal/OptimizationBackend/EnergyFunctional.h"
 #include "internal/GlobalCalib.h"
+#include "frontend/CoarseTracker.h"
 #include "ref_hooks.h"
 
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
@@ -255,6 +256,72 @@ double ref_ba_time_gn(void *o, int iters, int warmup) {
     std::sort(ts.begin(), ts.end());
     return ts.empty() ? 0.0 : ts[ts.size() / 2];
 }
+// ---- the reference's own CoarseTracker (src/frontend/CoarseTracker.cc, compiled unmodified): setCoarseTrackingRef + trackNewestCoarse
+struct RefTracker {
+    shared_ptr<CalibHessian> HC;
+    std::vector<shared_ptr<Frame>> FR; std::vector<shared_ptr<FrameHessian>> FH;
+    shared_ptr<FrameHessian> newFH;
+    std::vector<shared_ptr<PointFrameResidual>> keep;
+    CoarseTracker *T = nullptr;
+};
+static shared_ptr<FrameHessian> ref_make_fh(shared_ptr<Frame> fr) {
+    FrameHessian *p = new FrameHessian(fr);
+    for (int i = 0; i < PYR_LEVELS; i++) { p->dIp[i] = nullptr; p->absSquaredGrad[i] = nullptr; }
+    return shared_ptr<FrameHessian>(p, [](FrameHessian *q) { for (int i = 0; i < PYR_LEVELS; i++) { q->dIp[i] = nullptr; q->absSquaredGrad[i] = nullptr; } delete q; });
+}
+// refDIp / newDIp: `levels` pointers to (I, dx, dy) AoS pyramids; the n reference contributions are (centerProjectedTo[3], HdiF) of the
+// ACTIVE points whose newest residual targets the reference keyframe and is IN (CoarseTracker.cc:258-283)
+void *ref_tracker_create(int w, int h, int levels, const double K[4], const float **refDIp, float ref_aff_a, float ref_aff_b, float ref_exposure,
+                         int n, const float *cpt3, const float *HdiF, const float **newDIp, float new_exposure) {
+    RefTracker *R = new RefTracker();
+    pyrLevelsUsed = levels;
+    for (int l = 0; l < levels; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+    wM3G = w - 3; hM3G = h - 3;
+    R->HC = std::make_shared<CalibHessian>(std::make_shared<Camera>(K[0], K[1], K[2], K[3]));
+    auto fr = std::make_shared<Frame>(); auto fh = ref_make_fh(fr); fr->frameHessian = fh; fr->id = 1;
+    for (int l = 0; l < levels; l++) fh->dIp[l] = (Vec3f *) refDIp[l];
+    fh->dI = fh->dIp[0]; fh->ab_exposure = ref_exposure;
+    fh->setEvalPT_scaled(SE3(), AffLight(ref_aff_a, ref_aff_b));
+    for (int i = 0; i < n; i++) {
+        auto feat = std::make_shared<Feature>(0.f, 0.f, fr); auto pt = std::make_shared<Point>(); auto ph = std::make_shared<PointHessian>();
+        feat->point = pt; pt->mpPH = ph; feat->status = Feature::FeatureStatus::VALID; pt->status = Point::PointStatus::ACTIVE;
+        auto r = std::make_shared<PointFrameResidual>(ph, fh, fh);
+        r->isActiveAndIsGoodNEW = true;
+        r->centerProjectedTo = Vec3f(cpt3[3 * i], cpt3[3 * i + 1], cpt3[3 * i + 2]);
+        ph->HdiF = HdiF[i];
+        ph->lastResiduals[0] = std::make_pair(r, ResState::IN);
+        fr->features.push_back(feat); R->keep.push_back(r);
+    }
+    R->FR.push_back(fr); R->FH.push_back(fh);
+    R->newFH = ref_make_fh(nullptr);
+    for (int l = 0; l < levels; l++) R->newFH->dIp[l] = (Vec3f *) newDIp[l];
+    R->newFH->dI = R->newFH->dIp[0]; R->newFH->ab_exposure = new_exposure;
+    R->T = new CoarseTracker(w, h);
+    R->T->makeK(R->HC);
+    R->T->setCoarseTrackingRef(R->FH);
+    return R;
+}
+// trackNewestCoarse from (R, t), (a, b); returns its bool, the pose / brightness it found and seconds per call (median of `reps`)
+int ref_tracker_track(void *o, double Rm[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl, int reps, double *seconds) {
+    RefTracker *R = (RefTracker *) o;
+    const SE3 start(oracle::SE3::fromRt(Rm, t));
+    const AffLight aff0(*aff_a, *aff_b);
+    Vec5 minRes; for (int i = 0; i < 5; i++) minRes[i] = NAN;
+    std::vector<double> ts; bool ok = false; SE3 T; AffLight aff;
+    for (int k = 0; k < std::max(reps, 1); k++) {
+        T = start; aff = aff0;
+        auto t0 = std::chrono::steady_clock::now();
+        ok = R->T->trackNewestCoarse(R->newFH, T, aff, coarsestLvl, minRes);
+        ts.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    std::sort(ts.begin(), ts.end());
+    if (seconds) *seconds = ts[ts.size() / 2];
+    const Mat33 Ro = T.rotationMatrix();
+    for (int i = 0; i < 3; i++) { t[i] = T.translation()[i]; for (int j = 0; j < 3; j++) Rm[i * 3 + j] = Ro(i, j); }
+    *aff_a = aff.a; *aff_b = aff.b;
+    return ok ? 1 : 0;
+}
+
 // development aid: seconds spent in the phases of `iters` GN iterations: [backup + nullspaces, solveSystemF, doStepFromBackup, linearizeAll, applyRes]
 void ref_ba_profile(void *o, int iters, double out[5]) {
     RefWindow *W = (RefWindow *) o;

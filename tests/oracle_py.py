@@ -127,6 +127,34 @@ class RefBA:
         return a
 
 
+class RefTracker:
+    """The reference's own CoarseTracker (src/frontend/CoarseTracker.cc in oracle/_ref/libref_ba.so) on a synth.make_track_pair() case."""
+
+    def __init__(self, pair):
+        self.L = ref_lib()
+        if self.L is None:
+            raise RuntimeError("oracle/_ref/libref_ba.so is not built")
+        self.L.ref_tracker_create.restype = C.c_void_p
+        self.pair = pair
+        self._ref = [np.ascontiguousarray(p, np.float32) for p in pair.ref_pyr]
+        self._new = [np.ascontiguousarray(p, np.float32) for p in pair.new_pyr]
+        ref_arr = (c_fp * pair.levels)(*[_f(p) for p in self._ref])
+        new_arr = (c_fp * pair.levels)(*[_f(p) for p in self._new])
+        cpt = np.ascontiguousarray(pair.cpt, np.float32)
+        hd = np.ascontiguousarray(pair.HdiF, np.float32)
+        K = np.ascontiguousarray(pair.K, np.float64)
+        self.o = C.c_void_p(self.L.ref_tracker_create(pair.w, pair.h, pair.levels, _d(K), ref_arr, C.c_float(pair.ref_aff[0]), C.c_float(pair.ref_aff[1]),
+                                                      C.c_float(1.0), len(hd), _f(cpt), _f(hd), new_arr, C.c_float(1.0)))
+
+    def track(self, R, t, aff_a, aff_b, coarsest, reps=1):
+        """(ok, R, t, a, b, seconds per call)"""
+        R = np.ascontiguousarray(R, np.float64).copy()
+        t = np.ascontiguousarray(t, np.float64).copy()
+        a, b, sec = C.c_float(aff_a), C.c_float(aff_b), C.c_double(0.0)
+        ok = self.L.ref_tracker_track(self.o, _d(R), _d(t), C.byref(a), C.byref(b), int(coarsest), int(reps), C.byref(sec))
+        return bool(ok), R, t, a.value, b.value, sec.value
+
+
 class OracleBA:
     """One oracle window built from a ldso_b200.synth.Window."""
 

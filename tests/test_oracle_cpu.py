@@ -381,3 +381,15 @@ def test_select_activation_golden():
         assert np.array_equal(act, g["action" + key]) and np.array_equal(dmap.astype(np.uint16), g["map" + key])
     _, m0 = o.select_activation(newest, 2.0, *(a[:0] for a in args), frame_flagged=flagged)
     assert np.array_equal(m0.astype(np.uint16), g["map_seed_only"])
+
+
+@pytest.mark.skipif(oracle_py.ref_lib() is None, reason="oracle/_ref/libref_ba.so is built only where the reference tree is mounted")
+def test_reference_tracker_matches_oracle():
+    """The reference's own CoarseTracker::trackNewestCoarse (optimised build in libref_ba.so) and the oracle port find the same pose
+    and brightness on the full-size pair (the bit-exact comparison of the IEEE builds is oracle/ref_pin's)."""
+    pair = synth.make_track_pair()
+    r = oracle_py.RefTracker(pair).track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    o = oracle_py.OracleTracker(pair, fast=True).track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    assert r[0] and o[0]
+    assert np.abs(r[2] - o[2]).max() < 1e-5 and np.abs(r[1] - o[1]).max() < 1e-5 and abs(r[3] - o[3]) < 1e-4 and abs(r[4] - o[4]) < 1e-2
+    assert np.linalg.norm(r[2] - pair.t_true) < 0.05 * np.linalg.norm(pair.t_true)
