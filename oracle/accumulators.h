@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCES, EXCEPT EIGEN / SOPHUS INTERNALS (oracle/ref_pin compiles, unmodified, the reference's Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc, EnergyFunctional.cc, CoarseTracker.cc, Setting.cc and their headers against stand-in Eigen/Sophus headers and matches the oracle bit for bit on 102 checks; the float SSE / scalar code is pinned completely, the Eigen-expression code structurally - what is added where, in which order - with LDLT, PartialPivLU, JacobiSVD, SE3 exp/log and the product kernels being the oracle's own restatements on both sides; FullSystem.cc's driver loop needs the whole front end and stays restated from the cited lines).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see omath.h header). PARITY PINNED AGAINST THE REFERENCE'S OWN SOURCES, EXCEPT EIGEN / SOPHUS INTERNALS (oracle/ref_pin compiles, unmodified, the reference's Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc, EnergyFunctional.cc, CoarseTracker.cc, Setting.cc and their headers against stand-in Eigen/Sophus headers and matches the oracle bit for bit on 108 checks; the float SSE / scalar code is pinned completely, the Eigen-expression code structurally - what is added where, in which order - with LDLT, PartialPivLU, JacobiSVD, SE3 exp/log and the product kernels being the oracle's own restatements on both sides; FullSystem.cc's driver loop needs the whole front end and stays restated from the cited lines).
 // Restates include/internal/OptimizationBackend/MatrixAccumulators.h of the reference:
 //   AccumulatorXX<i,j> :20-66, Accumulator11 :68-142, AccumulatorX<i> :145-197,
 //   AccumulatorApprox :749-1101, Accumulator9 :1104-1135,1250-1369,1624-1642.
@@ -227,6 +227,41 @@ struct Accumulator9 {
             }
         }
         num += 4;
+        numIn1++;
+        shiftUp(false);
+    }
+    // updateSSE (MatrixAccumulators.h:1138-1248): SSEData[(r, c >= r)][lane] += J[r] * J[c], four residuals at a time
+    void updateSSE(const float J[9][4]) {
+        float *pt = SSEData;
+        for (int r = 0; r < 9; r++)
+            for (int c = r; c < 9; c++) {
+                for (int l = 0; l < 4; l++) pt[l] = pt[l] + J[r][l] * J[c][l];
+                pt += 4;
+            }
+        num += 4;
+        numIn1++;
+        shiftUp(false);
+    }
+    // updateSingle (:1372-1487): one residual into lane `off`
+    void updateSingle(const float J[9], int off = 0) {
+        float *pt = SSEData + off;
+        for (int r = 0; r < 9; r++)
+            for (int c = r; c < 9; c++) { *pt += J[c] * J[r]; pt += 4; }
+        num++;
+        numIn1++;
+        shiftUp(false);
+    }
+    // updateSingleWeighted (:1489-1604): the diagonal term is (J_r * J_r) * w, then J_r *= w feeds the rest of its row
+    void updateSingleWeighted(const float Jin[9], float w, int off = 0) {
+        float J[9];
+        for (int i = 0; i < 9; i++) J[i] = Jin[i];
+        float *pt = SSEData + off;
+        for (int r = 0; r < 9; r++) {
+            *pt += J[r] * J[r] * w; pt += 4;
+            if (r < 8) J[r] *= w;
+            for (int c = r + 1; c < 9; c++) { *pt += J[c] * J[r]; pt += 4; }
+        }
+        num++;
         numIn1++;
         shiftUp(false);
     }

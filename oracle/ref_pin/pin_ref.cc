@@ -20,6 +20,7 @@
 #include "../ba.h"
 #include "../trace.h"
 #include "../tracker.h"
+#include "../initializer.h"
 static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; }
 // the reference's own sources, unmodified, from /root/reference (their `#include "NumTypes.h"` is satisfied by the stand-in)
 #include "../ref_shim/NumTypes.h"
@@ -36,6 +37,7 @@ static inline int oracle_pattern(int i, int k) { return oracle::patternP[i][k]; 
 #include "frontend/CoarseTracker.h"       // the reference's own CoarseTracker; bodies in src/frontend/CoarseTracker.cc
 #include "internal/OptimizationBackend/AccumulatedTopHessian.h"     // the reference's own accumulators; bodies in AccumulatedTopHessian.cc / AccumulatedSCHessian.cc
 #include "internal/OptimizationBackend/AccumulatedSCHessian.h"
+#include "frontend/CoarseInitializer.h"    // the reference's own initializer; calcResAndGS lives in src/frontend/CoarseInitializer.cc
 #undef private
 namespace ldso { namespace internal { float wM3G, hM3G; int wG[PYR_LEVELS], hG[PYR_LEVELS]; } }
 
@@ -993,6 +995,75 @@ static void pin_tracker() {
     CHECK(okTrack, "CoarseTracker::trackNewestCoarse: return value, pose, affine brightness, lastResiduals, lastFlowIndicators");
 }
 
+// ---- CoarseInitializer::makeK / calcResAndGS: the reference's src/frontend/CoarseInitializer.cc against oracle/initializer.cc
+static void pin_initializer() {
+    using namespace ldso; using namespace ldso::internal;
+    const int w = 640, h = 480, L = 4;
+    pyrLevelsUsed = L;
+    for (int l = 0; l < L; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+    auto tex = [](float x, float y) { return 120.f + 40.f * sinf(0.013f * x + 0.3f) * cosf(0.017f * y) + 25.f * sinf(0.045f * (x + 0.6f * y)) + 14.f * cosf(0.11f * x - 0.07f * y); };
+    std::vector<float> c0(w * h), c1(w * h);
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) { c0[y * w + x] = tex(x, y); c1[y * w + x] = 1.03f * tex(x - 1.7f, y + 0.9f) + 2.f; }
+    std::vector<std::vector<float>> p0(L), p1(L); float *q0[PYR_LEVELS] = {}, *q1[PYR_LEVELS] = {};
+    for (int l = 0; l < L; l++) { p0[l].assign(3 * (w >> l) * (h >> l), 0.f); p1[l].assign(3 * (w >> l) * (h >> l), 0.f); q0[l] = p0[l].data(); q1[l] = p1[l].data(); }
+    oracle::makeImages(c0.data(), w, h, L, q0); oracle::makeImages(c1.data(), w, h, L, q1);
+    auto HC = make_calib(520.f, 522.f, 318.3f, 241.1f);
+    auto f0 = make_fh(nullptr), f1 = make_fh(nullptr);
+    for (int l = 0; l < L; l++) { f0->dIp[l] = (Vec3f *) q0[l]; f1->dIp[l] = (Vec3f *) q1[l]; }
+    CoarseInitializer RI(w, h); oracle::CoarseInitializer OI(w, h, L);
+    RI.makeK(HC); OI.makeK(520.f, 522.f, 318.3f, 241.1f);
+    RI.firstFrame = f0; RI.newFrame = f1;
+    RI.alphaK = OI.alphaK; RI.alphaW = OI.alphaW; RI.couplingWeight = OI.couplingWeight; RI.regWeight = 0.8f;
+    bool okK = true;
+    for (int l = 0; l < L; l++) { okK &= RI.w[l] == OI.w[l] && RI.h[l] == OI.h[l] && memcmp(&RI.fx[l], &OI.fx[l], 8) == 0 && memcmp(&RI.cy[l], &OI.cy[l], 8) == 0;
+                                  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) okK &= memcmp(&RI.K[l](i, j), &OI.K[l][i * 3 + j], 8) == 0 && memcmp(&RI.Ki[l](i, j), &OI.Ki[l][i * 3 + j], 8) == 0; }
+    CHECK(okK, "CoarseInitializer::makeK (double K, Ki per level)");
+    bool okRes = true, okH = true, okPts = true, okJb = true; int nGood = 0, nBad = 0, nCapped = 0;
+    for (int l = 0; l < L; l++) {
+        OI.firstDIp[l] = q0[l]; OI.newDIp[l] = q1[l];
+        const int wl = w >> l, hl = h >> l, n = (l == 0) ? 3000 : 1200 >> l;
+        RI.points[l] = new Pnt[n]; RI.numPoints[l] = n; OI.points[l].assign(n, oracle::InitPnt());
+        for (int i = 0; i < n; i++) {
+            Pnt &a = RI.points[l][i]; oracle::InitPnt &b = OI.points[l][i];
+            a.u = b.u = (float) (int) frand(3.f, wl - 4.f); a.v = b.v = (float) (int) frand(3.f, hl - 4.f);
+            if (i % 37 == 5) { a.u = b.u = 2.f; }                                   // pattern touches the border test of the warped position
+            a.idepth = b.idepth = 1; a.idepth_new = b.idepth_new = frand(0.4f, 2.2f); a.iR = b.iR = frand(0.8f, 1.2f);
+            a.isGood = b.isGood = (i % 11 != 3);
+            a.energy = Vec2f(frand(0.f, 300.f), frand(0.f, 1.f)); b.energy[0] = a.energy[0]; b.energy[1] = a.energy[1];
+            a.energy_new = Vec2f(0, 0); a.isGood_new = false; a.lastHessian = a.lastHessian_new = 0; a.maxstep = 0;
+            a.outlierTH = b.outlierTH = (i % 13 == 7) ? 0.5f : 8 * 12 * 12.f; a.my_type = 1;
+        }
+    }
+    for (int trial = 0; trial < 6; trial++) {
+        Vec6 xi; double xia[6];
+        for (int i = 0; i < 6; i++) { xia[i] = (trial == 0) ? 0.0 : frand(-1.f, 1.f) * (i < 3 ? (trial >= 4 ? 0.3 : 0.01) : 0.003); xi[i] = xia[i]; }
+        const SE3 Tr = SE3::exp(xi); const oracle::SE3 To = oracle::SE3::exp(xia);
+        const AffLight aff(frand(-0.05f, 0.05f), frand(-3.f, 3.f));
+        for (int l = L - 1; l >= 0; l--) {
+            Mat88f H, Hsc; Vec8f b, bsc; float Ho[64], bo[8], Hsco[64], bsco[8], ro[3];
+            const Vec3f rr = RI.calcResAndGS(l, H, b, Hsc, bsc, Tr, aff, false);
+            OI.calcResAndGS(l, Ho, bo, Hsco, bsco, To, aff.a, aff.b, ro);
+            okRes &= memcmp(rr.d, ro, 12) == 0;
+            if (ro[1] == OI.alphaK * OI.points[l].size()) nCapped++;
+            for (int i = 0; i < 8; i++) { okH &= memcmp(&b[i], &bo[i], 4) == 0 && memcmp(&bsc[i], &bsco[i], 4) == 0;
+                                          for (int j = 0; j < 8; j++) okH &= memcmp(&H(i, j), &Ho[i * 8 + j], 4) == 0 && memcmp(&Hsc(i, j), &Hsco[i * 8 + j], 4) == 0; }
+            for (size_t i = 0; i < OI.points[l].size(); i++) {
+                const Pnt &a = RI.points[l][i]; const oracle::InitPnt &c = OI.points[l][i];
+                okPts &= a.isGood_new == c.isGood_new && memcmp(a.energy_new.d, c.energy_new, 8) == 0 && memcmp(&a.maxstep, &c.maxstep, 4) == 0 &&
+                         memcmp(&a.lastHessian_new, &c.lastHessian_new, 4) == 0;
+                if (a.isGood) okJb &= memcmp(RI.JbBuffer_new[i].d, OI.JbBuffer_new[i].data(), 40) == 0;
+                nGood += a.isGood_new; nBad += !a.isGood_new;
+            }
+        }
+    }
+    printf("  initializer pin: %d good / %d rejected point evaluations, alpha energy capped in %d of 24 calls\n", nGood, nBad, nCapped);
+    CHECK(nGood > 10000 && nBad > 2000 && nCapped > 0 && nCapped < 24, "initializer scenario: good and rejected points, both alpha branches");
+    CHECK(okRes, "CoarseInitializer::calcResAndGS return vector (E.A, alphaEnergy, E.num)");
+    CHECK(okH, "calcResAndGS H, b, H_sc, b_sc");
+    CHECK(okPts, "calcResAndGS per-point isGood_new, energy_new, maxstep, lastHessian_new");
+    CHECK(okJb, "calcResAndGS JbBuffer_new (10 floats per point)");
+}
+
 static void pin_settings() {
     using namespace ldso;
     oracle::Settings S; oracle::TraceSettings T;
@@ -1035,8 +1106,9 @@ int main() {
     pin_hessians();
     pin_backend();
     pin_tracker();
+    pin_initializer();
     pin_settings();
     if (fails) { printf("PIN FAILED: %d of %d checks\n", fails, checks); return 1; }
-    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc, EnergyFunctional.cc and CoarseTracker.cc\n", checks);
+    printf("PIN OK: %d checks against the reference's own MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h, Setting.cc, Residuals.cc, ImmaturePoint.cc, PointHessian.cc, FrameHessian.cc, FrameFramePrecalc.cc, AccumulatedTopHessian.cc, AccumulatedSCHessian.cc, EnergyFunctional.cc, CoarseTracker.cc and CoarseInitializer.cc\n", checks);
     return 0;
 }

@@ -341,14 +341,33 @@ template<typename T, int R, int K, int C> inline Matrix<T, R, C> operator*(const
     return o;
 }
 template<typename T, int N> inline Matrix<T, N, 1> LDLTOf<T, N>::solve(const Matrix<T, N, 1> &b) const {
-    static_assert(std::is_same<T, double>::value, "only double systems are solved");
-    Matrix<T, N, 1> x; ref_shim_ldlt_solve(N, A.d, b.d, x.d); return x;
+    // double systems go to the oracle's LDLT restatement; the float systems of CoarseInitializer::trackFrame are solved through it in
+    // double and rounded (nothing that is pinned depends on them)
+    double Ad[N * N], bd[N], xd[N];
+    for (int i = 0; i < N * N; i++) Ad[i] = (double) A.d[i];
+    for (int i = 0; i < N; i++) bd[i] = (double) b.d[i];
+    ref_shim_ldlt_solve(N, Ad, bd, xd);
+    Matrix<T, N, 1> x; for (int i = 0; i < N; i++) x.d[i] = (T) xd[i]; return x;
+}
+// Eigen::DiagonalMatrix<T, N> as CoarseInitializer uses it (wM: the SCALE_* weights)
+template<typename T, int N> struct DiagonalMatrix {
+    Matrix<T, N, 1> dg;
+    Matrix<T, N, 1> &diagonal() { return dg; }
+    const Matrix<T, N, 1> &diagonal() const { return dg; }
+    Matrix<T, N, N> toDenseMatrix() const { Matrix<T, N, N> m; m.setZero(); for (int i = 0; i < N; i++) m(i, i) = dg.d[i]; return m; }
+};
+template<typename T, int N, int C> inline Matrix<T, N, C> operator*(const DiagonalMatrix<T, N> &D, const Matrix<T, N, C> &M) {
+    Matrix<T, N, C> o; for (int c = 0; c < C; c++) for (int r = 0; r < N; r++) o(r, c) = D.dg.d[r] * M(r, c); return o;
+}
+template<typename T, int R, int N> inline Matrix<T, R, N> operator*(const Matrix<T, R, N> &M, const DiagonalMatrix<T, N> &D) {
+    Matrix<T, R, N> o; for (int c = 0; c < N; c++) for (int r = 0; r < R; r++) o(r, c) = M(r, c) * D.dg.d[c]; return o;
 }
 typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 4, 1> Vector4f;
 typedef Matrix<int, 2, 1> Vector2i;
+typedef Matrix<int, 3, 1> Vector3i;
 }  // namespace Eigen
 
 const int CPARS = 4;
@@ -385,6 +404,7 @@ typedef Eigen::Matrix<float, 8, 1> Vec8f;
 typedef Eigen::Matrix<float, CPARS, 1> VecCf;
 typedef Eigen::Matrix<float, MAX_RES_PER_POINT, 1> VecNRf;
 typedef Eigen::Matrix<float, 9, 1> Vec9f;
+typedef Eigen::Matrix<float, 10, 1> Vec10f;
 typedef Eigen::Matrix<float, 14, 1> Vec14f;
 typedef Eigen::Matrix<float, 9, 9> Mat99f;
 typedef Eigen::Matrix<float, 13, 13> Mat1313f;

@@ -304,7 +304,7 @@ def test_oracle_pinned_against_reference_sources():
     PointHessian.cc, CoarseTracker.cc (makeK, makeCoarseDepthL0, calcRes, calcGSSSE, trackNewestCoarse), ImmaturePoint.cc (constructor,
     traceOn, linearizeResidual), MatrixAccumulators.h, GlobalFuncs.h, ResidualProjections.h, AffLight.h and Setting.cc, compiled
     unmodified where they lie (against oracle/ref_shim: stand-ins for Eigen / Sophus / Frame.h / OpenCV / glog), agree bit for bit
-    with the oracle on 102 checks; the negative controls (an operand scaled by 1 + 2e-7, two results moved by one ulp on the oracle
+    with the oracle on 108 checks; the negative controls (an operand scaled by 1 + 2e-7, two results moved by one ulp on the oracle
     side) are detected."""
     import subprocess
     odir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
