@@ -311,6 +311,19 @@ int ldso_b200_select_activation(ldso_b200_ctx *ctx, int newest_frame, float curr
                                 const int32_t *lastTraceStatus, const float *lastTracePixelInterval, const float *quality,
                                 const float *my_type, const uint8_t *frame_flagged, uint8_t *action, float *dist_map);
 
+/* EXPERIMENTAL (written at the end of round 1 against the pinned oracle, compiled, not yet run on hardware):
+ * CoarseInitializer::calcResAndGS (src/frontend/CoarseInitializer.cc:181-405) for the n points of pyramid level lvl. Images: slot
+ * first_slot = firstFrame, new_slot = newFrame (upload_frame / make_images). (R, t) = refToNew, tlog3 = refToNew.log().head<3>(),
+ * (aff_a, aff_b) = refToNew_aff, (fx0 .. cy0) = Hcalib's level-0 intrinsics (makeK, :689-715). Per point in: Pnt::u, v, idepth_new, iR,
+ * isGood, energy (2 floats), outlierTH; out: isGood_new, energy_new (2), maxstep, lastHessian_new (accepted points), JbBuffer_new
+ * (10 floats; zero for points with isGood == 0). H64 / Hsc64 row-major 8x8, b8 / bsc8, res3 = the returned Vec3f. alphaK, alphaW,
+ * couplingWeight as trackFrame sets them (:44-47). Points must keep the pattern radius (2 px) + 1 from the image border. */
+int ldso_b200_init_calc_res(ldso_b200_ctx *ctx, int first_slot, int new_slot, int lvl, const double R[9], const double t[3], const double tlog3[3],
+                            float aff_a, float aff_b, float fx0, float fy0, float cx0, float cy0, int n, const float *u, const float *v,
+                            const float *idepth_new, const float *iR, const uint8_t *isGood, const float *energy2, const float *outlierTH,
+                            float alphaK, float alphaW, float couplingWeight, uint8_t *isGood_new, float *energy_new2, float *maxstep,
+                            float *lastHessian_new, float *JbBuffer_new10, float *H64, float *b8, float *Hsc64, float *bsc8, float *res3);
+
 /* ---- coarse tracker (src/frontend/CoarseTracker.cc) ---------------------------------------------------- */
 /* CoarseTracker::makeK (:219-246) */
 int ldso_b200_tracker_make_k(ldso_b200_ctx *ctx, float fx, float fy, float cx, float cy);

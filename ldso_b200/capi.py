@@ -68,7 +68,7 @@ SYMBOLS = [
     "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_kernel_times", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
-    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_select_activation", "ldso_b200_optimize_begin",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_select_activation", "ldso_b200_init_calc_res", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
@@ -466,6 +466,24 @@ class Context:
                                                      _i(host), _f(imin), _f(imax), _i(status), _f(itv), _f(q), _f(mt), _b(flagged), _b(action),
                                                      _f(dmap) if want_map else None))
         return (action, dmap) if want_map else action
+
+    def init_calc_res(self, first_slot, new_slot, lvl, R, t, tlog3, aff_a, aff_b, K4, u, v, idepth_new, iR, isGood, energy2, outlierTH,
+                      alphaK=2.5 * 2.5, alphaW=150.0 * 150.0, couplingWeight=1.0):
+        """EXPERIMENTAL: CoarseInitializer::calcResAndGS for the points of one pyramid level (see include/ldso_b200.h)."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        u, v, idn, iR, e2, oth = map(f32, (u, v, idepth_new, iR, energy2, outlierTH))
+        good = np.ascontiguousarray(isGood, np.uint8)
+        n = u.shape[0]
+        R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64); tl = np.ascontiguousarray(tlog3, np.float64)
+        out = dict(isGood_new=np.zeros(n, np.uint8), energy_new=np.zeros((n, 2), np.float32), maxstep=np.zeros(n, np.float32),
+                   lastHessian_new=np.zeros(n, np.float32), Jb=np.zeros((n, 10), np.float32), H=np.zeros((8, 8), np.float32), b=np.zeros(8, np.float32),
+                   Hsc=np.zeros((8, 8), np.float32), bsc=np.zeros(8, np.float32), res=np.zeros(3, np.float32))
+        self._chk(self.L.ldso_b200_init_calc_res(self.ctx, int(first_slot), int(new_slot), int(lvl), _d(R), _d(t), _d(tl), C.c_float(aff_a), C.c_float(aff_b),
+                                                 C.c_float(K4[0]), C.c_float(K4[1]), C.c_float(K4[2]), C.c_float(K4[3]), n, _f(u), _f(v), _f(idn), _f(iR),
+                                                 _b(good), _f(e2), _f(oth), C.c_float(alphaK), C.c_float(alphaW), C.c_float(couplingWeight),
+                                                 _b(out["isGood_new"]), _f(out["energy_new"]), _f(out["maxstep"]), _f(out["lastHessian_new"]), _f(out["Jb"]),
+                                                 _f(out["H"]), _f(out["b"]), _f(out["Hsc"]), _f(out["bsc"]), _f(out["res"])))
+        return out
 
     def tracker_make_k(self, fx, fy, cx, cy):
         self._chk(self.L.ldso_b200_tracker_make_k(self.ctx, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy)))

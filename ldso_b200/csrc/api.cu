@@ -1181,6 +1181,90 @@ extern "C" int ldso_b200_select_activation(ldso_b200_ctx *c, int newest_frame, f
     return LDSO_B200_OK;
 }
 
+// CoarseInitializer::calcResAndGS (src/frontend/CoarseInitializer.cc:181-405) for the points of one pyramid level. EXPERIMENTAL: written
+// at the end of round 1 against the pinned oracle (oracle/initializer.cc), compiled, NOT yet run on hardware (tests/test_gpu_init.py is
+// skipped unless LDSO_B200_RUN_UNVALIDATED is set).
+extern "C" int ldso_b200_init_calc_res(ldso_b200_ctx *c, int first_slot, int new_slot, int lvl, const double R[9], const double t[3], const double tlog3[3],
+                                       float aff_a, float aff_b, float fx0, float fy0, float cx0, float cy0, int n, const float *u, const float *v,
+                                       const float *idepth_new, const float *iR, const uint8_t *isGood, const float *energy2, const float *outlierTH,
+                                       float alphaK, float alphaW, float couplingWeight, uint8_t *isGood_new, float *energy_new2, float *maxstep,
+                                       float *lastHessian_new, float *JbBuffer_new10, float *H64, float *b8, float *Hsc64, float *bsc8, float *res3) {
+    if (!c || n <= 0 || !R || !t || !tlog3) return LDSO_B200_ERR_ARG;
+    if (lvl < 0 || lvl >= c->levels) return c->fail(LDSO_B200_ERR_ARG, "pyramid level out of range");
+    if (first_slot < 0 || first_slot >= NSLOTS || new_slot < 0 || new_slot >= NSLOTS || !c->img[first_slot][lvl] || !c->img[new_slot][lvl])
+        return c->fail(LDSO_B200_ERR_ARG, "image slot not uploaded");
+    if (!u || !v || !idepth_new || !iR || !isGood || !energy2 || !outlierTH || !isGood_new || !energy_new2 || !maxstep || !lastHessian_new ||
+        !JbBuffer_new10 || !H64 || !b8 || !Hsc64 || !bsc8 || !res3) return c->fail(LDSO_B200_ERR_ARG, "null array");
+    const int wl = c->w >> lvl, hl = c->h >> lvl;
+    for (int i = 0; i < n; i++)      // the reference samples the first frame at (u + dx, v + dy) without a bounds check (its selector keeps a margin)
+        if (!(u[i] >= 2 && v[i] >= 2 && u[i] < wl - 3 && v[i] < hl - 3)) return c->fail(LDSO_B200_ERR_ARG, "initializer point closer than the pattern radius to the image border");
+    cudaSetDevice(c->device);
+    // CoarseInitializer::makeK (:689-715) in double, K^-1 by Eigen's 3x3 cofactor formula
+    double fx = fx0, fy = fy0, cx = cx0, cy = cy0;
+    for (int level = 1; level <= lvl; ++level) { fx = fx * 0.5; fy = fy * 0.5; }
+    if (lvl > 0) { cx = ((double) cx0 + 0.5) / ((int) 1 << lvl) - 0.5; cy = ((double) cy0 + 0.5) / ((int) 1 << lvl) - 0.5; }
+    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    double Ki[9];
+    {
+        const double c00 = K[4] * K[8] - K[5] * K[7], c01 = K[5] * K[6] - K[3] * K[8], c02 = K[3] * K[7] - K[4] * K[6];
+        const double det = K[0] * c00 + K[1] * c01 + K[2] * c02, invdet = 1.0 / det;
+        Ki[0] = c00 * invdet; Ki[3] = c01 * invdet; Ki[6] = c02 * invdet;
+        Ki[1] = (K[2] * K[7] - K[1] * K[8]) * invdet; Ki[4] = (K[0] * K[8] - K[2] * K[6]) * invdet; Ki[7] = (K[1] * K[6] - K[0] * K[7]) * invdet;
+        Ki[2] = (K[1] * K[5] - K[2] * K[4]) * invdet; Ki[5] = (K[2] * K[3] - K[0] * K[5]) * invdet; Ki[8] = (K[0] * K[4] - K[1] * K[3]) * invdet;
+    }
+    InitArgs A;
+    A.n = n; A.w = wl; A.h = hl;
+    A.imgRef = c->img[first_slot][lvl]; A.imgNew = c->img[new_slot][lvl];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) { double s = R[i * 3] * Ki[j]; s += R[i * 3 + 1] * Ki[3 + j]; s += R[i * 3 + 2] * Ki[6 + j]; A.RKi[i * 3 + j] = (float) s; }
+        A.t[i] = (float) t[i];
+    }
+    A.aff0 = std::exp(aff_a); A.aff1 = aff_b;
+    A.fx = (float) fx; A.fy = (float) fy; A.cx = (float) cx; A.cy = (float) cy; A.huberTH = c->S.huberTH;
+    // alpha energy (:336-356): the reference's EAlpha accumulator never receives a term, so it depends on the translation only
+    const double tsq = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    float alphaEnergy = (float) ((double) alphaW * ((double) 0.0f + tsq * n));
+    float alphaOpt;
+    if (alphaEnergy > alphaK * n) { alphaOpt = 0; alphaEnergy = alphaK * n; } else alphaOpt = alphaW;
+    A.alphaOpt = alphaOpt; A.couplingWeight = couplingWeight;
+    const size_t N = (size_t) n, grid = (N + INIT_THREADS / 8 - 1) / (INIT_THREADS / 8);
+    const size_t words = N * (1 + 1 + 1 + 1 + 2 + 1) /*in*/ + N * (2 + 1 + 1 + 10) /*out*/ + grid * INIT_NACC + 4 + 2 * INIT_NACC + 8;
+    RET_IF(trace_reserve(c, 4 * words + 2 * N + 64));
+    float *q = (float *) c->trace_buf;
+    float *du = q; q += N; float *dv = q; q += N; float *did = q; q += N; float *dir = q; q += N; float *de2 = q; q += 2 * N; float *doth = q; q += N;
+    float *den = q; q += 2 * N; float *dms = q; q += N; float *dlh = q; q += N; float *djb = q; q += 10 * N;
+    float *dpart = q; q += grid * INIT_NACC; unsigned *dcnt = (unsigned *) q; q += 4;
+    q = (float *) (((uintptr_t) q + 7) & ~(uintptr_t) 7);
+    double *dout = (double *) q; q += 2 * INIT_NACC;
+    unsigned char *dg = (unsigned char *) q, *dgn = dg + N;
+#define IN_H2D(dst_, src_, bytes_) CUDA_CHECK_RET(c, cudaMemcpyAsync(dst_, src_, bytes_, cudaMemcpyHostToDevice, c->stream))
+    IN_H2D(du, u, 4 * N); IN_H2D(dv, v, 4 * N); IN_H2D(did, idepth_new, 4 * N); IN_H2D(dir, iR, 4 * N); IN_H2D(de2, energy2, 8 * N); IN_H2D(doth, outlierTH, 4 * N);
+    IN_H2D(dg, isGood, N);
+#undef IN_H2D
+    CUDA_CHECK_RET(c, cudaMemsetAsync(den, 0, 4 * (size_t) (2 + 1 + 1 + 10) * N, c->stream));      // energy_new, maxstep, lastHessian_new, Jb
+    CUDA_CHECK_RET(c, cudaMemsetAsync(dcnt, 0, 16, c->stream));
+    A.u = du; A.v = dv; A.idepth_new = did; A.iR = dir; A.energy2 = de2; A.outlierTH = doth; A.isGood = dg;
+    A.isGood_new = dgn; A.energy_new2 = den; A.maxstep = dms; A.lastHessian_new = dlh; A.Jb = djb;
+    A.partials = dpart; A.counter = dcnt; A.out = dout;
+    launch_init_calc_res(A, c->stream);
+    LAUNCH_CHECK(c);
+    double sums[INIT_NACC];
+    D2H(isGood_new, dgn, N); D2H(energy_new2, den, 8 * N); D2H(maxstep, dms, 4 * N); D2H(lastHessian_new, dlh, 4 * N); D2H(JbBuffer_new10, djb, 40 * N);
+    D2H(sums, dout, sizeof(sums));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // acc9.H / acc9SC.H -> H_out, b_out, H_out_sc, b_out_sc (:390-403)
+    int k = 0;
+    for (int r = 0; r < 9; r++)
+        for (int cc = r; cc < 9; cc++, k++) {
+            const float hv = (float) sums[k], sv = (float) sums[45 + k];
+            if (cc < 8) { H64[r * 8 + cc] = H64[cc * 8 + r] = hv; Hsc64[r * 8 + cc] = Hsc64[cc * 8 + r] = sv; }
+            else if (r < 8) { b8[r] = hv; bsc8[r] = sv; }
+        }
+    for (int i = 0; i < 3; i++) { H64[i * 8 + i] += alphaOpt * n; b8[i] += (float) tlog3[i] * alphaOpt * n; }
+    res3[0] = (float) sums[90]; res3[1] = alphaEnergy; res3[2] = (float) (2 * n);      // E.num counts both loops (:211-303 and :339-347)
+    return LDSO_B200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- fused loop
 static const int K1_FUSED = K1F_LINEARIZE | K1F_ACCUMULATE | K1F_APPLY_RES;
 

@@ -21,3 +21,7 @@ void launch_activation_select(const ActSelArgs &A, cudaStream_t stream) {
     if (smem > configured) { cudaFuncSetAttribute(k_activation_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); configured = smem; }
     k_activation_select<<<1, ACTSEL_THREADS, smem, stream>>>(A);
 }
+void launch_init_calc_res(const InitArgs &A, cudaStream_t stream) {
+    const int grid = (A.n + INIT_THREADS / 8 - 1) / (INIT_THREADS / 8);
+    k_init_calc_res<<<grid, INIT_THREADS, 0, stream>>>(A);
+}

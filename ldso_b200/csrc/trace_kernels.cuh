@@ -596,3 +596,166 @@ __global__ void __launch_bounds__(ACTSEL_THREADS, 1) k_activation_select(ActSelA
     if (tid == 0 && A.dbg) A.dbg[3] = clock64();
     if (A.use_smem) for (int i = tid; i < A.map_bytes / 4; i += ACTSEL_THREADS) ((unsigned *) A.map)[i] = ((unsigned *) map)[i];
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// CoarseInitializer::calcResAndGS (src/frontend/CoarseInitializer.cc:181-405): 8 lanes per point (lane = pattern pixel), 4 points
+// per warp. The reference walks the pattern in order and leaves at the first pixel that projects outside or samples a non-finite
+// value; here every lane evaluates its pixel, the group finds the first failing index and the ordered sums (energy, the ten
+// JbBuffer entries) are folded in pattern order up to it, so the per-point outputs — including the partial JbBuffer / maxstep of
+// a rejected point — are the reference's bit for bit. The 45 + 45 Hessian entries and the energy are summed across points by
+// warp shuffles, per-CTA partials and a last-CTA fold (their order differs from the reference's SSE lanes: compared to tolerance).
+__device__ __forceinline__ float init_tap1(const float4 *img, int w, float x, float y) {        // getInterpolatedElement31
+    const int ix = (int) x, iy = (int) y;
+    const float dx = x - ix, dy = y - iy, dxdy = dx * dy;
+    const float4 *bp = img + ix + iy * w;
+    return dxdy * bp[1 + w].x + (dy - dxdy) * bp[w].x + (dx - dxdy) * bp[1].x + (1 - dx - dy + dxdy) * bp[0].x;
+}
+
+__global__ void __launch_bounds__(INIT_THREADS) k_init_calc_res(InitArgs A) {
+    __shared__ float s_part[(INIT_THREADS / 32) * INIT_NACC];
+    __shared__ double s_sum[INIT_NACC];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, idx = threadIdx.x & 7, gbase = lane & ~7;
+    const int p = blockIdx.x * (INIT_THREADS / 8) + (threadIdx.x >> 3);
+    const bool valid = p < A.n;
+    float acc[INIT_NACC];
+#pragma unroll
+    for (int k = 0; k < INIT_NACC; k++) acc[k] = 0.f;
+
+    const float pu = valid ? A.u[p] : 0.f, pv = valid ? A.v[p] : 0.f, idn = valid ? A.idepth_new[p] : 1.f;
+    const bool goodOld = valid && A.isGood[p] != 0;
+    // this lane's pattern pixel (:235-291)
+    bool bad = true;
+    float J[9], dd = 0.f, eterm = 0.f, ms = 1e10f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) J[k] = 0.f;
+    if (goodOld) {
+        const int dx = c_trace_pattern[idx][0], dy = c_trace_pattern[idx][1];
+        const float px = pu + dx, py = pv + dy;
+        float pt0 = A.RKi[0] * px; pt0 += A.RKi[1] * py; pt0 += A.RKi[2] * 1.0f; pt0 = pt0 + A.t[0] * idn;
+        float pt1 = A.RKi[3] * px; pt1 += A.RKi[4] * py; pt1 += A.RKi[5] * 1.0f; pt1 = pt1 + A.t[1] * idn;
+        float pt2 = A.RKi[6] * px; pt2 += A.RKi[7] * py; pt2 += A.RKi[8] * 1.0f; pt2 = pt2 + A.t[2] * idn;
+        const float u = pt0 / pt2, v = pt1 / pt2;
+        const float Ku = A.fx * u + A.cx, Kv = A.fy * v + A.cy;
+        const float new_idepth = idn / pt2;
+        if (Ku > 1 && Kv > 1 && Ku < A.w - 2 && Kv < A.h - 2 && new_idepth > 0) {
+            const float3 hit = trace_tap3(A.imgNew, A.w, A.h, Ku, Kv);
+            const float rlR = init_tap1(A.imgRef, A.w, px, py);
+            if (isfinite(rlR) && isfinite(hit.x)) {
+                bad = false;
+                const float residual = hit.x - A.aff0 * rlR - A.aff1;
+                float hw = fabsf(residual) < A.huberTH ? 1.f : A.huberTH / fabsf(residual);
+                eterm = hw * residual * residual * (2 - hw);
+                const float dxdd = (A.t[0] - A.t[2] * u) / pt2;
+                const float dydd = (A.t[1] - A.t[2] * v) / pt2;
+                if (hw < 1) hw = sqrtf(hw);
+                const float dxInterp = hw * hit.y * A.fx;
+                const float dyInterp = hw * hit.z * A.fy;
+                J[0] = new_idepth * dxInterp;
+                J[1] = new_idepth * dyInterp;
+                J[2] = -new_idepth * (u * dxInterp + v * dyInterp);
+                J[3] = -u * v * dxInterp - (1 + v * v) * dyInterp;
+                J[4] = (1 + u * u) * dxInterp + u * v * dyInterp;
+                J[5] = -v * dxInterp + u * dyInterp;
+                J[6] = -hw * A.aff0 * rlR;
+                J[7] = -hw * 1;
+                dd = dxInterp * dxdd + dyInterp * dydd;
+                J[8] = hw * residual;
+                const float a = dxdd * A.fx, b = dydd * A.fy;
+                ms = 1.0f / sqrtf(a * a + b * b);
+            }
+        }
+    }
+    // first failing pattern index of the group; sums in pattern order up to it
+    const unsigned badmask = (__ballot_sync(0xffffffffu, bad) >> gbase) & 0xffu;
+    const int firstBad = badmask ? (__ffs(badmask) - 1) : 8;
+    float energy = 0.f, Jb[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) Jb[k] = 0.f;
+    float prod[10];
+#pragma unroll
+    for (int k = 0; k < 8; k++) prod[k] = J[k] * dd;
+    prod[8] = J[8] * dd; prod[9] = dd * dd;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float ei = __shfl_sync(0xffffffffu, eterm, gbase + i);
+        if (i < firstBad) energy += ei;
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const float pk = __shfl_sync(0xffffffffu, prod[k], gbase + i);
+            if (i < firstBad) Jb[k] += pk;
+        }
+    }
+    float msg = (idx < firstBad) ? ms : 1e10f;      // point->maxstep: the minimum over the pixels visited (NaN never wins a `<`)
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { const float other = __shfl_xor_sync(0xffffffffu, msg, o); if (other < msg) msg = other; }
+
+    const float e0 = valid ? A.energy2[2 * p] : 0.f, e1 = valid ? A.energy2[2 * p + 1] : 0.f;
+    const bool accepted = goodOld && firstBad == 8 && !(energy > (valid ? A.outlierTH[p] : 0.f) * 20);
+    if (accepted) {      // acc9.updateSSE / updateSingle (:309-329): this lane's residual
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++)
+#pragma unroll
+            for (int c = r; c < 9; c++) acc[k++] += J[r] * J[c];
+    }
+    if (valid && idx == 0) {
+        acc[90] += accepted ? energy : e0;                       // E.updateSingle (:211, :296, :303)
+        A.isGood_new[p] = accepted ? 1 : 0;
+        A.maxstep[p] = goodOld ? msg : 1e10f;
+        if (!accepted) { A.energy_new2[2 * p] = e0; A.energy_new2[2 * p + 1] = e1; }
+        if (goodOld && !accepted) for (int k = 0; k < 10; k++) A.Jb[10 * p + k] = Jb[k];
+        if (accepted) {      // :344, :365-388
+            A.energy_new2[2 * p] = energy;
+            A.energy_new2[2 * p + 1] = (idn - 1) * (idn - 1);
+            A.lastHessian_new[p] = Jb[9];
+            Jb[8] += A.alphaOpt * (idn - 1);
+            Jb[9] += A.alphaOpt;
+            if (A.alphaOpt == 0) {
+                Jb[8] += A.couplingWeight * (idn - A.iR[p]);
+                Jb[9] += A.couplingWeight;
+            }
+            Jb[9] = 1 / (1 + Jb[9]);
+            for (int k = 0; k < 10; k++) A.Jb[10 * p + k] = Jb[k];
+            // acc9SC.updateSingleWeighted(Jb[0..8], w = Jb[9]) (MatrixAccumulators.h:1489-1604)
+            float Jw[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Jw[k] = Jb[k];
+            const float wgt = Jb[9];
+            int k = 45;
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                acc[k++] += Jw[r] * Jw[r] * wgt;
+                if (r < 8) Jw[r] *= wgt;
+#pragma unroll
+                for (int c = r + 1; c < 9; c++) acc[k++] += Jw[c] * Jw[r];
+            }
+        }
+    }
+    // block sum -> per-CTA partial -> the last CTA folds all partials in CTA order
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < INIT_NACC; k++) {
+        float vsum = acc[k];
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        if (lane == 0) s_part[warp * INIT_NACC + k] = vsum;
+    }
+    __syncthreads();
+    if (threadIdx.x < INIT_NACC) {
+        double s = 0.0;
+        for (int w8 = 0; w8 < INIT_THREADS / 32; w8++) s += (double) s_part[w8 * INIT_NACC + threadIdx.x];
+        A.partials[blockIdx.x * INIT_NACC + threadIdx.x] = (float) s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(A.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x < INIT_NACC) {
+        double s = 0.0;
+        for (unsigned bI = 0; bI < gridDim.x; bI++) s += (double) ((volatile float *) A.partials)[bI * INIT_NACC + threadIdx.x];
+        s_sum[threadIdx.x] = s;
+        A.out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *A.counter = 0;
+}

@@ -51,3 +51,18 @@ struct ActSelArgs {
 #define ACTSEL_LOCAL_CAP 512                   // one seed improves at most 8k cells at step k <= 39
 size_t actsel_smem_bytes(const ActSelArgs &A);
 void launch_activation_select(const ActSelArgs &A, cudaStream_t stream);
+
+// CoarseInitializer::calcResAndGS (src/frontend/CoarseInitializer.cc:181-405) for the points of one pyramid level
+#define INIT_NACC 91            // 45 entries of acc9.H (upper triangle, row by row), 45 of acc9SC.H, the energy sum
+#define INIT_THREADS 256        // 8 lanes (= pattern pixels) per point, 32 points per CTA
+struct InitArgs {
+    int n, w, h;
+    const float4 *imgRef, *imgNew;            // firstFrame->dIp[lvl], newFrame->dIp[lvl] as (I, dx, dy, 0)
+    float RKi[9], t[3], aff0, aff1;           // (R * Ki).cast<float>(), t.cast<float>(), exp(a), b
+    float fx, fy, cx, cy, huberTH;
+    const float *u, *v, *idepth_new, *iR, *energy2, *outlierTH; const unsigned char *isGood;
+    float alphaOpt, couplingWeight;
+    unsigned char *isGood_new; float *energy_new2, *maxstep, *lastHessian_new, *Jb;      // per point out (Jb: n*10)
+    float *partials; unsigned *counter; double *out;                                      // [grid][INIT_NACC], 1, [INIT_NACC]
+};
+void launch_init_calc_res(const InitArgs &A, cudaStream_t stream);

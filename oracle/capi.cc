@@ -4,6 +4,7 @@
 #include "ba.h"
 #include "tracker.h"
 #include "trace.h"
+#include "initializer.h"
 #include <chrono>
 
 using namespace oracle;
@@ -438,6 +439,33 @@ void oracle_ba_select_activation(void *o, int levels, int newest, float currentM
         selectActivation(M, &R[9 * host[i]], &T[3 * host[i]], flagged[host[i]] != 0, currentMinActDist, minTraceQuality, 1, &c, action + i);
     }
     if (dist_map) memcpy(dist_map, M.fwdWarpedIDDistFinal.data(), sizeof(float) * (size_t) M.w[1] * M.h[1]);
+}
+
+// CoarseInitializer::calcResAndGS for the n points of pyramid level `lvl` (firstDIp / newDIp: `levels` pointers to (I, dx, dy) AoS images).
+// Per-point outputs like the reference's Pnt fields / JbBuffer_new; H, b, Hsc, bsc row-major 8x8 / 8; res3 = (E.A, alphaEnergy, E.num).
+void oracle_init_calc_res(int w, int h, int levels, const double K4[4], const float **firstDIp, const float **newDIp, int lvl, const double R[9],
+                          const double t[3], float aff_a, float aff_b, int n, const float *u, const float *v, const float *idepth_new, const float *iR,
+                          const unsigned char *isGood, const float *energy2, const float *outlierTH, float alphaK, float alphaW, float couplingWeight,
+                          unsigned char *isGood_new, float *energy_new2, float *maxstep, float *lastHessian_new, float *Jb10, float *H64, float *b8,
+                          float *Hsc64, float *bsc8, float *res3) {
+    CoarseInitializer I(w, h, levels);
+    I.makeK((float) K4[0], (float) K4[1], (float) K4[2], (float) K4[3]);
+    for (int l = 0; l < levels; l++) { I.firstDIp[l] = firstDIp[l]; I.newDIp[l] = newDIp[l]; }
+    I.alphaK = alphaK; I.alphaW = alphaW; I.couplingWeight = couplingWeight;
+    I.points[lvl].assign(n, InitPnt());
+    for (int i = 0; i < n; i++) {
+        InitPnt &p = I.points[lvl][i];
+        p.u = u[i]; p.v = v[i]; p.idepth_new = idepth_new[i]; p.iR = iR[i]; p.isGood = isGood[i] != 0;
+        p.energy[0] = energy2[2 * i]; p.energy[1] = energy2[2 * i + 1]; p.outlierTH = outlierTH[i];
+    }
+    SE3 P = SE3::fromRt(R, t);
+    I.calcResAndGS(lvl, H64, b8, Hsc64, bsc8, P, aff_a, aff_b, res3);
+    for (int i = 0; i < n; i++) {
+        const InitPnt &p = I.points[lvl][i];
+        isGood_new[i] = p.isGood_new ? 1 : 0; energy_new2[2 * i] = p.energy_new[0]; energy_new2[2 * i + 1] = p.energy_new[1];
+        maxstep[i] = p.maxstep; lastHessian_new[i] = p.lastHessian_new;
+        for (int k = 0; k < 10; k++) Jb10[10 * i + k] = I.JbBuffer_new[i][k];
+    }
 }
 
 }  // extern "C"

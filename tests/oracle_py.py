@@ -423,3 +423,35 @@ class OracleTrace:
                                _f(self.energyTH), c.host.ctypes.data_as(c_ip), _f(KRKi), _f(Kt), _f(aff), _f(self.idepth_min),
                                _f(self.idepth_max), _f(self.quality), self.status.ctypes.data_as(c_ip), _f(self.uv), _f(self.interval))
         return self.status.copy()
+
+
+def se3_log(R, t, fast=False):
+    """Sophus SE3::log of (R, t): (upsilon[3], omega[3])."""
+    L = lib(fast)
+    R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64)
+    a = np.zeros(6, np.float64)
+    L.oracle_se3_log(_d(R), _d(t), _d(a))
+    return a
+
+
+def init_calc_res(pair, lvl, R, t, aff_a, aff_b, u, v, idepth_new, iR, isGood, energy2, outlierTH, alphaK=2.5 * 2.5, alphaW=150.0 * 150.0,
+                  couplingWeight=1.0, fast=False):
+    """CoarseInitializer::calcResAndGS (oracle/initializer.cc) on the pyramids of a synth.make_track_pair() case: first frame = ref, new = new."""
+    L = lib(fast)
+    ref = [np.ascontiguousarray(p, np.float32) for p in pair.ref_pyr]
+    new = [np.ascontiguousarray(p, np.float32) for p in pair.new_pyr]
+    ra = (c_fp * pair.levels)(*[_f(p) for p in ref]); na = (c_fp * pair.levels)(*[_f(p) for p in new])
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    u, v, idn, iR, e2, oth = map(f32, (u, v, idepth_new, iR, energy2, outlierTH))
+    good = np.ascontiguousarray(isGood, np.uint8)
+    n = u.shape[0]
+    K = np.ascontiguousarray(pair.K, np.float64); R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64)
+    out = dict(isGood_new=np.zeros(n, np.uint8), energy_new=np.zeros((n, 2), np.float32), maxstep=np.zeros(n, np.float32),
+               lastHessian_new=np.zeros(n, np.float32), Jb=np.zeros((n, 10), np.float32), H=np.zeros((8, 8), np.float32), b=np.zeros(8, np.float32),
+               Hsc=np.zeros((8, 8), np.float32), bsc=np.zeros(8, np.float32), res=np.zeros(3, np.float32))
+    ub = C.POINTER(C.c_ubyte)
+    L.oracle_init_calc_res(pair.w, pair.h, pair.levels, _d(K), ra, na, int(lvl), _d(R), _d(t), C.c_float(aff_a), C.c_float(aff_b), n, _f(u), _f(v), _f(idn),
+                           _f(iR), good.ctypes.data_as(ub), _f(e2), _f(oth), C.c_float(alphaK), C.c_float(alphaW), C.c_float(couplingWeight),
+                           out["isGood_new"].ctypes.data_as(ub), _f(out["energy_new"]), _f(out["maxstep"]), _f(out["lastHessian_new"]), _f(out["Jb"]),
+                           _f(out["H"]), _f(out["b"]), _f(out["Hsc"]), _f(out["bsc"]), _f(out["res"]))
+    return out
