@@ -41,6 +41,7 @@ struct ldso_b200_ctx {
     // window
     DevWindow d;
     std::vector<void *> win_allocs;
+    std::vector<void *> derived_allocs;      // work items, partials, reduced buffer: rebuilt by build_derived
     bool have_window = false, have_frames = false, derived_dirty = true;
     std::vector<unsigned char> h_scratch_bytes;     // select_activation's map read-back
     unsigned char *actsel_pin = nullptr; size_t actsel_pin_cap = 0;      // its pinned staging block
@@ -237,9 +238,17 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     return c;
 }
 
+static void free_derived(ldso_b200_ctx *c) {
+    for (void *p : c->derived_allocs) cudaFree(p);
+    c->derived_allocs.clear();
+    c->d.items = nullptr; c->d.host_item_begin = nullptr; c->d.res_newest_slot = nullptr;
+    c->d.partials = nullptr; c->d.item_stats = nullptr; c->d.red = nullptr; c->d.dbg = nullptr;
+}
+
 static void free_window(ldso_b200_ctx *c) {
     for (void *p : c->win_allocs) cudaFree(p);
     c->win_allocs.clear();
+    free_derived(c);
     if (c->arena_dev) { cudaFree(c->arena_dev); c->arena_dev = nullptr; }
     if (c->arena_host) { cudaFreeHost(c->arena_host); c->arena_host = nullptr; }
     { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
@@ -374,10 +383,10 @@ extern "C" int ldso_b200_download_frame_level(ldso_b200_ctx *c, int slot, int lv
 
 // ---------------------------------------------------------------------------------------------- window
 template<typename T>
-static int dev_alloc(ldso_b200_ctx *c, T **p, size_t count) {
+static int dev_alloc(ldso_b200_ctx *c, T **p, size_t count, std::vector<void *> *owner = nullptr) {
     void *q = nullptr;
     CUDA_CHECK_RET(c, cudaMalloc(&q, sizeof(T) * std::max<size_t>(count, 128)));   // empty windows still get valid buffers
-    c->win_allocs.push_back(q);
+    (owner ? *owner : c->win_allocs).push_back(q);
     *p = (T *) q;
     return 0;
 }
@@ -554,11 +563,14 @@ static int build_derived(ldso_b200_ctx *c) {
 
     int4 *items_dev; int *hib_dev, *slot_dev;
     int rc = 0;
-    rc |= dev_alloc(c, &items_dev, items.size()); rc |= dev_alloc(c, &hib_dev, MAXF + 1); rc |= dev_alloc(c, &slot_dev, nR);
-    rc |= dev_alloc(c, &d.partials, (size_t) std::max(d.nItems, 1) * PART_STRIDE);
-    rc |= dev_alloc(c, &d.item_stats, (size_t) std::max(d.nItems, 1) * 4);
-    rc |= dev_alloc(c, &d.red, (size_t) RED_SELECT + std::max(d.newest_total, 1) + 16);
-    rc |= dev_alloc(c, &d.dbg, 32 + 3 * (size_t) std::max(d.nItems, 1));
+    // the previous derived buffers (same window, other nF / shard description) may still be read by queued kernels
+    if (!c->derived_allocs.empty()) { CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream)); free_derived(c); }
+    std::vector<void *> *own = &c->derived_allocs;
+    rc |= dev_alloc(c, &items_dev, items.size(), own); rc |= dev_alloc(c, &hib_dev, MAXF + 1, own); rc |= dev_alloc(c, &slot_dev, nR, own);
+    rc |= dev_alloc(c, &d.partials, (size_t) std::max(d.nItems, 1) * PART_STRIDE, own);
+    rc |= dev_alloc(c, &d.item_stats, (size_t) std::max(d.nItems, 1) * 4, own);
+    rc |= dev_alloc(c, &d.red, (size_t) RED_SELECT + std::max(d.newest_total, 1) + 16, own);
+    rc |= dev_alloc(c, &d.dbg, 32 + 3 * (size_t) std::max(d.nItems, 1), own);
     if (rc) return LDSO_B200_ERR_CUDA;
     rc |= dev_upload(c, items_dev, items.data(), items.size());
     rc |= dev_upload(c, hib_dev, hib.data(), MAXF + 1);
@@ -1405,11 +1417,14 @@ extern "C" int ldso_b200_peer_export(ldso_b200_ctx *c, void *ipc_handle_64) {
     if (c->peers_connected || c->peer_local) return c->fail(LDSO_B200_ERR_STATE, "peer exchange already set up for this context");
     const size_t bytes = sizeof(uint4) * 2 * K2R_MAX_PEERS * (size_t) n;      // the inbox: [2 parities][8 senders][n] 16-byte slots
     CUDA_CHECK_RET(c, cudaMalloc(&c->peer_local, bytes));
-    CUDA_CHECK_RET(c, cudaMemset(c->peer_local, 0, bytes));
     CUDA_CHECK_RET(c, cudaMalloc(&c->peer_words, sizeof(int) * 4));
-    CUDA_CHECK_RET(c, cudaMemset(c->peer_words, 0, sizeof(int) * 4));
     CUDA_CHECK_RET(c, cudaMalloc(&c->red_sum, sizeof(double) * ((size_t) n + 16)));
-    CUDA_CHECK_RET(c, cudaMemset(c->red_sum, 0, sizeof(double) * ((size_t) n + 16)));
+    // cleared on the context's own (non-blocking) stream and completed before the handle is handed out: a peer's first push
+    // and this rank's first exchange kernel must find zeroed tags
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->peer_local, 0, bytes, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->peer_words, 0, sizeof(int) * 4, c->stream));
+    CUDA_CHECK_RET(c, cudaMemsetAsync(c->red_sum, 0, sizeof(double) * ((size_t) n + 16), c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     memset(&c->px, 0, sizeof(c->px));
     c->px.n_doubles = n; c->px.n_chunks = nch;
     cudaIpcMemHandle_t h;

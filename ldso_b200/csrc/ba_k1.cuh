@@ -81,16 +81,15 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = (flags >> K1F_MODE_SHIFT) & 3;
 
+#ifdef LDSO_B200_PROFILE
     int dbgi = 0;
+    long long k1_t0 = clock64();
+    unsigned long long k1_gt0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(k1_gt0));
 #define K1_STAMP() do { if (tid == 0 && blockIdx.x == 0) d.dbg[dbgi] = clock64(); dbgi++; } while (0)
-    K1_STAMP();
-    if (tid == 0) {          // per-CTA wall-clock span (development aid, 3 stores per CTA)
-        unsigned long long gt; unsigned smid;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        d.dbg[32 + 3 * blockIdx.x] = (long long) gt;
-        d.dbg[32 + 3 * blockIdx.x + 2] = smid;
-    }
+#else
+#define K1_STAMP() do { } while (0)
+#endif
     // ---------------- phase 0a (before pdl_wait: iteration-constant data only): clear records, request the point scalars
     // and the first round of residual records
     pdl_launch_dependents();
@@ -132,6 +131,16 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
     if (nres > 0) K1_PREFETCH_RES_TOPO(0);
     // ---------------- phase 0b: everything the solver kernel produced (pair records, xAd, calibration, thresholds)
     pdl_wait();
+#ifdef LDSO_B200_PROFILE
+    if (tid == 0) {          // per-CTA wall-clock span (3 stores per CTA; after pdl_wait: no global writes before it)
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        d.dbg[32 + 3 * blockIdx.x] = (long long) k1_gt0;
+        d.dbg[32 + 3 * blockIdx.x + 2] = smid;
+        if (blockIdx.x == 0) d.dbg[dbgi] = k1_t0;
+    }
+    dbgi++;
+#endif
     if (tid < npts) {        // point state written by the previous iteration's K1
         const int p = p0 + tid;
         pf_idepth = d.pt_idepth[p]; pf_idz = d.pt_idepth_zero[p];
@@ -635,9 +644,11 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         else if (tid < 84) part[PART_BC + (tid - 80)] = accX;
     }
     K1_STAMP();   // 7: phase C done
+#ifdef LDSO_B200_PROFILE
     if (tid == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         d.dbg[32 + 3 * blockIdx.x + 1] = (long long) gt;
     }
+#endif
 }

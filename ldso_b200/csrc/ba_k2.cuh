@@ -11,10 +11,12 @@
 //  AccumulatedTopHessian.cc:215-219, AccumulatedSCHessian.cc:78-83,101-105).
 // The last block folds the per-item scalar statistics.
 __device__ __forceinline__ void dbg_span(long long *slot_min_max, bool end) {
+#ifdef LDSO_B200_PROFILE
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     if (!end) atomicMin((unsigned long long *) slot_min_max, gt);
     else atomicMax((unsigned long long *) (slot_min_max + 1), gt);
+#endif
 }
 #define K2A_THREADS 512
 #define K2A_SLICES (K2A_THREADS / 64)     // 8 threads share one output element, each folds every 8th work item
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         // the marginalisation-prior element this thread will add in the epilogue: issue the load now
         double hm_pre = 0.0;
         if (do_assemble && tid < 64) hm_pre = sb.HM[(size_t) (CPARS + 8 * b + (tid & 7)) * n + CPARS + 8 * a + (tid >> 3)];
-        if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();
+        PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[8] = clock64();)
         // -------- stage
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {      // adjoints: constant for the window, staged before pdl_wait
             const int q = o >> 6, e = o & 63, m = K2B_M(q, e >> 3, e & 7);
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             }
         }
         __syncthreads();
-        if (blockIdx.x == 0 && tid == 0) d.dbg[9] = clock64();
+        PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[9] = clock64();)
         // -------- stage A: left products. Every thread runs short (8-term) chains only; sums over frames are kept as
         // independent partial chains and folded in a fixed order.
         for (int o = tid; o < nF * 64; o += K2B_THREADS) {         // Z_i = AT_ia * D_i[a,b]
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             (which ? sY3 : sY2)[K2B_M(0, e >> 3, e & 7)] = s;
         }
         __syncthreads();
-        if (blockIdx.x == 0 && tid == 0) d.dbg[10] = clock64();
+        PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[10] = clock64();)
         // -------- stage B: right products, K2B_NSLOT slots of 64 threads split the term lists
         {
             const int slot = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
                 if (row == col) sb.dg[row] = a0;
             }
         }
-        if (blockIdx.x == 0 && tid == 0) d.dbg[11] = clock64();
+        PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[11] = clock64();)
         { if (tid == 0) dbg_span(&ws->dbg[18], true); return; }
     }
     if ((int) blockIdx.x < nBlocks + nF) {
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     }
     if (!do_select) return;
     {
-        if (tid == 0) d.dbg[12] = clock64();
+        PROF_ONLY(if (tid == 0) d.dbg[12] = clock64();)
         const int N = d.newest_total;
         // settings (constant): requested now, consumed after the passes
         const float set_thn = ws->S.frameEnergyTHN, set_fac = ws->S.frameEnergyTHFacMedian, set_cw = ws->S.frameEnergyTHConstWeight,
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             th = th * th;
             th *= set_ow * set_ow;
         }
-        if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; d.dbg[13] = clock64(); }
+        if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; PROF_ONLY(d.dbg[13] = clock64();) }
     }
     if (tid == 0) dbg_span(&ws->dbg[18], true);
 }

@@ -175,71 +175,76 @@ __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
     stage_out(&S, ws);
 }
 
-// Factor the 8x8 diagonal block at (k0,k0) in place (lower): L below the diagonal (unit), D on it. The matrix is
-// padded to whole blocks, so there is no partial-block predicate anywhere on this serial path.
-// Executed by ONE WARP: lane j < 8 keeps row j of the block in registers; a step is one broadcast of the pivot,
-// one reciprocal, and 7-k shuffles of the unscaled column. (L = W * (1/d): <= 1 ulp from Eigen's W / d.)
+// ---------------------------------------------------------------------------------------------------------------------
+// The 68x68 solve. Everything below is one serial dependency chain on a tiny matrix, so the design goal is the LENGTH OF
+// THE CHAIN, not throughput:
+//   * LDL^T's inherent chain is one reciprocal + one FMA per pivot. The factorisation is blocked by 8 columns; inside a
+//     block step every row thread factors the 8x8 diagonal block REDUNDANTLY in its own registers (SIMT: the redundant
+//     arithmetic costs no extra issue slots) and substitutes its own row on the fly, so a block step has no shuffle, no
+//     shared-memory exchange and no barrier on the pivot chain: 8 x (rcp + FMA) back to back;
+//   * all trailing products are formed BEFORE the reciprocal they are scaled by is known (tmp = W_r * W_s, then one FMA with
+//     1/d), and the reciprocal is a MUFU seed + one cubically convergent Newton step (3 dependent FMAs, ~1 ulp);
+//   * the update of the NEXT panel's 8 columns is spread over all threads (one element each) between two barriers, the rest of
+//     the trailing update is done by the helper warps while the row threads already factor the next panel;
+//   * the right-hand side rides along as matrix row npad, so the forward substitution is free; the backward substitution is done
+//     by ONE warp with the vector in registers (no barriers), 8 unknowns per step solved redundantly per lane.
+// Eigen's LDLT pivots on the largest remaining |diagonal| of the INPUT matrix (its left-looking update never touches later
+// diagonal entries before they are chosen), i.e. a descending-|diag| order: computed by a rank sort and applied as a symmetric
+// permutation before the (then unpivoted) blocked factorisation; like Eigen, only the lower triangle of the input is referenced.
+
+// ~1 ulp reciprocal: MUFU.RCP64H seed (>= 20 bits) and y = y0 (1 + e + e^2), e = 1 - d y0 (error ~ e^3 < 2^-60)
+__device__ __forceinline__ double k3_rcp(double d) {
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
+    const double e = fma(-d, y0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y0, t, y0);
+}
 __device__ __forceinline__ double shfl_f64(double v, int src) {      // low word first: lands in an aligned register pair
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_sync(0xffffffffu, lo, src);
     hi = __shfl_sync(0xffffffffu, hi, src);
     return __hiloint2double(hi, lo);
 }
-__device__ __forceinline__ void ldlt_diag_block_warp(double *A, double *vinv, int k0, int lane) {
-    double a[K3_NB];
-    const int row = lane & 7;
-#pragma unroll
-    for (int c = 0; c < K3_NB; c++) a[c] = A[(k0 + row) * K3_LD + k0 + c];
-#pragma unroll
-    for (int k = 0; k < K3_NB; k++) {
-        const double w = a[k];                      // unscaled column entry of this lane's row (rows >= k)
-        // all exchanges of this step are issued before the reciprocal: only rcp -> mul -> fma stays on the chain
-        const double dk = shfl_f64(w, k);
-        double wj[K3_NB];
-#pragma unroll
-        for (int j = k + 1; j < K3_NB; j++) wj[j] = shfl_f64(w, j);
-        const bool valid = fabs(dk) > 0.0;
-        const double inv = valid ? __drcp_rn(dk) : 1.0;
-        const double l = w * inv;
-        // unconditional: for row < j this touches only the (never read, never stored) upper part of the lane's row
-#pragma unroll
-        for (int j = k + 1; j < K3_NB; j++) a[j] -= l * wj[j];
-        if (row > k) a[k] = l;
-        if (lane == 0) vinv[k0 + k] = inv;
-    }
-    if (lane < K3_NB) {
-#pragma unroll
-        for (int c = 0; c < K3_NB; c++) if (c <= lane) A[(k0 + lane) * K3_LD + k0 + c] = a[c];
-    }
-}
+#define K3_TRI(r, c) ((r) * ((r) + 1) / 2 + (c))      // packed lower triangle of the 8x8 diagonal block
 
-// z <- L11^{-1} z for the unit-lower block at (k0,k0); one warp, lane c holds z[k0+c]
-__device__ __forceinline__ void trsv_lower_warp(const double *A, double *v, int k0, int bs, int lane) {
-    const int c = lane & 7;
-    double Lr[K3_NB];
+// One block step of the panel for matrix row i (k0 <= i <= npad; row npad is the right-hand side). On entry the columns
+// k0..k0+7 of all rows >= k0 carry every earlier block step's update. Writes, for this row: L (scaled) into A, the unscaled W
+// into Wp (rows below the diagonal block only), the pivots' reciprocals (thread of row k0).
+__device__ __forceinline__ void k3_panel_row(double *A, double *Wp, double *vinv, int k0, int i) {
+    double D[36], a[K3_NB];
 #pragma unroll
-    for (int j = 0; j < K3_NB; j++) Lr[j] = (c < bs && j < c) ? A[(k0 + c) * K3_LD + k0 + j] : 0.0;
-    double z = (c < bs) ? v[k0 + c] : 0.0;
+    for (int r = 0; r < K3_NB; r++)
 #pragma unroll
-    for (int j = 0; j < K3_NB - 1; j++) {
-        const double zj = shfl_f64(z, j);
-        z -= Lr[j] * zj;          // Lr[j] == 0 for j >= c
+        for (int c = 0; c <= r; c++) D[K3_TRI(r, c)] = A[(k0 + r) * K3_LD + k0 + c];
+#pragma unroll
+    for (int c = 0; c < K3_NB; c++) a[c] = A[i * K3_LD + k0 + c];      // (rows inside the block: entries right of the diagonal are never stored)
+    const bool below = i >= k0 + K3_NB;
+#pragma unroll
+    for (int c = 0; c < K3_NB; c++) {
+        const double dk = D[K3_TRI(c, c)];
+        // the next pivot's update is formed before the reciprocal is known: the chain per pivot is rcp + one FMA
+        double sq = 0.0;
+        if (c + 1 < K3_NB) sq = D[K3_TRI(c + 1, c)] * D[K3_TRI(c + 1, c)];
+        const double inv = (fabs(dk) > 0.0) ? k3_rcp(dk) : 1.0;      // "don't scale by an invalid pivot" (Eigen LDLT)
+        if (c + 1 < K3_NB) D[K3_TRI(c + 1, c + 1)] = fma(-sq, inv, D[K3_TRI(c + 1, c + 1)]);
+        const double w = a[c], l = w * inv;
+#pragma unroll
+        for (int r = c + 1; r < K3_NB; r++) {
+            const double lr = D[K3_TRI(r, c)] * inv;
+#pragma unroll
+            for (int q = c + 1; q <= r; q++)
+                if (!(r == c + 1 && q == c + 1)) D[K3_TRI(r, q)] = fma(-lr, D[K3_TRI(q, c)], D[K3_TRI(r, q)]);
+            a[r] = fma(-l, D[K3_TRI(r, c)], a[r]);
+        }
+        if (k0 + c < i) {
+            A[i * K3_LD + k0 + c] = l;
+            if (below) Wp[c * K3_WPLD + i] = w;
+        } else if (k0 + c == i) {
+            A[i * K3_LD + i] = w;              // the pivot d (the pseudo-inverse test of the solve reads it)
+        }
+        if (i == k0) vinv[k0 + c] = inv;
     }
-    if (lane < bs) v[k0 + lane] = z;
-}
-// x <- L11^{-T} x
-__device__ __forceinline__ void trsv_lower_t_warp(const double *A, double *v, int k0, int bs, int lane) {
-    const int c = lane & 7;
-    double Lc[K3_NB];
-#pragma unroll
-    for (int j = 0; j < K3_NB; j++) Lc[j] = (j < bs && c < j) ? A[(k0 + j) * K3_LD + k0 + c] : 0.0;
-    double x = (c < bs) ? v[k0 + c] : 0.0;
-#pragma unroll
-    for (int j = K3_NB - 1; j >= 1; j--) {
-        const double xj = shfl_f64(x, j);
-        x -= Lc[j] * xj;          // Lc[j] == 0 for j <= c
-    }
-    if (lane < bs) v[k0 + lane] = x;
 }
 
 // Clock read that the compiler cannot move across memory operations, and that the hardware cannot execute before a
@@ -262,95 +267,229 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
-    extern __shared__ double sm3[];
-    double *A = sm3;                        // [(K3_NP + 1)][K3_LD] permuted, scaled, padded system (+ rhs as row npad), factorised in place
-    double *Wp = A + (K3_NP + 1) * K3_LD;    // [K3_NB][K3_WPLD] panel W = L*D of the current block step
-    double *vinv = Wp + K3_NB * K3_WPLD;    // [K3_NP] reciprocal pivots
-    double *vb = vinv + K3_NP;               // rhs / solution
-    double *vS = vb + MAXN;                 // SVecI
-    double *vd = vS + MAXN;                 // delta / temp
-    double *vx = vd + MAXN;                 // x
-    int *perm = (int *) (vx + MAXN);        // [MAXN]
-    K3Frames *S = (K3Frames *) (perm + MAXN + 2);
-    double *sPns = (double *) (S + 1);      // [n*n] null-space projector
-    float *sAdH = (float *) (sPns + MAXN * MAXN);   // [MAXPAIR][64] adHostF, adTargetF (index h + nF*t): staged once per launch
-    float *sAdT = sAdH + MAXPAIR * 64;
-    const int nF = ws->nF, n = ws->n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_launch_dependents();
-    constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
-    double b_pre = 0.0, dg_pre = 0.0, hs_pre[K3_HSCOPY];
+struct K3Smem {       // carve-up of the dynamic shared memory block (all 16-byte aligned)
+    double *A, *A0, *Wp, *vinv, *vb, *vS, *vd, *vx, *Pns;
+    int *perm;
+    K3Frames *S;
+    float *adH, *adT;
+};
+#define K3_A_DOUBLES ((K3_NP + 1) * K3_LD + 1)
+#define K3_SMEM_DOUBLES (K3_A_DOUBLES + MAXN * MAXN + 2 * K3_NB * K3_WPLD + 5 * K3_NP + MAXN * MAXN + K3_NP / 2 + 4)
+__device__ __forceinline__ K3Smem k3_carve(double *base) {
+    K3Smem m;
+    m.A = base;                                 // [(K3_NP + 1)][K3_LD] permuted, scaled, identity-padded system (+ rhs as row npad), factorised in place
+    m.A0 = m.A + K3_A_DOUBLES;                   // [n*n] the assembled system as the stitch kernel left it (column-major)
+    m.Wp = m.A0 + MAXN * MAXN;                   // [2][K3_NB][K3_WPLD] unscaled panel W = L*D of the current / previous block step
+    m.vinv = m.Wp + 2 * K3_NB * K3_WPLD;
+    m.vb = m.vinv + K3_NP; m.vS = m.vb + K3_NP; m.vd = m.vS + K3_NP; m.vx = m.vd + K3_NP;
+    m.Pns = m.vx + K3_NP;                        // [n*n] null-space projector
+    m.perm = (int *) (m.Pns + MAXN * MAXN);      // [K3_NP]
+    m.S = (K3Frames *) (m.perm + K3_NP + 8);
+    m.adH = (float *) (m.S + 1);                 // [MAXPAIR][64] adHostF, adTargetF (index h + nF*t)
+    m.adT = m.adH + MAXPAIR * 64;
+    return m;
+}
+
+// Scaled, Eigen-ordered LDL^T solve of the assembled system (EnergyFunctional.cc:326-335): x = S (S A S)^-1 S b.
+// In: m.A0 (n x n, column-major), m.vb = b, m.vd = diag(A0). Out: m.vx. Called by all K3_THREADS threads.
+__device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole 8x8 blocks; the rhs is row npad
-    // the f32 adjoints (constant for the window) feed xAd (solve) and adHTdeltaF (step) at the very end: asynchronous
-    // copies, 16 bytes each, issued before pdl_wait
-    for (int e = tid; e < nF * nF * 16; e += K3_THREADS) {
-        cp_async16(sAdH + 4 * e, &ws->adHostF[0][0] + 4 * e);
-        cp_async16(sAdT + 4 * e, &ws->adTargetF[0][0] + 4 * e);
+    double *A = m.A;
+    // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
+    if (tid < n) {
+        const double dg = m.vd[tid];
+        const double sv = 1.0 / sqrt(dg + 10.0);
+        m.vS[tid] = sv;
+        m.vd[tid] = fabs(dg * sv * sv);
     }
-    pdl_wait();
-    const int iteration = *iteration_dev;
-    float nid_pre = 0.f, num_pre = 1.f, tho_pre = 0.f;      // doStepFromBackup's canbreak inputs (thread 0 only)
-    if (tid == 0) { nid_pre = ws->sumNID; num_pre = ws->numID; tho_pre = ws->S.thOptIterations; }
-    if (flags & K3F_SOLVE) {
-        // What the stitch kernel left behind (k2b_stitch, do_assemble; EnergyFunctional.cc:257,283-291): HFinal_top and its
-        // diagonal, HFinal_top - H_sc (lastHS once solved), bFinal_top (lastbS). The diagonal comes first: it fixes SVecI
-        // and the pivot order, and with those the matrix is gathered straight into its permuted place by asynchronous
-        // global->shared copies (LDGSTS) that land while the frame state is staged.
-        if (tid < n) { dg_pre = sb.dg[tid]; b_pre = sb.bFg[tid]; }
-#pragma unroll
-        for (int k = 0; k < K3_HSCOPY; k++) {
-            const int e = tid + k * K3_THREADS;
-            hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
-        }
-        if (iteration >= 2)
-            for (int e = tid; e < n * n; e += K3_THREADS) cp_async8(sPns + e, sb.Pns + e);
-        // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
-        if (tid < n) {
-            const double sv = 1.0 / sqrt(dg_pre + 10.0);
-            vS[tid] = sv;
-            vd[tid] = fabs(dg_pre * sv * sv);          // |diagonal| of the scaled matrix
-            vb[tid] = b_pre;
-        }
-        __syncthreads();
-        {   // rank sort: 4 threads per row fold a quarter of the comparisons each
-            const int i = tid >> 2, q = tid & 3;
+    __syncthreads();
+    {   // rank sort: 4 threads per row fold a quarter of the comparisons each
+        for (int i4 = tid; i4 < ((4 * n + 31) & ~31); i4 += K3_THREADS) {      // whole warps: the shuffles below are full-mask
+            const int i = i4 >> 2, q = i4 & 3;
             int rank = 0;
             if (i < n) {
-                const double di = vd[i];
+                const double di = m.vd[i];
                 for (int j = q; j < n; j += 4) {
-                    const double dj = vd[j];
+                    const double dj = m.vd[j];
                     rank += (dj > di) || (dj == di && j < i);
                 }
             }
             rank += __shfl_xor_sync(0xffffffffu, rank, 1);
             rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-            if (i < n && q == 0) perm[rank] = i;
+            if (q == 0 && i < n) m.perm[rank] = i;
         }
-        __syncthreads();
-        // lower triangle (+ the whole diagonal blocks) of P A0 P^T; padding = identity
-        for (int r = warp; r < npad; r += K3_THREADS / 32) {
-            const int pr = (r < n) ? perm[r] : 0;
+    }
+    __syncthreads();
+    // A = P (S A0 S) P^T, lower triangle plus the whole diagonal blocks; padding = identity; row npad = P S b
+    for (int r = warp; r <= npad; r += K3_THREADS / 32) {
+        const bool rhs = r == npad;
+        const int pr = (r < n) ? m.perm[r] : 0;
+        const double sr = (r < n) ? m.vS[pr] : 0.0;
+        for (int c = lane; c < npad; c += 32) {
+            if (!(rhs || c <= r || (c >> 3) == (r >> 3))) continue;
+            double v;
+            if (rhs) v = (c < n) ? m.vb[m.perm[c]] * m.vS[m.perm[c]] : 0.0;
+            else if (r < n && c < n) {
+                const int pc = m.perm[c];
+                const int hi = max(pr, pc), lo = min(pr, pc);                 // lower triangle of the input (row hi, column lo)
+                v = (sr * m.A0[lo * n + hi]) * m.vS[pc];
+            } else v = (r == c) ? 1.0 : 0.0;
+            A[r * K3_LD + c] = v;
+        }
+    }
+    __syncthreads();
+    PROF_ONLY(if (tid == 0) prof[0] = clk_fenced();)
+    // ---- blocked in-place LDL^T of the matrix augmented with the right-hand side as row npad
+    const int nblk = npad / K3_NB;
+    for (int kb = 0; kb < nblk; kb++) {
+        const int k0 = kb * K3_NB, m0 = k0 + K3_NB;
+        double *Wp = m.Wp + (kb & 1) * K3_NB * K3_WPLD;
+        if (tid >= k0 && tid <= npad) k3_panel_row(A, Wp, m.vinv, k0, tid);
+        // (helper warps run the previous block step's far trailing update meanwhile, see below)
+        if (tid >= 96 && kb > 0) {
+            const int pk0 = k0 - K3_NB, j0 = k0 + K3_NB;             // previous step's panel columns; first far column
+            const double *Wq = m.Wp + ((kb - 1) & 1) * K3_NB * K3_WPLD;
+            const int t = tid - 96;
+            for (int i = j0 + (t >> 4); i <= npad; i += (K3_THREADS - 96) / 16) {
+                double li[K3_NB];
 #pragma unroll
-            for (int cc = 0; cc < (K3_NP + 31) / 32; cc++) {
-                const int c = lane + 32 * cc;
-                if (c < npad && (c <= r || (c >> 3) == (r >> 3))) {
-                    if (r < n && c < n) cp_async8(A + r * K3_LD + c, sb.A0g + (size_t) perm[c] * n + pr);
-                    else A[r * K3_LD + c] = (r == c) ? 1.0 : 0.0;
+                for (int c = 0; c < K3_NB; c++) li[c] = A[i * K3_LD + pk0 + c];
+                const int jmax = min(i, npad - 1);
+                for (int j = j0 + (t & 15); j <= jmax; j += 16) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c += 2) { s0 = fma(li[c], Wq[c * K3_WPLD + j], s0); s1 = fma(li[c + 1], Wq[(c + 1) * K3_WPLD + j], s1); }
+                    A[i * K3_LD + j] -= (s0 + s1);
                 }
             }
         }
+        __syncthreads();
+        // near update: the next panel's 8 columns, one element per thread: A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j < m0+8, j <= i <= npad
+        if (m0 < npad) {
+            for (int e = tid; e < (npad + 1 - m0) * K3_NB; e += K3_THREADS) {
+                const int i = m0 + (e >> 3), j = m0 + (e & 7);
+                if (j <= i) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c += 2) {
+                        s0 = fma(A[i * K3_LD + k0 + c], Wp[c * K3_WPLD + j], s0);
+                        s1 = fma(A[i * K3_LD + k0 + c + 1], Wp[(c + 1) * K3_WPLD + j], s1);
+                    }
+                    A[i * K3_LD + j] -= (s0 + s1);
+                }
+            }
+        }
+        __syncthreads();
     }
+    PROF_ONLY(if (tid == 0) prof[1] = clk_fenced();)
+    // ---- backward solve L^T x = z by ONE warp, the vector in registers: lane owns rows lane, lane+32, lane+64. Row npad holds
+    // z = D^-1 L^-1 b (unscaled where the pivot was invalid); Eigen's solve applies the pseudo-inverse of D.
+    if (warp == 0) {
+        double z[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int i = lane + 32 * q;
+            z[q] = 0.0;
+            if (i < npad) {
+                const double dk = A[i * K3_LD + i];
+                z[q] = (fabs(dk) > 2.2250738585072014e-308) ? A[npad * K3_LD + i] : 0.0;
+            }
+        }
+        for (int kb = nblk - 1; kb >= 0; kb--) {
+            const int k0 = kb * K3_NB, sl = k0 >> 5, l0 = k0 & 31;
+            const double zsel = (sl == 0) ? z[0] : (sl == 1) ? z[1] : z[2];
+            double x[K3_NB], Lb[28];
+#pragma unroll
+            for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
+#pragma unroll
+            for (int j = 1; j < K3_NB; j++)
+#pragma unroll
+                for (int c = 0; c < j; c++) Lb[j * (j - 1) / 2 + c] = A[(k0 + j) * K3_LD + k0 + c];
+            // x_c = z_c - sum_{j > c} L(k0+j, k0+c) x_j, solved redundantly by every lane
+#pragma unroll
+            for (int j = K3_NB - 1; j >= 1; j--)
+#pragma unroll
+                for (int c = 0; c < j; c++) x[c] = fma(-Lb[j * (j - 1) / 2 + c], x[j], x[c]);
+            // the block's unknowns go back to their owner lanes; earlier rows lose this block's contribution
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int i = lane + 32 * q;
+                if (q == sl) {
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c++) if (lane == l0 + c) z[q] = x[c];
+                }
+                if (i < k0) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < K3_NB; c += 2) {
+                        s0 = fma(A[(k0 + c) * K3_LD + i], x[c], s0);
+                        s1 = fma(A[(k0 + c + 1) * K3_LD + i], x[c + 1], s1);
+                    }
+                    z[q] -= (s0 + s1);
+                }
+            }
+        }
+        // x = S P^T xp
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int i = lane + 32 * q;
+            if (i < n) { const int pi = m.perm[i]; m.vx[pi] = z[q] * m.vS[pi]; }
+        }
+    }
+    __syncthreads();
+    PROF_ONLY(if (tid == 0) prof[2] = clk_fenced();)
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
+    extern __shared__ double sm3[];
+    const K3Smem m = k3_carve(sm3);
+    K3Frames *S = m.S;
+    const int nF = ws->nF, n = ws->n, tid = threadIdx.x;
+    pdl_launch_dependents();
+    // ---- before pdl_wait: data that is constant for the whole window (set_frames): the f32 adjoints (xAd, adHTdeltaF) and the
+    // null-space projector, as asynchronous 16-byte copies
+    for (int e = tid; e < nF * nF * 16; e += K3_THREADS) {
+        cp_async16(m.adH + 4 * e, &ws->adHostF[0][0] + 4 * e);
+        cp_async16(m.adT + 4 * e, &ws->adTargetF[0][0] + 4 * e);
+    }
+    for (int e = tid; e < n * n / 2; e += K3_THREADS) cp_async16(m.Pns + 2 * e, sb.Pns + 2 * e);
+    pdl_wait();
+    // ---- one round trip for everything the previous kernels produced: the assembled system (k2b_stitch, do_assemble;
+    // EnergyFunctional.cc:257,283-291: HFinal_top, its diagonal, bFinal_top, HFinal_top - H_sc), the frame / calibration records
+    const int iteration = *iteration_dev;
+    constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
+    double hs_pre[K3_HSCOPY], b_pre = 0.0;
+    float nid_pre = 0.f, num_pre = 1.f, tho_pre = 0.f;      // doStepFromBackup's canbreak inputs (thread 0 only)
+    if (flags & K3F_SOLVE) {
+        for (int e = tid; e < n * n / 2; e += K3_THREADS) cp_async16(m.A0 + 2 * e, sb.A0g + 2 * e);
+        if (tid < n) { m.vd[tid] = sb.dg[tid]; b_pre = sb.bFg[tid]; m.vb[tid] = b_pre; }
+#pragma unroll
+        for (int k = 0; k < K3_HSCOPY; k++) {
+            const int e = tid + k * K3_THREADS;
+            hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
+        }
+    }
+    for (int e = tid; e < (int) (sizeof(K3Frames) / 8); e += K3_THREADS) cp_async8((char *) S + 8 * e, (const char *) ws->fr + 8 * e);
+    if (tid == 0) { nid_pre = ws->sumNID; num_pre = ws->numID; tho_pre = ws->S.thOptIterations; }
+#ifdef LDSO_B200_PROFILE
     int dbgi = 0;
+    long long prof[4] = {0, 0, 0, 0};
 #define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clk_fenced(); dbgi++; } while (0)
-    K3_STAMP();
-    if (tid == 0) {      // wall-clock timeline of one iteration (development aid): K3 span here, K2a/K2b spans by atomics
+    if (tid == 0) {      // wall-clock timeline of one iteration: K3 span here, K2a/K2b spans by atomics
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         ws->dbg[14] = (long long) gt;
         ws->dbg[16] = 0x7fffffffffffffffLL; ws->dbg[17] = 0; ws->dbg[18] = 0x7fffffffffffffffLL; ws->dbg[19] = 0;
     }
-    stage_in(S, ws);
-    K3_STAMP();
+#else
+    long long *prof = nullptr;
+#define K3_STAMP() do { } while (0)
+#endif
+    K3_STAMP();   // 0
+    cp_async_wait_all();
+    __syncthreads();
+    K3_STAMP();   // 1: inputs staged
 
     if (flags & K3F_BACKUP) {
         if (tid < nF) for (int i = 0; i < 10; i++) S->fr[tid].state_backup[i] = S->fr[tid].state[i];
@@ -365,170 +504,49 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             if (e < n * n) sb.lastHS[e] = hs_pre[k];
         }
         if (tid < n) sb.lastbS[tid] = b_pre;
-        K3_STAMP();   // 2
-        // A = P (S A0 S) P^T: every thread scales the elements it copied itself (visible to it after the wait); b' = P S b
-        cp_async_wait_all();
-        for (int r = warp; r < n; r += K3_THREADS / 32) {
-            const double sr = vS[perm[r]];
-#pragma unroll
-            for (int cc = 0; cc < (K3_NP + 31) / 32; cc++) {
-                const int c = lane + 32 * cc;
-                if (c < n && (c <= r || (c >> 3) == (r >> 3))) A[r * K3_LD + c] = A[r * K3_LD + c] * sr * vS[perm[c]];
-            }
-        }
-        if (tid < npad) A[npad * K3_LD + tid] = (tid < n) ? vb[perm[tid]] * vS[perm[tid]] : 0.0;
-        __syncthreads();
-
-        K3_STAMP();   // 3: scaled+permuted
-        // ---- blocked in-place LDL^T (lower) of the matrix AUGMENTED with the right-hand side as row n:
-        // the panel/trailing steps then leave D^-1 L^-1 b in that row, i.e. the forward solve comes for free.
-        // Look-ahead schedule: while warps 1.. apply block step k to the rows below the NEXT diagonal block, warp 0
-        // applies it to that block and factorises it right away, so the serial 8-pivot chain of step k+1 is hidden
-        // behind the trailing update of step k (two barriers per step).
-        long long tp = 0, tw = 0, tb1 = 0, tb2 = 0, tq;     // this thread's clocks in panel / barrier / trailing(+diag) / barrier (development aid)
-        // (the loop starts one block early: that pass only factorises diagonal block 0, so the serial pivot code exists
-        // once -- a second inlined copy in front of the loop costs ~19 k cycles of cold instruction fetch per launch)
-        for (int k0 = -K3_NB; k0 < npad; k0 += K3_NB) {
-            const int m0 = k0 + K3_NB;
-            tq = clk_fenced();
-            if (tid == 0) ws->dbg[33 + (k0 >> 3)] = tq;
-            if (k0 >= 0 && tid < npad + 1 - m0) {      // panel row i (incl. the rhs row npad): w = L*D (unscaled), l = L
-                const int i = m0 + tid;
-                // all operands first (the 28 entries of L11 are warp-uniform broadcasts), then the 8-step substitution
-                double a[K3_NB], iv[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2], w[K3_NB];
-#pragma unroll
-                for (int c = 0; c < K3_NB; c++) { a[c] = A[i * K3_LD + k0 + c]; iv[c] = vinv[k0 + c]; }
-#pragma unroll
-                for (int c = 1; c < K3_NB; c++)
-#pragma unroll
-                    for (int j = 0; j < c; j++) Lb[c * (c - 1) / 2 + j] = A[(k0 + c) * K3_LD + k0 + j];
-#pragma unroll
-                for (int c = 0; c < K3_NB; c++) {
-                    double s0 = a[c], s1 = 0.0;
-#pragma unroll
-                    for (int j = 0; j < c; j += 2) s0 -= w[j] * Lb[c * (c - 1) / 2 + j];
-#pragma unroll
-                    for (int j = 1; j < c; j += 2) s1 -= w[j] * Lb[c * (c - 1) / 2 + j];
-                    w[c] = s0 + s1;
-                }
-#pragma unroll
-                for (int c = 0; c < K3_NB; c++) {
-                    A[i * K3_LD + k0 + c] = w[c] * iv[c];
-                    Wp[c * K3_WPLD + i] = w[c];
-                }
-            }
-            { const long long t1 = clk_fenced(); tp += t1 - tq; tq = t1; }
-            __syncthreads();
-            { const long long t1 = clk_fenced(); tb1 += t1 - tq; tq = t1; }
-            // trailing update A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j <= min(i, npad-1), i <= npad
-            if (warp == 0) {
-                if (m0 < npad) {
-                    if (k0 >= 0) {
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int e = lane + 32 * h, r = e >> 3, cc = e & 7;
-                            const int i = m0 + r, j = m0 + cc;
-                            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                            for (int c = 0; c < K3_NB; c += 2) {
-                                s0 += A[i * K3_LD + k0 + c] * Wp[c * K3_WPLD + j];
-                                s1 += A[i * K3_LD + k0 + c + 1] * Wp[(c + 1) * K3_WPLD + j];
-                            }
-                            if (cc <= r) A[i * K3_LD + j] -= (s0 + s1);
-                        }
-                    }
-                    __syncwarp();
-                    ldlt_diag_block_warp(A, vinv, m0, lane);
-                }
-            } else if (k0 >= 0) {
-                const int t = tid - 32;
-                for (int i = m0 + K3_NB + (t >> 4); i <= npad; i += (K3_THREADS - 32) / 16) {
-                    double li[K3_NB];
-#pragma unroll
-                    for (int c = 0; c < K3_NB; c++) li[c] = A[i * K3_LD + k0 + c];
-                    const int jmax = min(i, npad - 1);
-#pragma unroll 2
-                    for (int j = m0 + (t & 15); j <= jmax; j += 16) {
-                        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                        for (int c = 0; c < K3_NB; c += 2) { s0 += li[c] * Wp[c * K3_WPLD + j]; s1 += li[c + 1] * Wp[(c + 1) * K3_WPLD + j]; }
-                        A[i * K3_LD + j] -= (s0 + s1);
-                    }
-                }
-            }
-            { const long long t1 = clk_fenced(); tw += t1 - tq; tq = t1; }
-            __syncthreads();
-            tb2 += clk_fenced() - tq;
-        }
-        if (tid == 0) { ws->dbg[20] = tp; ws->dbg[21] = tb1; ws->dbg[22] = tw; ws->dbg[23] = tb2; ws->dbg[33 + 9] = clk_fenced(); }
-        if (tid == 32) { ws->dbg[24] = tp; ws->dbg[25] = tb1; ws->dbg[26] = tw; ws->dbg[27] = tb2; }
-        if (tid == 496) { ws->dbg[28] = tp; ws->dbg[29] = tb1; ws->dbg[30] = tw; ws->dbg[31] = tb2; }
-        K3_STAMP();   // 4: factorised
-        // row n now holds D^-1 L^-1 b (unscaled where the pivot was invalid): Eigen's solve uses the pseudo-inverse of D
-        if (tid < n) {
-            const double dk = A[tid * K3_LD + tid];
-            vb[tid] = (fabs(dk) > 2.2250738585072014e-308) ? A[npad * K3_LD + tid] : 0.0;
-        }
-        __syncthreads();
-        // ---- backward solve L^T x = z, blocked from the last block up, column oriented: once a block of x is final its
-        // contribution is removed from all earlier rows by one thread per row (no reduction on the critical path)
-        for (int k0 = ((n - 1) / K3_NB) * K3_NB; k0 >= 0; k0 -= K3_NB) {
-            const int bs = min(K3_NB, n - k0);
-            if (warp == 0) trsv_lower_t_warp(A, vb, k0, bs, lane);
-            __syncthreads();
-            if (tid < k0) {
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int c = 0; c < K3_NB; c += 2) {
-                    if (c < bs) s0 += A[(k0 + c) * K3_LD + tid] * vb[k0 + c];
-                    if (c + 1 < bs) s1 += A[(k0 + c + 1) * K3_LD + tid] * vb[k0 + c + 1];
-                }
-                vb[tid] -= (s0 + s1);
-            }
-            __syncthreads();
-        }
-        K3_STAMP();   // 5: back-substituted
-        if (tid < n) vx[perm[tid]] = vb[tid];
-        __syncthreads();
-        if (tid < n) vx[tid] *= vS[tid];
-        __syncthreads();
-        // orthogonalize(&x, 0) when iteration >= 2 (SOLVER_ORTHOGONALIZE_X_LATER, :339-343): x -= NNpiTS x
+        k3_ldlt_solve(m, n, prof);
+#ifdef LDSO_B200_PROFILE
+        if (tid == 0) { ws->dbg[20] = prof[0]; ws->dbg[21] = prof[1]; ws->dbg[22] = prof[2]; }
+#endif
+        K3_STAMP();   // 2: solved
+        // orthogonalize(&x, 0) when iteration >= 2 (SOLVER_ORTHOGONALIZE_X_LATER, :339-343): x -= NNpiTS x (NNpiTS is symmetric)
         if (iteration >= 2) {
-            for (int r = warp; r < n; r += K3_THREADS / 32) {
-                double s = 0.0;
-                for (int c = lane; c < n; c += 32) s += sPns[r * n + c] * vx[c];      // NNpiTS is symmetric
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) vd[r] = s;
+            for (int i4 = tid; i4 < ((4 * n + 31) & ~31); i4 += K3_THREADS) {
+                const int i = i4 >> 2, q = i4 & 3;
+                double s0 = 0.0;
+                if (i < n) for (int c = q; c < n; c += 4) s0 = fma(m.Pns[i * n + c], m.vx[c], s0);
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+                if (q == 0 && i < n) m.vd[i] = s0;
             }
             __syncthreads();
-            if (tid < n) vx[tid] -= vd[tid];
+            if (tid < n) m.vx[tid] -= m.vd[tid];
             __syncthreads();
         }
-        K3_STAMP();   // 6: orthogonalised
-        if (tid < n) sb.lastX[tid] = vx[tid];
+        K3_STAMP();   // 3: orthogonalised
+        if (tid < n) sb.lastX[tid] = m.vx[tid];
         // resubstituteF_MT frame part (:495-507)
         if (tid < CPARS) {
-            S->calib.step[tid] = -vx[tid];
-            ws->cstep[tid] = (float) vx[tid];
+            S->calib.step[tid] = -m.vx[tid];
+            ws->cstep[tid] = (float) m.vx[tid];
         }
         if (tid >= 32 && tid < 32 + nF) {
             const int h = tid - 32;
-            for (int i = 0; i < 8; i++) S->fr[h].step[i] = -vx[CPARS + 8 * h + i];
+            for (int i = 0; i < 8; i++) S->fr[h].step[i] = -m.vx[CPARS + 8 * h + i];
             S->fr[h].step[8] = S->fr[h].step[9] = 0.0;
         }
         for (int o = tid; o < nF * nF * 8; o += K3_THREADS) {
             const int q = o >> 3, j = o & 7, h = q / nF, t = q % nF;     // xAd[nFrames*h + t]
-            const float *AH = sAdH + (h + nF * t) * 64, *AT = sAdT + (h + nF * t) * 64;
+            const float *AH = m.adH + (h + nF * t) * 64, *AT = m.adT + (h + nF * t) * 64;
             float s1 = 0.f, s2 = 0.f;
-            for (int i = 0; i < 8; i++) s1 += (float) vx[CPARS + 8 * h + i] * AH[i * 8 + j];
-            for (int i = 0; i < 8; i++) s2 += (float) vx[CPARS + 8 * t + i] * AT[i * 8 + j];
+            for (int i = 0; i < 8; i++) s1 += (float) m.vx[CPARS + 8 * h + i] * AH[i * 8 + j];
+            for (int i = 0; i < 8; i++) s2 += (float) m.vx[CPARS + 8 * t + i] * AT[i * 8 + j];
             ws->xAd[nF * h + t][j] = s1 + s2;
         }
         __syncthreads();
     }
-    K3_STAMP();   // 7: xAd done
+    K3_STAMP();   // 4: xAd done
     if (flags & K3F_STEP) {
-        if (!(flags & K3F_SOLVE)) { cp_async_wait_all(); __syncthreads(); }     // the staged adjoints (the solve path waited already)
         // doStepFromBackup(1,1,1,1,1), frame/calib part (FullSystem.cc:1588-1597,1617-1627)
         if (tid == 0) {
             double nv[4];
@@ -553,16 +571,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             for (int i = 0; i < 10; i++) f.state[i] = f.state_backup[i] + f.step[i];
         }
         __syncthreads();
-        frames_refresh(S, ws, false, sAdH, sAdT);
+        frames_refresh(S, ws, false, m.adH, m.adT);
     }
-    K3_STAMP();   // 8: frames refreshed
+    K3_STAMP();   // 5: frames refreshed
     stage_out(S, ws);
-    K3_STAMP();   // 9
+    K3_STAMP();   // 6
+#ifdef LDSO_B200_PROFILE
     if (tid == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         ws->dbg[15] = (long long) gt;
     }
+#endif
     if ((flags & K3F_SOLVE) && tid == 0) *iteration_dev = iteration + 1;
 }
-#define K3_SMEM_BYTES (((K3_NP + 1) * K3_LD + K3_NB * K3_WPLD + 4 * MAXN + K3_NP) * sizeof(double) + (MAXN + 2) * sizeof(int) + sizeof(K3Frames) + MAXN * MAXN * sizeof(double) + 2 * MAXPAIR * 64 * sizeof(float) + 64)
+#define K3_SMEM_BYTES (K3_SMEM_DOUBLES * sizeof(double) + (K3_NP + 8) * sizeof(int) + sizeof(K3Frames) + 2 * MAXPAIR * 64 * sizeof(float) + 64)

@@ -164,6 +164,14 @@ struct DevWindow {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Development instrumentation (clock64 / globaltimer stamps written by the kernels, tools/k3clk.py): compiled in only with
+// -DLDSO_B200_PROFILE (LDSO_B200_CFLAGS=-DLDSO_B200_PROFILE python -m ldso_b200.build --force); production kernels carry none.
+#ifdef LDSO_B200_PROFILE
+#define PROF_ONLY(...) __VA_ARGS__
+#else
+#define PROF_ONLY(...)
+#endif
+
 #define CUDA_CHECK_RET(ctx, call)                                                         \
     do {                                                                                  \
         cudaError_t e__ = (call);                                                         \

@@ -686,7 +686,9 @@ __global__ void __launch_bounds__(INIT_THREADS) k_init_calc_res(InitArgs A) {
             if (i < firstBad) Jb[k] += pk;
         }
     }
-    float msg = (idx < firstBad) ? ms : 1e10f;      // point->maxstep: the minimum over the pixels visited (NaN never wins a `<`)
+    // point->maxstep starts at 1e10 and takes `maxstep < point->maxstep` per visited pixel (:74, :125-126): an infinite step
+    // (zero translation) or a NaN never wins that comparison, so such lanes enter the minimum as 1e10
+    float msg = (idx < firstBad && ms < 1e10f) ? ms : 1e10f;
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) { const float other = __shfl_xor_sync(0xffffffffu, msg, o); if (other < msg) msg = other; }
 

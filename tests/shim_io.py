@@ -28,9 +28,7 @@ def dump(win, path):
 
 def build():
     src = os.path.join(ROOT, "tests", "cpp", "shim_test.cc")
-    hdr = os.path.join(ROOT, "ldso_b200", "host", "ldso_shim.hpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        return EXE
+    # always rebuilt (a second of g++): mtimes are arbitrary after a checkout / snapshot, a stale binary must never be run
     libdir = os.path.join(ROOT, "ldso_b200", "lib")
     subprocess.check_call(["g++", "-std=c++17", "-O2", src, "-o", EXE, "-L" + libdir, "-lldso_b200", "-Wl,-rpath," + libdir, "-pthread"])
     return EXE

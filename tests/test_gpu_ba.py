@@ -95,7 +95,71 @@ def _check_solve(ctx, o, it):
     pg, po = ctx.points(), o.points()
     for k in ("HdiF", "bdSumF", "Hcd_accAF", "Hdd_accAF", "bd_accAF"):
         assert rel_err(pg[k], po[k]) < TOL, k
+    _check_point_step(ctx, o, X, so["lastX"], pg, po)
     return X, so["lastX"]
+
+
+def resubstitute_numpy(win, x, frames, pts, res):
+    """EnergyFunctional::resubstituteF_MT / resubstituteFPt (EnergyFunctional.cc:491-547) restated in float32 numpy from a
+    given x and one side's per-point / per-residual quantities: xAd[h,t] = x_h^T adHostF[h,t] + x_t^T adTargetF[h,t],
+    b = bdSumF - xc . Hcd - sum_r xAd[h,t_r] . JpJdF_r over the active residuals, step = -b * HdiF. Returns (step, scale):
+    scale = HdiF * (|bdSumF| + sum of the magnitudes of the subtracted terms), the size of the float sum `step` is the rest of."""
+    nF = win.nF
+    xf = x.astype(np.float32)
+    adH, adT = frames["adHost"].astype(np.float32), frames["adTarget"].astype(np.float32)
+    xAd = np.zeros((nF, nF, 8), np.float32)
+    for h in range(nF):
+        for t in range(nF):
+            q = h + nF * t
+            xAd[h, t] = xf[4 + 8 * h:12 + 8 * h] @ adH[q] + xf[4 + 8 * t:12 + 8 * t] @ adT[q]
+    xc = -(-xf[:4])          # cstep = -x[0:4]; xc = -cstep
+    step = np.zeros(win.nP, np.float32)
+    scale = np.zeros(win.nP, np.float64)
+    rp = win.res_point
+    for p in range(win.nP):
+        h = int(win.pt_host[p])
+        b = np.float32(pts["bdSumF"][p]) - np.float32(np.dot(xc, pts["Hcd_accAF"][p]))
+        mag = abs(float(pts["bdSumF"][p])) + abs(float(np.dot(xc, pts["Hcd_accAF"][p])))
+        ngood = 0
+        for r in range(win.res_begin[p], win.res_begin[p + 1]):
+            if not res["isActive"][r]:
+                continue
+            ngood += 1
+            term = np.float32(np.dot(xAd[h, int(win.res_target[r])], res["JpJdF"][r]))
+            b = np.float32(b - term)
+            mag += abs(float(term))
+        if ngood:
+            step[p] = -b * pts["HdiF"][p]
+            scale[p] = mag * float(pts["HdiF"][p])
+    return step, scale
+
+
+def _check_point_step(ctx, o, Xg, Xo, pg, po):
+    """Row a8: the per-point step of resubstituteFPt. x carries the gauge component the two sides cannot agree on (DESIGN.md
+    section 5), so x is INJECTED: each side's step is checked against the restated formula fed with that side's x.
+    (1) oracle x + oracle quantities vs the oracle's step: validates the restatement (1e-5 of the float sum's magnitude);
+    (2) device x + device quantities vs the device's step: the kernel's arithmetic alone, same bar;
+    (3) device x + ORACLE quantities vs the device's step: the whole path, 1e-4 in norm; the per-point maximum is
+        printed: a step is the small remainder of a float sum, so single points reach 1e-3 of that sum's magnitude where HdiF or
+        bdSumF (1e-4 each, asserted above in norm) cancel."""
+    win = o.win
+    ro, rg = o.residuals(), ctx.residuals(with_J=False)
+    fo = o.frames()
+    so_, sc_o = resubstitute_numpy(win, Xo, fo, po, ro)
+    err_o = np.max(np.abs(so_ - po["step"]) / np.maximum(sc_o, 1e-7))
+    assert err_o < 1e-5, ("restated resubstitute vs oracle", err_o)
+    sd_, sc_d = resubstitute_numpy(win, Xg, ctx.frames(), pg, rg)
+    err_d = np.max(np.abs(sd_ - pg["step"]) / np.maximum(sc_d, 1e-7))
+    assert err_d < 1e-5, ("device resubstituteFPt vs the restated formula on its own inputs", err_d)
+    both = (ro["isActive"] == rg["isActive"])
+    ok_pts = np.array([both[win.res_begin[p]:win.res_begin[p + 1]].all() for p in range(win.nP)])
+    sg_, sc_g = resubstitute_numpy(win, Xg, fo, po, ro)
+    err_g = np.abs(sg_ - pg["step"]) / np.maximum(sc_g, 1e-7)
+    nrm = rel_err(pg["step"][ok_pts], sg_[ok_pts])
+    print("point step: kernel arithmetic %.3g; vs oracle quantities: norm-rel %.3g, per-point max (vs sum magnitude) %.3g, plain max-rel %.3g, "
+          "points compared %d / %d" % (err_d, nrm, err_g[ok_pts].max(), max_rel(pg["step"][ok_pts], sg_[ok_pts]), int(ok_pts.sum()), win.nP))
+    assert nrm < TOL, ("device per-point step vs oracle quantities", nrm)
+    assert err_g[ok_pts].max() < 5e-3
 
 
 @pytest.mark.parametrize("which", ["small", "cfg2"])
@@ -195,6 +259,9 @@ def test_fused_gn_loop(which, small_win, cfg2_win):
     ctx3.optimize_begin(); ctx3.gn_iterations(0, 1); ctx3.synchronize()
     s3 = ctx3.last_solution()
     assert rel_err(s3["lastHS"], HS) < 1e-12 and rel_err(s3["lastbS"], bS) < 1e-9
+    # ... and of the per-point step: K1's phase R (fused) against k_points (piecewise, checked against the oracle in _check_solve)
+    st2, st3 = ctx2.points()["step"], ctx3.points()["step"]
+    assert max_rel(st3, st2, floor=1e-6) < 1e-5, max_rel(st3, st2, floor=1e-6)
     for c in (ctx, ctx2, ctx3):
         c.close()
 

@@ -1,6 +1,7 @@
 """CoarseInitializer::calcResAndGS on the device against the oracle, which oracle/ref_pin pins bit for bit against the
-reference's own CoarseInitializer.cc. The kernel and its entry point were written at the end of round 1 without GPU time left to run
-them: the GPU test is skipped unless LDSO_B200_RUN_UNVALIDATED=1 (first thing to run in the next round); the oracle half runs on the CPU."""
+reference's own CoarseInitializer.cc. Per-point outputs (decisions, energies, maxstep, JbBuffer) are compared bit for bit (the kernel's
+translation unit is built with -fmad=false and folds the pattern in the reference's order); the 45 + 45 Hessian sums and the energy to
+1e-4 (their cross-point summation order differs from the reference's SSE lanes). The oracle half runs on the CPU."""
 import os
 
 import numpy as np
@@ -35,7 +36,6 @@ def test_init_calc_res_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("LDSO_B200_RUN_UNVALIDATED"), reason="k_init_calc_res has not been run on hardware yet (written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("lvl", [0, 2])
 def test_init_calc_res_matches_oracle(lvl):
     from ldso_b200 import capi
@@ -48,12 +48,14 @@ def test_init_calc_res_matches_oracle(lvl):
         tl = oracle_py.se3_log(R, t)[:3]
         o = oracle_py.init_calc_res(pair, lvl, R, t, a, b, u, v, idn, iR, good, e2, oth)
         g = ctx.init_calc_res(0, 1, lvl, R, t, tl, a, b, pair.K, u, v, idn, iR, good, e2, oth)
-        assert np.array_equal(g["isGood_new"], o["isGood_new"])
         acc = o["isGood_new"] == 1
-        assert np.array_equal(g["energy_new"], o["energy_new"]) and np.array_equal(g["maxstep"], o["maxstep"])
-        assert np.array_equal(g["lastHessian_new"][acc], o["lastHessian_new"][acc])
         live = good == 1
-        assert np.array_equal(g["Jb"][live], o["Jb"][live])
+        bad = {"isGood_new": int(np.sum(g["isGood_new"] != o["isGood_new"])),
+               "energy_new": int(np.sum(g["energy_new"] != o["energy_new"])),
+               "maxstep": int(np.sum(g["maxstep"] != o["maxstep"])),
+               "lastHessian_new": int(np.sum(g["lastHessian_new"][acc] != o["lastHessian_new"][acc])),
+               "Jb": int(np.sum(g["Jb"][live] != o["Jb"][live]))}
+        assert not any(bad.values()), f"bit mismatches (entries): {bad}"
         for k in ("H", "b", "Hsc", "bsc"):
             assert np.linalg.norm(g[k].astype(np.float64) - o[k]) <= 1e-4 * np.linalg.norm(o[k]) + 1e-6, k
         assert abs(g["res"][0] - o["res"][0]) <= 1e-4 * abs(o["res"][0]) and g["res"][1] == o["res"][1] and g["res"][2] == o["res"][2]

@@ -1,10 +1,11 @@
 """GPU parity tests of the immature-point trace (ImmaturePoint ctor + ImmaturePoint::traceOn, driven like
 FullSystem::traceNewCoarse) through the C ABI, against the CPU oracle (oracle/trace.cc).
 
-Bar: candidate statistics (colour, weights, gradH) within 1e-6 relative; trace status (GOOD / OOB / OUTLIER / SKIPPED /
-BADCONDITION) equal for >= 99 % of the candidates — the statuses are thresholded float quantities and nvcc contracts
-a*b+c into FMAs where the strict oracle build does not, so a candidate sitting on a threshold may flip; for candidates with
-the same status the interval (relative to idepth_max), sub-pixel position and quality agree to 1e-3 (median < 1e-5)."""
+Bar: candidate statistics (colour, weights, gradH) within 1e-6 relative; traceOn itself BIT FOR BIT: the trace kernels'
+translation unit is built with -fmad=false, replays the reference's running sums in the reference's order, and the strict oracle
+build does not contract either, so status (GOOD / OOB / OUTLIER / SKIPPED / BADCONDITION), idepth interval, sub-pixel position,
+pixel interval and quality are identical on all three geometries (measured: 0 differing entries of 3 000 candidates x 2 passes,
+profiles/r02b_trace_diff.log). Any mismatch is printed with its count."""
 import os
 
 import numpy as np
@@ -57,24 +58,12 @@ def test_trace_matches_oracle(geom):
         so = tr.trace_on(new)
         ctx.trace_immature(new, pts, case.KRKi[new], case.Kt[new], case.aff[new])
         sg = pts["status"]
-        same = sg == so
-        assert same.mean() >= 0.99, (geom, new, np.bincount(sg, minlength=6), np.bincount(so, minlength=6))
-        good = same & (so == oracle_py.IPS_GOOD)
-        assert good.sum() > 0.3 * case.n
-        scale = np.maximum(np.abs(tr.idepth_max[good]), 1e-6)       # idepth_min may sit at 0: errors are measured against the interval's scale
-        for a, b, sc in ((pts["idepth_min"], tr.idepth_min, scale), (pts["idepth_max"], tr.idepth_max, scale),
-                         (pts["interval"], tr.interval, np.maximum(np.abs(tr.interval[good]), 1e-6))):
-            d = np.abs(a[good] - b[good]) / sc
-            assert np.median(d) < 1e-5 and np.quantile(d, 0.99) < 1e-3, (np.median(d), np.quantile(d, 0.99))
-        assert np.quantile(np.abs(pts["uv"][good] - tr.uv[good]), 0.99) < 1e-2
-        q = np.abs(pts["quality"][same] - tr.quality[same]) / np.maximum(np.abs(tr.quality[same]), 1e-6)
-        assert np.quantile(q, 0.99) < 1e-3
-        # keep the two state sets aligned for the next pass (a flipped candidate would otherwise diverge further)
-        flip = ~same
-        for k, o in (("idepth_min", tr.idepth_min), ("idepth_max", tr.idepth_max), ("quality", tr.quality), ("status", tr.status),
-                     ("interval", tr.interval)):
-            pts[k][flip] = o[flip]
-        pts["uv"][flip] = tr.uv[flip]
+        eq = lambda a, b: (a == b) | (np.isnan(a) & np.isnan(b))
+        diff = {"status": int(np.sum(sg != so)), "idepth_min": int(np.sum(~eq(pts["idepth_min"], tr.idepth_min))),
+                "idepth_max": int(np.sum(~eq(pts["idepth_max"], tr.idepth_max))), "quality": int(np.sum(~eq(pts["quality"], tr.quality))),
+                "interval": int(np.sum(~eq(pts["interval"], tr.interval))), "uv": int(np.sum(~eq(pts["uv"], tr.uv)))}
+        assert not any(diff.values()), (geom, new, "entries differing from the oracle", diff)
+        assert (so == oracle_py.IPS_GOOD).sum() > 0.3 * case.n
     ctx.close()
 
 
@@ -87,7 +76,7 @@ def test_trace_golden_and_edges():
         ctx.upload_frame(i, win.pyramids[i])
     pts = _fresh(case, dict(color=g["color"], weights=g["weights"], gradH=g["gradH"], energyTH=np.full(case.n, 8 * 144.0, np.float32)))
     ctx.trace_immature(win.nF - 2, pts, case.KRKi[win.nF - 2], case.Kt[win.nF - 2], case.aff[win.nF - 2])
-    assert (pts["status"] == g["status1"]).mean() >= 0.99
+    assert np.array_equal(pts["status"], g["status1"])
     # candidates already OOB are left untouched; a second OUTLIER becomes OOB
     st = pts["status"].copy(); before = {k: pts[k].copy() for k in ("idepth_min", "idepth_max", "quality", "uv", "interval")}
     oob = st == oracle_py.IPS_OOB

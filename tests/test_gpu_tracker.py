@@ -43,10 +43,7 @@ def test_track_matches_oracle_and_golden():
     ot, ctx = _setup(pair)
     okg, Rg, tg, ag, bg, lrg, lfg = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
     oko, Ro, to, ao, bo, lro, lfo, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
-    assert okg == oko
-    assert rel_err(Rg, Ro) < 1e-5 and rel_err(tg, to) < 1e-3
-    assert abs(ag - ao) < 1e-4 and abs(bg - bo) < 1e-2
-    assert rel_err(np.nan_to_num(lrg), np.nan_to_num(lro)) < 1e-3
+    _same_track((okg, Rg, tg, ag, bg, lrg, lfg), (oko, Ro, to, ao, bo, lro, lfo))
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tracker_small.npz"))
     assert rel_err(tg, g["t"]) < 1e-3 and rel_err(Rg, g["R"]) < 1e-5
     # abort path: an impossible minResForAbort makes trackNewestCoarse return false and leave the pose untouched
@@ -55,10 +52,28 @@ def test_track_matches_oracle_and_golden():
     ctx.close()
 
 
-def test_track_full_size_converges():
+def _same_track(g, o, res_tol=1e-4):
+    """trackNewestCoarse device vs oracle. The LM loop's accept / reject decisions are taken on float sums whose order differs
+    (H, b agree to 1e-4), so the two runs are not bit-identical; measured differences (profiles/r02b_parity.log): rotation 3e-8,
+    translation 6e-6 relative, a 2e-7, b 3e-5 absolute, flow indicators 4e-6, lastResiduals 4e-6 (3.5e-4 at the KITTI geometry).
+    The bars below are ~10x those."""
+    okg, Rg, tg, ag, bg, lrg, lfg = g
+    oko, Ro, to, ao, bo, lro, lfo = o
+    assert okg == oko
+    assert rel_err(Rg, Ro) < 1e-6 and rel_err(tg, to) < 1e-4, (rel_err(Rg, Ro), rel_err(tg, to))
+    assert abs(ag - ao) < 1e-5 and abs(bg - bo) < 1e-3, (abs(ag - ao), abs(bg - bo))
+    assert np.array_equal(np.isnan(lrg), np.isnan(lro))
+    assert rel_err(np.nan_to_num(lrg), np.nan_to_num(lro)) < res_tol and rel_err(lfg, lfo) < 1e-4
+
+
+def test_track_full_size_matches_oracle():
+    """BASELINE config 1's pair (640x480, all four levels) through the whole LM loop against the oracle, and against ground truth."""
     pair = synth.make_track_pair()
     ot, ctx = _setup(pair)
-    ok, R, t, a, b, lr, lf = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    g = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    o = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
+    _same_track(g, o[:7])
+    ok, R, t = g[0], g[1], g[2]
     assert ok
     assert np.linalg.norm(t - pair.t_true) < 0.05 * np.linalg.norm(pair.t_true)
     assert np.abs(R - pair.R_true).max() < 1e-3
@@ -95,6 +110,5 @@ def test_kitti_geometry_tracker():
         assert rel_err(Hg, Ho) < TOL and rel_err(bg, bo) < TOL
     okg, Rg, tg, ag, bg_, lrg, lfg = ctx.tracker_track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
     oko, Ro, to, ao, bo_, lro, lfo, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
-    assert okg == oko
-    assert rel_err(Rg, Ro) < 1e-5 and rel_err(tg, to) < 1e-3
+    _same_track((okg, Rg, tg, ag, bg_, lrg, lfg), (oko, Ro, to, ao, bo_, lro, lfo), res_tol=3e-3)
     ctx.close()
