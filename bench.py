@@ -29,6 +29,13 @@ PTS_PER_FRAME = 250       # per GPU: 8 KF x 250 = 2000 active points (BASELINE.j
 NF = 8
 
 
+def common_config(n_gpus, n_points, n_residuals):
+    """The workload description both arms print verbatim (the driver compares the two `config` objects)."""
+    return {"workload": f"8 KF x {PTS_PER_FRAME * NF} active points per GPU: one 8 KF x {n_points}-point sliding window "
+                        f"({n_residuals} residuals), 640x480, seed 42; value counts {n_gpus} x (window iterations / s), i.e. 2000-point-window iterations / s",
+            "nF": NF, "n_gpus": n_gpus, "n_points": int(n_points), "n_residuals": int(n_residuals), "points_per_gpu": PTS_PER_FRAME * NF}
+
+
 def algorithmic_bytes(n_res, n_pts, nF):
     """bytes the reference's algorithm must touch once per GN iteration."""
     n = 8 * nF + 4
@@ -36,52 +43,76 @@ def algorithmic_bytes(n_res, n_pts, nF):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The timed region of this bench is
+    milliseconds long (20 steps x ~60 us), far below nvidia-smi's 100 ms period, so the samples are taken through NVML itself: one
+    sample right before the loop, a polling thread (~2 kHz) while it runs, one right after. Falls back to one nvidia-smi query
+    before/after when NVML cannot be loaded."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
-        self.proc = None
+        self.stop_flag = False
+        self.h = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _one(self):
+        if self.nv is not None:
+            nv = self.nv
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:  # noqa: BLE001
+                pass
+        else:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                self.rows.append((float(f[0]), float(f[1]), int(f[2], 16)))
+            except Exception:  # noqa: BLE001
+                pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self._one()
+            time.sleep(0.0005)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+        self._one()
+        self.th = None
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        self._one()
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source (NVML and nvidia-smi unavailable)"]}
+        sm = [r[0] for r in self.rows]
+        reasons = set()
         for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
+            for bit, nm in self.REASONS.items():
+                if r[2] & bit:
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)), "sm_mhz_min": float(min(sm)), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "samples": len(sm), "reasons": sorted(reasons), "source": "NVML polled before / during / after the timed loop" if self.nv else "nvidia-smi before / after"}
 
 
 def peaks():
@@ -93,7 +124,7 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
-def _ref_arm_seconds_per_iter(steps, warmup):
+def _ref_arm_seconds_per_iter(steps, warmup, pts_per_frame=PTS_PER_FRAME):
     """Seconds per GN iteration of the REFERENCE'S OWN back end (oracle/_ref/libref_ba.so: the reference's translation units compiled
     unmodified against stand-in Eigen headers, its own 6-thread IndexThreadReduce; oracle/ref_pin/ref_bench.cc) on the bench window, or
     None when that library is not there or does not run on this host. A child process: a library built with -march=native elsewhere
@@ -102,7 +133,7 @@ def _ref_arm_seconds_per_iter(steps, warmup):
     if not os.path.exists(os.path.join(here, "oracle", "_ref", "libref_ba.so")):
         return None
     code = ("import time\nfrom ldso_b200 import synth\nfrom tests import oracle_py\n"
-            f"win = synth.make_window(nF={NF}, pts_per_frame={PTS_PER_FRAME}, seed=42)\n"
+            f"win = synth.make_window(nF={NF}, pts_per_frame={int(pts_per_frame)}, seed=42)\n"
             "r = oracle_py.RefBA(win, multithreaded=True)\nr.optimize_begin()\n"
             f"[r.gn_iteration(min(i, 3)) for i in range({int(warmup)})]\n"
             f"t0 = time.perf_counter()\n[r.gn_iteration(3) for _ in range({int(steps)})]\n"
@@ -141,12 +172,14 @@ def run_reference(args):
     if rank != 0:
         return
     from ldso_b200 import synth
-    win = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME, seed=42)
+    # the same window the GPU arm iterates at this N (weak scaling: 2000 points per GPU -> 2000*N points here, on the host CPU)
+    world = max(1, args.gpus)
+    win = synth.make_window(nF=NF, pts_per_frame=PTS_PER_FRAME * world, seed=42)
     sec_port = _port_seconds_per_iter(win, args.steps, args.warmup)
-    sec_ref = _ref_arm_seconds_per_iter(args.steps, args.warmup)
+    sec_ref = _ref_arm_seconds_per_iter(args.steps, args.warmup, PTS_PER_FRAME * world)
     kind = "reference" if sec_ref else "port"
     sec = sec_ref if sec_ref else sec_port
-    v = 1.0 / sec
+    v = world / sec            # 2000-point-window iterations per second, the unit of the GPU arm's value
     cores = os.cpu_count()
     what = ("the reference's own Residuals.cc / AccumulatedTopHessian.cc / AccumulatedSCHessian.cc / EnergyFunctional.cc / FrameHessian.cc / "
             "FrameFramePrecalc.cc compiled -O3 -march=native against stand-in Eigen headers (oracle/_ref/libref_ba.so), its own IndexThreadReduce"
@@ -155,12 +188,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GN-iters/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "8 KF x 2000 active points (14000 residuals), 640x480, seed 42", "nF": NF, "n_points": win.nP,
-                   "n_residuals": win.nR,
-                   "value_unit_note": "iterations/s of ONE 2000-point window on the host CPU; the GPU arm's value at N GPUs counts N such "
-                                      "2000-point shards per step, so both arms are in 2000-point-window iterations per second"},
-        "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": kind, "port_value": 1.0 / sec_port,
-                         "sample": f"{args.steps} full GN iterations of the same window; {what}, 6 worker threads "
+        "config": common_config(world, win.nP, win.nR),
+        "window_iters_per_s": 1.0 / sec,
+        "cpu_baseline": {"value": v, "unit": "GN-iters/s", "cores": 6, "kind": kind, "port_value": world / sec_port,
+                         "sample": f"{args.steps} full GN iterations of the same {win.nP}-point window; {what}, 6 worker threads "
                                    f"(reference NUM_THREADS) on a {cores}-core host; port_value = the oracle port on the same sample"},
         "e2e": {"value": v, "unit": "GN-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -306,6 +337,9 @@ def run_ours(args):
         big_extra = run_config3(args, torch, stream, flush)
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
+    strong_extra = None
+    if world > 1 and not use_nccl:
+        strong_extra = run_config3_sharded(torch, dist, stream, flush, rank, world, local_rank)
     # max over ranks
     if dist is not None:
         tt = torch.tensor([t_ms, t_warm_ms], device="cuda", dtype=torch.float64)
@@ -330,13 +364,12 @@ def run_ours(args):
         "metric": METRIC, "value": its_per_s, "unit": "GN-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"8 KF x {PTS_PER_FRAME * NF} active points per GPU ({full.nP} points, {full.nR} residuals in the window), 640x480, seed 42",
-                   "nF": NF, "n_points": full.nP, "n_residuals": full.nR, "points_per_gpu": n_pts_rank,
-                   "parallelism": (f"points sharded x{world}, " + ("1 NCCL all-reduce/step" if use_nccl else "1 peer-memory all-reduce kernel/step (NVLink, CUDA IPC), no NCCL in the loop")) if world > 1 else "single GPU",
-                   "value_unit_note": "value = n_gpus x (GN iterations/s of the sharded window): each rank iterates a 2000-point "
-                                      "shard per step; window_iters_per_s is the rate of the whole 2000*n_gpus-point window",
-                   "l2": "192 MB flush buffer written between timed iterations (inputs 45 MB < 126 MB L2)",
-                   "timing": "per-iteration CUDA events on the launching stream, summed; max over ranks"},
+        "config": common_config(world, full.nP, full.nR),
+        "run": {"parallelism": (f"points sharded x{world}, " + ("1 NCCL all-reduce/step" if use_nccl else "1 peer-memory all-reduce kernel/step (NVLink, CUDA IPC), no NCCL in the loop")) if world > 1 else "single GPU",
+                "value_unit_note": "value = n_gpus x (GN iterations/s of the sharded window): each rank iterates a 2000-point "
+                                   "shard per step; window_iters_per_s is the rate of the whole 2000*n_gpus-point window",
+                "l2": "192 MB flush buffer written between timed iterations (inputs 45 MB < 126 MB L2)",
+                "timing": "per-iteration CUDA events on the launching stream, summed; max over ranks"},
         "value_l2_warm": world * args.steps / (t_warm_ms * 1e-3),
         "window_iters_per_s": window_its_per_s,
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
@@ -355,6 +388,8 @@ def run_ours(args):
         line["extra_trace_immature"] = trace_extra
     if big_extra is not None:
         line["extra_config3_single_gpu"] = big_extra
+    if strong_extra is not None:
+        line["extra_config3_sharded"] = strong_extra
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(win)
     print(json.dumps(line), flush=True)
@@ -418,6 +453,66 @@ def run_config3(args, torch, stream, flush):
     ctx.close()
     return {"n_points": win.nP, "n_residuals": win.nR, "ms_per_step": t_ms, "gn_iters_per_s": 1e3 / t_ms, "kernel_us": kt,
             "k1_algorithmic_bytes": b_k1, "k1_achieved_GBs": ach, "k1_roofline_frac": ach / hbm_peak}
+
+
+def _timed_cold_steps(torch, stream, flush, step, steps, dist=None):
+    """ms per step of `step()` with the L2 flushed before every step, CUDA events on the launching stream, max over ranks."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        flush.fill_(k & 0xff)
+        ev[k][0].record(stream); step(); ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    t = float(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    if dist is not None:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    return t
+
+
+def run_config3_sharded(torch, dist, stream, flush, rank, world, local_rank):
+    """BASELINE configs[2]: the FIXED 8 KF x 20 000-point window with its points sharded over the job's GPUs (strong scaling, one
+    peer-memory exchange kernel per step), and the same window on rank 0's GPU alone in the same run, so that the line states what
+    sharding buys at this point count."""
+    from ldso_b200 import capi, synth
+    full = synth.make_window(nF=NF, pts_per_frame=2500, seed=42)
+    win = synth.shard_window(full, rank, world)
+    ctx = capi.Context(win.w, win.h, win.levels, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_synth_window(win)
+    newest = full.nF - 1
+    counts = [int(np.sum(synth.shard_window(full, r, world).res_target == newest)) for r in range(world)]
+    ctx.set_shard(int(np.sum(counts[:rank])), int(np.sum(counts)))
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export())
+    ctx.peer_connect(rank, world, handles)
+    dist.barrier()
+    ctx.optimize_begin(want_energy=False)
+    for i in range(5):
+        ctx.gn_iterations(min(i, 3), 1)
+    t_sharded = _timed_cold_steps(torch, stream, flush, lambda: ctx.gn_iterations(3, 1), 30, dist)
+    err = ctx.peer_error()
+    dist.barrier()
+    ctx.close()
+    t_one = 0.0
+    if rank == 0:
+        c1 = capi.Context(full.w, full.h, full.levels, device=local_rank)
+        c1.set_stream(stream.cuda_stream)
+        c1.load_synth_window(full)
+        c1.optimize_begin(want_energy=False)
+        for i in range(5):
+            c1.gn_iterations(min(i, 3), 1)
+        t_one = _timed_cold_steps(torch, stream, flush, lambda: c1.gn_iterations(3, 1), 30, None)
+        c1.close()
+    dist.barrier()
+    return {"n_points": int(full.nP), "n_residuals": int(full.nR), "n_gpus": world, "scaling": "strong (fixed window)",
+            "ms_per_step_sharded": t_sharded, "gn_iters_per_s_sharded": 1e3 / t_sharded,
+            "ms_per_step_one_gpu": t_one, "gn_iters_per_s_one_gpu": (1e3 / t_one) if t_one else None,
+            "speedup_vs_one_gpu": (t_one / t_sharded) if t_one else None, "peer_error": int(err),
+            "def": "same timing rules as the headline (L2 flushed before every step, CUDA events, max over ranks); one_gpu = the whole window on rank 0's GPU in the same job"}
 
 
 def _trace_inputs(win):

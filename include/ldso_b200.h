@@ -176,6 +176,23 @@ int ldso_b200_marginalize_points(ldso_b200_ctx *ctx, int n, const int32_t *point
  * The bookkeeping half of the reference function (frame list, makeIDX, :131-150) is the caller's set_frames/set_window. */
 int ldso_b200_marginalize_frame(ldso_b200_ctx *ctx, int frame_idx, int *new_dim);
 
+/* AccumulatedTopHessianSSE::addPoint<mode> over a set of points followed by stitchDouble(usePrior = false), and
+ * AccumulatedSCHessianSSE::addPoint(p, shiftPriorToZero) + stitchDouble on the same set
+ * (include/internal/OptimizationBackend/AccumulatedTopHessian.h:20-125, AccumulatedSCHessian.h:17-118;
+ * AccumulatedTopHessian.cc:9-118,129-255, AccumulatedSCHessian.cc:9-119): the calls behind EnergyFunctional::accumulateAF_MT /
+ * accumulateLF_MT / accumulateSCF_MT (EnergyFunctional.cc:550-625) and marginalizePointsF. mode = the reference's template argument
+ * (0: active, not linearized, resF; 1: active, linearized, res_toZeroF + J delta; 2: all active, res_toZeroF), 3 = modes 0 and 1 in
+ * one pass (what solveSystemF sums: HA + HL). point_idx == NULL means every point. Works from the Jacobians ldso_b200_linearize_all
+ * stored. Outputs are n x n / n column-major doubles without the frame / calibration priors; any of them may be NULL. */
+int ldso_b200_accumulate(ldso_b200_ctx *ctx, int mode, int n_points, const int32_t *point_idx, int shift_prior_to_zero,
+                         double *H_top, double *b_top, double *H_sc, double *b_sc, int *nres);
+
+/* EnergyFunctional::calcLEnergyF_MT and calcMEnergyF (include/internal/OptimizationBackend/EnergyFunctional.h:120,126;
+ * EnergyFunctional.cc:353-378, calcLEnergyPt :627-682) at the current state: energyL = frame / calibration / point priors plus the
+ * linearised residuals' (2 res_toZeroF + J delta) . (J delta); energyM = delta . (2 bM + HM delta) with the device-resident prior.
+ * FullSystem::optimize reads both around every step (FullSystem.cc:1697-1703). Either pointer may be NULL. */
+int ldso_b200_calc_energies(ldso_b200_ctx *ctx, double *energyL, double *energyM);
+
 /* ---- the fused, device-resident Gauss-Newton loop ------------------------------------------------------
  * FullSystem::optimize's prologue (resetOOB + linearizeAll(false) + applyRes, FullSystem.cc:734-771). */
 int ldso_b200_optimize_begin(ldso_b200_ctx *ctx, double *energy_out);

@@ -68,7 +68,7 @@ SYMBOLS = [
     "ldso_b200_synchronize", "ldso_b200_launch_count", "ldso_b200_kernel_times", "ldso_b200_upload_frame", "ldso_b200_make_images",
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
-    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_select_activation", "ldso_b200_init_calc_res", "ldso_b200_optimize_begin",
+    "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_calc_energies", "ldso_b200_accumulate", "ldso_b200_select_activation", "ldso_b200_init_calc_res", "ldso_b200_optimize_begin",
     "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
@@ -291,6 +291,23 @@ class Context:
         nd = C.c_int()
         self._chk(self.L.ldso_b200_marginalize_frame(self.ctx, int(idx), C.byref(nd)))
         return self.marg_prior(nd.value)
+
+    def accumulate(self, mode, idx=None, shift_prior=True):
+        """addPoint<mode> + stitchDouble(usePrior=False) and the Schur addPoint + stitchDouble over the points idx (None = all)."""
+        n = self.n
+        out = dict(HA=np.zeros((n, n), np.float64, order="F"), bA=np.zeros(n), Hsc=np.zeros((n, n), np.float64, order="F"), bsc=np.zeros(n))
+        r = C.c_int()
+        ip = None if idx is None else np.ascontiguousarray(idx, np.int32)
+        self._chk(self.L.ldso_b200_accumulate(self.ctx, int(mode), 0 if ip is None else len(ip), None if ip is None else ip.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              int(bool(shift_prior)), _d(out["HA"]), _d(out["bA"]), _d(out["Hsc"]), _d(out["bsc"]), C.byref(r)))
+        out["nres"] = r.value
+        return out
+
+    def calc_energies(self):
+        """(calcLEnergyF_MT, calcMEnergyF) at the current state."""
+        el, em = C.c_double(), C.c_double()
+        self._chk(self.L.ldso_b200_calc_energies(self.ctx, C.byref(el), C.byref(em)))
+        return el.value, em.value
 
     def marg_prior(self, n=None):
         n = self.n if n is None else n

@@ -43,6 +43,7 @@ struct ldso_b200_ctx {
     std::vector<void *> win_allocs;
     std::vector<void *> derived_allocs;      // work items, partials, reduced buffer: rebuilt by build_derived
     bool have_window = false, have_frames = false, derived_dirty = true;
+    bool has_lin = false;            // the window holds linearized (isLinearized) residuals: solve_system accumulates HA + HL in one pass
     std::vector<unsigned char> h_scratch_bytes;     // select_activation's map read-back
     unsigned char *actsel_pin = nullptr; size_t actsel_pin_cap = 0;      // its pinned staging block
     std::vector<int> h_pt_host, h_res_begin, h_res_target;
@@ -506,6 +507,8 @@ extern "C" int ldso_b200_set_window(ldso_b200_ctx *c, const ldso_b200_window *wi
         priorF[p] = (win->pt_has_prior && win->pt_has_prior[p]) ? c->S.idepthFixPrior * SCALE_IDEPTH * SCALE_IDEPTH : 0.f;
     memcpy(H + L.pt_idepth_backup, win->pt_idepth, 4 * (size_t) nP);
     if (win->res_is_linearized) memcpy(H + L.res_lin, win->res_is_linearized, nR); else memset(H + L.res_lin, 0, std::max(nR, 1));
+    c->has_lin = false;
+    if (win->res_is_linearized) for (int r = 0; r < nR; r++) if (win->res_is_linearized[r]) { c->has_lin = true; break; }
     if (win->res_state) memcpy(H + L.res_state, win->res_state, nR); else memset(H + L.res_state, LDSO_B200_RES_IN, std::max(nR, 1));
     memcpy(H + L.pt_idepth, win->pt_idepth, 4 * (size_t) nP); memcpy(H + L.pt_idepth_zero, win->pt_idepth_zero, 4 * (size_t) nP);
     const size_t ul_begin = same_topology ? L.topo_end : 0;
@@ -846,6 +849,7 @@ static int clear_select(ldso_b200_ctx *c) {   // multi-GPU: slots owned by other
     return LDSO_B200_OK;
 }
 
+static int trace_reserve(ldso_b200_ctx *c, size_t bytes);      // device scratch shared by the one-shot entry points
 extern "C" int ldso_b200_linearize_all(ldso_b200_ctx *c, int fixLinearization, int flags, double *energy_out) {
     if (!c) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
@@ -891,7 +895,9 @@ extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *l
     if (!c) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
-    RET_IF(launch_k1(c, K1F_ACCUMULATE));                 // mode 0 records from the stored Jacobians
+    // records from the stored Jacobians: accumulateAF (mode 0); with linearized residuals in the window, accumulateLF's terms
+    // (mode 1: res_toZeroF + J delta) ride in the same pass -- solveSystemF only ever uses HA + HL and the summed point terms
+    RET_IF(launch_k1(c, K1F_ACCUMULATE | ((c->has_lin ? 3 : 0) << K1F_MODE_SHIFT)));
     RET_IF(launch_k2a(c, 1));
     RET_IF(launch_k2b(c, 1, 0, 1));
     RET_IF(set_iteration(c, iteration));
@@ -901,6 +907,34 @@ extern "C" int ldso_b200_solve_system(ldso_b200_ctx *c, int iteration, double *l
         LAUNCH_CHECK(c);
     }
     return ldso_b200_get_last_solution(c, lastHS, lastbS, lastX);
+}
+
+// AccumulatedTopHessianSSE::addPoint<mode> over a set of points + stitchDouble, and AccumulatedSCHessianSSE::addPoint + stitchDouble
+// on the same set (AccumulatedTopHessian.cc:9-118,129-255; AccumulatedSCHessian.cc:9-119): what EnergyFunctional::accumulateAF_MT /
+// accumulateLF_MT / accumulateSCF_MT and marginalizePointsF call. Records are rebuilt from the stored Jacobians (linearize_all).
+// mode 0/1/2 as the reference's template argument, 3 = modes 0 and 1 in one pass. point_idx == NULL: all points. H, b WITHOUT the
+// frame / calibration priors (stitchDouble(usePrior = false)); the caller adds them where the reference passes usePrior = true.
+extern "C" int ldso_b200_accumulate(ldso_b200_ctx *c, int mode, int n_points, const int32_t *point_idx, int shift_prior_to_zero,
+                                    double *H_top, double *b_top, double *H_sc, double *b_sc, int *nres) {
+    if (!c || mode < 0 || mode > 3 || n_points < 0) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    const uint8_t *sel = nullptr;
+    if (point_idx) {
+        std::vector<uint8_t> hsel(std::max(c->d.nP, 1), 0);
+        for (int i = 0; i < n_points; i++) {
+            if (point_idx[i] < 0 || point_idx[i] >= c->d.nP) return c->fail(LDSO_B200_ERR_ARG, "point index out of range");
+            hsel[point_idx[i]] = 1;
+        }
+        CUDA_CHECK_RET(c, cudaMemcpyAsync(c->pt_sel_dev, hsel.data(), c->d.nP, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+        sel = c->pt_sel_dev;
+    }
+    RET_IF(launch_k1(c, K1F_ACCUMULATE | (shift_prior_to_zero ? 0 : K1F_NO_SHIFT_PRIOR) | (mode << K1F_MODE_SHIFT), sel));
+    RET_IF(launch_k2a(c, 1));
+    RET_IF(launch_k2b(c, 1, 0, 0));
+    c->restitch_ok = false;      // the reduced buffer describes this call's selection / mode, not the window's system
+    return ldso_b200_get_system(c, H_top, b_top, H_sc, b_sc, nres);
 }
 
 extern "C" int ldso_b200_get_last_solution(ldso_b200_ctx *c, double *lastHS, double *lastbS, double *lastX) {
@@ -974,6 +1008,7 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
         k_scale_prior<<<(c->d.nP + 255) / 256, 256, 0, c->stream>>>(c->d, c->pt_sel_dev, prior_fac);
         LAUNCH_CHECK(c);
     }
+    c->has_lin = c->has_lin || n > 0;
     RET_IF(launch_k1(c, K1F_ACCUMULATE | K1F_NO_SHIFT_PRIOR | (2 << K1F_MODE_SHIFT), c->pt_sel_dev));
     RET_IF(launch_k2a(c, 1));
     RET_IF(launch_k2b(c, 1, 0, 0));
@@ -986,6 +1021,28 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
         CUDA_CHECK_RET(c, cudaMemcpyAsync(resInM, &c->ws_dev->resInA, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     }
+    return LDSO_B200_OK;
+}
+
+// EnergyFunctional::calcLEnergyF_MT / calcMEnergyF (EnergyFunctional.cc:353-378): the prior + linearised-residual energy and the
+// marginalisation energy at the current state (FullSystem::optimize reads both around every step, FullSystem.cc:1697-1703).
+extern "C" int ldso_b200_calc_energies(ldso_b200_ctx *c, double *energyL, double *energyM) {
+    if (!c) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    RET_IF(build_derived(c));
+    if (c->prior_dim != 0 && c->prior_dim != c->n) return c->fail(LDSO_B200_ERR_STATE, "prior dimension does not match the frames: call set_frames first");
+    const int nb = std::max(1, (c->d.nP + KEN_THREADS - 1) / KEN_THREADS);
+    RET_IF(trace_reserve(c, sizeof(double) * ((size_t) nb + 4) + 16));
+    double *part = (double *) c->trace_buf, *out = part + nb;
+    unsigned *counter = (unsigned *) (out + 2);
+    CUDA_CHECK_RET(c, cudaMemsetAsync(counter, 0, sizeof(unsigned), c->stream));
+    k_calc_energies<<<nb, KEN_THREADS, 0, c->stream>>>(c->d, c->ws_dev, c->sb, part, counter, out);
+    LAUNCH_CHECK(c);
+    double h[2];
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    if (energyL) *energyL = h[0];
+    if (energyM) *energyM = h[1];
     return LDSO_B200_OK;
 }
 

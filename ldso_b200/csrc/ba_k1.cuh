@@ -389,6 +389,8 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         } else {
             new_state = old_state; new_energy = old_energy; energy_wo = -1.f; ret_energy = 0.f;
             const bool act = d.res_active[r] != 0;
+            // mode 0: addPoint<0> (active, not linearized); 1: addPoint<1> (active, linearized); 2: addPoint<2> (all active,
+            // res_toZeroF); 3: modes 0 and 1 in ONE pass -- what solveSystemF sums anyway (HA + HL, Hdd_accAF + Hdd_accLF, ...)
             active = (mode == 0) ? (act && !lin) : (mode == 1) ? (act && lin) : act;
             if (pin[6] == 0.f) active = false;
         }
@@ -396,9 +398,10 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
 
         // ---- resApprox per accumulate mode (AccumulatedTopHessian.cc:40-64) and JI_r, Jab_r, rr (:66-76)
         float resApprox = v_res;
-        if (!(flags & K1F_LINEARIZE) && mode != 0) {
+        const int rmode = (mode == 3) ? (lin ? 1 : 0) : mode;
+        if (!(flags & K1F_LINEARIZE) && rmode != 0) {
             const float rtz = d.res_toZero[8 * r + idx];
-            if (mode == 2) resApprox = rtz;
+            if (rmode == 2) resApprox = rtz;
             else {
                 const float *dp = s_dHT + t * 8;
                 float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;

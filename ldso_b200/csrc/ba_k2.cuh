@@ -856,3 +856,77 @@ __global__ void k_grow_prior(SolveBufs sb, const double *src, int n) {
     }
     if (e >= od && e < n) sb.bM[e] = 0.0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// EnergyFunctional::calcLEnergyF_MT (EnergyFunctional.cc:361-378) with calcLEnergyPt (:627-682) and calcMEnergyF (:353-359).
+// One thread per point folds its linearised, active residuals (2 res_toZeroF + J delta) . (J delta) and deltaF^2 priorF; block sums
+// are written per block and folded in block order by the last block to finish (deterministic), which also adds the frame / calibration
+// priors and evaluates the marginalisation energy delta . (2 bM + HM delta). out[0] = L energy, out[1] = M energy.
+#define KEN_THREADS 256
+__global__ void __launch_bounds__(KEN_THREADS) k_calc_energies(DevWindow d, const WinState *__restrict__ ws, SolveBufs sb, double *part, unsigned *counter, double *out) {
+    __shared__ double s_sum[KEN_THREADS / 32];
+    __shared__ bool s_last;
+    const int nF = ws->nF, n = ws->n, tid = threadIdx.x, p = blockIdx.x * KEN_THREADS + tid;
+    double e = 0.0;
+    if (p < d.nP) {
+        const float dd = d.pt_idepth[p] - d.pt_idepth_zero[p];      // deltaF (EnergyFunctional.cc:424)
+        const int h = d.pt_host[p];
+        float ef = 0.f;
+        for (int r = d.pt_res_begin[p]; r < d.pt_res_begin[p + 1]; r++) {
+            if (!d.res_lin[r] || !d.res_active[r]) continue;
+            const float *dp = ws->adHTdeltaF[h + nF * d.res_target[r]];
+            const float *J = d.res_J + (size_t) 74 * r;
+            float a = 0.f, b = 0.f;
+            for (int k = 0; k < 6; k++) a += J[8 + k] * dp[k];
+            for (int k = 0; k < 4; k++) b += J[20 + k] * ws->calib.cDeltaF[k];
+            const float jx = a + b + J[28] * dd;
+            a = 0.f; b = 0.f;
+            for (int k = 0; k < 6; k++) a += J[14 + k] * dp[k];
+            for (int k = 0; k < 4; k++) b += J[24 + k] * ws->calib.cDeltaF[k];
+            const float jy = a + b + J[29] * dd;
+            for (int k = 0; k < 8; k++) {
+                float jd = J[30 + k] * jx;
+                jd = jd + J[38 + k] * jy;
+                jd = jd + J[46 + k] * dp[6];
+                jd = jd + J[54 + k] * dp[7];
+                float r0 = d.res_toZero[8 * r + k];
+                r0 = r0 + r0;
+                r0 = r0 + jd;
+                ef += jd * r0;
+            }
+        }
+        ef += dd * dd * d.pt_priorF[p];
+        e = (double) ef;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if ((tid & 31) == 0) s_sum[tid >> 5] = e;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < KEN_THREADS / 32; w++) s += s_sum[w];
+        part[blockIdx.x] = s;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __shared__ double s_m[MAXN];
+    if (tid < n) {       // calcMEnergyF: delta . (2 bM + HM delta), getStitchedDeltaF (EnergyFunctional.h:178-184)
+        double hd = 0.0;
+        for (int c = 0; c < n; c++) hd += sb.HM[(size_t) c * n + tid] * k2b_delta(ws, c);
+        s_m[tid] = k2b_delta(ws, tid) * (2.0 * sb.bM[tid] + hd);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double EL = 0.0;
+        for (int f = 0; f < nF; f++) for (int i = 0; i < 8; i++) EL += ws->fr[f].delta_prior[i] * ws->fr[f].prior[i] * ws->fr[f].delta_prior[i];
+        float sc = 0.f;
+        for (int i = 0; i < 4; i++) sc += ws->calib.cDeltaF[i] * (float) ws->cPrior[i] * ws->calib.cDeltaF[i];
+        EL += (double) sc;
+        for (unsigned b = 0; b < gridDim.x; b++) EL += ((volatile double *) part)[b];
+        double EM = 0.0;
+        for (int r = 0; r < n; r++) EM += s_m[r];
+        out[0] = EL; out[1] = EM;
+        *counter = 0u;
+    }
+}

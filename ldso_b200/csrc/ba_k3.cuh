@@ -19,9 +19,9 @@
 #define K3F_STEP 2
 #define K3F_BACKUP 4
 #define K3_THREADS 512
-#define K3_NP ((MAXN + 7) & ~7)     // system dimension padded to whole 8x8 blocks (identity padding)
-#define K3_LD (K3_NP + 1)
-#define K3_NB 8
+#define K3_NP MAXN               // n = 8 nF + 4 is a multiple of the block size 4: no padding
+#define K3_LD (K3_NP + 1)        // odd leading dimension: a column of the matrix touches every bank once
+#define K3_NB 4
 #define K3_WPLD (K3_NP + 2)      // Wp is [K3_NB][K3_WPLD] (column of the panel major): conflict-free for consecutive rows
 
 struct K3Frames {       // shared-memory staging of the mutable window records
@@ -177,28 +177,35 @@ __global__ void __launch_bounds__(128) k_frames_refresh(WinState *ws) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The 68x68 solve. Everything below is one serial dependency chain on a tiny matrix, so the design goal is the LENGTH OF
-// THE CHAIN, not throughput:
-//   * LDL^T's inherent chain is one reciprocal + one FMA per pivot. The factorisation is blocked by 8 columns; inside a
-//     block step every row thread factors the 8x8 diagonal block REDUNDANTLY in its own registers (SIMT: the redundant
-//     arithmetic costs no extra issue slots) and substitutes its own row on the fly, so a block step has no shuffle, no
-//     shared-memory exchange and no barrier on the pivot chain: 8 x (rcp + FMA) back to back;
-//   * all trailing products are formed BEFORE the reciprocal they are scaled by is known (tmp = W_r * W_s, then one FMA with
-//     1/d), and the reciprocal is a MUFU seed + one cubically convergent Newton step (3 dependent FMAs, ~1 ulp);
-//   * the update of the NEXT panel's 8 columns is spread over all threads (one element each) between two barriers, the rest of
-//     the trailing update is done by the helper warps while the row threads already factor the next panel;
-//   * the right-hand side rides along as matrix row npad, so the forward substitution is free; the backward substitution is done
-//     by ONE warp with the vector in registers (no barriers), 8 unknowns per step solved redundantly per lane.
+// THE CHAIN, not throughput (measured on B200 with tools/panel_bench.cu and ncu's per-instruction stall samples):
+//   * LDL^T's inherent chain is one reciprocal + one FMA per pivot (~105 cycles in f64: MUFU seed + 5 dependent DFMAs + the FMA).
+//     The factorisation is blocked by 4 columns; inside a block step every row thread factors the 4x4 diagonal block REDUNDANTLY in
+//     its own registers and substitutes its own row on the fly, so a block step has no shuffle, no shared-memory exchange and no
+//     barrier on the pivot chain. (8-column blocks were measured slower: the redundant O(NB^3) update costs ~2.3 issue cycles per
+//     DFMA on the one warp that carries the chain.)
+//   * the routine is BRANCH-FREE: every store is unconditional (rows inside the diagonal block write their never-read upper
+//     entries, every row thread writes the same reciprocal): ncu attributed 30 % of the routine's time to branch_resolving stalls
+//     behind the reconvergence points of its conditional stores.
+//   * the next pivot's update is formed BEFORE the reciprocal it is scaled by is known (sq = W^2, then one FMA with 1/d).
+//   * the update of the NEXT panel's 4 columns is spread over all threads (one element each) between two barriers; the rest of the
+//     trailing update is done by the helper warps while the row threads already factor the next panel.
+//   * the right-hand side rides along as matrix row n, so the forward substitution is free; the backward substitution is done by
+//     ONE warp with the vector in registers (no barriers), 4 unknowns per step solved redundantly per lane.
 // Eigen's LDLT pivots on the largest remaining |diagonal| of the INPUT matrix (its left-looking update never touches later
 // diagonal entries before they are chosen), i.e. a descending-|diag| order: computed by a rank sort and applied as a symmetric
 // permutation before the (then unpivoted) blocked factorisation; like Eigen, only the lower triangle of the input is referenced.
 
-// ~1 ulp reciprocal: MUFU.RCP64H seed (>= 20 bits) and y = y0 (1 + e + e^2), e = 1 - d y0 (error ~ e^3 < 2^-60)
+// ~1 ulp reciprocal without the slow-path branches of __drcp_rn: MUFU.RCP64H seed (a "gross approximation", ~9-10 bits measured:
+// with the cubic step alone the solve was only good to 1e-9), one cubically convergent step y1 = y0 (1 + e + e^2), e = 1 - d y0,
+// and one Newton step: 5 dependent FMAs
 __device__ __forceinline__ double k3_rcp(double d) {
     double y0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
     const double e = fma(-d, y0, 1.0);
     const double t = fma(e, e, e);
-    return fma(y0, t, y0);
+    const double y1 = fma(y0, t, y0);
+    const double e1 = fma(-d, y1, 1.0);
+    return fma(y1, e1, y1);
 }
 __device__ __forceinline__ double shfl_f64(double v, int src) {      // low word first: lands in an aligned register pair
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -206,44 +213,39 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {      // low word
     hi = __shfl_sync(0xffffffffu, hi, src);
     return __hiloint2double(hi, lo);
 }
-#define K3_TRI(r, c) ((r) * ((r) + 1) / 2 + (c))      // packed lower triangle of the 8x8 diagonal block
+#define K3_TRI(r, c) ((r) * ((r) + 1) / 2 + (c))      // packed lower triangle of the 4x4 diagonal block
 
-// One block step of the panel for matrix row i (k0 <= i <= npad; row npad is the right-hand side). On entry the columns
-// k0..k0+7 of all rows >= k0 carry every earlier block step's update. Writes, for this row: L (scaled) into A, the unscaled W
-// into Wp (rows below the diagonal block only), the pivots' reciprocals (thread of row k0).
-__device__ __forceinline__ void k3_panel_row(double *A, double *Wp, double *vinv, int k0, int i) {
-    double D[36], a[K3_NB];
+// One block step of the panel for matrix row i (k0 <= i <= n; row n is the right-hand side). On entry the columns k0..k0+3 of all
+// rows >= k0 carry every earlier block step's update. Writes, for this row: L (scaled) into A -- the pivot d itself on the diagonal
+// -- and the unscaled W into Wp.
+__device__ __forceinline__ void k3_panel_row(double *A, double *Wp, int k0, int i) {
+    double D[K3_NB * (K3_NB + 1) / 2], a[K3_NB];
 #pragma unroll
     for (int r = 0; r < K3_NB; r++)
 #pragma unroll
         for (int c = 0; c <= r; c++) D[K3_TRI(r, c)] = A[(k0 + r) * K3_LD + k0 + c];
 #pragma unroll
-    for (int c = 0; c < K3_NB; c++) a[c] = A[i * K3_LD + k0 + c];      // (rows inside the block: entries right of the diagonal are never stored)
-    const bool below = i >= k0 + K3_NB;
+    for (int c = 0; c < K3_NB; c++) a[c] = A[i * K3_LD + k0 + c];      // (rows inside the block: entries right of the diagonal are never read back)
 #pragma unroll
-    for (int c = 0; c < K3_NB; c++) {
-        const double dk = D[K3_TRI(c, c)];
-        // the next pivot's update is formed before the reciprocal is known: the chain per pivot is rcp + one FMA
+    for (int C = 0; C < K3_NB; C++) {
+        const double dk = D[K3_TRI(C, C)];
         double sq = 0.0;
-        if (c + 1 < K3_NB) sq = D[K3_TRI(c + 1, c)] * D[K3_TRI(c + 1, c)];
+        if (C + 1 < K3_NB) sq = D[K3_TRI((C + 1) % K3_NB, C)] * D[K3_TRI((C + 1) % K3_NB, C)];
         const double inv = (fabs(dk) > 0.0) ? k3_rcp(dk) : 1.0;      // "don't scale by an invalid pivot" (Eigen LDLT)
-        if (c + 1 < K3_NB) D[K3_TRI(c + 1, c + 1)] = fma(-sq, inv, D[K3_TRI(c + 1, c + 1)]);
-        const double w = a[c], l = w * inv;
+        if (C + 1 < K3_NB) D[K3_TRI((C + 1) % K3_NB, (C + 1) % K3_NB)] = fma(-sq, inv, D[K3_TRI((C + 1) % K3_NB, (C + 1) % K3_NB)]);
+        const double w = a[C], l = w * inv;
 #pragma unroll
-        for (int r = c + 1; r < K3_NB; r++) {
-            const double lr = D[K3_TRI(r, c)] * inv;
+        for (int r = C + 1; r < K3_NB; r++) {
+            const double lr = D[K3_TRI(r, C)] * inv;
 #pragma unroll
-            for (int q = c + 1; q <= r; q++)
-                if (!(r == c + 1 && q == c + 1)) D[K3_TRI(r, q)] = fma(-lr, D[K3_TRI(q, c)], D[K3_TRI(r, q)]);
-            a[r] = fma(-l, D[K3_TRI(r, c)], a[r]);
+            for (int q = C + 1; q <= r; q++)
+                if (!(r == C + 1 && q == C + 1)) D[K3_TRI(r, q)] = fma(-lr, D[K3_TRI(q, C)], D[K3_TRI(r, q)]);
+            a[r] = fma(-l, D[K3_TRI(r, C)], a[r]);
         }
-        if (k0 + c < i) {
-            A[i * K3_LD + k0 + c] = l;
-            if (below) Wp[c * K3_WPLD + i] = w;
-        } else if (k0 + c == i) {
-            A[i * K3_LD + i] = w;              // the pivot d (the pseudo-inverse test of the solve reads it)
-        }
-        if (i == k0) vinv[k0 + c] = inv;
+        // unconditional stores (a select, no branch): below the pivot the scaled entry, on the diagonal the pivot itself (the
+        // pseudo-inverse test of the solve reads it), right of it a value nobody reads
+        A[i * K3_LD + k0 + C] = (k0 + C < i) ? l : w;
+        Wp[C * K3_WPLD + i] = w;
     }
 }
 
@@ -268,20 +270,19 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct K3Smem {       // carve-up of the dynamic shared memory block (all 16-byte aligned)
-    double *A, *A0, *Wp, *vinv, *vb, *vS, *vd, *vx, *Pns;
+    double *A, *A0, *Wp, *vb, *vS, *vd, *vx, *Pns;
     int *perm;
     K3Frames *S;
     float *adH, *adT;
 };
-#define K3_A_DOUBLES ((K3_NP + 1) * K3_LD + 1)
-#define K3_SMEM_DOUBLES (K3_A_DOUBLES + MAXN * MAXN + 2 * K3_NB * K3_WPLD + 5 * K3_NP + MAXN * MAXN + K3_NP / 2 + 4)
+#define K3_A_DOUBLES (((K3_NP + 1) * K3_LD + 1) & ~1)
+#define K3_SMEM_DOUBLES (K3_A_DOUBLES + MAXN * MAXN + 2 * K3_NB * K3_WPLD + 4 * K3_NP + MAXN * MAXN + K3_NP / 2 + 4)
 __device__ __forceinline__ K3Smem k3_carve(double *base) {
     K3Smem m;
     m.A = base;                                 // [(K3_NP + 1)][K3_LD] permuted, scaled, identity-padded system (+ rhs as row npad), factorised in place
     m.A0 = m.A + K3_A_DOUBLES;                   // [n*n] the assembled system as the stitch kernel left it (column-major)
     m.Wp = m.A0 + MAXN * MAXN;                   // [2][K3_NB][K3_WPLD] unscaled panel W = L*D of the current / previous block step
-    m.vinv = m.Wp + 2 * K3_NB * K3_WPLD;
-    m.vb = m.vinv + K3_NP; m.vS = m.vb + K3_NP; m.vd = m.vS + K3_NP; m.vx = m.vd + K3_NP;
+    m.vb = m.Wp + 2 * K3_NB * K3_WPLD; m.vS = m.vb + K3_NP; m.vd = m.vS + K3_NP; m.vx = m.vd + K3_NP;
     m.Pns = m.vx + K3_NP;                        // [n*n] null-space projector
     m.perm = (int *) (m.Pns + MAXN * MAXN);      // [K3_NP]
     m.S = (K3Frames *) (m.perm + K3_NP + 8);
@@ -294,7 +295,6 @@ __device__ __forceinline__ K3Smem k3_carve(double *base) {
 // In: m.A0 (n x n, column-major), m.vb = b, m.vd = diag(A0). Out: m.vx. Called by all K3_THREADS threads.
 __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int npad = (n + K3_NB - 1) & ~(K3_NB - 1);      // identity-padded to whole 8x8 blocks; the rhs is row npad
     double *A = m.A;
     // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
     if (tid < n) {
@@ -304,59 +304,59 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         m.vd[tid] = fabs(dg * sv * sv);
     }
     __syncthreads();
-    {   // rank sort: 4 threads per row fold a quarter of the comparisons each
-        for (int i4 = tid; i4 < ((4 * n + 31) & ~31); i4 += K3_THREADS) {      // whole warps: the shuffles below are full-mask
-            const int i = i4 >> 2, q = i4 & 3;
-            int rank = 0;
-            if (i < n) {
-                const double di = m.vd[i];
-                for (int j = q; j < n; j += 4) {
-                    const double dj = m.vd[j];
-                    rank += (dj > di) || (dj == di && j < i);
-                }
+    for (int i4 = tid; i4 < ((4 * n + 31) & ~31); i4 += K3_THREADS) {      // rank sort, 4 threads per row; whole warps: the shuffles are full-mask
+        const int i = i4 >> 2, q = i4 & 3;
+        int rank = 0;
+        if (i < n) {
+            const double di = m.vd[i];
+            for (int j = q; j < n; j += 4) {
+                const double dj = m.vd[j];
+                rank += (dj > di) || (dj == di && j < i);
             }
-            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-            if (q == 0 && i < n) m.perm[rank] = i;
         }
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        if (q == 0 && i < n) m.perm[rank] = i;
     }
     __syncthreads();
-    // A = P (S A0 S) P^T, lower triangle plus the whole diagonal blocks; padding = identity; row npad = P S b
-    for (int r = warp; r <= npad; r += K3_THREADS / 32) {
-        const bool rhs = r == npad;
-        const int pr = (r < n) ? m.perm[r] : 0;
-        const double sr = (r < n) ? m.vS[pr] : 0.0;
-        for (int c = lane; c < npad; c += 32) {
-            if (!(rhs || c <= r || (c >> 3) == (r >> 3))) continue;
+    // A = P (S A0 S) P^T, lower triangle plus the whole diagonal blocks; row n = P S b
+    for (int r = warp; r <= n; r += K3_THREADS / 32) {
+        const bool rhs = r == n;
+        const int pr = rhs ? 0 : m.perm[r];
+        const double sr = rhs ? 0.0 : m.vS[pr];
+        for (int c = lane; c < n; c += 32) {
+            if (!(rhs || c <= r || (c / K3_NB) == (r / K3_NB))) continue;
+            const int pc = m.perm[c];
             double v;
-            if (rhs) v = (c < n) ? m.vb[m.perm[c]] * m.vS[m.perm[c]] : 0.0;
-            else if (r < n && c < n) {
-                const int pc = m.perm[c];
+            if (rhs) v = m.vb[pc] * m.vS[pc];
+            else {
                 const int hi = max(pr, pc), lo = min(pr, pc);                 // lower triangle of the input (row hi, column lo)
                 v = (sr * m.A0[lo * n + hi]) * m.vS[pc];
-            } else v = (r == c) ? 1.0 : 0.0;
+            }
             A[r * K3_LD + c] = v;
         }
     }
     __syncthreads();
     PROF_ONLY(if (tid == 0) prof[0] = clk_fenced();)
-    // ---- blocked in-place LDL^T of the matrix augmented with the right-hand side as row npad
-    const int nblk = npad / K3_NB;
+    // ---- blocked in-place LDL^T of the matrix augmented with the right-hand side as row n
+    const int nblk = n / K3_NB;
     for (int kb = 0; kb < nblk; kb++) {
         const int k0 = kb * K3_NB, m0 = k0 + K3_NB;
         double *Wp = m.Wp + (kb & 1) * K3_NB * K3_WPLD;
-        if (tid >= k0 && tid <= npad) k3_panel_row(A, Wp, m.vinv, k0, tid);
-        // (helper warps run the previous block step's far trailing update meanwhile, see below)
+        PROF_ONLY(const long long tq0 = clk_fenced();)
+        if (tid >= k0 && tid <= n) k3_panel_row(A, Wp, k0, tid);
+        PROF_ONLY(if (kb == 4 && tid == 16) prof[4] = clk_fenced() - tq0;)
+        // meanwhile the helper warps apply the PREVIOUS block step to the columns right of this panel (far update)
         if (tid >= 96 && kb > 0) {
-            const int pk0 = k0 - K3_NB, j0 = k0 + K3_NB;             // previous step's panel columns; first far column
+            const int pk0 = k0 - K3_NB;
             const double *Wq = m.Wp + ((kb - 1) & 1) * K3_NB * K3_WPLD;
             const int t = tid - 96;
-            for (int i = j0 + (t >> 4); i <= npad; i += (K3_THREADS - 96) / 16) {
+            for (int i = m0 + (t >> 4); i <= n; i += (K3_THREADS - 96) / 16) {
                 double li[K3_NB];
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) li[c] = A[i * K3_LD + pk0 + c];
-                const int jmax = min(i, npad - 1);
-                for (int j = j0 + (t & 15); j <= jmax; j += 16) {
+                const int jmax = min(i, n - 1);
+                for (int j = m0 + (t & 15); j <= jmax; j += 16) {
                     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                     for (int c = 0; c < K3_NB; c += 2) { s0 = fma(li[c], Wq[c * K3_WPLD + j], s0); s1 = fma(li[c + 1], Wq[(c + 1) * K3_WPLD + j], s1); }
@@ -364,11 +364,14 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
                 }
             }
         }
+        PROF_ONLY(if (kb == 4 && tid == 96) prof[5] = clk_fenced() - tq0;)
+        PROF_ONLY(const long long tq1 = clk_fenced();)
         __syncthreads();
-        // near update: the next panel's 8 columns, one element per thread: A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j < m0+8, j <= i <= npad
-        if (m0 < npad) {
-            for (int e = tid; e < (npad + 1 - m0) * K3_NB; e += K3_THREADS) {
-                const int i = m0 + (e >> 3), j = m0 + (e & 7);
+        PROF_ONLY(const long long tq2 = clk_fenced(); if (kb == 4 && tid == 16) prof[6] = tq2 - tq1;)
+        // near update: the next panel's columns, one element per thread: A[i][j] -= sum_c L(i,c) W(j,c), m0 <= j < m0 + NB, j <= i <= n
+        if (m0 < n) {
+            for (int e = tid; e < (n + 1 - m0) * K3_NB; e += K3_THREADS) {
+                const int i = m0 + e / K3_NB, j = m0 + e % K3_NB;
                 if (j <= i) {
                     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -380,10 +383,12 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
                 }
             }
         }
+        PROF_ONLY(const long long tq3 = clk_fenced(); if (kb == 4 && tid == 16) prof[7] = tq3 - tq2;)
         __syncthreads();
+        PROF_ONLY(if (kb == 4 && tid == 16) prof[8] = clk_fenced() - tq3;)
     }
     PROF_ONLY(if (tid == 0) prof[1] = clk_fenced();)
-    // ---- backward solve L^T x = z by ONE warp, the vector in registers: lane owns rows lane, lane+32, lane+64. Row npad holds
+    // ---- backward solve L^T x = z by ONE warp, the vector in registers: lane owns rows lane, lane+32, lane+64. Row n holds
     // z = D^-1 L^-1 b (unscaled where the pivot was invalid); Eigen's solve applies the pseudo-inverse of D.
     if (warp == 0) {
         double z[3];
@@ -391,15 +396,16 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         for (int q = 0; q < 3; q++) {
             const int i = lane + 32 * q;
             z[q] = 0.0;
-            if (i < npad) {
+            if (i < n) {
                 const double dk = A[i * K3_LD + i];
-                z[q] = (fabs(dk) > 2.2250738585072014e-308) ? A[npad * K3_LD + i] : 0.0;
+                z[q] = (fabs(dk) > 2.2250738585072014e-308) ? A[n * K3_LD + i] : 0.0;
             }
         }
+#pragma unroll 1
         for (int kb = nblk - 1; kb >= 0; kb--) {
             const int k0 = kb * K3_NB, sl = k0 >> 5, l0 = k0 & 31;
             const double zsel = (sl == 0) ? z[0] : (sl == 1) ? z[1] : z[2];
-            double x[K3_NB], Lb[28];
+            double x[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2];
 #pragma unroll
             for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
 #pragma unroll
@@ -415,10 +421,9 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 const int i = lane + 32 * q;
-                if (q == sl) {
+                double xo = z[q];
 #pragma unroll
-                    for (int c = 0; c < K3_NB; c++) if (lane == l0 + c) z[q] = x[c];
-                }
+                for (int c = 0; c < K3_NB; c++) xo = (q == sl && lane == l0 + c) ? x[c] : xo;
                 if (i < k0) {
                     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -426,8 +431,9 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
                         s0 = fma(A[(k0 + c) * K3_LD + i], x[c], s0);
                         s1 = fma(A[(k0 + c + 1) * K3_LD + i], x[c + 1], s1);
                     }
-                    z[q] -= (s0 + s1);
+                    xo -= (s0 + s1);
                 }
+                z[q] = xo;
             }
         }
         // x = S P^T xp
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     if (tid == 0) { nid_pre = ws->sumNID; num_pre = ws->numID; tho_pre = ws->S.thOptIterations; }
 #ifdef LDSO_B200_PROFILE
     int dbgi = 0;
-    long long prof[4] = {0, 0, 0, 0};
+    long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define K3_STAMP() do { if (tid == 0) ws->dbg[dbgi] = clk_fenced(); dbgi++; } while (0)
     if (tid == 0) {      // wall-clock timeline of one iteration: K3 span here, K2a/K2b spans by atomics
         unsigned long long gt;
@@ -506,7 +512,9 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         if (tid < n) sb.lastbS[tid] = b_pre;
         k3_ldlt_solve(m, n, prof);
 #ifdef LDSO_B200_PROFILE
-        if (tid == 0) { ws->dbg[20] = prof[0]; ws->dbg[21] = prof[1]; ws->dbg[22] = prof[2]; }
+        if (tid == 0) for (int k = 0; k < 4; k++) ws->dbg[20 + k] = prof[k];
+        if (tid == 16) for (int k = 4; k < 9; k++) if (k != 5) ws->dbg[20 + k] = prof[k];
+        if (tid == 96) ws->dbg[25] = prof[5];
 #endif
         K3_STAMP();   // 2: solved
         // orthogonalize(&x, 0) when iteration >= 2 (SOLVER_ORTHOGONALIZE_X_LATER, :339-343): x -= NNpiTS x (NNpiTS is symmetric)

@@ -210,6 +210,10 @@ class OracleBA:
         """lastEnergyP of the last linearizeAll."""
         return self.L.oracle_ba_last_energy(self.o)
 
+    def calc_energies(self):
+        """(calcLEnergyF_MT, calcMEnergyF) at the current state."""
+        return self.L.oracle_ba_calc_l_energy(self.o), self.L.oracle_ba_calc_m_energy(self.o)
+
     def linearize_all(self, fix=False):
         return self.L.oracle_ba_linearize_all(self.o, int(fix))
 

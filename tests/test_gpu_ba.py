@@ -87,6 +87,7 @@ def _check_solve(ctx, o, it):
     lam = 1e-5
     Hf = HS + sg["Hsc"]
     H2 = Hf.copy(); H2[np.diag_indices_from(H2)] *= (1 + lam); H2 -= sg["Hsc"] / (1 + lam)
+    H2 = np.tril(H2) + np.tril(H2, -1).T      # Eigen's LDLT (and the device solver) reference the lower triangle only
     Sv = 1 / np.sqrt(np.diag(H2) + 10)
     xn = Sv * np.linalg.solve(Sv[:, None] * H2 * Sv[None, :], Sv * bS)
     if it >= 2:
@@ -386,6 +387,78 @@ def test_marginalize_points(small_win):
     HMg, bMg = ctx.marg_prior()
     assert rel_err(HMg, HMo) < TOL
     assert rel_err(bMg, bMo) < max(TOL, 3 * rel_err(o2.marg_prior()[1], bMo))
+    ctx.close()
+
+
+def test_linearized_residuals_mode1(small_win):
+    """AccumulatedTopHessianSSE::addPoint<1> (AccumulatedTopHessian.cc:40-64: res_toZeroF + J delta on linearized residuals) and a
+    solveSystemF with linearized residuals in the window. The reference only creates such residuals in flagPointsForRemoval, right
+    before marginalizePointsF drops them, so the state is built the same way: fix the linearization of some points, keep them.
+    (1) accumulate(mode 1) against the oracle's accumulateLF_MT (HL, bL minus the priors topStitch adds with usePrior = true);
+    (2) solve_system: lastHS / lastbS / lastX with HA + HL, and the summed point terms (Hdd_accAF + Hdd_accLF ...) in HdiF / bdSumF."""
+    import dataclasses
+    win = dataclasses.replace(small_win, pt_idepth=small_win.pt_idepth_zero.copy())
+    o = oracle_py.OracleBA(win, threads_mode=1)
+    ctx = _ctx(win)
+    o.optimize_begin()
+    ctx.linearize_all(False); ctx.apply_res()
+    idx = np.arange(1, win.nP, 3, dtype=np.int32)[:50]
+    o.marginalize_points(idx); ctx.marginalize_points(idx)
+    ro = o.residuals()
+    nlin = int(((ro["isLinearized"] == 1) & (ro["isActive"] == 1)).sum())
+    assert nlin > 100
+    o.solve_system(0)
+    so, fo = o.system(), o.frames()
+    n = 8 * win.nF + 4
+    prior = np.concatenate([np.full(4, 5e9), fo["prior"].reshape(-1)])
+    bprior = np.concatenate([np.zeros(4), (fo["prior"] * fo["delta_prior"]).reshape(-1)])
+    L = ctx.accumulate(1)
+    assert L["nres"] == nlin == o.res_counts()[1]
+    HLo, bLo = so["HL"] - np.diag(prior), so["bL"] - bprior
+    assert rel_err(L["HA"], HLo) < TOL, rel_err(L["HA"], HLo)
+    # noise floor of b_L: the same oracle with FMA contraction (res_toZeroF + J delta is a sum of cancelling terms, see test_marginalize_points)
+    o2 = oracle_py.OracleBA(win, threads_mode=1, fast=True)
+    o2.optimize_begin(); o2.marginalize_points(idx); o2.solve_system(0)
+    floor = rel_err(o2.system()["bL"] - bprior, bLo)
+    assert rel_err(L["bA"], bLo) < max(TOL, 3 * floor), (rel_err(L["bA"], bLo), floor)
+    # (2) the whole solve with HA + HL
+    ctx.backup_state()
+    HS, bS, X = ctx.solve_system(0)
+    sg = ctx.system()
+    assert sg["resInA"] == o.res_counts()[0] + o.res_counts()[1]
+    assert rel_err(sg["HA"], so["HA"] + HLo) < TOL
+    assert rel_err(HS, so["lastHS"]) < TOL, rel_err(HS, so["lastHS"])
+    floor_b = rel_err(o2.system()["lastbS"], so["lastbS"])
+    assert rel_err(bS, so["lastbS"]) < max(TOL, 3 * floor_b), (rel_err(bS, so["lastbS"]), floor_b)
+    pg, po = ctx.points(), o.points()
+    assert rel_err(pg["HdiF"], po["HdiF"]) < TOL
+    assert rel_err(pg["bdSumF"], po["bdSumF"]) < max(TOL, 3 * rel_err(o2.points()["bdSumF"], po["bdSumF"]))
+    ctx.close()
+
+
+def test_calc_energies(small_win):
+    """EnergyFunctional::calcLEnergyF_MT / calcMEnergyF against the oracle: with priors only (fresh window), with a
+    marginalisation prior, and with linearised residuals present (after marginalize_points the reference keeps the points'
+    fixed residuals until the caller drops them: calcLEnergyPt's (2 res_toZeroF + J delta) . (J delta) branch runs)."""
+    win = small_win
+    n = 8 * win.nF + 4
+    rng = np.random.default_rng(23)
+    B = rng.standard_normal((n, n)) * 3.0
+    HM, bM = B @ B.T, rng.standard_normal(n) * 10.0
+    o = oracle_py.OracleBA(win, threads_mode=1)
+    ctx = _ctx(win)
+    o.optimize_begin(); ctx.optimize_begin()
+    for stage in range(3):
+        if stage == 1:
+            o.set_marg_prior(HM, bM); ctx.set_marg_prior(HM, bM)
+        if stage == 2:
+            idx = np.arange(0, win.nP, 4, dtype=np.int32)[:30]
+            o.marginalize_points(idx); ctx.marginalize_points(idx)
+            assert o.residuals()["isLinearized"].sum() > 50
+        (lo, mo), (lg, mg) = o.calc_energies(), ctx.calc_energies()
+        assert abs(lg - lo) <= 1e-5 * abs(lo) + 1e-9, (stage, lg, lo)
+        # after marginalize_points the two sides' HM / bM differ by the accumulation noise (1e-4 bar, test_marginalize_points)
+        assert abs(mg - mo) <= (1e-9 if stage < 2 else 1e-4) * abs(mo) + 1e-12, (stage, mg, mo)
     ctx.close()
 
 

@@ -7,9 +7,9 @@ ctx = capi.Context(win.w, win.h, win.levels); ctx.load_synth_window(win)
 ctx.optimize_begin(); ctx.gn_iterations(0, 30); ctx.synchronize()
 buf = (C.c_longlong*80)()
 ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
-t = np.array(buf[:10]); print("K3 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
-print("K3 stamp3 -> step tops -> loop end:", [int(buf[32+i] - buf[3]) for i in range(11)], "stamp4 at", int(buf[4]-buf[3]))
-print("K3 factorisation clocks [panel, barrier, trailing/diag, barrier]: tid0", list(buf[20:24]), "tid32", list(buf[24:28]), "tid496", list(buf[28:32]))
+t = np.array(buf[:7]); print("K3 stamps delta cycles [stage-in wait | backup+solve | orthogonalise | xAd | step+refresh | stage-out]:", np.diff(t), "total", t[-1]-t[0])
+print("K3 solve: sort+permute %d | factorisation %d | back-substitution %d cycles" % (buf[20] - buf[1], buf[21] - buf[20], buf[22] - buf[21]))
+print("K3 block step 4 (row 16): panel %d | helper far update (thread 96) %d | barrier wait %d | near update %d | barrier wait %d" % tuple(buf[24:29]))
 t = np.array(buf[64:72]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
 t = np.array(buf[72:76]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
 t = np.array(buf[76:78]); print("K2b select-CTA cycles:", np.diff(t))
@@ -39,7 +39,7 @@ def timeline(tag):
     print("%s timeline ns rel. K3 start: K3 [0, %d]  K1 [%d, %d]  K2a [%d, %d]  K2b [%d, %d]" %
           (tag, buf[15] - k3s, int(a[:, 0].min()) - k3s, int(a[:, 1].max()) - k3s, buf[16] - k3s, buf[17] - k3s, buf[18] - k3s, buf[19] - k3s))
     d = a[:, 1] - a[:, 0]
-    print("   K1 CTA duration p50/p100 %d/%d ns; K3 stamps %s" % (int(np.median(d)), d.max(), np.diff(np.array(buf[:10]))))
+    print("   K1 CTA duration p50/p100 %d/%d ns; K3 stamps %s fact %d backsub %d" % (int(np.median(d)), d.max(), np.diff(np.array(buf[:7])), buf[21] - buf[20], buf[22] - buf[21]))
 
 import torch
 flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
