@@ -347,6 +347,8 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         if (tid >= k0 && tid <= n) k3_panel_row(A, Wp, k0, tid);
         PROF_ONLY(if (kb == 4 && tid == 16) prof[4] = clk_fenced() - tq0;)
         // meanwhile the helper warps apply the PREVIOUS block step to the columns right of this panel (far update)
+        // (a clamped, branch-free variant of this loop and of the near update below was measured slower: the wasted elements cost
+        // more than the branches they remove; the single-warp back-substitution is the other way round)
         if (tid >= 96 && kb > 0) {
             const int pk0 = k0 - K3_NB;
             const double *Wq = m.Wp + ((kb - 1) & 1) * K3_NB * K3_WPLD;
@@ -394,24 +396,26 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         double z[3];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            const int i = lane + 32 * q;
-            z[q] = 0.0;
-            if (i < n) {
-                const double dk = A[i * K3_LD + i];
-                z[q] = (fabs(dk) > 2.2250738585072014e-308) ? A[n * K3_LD + i] : 0.0;
-            }
+            const int iv = lane + 32 * q, i = min(iv, n - 1);
+            const double dk = A[i * K3_LD + i], zi = A[n * K3_LD + i];
+            z[q] = (iv < n && fabs(dk) > 2.2250738585072014e-308) ? zi : 0.0;
         }
 #pragma unroll 1
         for (int kb = nblk - 1; kb >= 0; kb--) {
             const int k0 = kb * K3_NB, sl = k0 >> 5, l0 = k0 & 31;
             const double zsel = (sl == 0) ? z[0] : (sl == 1) ? z[1] : z[2];
-            double x[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2];
-#pragma unroll
-            for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
+            double x[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2], Lu[3][K3_NB];
+            // every load of the step first (none depends on this step's unknowns); no branch anywhere in the step
 #pragma unroll
             for (int j = 1; j < K3_NB; j++)
 #pragma unroll
                 for (int c = 0; c < j; c++) Lb[j * (j - 1) / 2 + c] = A[(k0 + j) * K3_LD + k0 + c];
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+#pragma unroll
+                for (int c = 0; c < K3_NB; c++) Lu[q][c] = A[(k0 + c) * K3_LD + min(lane + 32 * q, n - 1)];
+#pragma unroll
+            for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
             // x_c = z_c - sum_{j > c} L(k0+j, k0+c) x_j, solved redundantly by every lane
 #pragma unroll
             for (int j = K3_NB - 1; j >= 1; j--)
@@ -421,18 +425,10 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 const int i = lane + 32 * q;
-                double xo = z[q];
+                const double s0 = fma(Lu[q][1], x[1], Lu[q][0] * x[0]), s1 = fma(Lu[q][3], x[3], Lu[q][2] * x[2]);
+                double xo = (i < k0) ? z[q] - (s0 + s1) : z[q];
 #pragma unroll
-                for (int c = 0; c < K3_NB; c++) xo = (q == sl && lane == l0 + c) ? x[c] : xo;
-                if (i < k0) {
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < K3_NB; c += 2) {
-                        s0 = fma(A[(k0 + c) * K3_LD + i], x[c], s0);
-                        s1 = fma(A[(k0 + c + 1) * K3_LD + i], x[c + 1], s1);
-                    }
-                    xo -= (s0 + s1);
-                }
+                for (int c = 0; c < K3_NB; c++) xo = (i == k0 + c) ? x[c] : xo;
                 z[q] = xo;
             }
         }
