@@ -335,6 +335,10 @@ def run_ours(args):
         except Exception as e:
             trace_extra["coarse_tracker"] = {"error": repr(e)}
         big_extra = run_config3(args, torch, stream, flush)
+        try:
+            trace_extra["config4_kitti_loop"] = run_config4(torch)
+        except Exception as e:      # an extra, never the headline
+            trace_extra["config4_kitti_loop"] = {"error": repr(e)}
     if world > 1 and not use_nccl and ctx.peer_error() != 0:
         raise RuntimeError("peer exchange timed out waiting for a rank")
     strong_extra = None
@@ -513,6 +517,87 @@ def run_config3_sharded(torch, dist, stream, flush, rank, world, local_rank):
             "ms_per_step_one_gpu": t_one, "gn_iters_per_s_one_gpu": (1e3 / t_one) if t_one else None,
             "speedup_vs_one_gpu": (t_one / t_sharded) if t_one else None, "peer_error": int(err),
             "def": "same timing rules as the headline (L2 flushed before every step, CUDA events, max over ranks); one_gpu = the whole window on rank 0's GPU in the same job"}
+
+
+def run_config4(torch, n_frames=50):
+    """BASELINE configs[3]: the tracker + BA LOOP on a synthetic 1232x368 (KITTI-cropped, 5 levels) fly-through, one GPU, through the C
+    ABI from host buffers: every frame = raw image H2D + device makeImages + trackNewestCoarse against the newest keyframe; every 5th
+    frame = a keyframe: frame states + the whole sliding window (<= 8 KF x 250 points, every point observed in every other keyframe)
+    H2D, FullSystem::optimize's prologue + 6 Gauss-Newton iterations + linearizeAll(fix), results D2H, and the tracker's new reference
+    (makeCoarseDepthL0 on the device). Host wall clock over the whole loop; the sequence is generated before the clock starts."""
+    from ldso_b200 import capi, seq as seqmod
+    sq = seqmod.make_sequence(n_frames=n_frames)
+    ctx = capi.Context(sq.w, sq.h, sq.levels, device=torch.cuda.current_device())
+    pin = [torch.from_numpy(im).pin_memory().numpy() for im in sq.images]
+    wins = {k: seqmod.window_arrays(sq, sq.window_kfs(k)) for k in range(0, n_frames, sq.kf_every)}
+
+    def loop():
+        ref_k, ref_slot, ref_aff = -1, -1, (0.0, 0.0)
+        n_its = n_tracked = n_ok = 0
+        t_track = t_ba = t_ba_full = 0.0
+        n_full = 0
+        errs = []
+        aff_est = (0.0, 0.0)
+        for k in range(n_frames):
+            is_kf = (k % sq.kf_every) == 0
+            slot = ((k // sq.kf_every) % 8) if is_kf else 8 + (k & 1)
+            ctx.make_images(slot, pin[k])
+            if ref_k >= 0:
+                t0 = time.perf_counter()
+                ctx.tracker_set_frames(ref_aff[0], ref_aff[1], 1.0, slot, 1.0)
+                R0, t0v = sq.rel_pose(ref_k, max(k - 1, ref_k))          # zero-velocity model: the previous frame's pose
+                ok, R, t, a, b, lr, lf = ctx.tracker_track(R0, t0v, aff_est[0], aff_est[1], sq.levels - 1)
+                t_track += time.perf_counter() - t0
+                n_tracked += 1; n_ok += int(ok)
+                Rg, tg = sq.rel_pose(ref_k, k)
+                errs.append(float(np.linalg.norm(t - tg) / max(np.linalg.norm(tg), 1e-9)))
+                aff_est = (a, b)
+            if is_kf:
+                t0 = time.perf_counter()
+                kfs = sq.window_kfs(k)
+                W = wins[k]
+                slots = [((f // sq.kf_every) % 8) for f in kfs]
+                ctx.set_frames(W["Rcw"], W["tcw"], W["state_zero"], W["state"], W["ab_exposure"], W["frame_id"], slots, sq.K)
+                ctx.set_window(W["pt_host"], W["pt_u"], W["pt_v"], W["pt_idepth"], W["pt_idepth_zero"], W["pt_has_prior"], W["pt_color"],
+                               W["pt_weights"], W["res_begin"], W["res_target"])
+                if len(kfs) > 1:
+                    ctx.optimize_begin(want_energy=False)
+                    ctx.gn_iterations(0, 6)
+                    n_its += 6
+                    ctx.linearize_all(True)                       # FullSystem::optimize ends with linearizeAll(true) (FullSystem.cc:843)
+                    res = ctx.residuals_light()
+                    pts = ctx.points()
+                    newest = len(kfs) - 1
+                    m = (W["res_target"] == newest) & (res["state_state"] == capi.RES_IN) & (res["isActive"] == 1)
+                    rp = np.repeat(np.arange(len(W["pt_host"])), np.diff(W["res_begin"]))
+                    ctx.tracker_make_k(*[float(x) for x in sq.K])
+                    ctx.tracker_make_coarse_depth(slot, res["centerProjectedTo"][m], pts["HdiF"][rp[m]])
+                else:                                             # the first keyframe: its own points seed the reference (the initializer's job in LDSO)
+                    ctx.tracker_make_k(*[float(x) for x in sq.K])
+                    ctx.tracker_make_coarse_depth(slot, np.stack([W["pt_u"], W["pt_v"], W["pt_idepth"]], 1), np.full(len(W["pt_u"]), 1e-3, np.float32))
+                ref_k, ref_slot = k, slot
+                ref_aff = (float(sq.aff[k, 0]), float(sq.aff[k, 1]))
+                aff_est = ref_aff
+                t_ba += time.perf_counter() - t0
+                if len(kfs) == sq.window:
+                    t_ba_full += time.perf_counter() - t0; n_full += 1
+        return n_its, n_tracked, n_ok, t_track, t_ba, errs, t_ba_full, n_full
+
+    loop()                                   # warm-up pass (allocations, graph capture for every window topology)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_its, n_tracked, n_ok, t_track, t_ba, errs, t_ba_full, n_full = loop()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ctx.close()
+    n_kf = (n_frames + sq.kf_every - 1) // sq.kf_every
+    return {"frames": n_frames, "keyframes": n_kf, "image": f"{sq.w}x{sq.h}, {sq.levels} levels", "frames_per_s": n_frames / dt,
+            "gn_iters_per_s_in_loop": n_its / dt, "ms_per_tracked_frame": 1e3 * t_track / max(n_tracked, 1), "ms_per_keyframe_ba": 1e3 * t_ba / n_kf,
+            "ms_per_keyframe_ba_full_window": (1e3 * t_ba_full / n_full) if n_full else None,
+            "gn_iterations": n_its, "tracked": n_tracked, "tracking_ok": n_ok, "median_translation_err_rel": float(np.median(errs)) if errs else None,
+            "def": "host wall clock over 50 frames: per frame raw image H2D + device makeImages + trackNewestCoarse (zero-velocity start) against the newest "
+                   "keyframe; every 5th frame a keyframe: frame states + sliding window (<= 8 KF x 250 points) H2D, optimize prologue + 6 GN iterations + "
+                   "linearizeAll(fix), point / residual results D2H, makeCoarseDepthL0 on the device; second pass of the same sequence (first pass warms up)"}
 
 
 def _trace_inputs(win):

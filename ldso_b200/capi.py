@@ -407,6 +407,14 @@ class Context:
             _f(out.get("projectedTo")), _f(out.get("centerProjectedTo"))))
         return out
 
+    def residuals_light(self):
+        """States, activity and centerProjectedTo only (no Jacobians, no per-pixel projections): what setCoarseTrackingRef reads."""
+        nR = self.nR
+        out = dict(state_state=np.zeros(nR, np.uint8), isActive=np.zeros(nR, np.uint8), centerProjectedTo=np.zeros((nR, 3), np.float32))
+        self._chk(self.L.ldso_b200_get_residuals(self.ctx, _b(out["state_state"]), None, None, None, None, _b(out["isActive"]), None, None, None,
+                                                 _f(out["centerProjectedTo"])))
+        return out
+
     def prefetch_results(self):
         self._chk(self.L.ldso_b200_prefetch_results(self.ctx))
 
