@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(K2R_THREADS) k2r_peer_allreduce(DevWindow d, P
         for (int p = 0; p < px.world; p++) {
             if (p == px.rank) continue;
             uint4 *dst = px.inbox[p] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * px.n_doubles + g);
-            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(lo), "r"(e) : "memory");
-            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"((char *) dst + 8), "r"(hi), "r"(e) : "memory");
+            // ONE 16-byte store per slot: a warp's 32 slots leave as four 128-byte NVLink writes instead of 64 8-byte ones. A torn
+            // delivery (8 + 8 bytes) is caught by the reader, which accepts a slot only when BOTH tags carry this exchange's number.
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(e), "r"(hi), "r"(e) : "memory");
         }
         double s = 0.0;
         bool late = false;

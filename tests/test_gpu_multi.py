@@ -17,3 +17,15 @@ def test_sharded_gn_matches_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_CHECK OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_config3_matches_oracle():
+    """BASELINE configs[2]'s 20 000-point window, sharded, against the CPU oracle (not only GPU vs GPU)."""
+    n = min(torch.cuda.device_count(), 8)
+    n = 8 if n >= 8 else (4 if n >= 4 else 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tools", "multi_check.py"), "--config3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_CHECK_CONFIG3 OK" in r.stdout

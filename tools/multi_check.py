@@ -21,10 +21,53 @@ class _DevBuf:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
 
 
+def config3_vs_oracle(rank, world, lr):
+    """BASELINE configs[2]: the 8 KF x 20 000-point window sharded over the job's GPUs (device-side peer exchange), first GN iteration
+    against the CPU ORACLE on rank 0: energy, lastHS, lastbS to 1e-4 (north_star), the update off the gauge direction."""
+    full = synth.make_window(nF=8, pts_per_frame=2500, seed=42)
+    win = synth.shard_window(full, rank, world)
+    ctx = capi.Context(win.w, win.h, win.levels, device=lr)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.load_synth_window(win)
+    counts = [int(np.sum(synth.shard_window(full, r, world).res_target == full.nF - 1)) for r in range(world)]
+    ctx.set_shard(int(np.sum(counts[:rank])), int(np.sum(counts)))
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export())
+    ctx.peer_connect(rank, world, handles)
+    dist.barrier()
+    e0 = ctx.optimize_begin()
+    ctx.gn_iterations(0, 1)
+    sol = ctx.last_solution()
+    e1 = ctx.energy()[0]
+    ok = ctx.peer_error() == 0
+    torch.cuda.synchronize(); dist.barrier()
+    if rank == 0:
+        from tests import oracle_py
+        o = oracle_py.OracleBA(full, threads_mode=0)
+        eo0 = o.optimize_begin()
+        o.gn_iteration(0)
+        so = o.system()
+        P = o.nullspace_projector(); I = np.eye(P.shape[0])
+        eh, eb = rel_err(sol["lastHS"], so["lastHS"]), rel_err(sol["lastbS"], so["lastbS"])
+        ex = rel_err((I - P) @ sol["lastX"], (I - P) @ so["lastX"])
+        eo1 = o.L.oracle_ba_last_energy(o.o)
+        print(f"config3 x{world} vs oracle: energy0 {abs(e0 - eo0) / abs(eo0):.2e} lastHS {eh:.2e} lastbS {eb:.2e} lastX(gauge-proj) {ex:.2e} energy1 {abs(e1 - eo1) / abs(eo1):.2e}")
+        ok &= abs(e0 - eo0) <= 1e-5 * abs(eo0) and eh < 1e-4 and eb < 1e-4 and ex < 1e-4 and abs(e1 - eo1) <= 2e-3 * abs(eo1)
+        print("MULTI_CHECK_CONFIG3", "OK" if ok else "FAIL", "world", world)
+    ctx.close()
+    return ok
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if "--config3" in sys.argv:
+        ok = config3_vs_oracle(rank, world, lr)
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag.item()) == 1 else 1)
     full = synth.make_window(nF=6, pts_per_frame=120, w=320, h=240, seed=17)
     win = synth.shard_window(full, rank, world)
     ctx = capi.Context(win.w, win.h, win.levels, device=lr)
