@@ -419,6 +419,12 @@ public:
     Vec3 t = Vec3(0, 0, 0);
     SE3d() {}
     explicit SE3d(const oracle::SE3 &s) : q(s.q), t(s.t[0], s.t[1], s.t[2]) {}
+    SE3d(const Mat33 &R, const Vec3 &tr) {      // Sophus::SE3d(rotation_matrix, translation) (thirdparty/sophus/se3.hpp)
+        double Rm[9], tv[3];
+        for (int i = 0; i < 3; i++) { tv[i] = tr[i]; for (int j = 0; j < 3; j++) Rm[i * 3 + j] = R(i, j); }
+        const oracle::SE3 s = oracle::SE3::fromRt(Rm, tv);
+        q = s.q; t = Vec3(s.t[0], s.t[1], s.t[2]);
+    }
     oracle::SE3 o() const { oracle::SE3 s; s.q = q; s.t = oracle::V3{{t[0], t[1], t[2]}}; return s; }
     Mat33 rotationMatrix() const { const oracle::M3 R = oracle::qmat(q); Mat33 m; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = R(i, j); return m; }
     Vec3 &translation() { return t; }

@@ -61,12 +61,18 @@ def _d(a):
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_ba.so")
 
 
-def ref_lib():
+DROPIN_LIB = os.path.join(ORACLE_DIR, "_ref", "libdropin_ba.so")
+
+
+def ref_lib(path=None):
     """oracle/_ref/libref_ba.so: the reference's own back-end translation units behind a C interface (oracle/ref_pin/ref_bench.cc).
-    Built by `make -C oracle ref_pin` where /root/reference is mounted; None where it is not there (the built file travels)."""
-    if not os.path.exists(REF_LIB):
+    Built by `make -C oracle ref_pin` where /root/reference is mounted; None where it is not there (the built file travels).
+    path = DROPIN_LIB: the same interface and driver over the product's drop-in translation units (ldso_b200/host/dropin/*.cc:
+    the reference's class declarations, forwarding to libldso_b200.so) instead of the reference's own five."""
+    path = path or REF_LIB
+    if not os.path.exists(path):
         return None
-    L = C.CDLL(REF_LIB)
+    L = C.CDLL(path)
     L.ref_ba_create.restype = C.c_void_p
     for f in ("ref_ba_optimize_begin", "ref_ba_energy", "ref_ba_time_gn"):
         getattr(L, f).restype = C.c_double
@@ -77,8 +83,8 @@ class RefBA:
     """The same window as OracleBA, held by the REFERENCE'S own classes (FrameHessian, PointHessian, PointFrameResidual,
     EnergyFunctional, IndexThreadReduce) compiled from /root/reference; only FullSystem.cc's driver loop is restated around them."""
 
-    def __init__(self, win, multithreaded=True, calib_delta=None):
-        self.L = ref_lib()
+    def __init__(self, win, multithreaded=True, calib_delta=None, lib_path=None):
+        self.L = ref_lib(lib_path)
         if self.L is None:
             raise RuntimeError("oracle/_ref/libref_ba.so is not built (needs the reference tree: make -C oracle ref_pin)")
         self.win = win
@@ -130,8 +136,8 @@ class RefBA:
 class RefTracker:
     """The reference's own CoarseTracker (src/frontend/CoarseTracker.cc in oracle/_ref/libref_ba.so) on a synth.make_track_pair() case."""
 
-    def __init__(self, pair):
-        self.L = ref_lib()
+    def __init__(self, pair, lib_path=None):
+        self.L = ref_lib(lib_path)
         if self.L is None:
             raise RuntimeError("oracle/_ref/libref_ba.so is not built")
         self.L.ref_tracker_create.restype = C.c_void_p
