@@ -223,6 +223,12 @@ typedef struct ldso_b200_fused_io {
     float *res_energy;                               /* [nResiduals] */
 } ldso_b200_fused_io;
 int ldso_b200_optimize_from_host(ldso_b200_ctx *ctx, const ldso_b200_fused_io *io);
+/* The same call split at its only synchronisation point: _submit queues uploads, prologue, iterations and the result read-back on the
+ * context's stream and returns at once (io->image must stay valid until _wait; every other input is consumed before _submit returns);
+ * _wait blocks until they are done and fills the outputs. One process may feed two contexts alternately (submit k+1, wait k): the
+ * uploads of one window then overlap the kernels of the other (FullSystem keeps mapping and tracking on separate threads the same way). */
+int ldso_b200_optimize_from_host_submit(ldso_b200_ctx *ctx, const ldso_b200_fused_io *io);
+int ldso_b200_optimize_from_host_wait(ldso_b200_ctx *ctx, const ldso_b200_fused_io *io);
 
 /* Multi-GPU: points are sharded over ranks (one context per GPU), frames/images replicated. A GN
  * iteration is split around the ONE collective: gn_phase_a(iteration) runs [solve + frame step of `iteration`

@@ -69,7 +69,7 @@ SYMBOLS = [
     "ldso_b200_download_frame_level", "ldso_b200_set_window", "ldso_b200_set_frames", "ldso_b200_set_marg_prior",
     "ldso_b200_get_marg_prior", "ldso_b200_linearize_all", "ldso_b200_apply_res", "ldso_b200_backup_state",
     "ldso_b200_solve_system", "ldso_b200_get_system", "ldso_b200_do_step", "ldso_b200_marginalize_points", "ldso_b200_marginalize_frame", "ldso_b200_calc_energies", "ldso_b200_accumulate", "ldso_b200_select_activation", "ldso_b200_init_calc_res", "ldso_b200_optimize_begin",
-    "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
+    "ldso_b200_gn_iterations", "ldso_b200_optimize_from_host", "ldso_b200_optimize_from_host_submit", "ldso_b200_optimize_from_host_wait", "ldso_b200_reduce_buffer", "ldso_b200_set_shard", "ldso_b200_gn_phase_a",
     "ldso_b200_gn_phase_b", "ldso_b200_peer_export", "ldso_b200_peer_connect", "ldso_b200_peer_error", "ldso_b200_prefetch_results", "ldso_b200_get_energy", "ldso_b200_get_last_solution", "ldso_b200_get_points",
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
     "ldso_b200_trace_immature", "ldso_b200_optimize_immature", "ldso_b200_tracker_make_k",
@@ -604,8 +604,25 @@ class StepIO:
                                                     "pt_color", "pt_weights", "res_begin", "res_target")))
         self.d2h_bytes = sum(v.nbytes for v in o.values())
 
+    def submit(self, iteration=0, n_iterations=1):
+        """ldso_b200_optimize_from_host_submit: queue the whole step, do not wait."""
+        self._prep(iteration, n_iterations)
+        self.ctx._chk(self.L.ldso_b200_optimize_from_host_submit(self.h, C.byref(self._io)))
+
+    def wait(self):
+        """ldso_b200_optimize_from_host_wait: block until the submitted step is done, outputs filled."""
+        self.ctx._chk(self.L.ldso_b200_optimize_from_host_wait(self.h, C.byref(self._io)))
+        self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
+        return self.out
+
     def fused(self, iteration=0, n_iterations=1):
         """The same step as upload() + step() + download(), as ONE C-ABI call (ldso_b200_optimize_from_host)."""
+        self._prep(iteration, n_iterations)
+        self.ctx._chk(self.L.ldso_b200_optimize_from_host(self.h, C.byref(self._io)))
+        self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
+        return self.out
+
+    def _prep(self, iteration, n_iterations):
         if not hasattr(self, "_io"):
             io = self._io = FusedIOC()
             o = self.out
@@ -618,9 +635,6 @@ class StepIO:
             io.pt_idepth = _f(o["idepth"]); io.pt_step = _f(o["step"]); io.pt_HdiF = _f(o["HdiF"])
             io.res_state = _b(o["state_state"]); io.res_new_state = _b(o["state_NewState"]); io.res_energy = _f(o["state_energy"])
         self._io.first_iteration = int(iteration); self._io.n_iterations = int(n_iterations)
-        self.ctx._chk(self.L.ldso_b200_optimize_from_host(self.h, C.byref(self._io)))
-        self.ctx.nF, self.ctx.nP, self.ctx.nR = self.nF, self.nP, self.nR
-        return self.out
 
     def upload(self):
         """newest keyframe's raw image (+ device makeImages), frame states, the whole window"""

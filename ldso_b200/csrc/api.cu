@@ -227,7 +227,7 @@ extern "C" ldso_b200_ctx *ldso_b200_create(int device, int w, int h, int pyr_lev
     c->sb.lastHS = p; p += nn; c->sb.lastbS = p; p += MAXN; c->sb.lastX = p; p += MAXN;
     c->sb.b_A = p; p += MAXN; c->sb.b_sc = p; p += MAXN; c->sb.bM = p; p += MAXN;
     c->sb.dg = p; p += MAXN; c->sb.bFg = p; p += MAXN;
-    ok = cudaMallocHost(&c->sol_host, sizeof(double) * (nn + 2 * MAXN)) == cudaSuccess;
+    ok = cudaMallocHost(&c->sol_host, sizeof(double) * (nn + 3 * MAXN)) == cudaSuccess;      // [lastHS | lastbS | lastX | scalars]
     if (!ok) { fprintf(stderr, "ldso_b200: pinned allocation failed\n"); delete c; return nullptr; }
     c->ktime = getenv("LDSO_B200_KTIME") != nullptr;
     c->use_graph = !c->ktime && getenv("LDSO_B200_NO_GRAPH") == nullptr;
@@ -1420,7 +1420,11 @@ extern "C" int ldso_b200_get_points(ldso_b200_ctx *c, float *idepth, float *idep
 extern "C" int ldso_b200_get_residuals(ldso_b200_ctx *c, uint8_t *state_state, uint8_t *state_NewState, float *state_energy,
                                        float *state_NewEnergy, float *state_NewEnergyWithOutlier, uint8_t *isActive, float *JpJdF8, float *J74,
                                        float *projectedTo16, float *centerProjectedTo3);
-extern "C" int ldso_b200_optimize_from_host(ldso_b200_ctx *c, const ldso_b200_fused_io *io) {
+// Queue one whole FullSystem::optimize (uploads, prologue, n iterations, result read-back into pinned staging) on the context's
+// stream and return WITHOUT waiting. The caller's buffers (io->image, frames, window arrays) are consumed before this returns except
+// io->image, which must stay valid until the matching _wait. Two contexts fed alternately overlap one window's uploads with the
+// other's kernels (bench.py's pipelined end-to-end leg); a single context just splits the call at its only synchronisation point.
+extern "C" int ldso_b200_optimize_from_host_submit(ldso_b200_ctx *c, const ldso_b200_fused_io *io) {
     if (!c || !io || !io->frames || !io->window || !io->calib_value_scaled || !io->calib_value_zero) return LDSO_B200_ERR_ARG;
     if (io->n_iterations < 0) return c->fail(LDSO_B200_ERR_ARG, "negative iteration count");
     // the image first: 1.2 MB over PCIe, in flight while the host packs the frame states and the window
@@ -1430,16 +1434,31 @@ extern "C" int ldso_b200_optimize_from_host(ldso_b200_ctx *c, const ldso_b200_fu
     RET_IF(ldso_b200_optimize_begin(c, nullptr));
     if (io->n_iterations > 0) RET_IF(ldso_b200_gn_iterations(c, io->first_iteration, io->n_iterations));
     RET_IF(ldso_b200_prefetch_results(c));
-    // the two scalars ride behind the prefetch; one wait covers everything (and frees the caller's image buffer)
-    if (io->energy) CUDA_CHECK_RET(c, cudaMemcpyAsync(io->energy, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (io->canbreak) CUDA_CHECK_RET(c, cudaMemcpyAsync(io->canbreak, &c->ws_dev->canbreak, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    // the two scalars ride behind the prefetch into pinned staging (sol_host has MAXN spare doubles behind lastX)
+    const size_t nn = (size_t) MAXN * MAXN;
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sol_host + nn + 2 * MAXN, &c->ws_dev->energy, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(c->sol_host + nn + 2 * MAXN + 1, &c->ws_dev->canbreak, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_optimize_from_host_wait(ldso_b200_ctx *c, const ldso_b200_fused_io *io) {
+    if (!c || !io) return LDSO_B200_ERR_ARG;
+    cudaSetDevice(c->device);
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));       // one wait covers everything (and frees the caller's image buffer)
+    const size_t nn = (size_t) MAXN * MAXN;
+    if (io->energy) *io->energy = c->sol_host[nn + 2 * MAXN];
+    if (io->canbreak) memcpy(io->canbreak, c->sol_host + nn + 2 * MAXN + 1, sizeof(int));
     if (io->lastHS || io->lastbS || io->lastX) RET_IF(ldso_b200_get_last_solution(c, io->lastHS, io->lastbS, io->lastX));
     if (io->pt_idepth || io->pt_step || io->pt_HdiF)
         RET_IF(ldso_b200_get_points(c, io->pt_idepth, nullptr, io->pt_step, io->pt_HdiF, nullptr, nullptr, nullptr, nullptr));
     if (io->res_state || io->res_new_state || io->res_energy)
         RET_IF(ldso_b200_get_residuals(c, io->res_state, io->res_new_state, io->res_energy, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
     return LDSO_B200_OK;
+}
+
+extern "C" int ldso_b200_optimize_from_host(ldso_b200_ctx *c, const ldso_b200_fused_io *io) {
+    RET_IF(ldso_b200_optimize_from_host_submit(c, io));
+    return ldso_b200_optimize_from_host_wait(c, io);
 }
 
 extern "C" int ldso_b200_reduce_buffer(ldso_b200_ctx *c, void **buf_dev, size_t *n_doubles) {

@@ -486,6 +486,14 @@ def test_stepio_prefetch_matches_getters(small_win):
     fused = {k: v.copy() for k, v in io.fused(0, 1).items()}
     for k in out:
         assert np.array_equal(fused[k], out[k]), k
+    # ... and so does the split form (ldso_b200_optimize_from_host_submit / _wait), also with a second context in flight between the two
+    other = _ctx(win)
+    io2 = capi.StepIO(other, win)
+    io.submit(0, 1); io2.submit(0, 1)
+    split, split2 = {k: v.copy() for k, v in io.wait().items()}, io2.wait()
+    for k in out:
+        assert np.array_equal(split[k], out[k]) and np.array_equal(split2[k], out[k]), k
+    other.close()
     # a launch after the prefetch invalidates it: the getters must return the newer state
     io.upload(); io.step(0)
     ctx.gn_iterations(1, 1)
