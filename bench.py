@@ -687,6 +687,28 @@ def run_tracker():
     t0 = time.perf_counter()
     ro = ot.track(I, z, 0.0, 0.0, pair.levels - 1)
     dto = time.perf_counter() - t0
+    # FullSystem::trackNewCoarse's hypothesis loop as one launch: identity + the 26 small rotations (rotDelta = 0.02, FullSystem.cc:300-330)
+    rd = 0.02
+    hyp = [np.zeros(3)] + [np.array(v, float) * rd for v in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1), (1, 1, 0), (0, 1, 1), (1, 0, 1),
+                                                                  (-1, 1, 0), (0, -1, 1), (-1, 0, 1), (1, -1, 0), (0, 1, -1), (1, 0, -1), (-1, -1, 0), (0, -1, -1), (-1, 0, -1),
+                                                                  (-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1))]
+    Rs = np.stack([synth.so3_exp(h) for h in hyp]); ts = np.zeros((len(hyp), 3)); af = np.zeros((len(hyp), 2), np.float32)
+    for _ in range(3):
+        bres = ctx.tracker_track_batch(Rs, ts, af, pair.levels - 1)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        bres = ctx.tracker_track_batch(Rs, ts, af, pair.levels - 1)
+    dtb = (time.perf_counter() - t0) / reps
+    # one calcRes + calcGSSSE evaluation at level 0 against the HBM roofline (pc_n (16 + 48) + 624 bytes)
+    n0 = len(ot.pc(0)[0])
+    for _ in range(5):
+        ctx.tracker_eval(0, pair.R_true, pair.t_true, 0.0, 0.0, 20.0)
+    t0 = time.perf_counter()
+    for _ in range(100):
+        ctx.tracker_eval(0, pair.R_true, pair.t_true, 0.0, 0.0, 20.0)
+    dte = (time.perf_counter() - t0) / 100
+    hbm_peak, _ = peaks()
+    eval_bytes = n0 * 64 + 624
     ctx.close()
     ref_ms = None
     try:                                   # the reference's own CoarseTracker.cc (oracle/_ref/libref_ba.so), when it is there
@@ -694,7 +716,12 @@ def run_tracker():
             ref_ms = 1e3 * oracle_py.RefTracker(pair).track(I, z, 0.0, 0.0, pair.levels - 1, reps=10)[5]
     except Exception:
         ref_ms = None
-    return {"ms_per_track": 1e3 * dt, "tracks_per_s": 1.0 / dt, "reference_ms_per_track_1core": ref_ms, "cpu_port_ms_per_track_1core": 1e3 * dto,
+    return {"ms_per_track": 1e3 * dt, "tracks_per_s": 1.0 / dt,
+            "batch": {"hypotheses": len(hyp), "ms_per_batch": 1e3 * dtb, "ms_per_hypothesis": 1e3 * dtb / len(hyp), "ok": int(bres["ok"].sum()),
+                      "def": "ldso_b200_tracker_track_batch: FullSystem::trackNewCoarse's 27 starting poses (identity + 26 rotations of 0.02 rad) in one launch, one CTA each, host arrays in/out"},
+            "roofline": {"bound": "hbm", "kernel": "k_trk_eval (calcRes + calcGSSSE, level 0)", "algorithmic_bytes_per_launch": eval_bytes, "pc_n": n0,
+                         "us_per_call_through_c_abi": 1e6 * dte, "achieved": eval_bytes / dte / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": eval_bytes / dte / 1e9 / hbm_peak,
+                         "note": "one evaluation moves ~0.6 MB: launch + synchronise + 624-byte read-back dominate; the call is latency-bound by construction"}, "reference_ms_per_track_1core": ref_ms, "cpu_port_ms_per_track_1core": 1e3 * dto,
             "calcRes_evaluations": int(ro[-1]),
             "converged": bool(r[0]), "same_outcome_as_cpu_port": bool(r[0] == ro[0]),
             "translation_err_rel": float(np.linalg.norm(r[2] - pair.t_true) / max(np.linalg.norm(pair.t_true), 1e-12)),

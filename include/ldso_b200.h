@@ -373,6 +373,14 @@ int ldso_b200_tracker_eval(ldso_b200_ctx *ctx, int lvl, const double R[9], const
 int ldso_b200_tracker_track(ldso_b200_ctx *ctx, double R[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl,
                             const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3],
                             int *ok);
+/* FullSystem::trackNewCoarse's hypothesis loop (src/frontend/FullSystem.cc:290-357: constant / double / half / zero motion and
+ * 26 x 3 small rotations, up to 83 calls of CoarseTracker::trackNewestCoarse per frame) as ONE launch: n <= 128 starting poses
+ * (R9_each[n][9] row-major refToNew rotations, t3_each[n][3], aff2_each[n][2]), each tracked through all levels by its own CTA,
+ * without abort thresholds. Per hypothesis: the refined pose / brightness, lastResiduals[5], lastFlowIndicators[3], the bool the
+ * reference returns. The caller applies the reference's acceptance rule (:337-356) to the results. Output arrays other than
+ * ok_each may be NULL. */
+int ldso_b200_tracker_track_batch(ldso_b200_ctx *ctx, int n, const double *R9_each, const double *t3_each, const float *aff2_each, int coarsestLvl,
+                                  double *R9_out, double *t3_out, float *aff2_out, double *lastResiduals5_each, double *lastFlow3_each, int *ok_each);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,7 @@ SYMBOLS = [
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
     "ldso_b200_trace_immature", "ldso_b200_optimize_immature", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
-    "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track",
+    "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track", "ldso_b200_tracker_track_batch",
 ]
 
 _lib = None
@@ -555,6 +555,20 @@ class Context:
         self._chk(self.L.ldso_b200_tracker_track(self.ctx, _d(R), _d(t), C.byref(a), C.byref(b), int(coarsest), _d(mr), _d(lr),
                                                  _d(lf), C.byref(ok)))
         return bool(ok.value), R, t, a.value, b.value, lr, lf
+
+
+    def _tracker_track_batch(self, R, t, aff, coarsest):
+        """n hypotheses side by side: R (n,3,3), t (n,3), aff (n,2) -> dict of per-hypothesis results."""
+        R = np.ascontiguousarray(R, np.float64); t = np.ascontiguousarray(t, np.float64); aff = np.ascontiguousarray(aff, np.float32)
+        n = R.shape[0]
+        out = dict(R=np.zeros((n, 3, 3)), t=np.zeros((n, 3)), aff=np.zeros((n, 2), np.float32), lastResiduals=np.zeros((n, 5)),
+                   lastFlowIndicators=np.zeros((n, 3)), ok=np.zeros(n, np.int32))
+        self._chk(self.L.ldso_b200_tracker_track_batch(self.ctx, n, _d(R), _d(t), _f(aff), int(coarsest), _d(out["R"]), _d(out["t"]), _f(out["aff"]),
+                                                       _d(out["lastResiduals"]), _d(out["lastFlowIndicators"]), _i(out["ok"])))
+        return out
+
+
+Context.tracker_track_batch = Context._tracker_track_batch
 
 
 class StepIO:

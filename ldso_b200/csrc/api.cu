@@ -1861,7 +1861,7 @@ extern "C" int ldso_b200_tracker_track(ldso_b200_ctx *c, double R[9], double t[3
     A.aff_a = *aff_a; A.aff_b = *aff_b;
     A.coarsestLvl = coarsestLvl;
     for (int i = 0; i < 5; i++) A.minResForAbort[i] = minResForAbort ? minResForAbort[i] : NAN;
-    k_trk_track<<<1, TRK_TRACK_THREADS, 0, c->stream>>>(A, c->trk_track_out);
+    k_trk_track<<<1, TRK_TRACK_THREADS, 0, c->stream>>>(A, c->trk_track_out, nullptr);
     LAUNCH_CHECK(c);
     TrkTrackOut o;
     CUDA_CHECK_RET(c, cudaMemcpyAsync(&o, c->trk_track_out, sizeof(o), cudaMemcpyDeviceToHost, c->stream));
@@ -1871,6 +1871,50 @@ extern "C" int ldso_b200_tracker_track(ldso_b200_ctx *c, double R[9], double t[3
     if (lastResiduals) memcpy(lastResiduals, o.lastResiduals, 40);
     if (lastFlowIndicators) memcpy(lastFlowIndicators, o.lastFlowIndicators, 24);
     *ok = o.ok;
+    return LDSO_B200_OK;
+}
+
+// FullSystem::trackNewCoarse's hypothesis loop (FullSystem.cc:290-357) as ONE launch: n starting poses (the constant-motion,
+// double-motion, half-motion, zero-motion guesses and the 26 x 3 small rotations), each tracked by its own CTA through all levels,
+// all without an abort threshold (the reference passes the best residuals so far as minResForAbort to the later tries: a pruning
+// of work that a parallel batch does not need). The caller applies the reference's acceptance rule to the n results.
+extern "C" int ldso_b200_tracker_track_batch(ldso_b200_ctx *c, int n, const double *R9_each, const double *t3_each, const float *aff2_each, int coarsestLvl,
+                                             double *R9_out, double *t3_out, float *aff2_out, double *lastResiduals5_each, double *lastFlow3_each, int *ok_each) {
+    if (!c || n <= 0 || !R9_each || !t3_each || !aff2_each || !ok_each) return LDSO_B200_ERR_ARG;
+    if (n > 128) return c->fail(LDSO_B200_ERR_ARG, "at most 128 hypotheses per batch");
+    if (coarsestLvl < 0 || coarsestLvl >= 5 || coarsestLvl >= c->levels) return c->fail(LDSO_B200_ERR_ARG, "coarsestLvl out of range");
+    if (c->new_slot < 0) return c->fail(LDSO_B200_ERR_STATE, "tracker_set_frames not called");
+    cudaSetDevice(c->device);
+    TrkTrackArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int l = 0; l < c->levels; l++) fill_level(c, l, A.L[l]);
+    A.nLevels = c->levels;
+    A.ref_aff_a = c->ref_aff_a; A.ref_aff_b = c->ref_aff_b; A.ref_exposure = c->ref_exposure; A.new_exposure = c->new_exposure;
+    A.huberTH = c->S.huberTH; A.coarseCutoffTH = c->S.coarseCutoffTH; A.affineOptModeA = c->S.affineOptModeA; A.affineOptModeB = c->S.affineOptModeB;
+    A.coarsestLvl = coarsestLvl;
+    for (int i = 0; i < 5; i++) A.minResForAbort[i] = NAN;
+    RET_IF(trace_reserve(c, (sizeof(TrkHypothesis) + sizeof(TrkTrackOut)) * (size_t) n + 64));
+    TrkHypothesis *dh = (TrkHypothesis *) c->trace_buf;
+    TrkTrackOut *dout = (TrkTrackOut *) (dh + n);
+    std::vector<TrkHypothesis> hh(n);
+    for (int i = 0; i < n; i++) {
+        memcpy(hh[i].R, R9_each + 9 * i, 72); memcpy(hh[i].t, t3_each + 3 * i, 24);
+        hh[i].aff_a = aff2_each[2 * i]; hh[i].aff_b = aff2_each[2 * i + 1];
+    }
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(dh, hh.data(), sizeof(TrkHypothesis) * n, cudaMemcpyHostToDevice, c->stream));
+    k_trk_track<<<n, TRK_TRACK_THREADS, 0, c->stream>>>(A, dout, dh);
+    LAUNCH_CHECK(c);
+    std::vector<TrkTrackOut> ho(n);
+    CUDA_CHECK_RET(c, cudaMemcpyAsync(ho.data(), dout, sizeof(TrkTrackOut) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) {
+        if (R9_out) memcpy(R9_out + 9 * i, ho[i].R, 72);
+        if (t3_out) memcpy(t3_out + 3 * i, ho[i].t, 24);
+        if (aff2_out) { aff2_out[2 * i] = ho[i].aff_a; aff2_out[2 * i + 1] = ho[i].aff_b; }
+        if (lastResiduals5_each) memcpy(lastResiduals5_each + 5 * i, ho[i].lastResiduals, 40);
+        if (lastFlow3_each) memcpy(lastFlow3_each + 3 * i, ho[i].lastFlowIndicators, 24);
+        ok_each[i] = ho[i].ok;
+    }
     return LDSO_B200_OK;
 }
 

@@ -256,8 +256,22 @@ __device__ void trk_make_pose(const TrkTrackArgs &A, const TrkLevel &L, const do
     P.maxEnergy = 2 * A.huberTH * cutoffTH - A.huberTH * A.huberTH;
 }
 
+// one starting pose of a batched track (FullSystem::trackNewCoarse tries up to 3 + 27 x 3 of them per frame, FullSystem.cc:290-357)
+struct TrkHypothesis {
+    double R[9], t[3];
+    float aff_a, aff_b;
+};
 #define TRK_TRACK_THREADS 512
-__global__ void __launch_bounds__(TRK_TRACK_THREADS) k_trk_track(TrkTrackArgs A, TrkTrackOut *out) {
+// One CTA runs one whole coarse-to-fine LM loop. hyp == nullptr: the pose in A, grid 1. hyp != nullptr: CTA b starts from hyp[b] and
+// writes out[b] -- the hypotheses of a frame tracked side by side, one SM each.
+__global__ void __launch_bounds__(TRK_TRACK_THREADS) k_trk_track(TrkTrackArgs A, TrkTrackOut *out, const TrkHypothesis *hyp) {
+    if (hyp != nullptr) {
+        const TrkHypothesis &h = hyp[blockIdx.x];
+        for (int i = 0; i < 9; i++) A.R[i] = h.R[i];
+        for (int i = 0; i < 3; i++) A.t[i] = h.t[i];
+        A.aff_a = h.aff_a; A.aff_b = h.aff_b;
+        out += blockIdx.x;
+    }
     __shared__ float s_part[(TRK_TRACK_THREADS / 32) * TRK_NACC];
     __shared__ double s_sum[TRK_NACC];
     __shared__ TrkShared S;

@@ -112,3 +112,24 @@ def test_kitti_geometry_tracker():
     oko, Ro, to, ao, bo_, lro, lfo, ne = ot.track(np.eye(3), np.zeros(3), 0.0, 0.0, pair.levels - 1)
     _same_track((okg, Rg, tg, ag, bg_, lrg, lfg), (oko, Ro, to, ao, bo_, lro, lfo), res_tol=3e-3)
     ctx.close()
+
+
+def test_track_batch_matches_single_tracks():
+    """ldso_b200_tracker_track_batch (one CTA per starting pose, FullSystem::trackNewCoarse's hypothesis loop in one launch): every
+    hypothesis' result is bit-identical to the single-pose call from the same start (same kernel, same arithmetic order)."""
+    pair = synth.make_track_pair(w=320, h=240, n_pts=400, seed=7)
+    ot, ctx = _setup(pair)
+    rng = np.random.default_rng(3)
+    n = 9
+    Rs = np.stack([synth.so3_exp(rng.normal(0, 0.01, 3)) for _ in range(n)]); Rs[0] = np.eye(3)
+    ts = rng.normal(0, 0.02, (n, 3)); ts[0] = 0
+    aff = np.zeros((n, 2), np.float32)
+    b = ctx.tracker_track_batch(Rs, ts, aff, pair.levels - 1)
+    for i in range(n):
+        ok, R, t, a, bb, lr, lf = ctx.tracker_track(Rs[i], ts[i], 0.0, 0.0, pair.levels - 1)
+        assert bool(b["ok"][i]) == ok
+        assert np.array_equal(b["R"][i], R) and np.array_equal(b["t"][i], t)
+        assert b["aff"][i, 0] == np.float32(a) and b["aff"][i, 1] == np.float32(bb)
+        assert np.array_equal(b["lastResiduals"][i], lr, equal_nan=True) and np.array_equal(b["lastFlowIndicators"][i], lf)
+    assert b["ok"].sum() >= 1
+    ctx.close()
