@@ -373,6 +373,18 @@ int ldso_b200_tracker_eval(ldso_b200_ctx *ctx, int lvl, const double R[9], const
 int ldso_b200_tracker_track(ldso_b200_ctx *ctx, double R[9], double t[3], float *aff_a, float *aff_b, int coarsestLvl,
                             const double minResForAbort[5], double lastResiduals[5], double lastFlowIndicators[3],
                             int *ok);
+/* Map::runPoseGraphOptimization (src/Map.cc:75-165; SURVEY 8f rank 4, BASELINE configs[4]): g2o Gauss-Newton over VertexSim3 /
+ * EdgeSim3 (include/internal/PR.h:57-76,151-179: error = log(measurement^-1 * v1 * v2^-1), oplus: estimate = Sim3::exp(update) *
+ * estimate) with g2o's numeric Jacobians (thirdparty/g2o/g2o/core/base_binary_edge.hpp:131-148, delta 1e-9), `iterations` rounds
+ * (Map.cc:141: 25), vertex `fixed` held (Map.cc:109-111). Poses q4[nV][4] / t3[nV][3] (in / out): Sophus' Sim3 storage, quaternion
+ * (w, x, y, z) with norm = scale + translation; edges ei / ej [nE] vertex indices, measurement mq4 / mt3, information info49[nE][49]
+ * row-major. Each round's normal equations are solved by block-Jacobi preconditioned conjugate gradients to the relative residual
+ * pcg_tol (at most pcg_max_iter iterations). chi2_out[iterations + 1]: sum e^T O e before every round and after the last (may be
+ * NULL); *pcg_iterations_total: CG iterations spent (may be NULL). */
+int ldso_b200_posegraph_optimize(ldso_b200_ctx *ctx, int nV, double *q4, double *t3, int nE, const int32_t *ei, const int32_t *ej,
+                                 const double *mq4, const double *mt3, const double *info49, int fixed, int iterations,
+                                 double pcg_tol, int pcg_max_iter, double *chi2_out, int *pcg_iterations_total);
+
 /* FullSystem::trackNewCoarse's hypothesis loop (src/frontend/FullSystem.cc:290-357: constant / double / half / zero motion and
  * 26 x 3 small rotations, up to 83 calls of CoarseTracker::trackNewestCoarse per frame) as ONE launch: n <= 128 starting poses
  * (R9_each[n][9] row-major refToNew rotations, t3_each[n][3], aff2_each[n][2]), each tracked through all levels by its own CTA,

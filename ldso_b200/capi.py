@@ -74,7 +74,7 @@ SYMBOLS = [
     "ldso_b200_get_residuals", "ldso_b200_get_frames", "ldso_b200_get_nullspace_projector", "ldso_b200_immature_init",
     "ldso_b200_trace_immature", "ldso_b200_optimize_immature", "ldso_b200_tracker_make_k",
     "ldso_b200_tracker_set_ref_level", "ldso_b200_tracker_make_coarse_depth", "ldso_b200_tracker_get_ref_level",
-    "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track", "ldso_b200_tracker_track_batch",
+    "ldso_b200_tracker_set_frames", "ldso_b200_tracker_eval", "ldso_b200_tracker_track", "ldso_b200_tracker_track_batch", "ldso_b200_posegraph_optimize",
 ]
 
 _lib = None
@@ -568,7 +568,19 @@ class Context:
         return out
 
 
+    def _posegraph_optimize(self, q, t, ei, ej, mq, mt, info, fixed, iterations=25, pcg_tol=1e-10, pcg_max_iter=2000):
+        """Sim(3) pose graph Gauss-Newton on the device; returns (q, t, chi2[iterations + 1], CG iterations spent)."""
+        q = np.ascontiguousarray(q, np.float64).copy(); t = np.ascontiguousarray(t, np.float64).copy()
+        ei = np.ascontiguousarray(ei, np.int32); ej = np.ascontiguousarray(ej, np.int32)
+        mq = np.ascontiguousarray(mq, np.float64); mt = np.ascontiguousarray(mt, np.float64); info = np.ascontiguousarray(info, np.float64)
+        chi = np.zeros(iterations + 1); ncg = C.c_int()
+        self._chk(self.L.ldso_b200_posegraph_optimize(self.ctx, len(q), _d(q), _d(t), len(ei), _i(ei), _i(ej), _d(mq), _d(mt), _d(info), int(fixed),
+                                                      int(iterations), C.c_double(pcg_tol), int(pcg_max_iter), _d(chi), C.byref(ncg)))
+        return q, t, chi, ncg.value
+
+
 Context.tracker_track_batch = Context._tracker_track_batch
+Context.posegraph_optimize = Context._posegraph_optimize
 
 
 class StepIO:
