@@ -336,6 +336,10 @@ def run_ours(args):
             trace_extra["coarse_tracker"] = {"error": repr(e)}
         big_extra = run_config3(args, torch, stream, flush)
         try:
+            trace_extra["config5_posegraph"] = run_posegraph()
+        except Exception as e:
+            trace_extra["config5_posegraph"] = {"error": repr(e)}
+        try:
             trace_extra["config4_kitti_loop"] = run_config4(torch)
         except Exception as e:      # an extra, never the headline
             trace_extra["config4_kitti_loop"] = {"error": repr(e)}
@@ -623,6 +627,31 @@ def run_config4(torch, n_frames=50):
             "def": "host wall clock over 50 frames: per frame raw image H2D + device makeImages + trackNewestCoarse (zero-velocity start) against the newest "
                    "keyframe; every 5th frame a keyframe: frame states + sliding window (<= 8 KF x 250 points) H2D, optimize prologue + 6 GN iterations + "
                    "linearizeAll(fix), point / residual results D2H, makeCoarseDepthL0 on the device; second pass of the same sequence (first pass warms up)"}
+
+
+def run_posegraph():
+    """BASELINE configs[4] (not the headline): Sim(3) pose-graph optimisation, 5000 keyframes / 10 000 loop edges (+ the odometry edges
+    to the previous two keyframes), 25 Gauss-Newton rounds as Map.cc:141, through the C ABI from host arrays (uploads and read-back
+    inside the timed call). CPU side: the oracle's linearisation of one round (numeric Jacobians, vectorised numpy, one core); its
+    sparse direct solve of this graph does not finish within minutes (the random loop edges fill the factor in), so only that part is
+    timed and said so."""
+    from ldso_b200 import capi
+    from oracle import posegraph as pg
+    g = pg.make_graph(5000, 10000, seed=0)
+    ctx = capi.Context(64, 64, 1)
+    ctx.posegraph_optimize(g["q"], g["t"], g["ei"], g["ej"], g["mq"], g["mt"], g["info"], g["fixed"], iterations=2)      # warm-up
+    t0 = time.perf_counter()
+    q, t, chi, ncg = ctx.posegraph_optimize(g["q"], g["t"], g["ei"], g["ej"], g["mq"], g["mt"], g["info"], g["fixed"], iterations=25, pcg_tol=1e-10)
+    dt = time.perf_counter() - t0
+    ctx.close()
+    t0 = time.perf_counter()
+    pg.linearize(g["q"], g["t"], g["ei"], g["ej"], g["mq"], g["mt"], g["info"])
+    dto = time.perf_counter() - t0
+    return {"keyframes": 5000, "edges": int(len(g["ei"])), "gn_rounds": 25, "seconds": dt, "ms_per_round": 1e3 * dt / 25, "cg_iterations_total": int(ncg),
+            "chi2_first": float(chi[0]), "chi2_last": float(chi[-1]), "max_translation_err_vs_truth": float(np.abs(t - g["gt"]).max()),
+            "cpu_oracle_linearize_ms_per_round_1core": 1e3 * dto,
+            "def": "ldso_b200_posegraph_optimize: warp-per-edge numeric-Jacobian linearisation + block-Jacobi PCG (relative residual 1e-10) + oplus, 25 rounds, host arrays in/out; "
+                   "cpu figure = the oracle's linearisation alone (its sparse direct solve of this graph does not finish within 10 minutes)"}
 
 
 def _trace_inputs(win):

@@ -44,6 +44,7 @@ struct ldso_b200_ctx {
     std::vector<void *> win_allocs;
     std::vector<void *> derived_allocs;      // work items, partials, reduced buffer: rebuilt by build_derived
     bool have_window = false, have_frames = false, derived_dirty = true;
+    bool select_pending = false;     // the newest frame's energy threshold of the last fused iteration has not been computed yet (flush_select)
     bool has_lin = false;            // the window holds linearized (isLinearized) residuals: solve_system accumulates HA + HL in one pass
     std::vector<unsigned char> h_scratch_bytes;     // select_activation's map read-back
     unsigned char *actsel_pin = nullptr; size_t actsel_pin_cap = 0;      // its pinned staging block
@@ -633,7 +634,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
         memcpy(D.evalR, f.evalR, sizeof(D.evalR)); memcpy(D.evalT, f.evalT, sizeof(D.evalT));
         memcpy(D.state, f.state, sizeof(D.state)); memcpy(D.state_zero, f.state_zero, sizeof(D.state_zero));
         memcpy(D.state_backup, f.state, sizeof(D.state));
-        D.frameEnergyTH = f.frameEnergyTH; D.ab_exposure = f.ab_exposure; D.frame_id = f.frame_id; D.slot = f.image_slot;
+        D.frameEnergyTH = f.frameEnergyTH; W.frameEnergyTH[i] = f.frameEnergyTH; D.ab_exposure = f.ab_exposure; D.frame_id = f.frame_id; D.slot = f.image_slot;
         // FrameHessian::getPrior (FrameHessian.h:125-150), takeData (FrameHessian.cc:108-112)
         double p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (f.frame_id == 0) {
@@ -743,7 +744,7 @@ extern "C" int ldso_b200_set_frames(ldso_b200_ctx *c, int nFrames, const ldso_b2
     }
     k_frames_refresh<<<1, 128, 0, c->stream>>>(c->ws_dev);
     LAUNCH_CHECK(c);
-    c->solve_ready = false; c->restitch_ok = false;
+    c->solve_ready = false; c->restitch_ok = false; c->select_pending = false;
     c->have_frames = true;
     if (prev_nF != nF) c->derived_dirty = true;    // work items / newest-frame slots depend on nF only
     return LDSO_B200_OK;
@@ -818,6 +819,7 @@ static int launch_k2b(ldso_b200_ctx *c, int do_stitch, int do_select, int do_ass
     c->kt_end();
     LAUNCH_CHECK(c);
     if (do_stitch) c->solve_ready = do_assemble != 0;
+    if (do_select) c->select_pending = false;
     return LDSO_B200_OK;
 }
 static int launch_k2r(ldso_b200_ctx *c) {
@@ -835,7 +837,9 @@ static int ensure_solve_ready(ldso_b200_ctx *c) {
 }
 static int launch_k3(ldso_b200_ctx *c, int flags) {
     c->kt_begin("k3");
-    launch_loop_kernel(c, k3_solve_step, dim3(1), dim3(K3_THREADS), K3_SMEM_BYTES, c->ws_dev, c->sb, flags, c->iteration_dev);
+    const double *sel_red = c->peers_connected ? c->red_sum : c->d.red;
+    launch_loop_kernel(c, k3_solve_step, dim3((flags & K3F_SELECT) ? 2 : 1), dim3(K3_THREADS), K3_SMEM_BYTES, c->ws_dev, c->sb, flags, c->iteration_dev,
+                       sel_red, std::max(c->d.newest_total, 0), c->d.dbg);
     c->kt_end();
     LAUNCH_CHECK(c);
     return LDSO_B200_OK;
@@ -851,11 +855,13 @@ static int clear_select(ldso_b200_ctx *c) {   // multi-GPU: slots owned by other
 }
 
 static int trace_reserve(ldso_b200_ctx *c, size_t bytes);      // device scratch shared by the one-shot entry points
+static int flush_select(ldso_b200_ctx *c);                      // run a deferred setNewFrameEnergyTH select (fused loop)
 extern "C" int ldso_b200_linearize_all(ldso_b200_ctx *c, int fixLinearization, int flags, double *energy_out) {
     if (!c) return LDSO_B200_ERR_ARG;
     cudaSetDevice(c->device);
     RET_IF(build_derived(c));
     (void) flags;   // the piecewise path always keeps the full Jacobian: solve_system rebuilds its records from it
+    RET_IF(flush_select(c));
     int f = K1F_LINEARIZE | K1F_STORE_J;
     if (fixLinearization) f |= K1F_APPLY_RES;
     RET_IF(clear_select(c));
@@ -1002,6 +1008,7 @@ extern "C" int ldso_b200_marginalize_points(ldso_b200_ctx *c, int n, const int32
     }
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->pt_sel_dev, sel.data(), c->d.nP, cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
+    RET_IF(flush_select(c));
     RET_IF(launch_k1(c, K1F_LINEARIZE | K1F_STORE_J | K1F_APPLY_RES | K1F_RESET_OOB, c->pt_sel_dev));
     if (c->d.nR > 0) {
         k_fix_linearization<<<(c->d.nR + 255) / 256, 256, 0, c->stream>>>(c->d, c->ws_dev, c->pt_sel_dev);
@@ -1355,13 +1362,25 @@ extern "C" int ldso_b200_optimize_begin(ldso_b200_ctx *c, double *energy_out) {
     return LDSO_B200_OK;
 }
 
+// One fused Gauss-Newton iteration: K3 (solve + step, and -- second CTA -- the energy-threshold select of the PREVIOUS linearisation)
+// -> K1 -> K2a -> [K2r] -> K2b (stitch + assemble). The select of the linearisation this body ends with stays pending: the next
+// body's K3 runs it, or flush_select() when something else needs the threshold first.
 static int launch_gn_body(ldso_b200_ctx *c) {
     struct Scope { ldso_b200_ctx *c; Scope(ldso_b200_ctx *c_) : c(c_) { c->pdl_now = true; } ~Scope() { c->pdl_now = false; } } scope(c);
-    RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
+    RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP | K3F_SELECT));
     RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
     RET_IF(launch_k2a(c, 1));
     if (c->peers_connected) RET_IF(launch_k2r(c));
-    RET_IF(launch_k2b(c, 1, 1, 1));
+    RET_IF(launch_k2b(c, 1, 0, 1));
+    c->select_pending = true;
+    return LDSO_B200_OK;
+}
+static int flush_select(ldso_b200_ctx *c) {
+    if (!c->select_pending) return LDSO_B200_OK;
+    c->select_pending = false;
+    const bool sr = c->solve_ready;
+    RET_IF(launch_k2b(c, 0, 1, 0));
+    c->solve_ready = sr;
     return LDSO_B200_OK;
 }
 
@@ -1406,6 +1425,7 @@ extern "C" int ldso_b200_gn_iterations(ldso_b200_ctx *c, int first_iteration, in
         for (int i = 0; i < n_iterations; i++) {
             CUDA_CHECK_RET(c, cudaGraphLaunch(c->gn_graph, c->stream));
             c->launches += c->peers_connected ? 5 : 4;
+            c->select_pending = true;
             { c->mirror_valid = false; c->results_inflight = false; c->sol_valid = false; c->mirror_full_valid = false; }
         }
         return LDSO_B200_OK;
@@ -1492,7 +1512,7 @@ extern "C" int ldso_b200_peer_export(ldso_b200_ctx *c, void *ipc_handle_64) {
     const int n = RED_SELECT + std::max(c->d.newest_total, 0);
     const int nch = (n + K2R_THREADS - 1) / K2R_THREADS;
     if (c->peers_connected || c->peer_local) return c->fail(LDSO_B200_ERR_STATE, "peer exchange already set up for this context");
-    const size_t bytes = sizeof(uint4) * 2 * K2R_MAX_PEERS * (size_t) n;      // the inbox: [2 parities][8 senders][n] 16-byte slots
+    const size_t bytes = sizeof(uint4) * (2 * K2R_MAX_PEERS + 2) * (size_t) n;      // the inbox: [2 parities][8 senders][n] 16-byte slots + the all-gather region [2][n]
     CUDA_CHECK_RET(c, cudaMalloc(&c->peer_local, bytes));
     CUDA_CHECK_RET(c, cudaMalloc(&c->peer_words, sizeof(int) * 4));
     CUDA_CHECK_RET(c, cudaMalloc(&c->red_sum, sizeof(double) * ((size_t) n + 16)));
@@ -1553,6 +1573,7 @@ extern "C" int ldso_b200_gn_phase_a(ldso_b200_ctx *c, int iteration) {
         RET_IF(launch_k1(c, K1_FUSED | K1F_RESET_OOB));
     } else {
         if (!c->solve_ready) return c->fail(LDSO_B200_ERR_STATE, "gn_phase_a(iteration >= 0) needs a preceding gn_phase_b");
+        RET_IF(flush_select(c));
         RET_IF(set_iteration(c, iteration));
         RET_IF(launch_k3(c, K3F_BACKUP | K3F_SOLVE | K3F_STEP));
         RET_IF(launch_k1(c, K1_FUSED | K1F_APPLY_STEP));
@@ -1662,6 +1683,7 @@ extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *s
                                     double *adHost64, double *adTarget64, float *adHTdeltaF8, double *calib_value4) {
     if (!c || !c->have_frames) return LDSO_B200_ERR_STATE;
     cudaSetDevice(c->device);
+    if (c->have_window && !c->derived_dirty) RET_IF(flush_select(c));
     CUDA_CHECK_RET(c, cudaMemcpyAsync(c->ws_host, c->ws_dev, sizeof(WinState), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK_RET(c, cudaStreamSynchronize(c->stream));
     const WinState &W = *c->ws_host;
@@ -1669,7 +1691,7 @@ extern "C" int ldso_b200_get_frames(ldso_b200_ctx *c, double *state10, double *s
     for (int h = 0; h < nF; h++) {
         if (state10) memcpy(state10 + 10 * h, W.fr[h].state, 80);
         if (step10) memcpy(step10 + 10 * h, W.fr[h].step, 80);
-        if (frameEnergyTH) frameEnergyTH[h] = W.fr[h].frameEnergyTH;
+        if (frameEnergyTH) frameEnergyTH[h] = W.frameEnergyTH[h];
     }
     for (int q = 0; q < nF * nF; q++) {
         if (precalc40) {

@@ -151,7 +151,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
         int t = i >> 5, k = i & 31;
         s_pair[i] = (t < nF) ? ((const float *) &ws->pair[host + nF * t])[k] : 0.f;
     }
-    if (tid < MAXF) s_thr[tid] = (tid < nF) ? ws->fr[tid].frameEnergyTH : 0.f;
+    if (tid < MAXF) s_thr[tid] = (tid < nF) ? ws->frameEnergyTH[tid] : 0.f;
     if (tid == 0) {
         s_cal[0] = ws->calib.fxl; s_cal[1] = ws->calib.fyl; s_cal[2] = ws->calib.cxl; s_cal[3] = ws->calib.cyl;
         s_cal[4] = ws->calib.fxli; s_cal[5] = ws->calib.fyli; s_cal[6] = ws->wM3G; s_cal[7] = ws->hM3G;

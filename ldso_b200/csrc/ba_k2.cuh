@@ -95,12 +95,32 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
 #define K2R_MAX_PEERS 8
 struct PeerExchange {
     int rank, world, n_doubles, n_chunks;
-    uint4 *inbox[K2R_MAX_PEERS];          // rank r's inbox (peer-mapped for r != rank): [2][K2R_MAX_PEERS][n_doubles]
+    uint4 *inbox[K2R_MAX_PEERS];          // rank r's inbox (peer-mapped for r != rank): [2][K2R_MAX_PEERS][n_doubles] (reduce-scatter / one-shot) + [2][n_doubles] (all-gather)
     int *epoch;                           // local: number of exchanges completed
     unsigned *done;                       // local: CTAs finished in this launch
     int *error;                           // local: set when a peer's data never arrived (bounded spin)
     double *out;                          // local: the summed buffer
 };
+__device__ __forceinline__ void k2r_push(uint4 *dst, double v, unsigned e) {
+    // ONE 16-byte store per slot: a warp's 32 slots leave as four 128-byte NVLink writes instead of 64 8-byte ones. A torn
+    // delivery (8 + 8 bytes) is caught by the reader, which accepts a slot only when BOTH tags carry this exchange's number.
+    const unsigned lo = (unsigned) __double2loint(v), hi = (unsigned) __double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(e), "r"(hi), "r"(e) : "memory");
+}
+__device__ __forceinline__ double k2r_poll(const uint4 *src, unsigned e, bool &late) {
+    unsigned a, f0, c, f1;
+    int spins = 0;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f0), "=r"(c), "=r"(f1) : "l"(src) : "memory");
+    } while ((f0 != e || f1 != e) && ++spins < (1 << 24));          // ~ seconds; never hang the GPU
+    if (f0 != e || f1 != e) late = true;
+    return __hiloint2double((int) c, (int) a);
+}
+// world <= 2: one-shot exchange (every rank pushes its whole buffer to the peer, sums in rank order).
+// world  > 2: reduce-scatter + all-gather inside the same kernel: element g belongs to rank g / len; every rank pushes its value of g
+// to the OWNER only; the owner's thread g sums the contributions in rank order and pushes the total to everybody (second inbox
+// region). Per rank 2 n (world-1)/world slots leave instead of n (world-1): 4x fewer bytes at 8 GPUs for one more NVLink hop.
+// Every rank ends with the same bits in both schemes. A thread only ever waits for the thread of the same element on another rank.
 __global__ void __launch_bounds__(K2R_THREADS) k2r_peer_allreduce(DevWindow d, PeerExchange px) {
     pdl_launch_dependents();
     pdl_wait();
@@ -111,31 +131,28 @@ __global__ void __launch_bounds__(K2R_THREADS) k2r_peer_allreduce(DevWindow d, P
     const unsigned e = (unsigned) s_epoch;
     const int par = (int) (e & 1u);
     const int g = blockIdx.x * K2R_THREADS + tid;
-    if (g < px.n_doubles) {
+    const int n = px.n_doubles;
+    if (g < n) {
         const double mine = d.red[g];
-        const unsigned lo = (unsigned) __double2loint(mine), hi = (unsigned) __double2hiint(mine);
-        for (int p = 0; p < px.world; p++) {
-            if (p == px.rank) continue;
-            uint4 *dst = px.inbox[p] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * px.n_doubles + g);
-            // ONE 16-byte store per slot: a warp's 32 slots leave as four 128-byte NVLink writes instead of 64 8-byte ones. A torn
-            // delivery (8 + 8 bytes) is caught by the reader, which accepts a slot only when BOTH tags carry this exchange's number.
-            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(e), "r"(hi), "r"(e) : "memory");
-        }
-        double s = 0.0;
         bool late = false;
-        for (int r = 0; r < px.world; r++) {
-            double v = mine;
-            if (r != px.rank) {
-                const uint4 *src = px.inbox[px.rank] + ((size_t) (par * K2R_MAX_PEERS + r) * px.n_doubles + g);
-                unsigned a, f0, c, f1;
-                int spins = 0;
-                do {
-                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f0), "=r"(c), "=r"(f1) : "l"(src) : "memory");
-                } while ((f0 != e || f1 != e) && ++spins < (1 << 24));          // ~ seconds; never hang the GPU
-                if (f0 != e || f1 != e) late = true;
-                v = __hiloint2double((int) c, (int) a);
+        double s = 0.0;
+        if (px.world <= 2) {
+            for (int p = 0; p < px.world; p++)
+                if (p != px.rank) k2r_push(px.inbox[p] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * n + g), mine, e);
+            for (int r = 0; r < px.world; r++)
+                s += (r == px.rank) ? mine : k2r_poll(px.inbox[px.rank] + ((size_t) (par * K2R_MAX_PEERS + r) * n + g), e, late);
+        } else {
+            const int len = (n + px.world - 1) / px.world, owner = g / len;
+            const size_t regB = (size_t) 2 * K2R_MAX_PEERS * n;           // the all-gather inbox region behind the reduce-scatter one
+            if (owner != px.rank) {
+                k2r_push(px.inbox[owner] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * n + g), mine, e);
+                s = k2r_poll(px.inbox[px.rank] + regB + (size_t) par * n + g, e, late);
+            } else {
+                for (int r = 0; r < px.world; r++)
+                    s += (r == px.rank) ? mine : k2r_poll(px.inbox[px.rank] + ((size_t) (par * K2R_MAX_PEERS + r) * n + g), e, late);
+                for (int p = 0; p < px.world; p++)
+                    if (p != px.rank) k2r_push(px.inbox[p] + regB + (size_t) par * n + g, s, e);
             }
-            s += v;
         }
         px.out[g] = s;
         if (late) *px.error = 1;
@@ -186,6 +203,122 @@ __device__ __forceinline__ double top_elem(const double *red, int h, int t, int 
     return red[h * PART_USED + PART_TOP + t * 96 + packed13(r13, c13)];
 }
 
+// FullSystem::setNewFrameEnergyTH (FullSystem.cc:1762-1793): the exact k-th order statistic of the newest frame's residual energies
+// (radix select, keys in shared memory). Called by all K2B_THREADS threads of ONE CTA: the last CTA of k2b_stitch (prologue, piecewise
+// API) or the second CTA of k3_solve_step, where it runs beside the solver instead of in front of it (the threshold is first read by
+// the next linearisation).
+__device__ void k2_select_body(const double *red, int N, WinState *ws, double *sk2, long long *dbg) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned hist_w[K2B_THREADS / 32][256];     // per-warp histograms (no cross-warp contention on the hot bins)
+    __shared__ unsigned sel_prefix, sel_k, sel_count;
+    const int tid = threadIdx.x, nF = ws->nF;
+
+        PROF_ONLY(if (tid == 0) dbg[12] = clock64();)
+                // settings (constant): requested now, consumed after the passes
+        const float set_thn = ws->S.frameEnergyTHN, set_fac = ws->S.frameEnergyTHFacMedian, set_cw = ws->S.frameEnergyTHConstWeight,
+                    set_ow = ws->S.overallEnergyTHWeight;
+        const double *vals = red + RED_SELECT;
+        unsigned *skey = (unsigned *) sk2;            // float bit patterns of the valid energies (0x80000000 = excluded)
+        const bool insm = N <= K2B_SELCAP;
+        if (tid == 0) { sel_count = 0; sel_prefix = 0; }
+        __syncthreads();
+        unsigned cnt = 0;
+        for (int i0 = tid; i0 < N; i0 += 8 * K2B_THREADS) {      // 8 independent loads per trip (the values come from L2 / HBM)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * K2B_THREADS; v[u] = (i < N) ? vals[i] : -1.0; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * K2B_THREADS;
+                const bool ok = v[u] >= 0.0;
+                if (insm && i < N) skey[i] = ok ? __float_as_uint((float) v[u]) : 0x80000000u;
+                cnt += ok;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((tid & 31) == 0) atomicAdd(&sel_count, cnt);
+        __syncthreads();
+        const unsigned m = sel_count;
+        float th;
+        if (m == 0) {
+            th = 12 * 12 * LDSO_B200_PATTERN;
+        } else {
+            if (tid == 0) sel_k = (unsigned) (int) (set_thn * (float) m);
+            __syncthreads();
+            for (int pass = 3; pass >= 0; pass--) {
+                for (int i = tid; i < 256 * (K2B_THREADS / 32); i += K2B_THREADS) (&hist_w[0][0])[i] = 0;
+                __syncthreads();
+                const unsigned pref = sel_prefix;
+                const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
+                // energies of one frame share their leading bytes: aggregate equal bins inside the warp first
+                // (one shared-memory atomic per distinct bin per warp instead of 32 serialised ones)
+                for (int i0 = tid; i0 < ((N + 31) & ~31); i0 += 4 * K2B_THREADS) {     // 4 independent keys per trip
+                    unsigned key[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = i0 + u * K2B_THREADS;
+                        key[u] = 0x80000000u;
+                        if (i < N) {
+                            if (insm) key[u] = skey[i];
+                            else { const double v = vals[i]; key[u] = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const bool act = (key[u] != 0x80000000u) && ((key[u] & himask) == pref);
+                        const unsigned bin = act ? ((key[u] >> (8 * pass)) & 0xffu) : 256u;
+                        // equal bins are aggregated inside the warp first (one atomic per distinct bin), on the warp's own histogram
+                        const unsigned mm = __match_any_sync(0xffffffffu, bin);
+                        if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist_w[tid >> 5][bin], (unsigned) __popc(mm));
+                    }
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    unsigned t = 0;
+#pragma unroll
+                    for (int wv = 0; wv < K2B_THREADS / 32; wv++) t += hist_w[wv][tid];
+                    hist[tid] = t;
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    // warp 0: lane owns 8 consecutive bins; find the bin holding rank sel_k
+                    unsigned hq[8], loc = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { hq[q] = hist[8 * tid + q]; loc += hq[q]; }
+                    unsigned incl = loc;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (tid >= o) incl += v;
+                    }
+                    const unsigned excl = incl - loc;
+                    const unsigned k0 = sel_k;
+                    const bool mine = (k0 >= excl) && (k0 < incl);
+                    __syncwarp();
+                    if (mine) {
+                        unsigned k = k0 - excl, bin = 8 * tid;
+                        bool found = false;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (!found) {
+                                if (k < hq[q]) found = true;
+                                else { k -= hq[q]; bin++; }
+                            }
+                        }
+                        sel_k = k;
+                        sel_prefix = pref | (bin << (8 * pass));
+                    }
+                }
+                __syncthreads();
+            }
+            const float nthElement = sqrtf(__uint_as_float(sel_prefix));
+            th = nthElement * set_fac;
+            th = 26.0f * set_cw + th * (1 - set_cw);
+            th = th * th;
+            th *= set_ow * set_ow;
+        }
+        if (tid == 0) { ws->frameEnergyTH[nF - 1] = th; PROF_ONLY(dbg[13] = clock64();) }
+    }
+
 #define K2B_LAMBDA 1e-5        // SOLVER_FIX_LAMBDA (EnergyFunctional.cc:243)
 __device__ __forceinline__ double k2b_delta(const WinState *ws, int c) {      // getStitchedDeltaF (EnergyFunctional.h:178-184)
     return (c < CPARS) ? (double) ws->calib.cDeltaF[c] : ws->fr[(c - CPARS) >> 3].delta[(c - CPARS) & 7];
@@ -196,10 +329,6 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     const int tid = threadIdx.x;
     const double *red = d.red;
     const int nBlocks = nF * nF;
-    __shared__ unsigned hist[256];
-    __shared__ unsigned hist_w[K2B_THREADS / 32][256];     // per-warp histograms of the select CTA (no cross-warp contention on the hot bins)
-    __shared__ unsigned sel_prefix, sel_k, sel_count;
-
     if ((int) blockIdx.x < nBlocks) {
         if (!do_stitch) return;
         // ---- 8x8 frame block (a,b) of H_A and H_sc. All operands (adjoints, D blocks, top blocks) are first staged
@@ -531,112 +660,8 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     }
     if (!do_select) return;
     {
-        PROF_ONLY(if (tid == 0) d.dbg[12] = clock64();)
-        const int N = d.newest_total;
-        // settings (constant): requested now, consumed after the passes
-        const float set_thn = ws->S.frameEnergyTHN, set_fac = ws->S.frameEnergyTHFacMedian, set_cw = ws->S.frameEnergyTHConstWeight,
-                    set_ow = ws->S.overallEnergyTHWeight;
-        const double *vals = red + RED_SELECT;
         extern __shared__ double sk2[];
-        unsigned *skey = (unsigned *) sk2;            // float bit patterns of the valid energies (0x80000000 = excluded)
-        const bool insm = N <= K2B_SELCAP;
-        if (tid == 0) { sel_count = 0; sel_prefix = 0; }
-        __syncthreads();
-        unsigned cnt = 0;
-        for (int i0 = tid; i0 < N; i0 += 8 * K2B_THREADS) {      // 8 independent loads per trip (the values come from L2 / HBM)
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { const int i = i0 + u * K2B_THREADS; v[u] = (i < N) ? vals[i] : -1.0; }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * K2B_THREADS;
-                const bool ok = v[u] >= 0.0;
-                if (insm && i < N) skey[i] = ok ? __float_as_uint((float) v[u]) : 0x80000000u;
-                cnt += ok;
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if ((tid & 31) == 0) atomicAdd(&sel_count, cnt);
-        __syncthreads();
-        const unsigned m = sel_count;
-        float th;
-        if (m == 0) {
-            th = 12 * 12 * LDSO_B200_PATTERN;
-        } else {
-            if (tid == 0) sel_k = (unsigned) (int) (set_thn * (float) m);
-            __syncthreads();
-            for (int pass = 3; pass >= 0; pass--) {
-                for (int i = tid; i < 256 * (K2B_THREADS / 32); i += K2B_THREADS) (&hist_w[0][0])[i] = 0;
-                __syncthreads();
-                const unsigned pref = sel_prefix;
-                const unsigned himask = (pass == 3) ? 0u : (0xffffffffu << (8 * (pass + 1)));
-                // energies of one frame share their leading bytes: aggregate equal bins inside the warp first
-                // (one shared-memory atomic per distinct bin per warp instead of 32 serialised ones)
-                for (int i0 = tid; i0 < ((N + 31) & ~31); i0 += 4 * K2B_THREADS) {     // 4 independent keys per trip
-                    unsigned key[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int i = i0 + u * K2B_THREADS;
-                        key[u] = 0x80000000u;
-                        if (i < N) {
-                            if (insm) key[u] = skey[i];
-                            else { const double v = vals[i]; key[u] = (v >= 0.0) ? __float_as_uint((float) v) : 0x80000000u; }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const bool act = (key[u] != 0x80000000u) && ((key[u] & himask) == pref);
-                        const unsigned bin = act ? ((key[u] >> (8 * pass)) & 0xffu) : 256u;
-                        // equal bins are aggregated inside the warp first (one atomic per distinct bin), on the warp's own histogram
-                        const unsigned mm = __match_any_sync(0xffffffffu, bin);
-                        if (act && (tid & 31) == __ffs(mm) - 1) atomicAdd(&hist_w[tid >> 5][bin], (unsigned) __popc(mm));
-                    }
-                }
-                __syncthreads();
-                if (tid < 256) {
-                    unsigned t = 0;
-#pragma unroll
-                    for (int wv = 0; wv < K2B_THREADS / 32; wv++) t += hist_w[wv][tid];
-                    hist[tid] = t;
-                }
-                __syncthreads();
-                if (tid < 32) {
-                    // warp 0: lane owns 8 consecutive bins; find the bin holding rank sel_k
-                    unsigned hq[8], loc = 0;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) { hq[q] = hist[8 * tid + q]; loc += hq[q]; }
-                    unsigned incl = loc;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (tid >= o) incl += v;
-                    }
-                    const unsigned excl = incl - loc;
-                    const unsigned k0 = sel_k;
-                    const bool mine = (k0 >= excl) && (k0 < incl);
-                    __syncwarp();
-                    if (mine) {
-                        unsigned k = k0 - excl, bin = 8 * tid;
-                        bool found = false;
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            if (!found) {
-                                if (k < hq[q]) found = true;
-                                else { k -= hq[q]; bin++; }
-                            }
-                        }
-                        sel_k = k;
-                        sel_prefix = pref | (bin << (8 * pass));
-                    }
-                }
-                __syncthreads();
-            }
-            const float nthElement = sqrtf(__uint_as_float(sel_prefix));
-            th = nthElement * set_fac;
-            th = 26.0f * set_cw + th * (1 - set_cw);
-            th = th * th;
-            th *= set_ow * set_ow;
-        }
-        if (tid == 0) { ws->fr[nF - 1].frameEnergyTH = th; PROF_ONLY(d.dbg[13] = clock64();) }
+        k2_select_body(red, d.newest_total, ws, sk2, d.dbg);
     }
     if (tid == 0) dbg_span(&ws->dbg[18], true);
 }

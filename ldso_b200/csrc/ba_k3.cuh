@@ -18,6 +18,7 @@
 #define K3F_SOLVE 1
 #define K3F_STEP 2
 #define K3F_BACKUP 4
+#define K3F_SELECT 8       // grid 2: CTA 1 runs setNewFrameEnergyTH's order-statistic select beside the solver
 #define K3_THREADS 512
 #define K3_NP MAXN               // n = 8 nF + 4 is a multiple of the block size 4: no padding
 #define K3_LD (K3_NP + 1)        // odd leading dimension: a column of the matrix touches every bank once
@@ -443,8 +444,17 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
     PROF_ONLY(if (tid == 0) prof[2] = clk_fenced();)
 }
 
-__global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev) {
+__global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveBufs sb, int flags, int *iteration_dev, const double *sel_red, int sel_n,
+                                                            long long *sel_dbg) {
     extern __shared__ double sm3[];
+    if (blockIdx.x == 1) {
+        // FullSystem::setNewFrameEnergyTH for the linearisation that produced the system being solved: its result is first read by the
+        // NEXT linearisation, so it runs beside the solver (another SM) instead of in front of it inside the stitch kernel
+        pdl_launch_dependents();
+        pdl_wait();
+        k2_select_body(sel_red, sel_n, ws, sm3, sel_dbg);
+        return;
+    }
     const K3Smem m = k3_carve(sm3);
     K3Frames *S = m.S;
     const int nF = ws->nF, n = ws->n, tid = threadIdx.x;

@@ -128,6 +128,7 @@ struct WinState {
     int canbreak;
     int iteration_count;
     float sumNID, numID;
+    float frameEnergyTH[MAXF];       // FrameHessian::frameEnergyTH of the window frames (the newest one is moved by setNewFrameEnergyTH on the device)
     long long dbg[64];               // clock64() phase stamps of the last K3 (development aid)
 };
 
