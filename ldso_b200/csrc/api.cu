@@ -1548,6 +1548,7 @@ extern "C" int ldso_b200_peer_connect(ldso_b200_ctx *c, int rank, int world, con
         c->px.inbox[r] = (uint4 *) base;
     }
     c->px.rank = rank; c->px.world = world;
+    c->px.two_hop = (world > 2 && getenv("LDSO_B200_K2R_ONESHOT") == nullptr) ? 1 : 0;
     c->px.epoch = c->peer_words; c->px.done = (unsigned *) (c->peer_words + 1); c->px.error = c->peer_words + 2;
     c->px.out = c->red_sum;
     c->peers_connected = true;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
 #define K2R_MAX_PEERS 8
 struct PeerExchange {
     int rank, world, n_doubles, n_chunks;
+    int two_hop;                          // reduce-scatter + all-gather (world > 2) instead of the one-shot push
     uint4 *inbox[K2R_MAX_PEERS];          // rank r's inbox (peer-mapped for r != rank): [2][K2R_MAX_PEERS][n_doubles] (reduce-scatter / one-shot) + [2][n_doubles] (all-gather)
     int *epoch;                           // local: number of exchanges completed
     unsigned *done;                       // local: CTAs finished in this launch
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(K2R_THREADS) k2r_peer_allreduce(DevWindow d, P
         const double mine = d.red[g];
         bool late = false;
         double s = 0.0;
-        if (px.world <= 2) {
+        if (!px.two_hop) {
             for (int p = 0; p < px.world; p++)
                 if (p != px.rank) k2r_push(px.inbox[p] + ((size_t) (par * K2R_MAX_PEERS + px.rank) * n + g), mine, e);
             for (int r = 0; r < px.world; r++)
