@@ -209,7 +209,7 @@ k1_linearize_accumulate(DevWindow d, const WinState *__restrict__ ws, int flags,
             }
             float step = pf_step;
             if (ngood == 0) step = 0.f;
-            else if (isfinite(b)) step = -b * pf_hdi;
+            else if (isfinite(b)) step = -b * pf_hdi;          // non-finite b: this point keeps its step (the reference leaves its whole thread range, :544)
             d.pt_step[p] = step;
             const float backup = idepth;                       // FullSystem::backupState
             d.pt_idepth_backup[p] = backup;

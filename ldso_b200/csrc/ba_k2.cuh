@@ -22,9 +22,17 @@ __device__ __forceinline__ void dbg_span(long long *slot_min_max, bool end) {
 #define K2A_SLICES (K2A_THREADS / 64)     // 8 threads share one output element, each folds every 8th work item
 __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState *ws, int full, int multi) {
     pdl_launch_dependents();
+    // before pdl_wait: what is constant for the window (frame count, the hosts' work-item ranges) -- two dependent L2 round trips
+    // that would otherwise sit between the wait and the first partial load
+    const int nF = ws->nF;
+    const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int g = blockIdx.x * 64 + el;
+    int pre_i0 = 0, pre_i1 = 0;
+    if (full && blockIdx.x != gridDim.x - 1 && g < MAXF * PART_USED && g / PART_USED < nF) {
+        pre_i0 = d.host_item_begin[g / PART_USED]; pre_i1 = d.host_item_begin[g / PART_USED + 1];
+    }
     pdl_wait();                      // everything below reads what K1 just wrote
     if (threadIdx.x == 0) dbg_span(&ws->dbg[16], false);
-    const int nF = ws->nF;
     if (blockIdx.x == gridDim.x - 1) {
         // stats: warp w (<4) reduces stat w over all items
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -48,13 +56,11 @@ __global__ void __launch_bounds__(K2A_THREADS) k2a_reduce(DevWindow d, WinState 
     // 64 consecutive output elements per CTA; slice q of 8 folds items i0+q, i0+q+8, ... with all of its loads in
     // flight at once (the fold is a chain of L2 round trips otherwise); the 8 slice sums are added in a fixed order.
     __shared__ double part[K2A_SLICES][64];
-    const int el = threadIdx.x & 63, q = threadIdx.x >> 6;
-    const int g = blockIdx.x * 64 + el;
     double s = 0.0;
     if (g < MAXF * PART_USED) {
         const int h = g / PART_USED, e = g - h * PART_USED;
         if (h < nF) {
-            const int i0 = d.host_item_begin[h], i1 = d.host_item_begin[h + 1];
+            const int i0 = pre_i0, i1 = pre_i1;
             const float *p = d.partials + (size_t) (i0 + q) * PART_STRIDE + e;
             int i = i0 + q;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -334,7 +340,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         if (!do_stitch) return;
         // ---- 8x8 frame block (a,b) of H_A and H_sc. All operands (adjoints, D blocks, top blocks) are first staged
         // in shared memory with one burst of independent loads; the triple products then run from shared memory.
-        extern __shared__ double sk2[];
+        extern __shared__ __align__(16) double sk2[];
         double *sAHa = sk2;                    // [nF] adHost[a + nF*j]
         double *sATa = sAHa + MAXF * K2B_MS;   // [nF] adTarget[i + nF*a]
         double *sATb = sATa + MAXF * K2B_MS;   // [nF] adTarget[i + nF*b]
@@ -392,14 +398,40 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[9] = clock64();)
         // -------- stage A: left products. Every thread runs short (8-term) chains only; sums over frames are kept as
         // independent partial chains and folded in a fixed order.
-        for (int o = tid; o < nF * 64; o += K2B_THREADS) {         // Z_i = AT_ia * D_i[a,b]
+        // On a diagonal block the 64-term X_k products dominate (32 k of the 53 k FMAs) and, one output per thread, they are bound by
+        // shared-memory load issue (2 loads per FMA): warps 0-3 compute them in 1x4 register tiles (3 loads -- one of them 16 bytes --
+        // per 4 FMAs, same summation order as before), the other 12 warps do the short products meanwhile.
+        const int lt0 = diag ? tid - 128 : tid, ltn = diag ? K2B_THREADS - 128 : K2B_THREADS;      // thread index / count for the short products
+        if (diag && tid < 128) {                                   // X_k = sum_j AH_aj * D_a[j,k]
+            const int k = tid >> 4, r = (tid >> 1) & 7, c0 = (tid & 1) * 4;
+            if (k < nF) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int j = 0; j < nF; j++) {
+                    double sj[4] = {0.0, 0.0, 0.0, 0.0};
+                    const double *Ar = sAHa + K2B_M(j, r, 0), *Dm = sD4 + K2B_M(j + nF * k, 0, c0);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const double av = Ar[i];
+                        const double2 d01 = *(const double2 *) (Dm + i * K2B_RS), d23 = *(const double2 *) (Dm + i * K2B_RS + 2);
+                        sj[0] += av * d01.x; sj[1] += av * d01.y; sj[2] += av * d23.x; sj[3] += av * d23.y;
+                    }
+                    if (j == 0) { acc[0] = sj[0]; acc[1] = sj[1]; acc[2] = sj[2]; acc[3] = sj[3]; }
+                    else { acc[0] += sj[0]; acc[1] += sj[1]; acc[2] += sj[2]; acc[3] += sj[3]; }
+                }
+                double *Xo = sX + K2B_M(k, r, c0);
+                *(double2 *) Xo = make_double2(acc[0], acc[1]);
+                *(double2 *) (Xo + 2) = make_double2(acc[2], acc[3]);
+            }
+        }
+        if (lt0 >= 0) {
+        for (int o = lt0; o < nF * 64; o += ltn) {         // Z_i = AT_ia * D_i[a,b]
             const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < 8; i++) s += sATa[K2B_M(q, r, i)] * sD1[K2B_M(q, i, c)];
             sZ[K2B_M(q, r, c)] = s;
         }
-        for (int u = tid; u < 2 * MAXF * 64; u += K2B_THREADS) {   // per-frame terms of Y2 and Y3
+        for (int u = lt0; u < 2 * MAXF * 64; u += ltn) {   // per-frame terms of Y2 and Y3
             const int which = u / (MAXF * 64), k = (u >> 6) & (MAXF - 1), e = u & 63, r = e >> 3, c = e & 7;
             double s = 0.0;
             if (k < nF) {
@@ -414,24 +446,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             sP[u] = s;
         }
         if (diag) {
-            for (int o = tid; o < nF * 64; o += K2B_THREADS) {     // X_k = sum_j AH_aj * D_a[j,k]
-                const int k = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
-                double acc[MAXF];
-#pragma unroll
-                for (int j = 0; j < MAXF; j++) {
-                    double s = 0.0;
-                    if (j < nF) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) s += sAHa[K2B_M(j, r, i)] * sD4[K2B_M(j + nF * k, i, c)];
-                    }
-                    acc[j] = s;
-                }
-                double s = acc[0];
-#pragma unroll
-                for (int j = 1; j < MAXF; j++) s += acc[j];
-                sX[K2B_M(k, r, c)] = s;
-            }
-            for (int o = tid; o < 2 * nF * 64; o += K2B_THREADS) { // T_q = L_q * M_q, L = AH_aq (q<nF) or AT_(q-nF)a
+            for (int o = lt0; o < 2 * nF * 64; o += ltn) { // T_q = L_q * M_q, L = AH_aq (q<nF) or AT_(q-nF)a
                 const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
                 const double *Lm = (q < nF) ? (sAHa + q * K2B_MS) : (sATa + (q - nF) * K2B_MS);
                 double s = 0.0;
@@ -446,6 +461,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
 #pragma unroll
             for (int i = 0; i < 8; i++) s += Lm[r * K2B_RS + i] * sM[K2B_M(q, i, c)];
             sT[K2B_M(q, r, c)] = s;
+        }
         }
         __syncthreads();
         if (tid < 128) {                                             // fold the per-frame terms of Y2 / Y3
@@ -661,7 +677,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
     }
     if (!do_select) return;
     {
-        extern __shared__ double sk2[];
+        extern __shared__ __align__(16) double sk2[];
         k2_select_body(red, d.newest_total, ws, sk2, d.dbg);
     }
     if (tid == 0) dbg_span(&ws->dbg[18], true);

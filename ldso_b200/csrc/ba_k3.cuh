@@ -4,12 +4,10 @@
 //
 // Everything here is a serial dependency chain on a 68x68 system, so the design goal is latency, not throughput:
 //   * the frame/calib records are staged in shared memory once (one global round trip instead of dozens);
-//   * the LDL^T is BLOCKED (8 columns per step): a step is [8x8 diagonal block by one thread, in registers] ->
-//     [panel rows, one thread per row] -> [trailing update, all threads], 3 barriers per 8 columns instead of
-//     2 barriers per column;
-//   * Eigen's LDLT pivots on the largest remaining |diagonal| of the INPUT matrix (its left-looking update never
-//     touches later diagonal entries before they are chosen), i.e. a descending-|diag| order: computed by a rank
-//     sort and applied as a symmetric permutation before the (then unpivoted) blocked factorisation.
+//   * the LDL^T is blocked by 4 columns with the diagonal block factored redundantly in every row thread's registers (see the
+//     comment in front of k3_rcp for what was measured and why);
+//   * after the solve, independent pieces run on different warps at once (frame step + SE3::exp | calibration + canbreak | xAd,
+//     adHTdeltaF) instead of one after the other.
 #pragma once
 #include "common.cuh"
 #include "se3_math.cuh"
@@ -65,32 +63,25 @@ __device__ void stage_out(const K3Frames *S, WinState *ws) {
     for (int i = threadIdx.x; i < nc; i += blockDim.x) dstc[i] = srcc[i];
 }
 
-// FrameHessian::setState (FrameHessian.h:78-91), FrameFramePrecalc::Set for all pairs (FrameFramePrecalc.cc:6-35),
-// EnergyFunctional::setDeltaF frame part (EnergyFunctional.cc:403-429). Frame records live in shared memory (S);
-// the pair records are written to global. Called by all threads of a CTA with >= 128 threads.
-__device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float *adHF, const float *adTF) {
+// part 1 (thread f < nF): FrameHessian::setState for frame f -- PRE_worldToCam = SE3::exp(scaled state) * worldToCam_evalPT, delta
+__device__ __forceinline__ void frames_exp_part(K3Frames *S, int f_idx) {
+    FrameDev &f = S->fr[f_idx];
+    double ss[6];
+    for (int i = 0; i < 3; i++) ss[i] = (double) SCALE_XI_TRANS * f.state[i];
+    for (int i = 3; i < 6; i++) ss[i] = (double) SCALE_XI_ROT * f.state[i];
+    double Re[9], te[3];
+    se3_exp(ss, Re, te);
+    se3_mul(Re, te, f.evalR, f.evalT, f.preR, f.preT);
+    for (int i = 0; i < 8; i++) {
+        f.delta[i] = f.state[i] - f.state_zero[i];
+        f.delta_prior[i] = f.state[i];
+    }
+}
+// part 2 (all threads of the CTA, after a barrier behind part 1): the nF^2 pair records, three short parallel phases instead of one
+// long per-pair chain: F2 (pair,row): one row of R = R_t R_h^T and of t = t_t - R t_h, in double; F3 (pair,row): one row of
+// K R K^-1 and K t in float (the reference's Mat33f products, FrameFramePrecalc.cc:21-31); F3' (pair): affine brightness transfer.
+__device__ void frames_pairs_part(K3Frames *S, WinState *ws, bool full) {
     const int nF = ws->nF, tid = threadIdx.x;
-    if (tid < nF) {
-        FrameDev &f = S->fr[tid];
-        double ss[6];
-        for (int i = 0; i < 3; i++) ss[i] = (double) SCALE_XI_TRANS * f.state[i];
-        for (int i = 3; i < 6; i++) ss[i] = (double) SCALE_XI_ROT * f.state[i];
-        double Re[9], te[3];
-        se3_exp(ss, Re, te);
-        se3_mul(Re, te, f.evalR, f.evalT, f.preR, f.preT);
-        for (int i = 0; i < 8; i++) {
-            f.delta[i] = f.state[i] - f.state_zero[i];
-            f.delta_prior[i] = f.state[i];
-        }
-    }
-    if (tid == 64) {
-        CalibDev &c = S->calib;
-        for (int i = 0; i < 4; i++) c.cDeltaF[i] = (float) (c.value[i] - c.value_zero[i]);
-    }
-    __syncthreads();
-    // pair records, three short parallel phases instead of one long per-pair chain:
-    // F2 (pair,row): one row of R = R_t R_h^T and of t = t_t - R t_h, in double; F3 (pair,row): one row of K R K^-1 and K t in
-    // float (the reference's Mat33f products, FrameFramePrecalc.cc:21-31); F3' (pair): affine brightness transfer.
     __shared__ float sRf[MAXPAIR][9], sTf[MAXPAIR][3];
     __shared__ double sTd[MAXPAIR][3];
     for (int o = tid; o < nF * nF * 3; o += blockDim.x) {
@@ -113,20 +104,24 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float
         sTd[q][i] = tt;
     }
     __syncthreads();
+    // outputs [0, 3 nF^2): (pair, row) of K R K^-1 / K t; [3 nF^2, 4 nF^2): the pairs' brightness transfer -- whole warps take one branch
+    const int nP3 = nF * nF * 3;
     for (int o = tid; o < nF * nF * 4; o += blockDim.x) {
-        const int q = o >> 2, i = o & 3;
-        PairRec &pc = ws->pair[q];
-        if (i < 3) {
+        if (o < nP3) {
+            const int q = o / 3, i = o - 3 * q;
+            PairRec &pc = ws->pair[q];
             const CalibDev &c = S->calib;
             const float K[9] = {c.fxl, 0, c.cxl, 0, c.fyl, c.cyl, 0, 0, 1};
             float Ki[9];
             m33f_inverse(K, Ki);
+            // row i of K by selects (a runtime index would put K into local memory)
+            const float k0 = (i == 0) ? c.fxl : 0.f, k1 = (i == 1) ? c.fyl : 0.f, k2 = (i == 0) ? c.cxl : (i == 1) ? c.cyl : 1.f;
             const float *Rf = sRf[q];
             float tmp[3];
             for (int j = 0; j < 3; j++) {
-                float s2 = K[i * 3 + 0] * Rf[0 * 3 + j];
-                s2 += K[i * 3 + 1] * Rf[1 * 3 + j];
-                s2 += K[i * 3 + 2] * Rf[2 * 3 + j];
+                float s2 = k0 * Rf[0 * 3 + j];
+                s2 += k1 * Rf[1 * 3 + j];
+                s2 += k2 * Rf[2 * 3 + j];
                 tmp[j] = s2;
             }
             for (int j = 0; j < 3; j++) {
@@ -135,14 +130,16 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float
                 s2 += tmp[2] * Ki[2 * 3 + j];
                 pc.KRKi[i * 3 + j] = s2;
             }
-            float s2 = K[i * 3 + 0] * sTf[q][0];
-            s2 += K[i * 3 + 1] * sTf[q][1];
-            s2 += K[i * 3 + 2] * sTf[q][2];
+            float s2 = k0 * sTf[q][0];
+            s2 += k1 * sTf[q][1];
+            s2 += k2 * sTf[q][2];
             pc.Kt[i] = s2;
             PairRecFull &pf = ws->pairFull[q];
             for (int j = 0; j < 3; j++) pf.RTll[i * 3 + j] = Rf[i * 3 + j];
             pf.tTll[i] = sTf[q][i];
         } else {
+            const int q = o - nP3;
+            PairRec &pc = ws->pair[q];
             const int h = q % nF, t = q / nF;
             const FrameDev &fh = S->fr[h], &ft = S->fr[t];
             // AffLight::fromToVecExposure (AffLight.h:27-35) with aff_g2l() = state_scaled[6..7]
@@ -156,16 +153,41 @@ __device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float
             pc.distanceLL = (float) sqrt(sTd[q][0] * sTd[q][0] + sTd[q][1] * sTd[q][1] + sTd[q][2] * sTd[q][2]);
         }
     }
-    // adHTdeltaF (EnergyFunctional.cc:406-414): one (pair, column) output per thread pass
-    for (int o = tid; o < nF * nF * 8; o += blockDim.x) {
+}
+// adHTdeltaF (EnergyFunctional.cc:406-414), outputs o0, o0 + stride, ... of the nF*nF*8 (pair, column) outputs. With vx != nullptr the
+// frame state is formed here as state_backup + (-vx) -- the bits doStepFromBackup stores -- so that the caller can run this beside
+// the threads that write state / step (no shared-memory record is read that another warp writes in the same phase).
+__device__ __forceinline__ void frames_adHTdelta(const K3Frames *S, WinState *ws, const float *adHF, const float *adTF, int o0, int stride, const double *vx) {
+    const int nF = ws->nF;
+    for (int o = o0; o < nF * nF * 8; o += stride) {
         const int q = o >> 3, j = o & 7, h = q % nF, t = q / nF;
         const FrameDev &fh = S->fr[h], &ft = S->fr[t];
         const float *AH = adHF + q * 64, *AT = adTF + q * 64;
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < 8; i++) s1 += (float) (fh.state[i] - fh.state_zero[i]) * AH[i * 8 + j];
-        for (int i = 0; i < 8; i++) s2 += (float) (ft.state[i] - ft.state_zero[i]) * AT[i * 8 + j];
+        if (vx != nullptr) {
+            for (int i = 0; i < 8; i++) { const double st = fh.state_backup[i] + (-vx[CPARS + 8 * h + i]); s1 += (float) (st - fh.state_zero[i]) * AH[i * 8 + j]; }
+            for (int i = 0; i < 8; i++) { const double st = ft.state_backup[i] + (-vx[CPARS + 8 * t + i]); s2 += (float) (st - ft.state_zero[i]) * AT[i * 8 + j]; }
+        } else {
+            for (int i = 0; i < 8; i++) s1 += (float) (fh.state[i] - fh.state_zero[i]) * AH[i * 8 + j];
+            for (int i = 0; i < 8; i++) s2 += (float) (ft.state[i] - ft.state_zero[i]) * AT[i * 8 + j];
+        }
         ws->adHTdeltaF[q][j] = s1 + s2;
     }
+}
+
+// FrameHessian::setState (FrameHessian.h:78-91), FrameFramePrecalc::Set for all pairs (FrameFramePrecalc.cc:6-35),
+// EnergyFunctional::setDeltaF frame part (EnergyFunctional.cc:403-429). Frame records live in shared memory (S);
+// the pair records are written to global. Called by all threads of a CTA with >= 128 threads.
+__device__ void frames_refresh(K3Frames *S, WinState *ws, bool full, const float *adHF, const float *adTF) {
+    const int nF = ws->nF, tid = threadIdx.x;
+    if (tid < nF) frames_exp_part(S, tid);
+    if (tid == 64) {
+        CalibDev &c = S->calib;
+        for (int i = 0; i < 4; i++) c.cDeltaF[i] = (float) (c.value[i] - c.value_zero[i]);
+    }
+    __syncthreads();
+    frames_pairs_part(S, ws, full);
+    frames_adHTdelta(S, ws, adHF, adTF, tid, blockDim.x, nullptr);
     __syncthreads();
 }
 
@@ -320,21 +342,31 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         if (q == 0 && i < n) m.perm[rank] = i;
     }
     __syncthreads();
-    // A = P (S A0 S) P^T, lower triangle plus the whole diagonal blocks; row n = P S b
-    for (int r = warp; r <= n; r += K3_THREADS / 32) {
-        const bool rhs = r == n;
-        const int pr = rhs ? 0 : m.perm[r];
-        const double sr = rhs ? 0.0 : m.vS[pr];
-        for (int c = lane; c < n; c += 32) {
-            if (!(rhs || c <= r || (c / K3_NB) == (r / K3_NB))) continue;
-            const int pc = m.perm[c];
-            double v;
-            if (rhs) v = m.vb[pc] * m.vS[pc];
-            else {
+    // A = P (S A0 S) P^T (both triangles: the upper one is never read, writing it keeps the copy branch-free); row n = P S b.
+    // A lane's columns (lane, lane+32, lane+64) are the same for every row: their permutation / scale / rhs entries are loaded once,
+    // and the 5 rows of a warp are independent chains (columns / rows past the end are clamped: duplicate stores of equal values).
+    {
+        int pcv[3];
+        double svc[3], bvc[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            pcv[q] = m.perm[min(lane + 32 * q, n - 1)];
+            svc[q] = m.vS[pcv[q]];
+            bvc[q] = m.vb[pcv[q]];
+        }
+#pragma unroll
+        for (int it = 0; it < (K3_NP + 1 + K3_THREADS / 32 - 1) / (K3_THREADS / 32); it++) {
+            const int r = min(warp + it * (K3_THREADS / 32), n);
+            const bool rhs = r == n;
+            const int pr = m.perm[rhs ? 0 : r];
+            const double sr = m.vS[pr];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int pc = pcv[q];
                 const int hi = max(pr, pc), lo = min(pr, pc);                 // lower triangle of the input (row hi, column lo)
-                v = (sr * m.A0[lo * n + hi]) * m.vS[pc];
+                const double v = (sr * m.A0[lo * n + hi]) * svc[q];
+                A[r * K3_LD + min(lane + 32 * q, n - 1)] = rhs ? bvc[q] * svc[q] : v;
             }
-            A[r * K3_LD + c] = v;
         }
     }
     __syncthreads();
@@ -401,27 +433,36 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
             const double dk = A[i * K3_LD + i], zi = A[n * K3_LD + i];
             z[q] = (iv < n && fabs(dk) > 2.2250738585072014e-308) ? zi : 0.0;
         }
+        // the factor entries a step needs do not depend on the unknowns. The diagonal block's entries, which the step's chain needs
+        // first, are loaded one step ahead (software pipeline); the update columns are requested at the top of the step and arrive
+        // while the block is solved: a step is the dependency chain shuffle -> 3 FMAs -> update only
+        double Lb[K3_NB * (K3_NB - 1) / 2];
+#define K3_BS_LOAD_LB(kq_)                                                                                          \
+        do {                                                                                                        \
+            const int kl_ = (kq_) * K3_NB;                                                                          \
+            _Pragma("unroll") for (int j = 1; j < K3_NB; j++)                                                       \
+                _Pragma("unroll") for (int c = 0; c < j; c++) Lb[j * (j - 1) / 2 + c] = A[(kl_ + j) * K3_LD + kl_ + c]; \
+        } while (0)
+        K3_BS_LOAD_LB(nblk - 1);
 #pragma unroll 1
         for (int kb = nblk - 1; kb >= 0; kb--) {
             const int k0 = kb * K3_NB, sl = k0 >> 5, l0 = k0 & 31;
             const double zsel = (sl == 0) ? z[0] : (sl == 1) ? z[1] : z[2];
-            double x[K3_NB], Lb[K3_NB * (K3_NB - 1) / 2], Lu[3][K3_NB];
-            // every load of the step first (none depends on this step's unknowns); no branch anywhere in the step
+            double x[K3_NB], cLb[K3_NB * (K3_NB - 1) / 2], Lu[3][K3_NB];
 #pragma unroll
-            for (int j = 1; j < K3_NB; j++)
+            for (int e = 0; e < K3_NB * (K3_NB - 1) / 2; e++) cLb[e] = Lb[e];
 #pragma unroll
-                for (int c = 0; c < j; c++) Lb[j * (j - 1) / 2 + c] = A[(k0 + j) * K3_LD + k0 + c];
+            for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
 #pragma unroll
             for (int q = 0; q < 3; q++)
 #pragma unroll
                 for (int c = 0; c < K3_NB; c++) Lu[q][c] = A[(k0 + c) * K3_LD + min(lane + 32 * q, n - 1)];
-#pragma unroll
-            for (int c = 0; c < K3_NB; c++) x[c] = shfl_f64(zsel, l0 + c);
+            K3_BS_LOAD_LB(max(kb - 1, 0));
             // x_c = z_c - sum_{j > c} L(k0+j, k0+c) x_j, solved redundantly by every lane
 #pragma unroll
             for (int j = K3_NB - 1; j >= 1; j--)
 #pragma unroll
-                for (int c = 0; c < j; c++) x[c] = fma(-Lb[j * (j - 1) / 2 + c], x[j], x[c]);
+                for (int c = 0; c < j; c++) x[c] = fma(-cLb[j * (j - 1) / 2 + c], x[j], x[c]);
             // the block's unknowns go back to their owner lanes; earlier rows lose this block's contribution
 #pragma unroll
             for (int q = 0; q < 3; q++) {
@@ -433,6 +474,7 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
                 z[q] = xo;
             }
         }
+#undef K3_BS_LOAD_LB
         // x = S P^T xp
 #pragma unroll
         for (int q = 0; q < 3; q++) {
@@ -538,6 +580,67 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
             __syncthreads();
         }
         K3_STAMP();   // 3: orthogonalised
+    }
+    if ((flags & K3F_SOLVE) && (flags & K3F_STEP)) {
+        // ---- fused tail (the Gauss-Newton loop): resubstituteF_MT's frame part (:495-507), doStepFromBackup's frame / calibration part
+        // (FullSystem.cc:1588-1597,1617-1627) and setDeltaF's adHTdeltaF only need x, so they run side by side on different warps:
+        //   warp 0     frame steps, states, SE3::exp (the long chain)
+        //   warp 1     calibration step + setValue + cDeltaF, canbreak
+        //   warps 2..  lastX, xAd, adHTdeltaF
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp == 0) {
+            if (lane < nF) {
+                FrameDev &f = S->fr[lane];
+                for (int i = 0; i < 8; i++) f.step[i] = -m.vx[CPARS + 8 * lane + i];
+                f.step[8] = f.step[9] = 0.0;
+                for (int i = 0; i < 10; i++) f.state[i] = f.state_backup[i] + f.step[i];
+                frames_exp_part(S, lane);
+            }
+        } else if (warp == 1) {
+            if (lane < CPARS) {
+                S->calib.step[lane] = -m.vx[lane];
+                ws->cstep[lane] = (float) m.vx[lane];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                CalibDev &c = S->calib;
+                double nv[4];
+                for (int i = 0; i < 4; i++) nv[i] = c.value_backup[i] + c.step[i];
+                calib_set_value(c, nv);
+                for (int i = 0; i < 4; i++) c.cDeltaF[i] = (float) (c.value[i] - c.value_zero[i]);
+                float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+                for (int h = 0; h < nF; h++) {
+                    double st[8];
+                    for (int i = 0; i < 8; i++) st[i] = -m.vx[CPARS + 8 * h + i];
+                    sumA += st[6] * st[6];
+                    sumB += st[7] * st[7];
+                    sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
+                    sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
+                }
+                sumA /= nF; sumB /= nF; sumR /= nF; sumT /= nF;
+                const float sumNID = nid_pre / num_pre;
+                const float thO = tho_pre;
+                ws->canbreak = (sqrtf(sumA) < 0.0005 * thO && sqrtf(sumB) < 0.00005 * thO && sqrtf(sumR) < 0.00005 * thO &&
+                                sqrtf(sumT) * sumNID < 0.00005 * thO) ? 1 : 0;
+            }
+        } else {
+            const int t0 = tid - 64, nt = K3_THREADS - 64;
+            for (int e = t0; e < n; e += nt) sb.lastX[e] = m.vx[e];
+            for (int o = t0; o < nF * nF * 8; o += nt) {
+                const int q = o >> 3, j = o & 7, h = q / nF, t = q % nF;     // xAd[nFrames*h + t]
+                const float *AH = m.adH + (h + nF * t) * 64, *AT = m.adT + (h + nF * t) * 64;
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < 8; i++) s1 += (float) m.vx[CPARS + 8 * h + i] * AH[i * 8 + j];
+                for (int i = 0; i < 8; i++) s2 += (float) m.vx[CPARS + 8 * t + i] * AT[i * 8 + j];
+                ws->xAd[nF * h + t][j] = s1 + s2;
+            }
+            frames_adHTdelta(S, ws, m.adH, m.adT, t0, nt, m.vx);
+        }
+        __syncthreads();
+        K3_STAMP();   // 4: x distributed, frame poses refreshed
+        frames_pairs_part(S, ws, false);      // (stage_out starts with the barrier that closes this phase)
+    } else {
+    if (flags & K3F_SOLVE) {
         if (tid < n) sb.lastX[tid] = m.vx[tid];
         // resubstituteF_MT frame part (:495-507)
         if (tid < CPARS) {
@@ -586,6 +689,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         }
         __syncthreads();
         frames_refresh(S, ws, false, m.adH, m.adT);
+    }
     }
     K3_STAMP();   // 5: frames refreshed
     stage_out(S, ws);
