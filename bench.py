@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "GN-iters/sec, 8-KF x 2k-point window; Hessian rel-err vs SSE ref"
 PTS_PER_FRAME = 250       # per GPU: 8 KF x 250 = 2000 active points (BASELINE.json configs[1])
 NF = 8
+E2E_CONTEXTS = 4          # windows in flight in the end-to-end leg (one host thread, one stream per context)
 
 
 def common_config(n_gpus, n_points, n_residuals):
@@ -408,14 +409,14 @@ def run_ours(args):
 def run_e2e(ctx, win, args, torch):
     """End to end through the C ABI from HOST buffers (pinned), every step: H2D of the newest keyframe's raw image (+ device
     makeImages), the frame states and the whole window; FullSystem::optimize's prologue + 1 GN iteration; D2H of lastHS / lastbS /
-    lastX, energy, point idepth / step / HdiF, residual states + energies. `value` = two contexts fed alternately through
-    ldso_b200_optimize_from_host_submit / _wait (step k+1's uploads overlap step k's kernels; every step still does all of its copies);
+    lastX, energy, point idepth / step / HdiF, residual states + energies. `value` = E2E_CONTEXTS contexts fed round-robin through
+    ldso_b200_optimize_from_host_submit / _wait (one window's copies overlap the others' kernels; every step still does all of its copies);
     value_one_context = the same step as ONE blocking call on one context; per_keyframe = one upload + prologue + 6 iterations + one
     read-back per call (what FullSystem::optimize does per keyframe), in GN iterations per second."""
     from ldso_b200 import capi
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     io = capi.StepIO(ctx, win, pinned_alloc=pin)
-    steps = min(max(args.steps, 20), 200)
+    steps = min(max(args.steps, 200), 400)      # host wall clock over a pipeline: enough steps that its fill / drain (about one step latency) is < 1 %
     for k in range(3):
         io.fused(0, 1)
     torch.cuda.synchronize()
@@ -424,35 +425,41 @@ def run_e2e(ctx, win, args, torch):
         io.fused(0, 1)           # ONE C-ABI call per step: ldso_b200_optimize_from_host
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    # two contexts, pipelined
-    ctx2 = capi.Context(win.w, win.h, win.levels, device=torch.cuda.current_device())
-    ctx2.load_synth_window(win)
-    ios = [io, capi.StepIO(ctx2, win, pinned_alloc=pin)]
-    for k in range(4):
-        ios[k & 1].fused(0, 1)
+    # E2E_CONTEXTS contexts fed round-robin from this one host thread: a step's critical path through its stream (uploads -> pyramid ->
+    # prologue -> iteration -> read-back, ~270 us) is mostly copy / launch latency, which only other windows in flight can hide
+    # (measured, tools/e2e_pipe_prof.py: 1 context 274, 2 contexts 157, 3 contexts 121 us per step; host time of a submit 53 us)
+    m = E2E_CONTEXTS
+    extra = [capi.Context(win.w, win.h, win.levels, device=torch.cuda.current_device()) for _ in range(m - 1)]
+    for c in extra:
+        c.load_synth_window(win)
+    ios = [io] + [capi.StepIO(c, win, pinned_alloc=pin) for c in extra]
+    for k in range(2 * m):
+        ios[k % m].fused(0, 1)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ios[0].submit(0, 1)
-    for k in range(1, steps):
-        ios[k & 1].submit(0, 1)
-        ios[(k - 1) & 1].wait()
-    ios[(steps - 1) & 1].wait()
+    for k in range(steps):
+        if k >= m:
+            ios[k % m].wait()            # the step submitted m steps ago on this context: results in the caller's buffers
+        ios[k % m].submit(0, 1)
+    for k in range(max(steps - m, 0), steps):
+        ios[k % m].wait()
     dt_pipe = time.perf_counter() - t0
     # one keyframe's optimize per call: 6 iterations per upload
     for k in range(2):
         io.fused(0, 6)
     t0 = time.perf_counter()
-    nkf = max(steps // 4, 5)
+    nkf = 50
     for k in range(nkf):
         io.fused(0, 6)
     dt_kf = time.perf_counter() - t0
-    ctx2.close()
-    return {"value": steps / dt_pipe, "unit": "GN-iters/s", "h2d_bytes_per_step": int(io.h2d_bytes), "d2h_bytes_per_step": int(io.d2h_bytes),
+    for c in extra:
+        c.close()
+    return {"value": steps / dt_pipe, "contexts_in_flight": m, "steps": steps, "unit": "GN-iters/s", "h2d_bytes_per_step": int(io.h2d_bytes), "d2h_bytes_per_step": int(io.d2h_bytes),
             "value_one_context": steps / dt,
             "per_keyframe": {"gn_iters_per_s": 6 * nkf / dt_kf, "ms_per_keyframe": 1e3 * dt_kf / nkf, "iterations_per_upload": 6},
             "def": "per step: H2D newest keyframe raw image from pinned memory (+device makeImages), frame states, full window; optimize prologue + "
-                   "1 GN iteration; D2H lastHS/lastbS/lastX, energy, point idepth/step/HdiF, residual states+energies; host wall clock. value = two "
-                   "contexts fed alternately (ldso_b200_optimize_from_host_submit / _wait: the uploads of step k+1 overlap the kernels of step k); "
+                   "1 GN iteration; D2H lastHS/lastbS/lastX, energy, point idepth/step/HdiF, residual states+energies; host wall clock. value = "
+                   f"{m} contexts fed round-robin from one host thread (ldso_b200_optimize_from_host_submit / _wait: the copies and launches of one window overlap the kernels of the others; every step still does all of its own copies); "
                    "value_one_context = one blocking ldso_b200_optimize_from_host per step; per_keyframe = one upload, prologue + 6 iterations, one read-back"}
 
 

@@ -326,6 +326,38 @@ __device__ void k2_select_body(const double *red, int N, WinState *ws, double *s
         if (tid == 0) { ws->frameEnergyTH[nF - 1] = th; PROF_ONLY(dbg[13] = clock64();) }
     }
 
+// 1x4 register tiles of the 8x8 triple products (operands staged in shared memory with row stride K2B_RS): one 8-term FMA chain per
+// output, ascending index -- the same sums as one output per thread, with 20 16-byte loads per 32 FMAs instead of 64 8-byte loads
+// (one output per thread is bound by shared-memory load issue, not by the FP64 pipe).
+// o[c] = sum_i Arow[i] * D[i][c0 + c]        (A * D;  Dc = &D[0][c0])
+__device__ __forceinline__ void k2b_tile_AD(const double *Arow, const double *Dc, double o[4]) {
+    double av[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) { const double2 a = *(const double2 *) (Arow + i); av[i] = a.x; av[i + 1] = a.y; }
+    o[0] = o[1] = o[2] = o[3] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double2 d01 = *(const double2 *) (Dc + i * K2B_RS), d23 = *(const double2 *) (Dc + i * K2B_RS + 2);
+        o[0] += av[i] * d01.x; o[1] += av[i] * d01.y; o[2] += av[i] * d23.x; o[3] += av[i] * d23.y;
+    }
+}
+// o[c] = sum_j Arow[j] * B[c0 + c][j]        (A * B^T;  Br = &B[c0][0])
+__device__ __forceinline__ void k2b_tile_ABt(const double *Arow, const double *Br, double o[4]) {
+    double av[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) { const double2 a = *(const double2 *) (Arow + i); av[i] = a.x; av[i + 1] = a.y; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) { const double2 b = *(const double2 *) (Br + c * K2B_RS + j); s += av[j] * b.x; s += av[j + 1] * b.y; }
+        o[c] = s;
+    }
+}
+__device__ __forceinline__ void k2b_store4(double *dst, const double o[4]) {      // dst 16-byte aligned
+    *(double2 *) dst = make_double2(o[0], o[1]);
+    *(double2 *) (dst + 2) = make_double2(o[2], o[3]);
+}
 #define K2B_LAMBDA 1e-5        // SOLVER_FIX_LAMBDA (EnergyFunctional.cc:243)
 __device__ __forceinline__ double k2b_delta(const WinState *ws, int c) {      // getStitchedDeltaF (EnergyFunctional.h:178-184)
     return (c < CPARS) ? (double) ws->calib.cDeltaF[c] : ws->fr[(c - CPARS) >> 3].delta[(c - CPARS) & 7];
@@ -356,7 +388,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         double *sY2 = sT + 2 * MAXF * K2B_MS;  // sum_k D_b[a,k] * AH_bk^T
         double *sY3 = sY2 + K2B_MS;            // sum_j AH_aj * D_a[j,b]
         double *sP = sY3 + K2B_MS;             // [2][MAXF][64] per-frame partial products of Y2 / Y3
-        double *sO = sP + 2 * MAXF * 64;       // [K2B_NSLOT][2][64] partial outputs
+        // (K2B_NSLOT * 128 more doubles follow: the allocation also has to hold the select CTA's K2B_SELCAP keys)
         const int a = blockIdx.x % nF, b = blockIdx.x / nF;
         const bool diag = (a == b);
         // the marginalisation-prior element this thread will add in the epilogue: issue the load now
@@ -424,44 +456,34 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
             }
         }
         if (lt0 >= 0) {
-        for (int o = lt0; o < nF * 64; o += ltn) {         // Z_i = AT_ia * D_i[a,b]
-            const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) s += sATa[K2B_M(q, r, i)] * sD1[K2B_M(q, i, c)];
-            sZ[K2B_M(q, r, c)] = s;
-        }
-        for (int u = lt0; u < 2 * MAXF * 64; u += ltn) {   // per-frame terms of Y2 and Y3
-            const int which = u / (MAXF * 64), k = (u >> 6) & (MAXF - 1), e = u & 63, r = e >> 3, c = e & 7;
-            double s = 0.0;
-            if (k < nF) {
-                if (which == 0) {                                    // D_b[a,k] * AH_bk^T
-#pragma unroll
-                    for (int j = 0; j < 8; j++) s += sD2[K2B_M(k, r, j)] * sAHb[K2B_M(k, c, j)];
-                } else {                                             // AH_ak * D_a[k,b]
-#pragma unroll
-                    for (int i = 0; i < 8; i++) s += sAHa[K2B_M(k, r, i)] * sD3[K2B_M(k, i, c)];
+            // the 8-term products as 1x4 tiles: tile u <-> (matrix q, row r, column half): [0,128) Z, [128,384) the per-frame terms of
+            // Y2 / Y3, then T (2 nF matrices on a diagonal block, 2 otherwise)
+            const int nTile = 3 * MAXF * 16 + (diag ? 2 * nF : 2) * 16;
+            for (int u = lt0; u < nTile; u += ltn) {
+                const int q = u >> 4, r = (u >> 1) & 7, c0 = (u & 1) * 4;
+                double o4[4];
+                if (q < MAXF) {                                          // Z_q = AT_qa * D_q[a,b]
+                    if (q < nF) {
+                        k2b_tile_AD(sATa + K2B_M(q, r, 0), sD1 + K2B_M(q, 0, c0), o4);
+                        k2b_store4(sZ + K2B_M(q, r, c0), o4);
+                    }
+                } else if (q < 3 * MAXF) {
+                    const int which = (q - MAXF) / MAXF, k = (q - MAXF) & (MAXF - 1);
+                    o4[0] = o4[1] = o4[2] = o4[3] = 0.0;
+                    if (k < nF) {
+                        if (which == 0) k2b_tile_ABt(sD2 + K2B_M(k, r, 0), sAHb + K2B_M(k, c0, 0), o4);      // D_b[a,k] * AH_bk^T
+                        else k2b_tile_AD(sAHa + K2B_M(k, r, 0), sD3 + K2B_M(k, 0, c0), o4);                   // AH_ak * D_a[k,b]
+                    }
+                    k2b_store4(sP + which * MAXF * 64 + k * 64 + r * 8 + c0, o4);
+                } else {
+                    const int t = q - 3 * MAXF;
+                    const double *Lm;
+                    if (diag) Lm = (t < nF) ? (sAHa + t * K2B_MS) : (sATa + (t - nF) * K2B_MS);               // T_t = L_t * M_t
+                    else Lm = (t == 0) ? (sAHa + b * K2B_MS) : (sAHb + a * K2B_MS);                           // AH_ab*M_ab, AH_ba*M_ba
+                    k2b_tile_AD(Lm + r * K2B_RS, sM + K2B_M(t, 0, c0), o4);
+                    k2b_store4(sT + K2B_M(t, r, c0), o4);
                 }
             }
-            sP[u] = s;
-        }
-        if (diag) {
-            for (int o = lt0; o < 2 * nF * 64; o += ltn) { // T_q = L_q * M_q, L = AH_aq (q<nF) or AT_(q-nF)a
-                const int q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;
-                const double *Lm = (q < nF) ? (sAHa + q * K2B_MS) : (sATa + (q - nF) * K2B_MS);
-                double s = 0.0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) s += Lm[r * K2B_RS + i] * sM[K2B_M(q, i, c)];
-                sT[K2B_M(q, r, c)] = s;
-            }
-        } else if (tid >= 128 && tid < 256) {
-            const int o = tid - 128, q = o >> 6, e = o & 63, r = e >> 3, c = e & 7;   // T_0 = AH_ab*M_ab, T_1 = AH_ba*M_ba
-            const double *Lm = (q == 0) ? (sAHa + b * K2B_MS) : (sAHb + a * K2B_MS);
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) s += Lm[r * K2B_RS + i] * sM[K2B_M(q, i, c)];
-            sT[K2B_M(q, r, c)] = s;
-        }
         }
         __syncthreads();
         if (tid < 128) {                                             // fold the per-frame terms of Y2 / Y3
@@ -473,61 +495,44 @@ __global__ void __launch_bounds__(K2B_THREADS) k2b_stitch(DevWindow d, WinState 
         }
         __syncthreads();
         PROF_ONLY(if (blockIdx.x == 0 && tid == 0) d.dbg[10] = clock64();)
-        // -------- stage B: right products, K2B_NSLOT slots of 64 threads split the term lists
+        // -------- stage B: right products as 1x4 tiles, 32 groups of 16 threads, one term of the sum per group (two for groups 16, 17):
+        //   H_sc terms s: [0,8) Z_s AT_sb^T | 8: AT_ba Y2 | 9: Y3 AT_ab^T | [10,18) X_(s-10) AH_a(s-10)^T (diagonal blocks)      -> group s
+        //   H_A  terms t: diagonal block: [0,8) T_t AH_at^T, [8,16) T_(nF+t-8) AT_(t-8)a^T; else 0: T_0 AT_ab^T, 1: (T_1 AT_ba^T)^T -> group 16+t
+        // The partial 8x8 outputs go to the (now dead) D_a[j,k] staging area; invalid terms store zeros.
+        double *sOS = sD4, *sOA = sD4 + 18 * 64;
         {
-            const int slot = tid >> 6, e = tid & 63, r = e >> 3, c = e & 7;
-            double accA = 0.0, accS = 0.0;
-            for (int i = slot; i < nF; i += K2B_NSLOT) {            // sum_i Z_i * AT_ib^T
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += sZ[K2B_M(i, r, j)] * sATb[K2B_M(i, c, j)];
-                accS += s;
+            const int g = tid >> 4, u = tid & 15, r = u >> 1, c0 = (u & 1) * 4;
+            double o4[4];
+            if (g < 18) {
+                o4[0] = o4[1] = o4[2] = o4[3] = 0.0;
+                if (g < MAXF) { if (g < nF) k2b_tile_ABt(sZ + K2B_M(g, r, 0), sATb + K2B_M(g, c0, 0), o4); }
+                else if (g == MAXF) k2b_tile_AD(sATa + K2B_M(b, r, 0), sY2 + K2B_M(0, 0, c0), o4);
+                else if (g == MAXF + 1) k2b_tile_ABt(sY3 + K2B_M(0, r, 0), sATb + K2B_M(a, c0, 0), o4);
+                else if (diag && g - (MAXF + 2) < nF) k2b_tile_ABt(sX + K2B_M(g - (MAXF + 2), r, 0), sAHa + K2B_M(g - (MAXF + 2), c0, 0), o4);
+                k2b_store4(sOS + g * 64 + r * 8 + c0, o4);
             }
-            if (slot == 0) {                                         // AT_ba * Y2
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += sATa[K2B_M(b, r, j)] * sY2[K2B_M(0, j, c)];
-                accS += s;
-            } else if (slot == 1) {                                  // Y3 * AT_ab^T
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += sY3[K2B_M(0, r, j)] * sATb[K2B_M(a, c, j)];
-                accS += s;
+            if (g >= 16) {
+                const int t = g - 16;
+                o4[0] = o4[1] = o4[2] = o4[3] = 0.0;
+                if (diag) {
+                    if ((t & (MAXF - 1)) < nF) {
+                        const int q = (t < MAXF) ? t : nF + (t - MAXF);
+                        const double *Rm = (t < MAXF) ? (sAHa + t * K2B_MS) : (sATa + (t - MAXF) * K2B_MS);
+                        k2b_tile_ABt(sT + K2B_M(q, r, 0), Rm + c0 * K2B_RS, o4);
+                    }
+                } else if (t == 0) k2b_tile_ABt(sT + K2B_M(0, r, 0), sATb + K2B_M(a, c0, 0), o4);
+                else if (t == 1) k2b_tile_ABt(sATa + K2B_M(b, r, 0), sT + K2B_M(1, c0, 0), o4);
+                k2b_store4(sOA + t * 64 + r * 8 + c0, o4);
             }
-            if (diag) {
-                for (int k = slot; k < nF; k += K2B_NSLOT) {        // sum_k X_k * AH_ak^T
-                    double s = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) s += sX[K2B_M(k, r, j)] * sAHa[K2B_M(k, c, j)];
-                    accS += s;
-                }
-                for (int q = slot; q < 2 * nF; q += K2B_NSLOT) {    // sum_q T_q * L_q^T (host==target blocks are zero)
-                    const double *Rm = (q < nF) ? (sAHa + q * K2B_MS) : (sATa + (q - nF) * K2B_MS);
-                    double s = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) s += sT[K2B_M(q, r, j)] * Rm[c * K2B_RS + j];
-                    accA += s;
-                }
-            } else if (slot == 2) {                                  // (AH_ab M_ab) AT_ab^T
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += sT[K2B_M(0, r, j)] * sATb[K2B_M(a, c, j)];
-                accA += s;
-            } else if (slot == 3) {                                  // ((AH_ba M_ba) AT_ba^T)^T
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) s += sT[K2B_M(1, c, j)] * sATa[K2B_M(b, r, j)];
-                accA += s;
-            }
-            sO[(slot * 2 + 0) * 64 + e] = accA;
-            sO[(slot * 2 + 1) * 64 + e] = accS;
         }
         __syncthreads();
         if (tid < 64) {
             const int e = tid, r = e >> 3, c = e & 7;
             double vA = 0.0, vS = 0.0;
 #pragma unroll
-            for (int q = 0; q < K2B_NSLOT; q++) { vA += sO[(2 * q) * 64 + e]; vS += sO[(2 * q + 1) * 64 + e]; }
+            for (int q = 0; q < 18; q++) vS += sOS[q * 64 + e];
+#pragma unroll
+            for (int q = 0; q < 16; q++) vA += sOA[q * 64 + e];
             const int row = CPARS + 8 * a + r, col = CPARS + 8 * b + c;
             sb.H_A[(size_t) col * n + row] = vA;
             sb.H_sc[(size_t) col * n + row] = vS;

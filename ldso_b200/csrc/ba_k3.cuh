@@ -21,6 +21,9 @@
 #define K3_NP MAXN               // n = 8 nF + 4 is a multiple of the block size 4: no padding
 #define K3_LD (K3_NP + 1)        // odd leading dimension: a column of the matrix touches every bank once
 #define K3_NB 4
+#define K3_A0LD (MAXN + 1)       // staged input: odd column stride (with the natural stride 68 a walk along a row of the column-major matrix
+                                 // touches 4 bank groups only: 8-way conflicts on half of the permuted copy's loads)
+static_assert((MAXN * K3_A0LD) % 2 == 0, "shared-memory carve-up: 16-byte alignment behind A0");
 #define K3_WPLD (K3_NP + 2)      // Wp is [K3_NB][K3_WPLD] (column of the panel major): conflict-free for consecutive rows
 
 struct K3Frames {       // shared-memory staging of the mutable window records
@@ -299,12 +302,12 @@ struct K3Smem {       // carve-up of the dynamic shared memory block (all 16-byt
     float *adH, *adT;
 };
 #define K3_A_DOUBLES (((K3_NP + 1) * K3_LD + 1) & ~1)
-#define K3_SMEM_DOUBLES (K3_A_DOUBLES + MAXN * MAXN + 2 * K3_NB * K3_WPLD + 4 * K3_NP + MAXN * MAXN + K3_NP / 2 + 4)
+#define K3_SMEM_DOUBLES (K3_A_DOUBLES + MAXN * K3_A0LD + 2 * K3_NB * K3_WPLD + 4 * K3_NP + MAXN * MAXN + K3_NP / 2 + 4)
 __device__ __forceinline__ K3Smem k3_carve(double *base) {
     K3Smem m;
     m.A = base;                                 // [(K3_NP + 1)][K3_LD] permuted, scaled, identity-padded system (+ rhs as row npad), factorised in place
-    m.A0 = m.A + K3_A_DOUBLES;                   // [n*n] the assembled system as the stitch kernel left it (column-major)
-    m.Wp = m.A0 + MAXN * MAXN;                   // [2][K3_NB][K3_WPLD] unscaled panel W = L*D of the current / previous block step
+    m.A0 = m.A + K3_A_DOUBLES;                   // [n][K3_A0LD] the assembled system as the stitch kernel left it (column-major, padded columns)
+    m.Wp = m.A0 + MAXN * K3_A0LD;                // [2][K3_NB][K3_WPLD] unscaled panel W = L*D of the current / previous block step (68 * 69 is even)
     m.vb = m.Wp + 2 * K3_NB * K3_WPLD; m.vS = m.vb + K3_NP; m.vd = m.vS + K3_NP; m.vx = m.vd + K3_NP;
     m.Pns = m.vx + K3_NP;                        // [n*n] null-space projector
     m.perm = (int *) (m.Pns + MAXN * MAXN);      // [K3_NP]
@@ -315,10 +318,11 @@ __device__ __forceinline__ K3Smem k3_carve(double *base) {
 }
 
 // Scaled, Eigen-ordered LDL^T solve of the assembled system (EnergyFunctional.cc:326-335): x = S (S A S)^-1 S b.
-// In: m.A0 (n x n, column-major), m.vb = b, m.vd = diag(A0). Out: m.vx. Called by all K3_THREADS threads.
+// In: m.A0 (n x n, column-major with column stride K3_A0LD), m.vb = b, m.vd = diag(A0). Out: m.vx. Called by all K3_THREADS threads.
 __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *A = m.A;
+    PROF_ONLY(if (tid == 0) prof[9] = clk_fenced();)
     // SVecI = (diag + 10)^-1/2 (:326-327); Eigen's pivot order = descending |diag| of the scaled matrix
     if (tid < n) {
         const double dg = m.vd[tid];
@@ -327,6 +331,7 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         m.vd[tid] = fabs(dg * sv * sv);
     }
     __syncthreads();
+    PROF_ONLY(if (tid == 0) prof[10] = clk_fenced();)
     for (int i4 = tid; i4 < ((4 * n + 31) & ~31); i4 += K3_THREADS) {      // rank sort, 4 threads per row; whole warps: the shuffles are full-mask
         const int i = i4 >> 2, q = i4 & 3;
         int rank = 0;
@@ -342,6 +347,7 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
         if (q == 0 && i < n) m.perm[rank] = i;
     }
     __syncthreads();
+    PROF_ONLY(if (tid == 0) prof[11] = clk_fenced();)
     // A = P (S A0 S) P^T (both triangles: the upper one is never read, writing it keeps the copy branch-free); row n = P S b.
     // A lane's columns (lane, lane+32, lane+64) are the same for every row: their permutation / scale / rhs entries are loaded once,
     // and the 5 rows of a warp are independent chains (columns / rows past the end are clamped: duplicate stores of equal values).
@@ -364,7 +370,7 @@ __device__ void k3_ldlt_solve(const K3Smem &m, int n, long long *prof) {
             for (int q = 0; q < 3; q++) {
                 const int pc = pcv[q];
                 const int hi = max(pr, pc), lo = min(pr, pc);                 // lower triangle of the input (row hi, column lo)
-                const double v = (sr * m.A0[lo * n + hi]) * svc[q];
+                const double v = (sr * m.A0[lo * K3_A0LD + hi]) * svc[q];
                 A[r * K3_LD + min(lane + 32 * q, n - 1)] = rhs ? bvc[q] * svc[q] : v;
             }
         }
@@ -494,6 +500,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
         // NEXT linearisation, so it runs beside the solver (another SM) instead of in front of it inside the stitch kernel
         pdl_launch_dependents();
         pdl_wait();
+        // ... and it publishes the system being solved as lastHS (EnergyFunctional.cc:285), a 37 KB copy the solver CTA does not need
+        if (flags & K3F_SOLVE) {
+            const int nn = ws->n * ws->n;
+            for (int e = threadIdx.x; e < nn; e += K3_THREADS) sb.lastHS[e] = sb.HSg[e];
+        }
         k2_select_body(sel_red, sel_n, ws, sm3, sel_dbg);
         return;
     }
@@ -514,14 +525,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     const int iteration = *iteration_dev;
     constexpr int K3_HSCOPY = (MAXN * MAXN + K3_THREADS - 1) / K3_THREADS;
     double hs_pre[K3_HSCOPY], b_pre = 0.0;
+    const bool copy_hs = gridDim.x == 1;      // with a second CTA in the grid (the Gauss-Newton loop) that one copies HFinal_top - H_sc to lastHS
     float nid_pre = 0.f, num_pre = 1.f, tho_pre = 0.f;      // doStepFromBackup's canbreak inputs (thread 0 only)
     if (flags & K3F_SOLVE) {
-        for (int e = tid; e < n * n / 2; e += K3_THREADS) cp_async16(m.A0 + 2 * e, sb.A0g + 2 * e);
+        for (int cc = tid >> 5; cc < n; cc += K3_THREADS / 32)        // a warp per column (no division), 8-byte copies: the padded columns are not 16-byte aligned
+            for (int r = tid & 31; r < n; r += 32) cp_async8(m.A0 + cc * K3_A0LD + r, sb.A0g + cc * n + r);
         if (tid < n) { m.vd[tid] = sb.dg[tid]; b_pre = sb.bFg[tid]; m.vb[tid] = b_pre; }
+        if (copy_hs) {
 #pragma unroll
-        for (int k = 0; k < K3_HSCOPY; k++) {
-            const int e = tid + k * K3_THREADS;
-            hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
+            for (int k = 0; k < K3_HSCOPY; k++) {
+                const int e = tid + k * K3_THREADS;
+                hs_pre[k] = (e < n * n) ? sb.HSg[e] : 0.0;
+            }
         }
     }
     for (int e = tid; e < (int) (sizeof(K3Frames) / 8); e += K3_THREADS) cp_async8((char *) S + 8 * e, (const char *) ws->fr + 8 * e);
@@ -552,15 +567,18 @@ __global__ void __launch_bounds__(K3_THREADS) k3_solve_step(WinState *ws, SolveB
     }
     if (flags & K3F_SOLVE) {
         // The system being solved now becomes the public lastHS / lastbS (EnergyFunctional.cc:285,:335).
+        if (copy_hs) {
 #pragma unroll
-        for (int k = 0; k < K3_HSCOPY; k++) {
-            const int e = tid + k * K3_THREADS;
-            if (e < n * n) sb.lastHS[e] = hs_pre[k];
+            for (int k = 0; k < K3_HSCOPY; k++) {
+                const int e = tid + k * K3_THREADS;
+                if (e < n * n) sb.lastHS[e] = hs_pre[k];
+            }
         }
         if (tid < n) sb.lastbS[tid] = b_pre;
         k3_ldlt_solve(m, n, prof);
 #ifdef LDSO_B200_PROFILE
         if (tid == 0) for (int k = 0; k < 4; k++) ws->dbg[20 + k] = prof[k];
+        if (tid == 0) for (int k = 9; k < 12; k++) ws->dbg[31 + k] = prof[k];
         if (tid == 16) for (int k = 4; k < 9; k++) if (k != 5) ws->dbg[20 + k] = prof[k];
         if (tid == 96) ws->dbg[25] = prof[5];
 #endif

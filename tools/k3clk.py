@@ -9,6 +9,7 @@ buf = (C.c_longlong*80)()
 ctx.L.ldso_b200_debug_clocks(ctx.ctx, buf)
 t = np.array(buf[:7]); print("K3 stamps delta cycles [stage-in wait | backup+solve | orthogonalise | xAd | step+refresh | stage-out]:", np.diff(t), "total", t[-1]-t[0])
 print("K3 solve: sort+permute %d | factorisation %d | back-substitution %d cycles" % (buf[20] - buf[1], buf[21] - buf[20], buf[22] - buf[21]))
+print("K3 solve front: [inputs staged -> solve entry | SVecI | rank sort | permuted copy] %s" % [int(buf[40] - buf[1]), int(buf[41] - buf[40]), int(buf[42] - buf[41]), int(buf[20] - buf[42])])
 print("K3 block step 4 (row 16): panel %d | helper far update (thread 96) %d | barrier wait %d | near update %d | barrier wait %d" % tuple(buf[24:29]))
 t = np.array(buf[64:72]); print("K1 stamps delta cycles:", np.diff(t), "total", t[-1]-t[0])
 t = np.array(buf[72:76]); print("K2b diag-CTA stamps delta cycles:", np.diff(t))
