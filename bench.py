@@ -383,9 +383,9 @@ def run_ours(args):
         "window_iters_per_s": window_its_per_s,
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         "roofline": {"bound": "hbm", "kernel": "k1_linearize_accumulate", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": 12256512, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": 12254720, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b_k1, "kernel_us": ktimes,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of K1, one ncu --set full capture of this workload (profiles/r02p_ncu_full_summary.txt, r02p_gn_ncu_full_raw.csv); bench.py cannot run ncu on itself",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of K1, one ncu --set full capture of this workload (profiles/r02z_ncu_full_summary.txt, r02z_gn_ncu_full_raw.csv); bench.py cannot run ncu on itself",
                      "whole_iteration": {"achieved": achieved_iter, "frac": achieved_iter / hbm_peak, "algorithmic_bytes_per_step": b_iter},
                      "note": "2k points: latency-bound, not bandwidth-bound (ideal 0.93 us/iteration); see DESIGN.md §4"},
         "clocks": clocks,
