@@ -90,3 +90,35 @@ def test_allreduce_of_shards_equals_full_window():
     assert rel_err(Hsc.ravel(), s["Hsc"].ravel()) < 1e-6
     assert rel_err(bsc, s["bsc"]) < 1e-6
     assert abs(red[k] - e) < 1e-6 * abs(e)
+
+
+def test_sequence_generator_config4_inputs():
+    """ldso_b200.seq (BASELINE configs[3]'s synthetic sequence, host side only): sliding-window bookkeeping, the flattened window's CSR
+    layout, and geometric consistency of poses, depths and rendered images (a keyframe's point at its true depth reprojects into the
+    next keyframe onto the same scene intensity, up to the frames' affine brightness)."""
+    from ldso_b200 import seq as seqmod
+    K = seqmod.KITTI_K * np.array([0.25, 0.25, 0.25, 0.25])
+    s = seqmod.make_sequence(n_frames=11, w=308, h=92, K=K, kf_every=5, window=2, pts_per_kf=40, seed=3, outlier_frac=0.0)
+    assert s.levels == synth.pyr_levels_for(308, 92) and len(s.images) == 11 and sorted(s.kf_points) == [0, 5, 10]
+    assert s.window_kfs(0) == [0] and s.window_kfs(5) == [0, 5] and s.window_kfs(10) == [5, 10]
+    R, t = s.rel_pose(5, 10)
+    assert np.allclose(R @ s.Rcw[5], s.Rcw[10]) and np.allclose(R @ s.tcw[5] + t, s.tcw[10])
+    W = seqmod.window_arrays(s, [5, 10])
+    nP = len(W["pt_host"])
+    assert nP == 80 and W["res_begin"][0] == 0 and W["res_begin"][-1] == len(W["res_target"]) == nP
+    assert np.all(np.diff(W["res_begin"]) == 1) and np.all(W["res_target"] != W["pt_host"])
+    assert list(W["frame_id"]) == [1, 2] and W["state"].shape == (2, 10) and np.all(W["pt_idepth"] > 0)
+    # a point of keyframe 5 at its (noisy, 1 %) inverse depth, reprojected into keyframe 10
+    P = s.kf_points[5]
+    fx, fy, cx, cy = K
+    x = (P["u"] - cx) / fx; y = (P["v"] - cy) / fy
+    X = np.stack([x, y, np.ones_like(x)], 1) / P["idepth_zero"][:, None]
+    Y = X @ R.T + t
+    u2 = fx * Y[:, 0] / Y[:, 2] + cx; v2 = fy * Y[:, 1] / Y[:, 2] + cy
+    ok = (u2 > 2) & (u2 < s.w - 3) & (v2 > 2) & (v2 < s.h - 3)
+    assert ok.sum() >= 20
+    I5 = synth.sample_bilin(synth.make_images(s.images[5], 1)[0], P["u"][ok].astype(np.float64), P["v"][ok].astype(np.float64))[0]
+    I10 = synth.sample_bilin(synth.make_images(s.images[10], 1)[0], u2[ok], v2[ok])[0]
+    a5, b5 = s.aff[5]; a10, b10 = s.aff[10]
+    scene5 = (I5 - b5) / np.exp(a5); scene10 = (I10 - b10) / np.exp(a10)
+    assert np.median(np.abs(scene5 - scene10)) < 3.0        # grey levels; 1 % depth noise moves the reprojection by a fraction of a pixel
