@@ -52,3 +52,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in txt and "liboracle" not in txt and '#include "../oracle' not in txt, f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """ABI drift guard: size and every field offset of the structs in include/ldso_b200.h, as a C compiler lays them out, against the
+    ctypes mirrors in ldso_b200/capi.py (field names are taken from the ctypes side; a renamed or reordered field fails to compile or
+    to match)."""
+    import ctypes as C
+    import subprocess
+    pairs = [("ldso_b200_settings", capi.Settings), ("ldso_b200_window", capi.WindowC), ("ldso_b200_frame_state", capi.FrameStateC),
+             ("ldso_b200_fused_io", capi.FusedIOC), ("ldso_b200_immature", capi.ImmatureC)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ldso_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for fname, *_ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
