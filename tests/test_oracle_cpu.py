@@ -367,6 +367,31 @@ def test_reference_arm_matches_oracle():
     assert np.isfinite(r6.energy()) and r6.energy() < e_o
 
 
+@pytest.mark.skipif(oracle_py.ref_lib() is None, reason="oracle/_ref/libref_ba.so is built only where the reference tree is mounted (make -C oracle ref_pin)")
+def test_reference_lastx_noise_floor_is_along_the_gauge():
+    """Why parity on lastX is measured on the gauge-orthogonal complement: the reference's OWN library (its EnergyFunctional.cc, its
+    accumulators, the stand-in Eigen's LDLT) and the oracle (same pinned H and b, Eigen's LDLT restated) give update vectors that differ
+    by ~2e-3 as they stand -- twenty times the 1e-4 bar -- and by ~1e-5 once the seven gauge directions are projected out
+    (measured: 1.6e-3 / 6.3e-6 on this window, 2.1e-3 / 1.2e-5 on the 8 x 2000-point window). Its 6-thread runs reproduced the
+    1-thread bits in 5 of 5 runs on this host (the chunk scheduler hands one worker nearly everything), so the thread order is not
+    the larger effect here; the factorisation's rounding along the barely-damped scale direction is."""
+    win = synth.make_window(nF=6, pts_per_frame=120, w=320, h=240, seed=17)
+    r = oracle_py.RefBA(win, multithreaded=False)
+    r.optimize_begin(); r.gn_iteration(0)
+    xr = r.last_x()
+    o = oracle_py.OracleBA(win, threads_mode=0)
+    o.optimize_begin(); o.solve_system(0)
+    xo = o.system()["lastX"]
+    P = o.nullspace_projector()
+    I = np.eye(P.shape[0])
+    raw, proj = rel_err(xo, xr), rel_err((I - P) @ xo, (I - P) @ xr)
+    assert proj < 1e-4, proj
+    assert proj < 0.1 * raw or raw < 1e-5, (raw, proj)          # the disagreement lives in the gauge directions
+    r6 = oracle_py.RefBA(win, multithreaded=True)
+    r6.optimize_begin(); r6.gn_iteration(0)
+    assert rel_err((I - P) @ r6.last_x(), (I - P) @ xr) < 1e-4
+
+
 def test_select_activation_golden():
     """The frozen selection case (tests/golden/select_small.npz, written by tests/golden/make_golden.py from the pinned oracle)."""
     import importlib.util
