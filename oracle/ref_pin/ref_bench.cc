@@ -322,6 +322,46 @@ int ref_tracker_track(void *o, double Rm[9], double t[3], float *aff_a, float *a
     return ok ? 1 : 0;
 }
 
+// Host-side bookkeeping of the back end after a scripted piece of FullSystem's window maintenance -- no arithmetic member is called, so
+// the drop-in translation units (libdropin_ba.so) can be compared with the reference's own (libref_ba.so) WITHOUT a GPU:
+//   insertResidual for every residual (FullSystem.cc:1003-1005, activatePointsMT), dropResidual of every residual whose target is frame
+//   `drop_target` (flagFramesForMarginalization, FullSystem.cc:1312-1330), removePoint of every `remove_every`-th point after marking it
+//   OUT (flagPointsForRemoval + EnergyFunctional::dropPointsF's effect on the lists), makeIDX.
+// out: nFrames, nPoints, nResiduals, allPoints.size(), EFIndicesValid, resInA; per frame idx, frameID; per ordered pair (h, t) the two
+// connectivityMap counters; per remaining residual of every remaining point hostIDX * 64 + targetIDX. Returns the number of values.
+int ref_ba_bookkeeping(void *o, int drop_target, int remove_every, long long *out, int cap) {
+    RefWindow *W = (RefWindow *) o;
+    EnergyFunctional &ef = *W->ef;
+    for (auto &ph : W->points) { for (auto &r : ph->residuals) ef.insertResidual(r); ef.nPoints++; }       // insertPoint's counter (EnergyFunctional.h) + insertResidual
+    if (drop_target >= 0 && drop_target < (int) W->frames.size()) {
+        auto fh = W->frames[drop_target]->frameHessian;
+        for (auto &ph : W->points)
+            for (size_t i = 0; i < ph->residuals.size();) {
+                if (ph->residuals[i]->target.lock() == fh) ef.dropResidual(ph->residuals[i]);      // erases the entry from ph->residuals
+                else i++;
+            }
+    }
+    if (remove_every > 0)
+        for (size_t p = 0; p < W->points.size(); p += remove_every) {
+            W->pts[p]->status = Point::PointStatus::OUTLIER;
+            ef.removePoint(W->points[p]);
+        }
+    ef.makeIDX();
+    int k = 0;
+    auto put = [&](long long v) { if (k < cap) out[k] = v; k++; };
+    put(ef.nFrames); put(ef.nPoints); put(ef.nResiduals); put((long long) ef.allPoints.size()); put(EFIndicesValid ? 1 : 0); put(ef.resInA);
+    for (auto &f : ef.frames) { put(f->idx); put(f->frameID); }
+    for (auto &fh : ef.frames)
+        for (auto &ft : ef.frames) {
+            auto it = ef.connectivityMap.find((((uint64_t) fh->frameID) << 32) + ((uint64_t) ft->frameID));
+            put(it == ef.connectivityMap.end() ? -1 : it->second[0]);
+            put(it == ef.connectivityMap.end() ? -1 : it->second[1]);
+        }
+    for (auto &ph : ef.allPoints)
+        for (auto &r : ph->residuals) put(r->hostIDX * 64 + r->targetIDX);
+    return k;
+}
+
 // development aid: seconds spent in the phases of `iters` GN iterations: [backup + nullspaces, solveSystemF, doStepFromBackup, linearizeAll, applyRes]
 void ref_ba_profile(void *o, int iters, double out[5]) {
     RefWindow *W = (RefWindow *) o;

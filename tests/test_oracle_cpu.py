@@ -392,6 +392,30 @@ def test_reference_lastx_noise_floor_is_along_the_gauge():
     assert rel_err((I - P) @ r6.last_x(), (I - P) @ xr) < 1e-4
 
 
+@pytest.mark.skipif(oracle_py.ref_lib() is None or not os.path.exists(oracle_py.DROPIN_LIB),
+                    reason="oracle/_ref/libref_ba.so / libdropin_ba.so are built only where the reference tree is mounted (make -C oracle ref_pin dropin)")
+@pytest.mark.parametrize("drop_target,remove_every", [(-1, 0), (1, 7), (4, 3)])
+def test_dropin_bookkeeping_matches_reference(drop_target, remove_every):
+    """The drop-in translation units' HOST logic (ldso_b200/host/dropin: insertFrame / insertResidual / dropResidual / removePoint /
+    makeIDX, the counters, the connectivity map, hostIDX / targetIDX) against the reference's own EnergyFunctional.cc, both driven through
+    the reference's classes by the same scripted window maintenance (oracle/ref_pin/ref_bench.cc: ref_ba_bookkeeping). No arithmetic member
+    is called: the device context of the drop-in is created lazily, so this runs without a GPU."""
+    import ctypes as C
+    win = synth.make_window(nF=5, pts_per_frame=30, w=320, h=240, seed=5)
+    got = {}
+    for name, lib in (("ref", None), ("dropin", oracle_py.DROPIN_LIB)):
+        r = oracle_py.RefBA(win, multithreaded=False, lib_path=lib)
+        out = (C.c_longlong * 20000)()
+        r.L.ref_ba_bookkeeping.restype = C.c_int
+        n = r.L.ref_ba_bookkeeping(r.o, drop_target, remove_every, out, 20000)
+        assert 0 < n <= 20000
+        got[name] = np.array(out[:n])
+    assert np.array_equal(got["ref"], got["dropin"])
+    nF, nP_counter, nR, nAll = got["ref"][:4]
+    assert nF == win.nF and nAll == win.nP - (0 if remove_every <= 0 else len(range(0, win.nP, remove_every)))
+    assert nR > 0 and (drop_target >= 0 or remove_every > 0 or nR == win.nR)
+
+
 def test_select_activation_golden():
     """The frozen selection case (tests/golden/select_small.npz, written by tests/golden/make_golden.py from the pinned oracle)."""
     import importlib.util
