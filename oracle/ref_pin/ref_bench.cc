@@ -362,6 +362,23 @@ int ref_ba_bookkeeping(void *o, int drop_target, int remove_every, long long *ou
     return k;
 }
 
+// CoarseTracker(w, h) + makeK (CoarseTracker.cc:219-246): the public per-level intrinsics FullSystem and LoopClosing read. out: per level
+// w, h, fx, fy, cx, cy, fxi, fyi, cxi, cyi (10 values). Host logic only: comparable between the two libraries without a GPU.
+int ref_tracker_make_k(int w, int h, int levels, const double K[4], double *out) {
+    pyrLevelsUsed = levels;
+    for (int l = 0; l < levels; l++) { wG[l] = w >> l; hG[l] = h >> l; }
+    wM3G = w - 3; hM3G = h - 3;
+    auto HC = std::make_shared<CalibHessian>(std::make_shared<Camera>(K[0], K[1], K[2], K[3]));
+    CoarseTracker *T = new CoarseTracker(w, h);          // (leaked: the harness never frees trackers)
+    T->makeK(HC);
+    for (int l = 0; l < levels; l++) {
+        double *o = out + 10 * l;
+        o[0] = T->w[l]; o[1] = T->h[l]; o[2] = T->fx[l]; o[3] = T->fy[l]; o[4] = T->cx[l]; o[5] = T->cy[l];
+        o[6] = T->fxi[l]; o[7] = T->fyi[l]; o[8] = T->cxi[l]; o[9] = T->cyi[l];
+    }
+    return levels;
+}
+
 // development aid: seconds spent in the phases of `iters` GN iterations: [backup + nullspaces, solveSystemF, doStepFromBackup, linearizeAll, applyRes]
 void ref_ba_profile(void *o, int iters, double out[5]) {
     RefWindow *W = (RefWindow *) o;

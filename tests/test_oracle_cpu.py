@@ -416,6 +416,27 @@ def test_dropin_bookkeeping_matches_reference(drop_target, remove_every):
     assert nR > 0 and (drop_target >= 0 or remove_every > 0 or nR == win.nR)
 
 
+@pytest.mark.skipif(oracle_py.ref_lib() is None or not os.path.exists(oracle_py.DROPIN_LIB),
+                    reason="oracle/_ref/libref_ba.so / libdropin_ba.so are built only where the reference tree is mounted (make -C oracle ref_pin dropin)")
+@pytest.mark.parametrize("geom", [(640, 480, 4, (400.0, 400.0, 319.5, 239.5)), (1232, 368, 5, (718.856, 718.856, 607.1928, 185.2157))])
+def test_dropin_tracker_make_k_matches_reference(geom):
+    """CoarseTracker(w, h) + makeK of the drop-in unit (ldso_b200/host/dropin/dropin_tracker.cc) against the reference's CoarseTracker.cc:
+    the public per-level w, h, fx, fy, cx, cy and inverse intrinsics, bit for bit. Host logic only (the drop-in's device context cannot be
+    created here and says so on stderr; makeK's host side does not depend on it)."""
+    import ctypes as C
+    w, h, levels, K = geom
+    K = np.array(K, np.float64)
+    got = {}
+    for name, lib in (("ref", None), ("dropin", oracle_py.DROPIN_LIB)):
+        L = oracle_py.ref_lib(lib)
+        out = np.zeros(10 * levels)
+        L.ref_tracker_make_k.restype = C.c_int
+        assert L.ref_tracker_make_k(w, h, levels, K.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double))) == levels
+        got[name] = out
+    assert np.array_equal(got["ref"], got["dropin"])
+    assert got["ref"][0] == w and got["ref"][10 * (levels - 1)] == w >> (levels - 1)
+
+
 def test_select_activation_golden():
     """The frozen selection case (tests/golden/select_small.npz, written by tests/golden/make_golden.py from the pinned oracle)."""
     import importlib.util
